@@ -1,0 +1,105 @@
+"""Deterministic synthetic inputs and random-init weights for the hot path (CPU torch generators).
+
+Datasets, FlowNet2 weights and checkpoints are unavailable offline, so tests, `bench.py` and the golden
+fixture generator all draw from here.  Distributions follow SURVEY.md section 8(d):
+
+* path-level features  x_rgb, x_op ~ ReLU(N(0,1))  [b, C, h, w]  (post-ReLU `down3` activations,
+  reference Code/models/unet.py:985,992)
+* frames  gen, gt ~ U(-1, 1)  [b, 3, 256, 256]  (value range after Normalize(.5,.5),
+  reference Code/dataset/two_stream_dataset.py:503-506)
+* weights: reference constructor defaults -- Conv2d kaiming-uniform(a=sqrt(5)) for weight and
+  U(-1/sqrt(fan_in), 1/sqrt(fan_in)) for bias, bank ~ N(0,1) (unet.py:277), BatchNorm affine = (1, 0);
+  `trained_bn=True` instead draws non-trivial BN affine/running statistics, as a trained checkpoint has.
+
+Keys of the returned dicts are the reference `state_dict` names (checkpoint row).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict
+
+import torch
+
+
+def _gen(seed: int) -> torch.Generator:
+    g = torch.Generator(device="cpu")
+    g.manual_seed(int(seed))
+    return g
+
+
+def _uniform(shape, bound, g):
+    return (torch.rand(shape, generator=g, dtype=torch.float32) * 2.0 - 1.0) * bound
+
+
+def conv_default_init(out_c: int, in_c: int, ks: int, g: torch.Generator, bias: bool = True):
+    """torch.nn.Conv2d.reset_parameters: both bounds equal 1/sqrt(fan_in)."""
+    fan_in = in_c * ks * ks
+    bound = 1.0 / math.sqrt(fan_in)
+    w = _uniform((out_c, in_c, ks, ks), bound, g)
+    b = _uniform((out_c,), bound, g) if bias else None
+    return w, b
+
+
+def memory_params(seed: int, C: int = 512, D: int = 64, M: int = 256, k: int = 2,
+                  prefix: str = "") -> Dict[str, torch.Tensor]:
+    """Parameters and buffers of one `enc_quan_dec_topk` (reference unet.py:318-324, 268-280)."""
+    g = _gen(seed)
+    enc_w, enc_b = conv_default_init(D, C, 1, g)
+    dec_w, dec_b = conv_default_init(C, k * D, 1, g)
+    embed = torch.randn((D, M), generator=g, dtype=torch.float32)
+    return {
+        prefix + "enc.weight": enc_w, prefix + "enc.bias": enc_b,
+        prefix + "quantize.embed": embed,
+        prefix + "quantize.cluster_size": torch.zeros(M),
+        prefix + "quantize.embed_avg": embed.clone(),
+        prefix + "dec.weight": dec_w, prefix + "dec.bias": dec_b,
+    }
+
+
+def amft_params(seed: int, C: int = 512, prefix: str = "", trained_bn: bool = True) -> Dict[str, torch.Tensor]:
+    """Parameters and buffers of `bridge(in_c=C)` (reference unet.py:956-960, double_conv 8-16)."""
+    g = _gen(seed)
+    p: Dict[str, torch.Tensor] = {}
+    for branch in ("O2F", "F20"):
+        for ci, bi in ((0, 1), (3, 4)):
+            w, _ = conv_default_init(C, C, 3, g, bias=False)
+            p[f"{prefix}{branch}.conv.{ci}.weight"] = w
+            if trained_bn:
+                p[f"{prefix}{branch}.conv.{bi}.weight"] = 0.5 + torch.rand((C,), generator=g)
+                p[f"{prefix}{branch}.conv.{bi}.bias"] = 0.2 * torch.randn((C,), generator=g)
+                p[f"{prefix}{branch}.conv.{bi}.running_mean"] = 0.1 * torch.randn((C,), generator=g)
+                p[f"{prefix}{branch}.conv.{bi}.running_var"] = 0.05 + 0.2 * torch.rand((C,), generator=g)
+            else:
+                p[f"{prefix}{branch}.conv.{bi}.weight"] = torch.ones(C)
+                p[f"{prefix}{branch}.conv.{bi}.bias"] = torch.zeros(C)
+                p[f"{prefix}{branch}.conv.{bi}.running_mean"] = torch.zeros(C)
+                p[f"{prefix}{branch}.conv.{bi}.running_var"] = torch.ones(C)
+            p[f"{prefix}{branch}.conv.{bi}.num_batches_tracked"] = torch.zeros((), dtype=torch.long)
+    return p
+
+
+def path_params(seed: int, C: int = 512, D: int = 64, M: int = 256, k: int = 2) -> Dict[str, torch.Tensor]:
+    """All parameters the hot path reads, under the `twostream` state_dict names."""
+    p = {}
+    p.update(memory_params(seed * 10 + 1, C, D, M, k, prefix="rgb.vq_down3.quan."))
+    p.update(memory_params(seed * 10 + 2, C, D, M, k, prefix="op.vq_down3.quan."))
+    p.update(amft_params(seed * 10 + 3, C, prefix="bridge."))
+    return p
+
+
+def features(seed: int, b: int, C: int = 512, h: int = 32, w: int = 32) -> torch.Tensor:
+    """ReLU(N(0,1)) bottleneck features, NCHW fp32."""
+    return torch.relu(torch.randn((b, C, h, w), generator=_gen(seed), dtype=torch.float32))
+
+
+def frames(seed: int, b: int, c: int = 3, h: int = 256, w: int = 256, noise: float = 0.1):
+    """(gen, gt): gt ~ U(-1,1), gen = clamp(gt + noise*N(0,1)) so PSNR lands in a realistic 20-30 dB range."""
+    g = _gen(seed)
+    gt = _uniform((b, c, h, w), 1.0, g)
+    gen = (gt + noise * torch.randn((b, c, h, w), generator=g)).clamp_(-1.0, 1.0)
+    return gen, gt
+
+
+# video-length lists of the three datasets (frames per sub-video), recovered from the recorded score
+# pickles shipped with the reference (Code/ammcnet_os/model_result_save/*).
+PED2_VIDEO_LENGTHS = [180, 180, 150, 180, 150, 180, 180, 180, 120, 150, 180, 180]

@@ -1,0 +1,262 @@
+"""CPU oracle for the AMMC-Net memory + AMFT + scoring hot path.
+
+TEST INFRASTRUCTURE -- NOT PRODUCT CODE.  Only `tests/`, `__graft_entry__.smoke()` and the
+`cpu_baseline` / `--impl reference` legs of `bench.py` may import this file, and only as the checker
+(or, for `bench.py`, as the timed CPU baseline).  The shipped package `ammcnet_aaai2021_b200` never
+imports it and has no CPU fallback.
+
+It restates, op for op and in the same association order, what the reference computes with ATen on
+the CPU (fp32; pass dtype=torch.float64 for an adjudicating high-precision run).  Every function cites
+the reference lines it follows (paths relative to /root/reference).
+
+Parity pinning: the reference's own tree holds no test for the memory module, AMFT or PSNR
+(SURVEY.md section 4), so those parts are pinned by running the live reference in the build container
+(`oracle/gen_golden.py` -> `tests/golden/*.npz`, re-checked by `tests/test_oracle_golden.py`).  The
+score reduction is additionally pinned by the reference's recorded per-frame score pickles
+(`Code/ammcnet_os/model_result_save/*`), whose records and reduced scores are committed as fixtures.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+
+# --------------------------------------------------------------------------------------------------
+# memory module
+# --------------------------------------------------------------------------------------------------
+def squared_l2_distances(flatten: torch.Tensor, embed: torch.Tensor) -> torch.Tensor:
+    """dist[n, j] = (||z_n||^2 - 2 z_n.e_j) + ||e_j||^2, same association as Code/models/unet.py:283-288."""
+    return (flatten.pow(2).sum(1, keepdim=True) - 2 * flatten @ embed
+            + embed.pow(2).sum(0, keepdim=True))
+
+
+def quantize_topk_forward(z: torch.Tensor, embed: torch.Tensor, k: int, *, training: bool = False,
+                          cluster_size: Optional[torch.Tensor] = None,
+                          embed_avg: Optional[torch.Tensor] = None,
+                          decay: float = 0.99, eps: float = 1e-5) -> Dict[str, torch.Tensor]:
+    """Quantize_topk.forward, Code/models/unet.py:282-313 (embed_code: 315-316).
+
+    z: [b, h, w, D]; embed: [D, M].  Returns the three outputs of the reference plus the indices, the
+    distance matrix (for margin filters in tests) and -- in training -- the UPDATED buffers (the inputs
+    are not mutated; outputs use the pre-update bank, unet.py:298-309 run after the gathers).
+    """
+    D, M = embed.shape
+    flatten = z.reshape(-1, D)
+    dist = squared_l2_distances(flatten, embed)
+    embed_ind = (-dist).max(1)[1]                                     # unet.py:289
+    bank_t = embed.transpose(0, 1)
+    q1 = F.embedding(embed_ind.view(*z.shape[:-1]), bank_t)            # unet.py:291-292
+    idx_topk = (-dist).topk(k, dim=1)[1]                               # unet.py:293 (sorted, nearest first)
+    read = F.embedding(idx_topk.view(*z.shape[:-1], k), bank_t)        # [b,h,w,k,D]
+    read = read.view(*z.shape[:-1], k * D)                             # unet.py:296
+    out: Dict[str, torch.Tensor] = {}
+    if training:
+        onehot = F.one_hot(embed_ind, M).type(flatten.dtype)           # unet.py:290
+        counts = onehot.sum(0)
+        embed_sum = flatten.transpose(0, 1) @ onehot                   # unet.py:302
+        new_cs = cluster_size * decay + (1 - decay) * counts           # unet.py:299-301
+        new_avg = embed_avg * decay + (1 - decay) * embed_sum          # unet.py:303
+        n = new_cs.sum()
+        cs = (new_cs + eps) / (n + M * eps) * n                        # unet.py:304-307
+        out.update(counts=counts, embed_sum=embed_sum, cluster_size=new_cs, embed_avg=new_avg,
+                   embed=new_avg / cs.unsqueeze(0))                    # unet.py:308-309
+    diff = (q1 - z).pow(2).mean()                                      # unet.py:310
+    ste = z + (q1 - z)                                                 # unet.py:311 (value differs from q1 by <=1 ulp)
+    out.update(quantize_topk=read, diff=diff, quantize=ste, quantize_raw=q1, idx_topk=idx_topk,
+               idx_top1=embed_ind, dist=dist)
+    return out
+
+
+def memory_module_forward(x: torch.Tensor, enc_w: torch.Tensor, enc_b: torch.Tensor,
+                          embed: torch.Tensor, dec_w: torch.Tensor, dec_b: torch.Tensor, k: int,
+                          *, residual: bool = True, training: bool = False,
+                          cluster_size=None, embed_avg=None, decay=0.99, eps=1e-5):
+    """enc_quan_dec_topk.forward (unet.py:325-331) and, with residual=True, enc_quan_dec_res_topk.forward
+    (unet.py:384-387).  x: [b, C, h, w] NCHW.  enc_w: [D, C, 1, 1] or [D, C]; dec_w: [C, kD, 1, 1] or [C, kD]."""
+    D = enc_w.shape[0]
+    C = dec_w.shape[0]
+    z = F.conv2d(x, enc_w.reshape(D, -1, 1, 1), enc_b).permute(0, 2, 3, 1)   # unet.py:326
+    q = quantize_topk_forward(z, embed, k, training=training, cluster_size=cluster_size,
+                              embed_avg=embed_avg, decay=decay, eps=eps)
+    read_nchw = q["quantize_topk"].permute(0, 3, 1, 2)                        # unet.py:328
+    out = F.conv2d(read_nchw, dec_w.reshape(C, -1, 1, 1), dec_b)              # unet.py:330
+    if residual:
+        out = out + x                                                         # unet.py:386
+    b = x.shape[0]
+    sse_per_frame = (q["quantize_raw"] - z).pow(2).reshape(b, -1).sum(1)          # for per-frame partial parity
+    res = dict(q)
+    res.update(out=out, diff=q["diff"].unsqueeze(0), z=z, sse_per_frame=sse_per_frame)
+    return res
+
+
+def memory_module_backward(x, enc_w, enc_b, embed, dec_w, idx_topk, z, g_out, g_diff, g_q1=None,
+                           residual: bool = True):
+    """Closed-form backward of a9 (verified there against autograd of unet.py:282-331).
+
+    The read is gathered from a buffer, so no gradient reaches z through it; the commit loss and the
+    straight-through q1 do.  Returns dict(gx, g_enc_w, g_enc_b, g_dec_w, g_dec_b).
+    """
+    D, M = embed.shape
+    C = dec_w.shape[0]
+    k = idx_topk.shape[-1]
+    b, _, h, w = x.shape
+    N = b * h * w
+    zf = z.reshape(N, D)
+    bank_t = embed.t()
+    e1 = bank_t[idx_topk.reshape(N, k)[:, 0]]
+    gz = g_diff.reshape(()) * 2.0 * (zf - e1) / (N * D)
+    if g_q1 is not None:
+        gz = gz + g_q1.reshape(N, D)
+    go = g_out.permute(0, 2, 3, 1).reshape(N, C)
+    read = bank_t[idx_topk.reshape(N, k)].reshape(N, k * D)
+    xf = x.permute(0, 2, 3, 1).reshape(N, -1)
+    gx = gz @ enc_w.reshape(D, -1)
+    if residual:
+        gx = gx + go
+    return dict(
+        gx=gx.reshape(b, h, w, -1).permute(0, 3, 1, 2).contiguous(),
+        g_enc_w=(gz.t() @ xf).reshape(enc_w.shape), g_enc_b=gz.sum(0),
+        g_dec_w=(go.t() @ read).reshape(dec_w.shape), g_dec_b=go.sum(0), gz=gz)
+
+
+# --------------------------------------------------------------------------------------------------
+# AMFT (class `bridge`)
+# --------------------------------------------------------------------------------------------------
+def double_conv_forward(u, p: Dict[str, torch.Tensor], prefix: str, training: bool = False,
+                        momentum: float = 0.1, bn_eps: float = 1e-5):
+    """double_conv.forward, Code/models/unet.py:8-20: (conv3x3 no-bias -> BN -> ReLU) x 2.
+    `p` is a state_dict; keys `<prefix>.conv.{0,3}.weight`, `<prefix>.conv.{1,4}.{weight,bias,running_mean,running_var}`.
+    In training mode batch statistics are used and the updated running stats are returned."""
+    new_stats = {}
+    for ci, bi in ((0, 1), (3, 4)):
+        u = F.conv2d(u, p[f"{prefix}.conv.{ci}.weight"], None, padding=1)
+        rm, rv = p[f"{prefix}.conv.{bi}.running_mean"], p[f"{prefix}.conv.{bi}.running_var"]
+        if training:
+            rm, rv = rm.clone(), rv.clone()
+        u = F.batch_norm(u, rm, rv, p[f"{prefix}.conv.{bi}.weight"], p[f"{prefix}.conv.{bi}.bias"],
+                         training=training, momentum=momentum, eps=bn_eps)
+        if training:
+            new_stats[f"{prefix}.conv.{bi}.running_mean"] = rm
+            new_stats[f"{prefix}.conv.{bi}.running_var"] = rv
+        u = F.relu(u)
+    return u, new_stats
+
+
+def amft_forward(zx, zy, p: Dict[str, torch.Tensor], prefix: str = "", training: bool = False):
+    """bridge.forward, Code/models/unet.py:962-965: x' = zx + O2F(zy), y' = zy + F20(zx)."""
+    pre = prefix + "." if prefix and not prefix.endswith(".") else prefix
+    fo, s1 = double_conv_forward(zy, p, pre + "O2F", training)
+    ff, s2 = double_conv_forward(zx, p, pre + "F20", training)
+    s1.update(s2)
+    return zx + fo, zy + ff, s1
+
+
+# --------------------------------------------------------------------------------------------------
+# PSNR + per-frame records + score reduction
+# --------------------------------------------------------------------------------------------------
+def psnr_per_frame(gen: torch.Tensor, gt: torch.Tensor) -> torch.Tensor:
+    """Per-sample value of psnr_error (Code/utils/utils.py:141-147) -- the loop at
+    Code/run_helper/test_helper.py:445-452 calls it with batch 1, so the mean at utils.py:148 is the identity."""
+    n = gen.shape[1] * gen.shape[2] * gen.shape[3]
+    sq = ((gt + 1.0) / 2.0 - (gen + 1.0) / 2.0) ** 2
+    return 10 * torch.log10(1.0 / ((1.0 / n) * torch.sum(sq, [1, 2, 3])))
+
+
+def psnr_error(gen: torch.Tensor, gt: torch.Tensor) -> torch.Tensor:
+    """psnr_error, Code/utils/utils.py:130-148 (mean over the batch axis)."""
+    return torch.mean(psnr_per_frame(gen, gt))
+
+
+def assemble_video_records(psnr_clip: np.ndarray, commit_group: np.ndarray, clip_len: int = 5,
+                           group: int = 16, tail_copy: bool = False) -> Tuple[np.ndarray, np.ndarray]:
+    """Record semantics of Code/run_helper/test_helper.py:414-475 for ONE sub-video.
+
+    psnr_clip[c]  : PSNR of clip c (predicting frame c + clip_len - 1), c = 0..n_clips-1
+    commit_group[g]: the batch-level commit scalar of the g-th group of `group` consecutive clips
+    Returns (img_pred_arr, fea_comm_arr) of length n_clips + clip_len - 1; the first clip_len-1 entries
+    copy entry clip_len-1 (test_helper.py:465,472); with tail_copy (the op stream, whose clip length is
+    one shorter than the frame count implies) the last entry copies the one before (test_helper.py:467,474).
+    """
+    n_clips = len(psnr_clip)
+    num_frame = n_clips + clip_len - 1 + (1 if tail_copy else 0)
+    img = np.empty((num_frame,), np.float32)
+    fea = np.empty((num_frame,), np.float32)
+    for c in range(n_clips):
+        img[c + clip_len - 1] = psnr_clip[c]
+        fea[c + clip_len - 1] = commit_group[c // group]
+    img[:clip_len - 1] = img[clip_len - 1]
+    fea[:clip_len - 1] = fea[clip_len - 1]
+    if tail_copy:
+        img[num_frame - 1] = img[num_frame - 2]
+        fea[num_frame - 1] = fea[num_frame - 2]
+    return img, fea
+
+
+DECIDABLE_IDX = 4  # Code/main/eval_metric.py:15-17
+
+
+def norm_score(records: Sequence[np.ndarray]) -> np.ndarray:
+    """norm_score, Code/main/eval_metric.py:405-417 (float32; does not mutate its input, unlike the
+    reference which normalises the record arrays in place)."""
+    scores = np.array([], dtype=np.float32)
+    for rec in records:
+        d = np.array(rec, dtype=np.float32, copy=True)
+        d -= d.min()
+        d /= d.max()
+        scores = np.concatenate((scores, d[DECIDABLE_IDX:]), axis=0)
+    scores -= scores.min()
+    scores /= scores.max()
+    return scores
+
+
+def score_reduce(img_records: Sequence[np.ndarray], fea_records: Sequence[np.ndarray],
+                 lam: Tuple[float, float]) -> np.ndarray:
+    """Regularity scores, Code/main/eval_metric.py:418-427: mix then the non-recursive 2-tap smoothing
+    that runs across video boundaries.  Returns float32 [T]."""
+    img = norm_score(img_records)
+    fea = norm_score(fea_records)
+    identity = np.ones_like(fea)
+    l1, l2 = lam[0], lam[1]
+    s = (1 - l1) * img + l1 * (identity - fea)
+    out = [(1 - l2) * s[i - 1] + l2 * s[i] if i > 0 else s[i] for i in range(len(s))]
+    return np.asarray(out, dtype=np.float32)
+
+
+def roc_auc(labels: np.ndarray, scores: np.ndarray, pos_label: int = 0) -> float:
+    """sklearn.metrics.roc_curve + auc as called at Code/main/eval_metric.py:428-429, restated with numpy
+    (trapezoid over the ROC polyline with tied scores merged) so the oracle does not need sklearn."""
+    y = (np.asarray(labels) == pos_label).astype(np.float64)
+    s = np.asarray(scores, dtype=np.float64)
+    order = np.argsort(-s, kind="mergesort")
+    y, s = y[order], s[order]
+    distinct = np.where(np.diff(s))[0]
+    thr = np.r_[distinct, y.size - 1]
+    tps = np.cumsum(y)[thr]
+    fps = 1 + thr - tps
+    tps = np.r_[0, tps]
+    fps = np.r_[0, fps]
+    if tps[-1] == 0 or fps[-1] == 0:
+        return float("nan")
+    return float(np.trapezoid(tps / tps[-1], fps / fps[-1]))
+
+
+# --------------------------------------------------------------------------------------------------
+# whole path (one "step" of the metric): both memory modules + AMFT + rgb PSNR
+# --------------------------------------------------------------------------------------------------
+def path_forward(x_rgb, x_op, gen, gt, params: Dict[str, torch.Tensor], k: int):
+    """The starred region of twostream.forward (Code/models/unet.py:985-994) followed by the per-frame rgb
+    PSNR of test_helper.py:445-452.  `params` uses the reference state_dict key names
+    (rgb.vq_down3.quan.enc.weight, ..., bridge.O2F.conv.0.weight, ...)."""
+    outs = {}
+    for s, x in (("rgb", x_rgb), ("op", x_op)):
+        pre = f"{s}.vq_down3.quan."
+        outs[s] = memory_module_forward(x, params[pre + "enc.weight"], params[pre + "enc.bias"],
+                                        params[pre + "quantize.embed"], params[pre + "dec.weight"],
+                                        params[pre + "dec.bias"], k)
+    yx, yy, _ = amft_forward(outs["rgb"]["out"], outs["op"]["out"], params, "bridge")
+    return dict(rgb=outs["rgb"], op=outs["op"], amft_rgb=yx, amft_op=yy,
+                psnr=psnr_per_frame(gen, gt))
