@@ -1,0 +1,18 @@
+"""B200-native (sm_100a) implementation of AMMC-Net's memory + AMFT + scoring hot path.
+
+Public surface mirrors the reference (NjuHaoZhang/AMMCNet_AAAI2021, Code/models/unet.py, Code/utils/utils.py,
+Code/main/eval_metric.py): `Quantize_topk`, `enc_quan_dec_topk`, `enc_quan_dec_res_topk`, `bridge`, `psnr_error`,
+`evaluate`; plus `patch_reference` / `swap_modules` to slot them behind the reference's own factories.
+Importing the package does not need a GPU; calling any op does (there is no CPU fallback).
+"""
+from .modules import Quantize_topk, enc_quan_dec_topk, enc_quan_dec_res_topk, bridge, double_conv, psnr_error
+from .functions import psnr_per_frame
+from .scoring import VideoScorer, assemble_video_records, score_reduce, evaluate, LAM_MAP
+from .patch import patch_reference, unpatch_reference, swap_modules
+from .host_model import twostream, UNetMem_v7, get_twostream
+
+__all__ = [
+    "Quantize_topk", "enc_quan_dec_topk", "enc_quan_dec_res_topk", "bridge", "double_conv", "psnr_error",
+    "psnr_per_frame", "VideoScorer", "assemble_video_records", "score_reduce", "evaluate", "LAM_MAP",
+    "patch_reference", "unpatch_reference", "swap_modules", "twostream", "UNetMem_v7", "get_twostream",
+]

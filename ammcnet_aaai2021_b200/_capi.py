@@ -1,0 +1,76 @@
+"""ctypes binding of libammc_b200.so (C ABI declared in include/ammc_b200.h).
+
+The library is the only compute backend: if it is missing, cannot be loaded, or the device is not sm_100,
+every entry point raises -- there is no CPU or PyTorch fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_void_p
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libammc_b200.so")
+
+P, I, L, F, Z = c_void_p, c_int, c_int64, c_float, c_size_t
+
+# name -> (restype, argtypes); must list every symbol of include/ammc_b200.h (tests/test_capi.py checks it)
+SIGNATURES = {
+    "ammc_version": (I, []),
+    "ammc_last_error": (c_char_p, []),
+    "ammc_device_supported": (I, []),
+    "ammc_mem_workspace_bytes": (Z, [I] * 7),
+    "ammc_mem_fwd": (I, [P] * 6 + [P] * 6 + [P, P] + [P, Z] + [I] * 8 + [P]),
+    "ammc_quantize_workspace_bytes": (Z, [L, I, I, I]),
+    "ammc_quantize_fwd": (I, [P, P] + [P] * 5 + [P, P] + [P, Z] + [L, L, I, I, I] + [P]),
+    "ammc_quantize_bwd_workspace_bytes": (Z, [L, I, I]),
+    "ammc_quantize_bwd": (I, [P] * 6 + [P, Z] + [L, I, I, I] + [P]),
+    "ammc_embed_code": (I, [P, P, P, L, I, I, P]),
+    "ammc_ema_update": (I, [P] * 5 + [I, I, F, F, P]),
+    "ammc_mem_bwd_workspace_bytes": (Z, [I] * 7),
+    "ammc_mem_bwd": (I, [P] * 8 + [P] * 5 + [P, Z] + [I] * 8 + [P]),
+    "ammc_pack_conv_weights": (I, [P, P, I, I, P]),
+    "ammc_pack_nhwc": (I, [P, P, I, I, I, I, P]),
+    "ammc_conv3x3_bn_relu": (I, [P] * 7 + [I] * 7 + [P]),
+    "ammc_pack_conv_weights_1x1": (I, [P, P, I, I, P]),
+    "ammc_conv1x1_bn_relu": (I, [P] * 7 + [I] * 7 + [P]),
+    "ammc_bn_fold": (I, [P] * 4 + [F] + [P, P, I, P]),
+    "ammc_psnr_workspace_bytes": (Z, [I, L]),
+    "ammc_psnr_batch": (I, [P, P, P, P, Z, I, L, P]),
+    "ammc_score_workspace_bytes": (Z, [L, I]),
+    "ammc_score_reduce": (I, [P, P, P, I, F, F, F, F, P, P, Z, L, P]),
+}
+
+_lib = None
+
+
+def load():
+    """Load (once) and return the ctypes handle; raises RuntimeError when the extension is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "ammcnet_aaai2021_b200: %s is missing. Build it with `python -m ammcnet_aaai2021_b200.build` "
+            "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
+    try:
+        lib = ctypes.CDLL(LIB_PATH)
+    except OSError as e:  # pragma: no cover
+        raise RuntimeError("ammcnet_aaai2021_b200: cannot load %s: %s" % (LIB_PATH, e))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)        # AttributeError here means header and library disagree
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = load().ammc_last_error()
+        raise RuntimeError("ammc_b200 %s failed (code %d): %s" % (what, rc, (msg or b"").decode(errors="replace")))
+
+
+def call(name: str, *args):
+    """Call an int-returning entry point and raise RuntimeError on a non-zero code."""
+    check(getattr(load(), name)(*args), name)

@@ -1,0 +1,425 @@
+// AMFT (`bridge`, reference Code/models/unet.py:956-965): 3x3 convolution + folded BatchNorm + ReLU (+ residual)
+// as an implicit GEMM on the 5th-generation tensor cores.
+//
+//   GEMM view      M = pixels (128 per tile: W_box x H_box x B_box), N = output channels (BLOCK_N per tile),
+//                  K = 9 taps x Cin, walked as 64-channel blocks of one tap at a time.
+//   A operand      NHWC bf16 activation planes.  The tile of tap (dy,dx) is the SAME 5-D TMA box shifted by
+//                  (dx,dy): out-of-bounds coordinates are zero-filled by TMA, which is exactly the conv padding,
+//                  so no im2col buffer exists.  The box lands in shared memory as 128 rows x 128 B with the
+//                  128-byte swizzle = the canonical K-major UMMA layout.
+//   B operand      weights repacked once to [Cout][tap*Cin + cin] bf16 (K-major), TMA box 64 x BLOCK_N.
+//   accumulate     fp32 in TMEM (tcgen05.mma kind::f16, M=128, N=BLOCK_N, K=16), two accumulator buffers so the
+//                  epilogue of tile i overlaps the MMAs of tile i+1.
+//   precision      operands are split x = hi + lo (two bf16 planes).  precision=1 multiplies hi*hi only;
+//                  precision=3 runs the K loop three times over (hi,hi), (hi,lo), (lo,hi) into the same
+//                  accumulator -> ~2^-17 relative error, the fp32-parity mode.
+//   epilogue       TMEM -> registers (tcgen05.ld 32x32b), y = relu(acc*scale[c] + shift[c]) and either
+//                  (a) NHWC bf16 hi/lo planes (the next conv's A operand) or (b) + residual -> NCHW fp32.
+//   roles          warp 0 lane 0: TMA producer; warp 1 lane 0: MMA issuer (warp 1 owns TMEM alloc/dealloc);
+//                  warps 2-5: epilogue (one TMEM lane quarter each).  Persistent over tiles, one CTA per SM.
+#include "common.cuh"
+#include "ptx.cuh"
+#include <cuda_bf16.h>
+
+namespace ammc {
+
+constexpr int CONV_THREADS = 192;
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;                       // bf16 elements = 128 bytes = one swizzle row
+constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;    // 16 KB
+
+struct ConvParams {
+  int b, H, W, Cin, Cout;
+  int W_box, H_box, B_box, groups_h;
+  int tiles_m, tiles_n, ntaps;
+  int n_pass, pass_a[3], pass_b[3];
+  int relu;
+  const float* scale;
+  const float* shift;
+  __nv_bfloat16* out_planes;     // [2][b][H][W][Cout] or null
+  long long out_plane_stride;    // elements between the hi and lo plane
+  float* out_nchw;               // [b][Cout][H][W] or null
+  const float* res_nchw;         // same shape or null
+};
+
+template <int BLOCK_N>
+struct ConvSmem {
+  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8);
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // barriers + tmem slot + alignment slack
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(CONV_THREADS, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
+  using S = ConvSmem<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + S::STAGES;
+  uint64_t* tmem_full = empty_bar + S::STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = p.tiles_m * p.tiles_n;
+  const int kb_per_pass = p.ntaps * (p.Cin / BLOCK_K);
+  const int kb_total = kb_per_pass * p.n_pass;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tmA);
+    ptx::prefetch_tensormap(&tmB);
+    for (int s = 0; s < S::STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tmem_full[a], 1); ptx::mbar_init(&tmem_empty[a], 128); }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, 2 * BLOCK_N);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------------------------------------------ TMA producer
+      int s = 0; uint32_t ph = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int mt = t / p.tiles_n, nt = t % p.tiles_n;
+        const int img0 = (mt / p.groups_h) * p.B_box, h0 = (mt % p.groups_h) * p.H_box;
+        const int n0 = nt * BLOCK_N;
+        for (int ps = 0; ps < p.n_pass; ++ps) {
+          const int pa = p.pass_a[ps], pb = p.pass_b[ps];
+          for (int tap = 0; tap < p.ntaps; ++tap) {
+            const int dy = p.ntaps == 9 ? tap / 3 - 1 : 0, dx = p.ntaps == 9 ? tap % 3 - 1 : 0;
+            for (int cc = 0; cc < p.Cin / BLOCK_K; ++cc) {
+              ptx::mbar_wait(&empty_bar[s], ph ^ 1, 1);
+              ptx::mbar_expect_tx(&full_bar[s], S::STAGE_BYTES);
+              uint8_t* a_dst = smem + s * S::STAGE_BYTES;
+              ptx::tma_load_5d(a_dst, &tmA, &full_bar[s], cc * BLOCK_K, dx, h0 + dy, img0, pa);
+              ptx::tma_load_3d(a_dst + A_BYTES, &tmB, &full_bar[s], tap * p.Cin + cc * BLOCK_K, n0, pb);
+              if (++s == S::STAGES) { s = 0; ph ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ------------------------------------------------------------------ MMA issuer
+      constexpr uint32_t idesc = ptx::umma_idesc(1, BLOCK_M, BLOCK_N);
+      int s = 0; uint32_t ph = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_ph = (it >> 1) & 1;
+        ptx::mbar_wait(&tmem_empty[acc], acc_ph ^ 1, 2);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < kb_total; ++kb) {
+          ptx::mbar_wait(&full_bar[s], ph, 3);
+          ptx::tc_fence_after();
+          const uint32_t a_addr = ptx::smem_u32(smem + s * S::STAGE_BYTES);
+          const uint64_t adesc = ptx::umma_desc_k_sw128(a_addr);
+          const uint64_t bdesc = ptx::umma_desc_k_sw128(a_addr + A_BYTES);
+#pragma unroll
+          for (int k4 = 0; k4 < BLOCK_K / 16; ++k4) {
+            // advance 16 elements (32 B) along K inside the swizzled row: +2 in the (>>4) address field
+            ptx::mma_f16_ss(d_tmem, adesc + 2 * k4, bdesc + 2 * k4, idesc, (kb | k4) != 0 ? 1u : 0u);
+          }
+          ptx::mma_commit(&empty_bar[s]);
+          if (kb == kb_total - 1) ptx::mma_commit(&tmem_full[acc]);
+          if (++s == S::STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else {
+    // -------------------------------------------------------------------- epilogue warps
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;            // accumulator row = pixel within the tile
+    const int per_img = p.W_box * p.H_box;
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_ph = (it >> 1) & 1;
+      const int mt = t / p.tiles_n, nt = t % p.tiles_n;
+      const int img = (mt / p.groups_h) * p.B_box + r / per_img;
+      const int rem = r % per_img;
+      const int hh = (mt % p.groups_h) * p.H_box + rem / p.W_box, ww = rem % p.W_box;
+      const bool valid = img < p.b;
+      const int n0 = nt * BLOCK_N;
+      ptx::mbar_wait(&tmem_full[acc], acc_ph, 4);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N;
+#pragma unroll 1
+      for (int c32 = 0; c32 < BLOCK_N / 32; ++c32) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32(taddr + c32 * 32, v);
+        ptx::tmem_ld_wait();
+        const int cbase = n0 + c32 * 32;
+        float y[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float a = __uint_as_float(v[j]);
+          a = fmaf(a, __ldg(p.scale + cbase + j), __ldg(p.shift + cbase + j));
+          y[j] = p.relu ? fmaxf(a, 0.f) : a;
+        }
+        if (valid) {
+          if (p.out_nchw) {
+            const size_t hw = (size_t)p.H * p.W;
+            size_t o = ((size_t)img * p.Cout + cbase) * hw + (size_t)hh * p.W + ww;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float a = y[j];
+              if (p.res_nchw) a += __ldg(p.res_nchw + o);
+              p.out_nchw[o] = a;
+              o += hw;
+            }
+          }
+          if (p.out_planes) {
+            const size_t pix = ((size_t)img * p.H + hh) * p.W + ww;
+            __nv_bfloat16* hi = p.out_planes + pix * p.Cout + cbase;
+            __nv_bfloat16* lo = hi + p.out_plane_stride;
+            uint32_t hp[16], lp[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              __nv_bfloat16 h0 = __float2bfloat16_rn(y[2 * j]), h1 = __float2bfloat16_rn(y[2 * j + 1]);
+              __nv_bfloat16 l0 = __float2bfloat16_rn(y[2 * j] - __bfloat162float(h0));
+              __nv_bfloat16 l1 = __float2bfloat16_rn(y[2 * j + 1] - __bfloat162float(h1));
+              hp[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+              lp[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              reinterpret_cast<uint4*>(hi)[j] = make_uint4(hp[4 * j], hp[4 * j + 1], hp[4 * j + 2], hp[4 * j + 3]);
+              reinterpret_cast<uint4*>(lo)[j] = make_uint4(lp[4 * j], lp[4 * j + 1], lp[4 * j + 2], lp[4 * j + 3]);
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 2 * BLOCK_N);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// operand packing
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(v);
+  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+// x [b][C][HW] fp32  ->  xp [2][b][HW][C] bf16.  32x32 (c, p) tiles transposed through shared memory.
+__global__ void __launch_bounds__(256) pack_nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ xp,
+                                                         int C, int HW, long long plane_stride) {
+  __shared__ float tile[32][33];
+  const int img = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    int c = c0 + r, pp = p0 + tx;
+    tile[r][tx] = (c < C && pp < HW) ? x[((size_t)img * C + c) * HW + pp] : 0.f;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    int pp = p0 + r, c = c0 + tx;
+    if (pp < HW && c < C) {
+      __nv_bfloat16 hi, lo;
+      split_bf16(tile[tx][r], hi, lo);
+      size_t o = ((size_t)img * HW + pp) * C + c;
+      xp[o] = hi;
+      xp[o + plane_stride] = lo;
+    }
+  }
+}
+
+// w [Cout][Cin][taps] fp32 -> wp [2][Cout][taps*Cin] bf16 with k = tap*Cin + cin   (taps = 9 for 3x3, 1 for 1x1)
+__global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp, int Cout, int Cin,
+                                    int taps) {
+  const long long total = (long long)Cout * Cin * taps;
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int cin = (int)(e % Cin);
+  const int tap = (int)((e / Cin) % taps);
+  const int co = (int)(e / ((long long)Cin * taps));
+  __nv_bfloat16 hi, lo;
+  split_bf16(w[((size_t)co * Cin + cin) * taps + tap], hi, lo);
+  wp[e] = hi;
+  wp[e + total] = lo;
+}
+
+__global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                               const float* __restrict__ mean, const float* __restrict__ var, float eps,
+                               float* __restrict__ scale, float* __restrict__ shift, int C) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s = gamma[c] / sqrtf(var[c] + eps);
+  scale[c] = s;
+  shift[c] = beta[c] - mean[c] * s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host: tensor maps + launch
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+static int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+                    const cuuint32_t* box) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(AMMC_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box,
+                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(AMMC_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return 0;
+}
+
+template <int BLOCK_N>
+static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t st) {
+  using S = ConvSmem<BLOCK_N>;
+  static bool configured[64] = {false};
+  int dev = 0;
+  AMMC_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && !configured[dev]) {
+    AMMC_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         S::TOTAL));
+    configured[dev] = true;
+  }
+  int grid = min(num_sms(), p.tiles_m * p.tiles_n);
+  conv_igemm_kernel<BLOCK_N><<<grid, CONV_THREADS, S::TOTAL, st>>>(tmA, tmB, p);
+  AMMC_LAUNCH_CHECK("conv_igemm_kernel");
+  return 0;
+}
+
+// Shared by the 3x3 (ntaps = 9) and 1x1 (ntaps = 1) entry points.
+int conv_igemm(const void* xp, const void* wp, const float* scale, const float* shift, void* out_planes,
+               float* out_nchw, const float* res_nchw, int b, int Cin, int Cout, int h, int w, int ntaps,
+               int precision, int relu, cudaStream_t st) {
+  AMMC_REQUIRE(xp && wp && scale && shift && (out_planes || out_nchw), "null pointer argument");
+  AMMC_REQUIRE(b > 0 && h > 0 && w > 0, "bad shape b=%d h=%d w=%d", b, h, w);
+  if (precision != 1 && precision != 3) return fail(AMMC_EINVAL, "precision must be 1 or 3 (got %d)", precision);
+  if (Cin % 64 != 0 || Cout % 64 != 0)
+    return fail(AMMC_EUNSUPPORTED, "tcgen05 conv needs Cin and Cout multiples of 64 (got %d, %d)", Cin, Cout);
+  if (w > 128 || (128 % w) != 0)
+    return fail(AMMC_EUNSUPPORTED, "tcgen05 conv needs a feature-map width that divides 128 (got %d)", w);
+  ConvParams p;
+  p.b = b; p.H = h; p.W = w; p.Cin = Cin; p.Cout = Cout;
+  p.W_box = w;
+  p.H_box = min(h, 128 / w);
+  if (h % p.H_box != 0 || (128 % (w * p.H_box)) != 0)
+    return fail(AMMC_EUNSUPPORTED, "tcgen05 conv cannot tile a %dx%d feature map into 128-pixel boxes", h, w);
+  p.B_box = 128 / (w * p.H_box);
+  p.groups_h = h / p.H_box;
+  p.tiles_m = ceil_div(b, p.B_box) * p.groups_h;
+  const int block_n = (Cout % 256 == 0) ? 256 : (Cout % 128 == 0 ? 128 : 64);
+  p.tiles_n = Cout / block_n;
+  p.ntaps = ntaps;
+  p.n_pass = precision;
+  const int pa[3] = {0, 0, 1}, pb[3] = {0, 1, 0};
+  for (int i = 0; i < 3; ++i) { p.pass_a[i] = pa[i]; p.pass_b[i] = pb[i]; }
+  p.relu = relu;
+  p.scale = scale; p.shift = shift;
+  p.out_planes = (__nv_bfloat16*)out_planes;
+  p.out_plane_stride = (long long)b * h * w * Cout;
+  p.out_nchw = out_nchw;
+  p.res_nchw = res_nchw;
+
+  CUtensorMap tmA, tmB;
+  {
+    cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)b, 2};
+    cuuint64_t strides[4] = {(cuuint64_t)Cin * 2, (cuuint64_t)w * Cin * 2, (cuuint64_t)h * w * Cin * 2,
+                             (cuuint64_t)b * h * w * Cin * 2};
+    cuuint32_t box[5] = {64, (cuuint32_t)p.W_box, (cuuint32_t)p.H_box, (cuuint32_t)p.B_box, 1};
+    if (int rc = make_map(&tmA, xp, 5, dims, strides, box)) return rc;
+  }
+  {
+    const cuuint64_t K = (cuuint64_t)ntaps * Cin;
+    cuuint64_t dims[3] = {K, (cuuint64_t)Cout, 2};
+    cuuint64_t strides[2] = {K * 2, (cuuint64_t)Cout * K * 2};
+    cuuint32_t box[3] = {64, (cuuint32_t)block_n, 1};
+    if (int rc = make_map(&tmB, wp, 3, dims, strides, box)) return rc;
+  }
+  switch (block_n) {
+    case 256: return launch_conv<256>(tmA, tmB, p, st);
+    case 128: return launch_conv<128>(tmA, tmB, p, st);
+    default: return launch_conv<64>(tmA, tmB, p, st);
+  }
+}
+
+}  // namespace ammc
+
+using namespace ammc;
+
+extern "C" int ammc_pack_conv_weights(const float* w, void* wp, int Cout, int Cin, void* stream) {
+  AMMC_REQUIRE(w && wp && Cout > 0 && Cin > 0, "bad argument");
+  long long total = (long long)Cout * Cin * 9;
+  pack_weights_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)wp, Cout, Cin, 9);
+  AMMC_LAUNCH_CHECK("pack_weights_kernel");
+  return 0;
+}
+
+extern "C" int ammc_pack_conv_weights_1x1(const float* w, void* wp, int Cout, int Cin, void* stream) {
+  AMMC_REQUIRE(w && wp && Cout > 0 && Cin > 0, "bad argument");
+  long long total = (long long)Cout * Cin;
+  pack_weights_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)wp, Cout, Cin, 1);
+  AMMC_LAUNCH_CHECK("pack_weights_kernel");
+  return 0;
+}
+
+extern "C" int ammc_conv1x1_bn_relu(const void* xp, const void* wp, const float* scale, const float* shift,
+                                    void* out_planes, float* out_nchw, const float* res_nchw, int b, int Cin, int Cout,
+                                    int h, int w, int precision, int relu, void* stream) {
+  return conv_igemm(xp, wp, scale, shift, out_planes, out_nchw, res_nchw, b, Cin, Cout, h, w, 1, precision, relu,
+                    (cudaStream_t)stream);
+}
+
+extern "C" int ammc_pack_nhwc(const float* x, void* xp, int b, int C, int h, int w, void* stream) {
+  AMMC_REQUIRE(x && xp && b > 0 && C > 0 && h > 0 && w > 0, "bad argument");
+  AMMC_REQUIRE(b <= 65535, "batch %d too large for one pack launch", b);
+  const int HW = h * w;
+  pack_nhwc_kernel<<<dim3(ceil_div(HW, 32), ceil_div(C, 32), b), 256, 0, (cudaStream_t)stream>>>(
+      x, (__nv_bfloat16*)xp, C, HW, (long long)b * HW * C);
+  AMMC_LAUNCH_CHECK("pack_nhwc_kernel");
+  return 0;
+}
+
+extern "C" int ammc_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, float eps,
+                            float* scale, float* shift, int C, void* stream) {
+  AMMC_REQUIRE(gamma && beta && mean && var && scale && shift && C > 0, "bad argument");
+  bn_fold_kernel<<<ceil_div(C, 256), 256, 0, (cudaStream_t)stream>>>(gamma, beta, mean, var, eps, scale, shift, C);
+  AMMC_LAUNCH_CHECK("bn_fold_kernel");
+  return 0;
+}
+
+extern "C" int ammc_conv3x3_bn_relu(const void* xp, const void* wp, const float* scale, const float* shift,
+                                    void* out_planes, float* out_nchw, const float* res_nchw, int b, int Cin, int Cout,
+                                    int h, int w, int precision, int relu, void* stream) {
+  return conv_igemm(xp, wp, scale, shift, out_planes, out_nchw, res_nchw, b, Cin, Cout, h, w, 9, precision, relu,
+                    (cudaStream_t)stream);
+}

@@ -1,0 +1,865 @@
+// Memory module (VQ codebook with top-k read), generic-shape fp32 path.
+//
+// Replaces the ATen op sequence of reference Code/models/unet.py:282-331,384-387 (forward), its autograd
+// backward, and the EMA bank update (unet.py:298-309).  Everything is exact fp32 FMA arithmetic, so the
+// top-k ranking follows the reference's fp32 ranking; `dist`, the one-hot matrix and the permuted copies
+// the reference materialises never exist in HBM.
+//
+// Kernels (N = b*h*w pixels, C channels, D embed_dim, M items, k):
+//   bank_transpose / bank_norms / dec_table   per-call operand prep (tiny):  E^T [M,D], ||e||^2 [M],
+//                                             T_j = (dec_w[:, jD:(j+1)D] . E)^T  [k][M][C]
+//   enc1x1_kernel     z[n,:] = enc_w . x[n,:] + enc_b          NCHW in, [N,D] out         (unet.py:326)
+//   address_kernel    dist -> top-k -> idx, read, q1, per-pixel SSE, EMA statistics      (unet.py:283-311)
+//   dec_gather_kernel out[n,:] = sum_j T_j[idx_j(n)] + dec_b (+ x[n,:])  NCHW out         (unet.py:328-330,386)
+//        (dec is linear and the read is a concatenation of bank rows, so dec(read_n) is a sum of k rows of
+//         the precomputed tables: the N x kD x C contraction becomes a gather)
+//   sse_frame_kernel / diff_kernel            deterministic per-frame and global commit reductions (unet.py:310)
+//   backward: gz_kernel, gx_kernel, genc_w_kernel, gdec_scatter_kernel, gdec_w_kernel
+//   ema_*                                     unet.py:298-309
+#include "common.cuh"
+#include <float.h>
+
+namespace ammc {
+
+// ------------------------------------------------------------------------------------------------
+// prep
+// ------------------------------------------------------------------------------------------------
+__global__ void bank_transpose_kernel(const float* __restrict__ embed, float* __restrict__ bank_t, int D, int M) {
+  __shared__ float tile[32][33];
+  const int m0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    int d = d0 + r, m = m0 + threadIdx.x;
+    tile[r][threadIdx.x] = (d < D && m < M) ? embed[(size_t)d * M + m] : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    int m = m0 + r, d = d0 + threadIdx.x;
+    if (m < M && d < D) bank_t[(size_t)m * D + d] = tile[threadIdx.x][r];
+  }
+}
+
+__global__ void bank_norms_kernel(const float* __restrict__ embed, float* __restrict__ en2, int D, int M) {
+  int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  float acc = 0.f;
+  for (int d = 0; d < D; ++d) {
+    float v = embed[(size_t)d * M + m];
+    acc = fmaf(v, v, acc);
+  }
+  en2[m] = acc;
+}
+
+// T[j][m][c] = sum_d dec_w[c][j*D + d] * embed[d][m]
+__global__ void dec_table_kernel(const float* __restrict__ dec_w, const float* __restrict__ embed,
+                                 float* __restrict__ T, int C, int D, int M, int k) {
+  __shared__ float Ws[32][33];  // [c][d]
+  __shared__ float Es[32][33];  // [d][m]
+  const int c0 = blockIdx.x * 32, m0 = blockIdx.y * 32, j = blockIdx.z;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int d0 = 0; d0 < D; d0 += 32) {
+    for (int r = ty; r < 32; r += 8) {
+      int c = c0 + r, d = d0 + tx;
+      Ws[r][tx] = (c < C && d < D) ? dec_w[(size_t)c * (k * D) + (size_t)j * D + d] : 0.f;
+      int dd = d0 + r, m = m0 + tx;
+      Es[r][tx] = (dd < D && m < M) ? embed[(size_t)dd * M + m] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int d = 0; d < 32; ++d) {
+      float wv = Ws[tx][d];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[i] = fmaf(wv, Es[d][ty * 4 + i], acc[i]);
+    }
+    __syncthreads();
+  }
+  int c = c0 + tx;
+  if (c < C) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int m = m0 + ty * 4 + i;
+      if (m < M) T[((size_t)j * M + m) * C + c] = acc[i];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// enc 1x1:  z[n, d] = sum_c w[d, c] * x[img, c, p] + bias[d]
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) enc1x1_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                      const float* __restrict__ bias, float* __restrict__ z,
+                                                      int N, int HW, int C, int D) {
+  __shared__ __align__(16) float Xs[16][64];
+  __shared__ __align__(16) float Ws[16][68];
+  const int t = threadIdx.x;
+  const int n0 = blockIdx.x * 64, d0 = blockIdx.y * 64;
+  const int tx = t & 15, ty = t >> 4;  // tx -> d group, ty -> px group
+  // fixed pixel for this thread's X loads
+  const int lp = t & 63, lc = t >> 6;
+  const int ln = n0 + lp;
+  const bool lvalid = ln < N;
+  const int limg = lvalid ? ln / HW : 0, lpp = lvalid ? ln % HW : 0;
+  const float* xbase = x + ((size_t)limg * C) * HW + lpp;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int c0 = 0; c0 < C; c0 += 16) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int c = c0 + lc + 4 * i;
+      Xs[lc + 4 * i][lp] = (lvalid && c < C) ? xbase[(size_t)c * HW] : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int e = t + i * 256;
+      int d = e >> 4, c = e & 15;
+      Ws[c][d] = (d0 + d < D && c0 + c < C) ? w[(size_t)(d0 + d) * C + c0 + c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float4 a = *reinterpret_cast<const float4*>(&Xs[kk][ty * 4]);
+      float4 bq = *reinterpret_cast<const float4*>(&Ws[kk][tx * 4]);
+      float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {bq.x, bq.y, bq.z, bq.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int n = n0 + ty * 4 + i;
+    if (n >= N) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int d = d0 + tx * 4 + j;
+      if (d < D) z[(size_t)n * D + d] = acc[i][j] + bias[d];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// addressing: distances -> top-k -> gathers -> commit partials (+ EMA statistics)
+// ------------------------------------------------------------------------------------------------
+template <int K>
+struct TopK {
+  float v[K];
+  int id[K];
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int i = 0; i < K; ++i) { v[i] = INFINITY; id[i] = 0x7fffffff; }
+  }
+  // strict total order: smaller distance first, ties to the lower index
+  static __device__ __forceinline__ bool before(float a, int ia, float b, int ib) {
+    return a < b || (a == b && ia < ib);
+  }
+  __device__ __forceinline__ void insert(float d, int j) {
+    if (!before(d, j, v[K - 1], id[K - 1])) return;
+    v[K - 1] = d; id[K - 1] = j;
+#pragma unroll
+    for (int i = K - 1; i > 0; --i) {
+      if (before(v[i], id[i], v[i - 1], id[i - 1])) {
+        float tv = v[i]; v[i] = v[i - 1]; v[i - 1] = tv;
+        int ti = id[i]; id[i] = id[i - 1]; id[i - 1] = ti;
+      }
+    }
+  }
+};
+
+template <int K>
+__global__ void __launch_bounds__(256) address_kernel(
+    const float* __restrict__ z, const float* __restrict__ embed, const float* __restrict__ en2,
+    const float* __restrict__ bank_t, float* __restrict__ read, float* __restrict__ q1,
+    int64_t* __restrict__ idx, float* __restrict__ sse_px, float* __restrict__ counts,
+    float* __restrict__ embed_sum, int N, int D, int M) {
+  __shared__ __align__(16) float Zs[16][68];
+  __shared__ __align__(16) float Es[16][64];
+  __shared__ float Ds[64][65];
+  __shared__ float zn2_s[64];
+  const int t = threadIdx.x;
+  const int n0 = blockIdx.x * 64;
+  const int tx = t & 15, ty = t >> 4;     // tx -> item group, ty -> px group (GEMM phase)
+  const int px = t >> 2, part = t & 3;    // team-of-4 mapping (scan / gather phases)
+  const int n_team = n0 + px;
+  const bool team_valid = n_team < N;
+
+  // ||z||^2 per pixel
+  {
+    float s = 0.f;
+    if (team_valid) {
+      const float* zr = z + (size_t)n_team * D;
+      for (int d = part; d < D; d += 4) { float v = zr[d]; s = fmaf(v, v, s); }
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    if (part == 0) zn2_s[px] = s;
+  }
+  TopK<K> top;
+  top.init();
+  __syncthreads();
+
+  for (int m0 = 0; m0 < M; m0 += 64) {
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int d0 = 0; d0 < D; d0 += 16) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        int e = t + i * 256;
+        int p = e >> 4, d = e & 15;
+        Zs[d][p] = (n0 + p < N && d0 + d < D) ? z[(size_t)(n0 + p) * D + d0 + d] : 0.f;
+        int dd = e >> 6, m = e & 63;
+        Es[dd][m] = (d0 + dd < D && m0 + m < M) ? embed[(size_t)(d0 + dd) * M + m0 + m] : 0.f;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int kk = 0; kk < 16; ++kk) {
+        float4 a = *reinterpret_cast<const float4*>(&Zs[kk][ty * 4]);
+        float4 bq = *reinterpret_cast<const float4*>(&Es[kk][tx * 4]);
+        float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {bq.x, bq.y, bq.z, bq.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+    // dist = (||z||^2 - 2 z.e) + ||e||^2, same association as unet.py:283-288
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int m = m0 + tx * 4 + j;
+      float e2 = m < M ? en2[m] : 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float dv = __fadd_rn(__fsub_rn(zn2_s[ty * 4 + i], 2.f * acc[i][j]), e2);
+        Ds[ty * 4 + i][tx * 4 + j] = m < M ? dv : FLT_MAX;
+      }
+    }
+    __syncthreads();
+    for (int s = 0; s < 16; ++s) {
+      int j = part + 4 * s;
+      if (m0 + j < M) top.insert(Ds[px][j], m0 + j);
+    }
+    __syncthreads();
+  }
+  // merge the four partial lists of a team (butterfly; order-independent thanks to the total order)
+#pragma unroll
+  for (int o = 1; o <= 2; o <<= 1) {
+    float ov[K]; int oi[K];
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+      ov[i] = __shfl_xor_sync(0xffffffffu, top.v[i], o);
+      oi[i] = __shfl_xor_sync(0xffffffffu, top.id[i], o);
+    }
+#pragma unroll
+    for (int i = 0; i < K; ++i) top.insert(ov[i], oi[i]);
+  }
+  // NaN distances (a diverged bank) never enter the list; keep the gathers in bounds regardless
+#pragma unroll
+  for (int i = 0; i < K; ++i) top.id[i] = min(top.id[i], M - 1);
+  if (part == 0 && team_valid) {
+#pragma unroll
+    for (int i = 0; i < K; ++i) idx[(size_t)n_team * K + i] = (int64_t)top.id[i];
+  }
+  // gathers: every lane of the team holds the merged list
+  float sse = 0.f;
+  if (team_valid) {
+    const float* zr = z + (size_t)n_team * D;
+    const float* e1 = bank_t + (size_t)top.id[0] * D;
+    for (int d = part; d < D; d += 4) {
+      float zv = zr[d], ev = e1[d];
+      float df = ev - zv;
+      q1[(size_t)n_team * D + d] = zv + df;          // straight-through value, unet.py:311
+      sse = fmaf(df, df, sse);
+      if (embed_sum) atomicAdd(&embed_sum[(size_t)d * M + top.id[0]], zv);
+    }
+    if (read) {
+#pragma unroll
+      for (int i = 0; i < K; ++i) {
+        const float* er = bank_t + (size_t)top.id[i] * D;
+        float* rr = read + ((size_t)n_team * K + i) * D;
+        for (int d = part; d < D; d += 4) rr[d] = er[d];
+      }
+    }
+  }
+  sse += __shfl_xor_sync(0xffffffffu, sse, 1);
+  sse += __shfl_xor_sync(0xffffffffu, sse, 2);
+  if (part == 0 && team_valid) {
+    sse_px[n_team] = sse;
+    if (counts) atomicAdd(&counts[top.id[0]], 1.f);
+  }
+}
+
+__global__ void sse_frame_kernel(const float* __restrict__ sse_px, float* __restrict__ sse_frame, int64_t rows) {
+  __shared__ float red[33];
+  const float* p = sse_px + (size_t)blockIdx.x * rows;
+  float s = 0.f;
+  for (int64_t i = threadIdx.x; i < rows; i += blockDim.x) s += p[i];
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) sse_frame[blockIdx.x] = s;
+}
+
+__global__ void diff_kernel(const float* __restrict__ sse_frame, float* __restrict__ diff, int frames, double inv_count) {
+  __shared__ float red[33];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < frames; i += blockDim.x) s += sse_frame[i];
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) diff[0] = (float)((double)s * inv_count);
+}
+
+// ------------------------------------------------------------------------------------------------
+// dec 1x1 as a table gather + bias + residual, NCHW output
+// ------------------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(256) dec_gather_kernel(
+    const float* __restrict__ T, const int64_t* __restrict__ idx, const float* __restrict__ dec_b,
+    const float* __restrict__ x, float* __restrict__ out, int N, int HW, int C, int M, int chunks_per_block) {
+  __shared__ float tile[32][33];
+  __shared__ int idx_s[32][K];
+  const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
+  const int n0 = blockIdx.x * 32;
+  for (int e = threadIdx.x; e < 32 * K; e += 256) {
+    int p = e / K, j = e % K;
+    idx_s[p][j] = (n0 + p < N) ? (int)idx[(size_t)(n0 + p) * K + j] : 0;
+  }
+  const int n = n0 + lane;
+  const bool nvalid = n < N;
+  const int img = nvalid ? n / HW : 0, pp = nvalid ? n % HW : 0;
+  __syncthreads();
+  const int cbeg = blockIdx.y * chunks_per_block * 32;
+  for (int cc = 0; cc < chunks_per_block; ++cc) {
+    const int c0 = cbeg + cc * 32;
+    if (c0 >= C) break;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      int p = wv * 4 + r;
+      float v = 0.f;
+      if (n0 + p < N && c0 + lane < C) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) v += T[((size_t)j * M + idx_s[p][j]) * C + c0 + lane];
+      }
+      tile[p][lane] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      int ch = wv * 4 + r, c = c0 + ch;
+      if (nvalid && c < C) {
+        size_t o = ((size_t)img * C + c) * HW + pp;
+        float v = tile[lane][ch] + dec_b[c];
+        if (x) v += x[o];
+        out[o] = v;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// embed_code
+// ------------------------------------------------------------------------------------------------
+__global__ void embed_code_kernel(const int64_t* __restrict__ ids, const float* __restrict__ embed,
+                                  float* __restrict__ out, int64_t n_ids, int D, int M) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_ids * D) return;
+  int64_t i = e / D;
+  int d = (int)(e % D);
+  int64_t id = ids[i];
+  out[e] = (id >= 0 && id < M) ? embed[(size_t)d * M + id] : 0.f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// EMA bank update (unet.py:298-309)
+// ------------------------------------------------------------------------------------------------
+__global__ void ema_cluster_kernel(float* __restrict__ cluster_size, const float* __restrict__ counts, int M,
+                                   float decay) {
+  const float om = 1.f - decay;
+  for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < M; m += gridDim.x * blockDim.x)
+    cluster_size[m] = __fadd_rn(__fmul_rn(cluster_size[m], decay), __fmul_rn(om, counts[m]));
+}
+
+// Every block recomputes n = sum(cluster_size) in the same order, so all blocks use the identical value.
+__global__ void __launch_bounds__(256) ema_embed_kernel(float* __restrict__ embed, float* __restrict__ embed_avg,
+                                                         const float* __restrict__ embed_sum,
+                                                         const float* __restrict__ cluster_size, int D, int M,
+                                                         float decay, float eps, int elems_per_block) {
+  __shared__ float red[33];
+  float s = 0.f;
+  for (int m = threadIdx.x; m < M; m += blockDim.x) s += cluster_size[m];
+  const float n = block_sum(s, red);
+  const float om = 1.f - decay;
+  const float denom = __fadd_rn(n, (float)((double)M * (double)eps));
+  const int64_t total = (int64_t)D * M;
+  const int64_t beg = (int64_t)blockIdx.x * elems_per_block;
+  const int64_t end = min(total, beg + elems_per_block);
+  for (int64_t e = beg + threadIdx.x; e < end; e += blockDim.x) {
+    int m = (int)(e % M);
+    float cs = __fmul_rn(__fdiv_rn(__fadd_rn(cluster_size[m], eps), denom), n);
+    float avg = __fadd_rn(__fmul_rn(embed_avg[e], decay), __fmul_rn(om, embed_sum[e]));
+    embed_avg[e] = avg;
+    embed[e] = __fdiv_rn(avg, cs);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------
+// gz[n,d] = g_diff * 2 (z - e1) / (N D) + g_q1 ;  g_enc_b[d] += sum_n gz
+__global__ void __launch_bounds__(256) gz_kernel(const float* __restrict__ z, const float* __restrict__ bank_t,
+                                                  const int64_t* __restrict__ idx, const float* __restrict__ g_diff,
+                                                  const float* __restrict__ g_q1, float* __restrict__ gz,
+                                                  float* __restrict__ g_enc_b, int N, int D, int K, double inv_count) {
+  extern __shared__ float colsum[];  // D
+  for (int d = threadIdx.x; d < D; d += blockDim.x) colsum[d] = 0.f;
+  __syncthreads();
+  const float coef = (float)((double)g_diff[0] * 2.0 * inv_count);
+  const int n0 = blockIdx.x * 64;
+  const int rows = min(64, N - n0);
+  for (int e = threadIdx.x; e < rows * D; e += blockDim.x) {
+    int p = e / D, d = e % D;
+    size_t n = (size_t)(n0 + p);
+    int i1 = (int)idx[n * K];
+    float v = coef * (z[n * D + d] - bank_t[(size_t)i1 * D + d]);
+    if (g_q1) v += g_q1[n * D + d];
+    gz[n * D + d] = v;
+    atomicAdd(&colsum[d], v);
+  }
+  __syncthreads();
+  for (int d = threadIdx.x; d < D; d += blockDim.x) atomicAdd(&g_enc_b[d], colsum[d]);
+}
+
+// gx[img,c,p] = sum_d enc_w[d,c] gz[n,d] (+ g_out[img,c,p])
+__global__ void __launch_bounds__(256) gx_kernel(const float* __restrict__ gz, const float* __restrict__ enc_w,
+                                                  const float* __restrict__ g_out, float* __restrict__ gx,
+                                                  int N, int HW, int C, int D, int residual) {
+  __shared__ __align__(16) float As[16][68];  // [d][px]
+  __shared__ __align__(16) float Bs[16][64];  // [d][c]
+  const int t = threadIdx.x;
+  const int n0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+  const int tx = t & 15, ty = t >> 4;  // tx -> px group, ty -> c group
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int d0 = 0; d0 < D; d0 += 16) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int e = t + i * 256;
+      int p = e >> 4, d = e & 15;
+      As[d][p] = (n0 + p < N && d0 + d < D) ? gz[(size_t)(n0 + p) * D + d0 + d] : 0.f;
+      int dd = e >> 6, c = e & 63;
+      Bs[dd][c] = (d0 + dd < D && c0 + c < C) ? enc_w[(size_t)(d0 + dd) * C + c0 + c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float4 a = *reinterpret_cast<const float4*>(&As[kk][tx * 4]);
+      float4 bq = *reinterpret_cast<const float4*>(&Bs[kk][ty * 4]);
+      float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {bq.x, bq.y, bq.z, bq.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int n = n0 + tx * 4 + i;
+    if (n >= N) continue;
+    int img = n / HW, pp = n % HW;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int c = c0 + ty * 4 + j;
+      if (c >= C) continue;
+      size_t o = ((size_t)img * C + c) * HW + pp;
+      float v = acc[i][j];
+      if (residual) v += g_out[o];
+      gx[o] = v;
+    }
+  }
+}
+
+// g_enc_w[d,c] += sum_{n in split} gz[n,d] x[img,c,p]   (split-K over pixels, atomics)
+__global__ void __launch_bounds__(256) genc_w_kernel(const float* __restrict__ gz, const float* __restrict__ x,
+                                                      float* __restrict__ g_enc_w, int N, int HW, int C, int D,
+                                                      int px_per_split) {
+  __shared__ __align__(16) float As[16][64];  // [n][d]
+  __shared__ __align__(16) float Bs[16][68];  // [n][c]
+  const int t = threadIdx.x;
+  const int d0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+  const int nbeg = blockIdx.z * px_per_split, nend = min(N, nbeg + px_per_split);
+  const int tx = t & 15, ty = t >> 4;  // tx -> c group, ty -> d group
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int nn = nbeg; nn < nend; nn += 16) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int e = t + i * 256;
+      int r = e >> 6, d = e & 63;
+      int n = nn + r;
+      As[r][d] = (n < nend && d0 + d < D) ? gz[(size_t)n * D + d0 + d] : 0.f;
+      int r2 = e & 15, c = e >> 4;
+      int n2 = nn + r2;
+      float v = 0.f;
+      if (n2 < nend && c0 + c < C) {
+        int img = n2 / HW, pp = n2 % HW;
+        v = x[((size_t)img * C + c0 + c) * HW + pp];
+      }
+      Bs[r2][c] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      float4 bq = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {bq.x, bq.y, bq.z, bq.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int d = d0 + ty * 4 + i;
+    if (d >= D) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int c = c0 + tx * 4 + j;
+      if (c < C) atomicAdd(&g_enc_w[(size_t)d * C + c], acc[i][j]);
+    }
+  }
+}
+
+// G[j][idx_j(n)][c] += g_out[img,c,p] ;  g_dec_b[c] += sum_n g_out
+template <int K>
+__global__ void __launch_bounds__(256) gdec_scatter_kernel(const float* __restrict__ g_out,
+                                                            const int64_t* __restrict__ idx, float* __restrict__ G,
+                                                            float* __restrict__ g_dec_b, int N, int HW, int C, int M,
+                                                            int chunks_per_block) {
+  __shared__ float tile[32][33];  // [ch][px]
+  __shared__ int idx_s[32][K];
+  const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
+  const int n0 = blockIdx.x * 32;
+  for (int e = threadIdx.x; e < 32 * K; e += 256) {
+    int p = e / K, j = e % K;
+    idx_s[p][j] = (n0 + p < N) ? (int)idx[(size_t)(n0 + p) * K + j] : 0;
+  }
+  const int n = n0 + lane;
+  const bool nvalid = n < N;
+  const int img = nvalid ? n / HW : 0, pp = nvalid ? n % HW : 0;
+  __syncthreads();
+  const int cbeg = blockIdx.y * chunks_per_block * 32;
+  for (int cc = 0; cc < chunks_per_block; ++cc) {
+    const int c0 = cbeg + cc * 32;
+    if (c0 >= C) break;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      int ch = wv * 4 + r, c = c0 + ch;
+      float v = (nvalid && c < C) ? g_out[((size_t)img * C + c) * HW + pp] : 0.f;
+      tile[ch][lane] = v;
+      float s = warp_sum(v);
+      if (lane == 0 && c < C) atomicAdd(&g_dec_b[c], s);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      int p = wv * 4 + r;
+      if (n0 + p < N && c0 + lane < C) {
+        float v = tile[lane][p];
+#pragma unroll
+        for (int j = 0; j < K; ++j) atomicAdd(&G[((size_t)j * M + idx_s[p][j]) * C + c0 + lane], v);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// g_dec_w[c][j*D + d] = sum_m G[j][m][c] * embed[d][m]
+__global__ void gdec_w_kernel(const float* __restrict__ G, const float* __restrict__ embed,
+                              float* __restrict__ g_dec_w, int C, int D, int M, int k) {
+  __shared__ float Gs[32][33];  // [m][c]
+  __shared__ float Es[32][33];  // [d][m]
+  const int d0 = blockIdx.x * 32, c0 = blockIdx.y * 32, j = blockIdx.z;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int m0 = 0; m0 < M; m0 += 32) {
+    for (int r = ty; r < 32; r += 8) {
+      int m = m0 + r, c = c0 + tx;
+      Gs[r][tx] = (m < M && c < C) ? G[((size_t)j * M + m) * C + c] : 0.f;
+      int d = d0 + r, mm = m0 + tx;
+      Es[r][tx] = (d < D && mm < M) ? embed[(size_t)d * M + mm] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int m = 0; m < 32; ++m) {
+      float ev = Es[tx][m];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[i] = fmaf(Gs[m][ty * 4 + i], ev, acc[i]);
+    }
+    __syncthreads();
+  }
+  int d = d0 + tx;
+  if (d < D) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int c = c0 + ty * 4 + i;
+      if (c < C) g_dec_w[(size_t)c * (k * D) + (size_t)j * D + d] = acc[i];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+struct MemWs {
+  float* bank_t; float* en2; float* T; float* sse_px;
+};
+
+static size_t mem_ws_bytes(int64_t N, int C, int D, int M, int k, bool with_table) {
+  size_t s = 0;
+  s += align_up((size_t)M * D * 4, 256);
+  s += align_up((size_t)M * 4, 256);
+  if (with_table) s += align_up((size_t)k * M * C * 4, 256);
+  s += align_up((size_t)N * 4, 256);
+  return s;
+}
+
+static int carve(Workspace& ws, MemWs& m, int64_t N, int C, int D, int M, int k, bool with_table) {
+  m.bank_t = ws.take<float>((size_t)M * D);
+  m.en2 = ws.take<float>(M);
+  m.T = with_table ? ws.take<float>((size_t)k * M * C) : nullptr;
+  m.sse_px = ws.take<float>(N);
+  if (!ws.ok()) return fail(AMMC_EWORKSPACE, "workspace too small");
+  return 0;
+}
+
+template <int K>
+static void launch_address(const float* z, const float* embed, const MemWs& m, float* read, float* q1, int64_t* idx,
+                           float* counts, float* embed_sum, int N, int D, int M, cudaStream_t st) {
+  address_kernel<K><<<ceil_div(N, 64), 256, 0, st>>>(z, embed, m.en2, m.bank_t, read, q1, idx, m.sse_px, counts,
+                                                      embed_sum, N, D, M);
+}
+
+static int run_address(const float* z, const float* embed, const MemWs& m, float* read, float* q1, int64_t* idx,
+                       float* counts, float* embed_sum, int64_t N, int D, int M, int k, cudaStream_t st) {
+  bank_transpose_kernel<<<dim3(ceil_div(M, 32), ceil_div(D, 32)), dim3(32, 8), 0, st>>>(embed, m.bank_t, D, M);
+  AMMC_LAUNCH_CHECK("bank_transpose_kernel");
+  bank_norms_kernel<<<ceil_div(M, 128), 128, 0, st>>>(embed, m.en2, D, M);
+  AMMC_LAUNCH_CHECK("bank_norms_kernel");
+  if (counts) AMMC_CUDA_CHECK(cudaMemsetAsync(counts, 0, (size_t)M * 4, st));
+  if (embed_sum) AMMC_CUDA_CHECK(cudaMemsetAsync(embed_sum, 0, (size_t)D * M * 4, st));
+  switch (k) {
+    case 1: launch_address<1>(z, embed, m, read, q1, idx, counts, embed_sum, (int)N, D, M, st); break;
+    case 2: launch_address<2>(z, embed, m, read, q1, idx, counts, embed_sum, (int)N, D, M, st); break;
+    case 3: launch_address<3>(z, embed, m, read, q1, idx, counts, embed_sum, (int)N, D, M, st); break;
+    case 4: launch_address<4>(z, embed, m, read, q1, idx, counts, embed_sum, (int)N, D, M, st); break;
+    case 5: launch_address<5>(z, embed, m, read, q1, idx, counts, embed_sum, (int)N, D, M, st); break;
+    case 6: launch_address<6>(z, embed, m, read, q1, idx, counts, embed_sum, (int)N, D, M, st); break;
+    case 7: launch_address<7>(z, embed, m, read, q1, idx, counts, embed_sum, (int)N, D, M, st); break;
+    case 8: launch_address<8>(z, embed, m, read, q1, idx, counts, embed_sum, (int)N, D, M, st); break;
+    default: return fail(AMMC_EUNSUPPORTED, "k=%d outside 1..%d", k, AMMC_MAX_K);
+  }
+  AMMC_LAUNCH_CHECK("address_kernel");
+  return 0;
+}
+
+static int run_commit(const MemWs& m, float* sse_frame, float* diff, int64_t N, int64_t rows_per_frame, int D,
+                      cudaStream_t st) {
+  int frames = (int)(N / rows_per_frame);
+  sse_frame_kernel<<<frames, 256, 0, st>>>(m.sse_px, sse_frame, rows_per_frame);
+  AMMC_LAUNCH_CHECK("sse_frame_kernel");
+  diff_kernel<<<1, 256, 0, st>>>(sse_frame, diff, frames, 1.0 / ((double)N * (double)D));
+  AMMC_LAUNCH_CHECK("diff_kernel");
+  return 0;
+}
+
+}  // namespace ammc
+
+using namespace ammc;
+
+extern "C" size_t ammc_mem_workspace_bytes(int b, int h, int w, int C, int D, int M, int k) {
+  return mem_ws_bytes((int64_t)b * h * w, C, D, M, k, true);
+}
+
+extern "C" size_t ammc_quantize_workspace_bytes(int64_t N, int D, int M, int k) {
+  return mem_ws_bytes(N, 0, D, M, k, false);
+}
+
+static int check_dims(int64_t N, int C, int D, int M, int k) {
+  AMMC_REQUIRE(N > 0 && N < (1LL << 31), "N=%lld out of range", (long long)N);
+  AMMC_REQUIRE(D > 0 && M > 0 && C >= 0, "bad dims C=%d D=%d M=%d", C, D, M);
+  if (k < 1 || k > AMMC_MAX_K) return fail(AMMC_EUNSUPPORTED, "k=%d outside 1..%d", k, AMMC_MAX_K);
+  AMMC_REQUIRE(k <= M, "k=%d exceeds n_embed=%d", k, M);  // torch.topk raises for k > M as well
+  return 0;
+}
+
+extern "C" int ammc_mem_fwd(const float* x, const float* enc_w, const float* enc_b, const float* embed,
+                            const float* dec_w, const float* dec_b, float* out, float* q1, int64_t* idx, float* z,
+                            float* sse_frame, float* diff, float* counts, float* embed_sum, void* workspace,
+                            size_t workspace_bytes, int b, int h, int w, int C, int D, int M, int k, int residual,
+                            void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t N = (int64_t)b * h * w;
+  const int HW = h * w;
+  if (int rc = check_dims(N, C, D, M, k)) return rc;
+  AMMC_REQUIRE(x && enc_w && enc_b && embed && dec_w && dec_b && out && q1 && idx && z && sse_frame && diff,
+               "null pointer argument");
+  Workspace ws(workspace, workspace_bytes);
+  MemWs m;
+  if (int rc = carve(ws, m, N, C, D, M, k, true)) return rc;
+  dec_table_kernel<<<dim3(ceil_div(C, 32), ceil_div(M, 32), k), dim3(32, 8), 0, st>>>(dec_w, embed, m.T, C, D, M, k);
+  AMMC_LAUNCH_CHECK("dec_table_kernel");
+  enc1x1_kernel<<<dim3(ceil_div(N, 64), ceil_div(D, 64)), 256, 0, st>>>(x, enc_w, enc_b, z, (int)N, HW, C, D);
+  AMMC_LAUNCH_CHECK("enc1x1_kernel");
+  if (int rc = run_address(z, embed, m, nullptr, q1, idx, counts, embed_sum, N, D, M, k, st)) return rc;
+  if (int rc = run_commit(m, sse_frame, diff, N, HW, D, st)) return rc;
+  const int chunks = 4;
+  dim3 grid(ceil_div(N, 32), ceil_div(ceil_div(C, 32), chunks));
+  const float* res = residual ? x : nullptr;
+  switch (k) {
+#define AMMC_DEC_CASE(KK) \
+  case KK: dec_gather_kernel<KK><<<grid, 256, 0, st>>>(m.T, idx, dec_b, res, out, (int)N, HW, C, M, chunks); break;
+    AMMC_DEC_CASE(1) AMMC_DEC_CASE(2) AMMC_DEC_CASE(3) AMMC_DEC_CASE(4)
+    AMMC_DEC_CASE(5) AMMC_DEC_CASE(6) AMMC_DEC_CASE(7) AMMC_DEC_CASE(8)
+#undef AMMC_DEC_CASE
+  }
+  AMMC_LAUNCH_CHECK("dec_gather_kernel");
+  return 0;
+}
+
+extern "C" int ammc_quantize_fwd(const float* z, const float* embed, float* read, float* q1, int64_t* idx,
+                                 float* sse_frame, float* diff, float* counts, float* embed_sum, void* workspace,
+                                 size_t workspace_bytes, int64_t N, int64_t rows_per_frame, int D, int M, int k,
+                                 void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int rc = check_dims(N, 0, D, M, k)) return rc;
+  AMMC_REQUIRE(z && embed && read && q1 && idx && sse_frame && diff, "null pointer argument");
+  AMMC_REQUIRE(rows_per_frame > 0 && N % rows_per_frame == 0, "N=%lld not a multiple of rows_per_frame=%lld",
+               (long long)N, (long long)rows_per_frame);
+  Workspace ws(workspace, workspace_bytes);
+  MemWs m;
+  if (int rc = carve(ws, m, N, 0, D, M, k, false)) return rc;
+  if (int rc = run_address(z, embed, m, read, q1, idx, counts, embed_sum, N, D, M, k, st)) return rc;
+  return run_commit(m, sse_frame, diff, N, rows_per_frame, D, st);
+}
+
+extern "C" size_t ammc_quantize_bwd_workspace_bytes(int64_t N, int D, int M) {
+  (void)N;
+  return align_up((size_t)M * D * 4, 256) + align_up((size_t)D * 4, 256);
+}
+
+extern "C" int ammc_quantize_bwd(const float* z, const float* embed, const int64_t* idx, const float* g_diff,
+                                 const float* g_q1, float* gz, void* workspace, size_t workspace_bytes, int64_t N,
+                                 int D, int M, int k, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int rc = check_dims(N, 0, D, M, k)) return rc;
+  AMMC_REQUIRE(z && embed && idx && g_diff && gz, "null pointer argument");
+  AMMC_REQUIRE(D <= 8192, "embed_dim %d too large for the backward column-sum buffer", D);
+  Workspace ws(workspace, workspace_bytes);
+  float* bank_t = ws.take<float>((size_t)M * D);
+  float* colsum = ws.take<float>(D);
+  if (!ws.ok()) return fail(AMMC_EWORKSPACE, "workspace too small");
+  bank_transpose_kernel<<<dim3(ceil_div(M, 32), ceil_div(D, 32)), dim3(32, 8), 0, st>>>(embed, bank_t, D, M);
+  AMMC_LAUNCH_CHECK("bank_transpose_kernel");
+  AMMC_CUDA_CHECK(cudaMemsetAsync(colsum, 0, (size_t)D * 4, st));
+  gz_kernel<<<ceil_div(N, 64), 256, (size_t)D * 4, st>>>(z, bank_t, idx, g_diff, g_q1, gz, colsum, (int)N, D, k,
+                                                        1.0 / ((double)N * (double)D));
+  AMMC_LAUNCH_CHECK("gz_kernel");
+  return 0;
+}
+
+extern "C" int ammc_embed_code(const int64_t* ids, const float* embed, float* out, int64_t n_ids, int D, int M,
+                               void* stream) {
+  AMMC_REQUIRE(ids && embed && out && n_ids >= 0 && D > 0 && M > 0, "bad argument");
+  if (n_ids == 0) return 0;
+  int64_t total = n_ids * D;
+  embed_code_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(ids, embed, out, n_ids, D, M);
+  AMMC_LAUNCH_CHECK("embed_code_kernel");
+  return 0;
+}
+
+extern "C" int ammc_ema_update(float* embed, float* cluster_size, float* embed_avg, const float* counts,
+                               const float* embed_sum, int D, int M, float decay, float eps, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  AMMC_REQUIRE(embed && cluster_size && embed_avg && counts && embed_sum && D > 0 && M > 0, "bad argument");
+  ema_cluster_kernel<<<ceil_div(M, 256), 256, 0, st>>>(cluster_size, counts, M, decay);
+  AMMC_LAUNCH_CHECK("ema_cluster_kernel");
+  const int64_t total = (int64_t)D * M;
+  const int per_block = 4096;
+  ema_embed_kernel<<<ceil_div(total, per_block), 256, 0, st>>>(embed, embed_avg, embed_sum, cluster_size, D, M, decay,
+                                                               eps, per_block);
+  AMMC_LAUNCH_CHECK("ema_embed_kernel");
+  return 0;
+}
+
+extern "C" size_t ammc_mem_bwd_workspace_bytes(int b, int h, int w, int C, int D, int M, int k) {
+  int64_t N = (int64_t)b * h * w;
+  return align_up((size_t)M * D * 4, 256) + align_up((size_t)N * D * 4, 256) + align_up((size_t)k * M * C * 4, 256);
+}
+
+extern "C" int ammc_mem_bwd(const float* x, const float* enc_w, const float* embed, const int64_t* idx,
+                            const float* z, const float* g_out, const float* g_diff, const float* g_q1, float* gx,
+                            float* g_enc_w, float* g_enc_b, float* g_dec_w, float* g_dec_b, void* workspace,
+                            size_t workspace_bytes, int b, int h, int w, int C, int D, int M, int k, int residual,
+                            void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t N = (int64_t)b * h * w;
+  const int HW = h * w;
+  if (int rc = check_dims(N, C, D, M, k)) return rc;
+  AMMC_REQUIRE(x && enc_w && embed && idx && z && g_out && g_diff && gx && g_enc_w && g_enc_b && g_dec_w && g_dec_b,
+               "null pointer argument");
+  AMMC_REQUIRE(D <= 8192, "embed_dim %d too large for the backward column-sum buffer", D);
+  Workspace ws(workspace, workspace_bytes);
+  float* bank_t = ws.take<float>((size_t)M * D);
+  float* gz = ws.take<float>((size_t)N * D);
+  float* G = ws.take<float>((size_t)k * M * C);
+  if (!ws.ok()) return fail(AMMC_EWORKSPACE, "workspace too small");
+  bank_transpose_kernel<<<dim3(ceil_div(M, 32), ceil_div(D, 32)), dim3(32, 8), 0, st>>>(embed, bank_t, D, M);
+  AMMC_LAUNCH_CHECK("bank_transpose_kernel");
+  AMMC_CUDA_CHECK(cudaMemsetAsync(g_enc_b, 0, (size_t)D * 4, st));
+  AMMC_CUDA_CHECK(cudaMemsetAsync(g_enc_w, 0, (size_t)D * C * 4, st));
+  AMMC_CUDA_CHECK(cudaMemsetAsync(g_dec_b, 0, (size_t)C * 4, st));
+  AMMC_CUDA_CHECK(cudaMemsetAsync(G, 0, (size_t)k * M * C * 4, st));
+  gz_kernel<<<ceil_div(N, 64), 256, (size_t)D * 4, st>>>(z, bank_t, idx, g_diff, g_q1, gz, g_enc_b, (int)N, D, k,
+                                                        1.0 / ((double)N * (double)D));
+  AMMC_LAUNCH_CHECK("gz_kernel");
+  gx_kernel<<<dim3(ceil_div(N, 64), ceil_div(C, 64)), 256, 0, st>>>(gz, enc_w, g_out, gx, (int)N, HW, C, D, residual);
+  AMMC_LAUNCH_CHECK("gx_kernel");
+  {
+    int tiles = ceil_div(D, 64) * ceil_div(C, 64);
+    int splits = max(1, min((int)ceil_div(N, 256), ceil_div(4 * num_sms(), tiles)));
+    int per = (int)align_up((size_t)ceil_div(N, splits), 16);
+    splits = ceil_div(N, per);
+    genc_w_kernel<<<dim3(ceil_div(D, 64), ceil_div(C, 64), splits), 256, 0, st>>>(gz, x, g_enc_w, (int)N, HW, C, D, per);
+    AMMC_LAUNCH_CHECK("genc_w_kernel");
+  }
+  {
+    const int chunks = 4;
+    dim3 grid(ceil_div(N, 32), ceil_div(ceil_div(C, 32), chunks));
+    switch (k) {
+#define AMMC_SC_CASE(KK) \
+  case KK: gdec_scatter_kernel<KK><<<grid, 256, 0, st>>>(g_out, idx, G, g_dec_b, (int)N, HW, C, M, chunks); break;
+      AMMC_SC_CASE(1) AMMC_SC_CASE(2) AMMC_SC_CASE(3) AMMC_SC_CASE(4)
+      AMMC_SC_CASE(5) AMMC_SC_CASE(6) AMMC_SC_CASE(7) AMMC_SC_CASE(8)
+#undef AMMC_SC_CASE
+    }
+    AMMC_LAUNCH_CHECK("gdec_scatter_kernel");
+  }
+  gdec_w_kernel<<<dim3(ceil_div(D, 32), ceil_div(C, 32), k), dim3(32, 8), 0, st>>>(G, embed, g_dec_w, C, D, M, k);
+  AMMC_LAUNCH_CHECK("gdec_w_kernel");
+  return 0;
+}

@@ -1,0 +1,344 @@
+"""torch.autograd.Function wrappers around the C ABI (raw device pointers + the current CUDA stream).
+
+PyTorch is plumbing here: it owns device memory (caching allocator), streams and autograd bookkeeping; all
+arithmetic of the path runs in libammc_b200.so.  Inputs must be CUDA fp32 tensors -- anything else raises.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _capi
+
+
+# --------------------------------------------------------------------------------------------------
+# plumbing
+# --------------------------------------------------------------------------------------------------
+def _p(t: Optional[torch.Tensor]):
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda_f32(*tensors, names=()):
+    for i, t in enumerate(tensors):
+        if t is None:
+            continue
+        nm = names[i] if i < len(names) else "tensor %d" % i
+        if not t.is_cuda:
+            raise RuntimeError("ammc_b200: %s must live on a CUDA device (there is no CPU path)" % nm)
+        if t.dtype != torch.float32:
+            raise RuntimeError("ammc_b200: %s must be float32, got %s" % (nm, t.dtype))
+
+
+_checked_devices = set()
+
+
+def _check_device(dev: torch.device):
+    if dev.index in _checked_devices:
+        return
+    with torch.cuda.device(dev):
+        if not _capi.load().ammc_device_supported():
+            raise RuntimeError("ammc_b200: device %s is not sm_100 (B200); this library has no other target" % dev)
+    _checked_devices.add(dev.index)
+
+
+_workspaces: Dict[Tuple[int, int], torch.Tensor] = {}
+
+
+def _workspace(nbytes: int, device: torch.device) -> torch.Tensor:
+    """Grow-only scratch buffer per (device, stream), owned by PyTorch's caching allocator."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+# launch counter: bench.py reports how many of OUR kernels ran in the timed region
+LAUNCHES = {"count": 0}
+
+
+def _count(n):
+    LAUNCHES["count"] += n
+
+
+# --------------------------------------------------------------------------------------------------
+# memory module
+# --------------------------------------------------------------------------------------------------
+def mem_forward_raw(x, enc_w, enc_b, embed, dec_w, dec_b, k: int, residual: bool, want_stats: bool):
+    """One fused-module forward.  Returns dict(out, q1[N,D], idx[N,k], z[N,D], sse_frame[b], diff[1], counts, embed_sum)."""
+    _require_cuda_f32(x, enc_w, enc_b, embed, dec_w, dec_b, names=("x", "enc.weight", "enc.bias", "embed", "dec.weight", "dec.bias"))
+    if x.dim() != 4:
+        raise RuntimeError("ammc_b200: memory module input must be [b, C, h, w], got %s" % (tuple(x.shape),))
+    _check_device(x.device)
+    x = x.contiguous()
+    b, C, h, w = x.shape
+    D, M = embed.shape
+    if enc_w.shape[0] != D or enc_w.shape[1] != C or dec_w.shape[0] != C or dec_w.shape[1] != k * D:
+        raise RuntimeError("ammc_b200: inconsistent memory-module parameter shapes")
+    N = b * h * w
+    dev = x.device
+    out = torch.empty_like(x)
+    q1 = torch.empty((N, D), dtype=torch.float32, device=dev)
+    idx = torch.empty((N, k), dtype=torch.int64, device=dev)
+    z = torch.empty((N, D), dtype=torch.float32, device=dev)
+    sse = torch.empty((b,), dtype=torch.float32, device=dev)
+    diff = torch.empty((1,), dtype=torch.float32, device=dev)
+    counts = torch.empty((M,), dtype=torch.float32, device=dev) if want_stats else None
+    esum = torch.empty((D, M), dtype=torch.float32, device=dev) if want_stats else None
+    lib = _capi.load()
+    ws = _workspace(lib.ammc_mem_workspace_bytes(b, h, w, C, D, M, k), dev)
+    with torch.cuda.device(dev):
+        _capi.call("ammc_mem_fwd", _p(x), _p(enc_w.contiguous()), _p(enc_b.contiguous()), _p(embed.contiguous()),
+                   _p(dec_w.contiguous()), _p(dec_b.contiguous()), _p(out), _p(q1), _p(idx), _p(z), _p(sse), _p(diff),
+                   _p(counts), _p(esum), _p(ws), ws.numel(), b, h, w, C, D, M, k, int(bool(residual)), _stream())
+    _count(8 + (2 if want_stats else 0))
+    return dict(out=out, q1=q1, idx=idx, z=z, sse_frame=sse, diff=diff, counts=counts, embed_sum=esum, x=x)
+
+
+class MemoryModuleFn(torch.autograd.Function):
+    """enc 1x1 -> top-k addressing -> read -> dec 1x1 (+ residual); reference Code/models/unet.py:325-331,384-387.
+
+    forward(x, enc_w[D,C,1,1], enc_b, embed[D,M], dec_w[C,kD,1,1], dec_b, k, residual, want_stats)
+      -> out[b,C,h,w], diff[1], q1[b,h,w,D], idx[N,k], sse_frame[b], counts[M]|empty, embed_sum[D,M]|empty
+    backward: SURVEY.md Appendix A (no gradient to the bank; the read carries none to z).
+    """
+
+    @staticmethod
+    def forward(ctx, x, enc_w, enc_b, embed, dec_w, dec_b, k, residual, want_stats):
+        r = mem_forward_raw(x, enc_w.reshape(enc_w.shape[0], -1), enc_b, embed, dec_w.reshape(dec_w.shape[0], -1),
+                            dec_b, k, residual, want_stats)
+        b, C, h, w = r["x"].shape
+        D, M = embed.shape
+        # training: the caller updates the bank in place right after this forward (EMA, unet.py:298-309);
+        # backward needs the PRE-update items, exactly what reference autograd keeps alive -> snapshot (D*M floats)
+        bank = embed.clone() if want_stats else embed
+        ctx.save_for_backward(r["x"], enc_w, bank, r["idx"], r["z"])
+        ctx.dims = (b, h, w, C, D, M, k, bool(residual))
+        ctx.wshapes = (enc_w.shape, dec_w.shape)
+        empty = x.new_empty((0,))
+        outs = (r["out"], r["diff"], r["q1"].view(b, h, w, D), r["idx"], r["sse_frame"],
+                r["counts"] if want_stats else empty, r["embed_sum"] if want_stats else empty)
+        ctx.mark_non_differentiable(*outs[3:])
+        return outs
+
+    @staticmethod
+    def backward(ctx, g_out, g_diff, g_q1, *_unused):
+        x, enc_w, embed, idx, z = ctx.saved_tensors
+        b, h, w, C, D, M, k, residual = ctx.dims
+        dev = x.device
+        g_out = (torch.zeros_like(x) if g_out is None else g_out.contiguous())
+        g_diff = (torch.zeros((1,), dtype=torch.float32, device=dev) if g_diff is None else g_diff.contiguous())
+        g_q1 = None if g_q1 is None else g_q1.contiguous()
+        _require_cuda_f32(g_out, g_diff, g_q1, names=("grad_out", "grad_diff", "grad_q1"))
+        gx = torch.empty_like(x)
+        g_enc_w = torch.empty((D, C), dtype=torch.float32, device=dev)
+        g_enc_b = torch.empty((D,), dtype=torch.float32, device=dev)
+        g_dec_w = torch.empty((C, k * D), dtype=torch.float32, device=dev)
+        g_dec_b = torch.empty((C,), dtype=torch.float32, device=dev)
+        lib = _capi.load()
+        ws = _workspace(lib.ammc_mem_bwd_workspace_bytes(b, h, w, C, D, M, k), dev)
+        with torch.cuda.device(dev):
+            _capi.call("ammc_mem_bwd", _p(x), _p(enc_w.reshape(D, C).contiguous()), _p(embed.contiguous()), _p(idx),
+                       _p(z), _p(g_out), _p(g_diff), _p(g_q1), _p(gx), _p(g_enc_w), _p(g_enc_b), _p(g_dec_w),
+                       _p(g_dec_b), _p(ws), ws.numel(), b, h, w, C, D, M, k, int(residual), _stream())
+        _count(10)
+        es, ds = ctx.wshapes
+        return gx, g_enc_w.view(es), g_enc_b, None, g_dec_w.view(ds), g_dec_b, None, None, None
+
+
+class QuantizeFn(torch.autograd.Function):
+    """Quantize_topk.forward on a [b,h,w,D] input (reference unet.py:282-313).
+
+    -> read[b,h,w,kD], diff (0-d), q1[b,h,w,D], idx[N,k], sse_frame[b], counts, embed_sum
+    """
+
+    @staticmethod
+    def forward(ctx, z, embed, k, want_stats):
+        _require_cuda_f32(z, embed, names=("input", "embed"))
+        _check_device(z.device)
+        D, M = embed.shape
+        if z.shape[-1] != D:
+            raise RuntimeError("ammc_b200: Quantize_topk input last dim %d != dim %d" % (z.shape[-1], D))
+        zc = z.contiguous()
+        lead = zc.shape[:-1]
+        N = zc.numel() // D
+        frames = lead[0] if len(lead) >= 1 and lead[0] > 0 else 1
+        rows = N // frames
+        dev = z.device
+        read = torch.empty((N, k * D), dtype=torch.float32, device=dev)
+        q1 = torch.empty((N, D), dtype=torch.float32, device=dev)
+        idx = torch.empty((N, k), dtype=torch.int64, device=dev)
+        sse = torch.empty((frames,), dtype=torch.float32, device=dev)
+        diff = torch.empty((1,), dtype=torch.float32, device=dev)
+        counts = torch.empty((M,), dtype=torch.float32, device=dev) if want_stats else None
+        esum = torch.empty((D, M), dtype=torch.float32, device=dev) if want_stats else None
+        lib = _capi.load()
+        ws = _workspace(lib.ammc_quantize_workspace_bytes(N, D, M, k), dev)
+        with torch.cuda.device(dev):
+            _capi.call("ammc_quantize_fwd", _p(zc), _p(embed.contiguous()), _p(read), _p(q1), _p(idx), _p(sse),
+                       _p(diff), _p(counts), _p(esum), _p(ws), ws.numel(), N, rows, D, M, k, _stream())
+        _count(5 + (2 if want_stats else 0))
+        ctx.save_for_backward(zc, embed.clone() if want_stats else embed, idx)
+        ctx.dims = (N, D, M, k)
+        empty = z.new_empty((0,))
+        outs = (read.view(*lead, k * D), diff.view(()), q1.view(*lead, D), idx, sse,
+                counts if want_stats else empty, esum if want_stats else empty)
+        ctx.mark_non_differentiable(outs[0], *outs[3:])
+        return outs
+
+    @staticmethod
+    def backward(ctx, _g_read, g_diff, g_q1, *_unused):
+        zc, embed, idx = ctx.saved_tensors
+        N, D, M, k = ctx.dims
+        dev = zc.device
+        g_diff = (torch.zeros((1,), dtype=torch.float32, device=dev) if g_diff is None
+                  else g_diff.reshape(1).contiguous())
+        g_q1 = None if g_q1 is None else g_q1.contiguous()
+        gz = torch.empty_like(zc)
+        lib = _capi.load()
+        ws = _workspace(lib.ammc_quantize_bwd_workspace_bytes(N, D, M), dev)
+        with torch.cuda.device(dev):
+            _capi.call("ammc_quantize_bwd", _p(zc), _p(embed.contiguous()), _p(idx), _p(g_diff), _p(g_q1), _p(gz),
+                       _p(ws), ws.numel(), N, D, M, k, _stream())
+        _count(3)
+        return gz, None, None, None
+
+
+def embed_code(ids: torch.Tensor, embed: torch.Tensor) -> torch.Tensor:
+    """Quantize_topk.embed_code (unet.py:315-316)."""
+    _require_cuda_f32(embed, names=("embed",))
+    if not ids.is_cuda or ids.dtype != torch.int64:
+        raise RuntimeError("ammc_b200: embed_code ids must be a CUDA int64 tensor")
+    D, M = embed.shape
+    idc = ids.contiguous()
+    out = torch.empty((*ids.shape, D), dtype=torch.float32, device=embed.device)
+    with torch.cuda.device(embed.device):
+        _capi.call("ammc_embed_code", _p(idc), _p(embed.contiguous()), _p(out), idc.numel(), D, M, _stream())
+    _count(1)
+    return out
+
+
+def ema_update_(embed, cluster_size, embed_avg, counts, embed_sum, decay: float, eps: float):
+    """In-place EMA bank update on the registered buffers (unet.py:298-309)."""
+    _require_cuda_f32(embed, cluster_size, embed_avg, counts, embed_sum)
+    for t in (embed, cluster_size, embed_avg):
+        if not t.is_contiguous():
+            raise RuntimeError("ammc_b200: memory-bank buffers must be contiguous")
+    D, M = embed.shape
+    with torch.cuda.device(embed.device):
+        _capi.call("ammc_ema_update", _p(embed), _p(cluster_size), _p(embed_avg), _p(counts.contiguous()),
+                   _p(embed_sum.contiguous()), D, M, float(decay), float(eps), _stream())
+    _count(2)
+
+
+# --------------------------------------------------------------------------------------------------
+# AMFT
+# --------------------------------------------------------------------------------------------------
+def pack_conv_weights(w: torch.Tensor) -> torch.Tensor:
+    """[Cout, Cin, 3, 3] (or [Cout, Cin, 1, 1]) fp32 -> [2, Cout, taps*Cin] bf16 (hi, lo planes, k = tap*Cin + cin)."""
+    _require_cuda_f32(w, names=("conv weight",))
+    Cout, Cin = w.shape[0], w.shape[1]
+    taps = w[0, 0].numel()
+    if taps not in (1, 9):
+        raise RuntimeError("ammc_b200: only 3x3 and 1x1 conv weights are supported")
+    wp = torch.empty((2, Cout, taps * Cin), dtype=torch.bfloat16, device=w.device)
+    with torch.cuda.device(w.device):
+        _capi.call("ammc_pack_conv_weights" if taps == 9 else "ammc_pack_conv_weights_1x1", _p(w.contiguous()),
+                   _p(wp), Cout, Cin, _stream())
+    _count(1)
+    return wp
+
+
+def bn_fold(gamma, beta, mean, var, eps: float):
+    _require_cuda_f32(gamma, beta, mean, var)
+    C = gamma.numel()
+    scale = torch.empty((C,), dtype=torch.float32, device=gamma.device)
+    shift = torch.empty_like(scale)
+    with torch.cuda.device(gamma.device):
+        _capi.call("ammc_bn_fold", _p(gamma.contiguous()), _p(beta.contiguous()), _p(mean.contiguous()),
+                   _p(var.contiguous()), float(eps), _p(scale), _p(shift), C, _stream())
+    _count(1)
+    return scale, shift
+
+
+def pack_nhwc(x: torch.Tensor) -> torch.Tensor:
+    """[b, C, h, w] fp32 NCHW -> [2, b, h, w, C] bf16 (hi, lo planes)."""
+    _require_cuda_f32(x, names=("activation",))
+    b, C, h, w = x.shape
+    xp = torch.empty((2, b, h, w, C), dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        _capi.call("ammc_pack_nhwc", _p(x.contiguous()), _p(xp), b, C, h, w, _stream())
+    _count(1)
+    return xp
+
+
+def conv3x3_bn_relu(xp, wp, scale, shift, *, to_planes: bool, residual: Optional[torch.Tensor] = None,
+                    precision: int = 3, relu: bool = True):
+    """One implicit-GEMM conv.  xp [2,b,h,w,Cin] bf16, wp [2,Cout,9Cin] bf16.
+    to_planes=True -> [2,b,h,w,Cout] bf16 planes; else fp32 NCHW [b,Cout,h,w] (+ residual)."""
+    _, b, h, w, Cin = xp.shape
+    Cout = wp.shape[1]
+    taps = wp.shape[2] // Cin
+    dev = xp.device
+    _check_device(dev)
+    out_p = torch.empty((2, b, h, w, Cout), dtype=torch.bfloat16, device=dev) if to_planes else None
+    out_n = None if to_planes else torch.empty((b, Cout, h, w), dtype=torch.float32, device=dev)
+    if residual is not None:
+        _require_cuda_f32(residual, names=("residual",))
+        residual = residual.contiguous()
+    with torch.cuda.device(dev):
+        _capi.call("ammc_conv3x3_bn_relu" if taps == 9 else "ammc_conv1x1_bn_relu", _p(xp), _p(wp), _p(scale), _p(shift), _p(out_p), _p(out_n), _p(residual),
+                   b, Cin, Cout, h, w, int(precision), int(bool(relu)), _stream())
+    _count(1)
+    return out_p if to_planes else out_n
+
+
+# --------------------------------------------------------------------------------------------------
+# scoring
+# --------------------------------------------------------------------------------------------------
+def psnr_per_frame(gen: torch.Tensor, gt: torch.Tensor) -> torch.Tensor:
+    """[n, ...] x 2 -> psnr[n]; the batched form of the reference's per-frame psnr_error calls."""
+    _require_cuda_f32(gen, gt, names=("gen_frames", "gt_frames"))
+    if gen.shape != gt.shape:
+        raise RuntimeError("ammc_b200: psnr needs equal shapes, got %s vs %s (the reference's broadcasting op-stream "
+                           "artefact is not reproduced)" % (tuple(gen.shape), tuple(gt.shape)))
+    _check_device(gen.device)
+    n = gen.shape[0]
+    elems = gen[0].numel() if n > 0 else 1
+    g, t = gen.contiguous(), gt.contiguous()
+    out = torch.empty((n,), dtype=torch.float32, device=gen.device)
+    if n == 0:
+        return out
+    lib = _capi.load()
+    ws = _workspace(lib.ammc_psnr_workspace_bytes(n, elems), gen.device)
+    with torch.cuda.device(gen.device):
+        _capi.call("ammc_psnr_batch", _p(g), _p(t), _p(out), _p(ws), ws.numel(), n, elems, _stream())
+    _count(2)
+    return out
+
+
+def score_reduce_device(img: torch.Tensor, fea: torch.Tensor, offsets: torch.Tensor, lam) -> torch.Tensor:
+    """Concatenated per-video records (+ int64 offsets [V+1]) -> regularity scores [T - 4V] (eval_metric.py:405-427)."""
+    import numpy as np
+    _require_cuda_f32(img, fea, names=("img records", "fea records"))
+    V = offsets.numel() - 1
+    T = img.numel()
+    out = torch.empty((T - 4 * V,), dtype=torch.float32, device=img.device)
+    l1, l2 = float(lam[0]), float(lam[1])
+    # numpy casts the python doubles (1-lam) and lam to float32 before multiplying a float32 array
+    oml1, l1f = float(np.float32(1 - l1)), float(np.float32(l1))
+    oml2, l2f = float(np.float32(1 - l2)), float(np.float32(l2))
+    lib = _capi.load()
+    ws = _workspace(lib.ammc_score_workspace_bytes(T, V), img.device)
+    with torch.cuda.device(img.device):
+        _capi.call("ammc_score_reduce", _p(img.contiguous()), _p(fea.contiguous()), _p(offsets.contiguous()), V,
+                   oml1, l1f, oml2, l2f, _p(out), _p(ws), ws.numel(), T, _stream())
+    _count(2)
+    return out

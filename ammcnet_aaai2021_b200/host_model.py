@@ -1,0 +1,101 @@
+"""Host-side two-stream generator wiring (row a8 of SURVEY.md section 8): the caller of the hot path.
+
+The encoder / decoder convolutions are NOT part of the accelerated path -- they are stock torch.nn layers that run
+on cuDNN exactly as in the reference (north-star: "the conv encoder/decoder (left on cuDNN) ... unchanged").  This
+file only exists so the package can be exercised end to end without the reference tree (which is absent on the GPU
+box): it mirrors the layer names of reference Code/models/unet.py (`inconv/down/up` 23-59, `UNetMem_v7` 908-937,
+`twostream` 967-1007) so a reference checkpoint loads with strict=True, and places this package's memory modules
+and AMFT block in the starred region (unet.py:985-994).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .modules import bridge, double_conv, enc_quan_dec_res_topk
+
+
+class inconv(nn.Module):
+    def __init__(self, in_ch, out_ch):
+        super().__init__()
+        self.conv = double_conv(in_ch, out_ch)
+
+    def forward(self, x):
+        return self.conv.conv(x)
+
+
+class down(nn.Module):
+    def __init__(self, in_ch, out_ch):
+        super().__init__()
+        self.mpconv = nn.Sequential(nn.MaxPool2d(2), double_conv(in_ch, out_ch))
+
+    def forward(self, x):
+        return self.mpconv[1].conv(self.mpconv[0](x))
+
+
+class up(nn.Module):
+    def __init__(self, in_ch, out_ch):
+        super().__init__()
+        self.up = nn.ConvTranspose2d(in_ch, in_ch // 2, 2, stride=2)
+        self.conv = double_conv(in_ch, out_ch)
+
+    def forward(self, x1, x2):
+        x1 = self.up(x1)
+        dy, dx = x2.size(2) - x1.size(2), x2.size(3) - x1.size(3)
+        x1 = F.pad(x1, (dx // 2, dx - dx // 2, dy // 2, dy - dy // 2))
+        return self.conv.conv(torch.cat([x2, x1], dim=1))
+
+
+class UNetMem_v7(nn.Module):
+    def __init__(self, input_channels=3, output_channel=3, embed_dim=64, n_embed=512, k=1,
+                 layer_nums=4, features_root=64):
+        super().__init__()
+        self.inc = inconv(input_channels, 64)
+        self.down1 = down(64, 128)
+        self.down2 = down(128, 256)
+        self.down3 = down(256, 512)
+        self.up1 = up(512, 256)
+        self.up2 = up(256, 128)
+        self.up3 = up(128, 64)
+        self.outc = nn.Conv2d(64, output_channel, kernel_size=3, padding=1)
+        self.vq_down3 = enc_quan_dec_res_topk(512, embed_dim, n_embed, k=k)
+
+    def encode(self, x):
+        x1 = self.inc(x)
+        x2 = self.down1(x1)
+        x3 = self.down2(x2)
+        return x1, x2, x3, self.down3(x3)
+
+    def decode(self, x4, x3, x2, x1):
+        return self.outc(self.up3(self.up2(self.up1(x4, x3), x2), x1))
+
+    def forward(self, x):
+        x1, x2, x3, x4 = self.encode(x)
+        x4, diff, q1 = self.vq_down3(x4)
+        return torch.tanh(self.decode(x4, x3, x2, x1)), diff, q1
+
+
+class twostream(nn.Module):
+    def __init__(self, rgb_in_c, rgb_out_c, op_in_c, op_out_c, embed_dim=64, n_embed=512, k=1,
+                 layer_nums=4, features_root=64):
+        super().__init__()
+        self.rgb = UNetMem_v7(rgb_in_c, rgb_out_c, embed_dim, n_embed, k, layer_nums, features_root)
+        self.op = UNetMem_v7(op_in_c, op_out_c, embed_dim, n_embed, k, layer_nums, features_root)
+        self.bridge = bridge(in_c=512)
+
+    def forward(self, rgb_x, op_x):
+        r1, r2, r3, r4 = self.rgb.encode(rgb_x)
+        r4, rgb_diff, rgb_q = self.rgb.vq_down3(r4)
+        o1, o2, o3, o4 = self.op.encode(op_x)
+        o4, op_diff, op_q = self.op.vq_down3(o4)
+        r4, o4 = self.bridge(r4, o4)
+        rgb_y = self.rgb.decode(r4, r3, r2, r1)
+        op_y = self.op.decode(o4, o3, o2, o1)
+        return torch.tanh(rgb_y), torch.tanh(op_y), (rgb_diff, op_diff), (rgb_q, op_q)
+
+
+def get_twostream(in_channel=(12, 6), out_channel=(3, 2), embed_dim=64, n_embed=256, k=2):
+    """Shipped configuration (reference Code/models/unet.py:1241-1249, net_params/*.pkl)."""
+    return twostream(in_channel[0], out_channel[0], in_channel[1], out_channel[1], embed_dim=embed_dim,
+                     n_embed=n_embed, k=k)

@@ -1,0 +1,160 @@
+"""Drop-in replacements for the reference's hot-path modules, same names / ctor signatures / state_dict keys.
+
+    reference class (Code/models/unet.py)        here
+    Quantize_topk            267-316             Quantize_topk
+    enc_quan_dec_topk        318-331             enc_quan_dec_topk
+    enc_quan_dec_res_topk    379-387             enc_quan_dec_res_topk
+    double_conv                8-20              double_conv   (parameter container of `bridge`)
+    bridge (AMFT)            956-965             bridge
+    psnr_error   (Code/utils/utils.py:130-148)   psnr_error
+
+Forward/backward run in libammc_b200.so (sm_100a CUDA); parameters and buffers stay ordinary torch tensors
+so `load_state_dict(strict=True)` of a reference checkpoint works.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import functions as F_
+
+
+class _Hooks:
+    """Optional data-parallel hook: all-reduce(SUM) of the EMA statistics before the bank update."""
+    stats_allreduce = None   # callable(list[tensor]) -> None, installed by ammcnet_aaai2021_b200.dist
+
+
+class Quantize_topk(nn.Module):
+    """Memory bank with top-k nearest-item read (reference unet.py:267-316)."""
+
+    def __init__(self, dim, n_embed, decay=0.99, eps=1e-5, k=1):
+        super().__init__()
+        self.dim = dim
+        self.n_embed = n_embed
+        self.decay = decay
+        self.eps = eps
+        self.k = k
+        embed = torch.randn(dim, n_embed)
+        self.register_buffer('embed', embed)
+        self.register_buffer('cluster_size', torch.zeros(n_embed))
+        self.register_buffer('embed_avg', embed.clone())
+        # side outputs of the last forward, for the per-frame scoring loop and tests (not part of state_dict)
+        self.last_idx: Optional[torch.Tensor] = None
+        self.last_sse_frame: Optional[torch.Tensor] = None
+
+    def _ema(self, counts, embed_sum):
+        if _Hooks.stats_allreduce is not None:
+            _Hooks.stats_allreduce([counts, embed_sum])
+        F_.ema_update_(self.embed, self.cluster_size, self.embed_avg, counts, embed_sum, self.decay, self.eps)
+
+    def forward(self, input):
+        read, diff, q1, idx, sse, counts, esum = F_.QuantizeFn.apply(input, self.embed, self.k, self.training)
+        self.last_idx, self.last_sse_frame = idx, sse
+        if self.training:
+            self._ema(counts, esum)
+        return read, diff, q1
+
+    def embed_code(self, embed_id):
+        return F_.embed_code(embed_id, self.embed)
+
+
+class enc_quan_dec_topk(nn.Module):
+    """enc 1x1 -> Quantize_topk -> dec 1x1 (reference unet.py:318-331), one fused call."""
+    _residual = False
+
+    def __init__(self, in_c, embed_dim, n_embed, k=1):
+        super().__init__()
+        self.enc = nn.Conv2d(in_c, embed_dim, 1)
+        self.quantize = Quantize_topk(dim=embed_dim, n_embed=n_embed, k=k)
+        self.dec = nn.Conv2d(embed_dim * k, in_c, 1)
+
+    def _run(self, x, residual):
+        q = self.quantize
+        out, diff, q1, idx, sse, counts, esum = F_.MemoryModuleFn.apply(
+            x, self.enc.weight, self.enc.bias, q.embed, self.dec.weight, self.dec.bias, q.k, residual, self.training)
+        q.last_idx, q.last_sse_frame = idx, sse
+        if self.training:
+            q._ema(counts, esum)
+        return out, diff, q1
+
+    def forward(self, x):
+        return self._run(x, False)
+
+
+class enc_quan_dec_res_topk(nn.Module):
+    """enc_quan_dec_topk + residual add (reference unet.py:379-387); the add is fused into the dec epilogue."""
+
+    def __init__(self, in_c, embed_dim, n_embed, k=1):
+        super().__init__()
+        self.quan = enc_quan_dec_topk(in_c, embed_dim, n_embed, k=k)
+
+    def forward(self, x):
+        return self.quan._run(x, True)
+
+
+class double_conv(nn.Module):
+    """Parameter container with the reference layout (unet.py:8-20): conv.{0,3} = Conv2d 3x3 no bias,
+    conv.{1,4} = BatchNorm2d, conv.{2,5} = ReLU.  `bridge` reads the tensors and runs the fused kernels."""
+
+    def __init__(self, in_ch, out_ch):
+        super().__init__()
+        self.conv = nn.Sequential(nn.Conv2d(in_ch, out_ch, 3, padding=1, bias=False),
+                                  nn.BatchNorm2d(out_ch),
+                                  nn.ReLU(inplace=True),
+                                  nn.Conv2d(out_ch, out_ch, 3, padding=1, bias=False),
+                                  nn.BatchNorm2d(out_ch),
+                                  nn.ReLU(inplace=True))
+        self._packed = {}
+
+    def packed(self, ci, bi):
+        """(weight planes, scale, shift) of conv `ci` / BN `bi`, re-packed only when a tensor changed."""
+        conv, bn = self.conv[ci], self.conv[bi]
+        src = (conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var)
+        key = tuple((t.data_ptr(), t._version) for t in src)
+        hit = self._packed.get(ci)
+        if hit is None or hit[0] != key:
+            wp = F_.pack_conv_weights(conv.weight.detach())
+            scale, shift = F_.bn_fold(bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, bn.eps)
+            hit = (key, wp, scale, shift)
+            self._packed[ci] = hit
+        return hit[1], hit[2], hit[3]
+
+    def forward_fused(self, xp, residual, precision):
+        w1, s1, b1 = self.packed(0, 1)
+        w2, s2, b2 = self.packed(3, 4)
+        mid = F_.conv3x3_bn_relu(xp, w1, s1, b1, to_planes=True, precision=precision)
+        return F_.conv3x3_bn_relu(mid, w2, s2, b2, to_planes=False, residual=residual, precision=precision)
+
+
+class bridge(nn.Module):
+    """AMFT: x' = zx + O2F(zy), y' = zy + F20(zx) (reference unet.py:956-965).
+
+    `precision` = 3 (default): split-bf16 three-pass tensor-core convolution, fp32-parity numerics;
+    `precision` = 1: single bf16 pass (the "bf16 variant", stated separately in every report).
+    """
+
+    def __init__(self, in_c=64, precision: int = 3):
+        super().__init__()
+        self.O2F = double_conv(in_c, in_c)
+        self.F20 = double_conv(in_c, in_c)
+        self.precision = precision
+
+    def forward(self, zx, zy):
+        if self.training or torch.is_grad_enabled() and (zx.requires_grad or zy.requires_grad):
+            raise RuntimeError(
+                "ammc_b200.bridge: the training path (batch-statistic BatchNorm + backward) of the AMFT block is not "
+                "implemented yet in the sm_100a library; run the block under eval() and torch.no_grad(). "
+                "There is deliberately no cuDNN fallback.")
+        px = F_.pack_nhwc(zx)
+        py = F_.pack_nhwc(zy)
+        x = self.O2F.forward_fused(py, zx, self.precision)
+        y = self.F20.forward_fused(px, zy, self.precision)
+        return x, y
+
+
+def psnr_error(gen_frames, gt_frames):
+    """Mean per-frame PSNR of a batch (reference Code/utils/utils.py:130-148); returns a 0-d tensor."""
+    per = F_.psnr_per_frame(gen_frames, gt_frames)
+    return per.mean() if per.numel() > 1 else per.reshape(())

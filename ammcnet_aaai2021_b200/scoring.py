@@ -1,0 +1,164 @@
+"""Per-frame scoring loop and regularity-score reduction (reference rows a12 / a13 of SURVEY.md section 8).
+
+* `VideoScorer`            batched, sync-free replacement of the per-frame loop in
+                           Code/run_helper/test_helper.py:408-475.  Frames are pushed through the generator in
+                           large batches; PSNR comes from one batched kernel and the reference's batch-of-16
+                           commit scalar is rebuilt from the per-frame SSE partials the memory kernel emits, so
+                           the records are independent of how frames are batched or sharded over GPUs.
+* `assemble_video_records` the record layout of test_helper.py:445-475 (back-filled head, op-stream tail copy).
+* `score_reduce`           eval_metric.py:405-427 on the GPU (bit-exact with numpy float32).
+* `evaluate`               eval_metric.evaluate / img_pred_fea_comm_single_auc (eval_metric.py:382-454); the ROC-AUC
+                           itself stays on the host (sklearn.metrics, as in the reference).
+"""
+from __future__ import annotations
+
+import os
+import pickle
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import functions as F_
+
+DECIDABLE_IDX = 4            # Code/main/eval_metric.py:15-17
+REFERENCE_GROUP = 16         # DataLoader batch_size in test_helper.py:414-417
+LAM_MAP = {"avenue": (0.04, 0.65), "ped2": (0.01, 0.55), "shanghaitech": (0.13, 0.60)}  # test_helper.py:565-569
+
+
+def assemble_video_records(psnr_clip: np.ndarray, commit_group: np.ndarray, clip_len: int = 5,
+                           group: int = REFERENCE_GROUP, tail_copy: bool = False):
+    """psnr_clip[c] / commit_group[c // group] -> (img_pred_arr, fea_comm_arr) of one sub-video."""
+    psnr_clip = np.asarray(psnr_clip, dtype=np.float32)
+    commit_group = np.asarray(commit_group, dtype=np.float32)
+    n_clips = psnr_clip.shape[0]
+    head = clip_len - 1
+    num_frame = n_clips + head + (1 if tail_copy else 0)
+    img = np.empty((num_frame,), np.float32)
+    fea = np.empty((num_frame,), np.float32)
+    img[head:head + n_clips] = psnr_clip
+    fea[head:head + n_clips] = commit_group[np.arange(n_clips) // group]
+    img[:head] = img[head]
+    fea[:head] = fea[head]
+    if tail_copy:
+        img[-1] = img[-2]
+        fea[-1] = fea[-2]
+    return img, fea
+
+
+def group_commit_from_frames(sse_frame: torch.Tensor, elems_per_frame: int, group: int = REFERENCE_GROUP) -> torch.Tensor:
+    """Per-frame SSE partials of ONE video (in clip order) -> the commit scalar the reference records for each
+    group of `group` consecutive clips: mean over the group's elements (unet.py:310 on a batch of <=16 clips)."""
+    n = sse_frame.numel()
+    n_groups = (n + group - 1) // group
+    pad = n_groups * group - n
+    s = torch.nn.functional.pad(sse_frame, (0, pad)).view(n_groups, group).sum(1)
+    cnt = torch.full((n_groups,), float(group), device=sse_frame.device)
+    if pad:
+        cnt[-1] = float(group - pad)
+    return s / (cnt * float(elems_per_frame))
+
+
+class VideoScorer:
+    """Runs a two-stream generator over sub-videos and produces the reference's record pickle.
+
+    generator(rgb_input[b,12,H,W], op_input[b,6,H,W]) -> (rgb_pred, op_pred, (rgb_diff, op_diff), _) as the reference
+    `twostream.forward` (unet.py:981-1007).  The generator's memory modules must be this package's (they expose
+    `quantize.last_sse_frame`).
+    """
+
+    def __init__(self, generator, batch: int = 64, rgb_clip_len: int = 5, op_clip_len: int = 4):
+        self.g = generator
+        self.batch = batch
+        self.rgb_clip_len = rgb_clip_len
+        self.op_clip_len = op_clip_len
+
+    def _memories(self):
+        return self.g.rgb.vq_down3.quan.quantize, self.g.op.vq_down3.quan.quantize
+
+    @torch.no_grad()
+    def score_video(self, rgb_frames: torch.Tensor, op_frames: torch.Tensor):
+        """rgb_frames [T,3,H,W], op_frames [T-1,2,H,W] (device tensors) -> dict of the four record arrays."""
+        T = rgb_frames.shape[0]
+        n_clips = T - self.rgb_clip_len + 1
+        L, Lo = self.rgb_clip_len, self.op_clip_len
+        psnr_parts, sse_rgb, sse_op = [], [], []
+        q_rgb, q_op = self._memories()
+        for c0 in range(0, n_clips, self.batch):
+            c1 = min(n_clips, c0 + self.batch)
+            idx = torch.arange(c0, c1, device=rgb_frames.device)
+            rgb_in = torch.stack([rgb_frames[idx + t] for t in range(L - 1)], 1).flatten(1, 2)
+            op_in = torch.stack([op_frames[idx + t] for t in range(Lo - 1)], 1).flatten(1, 2)
+            target = rgb_frames[idx + (L - 1)]
+            pred, _op_pred, _diffs, _ = self.g(rgb_in, op_in)
+            psnr_parts.append(F_.psnr_per_frame(pred, target))
+            sse_rgb.append(q_rgb.last_sse_frame)
+            sse_op.append(q_op.last_sse_frame)
+        psnr = torch.cat(psnr_parts)
+        elems = q_rgb.last_idx.shape[0] // max(1, sse_rgb[-1].numel()) * q_rgb.dim
+        commit_rgb = group_commit_from_frames(torch.cat(sse_rgb), elems)
+        commit_op = group_commit_from_frames(torch.cat(sse_op), elems)
+        # ONE device->host transfer per video (the reference does 4 per frame)
+        packed = torch.cat([psnr, commit_rgb, commit_op]).cpu().numpy()
+        n_g = commit_rgb.numel()
+        psnr_h, crgb_h, cop_h = packed[:n_clips], packed[n_clips:n_clips + n_g], packed[n_clips + n_g:]
+        rgb_img, rgb_fea = assemble_video_records(psnr_h, crgb_h, L)
+        # op records: the reference's op PSNR is a 5-D broadcasting artefact that nothing downstream reads
+        # (test_helper.py:431,455-464); the commit record is reproduced, the PSNR slot holds NaN.
+        op_img, op_fea = assemble_video_records(np.full((n_clips,), np.nan, np.float32), cop_h, Lo, tail_copy=True)
+        return dict(rgb_img_pred=rgb_img, rgb_fea_comm=rgb_fea, op_img_pred=op_img, op_fea_comm=op_fea)
+
+    def score_dataset(self, videos: Sequence[Tuple[torch.Tensor, torch.Tensor]], dataset_name: str,
+                      pickle_path: Optional[str] = None) -> Dict:
+        """videos: sequence of (rgb_frames, op_frames) in sorted sub-video order -> the reference's result dict
+        (test_helper.py:479-488), optionally pickled."""
+        res = {"dataset": dataset_name, "rgb_img_pred_records": [], "rgb_fea_comm_records": [],
+               "op_img_pred_records": [], "op_fea_comm_records": []}
+        for rgb, op in videos:
+            r = self.score_video(rgb, op)
+            res["rgb_img_pred_records"].append(r["rgb_img_pred"])
+            res["rgb_fea_comm_records"].append(r["rgb_fea_comm"])
+            res["op_img_pred_records"].append(r["op_img_pred"])
+            res["op_fea_comm_records"].append(r["op_fea_comm"])
+        if pickle_path:
+            with open(pickle_path, "wb") as fp:
+                pickle.dump(res, fp, pickle.HIGHEST_PROTOCOL)
+        return res
+
+
+def score_reduce(img_records: Sequence[np.ndarray], fea_records: Sequence[np.ndarray], lam: Tuple[float, float],
+                 device: Optional[torch.device] = None) -> np.ndarray:
+    """Regularity scores of a whole dataset (eval_metric.py:405-427), computed on the GPU, returned as float32 numpy.
+    Unlike the reference's norm_score this does not normalise the caller's record arrays in place."""
+    device = device or torch.device("cuda", torch.cuda.current_device())
+    lens = np.array([len(r) for r in img_records], dtype=np.int64)
+    if len(fea_records) != len(img_records) or any(len(f) != n for f, n in zip(fea_records, lens)):
+        raise RuntimeError("ammc_b200: img and fea records must have the same per-video lengths")
+    offsets = torch.from_numpy(np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)).to(device)
+    img = torch.from_numpy(np.concatenate([np.asarray(r, np.float32) for r in img_records])).to(device)
+    fea = torch.from_numpy(np.concatenate([np.asarray(r, np.float32) for r in fea_records])).to(device)
+    return F_.score_reduce_device(img, fea, offsets, lam).cpu().numpy()
+
+
+def evaluate(eval_type: str, save_file: str, lam=None, gt_labels: Optional[Sequence[np.ndarray]] = None) -> Dict:
+    """eval_metric.evaluate('img_pred_fea_comm_rgb_auc', pickle_or_dir, lam) (eval_metric.py:382-454).
+
+    gt_labels: per-video int8 label arrays (what the reference's GroundTruthLoader returns from the dataset's
+    .mat/.npy files, eval_metric.py:41-210 -- those files live in the datasets, so the loader is the caller's)."""
+    if eval_type != "img_pred_fea_comm_rgb_auc":
+        raise AssertionError("there is no type of evaluation %s" % eval_type)
+    if gt_labels is None:
+        raise RuntimeError("ammc_b200.evaluate needs gt_labels (the dataset ground truth is not shipped)")
+    from sklearn import metrics
+    files = [save_file] if not os.path.isdir(save_file) else [os.path.join(save_file, f) for f in os.listdir(save_file)]
+    best = None
+    for f in files:
+        with open(f, "rb") as fp:
+            res = pickle.load(fp)
+        scores = score_reduce(res["rgb_img_pred_records"], res["rgb_fea_comm_records"], lam)
+        labels = np.concatenate([np.asarray(g)[DECIDABLE_IDX:] for g in gt_labels])
+        fpr, tpr, _ = metrics.roc_curve(labels, scores, pos_label=0)
+        auc = metrics.auc(fpr, tpr)
+        if best is None or auc > best[1]:
+            best = (f, auc)
+    return {"optimal_loss": "{}".format(best[0]), "auc": round(best[1], 3)}

@@ -1,0 +1,159 @@
+/*
+ * ammc_b200.h -- C ABI of the B200-native AMMC-Net memory + AMFT + scoring hot path.
+ *
+ * The reference (NjuHaoZhang/AMMCNet_AAAI2021) is pure Python/PyTorch and has no FFI of its own
+ * (SURVEY.md section 2.2): its "plugin API" for this path is a set of torch.nn.Module classes and two
+ * functions.  Each entry point below replaces the ATen op sequence of one of them; the Python mirror in
+ * ammcnet_aaai2021_b200/ binds these symbols with ctypes and keeps the reference's class names,
+ * signatures and state_dict keys.  INTEGRATION.md shows the reference-side binding.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host; tensors are dense, row-major in the
+ *     order written in the comment; fp32 unless stated; indices are int64 like torch's.
+ *   - `stream` is a cudaStream_t passed as void*; all work is stream-ordered, nothing synchronises,
+ *     nothing allocates: the caller owns inputs, outputs and the workspace (size from the *_workspace_bytes
+ *     query) and may free them once the stream has passed the call.
+ *   - return value: 0 on success, negative AMMC_E* on failure; ammc_last_error() gives the message of the
+ *     calling thread's last failure.  There is no CPU fallback and no alternate backend.
+ *   - notation: N = b*h*w pixels ("queries"), C feature channels, D embed_dim, M n_embed (memory items), k.
+ */
+#ifndef AMMC_B200_H_
+#define AMMC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AMMC_OK 0
+#define AMMC_EINVAL (-1)      /* bad pointer / size / unsupported shape */
+#define AMMC_ECUDA (-2)       /* CUDA runtime or driver error (message has the cudaError string) */
+#define AMMC_EWORKSPACE (-3)  /* workspace too small */
+#define AMMC_EUNSUPPORTED (-4)/* shape outside what the sm_100a kernels implement */
+
+#define AMMC_MAX_K 8          /* top-k width supported by the addressing kernels */
+
+int ammc_version(void);
+const char* ammc_last_error(void);
+/* 1 when the current device is sm_100 (B200); the library refuses to run anywhere else. */
+int ammc_device_supported(void);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Memory module.  Replaces enc_quan_dec_topk.forward / enc_quan_dec_res_topk.forward
+ * (reference Code/models/unet.py:325-331, 384-387) including Quantize_topk.forward (unet.py:282-313).
+ *
+ *   x        [b, C, h, w]   NCHW input features
+ *   enc_w    [D, C], enc_b [D]          1x1 conv `enc`  (unet.py:321)
+ *   embed    [D, M]                     memory bank buffer (unet.py:277-278), column j = item j
+ *   dec_w    [C, k*D], dec_b [C]        1x1 conv `dec`  (unet.py:323)
+ *   out      [b, C, h, w]   dec(read) + dec_b (+ x when residual != 0)
+ *   q1       [N, D]         value of the straight-through top-1 read  z + (e_top1 - z)   (unet.py:311)
+ *   idx      [N, k] int64   top-k item indices, nearest first                                (unet.py:293)
+ *   z        [N, D]         enc output in NHWC order (saved for backward / EMA)              (unet.py:326)
+ *   sse_frame[b]            per-frame sum of (e_top1 - z)^2   (the per-frame partial of unet.py:310)
+ *   diff     [1]            mean over all N*D elements = reference `diff`                    (unet.py:310,329)
+ *   counts   [M], embed_sum [D, M]  (both NULL in eval) assignment statistics of unet.py:298-302
+ * ------------------------------------------------------------------------------------------------- */
+size_t ammc_mem_workspace_bytes(int b, int h, int w, int C, int D, int M, int k);
+
+int ammc_mem_fwd(const float* x, const float* enc_w, const float* enc_b, const float* embed,
+                 const float* dec_w, const float* dec_b,
+                 float* out, float* q1, int64_t* idx, float* z, float* sse_frame, float* diff,
+                 float* counts, float* embed_sum,
+                 void* workspace, size_t workspace_bytes,
+                 int b, int h, int w, int C, int D, int M, int k, int residual, void* stream);
+
+/* Quantize_topk.forward on its own (unet.py:282-313): z [N, D] contiguous (N = frames*rows_per_frame).
+ *   read [N, k*D]  concatenated top-k items, nearest first (unet.py:295-297); other outputs as above. */
+size_t ammc_quantize_workspace_bytes(int64_t N, int D, int M, int k);
+
+int ammc_quantize_fwd(const float* z, const float* embed,
+                      float* read, float* q1, int64_t* idx, float* sse_frame, float* diff,
+                      float* counts, float* embed_sum,
+                      void* workspace, size_t workspace_bytes,
+                      int64_t N, int64_t rows_per_frame, int D, int M, int k, void* stream);
+
+/* Backward of Quantize_topk.forward w.r.t. its input (autograd of unet.py:310-311):
+ *   gz[n,:] = g_diff * 2 (z_n - e_top1(n)) / (N*D) + g_q1[n,:]        (g_q1 may be NULL) */
+size_t ammc_quantize_bwd_workspace_bytes(int64_t N, int D, int M);
+
+int ammc_quantize_bwd(const float* z, const float* embed, const int64_t* idx, const float* g_diff,
+                      const float* g_q1, float* gz, void* workspace, size_t workspace_bytes,
+                      int64_t N, int D, int M, int k, void* stream);
+
+/* Quantize_topk.embed_code (unet.py:315-316): out[i, :] = embed[:, ids[i]]. */
+int ammc_embed_code(const int64_t* ids, const float* embed, float* out, int64_t n_ids, int D, int M,
+                    void* stream);
+
+/* Training-mode bank update (unet.py:298-309), in place on the registered buffers:
+ *   cluster_size <- decay*cluster_size + (1-decay)*counts ;  embed_avg <- decay*embed_avg + (1-decay)*embed_sum
+ *   embed <- embed_avg / ((cluster_size+eps)/(sum+M*eps)*sum)
+ * In data-parallel training all-reduce counts / embed_sum over ranks BEFORE this call. */
+int ammc_ema_update(float* embed, float* cluster_size, float* embed_avg,
+                    const float* counts, const float* embed_sum,
+                    int D, int M, float decay, float eps, void* stream);
+
+/* Backward of the memory module (autograd of unet.py:282-331, 384-387).
+ *   g_out [b,C,h,w], g_diff [1] (device), g_q1 [N,D] or NULL
+ *   gx [b,C,h,w], g_enc_w [D,C], g_enc_b [D], g_dec_w [C,k*D], g_dec_b [C]   (all overwritten)
+ * The read is gathered from a buffer, so no gradient reaches z through it and none reaches embed. */
+size_t ammc_mem_bwd_workspace_bytes(int b, int h, int w, int C, int D, int M, int k);
+
+int ammc_mem_bwd(const float* x, const float* enc_w, const float* embed, const int64_t* idx,
+                 const float* z, const float* g_out, const float* g_diff, const float* g_q1,
+                 float* gx, float* g_enc_w, float* g_enc_b, float* g_dec_w, float* g_dec_b,
+                 void* workspace, size_t workspace_bytes,
+                 int b, int h, int w, int C, int D, int M, int k, int residual, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * AMFT.  Replaces bridge.forward (unet.py:962-965) = two double_conv stacks (unet.py:8-20) + residuals.
+ * The block is run as four 3x3 implicit-GEMM convolutions on tcgen05 tensor cores over NHWC bf16
+ * operand planes.  `precision`: 1 = single bf16 pass; 3 = three-pass split-bf16 (hi*hi + hi*lo + lo*hi,
+ * fp32 accumulate, ~2^-17 relative error: the fp32-parity mode).
+ *
+ * ammc_pack_conv_weights:   w [Cout, Cin, 3, 3] fp32  ->  wp [2 planes][Cout][9*Cin] bf16 (k = tap*Cin+cin)
+ * ammc_pack_nhwc:           x [b, C, h, w] fp32 NCHW  ->  xp [2 planes][b, h, w, C] bf16   (hi, lo)
+ * ammc_conv3x3_bn_relu:     y = relu(conv3x3(x) * scale[c] + shift[c])  (+ res)   BN folded to scale/shift:
+ *        scale = gamma / sqrt(var + eps), shift = beta - mean * scale       (unet.py:11-16, eval mode)
+ *     out_planes != NULL : y written as NHWC bf16 (hi, lo) planes (input of the next conv)
+ *     out_nchw   != NULL : y (+ res_nchw if not NULL) written as fp32 NCHW
+ * ------------------------------------------------------------------------------------------------- */
+int ammc_pack_conv_weights(const float* w, void* wp, int Cout, int Cin, void* stream);
+int ammc_pack_nhwc(const float* x, void* xp, int b, int C, int h, int w, void* stream);
+int ammc_conv3x3_bn_relu(const void* xp, const void* wp, const float* scale, const float* shift,
+                         void* out_planes, float* out_nchw, const float* res_nchw,
+                         int b, int Cin, int Cout, int h, int w, int precision, int relu, void* stream);
+/* 1x1 convolution on the same tensor-core engine (a plain [N,Cin] x [Cout,Cin]^T GEMM, no halo):
+ *   wp [2 planes][Cout][Cin] bf16 (pack with ammc_pack_conv_weights_1x1). */
+int ammc_pack_conv_weights_1x1(const float* w, void* wp, int Cout, int Cin, void* stream);
+int ammc_conv1x1_bn_relu(const void* xp, const void* wp, const float* scale, const float* shift,
+                         void* out_planes, float* out_nchw, const float* res_nchw,
+                         int b, int Cin, int Cout, int h, int w, int precision, int relu, void* stream);
+/* BatchNorm (eval) folding: scale/shift [C] from gamma, beta, running_mean, running_var. */
+int ammc_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, float eps,
+                 float* scale, float* shift, int C, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Scoring.  ammc_psnr_batch replaces the per-frame psnr_error calls of the scoring loop
+ * (reference Code/utils/utils.py:130-148 called at Code/run_helper/test_helper.py:445-452):
+ *   psnr[i] = 10*log10( 1 / ( (1/elems) * sum_j ((gt+1)/2 - (gen+1)/2)^2 ) ),  gen/gt [n, elems]
+ * ammc_score_reduce replaces norm_score + mixing + smoothing (Code/main/eval_metric.py:405-427):
+ *   img/fea [T_total] concatenated per-video records, offsets [V+1] int64 (video v = [offsets[v], offsets[v+1]))
+ *   scores [T_total - 4*V]; one_minus_lam* are the fp32 roundings of the host doubles (1-lam), as numpy uses.
+ *   Bit-exact with the numpy float32 reference (no FMA contraction, IEEE division).
+ * ------------------------------------------------------------------------------------------------- */
+size_t ammc_psnr_workspace_bytes(int n, int64_t elems);
+int ammc_psnr_batch(const float* gen, const float* gt, float* psnr, void* workspace, size_t workspace_bytes,
+                    int n, int64_t elems, void* stream);
+
+size_t ammc_score_workspace_bytes(int64_t t_total, int n_videos);
+int ammc_score_reduce(const float* img, const float* fea, const int64_t* offsets, int n_videos,
+                      float one_minus_lam1, float lam1, float one_minus_lam2, float lam2,
+                      float* scores, void* workspace, size_t workspace_bytes, int64_t t_total, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AMMC_B200_H_ */

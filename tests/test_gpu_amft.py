@@ -1,0 +1,116 @@
+"""GPU parity: AMFT block (tcgen05 implicit-GEMM convolutions) against the golden fixtures and the oracle."""
+import numpy as np
+import pytest
+import torch
+
+import ammc_oracle as O
+import ammcnet_aaai2021_b200 as A
+from ammcnet_aaai2021_b200 import synth, functions as F_
+from conftest import load_golden, assert_close, rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _bridge(c, p, precision):
+    m = A.bridge(in_c=c["C"], precision=precision)
+    m.load_state_dict({k: v.clone() for k, v in p.items()}, strict=True)
+    return m.to(DEV).eval()
+
+
+def _inputs(c):
+    p = synth.amft_params(c["seed"], c["C"])
+    zx = synth.features(c["seed"] + 1000, c["b"], c["C"], c["h"], c["w"])
+    zy = synth.features(c["seed"] + 2000, c["b"], c["C"], c["h"], c["w"])
+    return p, zx, zy
+
+
+def test_pack_nhwc_roundtrip():
+    x = synth.features(5, 3, 96, 6, 10).to(DEV)
+    xp = F_.pack_nhwc(x)
+    assert xp.shape == (2, 3, 6, 10, 96) and xp.dtype == torch.bfloat16
+    rec = (xp[0].float() + xp[1].float()).permute(0, 3, 1, 2)
+    assert (rec - x).abs().max() <= 2.0 ** -16 * x.abs().max()
+    assert torch.equal(xp[0], x.permute(0, 2, 3, 1).to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("cin,cout,h,w,b", [(64, 64, 8, 16, 2), (128, 256, 4, 32, 1), (64, 128, 8, 8, 3), (512, 512, 32, 32, 2)])
+def test_conv1x1_engine(cin, cout, h, w, b):
+    """The tensor-core engine without the conv halo: a plain GEMM, hi-plane only, must match fp64 on bf16 inputs."""
+    g = torch.Generator().manual_seed(cin + cout + h)
+    x = torch.randn((b, cin, h, w), generator=g)
+    wt = torch.randn((cout, cin, 1, 1), generator=g) / cin ** 0.5
+    xp = F_.pack_nhwc(x.to(DEV))
+    wp = F_.pack_conv_weights(wt.to(DEV))
+    one, zero = torch.ones(cout, device=DEV), torch.zeros(cout, device=DEV)
+    y = F_.conv3x3_bn_relu(xp, wp, one, zero, to_planes=False, precision=1, relu=False)
+    xb, wb = x.to(torch.bfloat16).double(), wt.to(torch.bfloat16).double()
+    ref = torch.nn.functional.conv2d(xb, wb)
+    assert rel_err(y.cpu(), ref) < 1e-5
+    y3 = F_.conv3x3_bn_relu(xp, wp, one, zero, to_planes=False, precision=3, relu=False)
+    assert rel_err(y3.cpu(), torch.nn.functional.conv2d(x.double(), wt.double())) < 5e-5
+
+
+@pytest.mark.parametrize("cin,cout,h,w,b", [(64, 64, 8, 8, 2), (64, 64, 8, 8, 3), (128, 64, 4, 32, 2), (64, 256, 16, 16, 1), (512, 512, 32, 32, 1)])
+def test_conv3x3_engine(cin, cout, h, w, b):
+    g = torch.Generator().manual_seed(cin * 3 + cout + h)
+    x = torch.randn((b, cin, h, w), generator=g)
+    wt = torch.randn((cout, cin, 3, 3), generator=g) / (9 * cin) ** 0.5
+    scale = (0.5 + torch.rand(cout, generator=g)).to(DEV)
+    shift = torch.randn(cout, generator=g).to(DEV)
+    res = torch.randn((b, cout, h, w), generator=g)
+    xp = F_.pack_nhwc(x.to(DEV))
+    wp = F_.pack_conv_weights(wt.to(DEV))
+    ref = torch.relu(torch.nn.functional.conv2d(x.double(), wt.double(), padding=1) * scale.cpu().double().view(1, -1, 1, 1)
+                     + shift.cpu().double().view(1, -1, 1, 1))
+    y = F_.conv3x3_bn_relu(xp, wp, scale, shift, to_planes=False, residual=res.to(DEV), precision=3)
+    assert_close(y.cpu(), ref + res.double(), 1e-3, "conv3x3.nchw")
+    assert rel_err(y.cpu(), ref + res.double()) < 5e-5
+    yp = F_.conv3x3_bn_relu(xp, wp, scale, shift, to_planes=True, precision=3)
+    rec = (yp[0].float() + yp[1].float()).permute(0, 3, 1, 2)
+    assert rel_err(rec.cpu(), ref) < 5e-5
+    y1 = F_.conv3x3_bn_relu(xp, wp, scale, shift, to_planes=False, precision=1)
+    assert rel_err(y1.cpu(), ref) < 2e-2          # bf16 variant, stated separately
+
+
+@pytest.mark.parametrize("name", ["amft_c64", "amft_c512"])
+def test_bridge_vs_golden(name):
+    c, g = load_golden(name)
+    p, zx, zy = _inputs(c)
+    m = _bridge(c, p, precision=3)
+    with torch.no_grad():
+        x, y = m(zx.to(DEV), zy.to(DEV))
+    assert_close(x.cpu(), g["x"], 1e-3, name + ".x")
+    assert_close(y.cpu(), g["y"], 1e-3, name + ".y")
+    print(name, "fp32-parity mode rel err", rel_err(x.cpu(), g["x"]), rel_err(y.cpu(), g["y"]))
+    m1 = _bridge(c, p, precision=1)
+    with torch.no_grad():
+        x1, y1 = m1(zx.to(DEV), zy.to(DEV))
+    e = max(rel_err(x1.cpu(), g["x"]), rel_err(y1.cpu(), g["y"]))
+    print(name, "bf16 variant rel err", e)
+    assert e < 3e-2
+
+
+def test_bridge_full_size_linearity_and_oracle_sample():
+    """b=8 at the shipped 512x32x32 shape: oracle on 1 frame (frames are independent in eval mode) + batch-split invariance."""
+    C = 512
+    p = synth.amft_params(91, C)
+    zx, zy = synth.features(92, 8, C, 32, 32), synth.features(93, 8, C, 32, 32)
+    m = A.bridge(in_c=C)
+    m.load_state_dict(p)
+    m = m.to(DEV).eval()
+    with torch.no_grad():
+        x, y = m(zx.to(DEV), zy.to(DEV))
+        xa, ya = m(zx[3:5].to(DEV), zy[3:5].to(DEV))
+    assert torch.equal(xa, x[3:5]) and torch.equal(ya, y[3:5])
+    ox, oy, _ = O.amft_forward(zx[3:4], zy[3:4], p)
+    assert_close(x[3:4].cpu(), ox, 1e-3, "bridge.full.x")
+    assert_close(y[3:4].cpu(), oy, 1e-3, "bridge.full.y")
+
+
+def test_bridge_rejects_unsupported_and_training():
+    m = A.bridge(in_c=64).to(DEV)
+    with pytest.raises(RuntimeError, match="not implemented"):
+        m.train()(torch.zeros(1, 64, 8, 8, device=DEV), torch.zeros(1, 64, 8, 8, device=DEV))
+    with torch.no_grad(), pytest.raises(RuntimeError, match="divides 128|128-pixel"):
+        m.eval()(torch.zeros(1, 64, 5, 7, device=DEV), torch.zeros(1, 64, 5, 7, device=DEV))

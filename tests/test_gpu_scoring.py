@@ -1,0 +1,74 @@
+"""GPU parity: batched PSNR, bit-exact score reduction, record assembly through the scorer."""
+import numpy as np
+import pytest
+import torch
+
+import ammc_oracle as O
+import ammcnet_aaai2021_b200 as A
+from ammcnet_aaai2021_b200 import synth, scoring
+from conftest import load_golden, assert_close
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def test_psnr_vs_golden():
+    c, g = load_golden("psnr")
+    gen, gt = synth.frames(c["seed"], c["b"], c["c"], c["h"], c["w"])
+    per = A.psnr_per_frame(gen.to(DEV), gt.to(DEV))
+    assert_close(per.cpu(), g["per_frame"], 1e-5, "psnr.per_frame")
+    assert_close(A.psnr_error(gen.to(DEV), gt.to(DEV)).cpu(), g["batch_mean"], 1e-5, "psnr.batch")
+    one = A.psnr_error(gen[:1].to(DEV), gt[:1].to(DEV))
+    assert one.dim() == 0
+    assert_close(one.cpu().reshape(1), g["per_frame"][:1], 1e-5, "psnr.single")
+
+
+@pytest.mark.parametrize("shape", [(64, 3, 256, 256), (3, 3, 37, 41), (1, 1, 1, 1), (5, 2, 256, 256)])
+def test_psnr_shapes_vs_oracle(shape):
+    gen, gt = synth.frames(41, *shape)
+    per = A.psnr_per_frame(gen.to(DEV), gt.to(DEV))
+    ref = O.psnr_per_frame(gen, gt)
+    assert_close(per.cpu(), ref, 1e-5, f"psnr{shape}")
+
+
+def test_psnr_unaligned_view():
+    gen, gt = synth.frames(42, 4, 3, 33, 35)
+    g1, t1 = gen.to(DEV)[:, :, 1:, 2:], gt.to(DEV)[:, :, 1:, 2:]
+    assert_close(A.psnr_per_frame(g1, t1).cpu(), O.psnr_per_frame(gen[:, :, 1:, 2:], gt[:, :, 1:, 2:]), 1e-5, "psnr.view")
+
+
+@pytest.mark.parametrize("ds", ["ped2", "avenue", "shanghaitech"])
+def test_score_reduce_bit_exact(ds):
+    c, g = load_golden("scores_" + ds)
+    offs = np.concatenate([[0], np.cumsum(g["lengths"])])
+    img = [g["img"][offs[i]:offs[i + 1]] for i in range(len(g["lengths"]))]
+    fea = [g["fea"][offs[i]:offs[i + 1]] for i in range(len(g["lengths"]))]
+    s = A.score_reduce(img, fea, tuple(c["lam"]))
+    assert s.dtype == np.float32 and s.shape == g["scores"].shape
+    assert np.array_equal(s, g["scores"]), "max abs diff %g" % float(np.abs(s - g["scores"]).max())
+    assert np.array_equal(img[0], g["img"][:offs[1]]), "caller records must not be normalised in place"
+
+
+def test_score_reduce_ragged_and_constant():
+    rng = np.random.RandomState(3)
+    lens = [5, 6, 40, 1439, 9]
+    img = [rng.rand(n).astype(np.float32) * 30 + 10 for n in lens]
+    fea = [rng.rand(n).astype(np.float32) * 1e-5 for n in lens]
+    for lam in [(0.0, 0.0), (0.5, 1.0), (0.13, 0.6)]:
+        assert np.array_equal(A.score_reduce(img, fea, lam), O.score_reduce(img, fea, lam))
+
+
+def test_evaluate_matches_sklearn_on_reference_records(tmp_path):
+    import pickle
+    c, g = load_golden("scores_ped2")
+    offs = np.concatenate([[0], np.cumsum(g["lengths"])])
+    nv = len(g["lengths"])
+    rec = {"dataset": "ped2",
+           "rgb_img_pred_records": [g["img"][offs[i]:offs[i + 1]].copy() for i in range(nv)],
+           "rgb_fea_comm_records": [g["fea"][offs[i]:offs[i + 1]].copy() for i in range(nv)],
+           "op_img_pred_records": [], "op_fea_comm_records": []}
+    pk = tmp_path / "ped2"
+    pickle.dump(rec, open(pk, "wb"))
+    labels = [g["labels"][offs[i]:offs[i + 1]] for i in range(nv)]
+    ret = A.evaluate("img_pred_fea_comm_rgb_auc", str(pk), tuple(c["lam"]), gt_labels=labels)
+    assert ret["auc"] == round(float(g["auc"]), 3) and ret["optimal_loss"] == str(pk)

@@ -1,0 +1,76 @@
+"""CPU: host-side mirror of the reference interface -- state_dict layout, record assembly, patching."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import ammcnet_aaai2021_b200 as A
+from ammcnet_aaai2021_b200 import scoring
+from conftest import load_golden
+
+HAVE_REF = os.path.isdir("/root/reference/Code/models")
+
+
+def test_twostream_matches_reference_known_answers():
+    """25.049029 M parameters (docstring at reference Code/models/unet.py:1268-1275) and 222 state_dict entries."""
+    m = A.get_twostream()
+    assert sum(p.numel() for p in m.parameters()) == 25049029
+    sd = m.state_dict()
+    assert len(sd) == 222
+    assert tuple(sd["rgb.vq_down3.quan.enc.weight"].shape) == (64, 512, 1, 1)
+    assert tuple(sd["op.vq_down3.quan.quantize.embed"].shape) == (64, 256)
+    assert tuple(sd["rgb.vq_down3.quan.dec.weight"].shape) == (512, 128, 1, 1)
+    assert tuple(sd["bridge.O2F.conv.3.weight"].shape) == (512, 512, 3, 3)
+    assert "bridge.F20.conv.4.num_batches_tracked" in sd
+
+
+def test_single_stream_known_answer():
+    """UNetMem_v7(12 -> 3 channels, k=2): 7.805891 M parameters (reference unet.py:1232-1235)."""
+    m = A.UNetMem_v7(12, 3, embed_dim=64, n_embed=512, k=2)
+    assert sum(p.numel() for p in m.parameters()) == 7805891
+
+
+def test_record_assembly_matches_reference_records():
+    c, g = load_golden("records")
+    for v, T in enumerate(c["lengths"]):
+        rgb_img, rgb_fea = g[f"rgb_img_pred_records_{v}"], g[f"rgb_fea_comm_records_{v}"]
+        n_clips = T - 4
+        groups = np.array([rgb_fea[4 + 16 * i] for i in range((n_clips + 15) // 16)], np.float32)
+        img, fea = scoring.assemble_video_records(rgb_img[4:], groups, clip_len=5)
+        assert np.array_equal(img, rgb_img) and np.array_equal(fea, rgb_fea)
+        op_fea = g[f"op_fea_comm_records_{v}"]
+        og = np.array([op_fea[3 + 16 * i] for i in range((n_clips + 15) // 16)], np.float32)
+        _, fea2 = scoring.assemble_video_records(np.zeros(n_clips, np.float32), og, clip_len=4, tail_copy=True)
+        assert np.array_equal(fea2, op_fea)
+
+
+def test_group_commit_from_frames():
+    sse = torch.arange(1, 38, dtype=torch.float32)
+    out = scoring.group_commit_from_frames(sse, elems_per_frame=10, group=16)
+    exp = [sse[0:16].sum() / 160, sse[16:32].sum() / 160, sse[32:37].sum() / 50]
+    assert torch.allclose(out, torch.stack(exp))
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference tree only exists in the build container")
+def test_swap_and_patch_against_live_reference():
+    import ref_harness
+    ref_unet, ref_utils, _ = ref_harness.import_reference()
+    g = ref_unet.get_twostream(in_channel=(12, 6), out_channel=(3, 2), embed_dim=64, n_embed=256, k=2)
+    ref_sd = {k: v.clone() for k, v in g.state_dict().items()}
+    A.swap_modules(g)
+    assert isinstance(g.bridge, A.bridge) and isinstance(g.rgb.vq_down3, A.enc_quan_dec_res_topk)
+    new_sd = g.state_dict()
+    assert list(new_sd) == list(ref_sd)
+    assert all(torch.equal(new_sd[k], ref_sd[k]) for k in ref_sd)
+    ours = A.get_twostream()
+    ours.load_state_dict(ref_sd, strict=True)          # reference checkpoint loads into the standalone host model
+    saved = A.patch_reference(ref_unet, ref_utils)
+    try:
+        g2 = ref_unet.get_twostream(in_channel=(12, 6), out_channel=(3, 2), embed_dim=64, n_embed=256, k=2)
+        assert isinstance(g2.bridge, A.bridge) and isinstance(g2.op.vq_down3.quan.quantize, A.Quantize_topk)
+        assert list(g2.state_dict()) == list(ref_sd)
+        assert ref_utils.psnr_error is A.psnr_error
+    finally:
+        A.unpatch_reference(ref_unet, saved, ref_utils)
+    assert ref_unet.bridge is saved["bridge"]

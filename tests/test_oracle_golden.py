@@ -1,0 +1,119 @@
+"""CPU: the oracle restatement reproduces every fixture the live reference generated (oracle/gen_golden.py)."""
+import numpy as np
+import pytest
+import torch
+
+import ammc_oracle as O
+from ammcnet_aaai2021_b200 import synth
+from conftest import load_golden, assert_close
+
+MEM = ["mem_shipped", "mem_cfg1", "mem_k3", "mem_k1"]
+
+
+def _mem_inputs(c):
+    p = synth.memory_params(c["seed"], c["C"], c["D"], c["M"], c["k"])
+    x = synth.features(c["seed"] + 1000, c["b"], c["C"], c["h"], c["w"])
+    return p, x
+
+
+@pytest.mark.parametrize("name", MEM)
+def test_memory_forward(name):
+    c, g = load_golden(name)
+    p, x = _mem_inputs(c)
+    o = O.memory_module_forward(x, p["enc.weight"], p["enc.bias"], p["quantize.embed"], p["dec.weight"],
+                                p["dec.bias"], c["k"])
+    assert np.array_equal(o["idx_topk"].numpy(), g["idx_topk"])
+    assert np.array_equal(o["quantize_topk"].numpy(), g["read"])
+    assert_close(o["out"], g["out"], 1e-6, name + ".out")
+    assert_close(o["diff"], g["diff"], 1e-6, name + ".diff")
+    assert_close(o["quantize"], g["q1"], 1e-6, name + ".q1")
+    assert_close(o["sse_per_frame"], g["sse_per_frame"], 1e-6, name + ".sse")
+
+
+@pytest.mark.parametrize("name", MEM)
+def test_memory_training_ema(name):
+    c, g = load_golden(name)
+    p, x = _mem_inputs(c)
+    x2 = synth.features(c["seed"] + 2000, c["b"], c["C"], c["h"], c["w"])
+    cs, ea, em = p["quantize.cluster_size"], p["quantize.embed_avg"], p["quantize.embed"]
+    for step, xs in enumerate((x, x2)):
+        o = O.memory_module_forward(xs, p["enc.weight"], p["enc.bias"], em, p["dec.weight"], p["dec.bias"], c["k"],
+                                    training=True, cluster_size=cs, embed_avg=ea)
+        cs, ea, em = o["cluster_size"], o["embed_avg"], o["embed"]
+        assert_close(o["out"], g[f"train{step}_out"], 1e-5, f"{name}.train{step}.out")
+        assert_close(cs, g[f"train{step}_cluster_size"], 1e-5, f"{name}.train{step}.cs")
+        assert_close(ea, g[f"train{step}_embed_avg"], 1e-5, f"{name}.train{step}.avg")
+        assert_close(em, g[f"train{step}_embed"], 1e-4, f"{name}.train{step}.embed")
+
+
+@pytest.mark.parametrize("name", MEM)
+def test_memory_backward(name):
+    c, g = load_golden(name)
+    p, x = _mem_inputs(c)
+    o = O.memory_module_forward(x, p["enc.weight"], p["enc.bias"], p["quantize.embed"], p["dec.weight"],
+                                p["dec.bias"], c["k"])
+    gen = torch.Generator().manual_seed(c["seed"] + 3000)
+    r_out = torch.randn(o["out"].shape, generator=gen)
+    r_q1 = torch.randn(o["quantize"].shape, generator=gen)
+    ob = O.memory_module_backward(x, p["enc.weight"], p["enc.bias"], p["quantize.embed"], p["dec.weight"],
+                                  o["idx_topk"], o["z"], r_out, torch.tensor(3.0), r_q1)
+    for k in ("gx", "g_enc_w", "g_enc_b", "g_dec_w", "g_dec_b"):
+        assert_close(ob[k], g[k], 1e-4, f"{name}.{k}")
+
+
+@pytest.mark.parametrize("name", ["amft_c64", "amft_c512"])
+def test_amft(name):
+    c, g = load_golden(name)
+    p = synth.amft_params(c["seed"], c["C"])
+    zx = synth.features(c["seed"] + 1000, c["b"], c["C"], c["h"], c["w"])
+    zy = synth.features(c["seed"] + 2000, c["b"], c["C"], c["h"], c["w"])
+    x, y, _ = O.amft_forward(zx, zy, p)
+    assert_close(x, g["x"], 1e-5, name + ".x")
+    assert_close(y, g["y"], 1e-5, name + ".y")
+    tx, ty, stats = O.amft_forward(zx, zy, p, training=True)
+    assert_close(tx, g["train_x"], 1e-4, name + ".train_x")
+    assert_close(ty, g["train_y"], 1e-4, name + ".train_y")
+    for k, v in stats.items():
+        assert_close(v, g["stat_" + k], 1e-5, name + "." + k)
+
+
+def test_psnr():
+    c, g = load_golden("psnr")
+    gen, gt = synth.frames(c["seed"], c["b"], c["c"], c["h"], c["w"])
+    assert_close(O.psnr_per_frame(gen, gt), g["per_frame"], 1e-6, "psnr.per_frame")
+    assert_close(O.psnr_error(gen, gt), g["batch_mean"], 1e-6, "psnr.batch")
+
+
+@pytest.mark.parametrize("ds", ["ped2", "avenue", "shanghaitech"])
+def test_score_reduction_known_answers(ds):
+    """Recorded per-frame score pickles of the reference's real runs -> scores (bit-exact) and the KAT sums of BASELINE.md."""
+    c, g = load_golden("scores_" + ds)
+    offs = np.concatenate([[0], np.cumsum(g["lengths"])])
+    img = [g["img"][offs[i]:offs[i + 1]] for i in range(len(g["lengths"]))]
+    fea = [g["fea"][offs[i]:offs[i + 1]] for i in range(len(g["lengths"]))]
+    s = O.score_reduce(img, fea, tuple(c["lam"]))
+    assert s.dtype == np.float32 and np.array_equal(s, g["scores"])
+    kat = {"ped2": (1962, 910.9196372), "avenue": (15240, 11922.8437268), "shanghaitech": (40363, 28164.4554798)}[ds]
+    assert len(s) == kat[0]
+    assert abs(float(np.sum(s.astype(np.float64))) - kat[1]) < 1e-4
+    assert abs(O.roc_auc(g["labels_kept"] if "labels_kept" in g else
+                         np.concatenate([g["labels"][offs[i] + 4:offs[i + 1]] for i in range(len(g["lengths"]))]),
+                         s) - float(g["auc"])) < 1e-12
+
+
+def test_record_assembly():
+    """Record layout of the reference scoring loop, from records the reference itself wrote (gen_golden.gen_records)."""
+    c, g = load_golden("records")
+    for v, T in enumerate(c["lengths"]):
+        rgb_img = g[f"rgb_img_pred_records_{v}"]
+        rgb_fea = g[f"rgb_fea_comm_records_{v}"]
+        n_clips = T - 4
+        psnr_clip = rgb_img[4:]
+        groups = np.array([rgb_fea[4 + 16 * i] for i in range((n_clips + 15) // 16)], np.float32)
+        img, fea = O.assemble_video_records(psnr_clip, groups, clip_len=5)
+        assert np.array_equal(img, rgb_img) and np.array_equal(fea, rgb_fea)
+        op_fea = g[f"op_fea_comm_records_{v}"]
+        op_img = g[f"op_img_pred_records_{v}"]
+        ogroups = np.array([op_fea[3 + 16 * i] for i in range((n_clips + 15) // 16)], np.float32)
+        img2, fea2 = O.assemble_video_records(op_img[3:3 + n_clips], ogroups, clip_len=4, tail_copy=True)
+        assert np.array_equal(fea2, op_fea) and np.array_equal(img2, op_img)
