@@ -68,6 +68,10 @@ def _count(n):
     LAUNCHES["count"] += n
 
 
+# optional CUDA-event bracketing of the dominant kernel (bench.py's roofline measurement, live in the timed region)
+PROFILE = {"on": False, "events": []}
+
+
 # --------------------------------------------------------------------------------------------------
 # memory module
 # --------------------------------------------------------------------------------------------------
@@ -294,8 +298,14 @@ def conv3x3_bn_relu(xp, wp, scale, shift, *, to_planes: bool, residual: Optional
         _require_cuda_f32(residual, names=("residual",))
         residual = residual.contiguous()
     with torch.cuda.device(dev):
+        if PROFILE["on"]:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
         _capi.call("ammc_conv3x3_bn_relu" if taps == 9 else "ammc_conv1x1_bn_relu", _p(xp), _p(wp), _p(scale), _p(shift), _p(out_p), _p(out_n), _p(residual),
                    b, Cin, Cout, h, w, int(precision), int(bool(relu)), _stream())
+        if PROFILE["on"]:
+            ev1.record()
+            PROFILE["events"].append((ev0, ev1))
     _count(1)
     return out_p if to_planes else out_n
 
