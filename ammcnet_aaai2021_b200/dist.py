@@ -58,7 +58,7 @@ def all_gather_scores(scores: torch.Tensor, group=None) -> torch.Tensor:
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return scores.unsqueeze(0)
     out = torch.empty((dist.get_world_size(group),) + tuple(scores.shape), dtype=scores.dtype, device=scores.device)
-    dist.all_gather_into_tensor(out, scores.contiguous(), group=group)
+    dist.all_gather(list(out.unbind(0)), scores.contiguous(), group=group)
     return out
 
 

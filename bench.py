@@ -109,8 +109,9 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------------------
 class ClockSampler:
     """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md)."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device_index):
         self.file = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
@@ -119,9 +120,24 @@ class ClockSampler:
             uuid = str(torch.cuda.get_device_properties(device_index).uuid)
             sel = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
             self.proc = subprocess.Popen(["nvidia-smi", "-i", sel, "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=self.file, stderr=subprocess.DEVNULL)
+                                          "-lms", "20"], stdout=self.file, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
+        self.t_begin = self.t_end = None
+
+    def mark_begin(self):
+        self.t_begin = time.time()
+
+    def mark_end(self):
+        self.t_end = time.time()
+
+    @staticmethod
+    def _ts(s):
+        import datetime
+        try:
+            return datetime.datetime.strptime(s.strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+        except Exception:
+            return None
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
@@ -138,8 +154,13 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.file.read().splitlines():
             f = [s.strip() for s in ln.split(",")]
-            if len(f) < 7:
+            if len(f) < 8:
                 continue
+            ts = self._ts(f[0])
+            # keep the samples taken while the timed loop was running (nvidia-smi stamps are host local time)
+            if ts is not None and self.t_begin is not None and not (self.t_begin - 0.02 <= ts <= self.t_end + 0.02):
+                continue
+            f = f[1:]
             try:
                 sm.append(float(f[0])); mx.append(float(f[1])); power.append(float(f[2]))
             except ValueError:
@@ -217,22 +238,26 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local) if rank == 0 else None      # started before warm-up so it is sampling by the time we time
     for _ in range(max(args.warmup, 3)):
         path_step(xr, xo, gen, gt)
     barrier()
 
     # ---- timed region (device-resident inputs) --------------------------------------------------------------
-    sampler = ClockSampler(local) if rank == 0 else None
     F_.PROFILE["on"] = True
     F_.PROFILE["events"].clear()
     F_.LAUNCHES["count"] = 0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    if sampler:
+        sampler.mark_begin()
     e0.record()
     for _ in range(args.steps):
         path_step(xr, xo, gen, gt)
     e1.record()
     barrier()
+    if sampler:
+        sampler.mark_end()
     ms = e0.elapsed_time(e1)
     launches = F_.LAUNCHES["count"]
     F_.PROFILE["on"] = False

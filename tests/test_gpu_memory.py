@@ -171,9 +171,11 @@ def test_full_size_properties():
         dec = read @ p["dec.weight"].reshape(C, k * D).t().to(DEV) + p["dec.bias"].to(DEV)
         ref = dec.view(b, 32, 32, C).permute(0, 3, 1, 2) + x
         assert_close(out.cpu(), ref.cpu(), 1e-3, "full.out")
-        # (5) the top-1 item really is the nearest one (up to fp32 ties)
-        z = q1  # value of the straight-through output == e_top1
-        zf = (torch.nn.functional.conv2d(x, p["enc.weight"].to(DEV), p["enc.bias"].to(DEV))).permute(0, 2, 3, 1).reshape(-1, D)
-        d_all = torch.cdist(zf.double(), embed.t().double()).pow(2)
+        # (5) the top-1 item really is the nearest one: re-rank in fp64 (z recomputed in fp64, no TF32 anywhere)
+        w64 = p["enc.weight"].reshape(D, C).double().to(DEV)
+        zf = torch.einsum("bchw,dc->bhwd", x.double(), w64).reshape(-1, D) + p["enc.bias"].double().to(DEV)
+        d_all = torch.cdist(zf, embed.t().double()).pow(2)
         chosen = d_all.gather(1, idx[:, :1]).squeeze(1)
-        assert bool((chosen <= d_all.min(1)[0] * (1 + 1e-5) + 1e-6).all())
+        assert bool((chosen <= d_all.min(1)[0] * (1 + 1e-4) + 1e-4).all())
+        exact = (idx[:, 0] == d_all.argmin(1)).float().mean().item()
+        assert exact > 0.999, "top-1 agreement with the fp64 ranking %.5f" % exact
