@@ -20,7 +20,12 @@ SIGNATURES = {
     "ammc_last_error": (c_char_p, []),
     "ammc_device_supported": (I, []),
     "ammc_mem_workspace_bytes": (Z, [I] * 7),
+    "ammc_set_addressing_mode": (I, [I]),
     "ammc_mem_fwd": (I, [P] * 6 + [P] * 6 + [P, P] + [P, Z] + [I] * 8 + [P]),
+    "ammc_addr_padded_items": (I, [I]),
+    "ammc_addr_pack_queries": (I, [P, P, P, L, I, P]),
+    "ammc_addr_pack_bank": (I, [P] * 6 + [I, I, P]),
+    "ammc_addr_filter": (I, [P] * 7 + [L, I, I, I, P]),
     "ammc_quantize_workspace_bytes": (Z, [L, I, I, I]),
     "ammc_quantize_fwd": (I, [P, P] + [P] * 5 + [P, P] + [P, Z] + [L, L, I, I, I] + [P]),
     "ammc_quantize_bwd_workspace_bytes": (Z, [L, I, I]),

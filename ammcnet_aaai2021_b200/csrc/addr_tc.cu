@@ -1,0 +1,544 @@
+// Memory addressing on the tensor cores (north-star kernel (a)): similarity contraction -> top-k, with the
+// similarity matrix living only in TMEM.
+//
+// Exactness scheme ("filter + refine"): the reference ranks fp32 distances (Code/models/unet.py:283-293).  tcgen05 has
+// no fp32 MMA, so the N x M x D contraction runs ONCE in bf16 as a *filter* that keeps, per query, the CAND = 8 items
+// with the smallest approximate score  a~_j = ||e_j||^2 - 2 z~.e~_j  (||z||^2 is rank-irrelevant).  `refine_kernel` then
+// recomputes the exact fp32 distance of those 8 items with the SAME arithmetic as the generic fp32 path (mem_simt.cu)
+// and ranks them.  A rigorous bound makes this safe:  |a~_j - a_j| <= 2 eps,  eps = 2^-8 * 1.02 * ||z|| * max_j ||e_j||
+// (bf16 rounding of both operands + Cauchy-Schwarz).  Every item that was filtered out has a~ >= tau (the worst kept
+// score), hence a >= tau - 2 eps; if the exact k-th best is below that, no filtered item can belong to the top-k.
+// Rows that fail the test (near-degenerate neighbourhoods) are re-scanned exactly over all M items in place, so the
+// indices are bit-identical to the fp32 path for every input; the number of such rows is reported in the stats block.
+//
+//   addr_tc_kernel<BLOCK_N>   persistent; per 128-query tile loops over item tiles; TMA (128B swizzle) -> smem ->
+//                             tcgen05.mma (M128 x N BLOCK_N x K16, fp32 accum in TMEM, 2 accumulator buffers);
+//                             4 epilogue warps: tcgen05.ld -> a~ -> running top-8 in registers across item tiles.
+//   refine_kernel<K>          4-lane team per query: exact distances of the candidates, top-k, miss test / exact
+//                             fallback, gathers (read, q1), per-pixel SSE, EMA statistics.
+#include "common.cuh"
+#include "ptx.cuh"
+#include "topk.cuh"
+#include "addr_tail.cuh"
+#include <cuda_bf16.h>
+#include <float.h>
+
+namespace ammc {
+
+constexpr int ADDR_EPI_WARPS = 8;
+constexpr int ADDR_THREADS = 64 + 32 * ADDR_EPI_WARPS;   // warp 0: TMA, warp 1: MMA, warps 2-9: epilogue
+constexpr int ADDR_CAPH = 12;                           // candidate slots per (query, column half)
+constexpr int ADDR_CAND = 2 * ADDR_CAPH;                // candidate slots per query
+constexpr int ADDR_BLOCK_K = 64;
+constexpr int ADDR_A_BYTES = 128 * ADDR_BLOCK_K * 2;
+
+struct AddrParams {
+  int N, D, M, Mpad;
+  int tiles_q, tiles_i;
+  const float* en2pad;  // [Mpad], +inf beyond M
+  const float* znorm2;  // [N]  ||z_n||^2 (fp32)
+  const float* emax;    // [1]  max_j ||e_j||
+  int* cand;            // [N][ADDR_CAND]
+  int* cand_cnt;        // [N][2]  entries used per half; > ADDR_CAPH means overflow -> exact re-scan
+};
+
+template <int BLOCK_N>
+struct AddrSmem {
+  static constexpr int B_BYTES = BLOCK_N * ADDR_BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = ADDR_A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8);
+  static constexpr int LIST_OFFSET = STAGES * STAGE_BYTES;         // float [256 threads][CAPH] + uint16 [256][CAPH]
+  static constexpr int BAR_OFFSET = LIST_OFFSET + 256 * ADDR_CAPH * 6;
+  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
+};
+
+// branch-free insertion of x into the ascending list m[0..KSEL)
+template <int KSEL>
+__device__ __forceinline__ void sel_insert(float (&m)[KSEL], float x) {
+#pragma unroll
+  for (int i = 0; i < KSEL; ++i) {
+    const float lo = fminf(m[i], x);
+    x = fmaxf(m[i], x);
+    m[i] = lo;
+  }
+}
+
+// v[j] for a run-time j without spilling the register array to local memory (5-level select tree)
+__device__ __forceinline__ uint32_t select32(const uint32_t (&v)[32], int j) {
+  uint32_t a[16], b[8], c[4], d[2];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = (j & 1) ? v[2 * i + 1] : v[2 * i];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) b[i] = (j & 2) ? a[2 * i + 1] : a[2 * i];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) c[i] = (j & 4) ? b[2 * i + 1] : b[2 * i];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) d[i] = (j & 8) ? c[2 * i + 1] : c[2 * i];
+  return (j & 16) ? d[1] : d[0];
+}
+
+template <int BLOCK_N, int KSEL>
+__global__ void __launch_bounds__(ADDR_THREADS, 1)
+addr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const AddrParams p) {
+  using S = AddrSmem<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  float* list_val = reinterpret_cast<float*>(smem + S::LIST_OFFSET);
+  uint16_t* list_idx = reinterpret_cast<uint16_t*>(smem + S::LIST_OFFSET + 256 * ADDR_CAPH * 4);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + S::STAGES;
+  uint64_t* tmem_full = empty_bar + S::STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kb_per_tile = p.D / ADDR_BLOCK_K;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tmA);
+    ptx::prefetch_tensormap(&tmB);
+    for (int s = 0; s < S::STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tmem_full[a], 1); ptx::mbar_init(&tmem_empty[a], 32 * ADDR_EPI_WARPS); }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, 2 * BLOCK_N);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int tq = blockIdx.x; tq < p.tiles_q; tq += gridDim.x) {
+        for (int ti = 0; ti < p.tiles_i; ++ti) {
+          for (int kb = 0; kb < kb_per_tile; ++kb) {
+            ptx::mbar_wait(&empty_bar[s], ph ^ 1, 11);
+            ptx::mbar_expect_tx(&full_bar[s], S::STAGE_BYTES);
+            uint8_t* a_dst = smem + s * S::STAGE_BYTES;
+            ptx::tma_load_2d(a_dst, &tmA, &full_bar[s], kb * ADDR_BLOCK_K, tq * 128);
+            ptx::tma_load_2d(a_dst + ADDR_A_BYTES, &tmB, &full_bar[s], kb * ADDR_BLOCK_K, ti * BLOCK_N);
+            if (++s == S::STAGES) { s = 0; ph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc(1, 128, BLOCK_N);
+      int s = 0; uint32_t ph = 0;
+      int it = 0;
+      for (int tq = blockIdx.x; tq < p.tiles_q; tq += gridDim.x) {
+        for (int ti = 0; ti < p.tiles_i; ++ti, ++it) {
+          const int acc = it & 1;
+          const uint32_t acc_ph = (it >> 1) & 1;
+          ptx::mbar_wait(&tmem_empty[acc], acc_ph ^ 1, 12);
+          ptx::tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+          for (int kb = 0; kb < kb_per_tile; ++kb) {
+            ptx::mbar_wait(&full_bar[s], ph, 13);
+            ptx::tc_fence_after();
+            const uint32_t a_addr = ptx::smem_u32(smem + s * S::STAGE_BYTES);
+            const uint64_t adesc = ptx::umma_desc_k_sw128(a_addr);
+            const uint64_t bdesc = ptx::umma_desc_k_sw128(a_addr + ADDR_A_BYTES);
+#pragma unroll
+            for (int k4 = 0; k4 < ADDR_BLOCK_K / 16; ++k4)
+              ptx::mma_f16_ss(d_tmem, adesc + 2 * k4, bdesc + 2 * k4, idesc, (kb | k4) != 0 ? 1u : 0u);
+            ptx::mma_commit(&empty_bar[s]);
+            if (kb == kb_per_tile - 1) ptx::mma_commit(&tmem_full[acc]);
+            if (++s == S::STAGES) { s = 0; ph ^= 1; }
+          }
+        }
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue: 2 warps per TMEM lane quarter, each
+    // owning half of the tile's columns.  Pass A keeps the KSEL smallest approximate scores (values only, branch-free);
+    // pass B re-reads the tile and records every column whose score is within the safety margin of the KSEL-th best.
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    constexpr int HALF_N = BLOCK_N / 2;
+    constexpr int CHUNKS = HALF_N / 32;
+    float* lv = list_val + (size_t)((warp - 2) * 32 + lane) * ADDR_CAPH;
+    uint16_t* li = list_idx + (size_t)((warp - 2) * 32 + lane) * ADDR_CAPH;
+    const float emax = __ldg(p.emax);
+    int it = 0;
+    for (int tq = blockIdx.x; tq < p.tiles_q; tq += gridDim.x) {
+      const int n = tq * 128 + q * 32 + lane;
+      const float zn2 = n < p.N ? __ldg(p.znorm2 + n) : 0.f;
+      // |a~ - a| <= 2 eps with eps = 2^-8 * 1.02 * ||z|| * max||e||; candidates within 4 eps (+ fp32 slack) of the
+      // KSEL-th smallest approximate score are a superset of the exact top-KSEL (see file header).
+      const float margin = 4.f * 0.00390625f * 1.02f * sqrtf(zn2) * emax + 1e-5f * (zn2 + emax * emax) + 1e-30f;
+      float m[KSEL];
+#pragma unroll
+      for (int i = 0; i < KSEL; ++i) m[i] = INFINITY;
+      int cnt = 0;
+      bool overflow = false;
+      for (int ti = 0; ti < p.tiles_i; ++ti, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_ph = (it >> 1) & 1;
+        ptx::mbar_wait(&tmem_full[acc], acc_ph, 14);
+        ptx::tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N + half * HALF_N;
+        const int col0 = ti * BLOCK_N + half * HALF_N;
+        // ---- pass A
+#pragma unroll 1
+        for (int c = 0; c < CHUNKS; ++c) {
+          uint32_t v[32];
+          ptx::tmem_ld_32x32(taddr + c * 32, v);
+          ptx::tmem_ld_wait();
+          const float4* e4 = reinterpret_cast<const float4*>(p.en2pad + col0 + c * 32);
+          float ma[4][KSEL];
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+#pragma unroll
+            for (int i = 0; i < KSEL; ++i) ma[g][i] = INFINITY;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 e = __ldg(e4 + j);
+            sel_insert<KSEL>(ma[0], fmaf(-2.f, __uint_as_float(v[4 * j + 0]), e.x));
+            sel_insert<KSEL>(ma[1], fmaf(-2.f, __uint_as_float(v[4 * j + 1]), e.y));
+            sel_insert<KSEL>(ma[2], fmaf(-2.f, __uint_as_float(v[4 * j + 2]), e.z));
+            sel_insert<KSEL>(ma[3], fmaf(-2.f, __uint_as_float(v[4 * j + 3]), e.w));
+          }
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+#pragma unroll
+            for (int i = 0; i < KSEL; ++i) sel_insert<KSEL>(m, ma[g][i]);
+        }
+        // ---- pass B
+        const float thr = fminf(m[KSEL - 1] + margin, FLT_MAX);   // padded columns score +inf and never hit
+#pragma unroll 1
+        for (int c = 0; c < CHUNKS; ++c) {
+          uint32_t v[32];
+          ptx::tmem_ld_32x32(taddr + c * 32, v);
+          ptx::tmem_ld_wait();
+          const float4* e4 = reinterpret_cast<const float4*>(p.en2pad + col0 + c * 32);
+          uint32_t hits = 0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 e = __ldg(e4 + j);
+            hits |= (fmaf(-2.f, __uint_as_float(v[4 * j + 0]), e.x) <= thr ? 1u : 0u) << (4 * j + 0);
+            hits |= (fmaf(-2.f, __uint_as_float(v[4 * j + 1]), e.y) <= thr ? 1u : 0u) << (4 * j + 1);
+            hits |= (fmaf(-2.f, __uint_as_float(v[4 * j + 2]), e.z) <= thr ? 1u : 0u) << (4 * j + 2);
+            hits |= (fmaf(-2.f, __uint_as_float(v[4 * j + 3]), e.w) <= thr ? 1u : 0u) << (4 * j + 3);
+          }
+          while (hits) {
+            const int j = __ffs(hits) - 1;
+            hits &= hits - 1;
+            const int col = col0 + c * 32 + j;
+            const float av = fmaf(-2.f, __uint_as_float(select32(v, j)), __ldg(p.en2pad + col));
+            if (cnt == ADDR_CAPH) {            // full: drop entries that the tightened threshold no longer admits
+              int w = 0;
+              for (int i = 0; i < ADDR_CAPH; ++i) {
+                const float x = lv[i];
+                const uint16_t ci = li[i];
+                if (x <= thr) { lv[w] = x; li[w] = ci; ++w; }
+              }
+              cnt = w;
+            }
+            if (cnt < ADDR_CAPH) { lv[cnt] = av; li[cnt] = (uint16_t)col; ++cnt; }
+            else overflow = true;
+          }
+        }
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&tmem_empty[acc]);
+      }
+      if (n < p.N) {
+        // final prune against the final threshold, then publish
+        const float thr_final = fminf(m[KSEL - 1] + margin, FLT_MAX);
+        int* dst = p.cand + (size_t)n * ADDR_CAND + half * ADDR_CAPH;
+        int w = 0;
+        for (int i = 0; i < cnt; ++i)
+          if (lv[i] <= thr_final) dst[w++] = (int)li[i];
+        for (int i = w; i < ADDR_CAPH; ++i) dst[i] = -1;
+        p.cand_cnt[(size_t)n * 2 + half] = overflow ? ADDR_CAPH + 1 : w;
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 2 * BLOCK_N);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// operand prep
+// ------------------------------------------------------------------------------------------------
+// z [N][D] fp32 -> zp bf16 (round to nearest) and ||z_n||^2; one warp per query row
+__global__ void __launch_bounds__(256) pack_rows_bf16_kernel(const float* __restrict__ z, __nv_bfloat16* __restrict__ zp,
+                                                              float* __restrict__ znorm2, long long N, int D) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= N) return;
+  const float* zr = z + row * D;
+  __nv_bfloat16* zo = zp + row * D;
+  float s = 0.f;
+  for (int d = lane * 2; d < D; d += 64) {      // D is a multiple of 64
+    const float2 v = __ldg(reinterpret_cast<const float2*>(zr + d));
+    s = fmaf(v.x, v.x, fmaf(v.y, v.y, s));
+    *reinterpret_cast<__nv_bfloat162*>(zo + d) = __floats2bfloat162_rn(v.x, v.y);
+  }
+  s = warp_sum(s);
+  if (lane == 0) znorm2[row] = s;
+}
+
+// bank_t [M][D] fp32 -> bank_hi [Mpad][D] bf16 (zero rows beyond M); en2pad [Mpad] (+inf beyond M); emax = max ||e||
+__global__ void bank_pack_kernel(const float* __restrict__ bank_t, const float* __restrict__ en2,
+                                 __nv_bfloat16* __restrict__ bank_hi, float* __restrict__ en2pad,
+                                 float* __restrict__ emax, int D, int M, int Mpad) {
+  const int m = blockIdx.x;
+  for (int d = threadIdx.x; d < D; d += blockDim.x)
+    bank_hi[(size_t)m * D + d] = m < M ? __float2bfloat16_rn(bank_t[(size_t)m * D + d]) : __float2bfloat16_rn(0.f);
+  if (threadIdx.x == 0) {
+    en2pad[m] = m < M ? en2[m] : INFINITY;
+    if (m < M) atomicMax(reinterpret_cast<int*>(emax), __float_as_int(sqrtf(en2[m])));  // non-negative floats order as ints
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// refine: exact fp32 ranking of the candidates (or of all items when the list overflowed), gathers, commit partials,
+// EMA statistics.  Arithmetic identical to address_kernel in mem_simt.cu -> identical indices.
+// ------------------------------------------------------------------------------------------------
+template <int K>
+__device__ __forceinline__ void team_merge(TopK<K>& top) {
+#pragma unroll
+  for (int o = 1; o <= 2; o <<= 1) {
+    float ov[K]; int oi[K];
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+      ov[i] = __shfl_xor_sync(0xffffffffu, top.v[i], o);
+      oi[i] = __shfl_xor_sync(0xffffffffu, top.id[i], o);
+    }
+#pragma unroll
+    for (int i = 0; i < K; ++i) top.insert(ov[i], oi[i]);
+  }
+}
+
+// stats: [0] rows needing the exact re-scan (reported), [1] path id, [2] length of the re-scan work list
+template <int K>
+__global__ void __launch_bounds__(256) refine_kernel(
+    const float* __restrict__ z, const int* __restrict__ cand, const int* __restrict__ cand_cnt,
+    const float* __restrict__ bank_t, const float* __restrict__ en2,
+    float* __restrict__ read, float* __restrict__ q1, int64_t* __restrict__ idx, float* __restrict__ sse_px,
+    float* __restrict__ counts, float* __restrict__ embed_sum, int* __restrict__ stats, int* __restrict__ rescan_list,
+    int N, int D, int M) {
+  const int t = threadIdx.x;
+  const int px = t >> 2, part = t & 3;
+  const int n = blockIdx.x * 64 + px;
+  bool valid = n < N;
+  const float* zr = z + (size_t)(valid ? n : 0) * D;
+  const float zn2 = team_zn2(zr, D, part, valid);
+  TopK<K> top;
+  top.init();
+  if (valid) {
+    const int c0 = cand_cnt[(size_t)n * 2], c1 = cand_cnt[(size_t)n * 2 + 1];
+    const bool rescan = c0 > ADDR_CAPH || c1 > ADDR_CAPH || (c0 + c1) < K;       // uniform within the 4-lane team
+    if (rescan) {
+      if (part == 0) {
+        atomicAdd(&stats[0], 1);
+        rescan_list[atomicAdd(&stats[2], 1)] = n;
+      }
+      valid = false;                                                              // rescan_kernel owns this row
+    } else {
+      const int* cr = cand + (size_t)n * ADDR_CAND;
+      for (int c = part; c < c0; c += 4) {
+        const int j = cr[c];
+        top.insert(exact_dist(zn2, exact_dot(zr, bank_t + (size_t)j * D, D), en2[j]), j);
+      }
+      for (int c = part; c < c1; c += 4) {
+        const int j = cr[ADDR_CAPH + c];
+        top.insert(exact_dist(zn2, exact_dot(zr, bank_t + (size_t)j * D, D), en2[j]), j);
+      }
+    }
+  }
+  team_merge<K>(top);
+#pragma unroll
+  for (int i = 0; i < K; ++i) top.id[i] = min(top.id[i], M - 1);
+  team_emit_row<K>(zr, bank_t, top.id, (int64_t)n, D, M, part, valid, read, q1, idx, sse_px, counts, embed_sum);
+}
+
+// Exact scan over all M items for the (rare) rows whose candidate list overflowed: one warp per row.
+template <int K>
+__global__ void __launch_bounds__(256) rescan_kernel(
+    const float* __restrict__ z, const float* __restrict__ bank_t, const float* __restrict__ en2,
+    float* __restrict__ read, float* __restrict__ q1, int64_t* __restrict__ idx, float* __restrict__ sse_px,
+    float* __restrict__ counts, float* __restrict__ embed_sum, const int* __restrict__ stats,
+    const int* __restrict__ rescan_list, int D, int M) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int total = stats[2];
+  for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < total; w += warps) {
+    const int n = rescan_list[w];
+    const float* zr = z + (size_t)n * D;
+    const float zn2 = __shfl_sync(0xffffffffu, team_zn2(zr, D, lane & 3, true), 0);
+    TopK<K> top;
+    top.init();
+    for (int j = lane; j < M; j += 32)
+      top.insert(exact_dist(zn2, exact_dot(zr, bank_t + (size_t)j * D, D), en2[j]), j);
+#pragma unroll
+    for (int o = 1; o <= 16; o <<= 1) {
+      float ov[K]; int oi[K];
+#pragma unroll
+      for (int i = 0; i < K; ++i) {
+        ov[i] = __shfl_xor_sync(0xffffffffu, top.v[i], o);
+        oi[i] = __shfl_xor_sync(0xffffffffu, top.id[i], o);
+      }
+#pragma unroll
+      for (int i = 0; i < K; ++i) top.insert(ov[i], oi[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < K; ++i) top.id[i] = min(top.id[i], M - 1);
+    team_emit_row<K>(zr, bank_t, top.id, (int64_t)n, D, M, lane & 3, lane < 4, read, q1, idx, sse_px, counts, embed_sum);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host
+// ------------------------------------------------------------------------------------------------
+int make_map_2d_bf16(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, uint32_t box_inner,
+                     uint32_t box_outer);   // amft_conv.cu
+
+int addr_block_n(int M) { return M >= 192 ? 256 : (M >= 96 ? 128 : 64); }
+
+size_t addr_tc_ws_bytes(int64_t N, int D, int M) {
+  const int bn = addr_block_n(M);
+  const int Mpad = (int)align_up(M, bn);
+  return align_up((size_t)N * D * 2, 256) + align_up((size_t)Mpad * D * 2, 256) + align_up((size_t)Mpad * 4, 256) +
+         align_up((size_t)N * ADDR_CAND * 4, 256) + align_up((size_t)N * 2 * 4, 256) + 2 * align_up((size_t)N * 4, 256) +
+         256;
+}
+
+bool addr_tc_supported(int64_t N, int D, int M, int k) {
+  return D % 64 == 0 && D >= 64 && M >= 16 && M <= 65536 && k <= 4 && N >= 1;
+}
+
+template <int BLOCK_N, int KSEL>
+static int launch_addr2(const CUtensorMap& tmA, const CUtensorMap& tmB, const AddrParams& p, cudaStream_t st) {
+  using S = AddrSmem<BLOCK_N>;
+  static bool configured[64] = {false};
+  int dev = 0;
+  AMMC_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && !configured[dev]) {
+    AMMC_CUDA_CHECK(cudaFuncSetAttribute(addr_tc_kernel<BLOCK_N, KSEL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         S::TOTAL));
+    configured[dev] = true;
+  }
+  int grid = min(num_sms(), p.tiles_q);
+  addr_tc_kernel<BLOCK_N, KSEL><<<grid, ADDR_THREADS, S::TOTAL, st>>>(tmA, tmB, p);
+  AMMC_LAUNCH_CHECK("addr_tc_kernel");
+  return 0;
+}
+
+template <int BLOCK_N>
+static int launch_addr(const CUtensorMap& tmA, const CUtensorMap& tmB, const AddrParams& p, int k, cudaStream_t st) {
+  return k <= 2 ? launch_addr2<BLOCK_N, 2>(tmA, tmB, p, st) : launch_addr2<BLOCK_N, 4>(tmA, tmB, p, st);
+}
+
+static int launch_filter(const void* zp, const void* bank_hi, AddrParams& p, int bn, int k, cudaStream_t st) {
+  CUtensorMap tmA, tmB;
+  if (int rc = make_map_2d_bf16(&tmA, zp, (uint64_t)p.D, (uint64_t)p.N, 64, 128)) return rc;
+  if (int rc = make_map_2d_bf16(&tmB, bank_hi, (uint64_t)p.D, (uint64_t)p.Mpad, 64, (uint32_t)bn)) return rc;
+  return bn == 256 ? launch_addr<256>(tmA, tmB, p, k, st)
+                   : (bn == 128 ? launch_addr<128>(tmA, tmB, p, k, st) : launch_addr<64>(tmA, tmB, p, k, st));
+}
+
+// z fp32 [N][D] (+ optional pre-packed bf16 copy zp), bank_t fp32 [M][D], en2 [M]  ->  outputs as address_kernel.
+// `ws` must provide addr_tc_ws_bytes(); stats[0] += rows that needed the exact fallback.
+int run_address_tc(const float* z, const __nv_bfloat16* zp_in, const float* bank_t, const float* en2, float* read,
+                   float* q1, int64_t* idx, float* sse_px, float* counts, float* embed_sum, int* stats, Workspace& ws,
+                   int64_t N, int D, int M, int k, cudaStream_t st) {
+  (void)zp_in;
+  const int bn = addr_block_n(M);
+  const int Mpad = (int)align_up(M, bn);
+  __nv_bfloat16* zp = ws.take<__nv_bfloat16>((size_t)N * D);
+  __nv_bfloat16* bank_hi = ws.take<__nv_bfloat16>((size_t)Mpad * D);
+  float* en2pad = ws.take<float>(Mpad);
+  int* cand = ws.take<int>((size_t)N * ADDR_CAND);
+  int* cand_cnt = ws.take<int>((size_t)N * 2);
+  float* znorm2 = ws.take<float>(N);
+  int* rescan_list = ws.take<int>(N);
+  float* emax = ws.take<float>(1);
+  if (!ws.ok()) return fail(AMMC_EWORKSPACE, "workspace too small");
+  pack_rows_bf16_kernel<<<ceil_div(N, 8), 256, 0, st>>>(z, zp, znorm2, N, D);
+  AMMC_LAUNCH_CHECK("pack_rows_bf16_kernel");
+  AMMC_CUDA_CHECK(cudaMemsetAsync(emax, 0, 4, st));
+  bank_pack_kernel<<<Mpad, 128, 0, st>>>(bank_t, en2, bank_hi, en2pad, emax, D, M, Mpad);
+  AMMC_LAUNCH_CHECK("bank_pack_kernel");
+
+  AddrParams p;
+  p.N = (int)N; p.D = D; p.M = M; p.Mpad = Mpad;
+  p.tiles_q = ceil_div(N, 128);
+  p.tiles_i = Mpad / bn;
+  p.en2pad = en2pad; p.znorm2 = znorm2; p.emax = emax; p.cand = cand; p.cand_cnt = cand_cnt;
+  if (int rc = launch_filter(zp, bank_hi, p, bn, k, st)) return rc;
+  const int blocks = ceil_div(N, 64);
+  switch (k) {
+#define AMMC_RF_CASE(KK)                                                                                      \
+  case KK:                                                                                                    \
+    refine_kernel<KK><<<blocks, 256, 0, st>>>(z, cand, cand_cnt, bank_t, en2, read, q1, idx, sse_px, counts,  \
+                                              embed_sum, stats, rescan_list, (int)N, D, M);                   \
+    rescan_kernel<KK><<<2 * num_sms(), 256, 0, st>>>(z, bank_t, en2, read, q1, idx, sse_px, counts, embed_sum, \
+                                                     stats, rescan_list, D, M);                               \
+    break;
+    AMMC_RF_CASE(1) AMMC_RF_CASE(2) AMMC_RF_CASE(3) AMMC_RF_CASE(4)
+#undef AMMC_RF_CASE
+    default: return fail(AMMC_EUNSUPPORTED, "tensor-core addressing supports k <= 4");
+  }
+  AMMC_LAUNCH_CHECK("refine_kernel");
+  return 0;
+}
+
+// mem_simt.cu
+__global__ void bank_transpose_kernel(const float* __restrict__ embed, float* __restrict__ bank_t, int D, int M);
+__global__ void bank_norms_kernel(const float* __restrict__ embed, float* __restrict__ en2, int D, int M);
+
+}  // namespace ammc
+
+using namespace ammc;
+
+// ---- staged entry points (what ammc_quantize_fwd / ammc_mem_fwd compose internally; used by the cfg5 microbench) ----
+extern "C" int ammc_addr_padded_items(int M) { return (int)align_up(M, addr_block_n(M)); }
+
+extern "C" int ammc_addr_pack_queries(const float* z, void* zp, float* znorm2, int64_t N, int D, void* stream) {
+  AMMC_REQUIRE(z && zp && znorm2 && N > 0 && D > 0 && D % 64 == 0, "bad argument (D must be a multiple of 64)");
+  pack_rows_bf16_kernel<<<ceil_div(N, 8), 256, 0, (cudaStream_t)stream>>>(z, (__nv_bfloat16*)zp, znorm2, N, D);
+  AMMC_LAUNCH_CHECK("pack_rows_bf16_kernel");
+  return 0;
+}
+
+extern "C" int ammc_addr_pack_bank(const float* embed, float* bank_t, float* en2, void* bank_hi, float* en2pad,
+                                   float* emax, int D, int M, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  AMMC_REQUIRE(embed && bank_t && en2 && bank_hi && en2pad && emax && D > 0 && M > 0, "bad argument");
+  const int Mpad = ammc_addr_padded_items(M);
+  bank_transpose_kernel<<<dim3(ceil_div(M, 32), ceil_div(D, 32)), dim3(32, 8), 0, st>>>(embed, bank_t, D, M);
+  AMMC_LAUNCH_CHECK("bank_transpose_kernel");
+  bank_norms_kernel<<<ceil_div(M, 128), 128, 0, st>>>(embed, en2, D, M);
+  AMMC_LAUNCH_CHECK("bank_norms_kernel");
+  AMMC_CUDA_CHECK(cudaMemsetAsync(emax, 0, 4, st));
+  bank_pack_kernel<<<Mpad, 128, 0, st>>>(bank_t, en2, (__nv_bfloat16*)bank_hi, en2pad, emax, D, M, Mpad);
+  AMMC_LAUNCH_CHECK("bank_pack_kernel");
+  return 0;
+}
+
+extern "C" int ammc_addr_filter(const void* zp, const float* znorm2, const void* bank_hi, const float* en2pad,
+                                const float* emax, int* cand, int* cand_cnt, int64_t N, int D, int M, int k,
+                                void* stream) {
+  AMMC_REQUIRE(zp && znorm2 && bank_hi && en2pad && emax && cand && cand_cnt, "null pointer argument");
+  if (!addr_tc_supported(N, D, M, k))
+    return fail(AMMC_EUNSUPPORTED, "tensor-core addressing needs D %% 64 == 0, 16 <= M <= 65536, k <= 4 (got D=%d M=%d k=%d)", D, M, k);
+  AMMC_REQUIRE(N < (1LL << 31), "N too large");
+  const int bn = addr_block_n(M);
+  AddrParams p;
+  p.N = (int)N; p.D = D; p.M = M; p.Mpad = ammc_addr_padded_items(M);
+  p.tiles_q = ceil_div(N, 128);
+  p.tiles_i = p.Mpad / bn;
+  p.en2pad = en2pad; p.znorm2 = znorm2; p.emax = emax; p.cand = cand; p.cand_cnt = cand_cnt;
+  return launch_filter(zp, bank_hi, p, bn, k, (cudaStream_t)stream);
+}

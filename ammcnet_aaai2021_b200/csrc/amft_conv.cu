@@ -300,6 +300,15 @@ static int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t
   return 0;
 }
 
+// [outer][inner] bf16 row-major matrix, 128B-swizzled boxes of box_outer rows x box_inner (=64) elements
+int make_map_2d_bf16(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, uint32_t box_inner,
+                     uint32_t box_outer) {
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {inner * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  return make_map(m, base, 2, dims, strides, box);
+}
+
 template <int BLOCK_N>
 static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvParams& p, cudaStream_t st) {
   using S = ConvSmem<BLOCK_N>;

@@ -17,6 +17,9 @@
 //   backward: gz_kernel, gx_kernel, genc_w_kernel, gdec_scatter_kernel, gdec_w_kernel
 //   ema_*                                     unet.py:298-309
 #include "common.cuh"
+#include "topk.cuh"
+#include "addr_tail.cuh"
+#include <cuda_bf16.h>
 #include <float.h>
 
 namespace ammc {
@@ -88,7 +91,7 @@ __global__ void dec_table_kernel(const float* __restrict__ dec_w, const float* _
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) enc1x1_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                       const float* __restrict__ bias, float* __restrict__ z,
-                                                      int N, int HW, int C, int D) {
+                                                      __nv_bfloat16* __restrict__ zp, int N, int HW, int C, int D) {
   __shared__ __align__(16) float Xs[16][64];
   __shared__ __align__(16) float Ws[16][68];
   const int t = threadIdx.x;
@@ -138,7 +141,11 @@ __global__ void __launch_bounds__(256) enc1x1_kernel(const float* __restrict__ x
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       int d = d0 + tx * 4 + j;
-      if (d < D) z[(size_t)n * D + d] = acc[i][j] + bias[d];
+      if (d < D) {
+        const float v = acc[i][j] + bias[d];
+        z[(size_t)n * D + d] = v;
+        if (zp) zp[(size_t)n * D + d] = __float2bfloat16_rn(v);   // operand of the tensor-core addressing filter
+      }
     }
   }
 }
@@ -146,31 +153,6 @@ __global__ void __launch_bounds__(256) enc1x1_kernel(const float* __restrict__ x
 // ------------------------------------------------------------------------------------------------
 // addressing: distances -> top-k -> gathers -> commit partials (+ EMA statistics)
 // ------------------------------------------------------------------------------------------------
-template <int K>
-struct TopK {
-  float v[K];
-  int id[K];
-  __device__ __forceinline__ void init() {
-#pragma unroll
-    for (int i = 0; i < K; ++i) { v[i] = INFINITY; id[i] = 0x7fffffff; }
-  }
-  // strict total order: smaller distance first, ties to the lower index
-  static __device__ __forceinline__ bool before(float a, int ia, float b, int ib) {
-    return a < b || (a == b && ia < ib);
-  }
-  __device__ __forceinline__ void insert(float d, int j) {
-    if (!before(d, j, v[K - 1], id[K - 1])) return;
-    v[K - 1] = d; id[K - 1] = j;
-#pragma unroll
-    for (int i = K - 1; i > 0; --i) {
-      if (before(v[i], id[i], v[i - 1], id[i - 1])) {
-        float tv = v[i]; v[i] = v[i - 1]; v[i - 1] = tv;
-        int ti = id[i]; id[i] = id[i - 1]; id[i - 1] = ti;
-      }
-    }
-  }
-};
-
 template <int K>
 __global__ void __launch_bounds__(256) address_kernel(
     const float* __restrict__ z, const float* __restrict__ embed, const float* __restrict__ en2,
@@ -190,13 +172,7 @@ __global__ void __launch_bounds__(256) address_kernel(
 
   // ||z||^2 per pixel
   {
-    float s = 0.f;
-    if (team_valid) {
-      const float* zr = z + (size_t)n_team * D;
-      for (int d = part; d < D; d += 4) { float v = zr[d]; s = fmaf(v, v, s); }
-    }
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    const float s = team_zn2(z + (size_t)(team_valid ? n_team : 0) * D, D, part, team_valid);
     if (part == 0) zn2_s[px] = s;
   }
   TopK<K> top;
@@ -238,7 +214,7 @@ __global__ void __launch_bounds__(256) address_kernel(
       float e2 = m < M ? en2[m] : 0.f;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        float dv = __fadd_rn(__fsub_rn(zn2_s[ty * 4 + i], 2.f * acc[i][j]), e2);
+        float dv = exact_dist(zn2_s[ty * 4 + i], acc[i][j], e2);
         Ds[ty * 4 + i][tx * 4 + j] = m < M ? dv : FLT_MAX;
       }
     }
@@ -264,37 +240,8 @@ __global__ void __launch_bounds__(256) address_kernel(
   // NaN distances (a diverged bank) never enter the list; keep the gathers in bounds regardless
 #pragma unroll
   for (int i = 0; i < K; ++i) top.id[i] = min(top.id[i], M - 1);
-  if (part == 0 && team_valid) {
-#pragma unroll
-    for (int i = 0; i < K; ++i) idx[(size_t)n_team * K + i] = (int64_t)top.id[i];
-  }
-  // gathers: every lane of the team holds the merged list
-  float sse = 0.f;
-  if (team_valid) {
-    const float* zr = z + (size_t)n_team * D;
-    const float* e1 = bank_t + (size_t)top.id[0] * D;
-    for (int d = part; d < D; d += 4) {
-      float zv = zr[d], ev = e1[d];
-      float df = ev - zv;
-      q1[(size_t)n_team * D + d] = zv + df;          // straight-through value, unet.py:311
-      sse = fmaf(df, df, sse);
-      if (embed_sum) atomicAdd(&embed_sum[(size_t)d * M + top.id[0]], zv);
-    }
-    if (read) {
-#pragma unroll
-      for (int i = 0; i < K; ++i) {
-        const float* er = bank_t + (size_t)top.id[i] * D;
-        float* rr = read + ((size_t)n_team * K + i) * D;
-        for (int d = part; d < D; d += 4) rr[d] = er[d];
-      }
-    }
-  }
-  sse += __shfl_xor_sync(0xffffffffu, sse, 1);
-  sse += __shfl_xor_sync(0xffffffffu, sse, 2);
-  if (part == 0 && team_valid) {
-    sse_px[n_team] = sse;
-    if (counts) atomicAdd(&counts[top.id[0]], 1.f);
-  }
+  team_emit_row<K>(z + (size_t)(team_valid ? n_team : 0) * D, bank_t, top.id, (int64_t)n_team, D, M, part, team_valid,
+                   read, q1, idx, sse_px, counts, embed_sum);
 }
 
 __global__ void sse_frame_kernel(const float* __restrict__ sse_px, float* __restrict__ sse_frame, int64_t rows) {
@@ -626,11 +573,26 @@ __global__ void gdec_w_kernel(const float* __restrict__ G, const float* __restri
 // host side
 // ------------------------------------------------------------------------------------------------
 struct MemWs {
-  float* bank_t; float* en2; float* T; float* sse_px;
+  int* stats; float* bank_t; float* en2; float* T; float* sse_px; __nv_bfloat16* zp;
 };
 
+// addr_tc.cu
+size_t addr_tc_ws_bytes(int64_t N, int D, int M);
+bool addr_tc_supported(int64_t N, int D, int M, int k);
+int run_address_tc(const float* z, const __nv_bfloat16* zp_in, const float* bank_t, const float* en2, float* read,
+                   float* q1, int64_t* idx, float* sse_px, float* counts, float* embed_sum, int* stats, Workspace& ws,
+                   int64_t N, int D, int M, int k, cudaStream_t st);
+
+static int g_addr_mode = 0;   // 0 auto, 1 generic fp32 (CUDA cores), 2 tensor-core filter + exact refine
+
+static bool use_tc(int64_t N, int D, int M, int k) {
+  if (g_addr_mode == 1) return false;
+  return addr_tc_supported(N, D, M, k);
+}
+
 static size_t mem_ws_bytes(int64_t N, int C, int D, int M, int k, bool with_table) {
-  size_t s = 0;
+  size_t s = 256;                                   // stats block: [0] exact-fallback rows, [1] path (1 fp32, 2 tensor)
+  s += addr_tc_ws_bytes(N, D, M);
   s += align_up((size_t)M * D * 4, 256);
   s += align_up((size_t)M * 4, 256);
   if (with_table) s += align_up((size_t)k * M * C * 4, 256);
@@ -639,6 +601,8 @@ static size_t mem_ws_bytes(int64_t N, int C, int D, int M, int k, bool with_tabl
 }
 
 static int carve(Workspace& ws, MemWs& m, int64_t N, int C, int D, int M, int k, bool with_table) {
+  m.stats = ws.take<int>(64);
+  m.zp = nullptr;
   m.bank_t = ws.take<float>((size_t)M * D);
   m.en2 = ws.take<float>(M);
   m.T = with_table ? ws.take<float>((size_t)k * M * C) : nullptr;
@@ -655,13 +619,22 @@ static void launch_address(const float* z, const float* embed, const MemWs& m, f
 }
 
 static int run_address(const float* z, const float* embed, const MemWs& m, float* read, float* q1, int64_t* idx,
-                       float* counts, float* embed_sum, int64_t N, int D, int M, int k, cudaStream_t st) {
+                       float* counts, float* embed_sum, int64_t N, int D, int M, int k, cudaStream_t st, Workspace& ws) {
+  AMMC_CUDA_CHECK(cudaMemsetAsync(m.stats, 0, 256, st));
   bank_transpose_kernel<<<dim3(ceil_div(M, 32), ceil_div(D, 32)), dim3(32, 8), 0, st>>>(embed, m.bank_t, D, M);
   AMMC_LAUNCH_CHECK("bank_transpose_kernel");
   bank_norms_kernel<<<ceil_div(M, 128), 128, 0, st>>>(embed, m.en2, D, M);
   AMMC_LAUNCH_CHECK("bank_norms_kernel");
   if (counts) AMMC_CUDA_CHECK(cudaMemsetAsync(counts, 0, (size_t)M * 4, st));
   if (embed_sum) AMMC_CUDA_CHECK(cudaMemsetAsync(embed_sum, 0, (size_t)D * M * 4, st));
+  if (g_addr_mode == 2 && !addr_tc_supported(N, D, M, k))
+    return fail(AMMC_EUNSUPPORTED, "tensor-core addressing needs D %% 64 == 0, M >= 16, k <= 4 (got D=%d M=%d k=%d)", D, M, k);
+  {
+    const int path = use_tc(N, D, M, k) ? 2 : 1;
+    AMMC_CUDA_CHECK(cudaMemsetAsync(m.stats + 1, path, 1, st));   // low byte of stats[1] (rest zeroed above)
+  }
+  if (use_tc(N, D, M, k))
+    return run_address_tc(z, m.zp, m.bank_t, m.en2, read, q1, idx, m.sse_px, counts, embed_sum, m.stats, ws, N, D, M, k, st);
   switch (k) {
     case 1: launch_address<1>(z, embed, m, read, q1, idx, counts, embed_sum, (int)N, D, M, st); break;
     case 2: launch_address<2>(z, embed, m, read, q1, idx, counts, embed_sum, (int)N, D, M, st); break;
@@ -690,6 +663,12 @@ static int run_commit(const MemWs& m, float* sse_frame, float* diff, int64_t N, 
 }  // namespace ammc
 
 using namespace ammc;
+
+extern "C" int ammc_set_addressing_mode(int mode) {
+  AMMC_REQUIRE(mode >= 0 && mode <= 2, "addressing mode must be 0 (auto), 1 (fp32 CUDA-core) or 2 (tensor-core)");
+  g_addr_mode = mode;
+  return 0;
+}
 
 extern "C" size_t ammc_mem_workspace_bytes(int b, int h, int w, int C, int D, int M, int k) {
   return mem_ws_bytes((int64_t)b * h * w, C, D, M, k, true);
@@ -723,9 +702,9 @@ extern "C" int ammc_mem_fwd(const float* x, const float* enc_w, const float* enc
   if (int rc = carve(ws, m, N, C, D, M, k, true)) return rc;
   dec_table_kernel<<<dim3(ceil_div(C, 32), ceil_div(M, 32), k), dim3(32, 8), 0, st>>>(dec_w, embed, m.T, C, D, M, k);
   AMMC_LAUNCH_CHECK("dec_table_kernel");
-  enc1x1_kernel<<<dim3(ceil_div(N, 64), ceil_div(D, 64)), 256, 0, st>>>(x, enc_w, enc_b, z, (int)N, HW, C, D);
+  enc1x1_kernel<<<dim3(ceil_div(N, 64), ceil_div(D, 64)), 256, 0, st>>>(x, enc_w, enc_b, z, m.zp, (int)N, HW, C, D);
   AMMC_LAUNCH_CHECK("enc1x1_kernel");
-  if (int rc = run_address(z, embed, m, nullptr, q1, idx, counts, embed_sum, N, D, M, k, st)) return rc;
+  if (int rc = run_address(z, embed, m, nullptr, q1, idx, counts, embed_sum, N, D, M, k, st, ws)) return rc;
   if (int rc = run_commit(m, sse_frame, diff, N, HW, D, st)) return rc;
   const int chunks = 4;
   dim3 grid(ceil_div(N, 32), ceil_div(ceil_div(C, 32), chunks));
@@ -753,7 +732,7 @@ extern "C" int ammc_quantize_fwd(const float* z, const float* embed, float* read
   Workspace ws(workspace, workspace_bytes);
   MemWs m;
   if (int rc = carve(ws, m, N, 0, D, M, k, false)) return rc;
-  if (int rc = run_address(z, embed, m, read, q1, idx, counts, embed_sum, N, D, M, k, st)) return rc;
+  if (int rc = run_address(z, embed, m, read, q1, idx, counts, embed_sum, N, D, M, k, st, ws)) return rc;
   return run_commit(m, sse_frame, diff, N, rows_per_frame, D, st);
 }
 

@@ -106,6 +106,22 @@ def mem_forward_raw(x, enc_w, enc_b, embed, dec_w, dec_b, k: int, residual: bool
     return dict(out=out, q1=q1, idx=idx, z=z, sse_frame=sse, diff=diff, counts=counts, embed_sum=esum, x=x)
 
 
+def set_addressing_mode(mode: str = "auto"):
+    """'auto' | 'fp32' (generic CUDA-core kernel) | 'tensor' (tcgen05 filter + exact refine); process-wide."""
+    _capi.call("ammc_set_addressing_mode", {"auto": 0, "fp32": 1, "tensor": 2}[mode])
+
+
+def last_addressing_stats(device=None):
+    """(rows that needed the exact re-scan, path used: 1 = fp32 kernel, 2 = tensor-core filter) of the last memory /
+    Quantize_topk forward issued on the current stream of `device`.  Synchronises."""
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    ws = _workspaces.get((device.index, torch.cuda.current_stream(device).cuda_stream))
+    if ws is None:
+        return None
+    st = ws[:8].view(torch.int32).cpu()
+    return int(st[0]), int(st[1])
+
+
 class MemoryModuleFn(torch.autograd.Function):
     """enc 1x1 -> top-k addressing -> read -> dec 1x1 (+ residual); reference Code/models/unet.py:325-331,384-387.
 

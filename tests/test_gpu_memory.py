@@ -179,3 +179,79 @@ def test_full_size_properties():
         assert bool((chosen <= d_all.min(1)[0] * (1 + 1e-4) + 1e-4).all())
         exact = (idx[:, 0] == d_all.argmin(1)).float().mean().item()
         assert exact > 0.999, "top-1 agreement with the fp64 ranking %.5f" % exact
+
+
+# --------------------------------------------------------------------------------------------------
+# tensor-core addressing (tcgen05 bf16 filter + exact fp32 refine) must be bit-identical to the fp32 kernel
+# --------------------------------------------------------------------------------------------------
+from ammcnet_aaai2021_b200 import functions as F_   # noqa: E402
+
+
+@pytest.fixture
+def addressing_mode():
+    yield F_.set_addressing_mode
+    F_.set_addressing_mode("auto")
+
+
+def _quantize_both(z, embed, k, addressing_mode):
+    outs = {}
+    for mode in ("fp32", "tensor"):
+        addressing_mode(mode)
+        q = A.Quantize_topk(embed.shape[0], embed.shape[1], k=k).to(DEV).eval()
+        q.embed.copy_(embed)
+        with torch.no_grad():
+            read, diff, q1 = q(z)
+        stats = F_.last_addressing_stats()
+        outs[mode] = (q.last_idx.clone(), read.clone(), diff.clone(), q1.clone(), q.last_sse_frame.clone(), stats)
+    return outs
+
+
+@pytest.mark.parametrize("N,D,M,k", [(4096, 64, 256, 2), (1000, 64, 16, 1), (777, 128, 100, 3), (2048, 256, 1000, 4),
+                                      (130, 64, 2000, 2), (4096, 512, 300, 2), (65536, 64, 256, 2)])
+def test_tensor_path_bit_identical_to_fp32_path(N, D, M, k, addressing_mode):
+    g = torch.Generator().manual_seed(N + D + M)
+    z = torch.randn((1, N, 1, D), generator=g).to(DEV)
+    embed = torch.randn((D, M), generator=g).to(DEV)
+    o = _quantize_both(z, embed, k, addressing_mode)
+    a, b = o["fp32"], o["tensor"]
+    assert a[5][1] == 1 and b[5][1] == 2, "paths actually taken: %s %s" % (a[5], b[5])
+    assert torch.equal(a[0], b[0]), "indices differ between the fp32 and the tensor-core path"
+    assert torch.equal(a[1], b[1]) and torch.equal(a[3], b[3]) and torch.equal(a[4], b[4]) and torch.equal(a[2], b[2])
+    assert b[5][0] <= 0.05 * N + 4, "too many queries needed the exact re-scan: %d of %d" % (b[5][0], N)
+
+
+def test_tensor_path_adversarial_banks(addressing_mode):
+    """Near-duplicate items, queries sitting on items, huge norms: the miss test must route these to the exact re-scan."""
+    g = torch.Generator().manual_seed(3)
+    D, M, N, k = 64, 256, 3000, 2
+    base = torch.randn((D, 16), generator=g)
+    embed = base.repeat(1, 16) + 1e-3 * torch.randn((D, M), generator=g)      # 16 clusters of 16 near-duplicates
+    embed[:, 5] = embed[:, 4]                                                  # exact duplicate -> index tie-break
+    z = embed.t()[torch.randint(0, M, (N,), generator=g)] + 1e-4 * torch.randn((N, D), generator=g)
+    z[:100] *= 1e3
+    o = _quantize_both(z.view(1, N, 1, D).to(DEV), embed.to(DEV), k, addressing_mode)
+    assert torch.equal(o["fp32"][0], o["tensor"][0])
+    assert torch.equal(o["fp32"][1], o["tensor"][1])
+    print("adversarial bank: exact re-scans", o["tensor"][5][0], "of", N)
+
+
+def test_shipped_module_uses_tensor_path_and_matches_golden(addressing_mode):
+    c, g = load_golden("mem_shipped")
+    p, x = _inputs(c)
+    res = {}
+    for mode in ("fp32", "tensor", "auto"):
+        addressing_mode(mode)
+        m = _module(c, p).eval()
+        with torch.no_grad():
+            out, diff, q1 = m(x.to(DEV))
+        res[mode] = (m.quan.quantize.last_idx.clone(), out.clone(), diff.clone(), F_.last_addressing_stats())
+    assert res["auto"][3][1] == 2 and res["fp32"][3][1] == 1
+    for mode in ("tensor", "auto"):
+        assert torch.equal(res[mode][0], res["fp32"][0]) and torch.equal(res[mode][1], res["fp32"][1])
+        assert torch.equal(res[mode][2], res["fp32"][2])
+    keep = _no_tie_rows(g["dist_sorted"])
+    assert torch.equal(res["tensor"][0].cpu()[keep], torch.as_tensor(g["idx_topk"], dtype=torch.int64)[keep])
+    with pytest.raises(RuntimeError, match="tensor-core addressing"):
+        addressing_mode("tensor")
+        q = A.Quantize_topk(32, 50, k=3).to(DEV).eval()
+        q(torch.zeros(1, 4, 4, 32, device=DEV))
