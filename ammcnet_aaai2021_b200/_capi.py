@@ -19,6 +19,8 @@ SIGNATURES = {
     "ammc_version": (I, []),
     "ammc_last_error": (c_char_p, []),
     "ammc_device_supported": (I, []),
+    "ammc_debug_timeout": (I, [P]),
+    "ammc_debug_tma_probe": (I, [P, P, P, P, P, P, I, P]),
     "ammc_mem_workspace_bytes": (Z, [I] * 7),
     "ammc_set_addressing_mode": (I, [I]),
     "ammc_mem_fwd": (I, [P] * 6 + [P] * 6 + [P, P] + [P, Z] + [I] * 8 + [P]),
@@ -39,6 +41,12 @@ SIGNATURES = {
     "ammc_conv3x3_bn_relu": (I, [P] * 7 + [I] * 7 + [P]),
     "ammc_pack_conv_weights_1x1": (I, [P, P, I, I, P]),
     "ammc_conv1x1_bn_relu": (I, [P] * 7 + [I] * 7 + [P]),
+    "ammc_bn_batch_stats": (I, [P] * 9 + [P, Z] + [I, I, I, I, F, F, I, P]),
+    "ammc_bn_apply": (I, [P, P, P, I, P, P, P, P, I, I, I, I, P]),
+    "ammc_bn_backward": (I, [P] * 6 + [I, I] + [P] * 4 + [P, Z] + [I, I, I, I, P]),
+    "ammc_pack_planes": (I, [P, P, L, P]),
+    "ammc_pack_conv_weights_dgrad": (I, [P, P, I, I, P]),
+    "ammc_conv3x3_wgrad": (I, [P, P, P, I, I, I, I, I, I, P]),
     "ammc_bn_fold": (I, [P] * 4 + [F] + [P, P, I, P]),
     "ammc_psnr_workspace_bytes": (Z, [I, L]),
     "ammc_psnr_batch": (I, [P, P, P, P, Z, I, L, P]),

@@ -500,6 +500,8 @@ __global__ void bank_norms_kernel(const float* __restrict__ embed, float* __rest
 
 }  // namespace ammc
 
+namespace ammc { AMMC_DEFINE_TIMEOUT_READER(timeout_reader_addr) }
+
 using namespace ammc;
 
 // ---- staged entry points (what ammc_quantize_fwd / ammc_mem_fwd compose internally; used by the cfg5 microbench) ----

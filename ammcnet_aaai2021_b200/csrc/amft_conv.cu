@@ -300,6 +300,15 @@ static int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t
   return 0;
 }
 
+int make_map_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
+                  const uint32_t* box) {
+  cuuint64_t d[5], s[4];
+  cuuint32_t bx[5];
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; bx[i] = box[i]; }
+  for (int i = 0; i + 1 < rank; ++i) s[i] = strides[i];
+  return make_map(m, base, rank, d, s, bx);
+}
+
 // [outer][inner] bf16 row-major matrix, 128B-swizzled boxes of box_outer rows x box_inner (=64) elements
 int make_map_2d_bf16(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, uint32_t box_inner,
                      uint32_t box_outer) {
@@ -382,6 +391,8 @@ int conv_igemm(const void* xp, const void* wp, const float* scale, const float* 
 }
 
 }  // namespace ammc
+
+namespace ammc { AMMC_DEFINE_TIMEOUT_READER(timeout_reader_conv) }
 
 using namespace ammc;
 

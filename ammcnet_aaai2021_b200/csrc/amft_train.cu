@@ -1,0 +1,581 @@
+// AMFT training path: batch-statistic BatchNorm (forward + backward through ReLU) and the convolution weight gradient
+// on tcgen05.  Together with conv_igemm_kernel (forward and, with flipped/transposed weights, the data gradient) this is
+// the autograd of reference Code/models/unet.py:8-20,956-965.
+//
+//   bn_stats_kernel        per-channel sum / sum of squares of a NCHW fp32 tensor (fp64 accumulation)
+//   bn_finalize_kernel     mean, biased var -> scale = gamma*invstd, shift = beta - mean*scale; running stats (momentum,
+//                          unbiased var) exactly as torch.nn.BatchNorm2d in training mode
+//   bn_apply_pack_kernel   v = relu(y*scale + shift)  ->  NHWC bf16 hi/lo planes (next conv's A operand),
+//                          NCHW bf16 hi/lo planes (wgrad operand) and/or fp32 NCHW (+ residual)
+//   bn_bwd_reduce_kernel   sum g', sum g'*yhat  with g' = g * 1[relu active], yhat = (y - mean) * invstd
+//   bn_bwd_apply_kernel    g_y = scale * (g' - mean(g') - yhat * mean(g' yhat))   (training)   or   scale * g' (eval BN)
+//                          -> NHWC + NCHW bf16 planes; g_gamma, g_beta
+//   conv_wgrad_kernel      gW[co][ci][tap] = sum_pixels gy[p][co] * x[p + tap][ci]:  GEMM with M = Cout (128/tile),
+//                          N = Cin (256/tile), K = pixels (64 per block).  Both operands are the NHWC bf16 planes the
+//                          forward/backward pipeline already holds; a [pixels][64 channels] TMA box is an MN-major UMMA
+//                          operand (channels contiguous), so nothing is transposed.  The tap shift is a TMA box offset on
+//                          the (w,h) axes with zero fill, like the forward conv.  (Pixel-contiguous NCHW operands are not
+//                          usable: TMA needs a 128-byte inner box and 16-byte aligned inner coordinates -- measured.)
+//                          Split-K over images, fp32 atomics into gW.
+#include "common.cuh"
+#include "ptx.cuh"
+#include <cuda_bf16.h>
+
+namespace ammc {
+
+__device__ __forceinline__ void split_bf16_t(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(v);
+  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+// ------------------------------------------------------------------------------------------------
+// BatchNorm forward statistics
+// ------------------------------------------------------------------------------------------------
+// grid (C, splits); block 256.  sums[c] += sum y, sums[C + c] += sum y^2 over the images of this split
+__global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ y, double* __restrict__ sums, int b, int C,
+                                                        int hw, int imgs_per_split) {
+  __shared__ double red[2][8];
+  const int c = blockIdx.x;
+  const int i0 = blockIdx.y * imgs_per_split, i1 = min(b, i0 + imgs_per_split);
+  double s = 0.0, s2 = 0.0;
+  for (int img = i0; img < i1; ++img) {
+    const float* p = y + ((size_t)img * C + c) * hw;
+    float fs = 0.f, fs2 = 0.f;
+    for (int i = threadIdx.x; i < hw; i += 256) { const float v = p[i]; fs += v; fs2 = fmaf(v, v, fs2); }
+    s += (double)fs; s2 += (double)fs2;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) { red[0][wid] = s; red[1][wid] = s2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, a2 = 0.0;
+    for (int i = 0; i < 8; ++i) { a += red[0][i]; a2 += red[1][i]; }
+    atomicAdd(&sums[c], a);
+    atomicAdd(&sums[C + c], a2);
+  }
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var, float* __restrict__ scale, float* __restrict__ shift,
+                                   float* __restrict__ mean_out, float* __restrict__ invstd_out, int C, double count,
+                                   float momentum, float eps, int update_running) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double mean = sums[c] / count;
+  double var = sums[C + c] / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float sc = gamma[c] * invstd;
+  scale[c] = sc;
+  shift[c] = beta[c] - (float)mean * sc;
+  mean_out[c] = (float)mean;
+  invstd_out[c] = invstd;
+  if (update_running) {
+    const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+  }
+}
+
+// eval-mode BN expressed with the same (scale, shift, mean, invstd) quadruple
+__global__ void bn_eval_params_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                                      const float* __restrict__ running_mean, const float* __restrict__ running_var,
+                                      float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
+                                      float* __restrict__ invstd_out, int C, float eps) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float invstd = 1.f / sqrtf(running_var[c] + eps);
+  const float sc = gamma[c] * invstd;
+  scale[c] = sc;
+  shift[c] = beta[c] - running_mean[c] * sc;
+  mean_out[c] = running_mean[c];
+  invstd_out[c] = invstd;
+}
+
+// ------------------------------------------------------------------------------------------------
+// elementwise transforms with layout change: 32 (channels) x 32 (pixels) tiles through shared memory
+// ------------------------------------------------------------------------------------------------
+struct ApplyArgs {
+  const float* y;          // [b][C][hw] fp32
+  const float* g;          // gradient wrt the ReLU output (backward only) or null
+  const float* scale; const float* shift; const float* mean; const float* invstd;
+  const double* bsums;     // backward: [2][C] sum g', sum g' yhat
+  double inv_count;        // 1 / (b*hw)
+  int mode;                // 0: forward v = act(y*scale+shift); 1: backward (training BN); 2: backward (eval BN)
+  int relu;
+  __nv_bfloat16* nhwc;     // [2][b][hw][C] or null
+  __nv_bfloat16* nchw;     // [2][b][C][hw] or null
+  float* out_f32;          // [b][C][hw] or null
+  const float* res;        // added to out_f32, or null
+  long long plane_stride;
+};
+
+__global__ void __launch_bounds__(256) bn_apply_pack_kernel(const ApplyArgs a, int C, int HW) {
+  __shared__ float tile[32][33];
+  const int img = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int r = ty; r < 32; r += 8) {
+    const int c = c0 + r, pp = p0 + tx;
+    float v = 0.f;
+    if (c < C && pp < HW) {
+      const size_t o = ((size_t)img * C + c) * HW + pp;
+      const float yv = a.y[o];
+      const float act = fmaf(yv, a.scale[c], a.shift[c]);
+      if (a.mode == 0) {
+        v = a.relu ? fmaxf(act, 0.f) : act;
+      } else {
+        float gp = a.g[o];
+        if (a.relu && !(act > 0.f)) gp = 0.f;
+        if (a.mode == 1) {
+          const float yhat = (yv - a.mean[c]) * a.invstd[c];
+          const float mg = (float)(a.bsums[c] * a.inv_count), mgy = (float)(a.bsums[C + c] * a.inv_count);
+          v = a.scale[c] * (gp - mg - yhat * mgy);
+        } else {
+          v = a.scale[c] * gp;
+        }
+      }
+      if (a.out_f32) a.out_f32[o] = a.res ? v + a.res[o] : v;
+      if (a.nchw) {
+        __nv_bfloat16 hi, lo;
+        split_bf16_t(v, hi, lo);
+        a.nchw[o] = hi;
+        a.nchw[o + a.plane_stride] = lo;
+      }
+    }
+    tile[r][tx] = v;
+  }
+  if (!a.nhwc) return;
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int pp = p0 + r, c = c0 + tx;
+    if (pp < HW && c < C) {
+      __nv_bfloat16 hi, lo;
+      split_bf16_t(tile[tx][r], hi, lo);
+      const size_t o = ((size_t)img * HW + pp) * C + c;
+      a.nhwc[o] = hi;
+      a.nhwc[o + a.plane_stride] = lo;
+    }
+  }
+}
+
+// sums[c] += sum g', sums[C+c] += sum g' * yhat
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restrict__ g, const float* __restrict__ y,
+                                                             const float* __restrict__ scale, const float* __restrict__ shift,
+                                                             const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                             int relu, double* __restrict__ sums, int b, int C, int hw,
+                                                             int imgs_per_split) {
+  __shared__ double red[2][8];
+  const int c = blockIdx.x;
+  const int i0 = blockIdx.y * imgs_per_split, i1 = min(b, i0 + imgs_per_split);
+  const float sc = scale[c], sh = shift[c], mu = mean[c], is = invstd[c];
+  double s = 0.0, s2 = 0.0;
+  for (int img = i0; img < i1; ++img) {
+    const size_t base = ((size_t)img * C + c) * hw;
+    float fs = 0.f, fs2 = 0.f;
+    for (int i = threadIdx.x; i < hw; i += 256) {
+      const float yv = y[base + i];
+      float gp = g[base + i];
+      if (relu && !(fmaf(yv, sc, sh) > 0.f)) gp = 0.f;
+      fs += gp;
+      fs2 = fmaf(gp, (yv - mu) * is, fs2);
+    }
+    s += (double)fs; s2 += (double)fs2;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) { red[0][wid] = s; red[1][wid] = s2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, a2 = 0.0;
+    for (int i = 0; i < 8; ++i) { a += red[0][i]; a2 += red[1][i]; }
+    atomicAdd(&sums[c], a);
+    atomicAdd(&sums[C + c], a2);
+  }
+}
+
+__global__ void bn_param_grads_kernel(const double* __restrict__ sums, float* __restrict__ g_gamma,
+                                      float* __restrict__ g_beta, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  g_beta[c] = (float)sums[c];
+  g_gamma[c] = (float)sums[C + c];
+}
+
+// x fp32 (any layout) -> same layout bf16 hi/lo planes
+__global__ void pack_planes_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ xp, long long total) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  __nv_bfloat16 hi, lo;
+  split_bf16_t(x[e], hi, lo);
+  xp[e] = hi;
+  xp[e + total] = lo;
+}
+
+// w [Cout][Cin][3][3] -> wp [2][Cin][9*Cout] with k = tap'*Cout + co holding w[co][ci][8 - tap']  (data-gradient conv)
+__global__ void pack_weights_dgrad_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp, int Cout, int Cin) {
+  const long long total = (long long)Cout * Cin * 9;
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int co = (int)(e % Cout);
+  const int tp = (int)((e / Cout) % 9);
+  const int ci = (int)(e / ((long long)Cout * 9));
+  __nv_bfloat16 hi, lo;
+  split_bf16_t(w[((size_t)co * Cin + ci) * 9 + (8 - tp)], hi, lo);
+  wp[e] = hi;
+  wp[e + total] = lo;
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight gradient on tcgen05
+// ------------------------------------------------------------------------------------------------
+constexpr int WG_THREADS = 192;
+constexpr int WG_BLOCK_M = 128;   // output channels  (2 boxes of 64)
+constexpr int WG_BLOCK_N = 256;   // input channels   (4 boxes of 64)
+constexpr int WG_BLOCK_K = 64;    // pixels per pipeline stage
+constexpr int WG_BOX_BYTES = WG_BLOCK_K * 64 * 2;          // [64 px][64 ch] bf16 = 8 KB
+constexpr int WG_A_BYTES = (WG_BLOCK_M / 64) * WG_BOX_BYTES;
+constexpr int WG_B_BYTES = (WG_BLOCK_N / 64) * WG_BOX_BYTES;
+constexpr int WG_STAGE_BYTES = WG_A_BYTES + WG_B_BYTES;    // 48 KB
+constexpr int WG_STAGES = 4;
+constexpr int WG_BAR_OFFSET = WG_STAGES * WG_STAGE_BYTES;
+constexpr int WG_SMEM = WG_BAR_OFFSET + 256 + 1024;
+
+struct WgradParams {
+  int b, H, W, Cin, Cout;
+  int rows_per_kb;          // 64 / W
+  int kb_per_img;           // H*W / 64
+  int tiles_m, tiles_n, splits, imgs_per_split;
+  int n_pass, pass_a[3], pass_b[3];
+  int block_n;              // input channels actually present in an N tile (Cin may be < 256)
+  float* gw;                // [Cout][Cin][9]
+};
+
+__global__ void __launch_bounds__(WG_THREADS, 1)
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + WG_BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + WG_STAGES;
+  uint64_t* tmem_full = empty_bar + WG_STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int work_items = p.tiles_m * p.tiles_n * 9 * p.splits;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tmA);
+    ptx::prefetch_tensormap(&tmB);
+    for (int s = 0; s < WG_STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tmem_full[a], 1); ptx::mbar_init(&tmem_empty[a], 128); }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, 2 * WG_BLOCK_N);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // work item -> (split, tap, n tile, m tile).  NOTE: no by-reference lambdas in this kernel -- capturing the kernel
+  // parameters moves the __grid_constant__ tensor maps to the local stack, and TMA cannot read a descriptor from there.
+  const int tiles_m = p.tiles_m, tiles_n = p.tiles_n;
+#define WG_DECODE(wi_, mt_, nt_, tap_, sp_)            \
+  int mt_, nt_, tap_, sp_;                             \
+  {                                                    \
+    int w_ = (wi_);                                    \
+    mt_ = w_ % tiles_m; w_ /= tiles_m;                 \
+    nt_ = w_ % tiles_n; w_ /= tiles_n;                 \
+    tap_ = w_ % 9;      sp_ = w_ / 9;                  \
+  }
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int wi = blockIdx.x; wi < work_items; wi += gridDim.x) {
+        WG_DECODE(wi, mt, nt, tap, sp)
+        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+        const int i0 = sp * p.imgs_per_split, i1 = min(p.b, i0 + p.imgs_per_split);
+        for (int ps = 0; ps < p.n_pass; ++ps) {
+          const int pa = p.pass_a[ps], pb = p.pass_b[ps];
+          for (int img = i0; img < i1; ++img) {
+            for (int kb = 0; kb < p.kb_per_img; ++kb) {
+              const int h0 = kb * p.rows_per_kb;
+              ptx::mbar_wait(&empty_bar[s], ph ^ 1, 21);
+              ptx::mbar_expect_tx(&full_bar[s], WG_STAGE_BYTES);
+              uint8_t* dst = smem + s * WG_STAGE_BYTES;
+#pragma unroll
+              for (int i = 0; i < WG_BLOCK_M / 64; ++i)
+                ptx::tma_load_5d(dst + i * WG_BOX_BYTES, &tmA, &full_bar[s], mt * WG_BLOCK_M + i * 64, 0, h0, img, pa);
+#pragma unroll
+              for (int i = 0; i < WG_BLOCK_N / 64; ++i)
+                ptx::tma_load_5d(dst + WG_A_BYTES + i * WG_BOX_BYTES, &tmB, &full_bar[s], nt * WG_BLOCK_N + i * 64, dx,
+                                 h0 + dy, img, pb);
+              if (++s == WG_STAGES) { s = 0; ph ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc_mn(1, WG_BLOCK_M, WG_BLOCK_N);
+      int s = 0; uint32_t ph = 0;
+      int it = 0;
+      for (int wi = blockIdx.x; wi < work_items; wi += gridDim.x, ++it) {
+        WG_DECODE(wi, mt, nt, tap, sp)
+        (void)mt; (void)nt; (void)tap;
+        const int i0 = sp * p.imgs_per_split, i1 = min(p.b, i0 + p.imgs_per_split);
+        const int kb_total = p.n_pass * (i1 - i0) * p.kb_per_img;
+        const int acc = it & 1;
+        const uint32_t acc_ph = (it >> 1) & 1;
+        ptx::mbar_wait(&tmem_empty[acc], acc_ph ^ 1, 22);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * WG_BLOCK_N;
+        for (int kb = 0; kb < kb_total; ++kb) {
+          ptx::mbar_wait(&full_bar[s], ph, 23);
+          ptx::tc_fence_after();
+          const uint32_t a_addr = ptx::smem_u32(smem + s * WG_STAGE_BYTES);
+          const uint64_t adesc = ptx::umma_desc_mn_sw128(a_addr, WG_BOX_BYTES);
+          const uint64_t bdesc = ptx::umma_desc_mn_sw128(a_addr + WG_A_BYTES, WG_BOX_BYTES);
+#pragma unroll
+          for (int k4 = 0; k4 < WG_BLOCK_K / 16; ++k4) {
+            // 16 pixels (K) = 16 rows of 128 B = 2048 B further down each box: +128 in the (>>4) address field
+            ptx::mma_f16_ss(d_tmem, adesc + 128 * k4, bdesc + 128 * k4, idesc, (kb | k4) != 0 ? 1u : 0u);
+          }
+          ptx::mma_commit(&empty_bar[s]);
+          if (kb == kb_total - 1) ptx::mma_commit(&tmem_full[acc]);
+          if (++s == WG_STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;                 // accumulator row = output channel within the tile
+    int it = 0;
+    for (int wi = blockIdx.x; wi < work_items; wi += gridDim.x, ++it) {
+      WG_DECODE(wi, mt, nt, tap, sp)
+      (void)sp;
+      const int acc = it & 1;
+      const uint32_t acc_ph = (it >> 1) & 1;
+      const int co = mt * WG_BLOCK_M + r;
+      ptx::mbar_wait(&tmem_full[acc], acc_ph, 24);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * WG_BLOCK_N;
+#pragma unroll 1
+      for (int c32 = 0; c32 < WG_BLOCK_N / 32; ++c32) {
+        if (c32 * 32 >= p.block_n) break;        // uniform: Cin tile narrower than 256
+        uint32_t v[32];
+        ptx::tmem_ld_32x32(taddr + c32 * 32, v);
+        ptx::tmem_ld_wait();
+        if (co < p.Cout) {
+          const int ci0 = nt * WG_BLOCK_N + c32 * 32;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (ci0 + j < p.Cin) atomicAdd(&p.gw[((size_t)co * p.Cin + ci0 + j) * 9 + tap], __uint_as_float(v[j]));
+        }
+      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+#undef WG_DECODE
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 2 * WG_BLOCK_N);
+  }
+}
+
+int make_map_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
+                  const uint32_t* box);   // amft_conv.cu
+
+// Debug: load ONE 5-D box into shared memory with TMA and dump the raw bytes (layout / fault investigations).
+__global__ void tma_probe_kernel(const __grid_constant__ CUtensorMap tm, int c0, int c1, int c2, int c3, int c4,
+                                 uint32_t box_bytes, uint8_t* out, uint32_t out_bytes) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + out_bytes);
+  for (uint32_t i = threadIdx.x; i < out_bytes; i += blockDim.x) smem[i] = 0xEE;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ptx::mbar_init(bar, 1);
+    ptx::fence_mbar_init();
+    ptx::fence_proxy_async();
+    ptx::mbar_expect_tx(bar, box_bytes);
+    ptx::tma_load_5d(smem, &tm, bar, c0, c1, c2, c3, c4);
+    ptx::mbar_wait(bar, 0, 31);
+  }
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < out_bytes; i += blockDim.x) out[i] = smem[i];
+}
+
+}  // namespace ammc
+
+namespace ammc { AMMC_DEFINE_TIMEOUT_READER(timeout_reader_train) }
+
+using namespace ammc;
+
+extern "C" int ammc_debug_tma_probe(const void* base, const int64_t* dims5, const int64_t* strides4_bytes,
+                                    const int* box5, const int* coords5, void* out, int out_bytes, void* stream) {
+  uint64_t d[5], s[4];
+  uint32_t bx[5];
+  uint64_t box_elems = 1;
+  for (int i = 0; i < 5; ++i) { d[i] = (uint64_t)dims5[i]; bx[i] = (uint32_t)box5[i]; box_elems *= bx[i]; }
+  for (int i = 0; i < 4; ++i) s[i] = (uint64_t)strides4_bytes[i];
+  CUtensorMap tm;
+  if (int rc = make_map_bf16(&tm, base, 5, d, s, bx)) return rc;
+  AMMC_REQUIRE(out_bytes >= (int)(box_elems * 2) && out_bytes <= 200 * 1024, "bad out_bytes");
+  AMMC_CUDA_CHECK(cudaFuncSetAttribute(tma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, out_bytes + 2048));
+  tma_probe_kernel<<<1, 128, out_bytes + 2048, (cudaStream_t)stream>>>(tm, coords5[0], coords5[1], coords5[2], coords5[3],
+                                                                        coords5[4], (uint32_t)(box_elems * 2),
+                                                                        (uint8_t*)out, (uint32_t)out_bytes);
+  AMMC_LAUNCH_CHECK("tma_probe_kernel");
+  return 0;
+}
+
+extern "C" int ammc_bn_batch_stats(const float* y, const float* gamma, const float* beta, float* running_mean,
+                                   float* running_var, float* scale, float* shift, float* mean, float* invstd,
+                                   void* workspace, size_t workspace_bytes, int b, int C, int h, int w, float momentum,
+                                   float eps, int training, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  AMMC_REQUIRE(gamma && beta && running_mean && running_var && scale && shift && mean && invstd && C > 0, "bad argument");
+  if (!training) {
+    bn_eval_params_kernel<<<ceil_div(C, 128), 128, 0, st>>>(gamma, beta, running_mean, running_var, scale, shift, mean,
+                                                            invstd, C, eps);
+    AMMC_LAUNCH_CHECK("bn_eval_params_kernel");
+    return 0;
+  }
+  AMMC_REQUIRE(y && b > 0 && h > 0 && w > 0, "bad argument");
+  if (!workspace || workspace_bytes < (size_t)2 * C * sizeof(double)) return fail(AMMC_EWORKSPACE, "workspace too small");
+  double* sums = (double*)workspace;
+  AMMC_CUDA_CHECK(cudaMemsetAsync(sums, 0, (size_t)2 * C * sizeof(double), st));
+  const int splits = max(1, min(b, ceil_div(4 * num_sms(), C)));
+  const int per = ceil_div(b, splits);
+  bn_stats_kernel<<<dim3(C, ceil_div(b, per)), 256, 0, st>>>(y, sums, b, C, h * w, per);
+  AMMC_LAUNCH_CHECK("bn_stats_kernel");
+  bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(sums, gamma, beta, running_mean, running_var, scale, shift, mean,
+                                                       invstd, C, (double)b * h * w, momentum, eps, 1);
+  AMMC_LAUNCH_CHECK("bn_finalize_kernel");
+  return 0;
+}
+
+static int launch_apply(const ApplyArgs& a, int b, int C, int h, int w, cudaStream_t st) {
+  AMMC_REQUIRE(b <= 65535, "batch %d too large for one launch", b);
+  const int HW = h * w;
+  bn_apply_pack_kernel<<<dim3(ceil_div(HW, 32), ceil_div(C, 32), b), 256, 0, st>>>(a, C, HW);
+  AMMC_LAUNCH_CHECK("bn_apply_pack_kernel");
+  return 0;
+}
+
+extern "C" int ammc_bn_apply(const float* y, const float* scale, const float* shift, int relu, void* out_nhwc_planes,
+                             void* out_nchw_planes, float* out_f32, const float* res, int b, int C, int h, int w,
+                             void* stream) {
+  AMMC_REQUIRE(y && scale && shift && (out_nhwc_planes || out_nchw_planes || out_f32), "bad argument");
+  ApplyArgs a{};
+  a.y = y; a.scale = scale; a.shift = shift; a.mode = 0; a.relu = relu;
+  a.nhwc = (__nv_bfloat16*)out_nhwc_planes; a.nchw = (__nv_bfloat16*)out_nchw_planes; a.out_f32 = out_f32; a.res = res;
+  a.plane_stride = (long long)b * C * h * w;
+  return launch_apply(a, b, C, h, w, (cudaStream_t)stream);
+}
+
+extern "C" int ammc_bn_backward(const float* g, const float* y, const float* scale, const float* shift, const float* mean,
+                                const float* invstd, int relu, int training, void* gy_nhwc_planes, void* gy_nchw_planes,
+                                float* g_gamma, float* g_beta, void* workspace, size_t workspace_bytes, int b, int C, int h,
+                                int w, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  AMMC_REQUIRE(g && y && scale && shift && mean && invstd && g_gamma && g_beta && (gy_nhwc_planes || gy_nchw_planes),
+               "bad argument");
+  if (!workspace || workspace_bytes < (size_t)2 * C * sizeof(double)) return fail(AMMC_EWORKSPACE, "workspace too small");
+  double* sums = (double*)workspace;
+  AMMC_CUDA_CHECK(cudaMemsetAsync(sums, 0, (size_t)2 * C * sizeof(double), st));
+  const int splits = max(1, min(b, ceil_div(4 * num_sms(), C)));
+  const int per = ceil_div(b, splits);
+  bn_bwd_reduce_kernel<<<dim3(C, ceil_div(b, per)), 256, 0, st>>>(g, y, scale, shift, mean, invstd, relu, sums, b, C, h * w,
+                                                                  per);
+  AMMC_LAUNCH_CHECK("bn_bwd_reduce_kernel");
+  bn_param_grads_kernel<<<ceil_div(C, 128), 128, 0, st>>>(sums, g_gamma, g_beta, C);
+  AMMC_LAUNCH_CHECK("bn_param_grads_kernel");
+  ApplyArgs a{};
+  a.y = y; a.g = g; a.scale = scale; a.shift = shift; a.mean = mean; a.invstd = invstd; a.bsums = sums;
+  a.inv_count = 1.0 / ((double)b * h * w);
+  a.mode = training ? 1 : 2; a.relu = relu;
+  a.nhwc = (__nv_bfloat16*)gy_nhwc_planes; a.nchw = (__nv_bfloat16*)gy_nchw_planes;
+  a.plane_stride = (long long)b * C * h * w;
+  return launch_apply(a, b, C, h, w, st);
+}
+
+extern "C" int ammc_pack_planes(const float* x, void* xp, int64_t n, void* stream) {
+  AMMC_REQUIRE(x && xp && n > 0, "bad argument");
+  pack_planes_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)xp, n);
+  AMMC_LAUNCH_CHECK("pack_planes_kernel");
+  return 0;
+}
+
+extern "C" int ammc_pack_conv_weights_dgrad(const float* w, void* wp, int Cout, int Cin, void* stream) {
+  AMMC_REQUIRE(w && wp && Cout > 0 && Cin > 0, "bad argument");
+  const long long total = (long long)Cout * Cin * 9;
+  pack_weights_dgrad_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)wp, Cout, Cin);
+  AMMC_LAUNCH_CHECK("pack_weights_dgrad_kernel");
+  return 0;
+}
+
+extern "C" int ammc_conv3x3_wgrad(const void* gy_nhwc_planes, const void* x_nhwc_planes, float* gw, int b, int Cin,
+                                  int Cout, int h, int w, int precision, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  AMMC_REQUIRE(gy_nhwc_planes && x_nhwc_planes && gw && b > 0, "bad argument");
+  if (precision != 1 && precision != 3) return fail(AMMC_EINVAL, "precision must be 1 or 3 (got %d)", precision);
+  if (Cin % 64 != 0 || Cout % 64 != 0)
+    return fail(AMMC_EUNSUPPORTED, "tcgen05 wgrad needs Cin and Cout multiples of 64 (got %d, %d)", Cin, Cout);
+  if (w > 64 || 64 % w != 0 || h % (64 / w) != 0)
+    return fail(AMMC_EUNSUPPORTED, "tcgen05 wgrad cannot tile a %dx%d feature map into 64-pixel runs", h, w);
+  WgradParams p;
+  p.b = b; p.H = h; p.W = w; p.Cin = Cin; p.Cout = Cout;
+  p.rows_per_kb = 64 / w;
+  p.kb_per_img = h * w / 64;
+  p.tiles_m = ceil_div(Cout, WG_BLOCK_M);
+  p.tiles_n = ceil_div(Cin, WG_BLOCK_N);
+  p.block_n = min(Cin, WG_BLOCK_N);
+  const int base_items = p.tiles_m * p.tiles_n * 9;
+  p.splits = max(1, min(b, ceil_div(2 * num_sms(), base_items)));
+  p.imgs_per_split = ceil_div(b, p.splits);
+  p.splits = ceil_div(b, p.imgs_per_split);
+  p.n_pass = precision;
+  const int pa[3] = {0, 0, 1}, pb[3] = {0, 1, 0};
+  for (int i = 0; i < 3; ++i) { p.pass_a[i] = pa[i]; p.pass_b[i] = pb[i]; }
+  p.gw = gw;
+  AMMC_CUDA_CHECK(cudaMemsetAsync(gw, 0, (size_t)Cout * Cin * 9 * sizeof(float), st));
+  CUtensorMap tmA, tmB;
+  {
+    uint64_t dims[5] = {(uint64_t)Cout, (uint64_t)w, (uint64_t)h, (uint64_t)b, 2};
+    uint64_t strides[4] = {(uint64_t)Cout * 2, (uint64_t)w * Cout * 2, (uint64_t)h * w * Cout * 2,
+                           (uint64_t)b * h * w * Cout * 2};
+    uint32_t box[5] = {64, (uint32_t)w, (uint32_t)p.rows_per_kb, 1, 1};
+    if (int rc = make_map_bf16(&tmA, gy_nhwc_planes, 5, dims, strides, box)) return rc;
+  }
+  {
+    uint64_t dims[5] = {(uint64_t)Cin, (uint64_t)w, (uint64_t)h, (uint64_t)b, 2};
+    uint64_t strides[4] = {(uint64_t)Cin * 2, (uint64_t)w * Cin * 2, (uint64_t)h * w * Cin * 2,
+                           (uint64_t)b * h * w * Cin * 2};
+    uint32_t box[5] = {64, (uint32_t)w, (uint32_t)p.rows_per_kb, 1, 1};
+    if (int rc = make_map_bf16(&tmB, x_nhwc_planes, 5, dims, strides, box)) return rc;
+  }
+  static bool configured[64] = {false};
+  int dev = 0;
+  AMMC_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && !configured[dev]) {
+    AMMC_CUDA_CHECK(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM));
+    configured[dev] = true;
+  }
+  const int items = base_items * p.splits;
+  conv_wgrad_kernel<<<min(num_sms(), items), WG_THREADS, WG_SMEM, st>>>(tmA, tmB, p);
+  AMMC_LAUNCH_CHECK("conv_wgrad_kernel");
+  return 0;
+}

@@ -35,15 +35,23 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a pipeline bug must end in a trap (an error the host sees), never in a hung GPU.
+// Bounded wait: a pipeline bug must never hang the GPU.  On timeout the waiter records (tag, block, thread) in
+// g_ammc_timeout, poisons all later waits (they return immediately) and lets the kernel drain; the host reads the
+// record with ammc_debug_timeout() and raises.  Results of a poisoned launch are garbage by construction.
+static __device__ int g_ammc_timeout[4];   // per translation unit: [0] poisoned flag, [1] tag, [2] block, [3] thread
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
-      printf("ammc_b200: mbarrier wait timed out (tag %d, block %d, thread %d)\n", tag, (int)blockIdx.x,
-             (int)threadIdx.x);
-      __trap();
+    if (*reinterpret_cast<volatile int*>(&g_ammc_timeout[0])) return;
+    if (clock64() - t0 > 1000000000LL) {
+      if (atomicCAS(&g_ammc_timeout[0], 0, 1) == 0) {
+        g_ammc_timeout[1] = tag;
+        g_ammc_timeout[2] = (int)blockIdx.x;
+        g_ammc_timeout[3] = (int)threadIdx.x;
+        __threadfence();
+      }
+      return;
     }
   }
 }
@@ -140,11 +148,37 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                            // layout type SWIZZLE_128B, bits [61,64)
   return d;
 }
+// MN-major operand (the contiguous axis is M or N, e.g. a [pixels(K)][channels(MN)] NHWC tile): built from TMA boxes of
+// 64 channels (128 B rows, 128B swizzle) x K rows.  Canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units
+// (CUTLASS make_umma_desc<Major::MN>, SWIZZLE_128B): LBO = bytes between consecutive 64-channel boxes, SBO = bytes between
+// consecutive groups of 8 K-rows (= 1024).
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
 // Instruction descriptor for kind::f16 / kind::tf32, fp32 accumulate, both operands K-major.
 //   fmt: 0 = f16, 1 = bf16, 2 = tf32
 __host__ __device__ constexpr uint32_t umma_idesc(int fmt, int M, int N) {
   return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) |
          ((uint32_t)(M >> 4) << 24);
 }
+// Same with both operands MN-major (bits 15 and 16).
+__host__ __device__ constexpr uint32_t umma_idesc_mn(int fmt, int M, int N) {
+  return umma_idesc(fmt, M, N) | (1u << 15) | (1u << 16);
+}
 
 }  // namespace ptx
+
+// Defines `int name(int* out4)`: copies this translation unit's watchdog record to the host and clears it (synchronises).
+#define AMMC_DEFINE_TIMEOUT_READER(name)                                                          \
+  int name(int* out4) {                                                                           \
+    int zero[4] = {0, 0, 0, 0};                                                                   \
+    if (cudaMemcpyFromSymbol(out4, ptx::g_ammc_timeout, sizeof(zero)) != cudaSuccess) return -1;  \
+    if (out4[0] && cudaMemcpyToSymbol(ptx::g_ammc_timeout, zero, sizeof(zero)) != cudaSuccess) return -1; \
+    return 0;                                                                                     \
+  }

@@ -106,6 +106,17 @@ def mem_forward_raw(x, enc_w, enc_b, embed, dec_w, dec_b, k: int, residual: bool
     return dict(out=out, q1=q1, idx=idx, z=z, sse_frame=sse, diff=diff, counts=counts, embed_sum=esum, x=x)
 
 
+def check_pipeline_watchdog():
+    """Synchronise and raise if any tcgen05 pipeline wait timed out (a kernel bug, never expected in production)."""
+    rec = (ctypes.c_int * 4)()
+    rc = _capi.load().ammc_debug_timeout(rec)
+    if rc < 0:
+        _capi.check(rc, "ammc_debug_timeout")
+    if rc == 1:
+        raise RuntimeError("ammc_b200: tcgen05 pipeline wait timed out: family=%d tag=%d block=%d thread=%d"
+                           % (rec[0], rec[1], rec[2], rec[3]))
+
+
 def set_addressing_mode(mode: str = "auto"):
     """'auto' | 'fp32' (generic CUDA-core kernel) | 'tensor' (tcgen05 filter + exact refine); process-wide."""
     _capi.call("ammc_set_addressing_mode", {"auto": 0, "fp32": 1, "tensor": 2}[mode])
@@ -324,6 +335,129 @@ def conv3x3_bn_relu(xp, wp, scale, shift, *, to_planes: bool, residual: Optional
             PROFILE["events"].append((ev0, ev1))
     _count(1)
     return out_p if to_planes else out_n
+
+
+def bn_batch_stats(y, gamma, beta, running_mean, running_var, momentum: float, eps: float, training: bool):
+    """(scale, shift, mean, invstd) of a BatchNorm2d over y [b,C,h,w]; updates the running stats in place when training."""
+    b, C, h, w = y.shape
+    dev = y.device
+    scale, shift, mean, invstd = (torch.empty((C,), dtype=torch.float32, device=dev) for _ in range(4))
+    ws = _workspace(2 * C * 8, dev)
+    with torch.cuda.device(dev):
+        _capi.call("ammc_bn_batch_stats", _p(y), _p(gamma.contiguous()), _p(beta.contiguous()), _p(running_mean),
+                   _p(running_var), _p(scale), _p(shift), _p(mean), _p(invstd), _p(ws), ws.numel(), b, C, h, w,
+                   float(momentum), float(eps), int(bool(training)), _stream())
+    _count(3 if training else 1)
+    return scale, shift, mean, invstd
+
+
+def bn_apply(y, scale, shift, *, relu=True, nhwc=False, nchw=False, f32=False, res=None):
+    """relu(y*scale+shift) -> (NHWC bf16 planes | None, NCHW bf16 planes | None, fp32 NCHW (+res) | None)."""
+    b, C, h, w = y.shape
+    dev = y.device
+    o_nhwc = torch.empty((2, b, h, w, C), dtype=torch.bfloat16, device=dev) if nhwc else None
+    o_nchw = torch.empty((2, b, C, h, w), dtype=torch.bfloat16, device=dev) if nchw else None
+    o_f32 = torch.empty_like(y) if f32 else None
+    with torch.cuda.device(dev):
+        _capi.call("ammc_bn_apply", _p(y), _p(scale), _p(shift), int(bool(relu)), _p(o_nhwc), _p(o_nchw), _p(o_f32),
+                   _p(None if res is None else res.contiguous()), b, C, h, w, _stream())
+    _count(1)
+    return o_nhwc, o_nchw, o_f32
+
+
+def bn_backward(g, y, scale, shift, mean, invstd, *, relu=True, training=True):
+    """Gradient through ReLU+BN: -> (g_y as NHWC bf16 planes, g_gamma, g_beta)."""
+    b, C, h, w = y.shape
+    dev = y.device
+    gy_nhwc = torch.empty((2, b, h, w, C), dtype=torch.bfloat16, device=dev)
+    gy_nchw = None
+    gg = torch.empty((C,), dtype=torch.float32, device=dev)
+    gb = torch.empty((C,), dtype=torch.float32, device=dev)
+    ws = _workspace(2 * C * 8, dev)
+    with torch.cuda.device(dev):
+        _capi.call("ammc_bn_backward", _p(g.contiguous()), _p(y), _p(scale), _p(shift), _p(mean), _p(invstd),
+                   int(bool(relu)), int(bool(training)), _p(gy_nhwc), _p(gy_nchw), _p(gg), _p(gb), _p(ws), ws.numel(),
+                   b, C, h, w, _stream())
+    _count(4)
+    return gy_nhwc, gg, gb
+
+
+def pack_planes(x):
+    """fp32 tensor -> bf16 hi/lo planes with the same layout: [2, *x.shape]."""
+    _require_cuda_f32(x)
+    xc = x.contiguous()
+    xp = torch.empty((2,) + tuple(xc.shape), dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        _capi.call("ammc_pack_planes", _p(xc), _p(xp), xc.numel(), _stream())
+    _count(1)
+    return xp
+
+
+def pack_conv_weights_dgrad(w):
+    """[Cout,Cin,3,3] -> [2, Cin, 9*Cout] planes (taps flipped, channels transposed) for the data-gradient conv."""
+    _require_cuda_f32(w)
+    Cout, Cin = w.shape[0], w.shape[1]
+    wp = torch.empty((2, Cin, 9 * Cout), dtype=torch.bfloat16, device=w.device)
+    with torch.cuda.device(w.device):
+        _capi.call("ammc_pack_conv_weights_dgrad", _p(w.contiguous()), _p(wp), Cout, Cin, _stream())
+    _count(1)
+    return wp
+
+
+def conv3x3_wgrad(gy_nhwc_planes, x_nhwc_planes, precision: int = 3):
+    """gw [Cout,Cin,3,3] from the NHWC bf16 planes of the output gradient [2,b,h,w,Cout] and of the conv input."""
+    _, b, h, w, Cout = gy_nhwc_planes.shape
+    Cin = x_nhwc_planes.shape[4]
+    gw = torch.empty((Cout, Cin, 3, 3), dtype=torch.float32, device=gy_nhwc_planes.device)
+    with torch.cuda.device(gw.device):
+        _capi.call("ammc_conv3x3_wgrad", _p(gy_nhwc_planes), _p(x_nhwc_planes), _p(gw), b, Cin, Cout, h, w,
+                   int(precision), _stream())
+    _count(2)
+    return gw
+
+
+class AmftBranchFn(torch.autograd.Function):
+    """out = res + double_conv(u): (conv3x3 -> BN -> ReLU) x 2 with autograd (reference unet.py:8-20, 962-965).
+
+    Training mode uses batch statistics (and updates the running buffers in place); eval mode the running ones.
+    forward(u, res, w1, gamma1, beta1, rmean1, rvar1, w2, gamma2, beta2, rmean2, rvar2, training, precision, eps, momentum)
+    """
+
+    @staticmethod
+    def forward(ctx, u, res, w1, g1, b1, rm1, rv1, w2, g2, b2, rm2, rv2, training, precision, eps, momentum):
+        _require_cuda_f32(u, res, w1, w2, names=("input", "residual", "conv.0.weight", "conv.3.weight"))
+        u = u.contiguous()
+        C = u.shape[1]
+        dev = u.device
+        one = torch.ones((C,), dtype=torch.float32, device=dev)
+        zero = torch.zeros((C,), dtype=torch.float32, device=dev)
+        need_grad = any(ctx.needs_input_grad)
+        up = pack_nhwc(u)
+        y1 = conv3x3_bn_relu(up, pack_conv_weights(w1), one, zero, to_planes=False, precision=precision, relu=False)
+        sc1, sh1, mu1, is1 = bn_batch_stats(y1, g1, b1, rm1, rv1, momentum, eps, training)
+        a1_nhwc, _, _ = bn_apply(y1, sc1, sh1, relu=True, nhwc=True)
+        y2 = conv3x3_bn_relu(a1_nhwc, pack_conv_weights(w2), one, zero, to_planes=False, precision=precision, relu=False)
+        sc2, sh2, mu2, is2 = bn_batch_stats(y2, g2, b2, rm2, rv2, momentum, eps, training)
+        _, _, out = bn_apply(y2, sc2, sh2, relu=True, f32=True, res=res)
+        if need_grad:
+            ctx.save_for_backward(up, w1, w2, y1, y2, a1_nhwc, sc1, sh1, mu1, is1, sc2, sh2, mu2, is2, one, zero)
+            ctx.cfg = (bool(training), int(precision))
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        up, w1, w2, y1, y2, a1_nhwc, sc1, sh1, mu1, is1, sc2, sh2, mu2, is2, one, zero = ctx.saved_tensors
+        training, precision = ctx.cfg
+        g_out = g_out.contiguous()
+        gy2_nhwc, gg2, gb2 = bn_backward(g_out, y2, sc2, sh2, mu2, is2, relu=True, training=training)
+        gw2 = conv3x3_wgrad(gy2_nhwc, a1_nhwc, precision)
+        g_a1 = conv3x3_bn_relu(gy2_nhwc, pack_conv_weights_dgrad(w2), one, zero, to_planes=False, precision=precision,
+                               relu=False)
+        gy1_nhwc, gg1, gb1 = bn_backward(g_a1, y1, sc1, sh1, mu1, is1, relu=True, training=training)
+        gw1 = conv3x3_wgrad(gy1_nhwc, up, precision)
+        g_u = conv3x3_bn_relu(gy1_nhwc, pack_conv_weights_dgrad(w1), one, zero, to_planes=False, precision=precision,
+                              relu=False)
+        return (g_u, g_out, gw1, gg1, gb1, None, None, gw2, gg2, gb2, None, None, None, None, None, None)
 
 
 # --------------------------------------------------------------------------------------------------

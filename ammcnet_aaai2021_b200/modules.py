@@ -121,6 +121,19 @@ class double_conv(nn.Module):
             self._packed[ci] = hit
         return hit[1], hit[2], hit[3]
 
+    def forward_autograd(self, u, residual, precision):
+        """residual + double_conv(u) with autograd; batch-statistic BN when self.training (running stats updated)."""
+        c1, bn1, c2, bn2 = self.conv[0], self.conv[1], self.conv[3], self.conv[4]
+        if bn1.momentum is None or bn2.momentum is None:
+            raise RuntimeError("ammc_b200.double_conv: cumulative-average BatchNorm (momentum=None) is not supported")
+        out = F_.AmftBranchFn.apply(u, residual, c1.weight, bn1.weight, bn1.bias, bn1.running_mean, bn1.running_var,
+                                    c2.weight, bn2.weight, bn2.bias, bn2.running_mean, bn2.running_var,
+                                    self.training, precision, bn1.eps, bn1.momentum)
+        if self.training:
+            bn1.num_batches_tracked += 1
+            bn2.num_batches_tracked += 1
+        return out
+
     def forward_fused(self, xp, residual, precision):
         w1, s1, b1 = self.packed(0, 1)
         w2, s2, b2 = self.packed(3, 4)
@@ -142,11 +155,13 @@ class bridge(nn.Module):
         self.precision = precision
 
     def forward(self, zx, zy):
-        if self.training or torch.is_grad_enabled() and (zx.requires_grad or zy.requires_grad):
-            raise RuntimeError(
-                "ammc_b200.bridge: the training path (batch-statistic BatchNorm + backward) of the AMFT block is not "
-                "implemented yet in the sm_100a library; run the block under eval() and torch.no_grad(). "
-                "There is deliberately no cuDNN fallback.")
+        needs_graph = torch.is_grad_enabled() and (zx.requires_grad or zy.requires_grad or
+                                                   any(p.requires_grad for p in self.parameters()))
+        if self.training or needs_graph:
+            # batch-statistic BN and/or autograd: unfused pipeline (raw conv -> BN stats -> apply), tcgen05 dgrad/wgrad
+            x = self.O2F.forward_autograd(zy, zx, self.precision)
+            y = self.F20.forward_autograd(zx, zy, self.precision)
+            return x, y
         px = F_.pack_nhwc(zx)
         py = F_.pack_nhwc(zy)
         x = self.O2F.forward_fused(py, zx, self.precision)

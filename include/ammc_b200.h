@@ -39,6 +39,13 @@ int ammc_version(void);
 const char* ammc_last_error(void);
 /* 1 when the current device is sm_100 (B200); the library refuses to run anywhere else. */
 int ammc_device_supported(void);
+/* Debug aid: every mbarrier wait in the tcgen05 kernels is bounded; a pipeline that stalls records where and drains
+ * instead of hanging the GPU.  Returns 0 when no wait timed out since the last call, 1 with out4 = {kernel family
+ * (1 conv, 2 addressing, 3 training), wait tag, block, thread} otherwise, negative on CUDA errors.  Synchronises. */
+int ammc_debug_timeout(int* out4);
+/* Debug aid: TMA-load one 5-D bf16 box (128B swizzle, zero OOB fill) and dump the raw shared-memory bytes to `out`. */
+int ammc_debug_tma_probe(const void* base, const int64_t* dims5, const int64_t* strides4_bytes, const int* box5,
+                         const int* coords5, void* out, int out_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * Memory module.  Replaces enc_quan_dec_topk.forward / enc_quan_dec_res_topk.forward
@@ -156,6 +163,33 @@ int ammc_pack_conv_weights_1x1(const float* w, void* wp, int Cout, int Cin, void
 int ammc_conv1x1_bn_relu(const void* xp, const void* wp, const float* scale, const float* shift,
                          void* out_planes, float* out_nchw, const float* res_nchw,
                          int b, int Cin, int Cout, int h, int w, int precision, int relu, void* stream);
+/* ---- AMFT training path (autograd of double_conv, unet.py:8-20) -------------------------------------------------
+ * ammc_bn_batch_stats   training != 0: per-channel batch mean / biased variance of y [b,C,h,w] -> scale = gamma*invstd,
+ *                       shift = beta - mean*scale, mean, invstd; running_mean/var updated in place (momentum, unbiased
+ *                       variance) like torch.nn.BatchNorm2d.  training == 0: the same quadruple from the running stats.
+ *                       workspace: 2*C doubles.
+ * ammc_bn_apply         v = relu?(y*scale + shift) written as NHWC bf16 hi/lo planes, NCHW bf16 hi/lo planes and/or fp32
+ *                       NCHW (+ res); any subset of the three outputs.
+ * ammc_bn_backward      gradient through ReLU + BatchNorm: g [b,C,h,w] wrt the activation -> g_y wrt the conv output as
+ *                       NHWC and/or NCHW bf16 planes, g_gamma [C], g_beta [C].  workspace: 2*C doubles.
+ * ammc_pack_planes      fp32 -> bf16 hi/lo planes in the same layout ([2][n]).
+ * ammc_pack_conv_weights_dgrad   w [Cout,Cin,3,3] -> [2][Cin][9*Cout] (taps flipped): ammc_conv3x3_bn_relu on gradient
+ *                       planes with these weights is the data gradient of the convolution.
+ * ammc_conv3x3_wgrad    gw [Cout,Cin,3,3] = sum_pixels gy x x(shifted) on tcgen05; operands are the NHWC bf16 planes of
+ *                       the output gradient [2][b,h,w,Cout] and of the conv input [2][b,h,w,Cin] (MN-major UMMA). */
+int ammc_bn_batch_stats(const float* y, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                        float* scale, float* shift, float* mean, float* invstd, void* workspace, size_t workspace_bytes,
+                        int b, int C, int h, int w, float momentum, float eps, int training, void* stream);
+int ammc_bn_apply(const float* y, const float* scale, const float* shift, int relu, void* out_nhwc_planes,
+                  void* out_nchw_planes, float* out_f32, const float* res, int b, int C, int h, int w, void* stream);
+int ammc_bn_backward(const float* g, const float* y, const float* scale, const float* shift, const float* mean,
+                     const float* invstd, int relu, int training, void* gy_nhwc_planes, void* gy_nchw_planes,
+                     float* g_gamma, float* g_beta, void* workspace, size_t workspace_bytes, int b, int C, int h, int w,
+                     void* stream);
+int ammc_pack_planes(const float* x, void* xp, int64_t n, void* stream);
+int ammc_pack_conv_weights_dgrad(const float* w, void* wp, int Cout, int Cin, void* stream);
+int ammc_conv3x3_wgrad(const void* gy_nhwc_planes, const void* x_nhwc_planes, float* gw, int b, int Cin, int Cout,
+                       int h, int w, int precision, void* stream);
 /* BatchNorm (eval) folding: scale/shift [C] from gamma, beta, running_mean, running_var. */
 int ammc_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, float eps,
                  float* scale, float* shift, int C, void* stream);

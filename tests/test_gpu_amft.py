@@ -108,9 +108,58 @@ def test_bridge_full_size_linearity_and_oracle_sample():
     assert_close(y[3:4].cpu(), oy, 1e-3, "bridge.full.y")
 
 
-def test_bridge_rejects_unsupported_and_training():
+@pytest.mark.parametrize("name", ["amft_c64", "amft_c512"])
+def test_bridge_training_forward_backward_vs_reference_autograd(name):
+    """Train-mode forward (batch-statistic BN, running-stat update) and every gradient against the reference's autograd."""
+    c, g = load_golden(name)
+    p, zx, zy = _inputs(c)
+    m = A.bridge(in_c=c["C"], precision=3)
+    m.load_state_dict({k: v.clone() for k, v in p.items()}, strict=True)
+    m = m.to(DEV).train()
+    zxg, zyg = zx.to(DEV).requires_grad_(True), zy.to(DEV).requires_grad_(True)
+    tx, ty = m(zxg, zyg)
+    assert_close(tx.detach().cpu(), g["train_x"], 1e-3, name + ".train_x")
+    assert_close(ty.detach().cpu(), g["train_y"], 1e-3, name + ".train_y")
+    sd = m.state_dict()
+    for k in g:
+        if k.startswith("stat_"):
+            assert_close(sd[k[5:]].cpu(), g[k], 1e-3, name + "." + k)
+    assert int(sd["O2F.conv.1.num_batches_tracked"]) == 1
+    gen = torch.Generator().manual_seed(c["seed"] + 3000)
+    rx, ry = torch.randn(tx.shape, generator=gen).to(DEV), torch.randn(ty.shape, generator=gen).to(DEV)
+    ((tx * rx).sum() + (ty * ry).sum()).backward()
+    assert_close(zxg.grad.cpu(), g["g_zx"], 1e-3, name + ".g_zx")
+    assert_close(zyg.grad.cpu(), g["g_zy"], 1e-3, name + ".g_zy")
+    n_checked = 0
+    for pn, pv in m.named_parameters():
+        if "g_" + pn in g:
+            assert_close(pv.grad.cpu(), g["g_" + pn], 1e-3, name + ".g_" + pn)
+            n_checked += 1
+    assert n_checked == (12 if c["C"] <= 64 else 0)
+
+
+def test_bridge_eval_mode_with_grad_matches_fused_path():
+    """eval() + autograd (frozen BN) must give the same forward as the fused no-grad path and finite gradients."""
+    c, g = load_golden("amft_c64")
+    p, zx, zy = _inputs(c)
+    m = _bridge(c, p, precision=3)
+    with torch.no_grad():
+        x0, y0 = m(zx.to(DEV), zy.to(DEV))
+    zxg = zx.to(DEV).requires_grad_(True)
+    x1, y1 = m(zxg, zy.to(DEV))
+    assert_close(x1.detach().cpu(), x0.cpu(), 1e-4, "eval-grad.x")
+    assert_close(y1.detach().cpu(), y0.cpu(), 1e-4, "eval-grad.y")
+    (x1.sum() + y1.sum()).backward()
+    ref_m = torch.nn.Sequential()          # fp64 torch reference of the same frozen-BN block, for the input gradient
+    import ammc_oracle as O2
+    zr = zx.double().requires_grad_(True)
+    p64 = {k: (v.double() if v.is_floating_point() else v) for k, v in p.items()}
+    ox, oy, _ = O2.amft_forward(zr, zy.double(), p64)
+    (ox.sum() + oy.sum()).backward()
+    assert_close(zxg.grad.cpu(), zr.grad, 1e-3, "eval-grad.g_zx")
+
+
+def test_bridge_rejects_unsupported_shapes():
     m = A.bridge(in_c=64).to(DEV)
-    with pytest.raises(RuntimeError, match="not implemented"):
-        m.train()(torch.zeros(1, 64, 8, 8, device=DEV), torch.zeros(1, 64, 8, 8, device=DEV))
     with torch.no_grad(), pytest.raises(RuntimeError, match="divides 128|128-pixel"):
         m.eval()(torch.zeros(1, 64, 5, 7, device=DEV), torch.zeros(1, 64, 5, 7, device=DEV))

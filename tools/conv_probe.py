@@ -57,7 +57,36 @@ def conv_case(cin, cout, h, w, b, taps, precision):
     report("   -> planes output", rec, ref)
 
 
+def wgrad_case(cin, cout, h, w, b, precision):
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn((b, cin, h, w), generator=g)
+    gy = torch.randn((b, cout, h, w), generator=g)
+    gw = F_.conv3x3_wgrad(F_.pack_nhwc(gy.to(DEV)), F_.pack_nhwc(x.to(DEV)), precision)
+    torch.cuda.synchronize()
+    F_.check_pipeline_watchdog()
+    if precision == 1:
+        xr, gr = x.to(torch.bfloat16).double(), gy.to(torch.bfloat16).double()
+    else:
+        xr, gr = x.double(), gy.double()
+    wt = torch.zeros((cout, cin, 3, 3), dtype=torch.float64, requires_grad=True)
+    (torch.nn.functional.conv2d(xr, wt, padding=1) * gr).sum().backward()
+    ref = wt.grad
+    err = (gw.double().cpu() - ref).abs()
+    scale = ref.abs().max().item()
+    print(f"[wgrad cin={cin} cout={cout} {h}x{w} b={b} P={precision}] max_abs_err={err.max().item():.3e} scale={scale:.3e} "
+          f"rel={err.max().item() / scale:.3e}", flush=True)
+    if err.max().item() / scale > 1e-3:
+        bad = err > 1e-3 * scale
+        print("   bad fraction", bad.float().mean().item(), "per tap", bad.float().mean(dim=(0, 1)).flatten().tolist())
+        print("   sample gw ", gw[0, :3].flatten().tolist()[:9])
+        print("   sample ref", ref[0, :3].flatten().tolist()[:9])
+
+
 CASES = {
+    "w64": lambda: wgrad_case(64, 64, 8, 8, 2, 1),
+    "w64b": lambda: wgrad_case(64, 128, 8, 16, 3, 1),
+    "w512": lambda: wgrad_case(512, 512, 32, 32, 2, 1),
+    "w512p3": lambda: wgrad_case(512, 512, 32, 32, 5, 3),
     "g64": lambda: conv_case(64, 64, 8, 16, 1, 1, 1),
     "g64b": lambda: conv_case(64, 64, 8, 16, 4, 1, 1),
     "g128": lambda: conv_case(128, 128, 8, 16, 2, 1, 1),
