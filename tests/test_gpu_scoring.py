@@ -72,3 +72,46 @@ def test_evaluate_matches_sklearn_on_reference_records(tmp_path):
     labels = [g["labels"][offs[i]:offs[i + 1]] for i in range(nv)]
     ret = A.evaluate("img_pred_fea_comm_rgb_auc", str(pk), tuple(c["lam"]), gt_labels=labels)
     assert ret["auc"] == round(float(g["auc"]), 3) and ret["optimal_loss"] == str(pk)
+
+
+def test_video_scorer_reproduces_reference_loop_semantics():
+    """Row a12: the batched, sync-free scorer must write the records the reference loop writes
+    (Code/run_helper/test_helper.py:408-475): per-frame PSNR, the commit scalar of each 16-clip group, back-filled head,
+    op-stream tail copy -- independent of the batch size used on the device."""
+    torch.manual_seed(0)
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        g = A.get_twostream().to(DEV).eval()
+        T, H = 41, 64                                        # 37 clips -> groups of 16, 16, 5
+        gen = torch.Generator().manual_seed(5)
+        rgb = (torch.rand((T, 3, H, H), generator=gen) * 2 - 1).to(DEV)
+        op = (torch.randn((T - 1, 2, H, H), generator=gen) * 0.02).to(DEV)
+        rec = scoring.VideoScorer(g, batch=64).score_video(rgb, op)
+        rec7 = scoring.VideoScorer(g, batch=7).score_video(rgb, op)
+        # the reference's own procedure: batches of 16 clips, psnr_error per frame, the batch-level diff per frame
+        n_clips = T - 4
+        psnr_ref = np.empty(n_clips, np.float32)
+        commit_ref = np.empty(n_clips, np.float32)
+        commit_op_ref = np.empty(n_clips, np.float32)
+        with torch.no_grad():
+            for c0 in range(0, n_clips, 16):
+                idx = torch.arange(c0, min(n_clips, c0 + 16), device=DEV)
+                rgb_in = torch.stack([rgb[idx + t] for t in range(4)], 1).flatten(1, 2)
+                op_in = torch.stack([op[idx + t] for t in range(3)], 1).flatten(1, 2)
+                pred, _, (d_rgb, d_op), _ = g(rgb_in, op_in)
+                for i in range(idx.numel()):
+                    psnr_ref[c0 + i] = float(A.psnr_error(pred[i:i + 1], rgb[idx[i] + 4][None]))
+                    commit_ref[c0 + i] = float(d_rgb)
+                    commit_op_ref[c0 + i] = float(d_op)
+        img = np.concatenate([np.full(4, psnr_ref[0], np.float32), psnr_ref])
+        fea = np.concatenate([np.full(4, commit_ref[0], np.float32), commit_ref])
+        assert rec["rgb_img_pred"].shape == (T,) and rec["op_fea_comm"].shape == (T,)
+        for r in (rec, rec7):
+            assert_close(r["rgb_img_pred"], img, 1e-3, "records.psnr")
+            assert_close(r["rgb_fea_comm"], fea, 1e-3, "records.commit")
+            op_fea = np.concatenate([np.full(3, commit_op_ref[0], np.float32), commit_op_ref, commit_op_ref[-1:]])
+            assert_close(r["op_fea_comm"], op_fea, 1e-3, "records.op_commit")
+        assert len(set(np.round(rec["rgb_fea_comm"][4:], 12))) == 3       # one commit value per 16-clip group
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
