@@ -39,6 +39,7 @@ SIGNATURES = {
     "ammc_pack_conv_weights": (I, [P, P, I, I, P]),
     "ammc_pack_nhwc": (I, [P, P, I, I, I, I, P]),
     "ammc_conv3x3_bn_relu": (I, [P] * 7 + [I] * 7 + [P]),
+    "ammc_set_conv_pair_mode": (I, [I]),
     "ammc_pack_conv_weights_1x1": (I, [P, P, I, I, P]),
     "ammc_conv1x1_bn_relu": (I, [P] * 7 + [I] * 7 + [P]),
     "ammc_bn_batch_stats": (I, [P] * 9 + [P, Z] + [I, I, I, I, F, F, I, P]),

@@ -214,6 +214,182 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): one 256-pixel x 256-channel tile per pair of SMs.  Each CTA stages its own 128 pixel
+// rows of A and its own 128-channel half of B (32 KB per stage instead of 48 KB -> 6 stages, one third less L2->smem
+// traffic); the leader issues M=256 MMAs that read both CTAs' shared memory and writes rows 0-127 / 128-255 of the
+// accumulator into the leader's / the peer's TMEM.  Barrier protocol: both CTAs' TMA bytes are credited to the
+// leader's `full` barrier; `empty` and `tmem_full` are released in both CTAs by a multicast tcgen05.commit; the
+// peer's epilogue threads arrive remotely on the leader's `tmem_empty`.
+// ------------------------------------------------------------------------------------------------
+constexpr int PAIR_N = 256;
+constexpr int PAIR_B_BYTES = (PAIR_N / 2) * BLOCK_K * 2;      // this CTA's half of the B tile: 16 KB
+constexpr int PAIR_STAGE_BYTES = A_BYTES + PAIR_B_BYTES;       // 32 KB
+constexpr int PAIR_STAGES = 6;
+constexpr int PAIR_BAR_OFFSET = PAIR_STAGES * PAIR_STAGE_BYTES;
+constexpr int PAIR_SMEM = PAIR_BAR_OFFSET + 256 + 1024;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1)
+conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + PAIR_BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + PAIR_STAGES;
+  uint64_t* tmem_full = empty_bar + PAIR_STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();            // 0 = leader
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+  const int pair_tiles_m = (p.tiles_m + 1) >> 1;
+  const int num_tiles = pair_tiles_m * p.tiles_n;
+  const int kb_per_pass = p.ntaps * (p.Cin / BLOCK_K);
+  const int kb_total = kb_per_pass * p.n_pass;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tmA);
+    ptx::prefetch_tensormap(&tmB);
+    for (int s = 0; s < PAIR_STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
+    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tmem_full[a], 1); ptx::mbar_init(&tmem_empty[a], 256); }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc_2sm(tmem_slot, 2 * PAIR_N);
+    ptx::tmem_relinquish_2sm();
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------------------------------------------ TMA producer (both CTAs)
+      int s = 0; uint32_t ph = 0;
+      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+        const int mt = (t / p.tiles_n) * 2 + (int)rank, nt = t % p.tiles_n;
+        const int img0 = (mt / p.groups_h) * p.B_box, h0 = (mt % p.groups_h) * p.H_box;
+        const int n0 = nt * PAIR_N + (int)rank * (PAIR_N / 2);
+        for (int ps = 0; ps < p.n_pass; ++ps) {
+          const int pa = p.pass_a[ps], pb = p.pass_b[ps];
+          for (int tap = 0; tap < p.ntaps; ++tap) {
+            const int dy = p.ntaps == 9 ? tap / 3 - 1 : 0, dx = p.ntaps == 9 ? tap % 3 - 1 : 0;
+            for (int cc = 0; cc < p.Cin / BLOCK_K; ++cc) {
+              ptx::mbar_wait(&empty_bar[s], ph ^ 1, 41);
+              if (rank == 0) ptx::mbar_expect_tx(&full_bar[s], 2 * PAIR_STAGE_BYTES);
+              uint8_t* a_dst = smem + s * PAIR_STAGE_BYTES;
+              ptx::tma_load_5d_2sm(a_dst, &tmA, &full_bar[s], cc * BLOCK_K, dx, h0 + dy, img0, pa);
+              ptx::tma_load_3d_2sm(a_dst + A_BYTES, &tmB, &full_bar[s], tap * p.Cin + cc * BLOCK_K, n0, pb);
+              if (++s == PAIR_STAGES) { s = 0; ph ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      // ------------------------------------------------------------------ MMA issuer (leader only)
+      constexpr uint32_t idesc = ptx::umma_idesc(1, 2 * BLOCK_M, PAIR_N);
+      int s = 0; uint32_t ph = 0;
+      int it = 0;
+      for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_ph = (it >> 1) & 1;
+        ptx::mbar_wait(&tmem_empty[acc], acc_ph ^ 1, 42);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * PAIR_N;
+        for (int kb = 0; kb < kb_total; ++kb) {
+          ptx::mbar_wait(&full_bar[s], ph, 43);
+          ptx::tc_fence_after();
+          const uint32_t a_addr = ptx::smem_u32(smem + s * PAIR_STAGE_BYTES);
+          const uint64_t adesc = ptx::umma_desc_k_sw128(a_addr);
+          const uint64_t bdesc = ptx::umma_desc_k_sw128(a_addr + A_BYTES);
+#pragma unroll
+          for (int k4 = 0; k4 < BLOCK_K / 16; ++k4)
+            ptx::mma_f16_ss_2sm(d_tmem, adesc + 2 * k4, bdesc + 2 * k4, idesc, (kb | k4) != 0 ? 1u : 0u);
+          ptx::mma_commit_2sm(&empty_bar[s], 3);
+          if (kb == kb_total - 1) ptx::mma_commit_2sm(&tmem_full[acc], 3);
+          if (++s == PAIR_STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else {
+    // -------------------------------------------------------------------- epilogue warps (both CTAs, own 128 rows)
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int per_img = p.W_box * p.H_box;
+    int it = 0;
+    for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_ph = (it >> 1) & 1;
+      const int mt = (t / p.tiles_n) * 2 + (int)rank, nt = t % p.tiles_n;
+      const int img = (mt / p.groups_h) * p.B_box + r / per_img;
+      const int rem = r % per_img;
+      const int hh = (mt % p.groups_h) * p.H_box + rem / p.W_box, ww = rem % p.W_box;
+      const bool valid = img < p.b && mt < p.tiles_m;
+      const int n0 = nt * PAIR_N;
+      ptx::mbar_wait(&tmem_full[acc], acc_ph, 44);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * PAIR_N;
+#pragma unroll 1
+      for (int c32 = 0; c32 < PAIR_N / 32; ++c32) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32(taddr + c32 * 32, v);
+        ptx::tmem_ld_wait();
+        const int cbase = n0 + c32 * 32;
+        float y[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float a = __uint_as_float(v[j]);
+          a = fmaf(a, __ldg(p.scale + cbase + j), __ldg(p.shift + cbase + j));
+          y[j] = p.relu ? fmaxf(a, 0.f) : a;
+        }
+        if (valid) {
+          if (p.out_nchw) {
+            const size_t hw = (size_t)p.H * p.W;
+            size_t o = ((size_t)img * p.Cout + cbase) * hw + (size_t)hh * p.W + ww;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float a = y[j];
+              if (p.res_nchw) a += __ldg(p.res_nchw + o);
+              p.out_nchw[o] = a;
+              o += hw;
+            }
+          }
+          if (p.out_planes) {
+            const size_t pix = ((size_t)img * p.H + hh) * p.W + ww;
+            __nv_bfloat16* hi = p.out_planes + pix * p.Cout + cbase;
+            __nv_bfloat16* lo = hi + p.out_plane_stride;
+            uint32_t hp[16], lp[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              __nv_bfloat16 h0 = __float2bfloat16_rn(y[2 * j]), h1 = __float2bfloat16_rn(y[2 * j + 1]);
+              __nv_bfloat16 l0 = __float2bfloat16_rn(y[2 * j] - __bfloat162float(h0));
+              __nv_bfloat16 l1 = __float2bfloat16_rn(y[2 * j + 1] - __bfloat162float(h1));
+              hp[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+              lp[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              reinterpret_cast<uint4*>(hi)[j] = make_uint4(hp[4 * j], hp[4 * j + 1], hp[4 * j + 2], hp[4 * j + 3]);
+              reinterpret_cast<uint4*>(lo)[j] = make_uint4(lp[4 * j], lp[4 * j + 1], lp[4 * j + 2], lp[4 * j + 3]);
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive_cluster(&tmem_empty[acc], 0);      // the leader's MMA thread waits for both CTAs' epilogues
+    }
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc_2sm(tmem_base, 2 * PAIR_N);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // operand packing
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
@@ -335,6 +511,8 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const Con
   return 0;
 }
 
+static int g_conv_pair_mode = 1;   // 1: CTA-pair kernel when Cout % 256 == 0; 0: single-CTA kernel everywhere
+
 // Shared by the 3x3 (ntaps = 9) and 1x1 (ntaps = 1) entry points.
 int conv_igemm(const void* xp, const void* wp, const float* scale, const float* shift, void* out_planes,
                float* out_nchw, const float* res_nchw, int b, int Cin, int Cout, int h, int w, int ntaps,
@@ -383,6 +561,26 @@ int conv_igemm(const void* xp, const void* wp, const float* scale, const float* 
     cuuint32_t box[3] = {64, (cuuint32_t)block_n, 1};
     if (int rc = make_map(&tmB, wp, 3, dims, strides, box)) return rc;
   }
+  if (block_n == 256 && g_conv_pair_mode) {
+    // B boxes are per-CTA halves (128 channels) in the pair kernel
+    const cuuint64_t K = (cuuint64_t)ntaps * Cin;
+    cuuint64_t dims[3] = {K, (cuuint64_t)Cout, 2};
+    cuuint64_t strides[2] = {K * 2, (cuuint64_t)Cout * K * 2};
+    cuuint32_t box[3] = {64, (cuuint32_t)(PAIR_N / 2), 1};
+    if (int rc = make_map(&tmB, wp, 3, dims, strides, box)) return rc;
+    static bool configured[64] = {false};
+    int dev = 0;
+    AMMC_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && !configured[dev]) {
+      AMMC_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM));
+      configured[dev] = true;
+    }
+    const int pair_tiles = ((p.tiles_m + 1) / 2) * p.tiles_n;
+    const int clusters = min(num_sms() / 2, pair_tiles);
+    conv_igemm_pair_kernel<<<2 * clusters, CONV_THREADS, PAIR_SMEM, st>>>(tmA, tmB, p);
+    AMMC_LAUNCH_CHECK("conv_igemm_pair_kernel");
+    return 0;
+  }
   switch (block_n) {
     case 256: return launch_conv<256>(tmA, tmB, p, st);
     case 128: return launch_conv<128>(tmA, tmB, p, st);
@@ -395,6 +593,11 @@ int conv_igemm(const void* xp, const void* wp, const float* scale, const float* 
 namespace ammc { AMMC_DEFINE_TIMEOUT_READER(timeout_reader_conv) }
 
 using namespace ammc;
+
+extern "C" int ammc_set_conv_pair_mode(int on) {
+  g_conv_pair_mode = on ? 1 : 0;
+  return 0;
+}
 
 extern "C" int ammc_pack_conv_weights(const float* w, void* wp, int Cout, int Cin, void* stream) {
   AMMC_REQUIRE(w && wp && Cout > 0 && Cin > 0, "bad argument");

@@ -117,6 +117,11 @@ def check_pipeline_watchdog():
                            % (rec[0], rec[1], rec[2], rec[3]))
 
 
+def set_conv_pair_mode(on: bool):
+    """CTA-pair (cta_group::2) conv kernel on/off (default on); for A/B measurements only."""
+    _capi.call("ammc_set_conv_pair_mode", int(bool(on)))
+
+
 def set_addressing_mode(mode: str = "auto"):
     """'auto' | 'fp32' (generic CUDA-core kernel) | 'tensor' (tcgen05 filter + exact refine); process-wide."""
     _capi.call("ammc_set_addressing_mode", {"auto": 0, "fp32": 1, "tensor": 2}[mode])

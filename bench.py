@@ -200,6 +200,8 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
     prec = args.precision
+    if args.no_pair:
+        F_.set_conv_pair_mode(False)
 
     # ---- modules with random-init weights of the shipped architecture (replicated on every rank) ----------
     p = synth.path_params(1, C, D, M, K_TOP)
@@ -392,6 +394,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--precision", type=int, default=3, choices=[1, 3])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pair", action="store_true", help="A/B: single-CTA conv kernel instead of the CTA-pair one")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -157,6 +157,9 @@ int ammc_pack_nhwc(const float* x, void* xp, int b, int C, int h, int w, void* s
 int ammc_conv3x3_bn_relu(const void* xp, const void* wp, const float* scale, const float* shift,
                          void* out_planes, float* out_nchw, const float* res_nchw,
                          int b, int Cin, int Cout, int h, int w, int precision, int relu, void* stream);
+/* 1 (default): convolutions with Cout % 256 == 0 use the CTA-pair (cta_group::2, M=256) kernel; 0: always the
+ * single-CTA kernel.  Results are bit-identical; the switch exists for A/B measurements. */
+int ammc_set_conv_pair_mode(int on);
 /* 1x1 convolution on the same tensor-core engine (a plain [N,Cin] x [Cout,Cin]^T GEMM, no halo):
  *   wp [2 planes][Cout][Cin] bf16 (pack with ammc_pack_conv_weights_1x1). */
 int ammc_pack_conv_weights_1x1(const float* w, void* wp, int Cout, int Cin, void* stream);

@@ -73,6 +73,29 @@ def test_conv3x3_engine(cin, cout, h, w, b):
     assert rel_err(y1.cpu(), ref) < 2e-2          # bf16 variant, stated separately
 
 
+def test_cta_pair_kernel_matches_single_cta_kernel():
+    """cta_group::2 (M=256 over two SMs) and the single-CTA kernel accumulate in the same order -> identical bits."""
+    g = torch.Generator().manual_seed(9)
+    for (cin, cout, h, w, b) in [(64, 256, 16, 16, 3), (512, 512, 32, 32, 3), (128, 256, 8, 8, 5)]:
+        x = torch.randn((b, cin, h, w), generator=g)
+        wt = torch.randn((cout, cin, 3, 3), generator=g) / (9 * cin) ** 0.5
+        xp, wp = F_.pack_nhwc(x.to(DEV)), F_.pack_conv_weights(wt.to(DEV))
+        scale, shift = torch.rand(cout, generator=g).to(DEV) + 0.5, torch.randn(cout, generator=g).to(DEV)
+        outs = []
+        try:
+            for pair in (True, False):
+                F_.set_conv_pair_mode(pair)
+                outs.append((F_.conv3x3_bn_relu(xp, wp, scale, shift, to_planes=False, precision=3),
+                             F_.conv3x3_bn_relu(xp, wp, scale, shift, to_planes=True, precision=1)))
+        finally:
+            F_.set_conv_pair_mode(True)
+        F_.check_pipeline_watchdog()
+        assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+        ref = torch.relu(torch.nn.functional.conv2d(x.double(), wt.double(), padding=1) * scale.cpu().double().view(1, -1, 1, 1)
+                         + shift.cpu().double().view(1, -1, 1, 1))
+        assert rel_err(outs[0][0].cpu(), ref) < 5e-5
+
+
 @pytest.mark.parametrize("name", ["amft_c64", "amft_c512"])
 def test_bridge_vs_golden(name):
     c, g = load_golden(name)
