@@ -3,6 +3,7 @@
 // rows and commit partials are bit-identical by construction.
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_bf16.h>
 #include <stdint.h>
 
 namespace ammc {
@@ -59,7 +60,9 @@ __device__ __forceinline__ void team_emit_row(const float* __restrict__ zr, cons
                                               const int (&ids)[K], int64_t n, int D, int M, int part, bool valid,
                                               float* __restrict__ read, float* __restrict__ q1,
                                               int64_t* __restrict__ idx, float* __restrict__ sse_px,
-                                              float* __restrict__ counts, float* __restrict__ embed_sum) {
+                                              float* __restrict__ counts, float* __restrict__ embed_sum,
+                                              __nv_bfloat16* __restrict__ read_planes = nullptr,
+                                              long long read_plane_stride = 0) {
   float sse = 0.f;
   if (valid) {
     if (part == 0) {
@@ -89,6 +92,29 @@ __device__ __forceinline__ void team_emit_row(const float* __restrict__ zr, cons
           const float4* er = reinterpret_cast<const float4*>(bank_t + (size_t)ids[j] * D);
           float4* rr = reinterpret_cast<float4*>(read + (n * K + j) * D);
           for (int i = part; i < (D >> 2); i += 4) rr[i] = __ldg(er + i);
+        }
+      }
+      if (read_planes) {   // bf16 hi/lo split of the read: the A operand of the tensor-core `dec` GEMM
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+          const float4* er = reinterpret_cast<const float4*>(bank_t + (size_t)ids[j] * D);
+          __nv_bfloat16* hp = read_planes + (n * K + j) * D;
+          for (int i = part; i < (D >> 2); i += 4) {
+            const float4 v = __ldg(er + i);
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(v.x), h1 = __float2bfloat16_rn(v.y);
+            const __nv_bfloat16 h2 = __float2bfloat16_rn(v.z), h3 = __float2bfloat16_rn(v.w);
+            const __nv_bfloat16 l0 = __float2bfloat16_rn(v.x - __bfloat162float(h0));
+            const __nv_bfloat16 l1 = __float2bfloat16_rn(v.y - __bfloat162float(h1));
+            const __nv_bfloat16 l2 = __float2bfloat16_rn(v.z - __bfloat162float(h2));
+            const __nv_bfloat16 l3 = __float2bfloat16_rn(v.w - __bfloat162float(h3));
+            uint2 ph, pl;
+            ph.x = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+            ph.y = (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16);
+            pl.x = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+            pl.y = (uint32_t)__bfloat16_as_ushort(l2) | ((uint32_t)__bfloat16_as_ushort(l3) << 16);
+            *reinterpret_cast<uint2*>(hp + 4 * i) = ph;
+            *reinterpret_cast<uint2*>(hp + read_plane_stride + 4 * i) = pl;
+          }
         }
       }
     } else {

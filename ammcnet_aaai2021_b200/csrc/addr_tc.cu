@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(256) refine_kernel(
     const float* __restrict__ bank_t, const float* __restrict__ en2,
     float* __restrict__ read, float* __restrict__ q1, int64_t* __restrict__ idx, float* __restrict__ sse_px,
     float* __restrict__ counts, float* __restrict__ embed_sum, int* __restrict__ stats, int* __restrict__ rescan_list,
-    int N, int D, int M) {
+    __nv_bfloat16* __restrict__ read_planes, long long read_plane_stride, int N, int D, int M) {
   const int t = threadIdx.x;
   const int px = t >> 2, part = t & 3;
   const int n = blockIdx.x * 64 + px;
@@ -360,7 +360,8 @@ __global__ void __launch_bounds__(256) refine_kernel(
   team_merge<K>(top);
 #pragma unroll
   for (int i = 0; i < K; ++i) top.id[i] = min(top.id[i], M - 1);
-  team_emit_row<K>(zr, bank_t, top.id, (int64_t)n, D, M, part, valid, read, q1, idx, sse_px, counts, embed_sum);
+  team_emit_row<K>(zr, bank_t, top.id, (int64_t)n, D, M, part, valid, read, q1, idx, sse_px, counts, embed_sum,
+                   read_planes, read_plane_stride);
 }
 
 // Exact scan over all M items for the (rare) rows whose candidate list overflowed: one warp per row.
@@ -369,7 +370,8 @@ __global__ void __launch_bounds__(256) rescan_kernel(
     const float* __restrict__ z, const float* __restrict__ bank_t, const float* __restrict__ en2,
     float* __restrict__ read, float* __restrict__ q1, int64_t* __restrict__ idx, float* __restrict__ sse_px,
     float* __restrict__ counts, float* __restrict__ embed_sum, const int* __restrict__ stats,
-    const int* __restrict__ rescan_list, int D, int M) {
+    const int* __restrict__ rescan_list, __nv_bfloat16* __restrict__ read_planes, long long read_plane_stride, int D,
+    int M) {
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   const int total = stats[2];
@@ -394,7 +396,8 @@ __global__ void __launch_bounds__(256) rescan_kernel(
     }
 #pragma unroll
     for (int i = 0; i < K; ++i) top.id[i] = min(top.id[i], M - 1);
-    team_emit_row<K>(zr, bank_t, top.id, (int64_t)n, D, M, lane & 3, lane < 4, read, q1, idx, sse_px, counts, embed_sum);
+    team_emit_row<K>(zr, bank_t, top.id, (int64_t)n, D, M, lane & 3, lane < 4, read, q1, idx, sse_px, counts, embed_sum,
+                     read_planes, read_plane_stride);
   }
 }
 
@@ -450,10 +453,10 @@ static int launch_filter(const void* zp, const void* bank_hi, AddrParams& p, int
 
 // z fp32 [N][D] (+ optional pre-packed bf16 copy zp), bank_t fp32 [M][D], en2 [M]  ->  outputs as address_kernel.
 // `ws` must provide addr_tc_ws_bytes(); stats[0] += rows that needed the exact fallback.
-int run_address_tc(const float* z, const __nv_bfloat16* zp_in, const float* bank_t, const float* en2, float* read,
+int run_address_tc(const float* z, __nv_bfloat16* read_planes, const float* bank_t, const float* en2, float* read,
                    float* q1, int64_t* idx, float* sse_px, float* counts, float* embed_sum, int* stats, Workspace& ws,
                    int64_t N, int D, int M, int k, cudaStream_t st) {
-  (void)zp_in;
+  const long long rps = (long long)N * k * D;
   const int bn = addr_block_n(M);
   const int Mpad = (int)align_up(M, bn);
   __nv_bfloat16* zp = ws.take<__nv_bfloat16>((size_t)N * D);
@@ -482,9 +485,9 @@ int run_address_tc(const float* z, const __nv_bfloat16* zp_in, const float* bank
 #define AMMC_RF_CASE(KK)                                                                                      \
   case KK:                                                                                                    \
     refine_kernel<KK><<<blocks, 256, 0, st>>>(z, cand, cand_cnt, bank_t, en2, read, q1, idx, sse_px, counts,  \
-                                              embed_sum, stats, rescan_list, (int)N, D, M);                   \
+                                              embed_sum, stats, rescan_list, read_planes, rps, (int)N, D, M); \
     rescan_kernel<KK><<<2 * num_sms(), 256, 0, st>>>(z, bank_t, en2, read, q1, idx, sse_px, counts, embed_sum, \
-                                                     stats, rescan_list, D, M);                               \
+                                                     stats, rescan_list, read_planes, rps, D, M);             \
     break;
     AMMC_RF_CASE(1) AMMC_RF_CASE(2) AMMC_RF_CASE(3) AMMC_RF_CASE(4)
 #undef AMMC_RF_CASE

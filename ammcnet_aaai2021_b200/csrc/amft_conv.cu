@@ -169,16 +169,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           y[j] = p.relu ? fmaxf(a, 0.f) : a;
         }
         if (valid) {
-          if (p.out_nchw) {
-            const size_t hw = (size_t)p.H * p.W;
-            size_t o = ((size_t)img * p.Cout + cbase) * hw + (size_t)hh * p.W + ww;
+          const size_t hw = (size_t)p.H * p.W;
+          const size_t o0 = ((size_t)img * p.Cout + cbase) * hw + (size_t)hh * p.W + ww;
+          if (p.res_nchw) {                      // residual first: both output forms carry it
+            size_t o = o0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float a = y[j];
-              if (p.res_nchw) a += __ldg(p.res_nchw + o);
-              p.out_nchw[o] = a;
-              o += hw;
-            }
+            for (int j = 0; j < 32; ++j) { y[j] += __ldg(p.res_nchw + o); o += hw; }
+          }
+          if (p.out_nchw) {
+            size_t o = o0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { p.out_nchw[o] = y[j]; o += hw; }
           }
           if (p.out_planes) {
             const size_t pix = ((size_t)img * p.H + hh) * p.W + ww;
@@ -227,8 +228,10 @@ constexpr int PAIR_STAGE_BYTES = A_BYTES + PAIR_B_BYTES;       // 32 KB
 constexpr int PAIR_STAGES = 6;
 constexpr int PAIR_BAR_OFFSET = PAIR_STAGES * PAIR_STAGE_BYTES;
 constexpr int PAIR_SMEM = PAIR_BAR_OFFSET + 256 + 1024;
+constexpr int PAIR_EPI_WARPS = 8;
+constexpr int PAIR_THREADS = 64 + 32 * PAIR_EPI_WARPS;    // warp 0: TMA, warp 1: MMA, warps 2-9: epilogue
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1)
 conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -250,7 +253,7 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     ptx::prefetch_tensormap(&tmA);
     ptx::prefetch_tensormap(&tmB);
     for (int s = 0; s < PAIR_STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
-    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tmem_full[a], 1); ptx::mbar_init(&tmem_empty[a], 256); }
+    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tmem_full[a], 1); ptx::mbar_init(&tmem_empty[a], 2 * 32 * PAIR_EPI_WARPS); }
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
@@ -314,10 +317,15 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       }
     }
   } else {
-    // -------------------------------------------------------------------- epilogue warps (both CTAs, own 128 rows)
+    // -------------------------------------------------------------------- epilogue: 8 warps per CTA (own 128 rows);
+    // two warps share a TMEM lane quarter and split the 256 columns -> twice the loads/stores in flight, which is what
+    // bounds the kernel when K is short (the 1x1 `dec` GEMM: 2 K-blocks per tile, epilogue exposed)
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int r = q * 32 + lane;
     const int per_img = p.W_box * p.H_box;
+    constexpr int HALF_N = PAIR_N / 2;
+    const size_t hw = (size_t)p.H * p.W;
     int it = 0;
     for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
       const int acc = it & 1;
@@ -327,52 +335,60 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       const int rem = r % per_img;
       const int hh = (mt % p.groups_h) * p.H_box + rem / p.W_box, ww = rem % p.W_box;
       const bool valid = img < p.b && mt < p.tiles_m;
-      const int n0 = nt * PAIR_N;
+      const int n0 = nt * PAIR_N + half * HALF_N;
+      const size_t obase = ((size_t)img * p.Cout + n0) * hw + (size_t)hh * p.W + ww;
+      const bool has_res = valid && p.res_nchw != nullptr;
       ptx::mbar_wait(&tmem_full[acc], acc_ph, 44);
       ptx::tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * PAIR_N;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * PAIR_N + half * HALF_N;
 #pragma unroll 1
-      for (int c32 = 0; c32 < PAIR_N / 32; ++c32) {
-        uint32_t v[32];
-        ptx::tmem_ld_32x32(taddr + c32 * 32, v);
-        ptx::tmem_ld_wait();
-        const int cbase = n0 + c32 * 32;
-        float y[32];
+      for (int c16 = 0; c16 < HALF_N / 16; ++c16) {       // 16 columns at a time: v[16] + rv[16] stay in registers
+        float rv[16];
+        const size_t oc = obase + (size_t)c16 * 16 * hw;
+        if (has_res) {                    // issue the residual loads first: they overlap the TMEM read below
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float a = __uint_as_float(v[j]);
-          a = fmaf(a, __ldg(p.scale + cbase + j), __ldg(p.shift + cbase + j));
-          y[j] = p.relu ? fmaxf(a, 0.f) : a;
+          for (int j = 0; j < 16; ++j) rv[j] = __ldg(p.res_nchw + oc + (size_t)j * hw);
+        }
+        uint32_t v[16];
+        ptx::tmem_ld_32x16(taddr + c16 * 16, v);
+        ptx::tmem_ld_wait();
+        const int cbase = n0 + c16 * 16;
+#pragma unroll
+        for (int g4 = 0; g4 < 4; ++g4) {
+          const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + cbase + 4 * g4));
+          const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + cbase + 4 * g4));
+          const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float a = fmaf(__uint_as_float(v[4 * g4 + j]), scv[j], shv[j]);
+            a = p.relu ? fmaxf(a, 0.f) : a;
+            v[4 * g4 + j] = __float_as_uint(has_res ? a + rv[4 * g4 + j] : a);
+          }
         }
         if (valid) {
           if (p.out_nchw) {
-            const size_t hw = (size_t)p.H * p.W;
-            size_t o = ((size_t)img * p.Cout + cbase) * hw + (size_t)hh * p.W + ww;
+            size_t o = oc;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float a = y[j];
-              if (p.res_nchw) a += __ldg(p.res_nchw + o);
-              p.out_nchw[o] = a;
-              o += hw;
-            }
+            for (int j = 0; j < 16; ++j) { p.out_nchw[o] = __uint_as_float(v[j]); o += hw; }
           }
           if (p.out_planes) {
             const size_t pix = ((size_t)img * p.H + hh) * p.W + ww;
             __nv_bfloat16* hi = p.out_planes + pix * p.Cout + cbase;
             __nv_bfloat16* lo = hi + p.out_plane_stride;
-            uint32_t hp[16], lp[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              __nv_bfloat16 h0 = __float2bfloat16_rn(y[2 * j]), h1 = __float2bfloat16_rn(y[2 * j + 1]);
-              __nv_bfloat16 l0 = __float2bfloat16_rn(y[2 * j] - __bfloat162float(h0));
-              __nv_bfloat16 l1 = __float2bfloat16_rn(y[2 * j + 1] - __bfloat162float(h1));
-              hp[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-              lp[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-            }
+            for (int g8 = 0; g8 < 2; ++g8) {               // 8 channels (16 B per plane) at a time
+              uint32_t hp[4], lp[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              reinterpret_cast<uint4*>(hi)[j] = make_uint4(hp[4 * j], hp[4 * j + 1], hp[4 * j + 2], hp[4 * j + 3]);
-              reinterpret_cast<uint4*>(lo)[j] = make_uint4(lp[4 * j], lp[4 * j + 1], lp[4 * j + 2], lp[4 * j + 3]);
+              for (int j = 0; j < 4; ++j) {
+                const float y0 = __uint_as_float(v[8 * g8 + 2 * j]), y1 = __uint_as_float(v[8 * g8 + 2 * j + 1]);
+                const __nv_bfloat16 h0 = __float2bfloat16_rn(y0), h1 = __float2bfloat16_rn(y1);
+                const __nv_bfloat16 l0 = __float2bfloat16_rn(y0 - __bfloat162float(h0));
+                const __nv_bfloat16 l1 = __float2bfloat16_rn(y1 - __bfloat162float(h1));
+                hp[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                lp[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+              }
+              reinterpret_cast<uint4*>(hi)[g8] = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+              reinterpret_cast<uint4*>(lo)[g8] = make_uint4(lp[0], lp[1], lp[2], lp[3]);
             }
           }
         }
@@ -513,6 +529,21 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const Con
 
 static int g_conv_pair_mode = 1;   // 1: CTA-pair kernel when Cout % 256 == 0; 0: single-CTA kernel everywhere
 
+bool conv_shape_supported(int b, int Cin, int Cout, int h, int w) {
+  if (b <= 0 || h <= 0 || w <= 0 || Cin % 64 != 0 || Cout % 64 != 0) return false;
+  if (w > 128 || (128 % w) != 0) return false;
+  const int hb = min(h, 128 / w);
+  return h % hb == 0 && (128 % (w * hb)) == 0;
+}
+
+// w [Cout][Cin] fp32 -> [2][Cout][Cin] bf16 planes (1x1 conv / plain GEMM weights)
+int pack_weights_1x1(const float* w, void* wp, int Cout, int Cin, cudaStream_t st) {
+  const long long total = (long long)Cout * Cin;
+  pack_weights_kernel<<<ceil_div(total, 256), 256, 0, st>>>(w, (__nv_bfloat16*)wp, Cout, Cin, 1);
+  AMMC_LAUNCH_CHECK("pack_weights_kernel");
+  return 0;
+}
+
 // Shared by the 3x3 (ntaps = 9) and 1x1 (ntaps = 1) entry points.
 int conv_igemm(const void* xp, const void* wp, const float* scale, const float* shift, void* out_planes,
                float* out_nchw, const float* res_nchw, int b, int Cin, int Cout, int h, int w, int ntaps,
@@ -577,7 +608,7 @@ int conv_igemm(const void* xp, const void* wp, const float* scale, const float* 
     }
     const int pair_tiles = ((p.tiles_m + 1) / 2) * p.tiles_n;
     const int clusters = min(num_sms() / 2, pair_tiles);
-    conv_igemm_pair_kernel<<<2 * clusters, CONV_THREADS, PAIR_SMEM, st>>>(tmA, tmB, p);
+    conv_igemm_pair_kernel<<<2 * clusters, PAIR_THREADS, PAIR_SMEM, st>>>(tmA, tmB, p);
     AMMC_LAUNCH_CHECK("conv_igemm_pair_kernel");
     return 0;
   }

@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(256) address_kernel(
     const float* __restrict__ z, const float* __restrict__ embed, const float* __restrict__ en2,
     const float* __restrict__ bank_t, float* __restrict__ read, float* __restrict__ q1,
     int64_t* __restrict__ idx, float* __restrict__ sse_px, float* __restrict__ counts,
-    float* __restrict__ embed_sum, int N, int D, int M) {
+    float* __restrict__ embed_sum, __nv_bfloat16* __restrict__ read_planes, int N, int D, int M) {
   __shared__ __align__(16) float Zs[16][68];
   __shared__ __align__(16) float Es[16][64];
   __shared__ float Ds[64][65];
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(256) address_kernel(
 #pragma unroll
   for (int i = 0; i < K; ++i) top.id[i] = min(top.id[i], M - 1);
   team_emit_row<K>(z + (size_t)(team_valid ? n_team : 0) * D, bank_t, top.id, (int64_t)n_team, D, M, part, team_valid,
-                   read, q1, idx, sse_px, counts, embed_sum);
+                   read, q1, idx, sse_px, counts, embed_sum, read_planes, (long long)N * K * D);
 }
 
 __global__ void sse_frame_kernel(const float* __restrict__ sse_px, float* __restrict__ sse_frame, int64_t rows) {
@@ -573,16 +573,25 @@ __global__ void gdec_w_kernel(const float* __restrict__ G, const float* __restri
 // host side
 // ------------------------------------------------------------------------------------------------
 struct MemWs {
-  int* stats; float* bank_t; float* en2; float* T; float* sse_px; __nv_bfloat16* zp;
+  int* stats; float* bank_t; float* en2; float* T; float* sse_px; __nv_bfloat16* read_planes;
 };
+
 
 // addr_tc.cu
 size_t addr_tc_ws_bytes(int64_t N, int D, int M);
 bool addr_tc_supported(int64_t N, int D, int M, int k);
-int run_address_tc(const float* z, const __nv_bfloat16* zp_in, const float* bank_t, const float* en2, float* read,
+int run_address_tc(const float* z, __nv_bfloat16* read_planes, const float* bank_t, const float* en2, float* read,
                    float* q1, int64_t* idx, float* sse_px, float* counts, float* embed_sum, int* stats, Workspace& ws,
                    int64_t N, int D, int M, int k, cudaStream_t st);
 
+// amft_conv.cu
+bool conv_shape_supported(int b, int Cin, int Cout, int h, int w);
+int pack_weights_1x1(const float* w, void* wp, int Cout, int Cin, cudaStream_t st);
+int conv_igemm(const void* xp, const void* wp, const float* scale, const float* shift, void* out_planes,
+               float* out_nchw, const float* res_nchw, int b, int Cin, int Cout, int h, int w, int ntaps, int precision,
+               int relu, cudaStream_t st);
+
+static int g_dec_mode = 0;    // 0 auto, 1 fp32 table gather (CUDA cores), 2 tensor-core GEMM (split-bf16 x3)
 static int g_addr_mode = 0;   // 0 auto, 1 generic fp32 (CUDA cores), 2 tensor-core filter + exact refine
 
 static bool use_tc(int64_t N, int D, int M, int k) {
@@ -590,19 +599,33 @@ static bool use_tc(int64_t N, int D, int M, int k) {
   return addr_tc_supported(N, D, M, k);
 }
 
+__global__ void fill_kernel(float* p, float v, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+static bool use_tc_dec(int b, int h, int w, int C, int D, int k) {
+  if (g_dec_mode == 1) return false;
+  return ((k * D) % 64 == 0) && (D % 4 == 0) && conv_shape_supported(b, k * D, C, h, w);
+}
+
 static size_t mem_ws_bytes(int64_t N, int C, int D, int M, int k, bool with_table) {
   size_t s = 256;                                   // stats block: [0] exact-fallback rows, [1] path (1 fp32, 2 tensor)
   s += addr_tc_ws_bytes(N, D, M);
   s += align_up((size_t)M * D * 4, 256);
   s += align_up((size_t)M * 4, 256);
-  if (with_table) s += align_up((size_t)k * M * C * 4, 256);
+  if (with_table) {
+    s += align_up((size_t)k * M * C * 4, 256);                       // dec tables (fp32 gather path)
+    s += align_up((size_t)N * k * D * 2 * 2, 256);                    // read planes (tensor-core dec)
+    s += align_up((size_t)C * k * D * 2 * 2, 256) + align_up((size_t)C * 4, 256);
+  }
   s += align_up((size_t)N * 4, 256);
   return s;
 }
 
 static int carve(Workspace& ws, MemWs& m, int64_t N, int C, int D, int M, int k, bool with_table) {
   m.stats = ws.take<int>(64);
-  m.zp = nullptr;
+  m.read_planes = nullptr;
   m.bank_t = ws.take<float>((size_t)M * D);
   m.en2 = ws.take<float>(M);
   m.T = with_table ? ws.take<float>((size_t)k * M * C) : nullptr;
@@ -615,7 +638,7 @@ template <int K>
 static void launch_address(const float* z, const float* embed, const MemWs& m, float* read, float* q1, int64_t* idx,
                            float* counts, float* embed_sum, int N, int D, int M, cudaStream_t st) {
   address_kernel<K><<<ceil_div(N, 64), 256, 0, st>>>(z, embed, m.en2, m.bank_t, read, q1, idx, m.sse_px, counts,
-                                                      embed_sum, N, D, M);
+                                                      embed_sum, m.read_planes, N, D, M);
 }
 
 static int run_address(const float* z, const float* embed, const MemWs& m, float* read, float* q1, int64_t* idx,
@@ -634,7 +657,8 @@ static int run_address(const float* z, const float* embed, const MemWs& m, float
     AMMC_CUDA_CHECK(cudaMemsetAsync(m.stats + 1, path, 1, st));   // low byte of stats[1] (rest zeroed above)
   }
   if (use_tc(N, D, M, k))
-    return run_address_tc(z, m.zp, m.bank_t, m.en2, read, q1, idx, m.sse_px, counts, embed_sum, m.stats, ws, N, D, M, k, st);
+    return run_address_tc(z, m.read_planes, m.bank_t, m.en2, read, q1, idx, m.sse_px, counts, embed_sum, m.stats, ws, N, D,
+                          M, k, st);
   switch (k) {
     case 1: launch_address<1>(z, embed, m, read, q1, idx, counts, embed_sum, (int)N, D, M, st); break;
     case 2: launch_address<2>(z, embed, m, read, q1, idx, counts, embed_sum, (int)N, D, M, st); break;
@@ -688,9 +712,9 @@ static int check_dims(int64_t N, int C, int D, int M, int k) {
 
 extern "C" int ammc_mem_fwd(const float* x, const float* enc_w, const float* enc_b, const float* embed,
                             const float* dec_w, const float* dec_b, float* out, float* q1, int64_t* idx, float* z,
-                            float* sse_frame, float* diff, float* counts, float* embed_sum, void* workspace,
-                            size_t workspace_bytes, int b, int h, int w, int C, int D, int M, int k, int residual,
-                            void* stream) {
+                            float* sse_frame, float* diff, float* counts, float* embed_sum, void* out_planes,
+                            void* workspace, size_t workspace_bytes, int b, int h, int w, int C, int D, int M, int k,
+                            int residual, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t N = (int64_t)b * h * w;
   const int HW = h * w;
@@ -700,15 +724,37 @@ extern "C" int ammc_mem_fwd(const float* x, const float* enc_w, const float* enc
   Workspace ws(workspace, workspace_bytes);
   MemWs m;
   if (int rc = carve(ws, m, N, C, D, M, k, true)) return rc;
-  dec_table_kernel<<<dim3(ceil_div(C, 32), ceil_div(M, 32), k), dim3(32, 8), 0, st>>>(dec_w, embed, m.T, C, D, M, k);
-  AMMC_LAUNCH_CHECK("dec_table_kernel");
-  enc1x1_kernel<<<dim3(ceil_div(N, 64), ceil_div(D, 64)), 256, 0, st>>>(x, enc_w, enc_b, z, m.zp, (int)N, HW, C, D);
+  const bool tc_dec = use_tc_dec(b, h, w, C, D, k);
+  if (g_dec_mode == 2 && !tc_dec)
+    return fail(AMMC_EUNSUPPORTED, "tensor-core dec needs k*D %% 64 == 0, C %% 64 == 0 and a feature map the conv engine tiles");
+  AMMC_REQUIRE(!out_planes || tc_dec, "out_planes requested but the tensor-core dec path is not in use "
+                                      "(query ammc_mem_dec_uses_tensor first)");
+  __nv_bfloat16* dec_wp = nullptr;
+  float* ones = nullptr;
+  if (tc_dec) {
+    m.read_planes = ws.take<__nv_bfloat16>((size_t)N * k * D * 2);
+    dec_wp = ws.take<__nv_bfloat16>((size_t)C * k * D * 2);
+    ones = ws.take<float>(C);
+    if (!ws.ok()) return fail(AMMC_EWORKSPACE, "workspace too small");
+  } else {
+    dec_table_kernel<<<dim3(ceil_div(C, 32), ceil_div(M, 32), k), dim3(32, 8), 0, st>>>(dec_w, embed, m.T, C, D, M, k);
+    AMMC_LAUNCH_CHECK("dec_table_kernel");
+  }
+  enc1x1_kernel<<<dim3(ceil_div(N, 64), ceil_div(D, 64)), 256, 0, st>>>(x, enc_w, enc_b, z, nullptr, (int)N, HW, C, D);
   AMMC_LAUNCH_CHECK("enc1x1_kernel");
   if (int rc = run_address(z, embed, m, nullptr, q1, idx, counts, embed_sum, N, D, M, k, st, ws)) return rc;
   if (int rc = run_commit(m, sse_frame, diff, N, HW, D, st)) return rc;
+  const float* res = residual ? x : nullptr;
+  if (tc_dec) {
+    // dec(read) as a [N, kD] x [kD, C] GEMM on tcgen05 (split-bf16 x3); bias, residual and -- when asked -- the NHWC
+    // bf16 planes of `out` (the AMFT block's operand) all come out of the same epilogue
+    if (int rc = pack_weights_1x1(dec_w, dec_wp, C, k * D, st)) return rc;
+    fill_kernel<<<ceil_div(C, 256), 256, 0, st>>>(ones, 1.f, C);
+    AMMC_LAUNCH_CHECK("fill_kernel");
+    return conv_igemm(m.read_planes, dec_wp, ones, dec_b, out_planes, out, res, b, k * D, C, h, w, 1, 3, 0, st);
+  }
   const int chunks = 4;
   dim3 grid(ceil_div(N, 32), ceil_div(ceil_div(C, 32), chunks));
-  const float* res = residual ? x : nullptr;
   switch (k) {
 #define AMMC_DEC_CASE(KK) \
   case KK: dec_gather_kernel<KK><<<grid, 256, 0, st>>>(m.T, idx, dec_b, res, out, (int)N, HW, C, M, chunks); break;
@@ -717,6 +763,17 @@ extern "C" int ammc_mem_fwd(const float* x, const float* enc_w, const float* enc
 #undef AMMC_DEC_CASE
   }
   AMMC_LAUNCH_CHECK("dec_gather_kernel");
+  return 0;
+}
+
+extern "C" int ammc_mem_dec_uses_tensor(int b, int h, int w, int C, int D, int M, int k) {
+  (void)M;
+  return use_tc_dec(b, h, w, C, D, k) ? 1 : 0;
+}
+
+extern "C" int ammc_set_dec_mode(int mode) {
+  AMMC_REQUIRE(mode >= 0 && mode <= 2, "dec mode must be 0 (auto), 1 (fp32 table gather) or 2 (tensor-core)");
+  g_dec_mode = mode;
   return 0;
 }
 

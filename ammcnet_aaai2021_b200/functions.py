@@ -75,7 +75,30 @@ PROFILE = {"on": False, "events": []}
 # --------------------------------------------------------------------------------------------------
 # memory module
 # --------------------------------------------------------------------------------------------------
-def mem_forward_raw(x, enc_w, enc_b, embed, dec_w, dec_b, k: int, residual: bool, want_stats: bool):
+def set_dec_mode(mode: str = "auto"):
+    """'auto' | 'fp32' (table gather on CUDA cores) | 'tensor' (split-bf16 x3 GEMM on tcgen05); process-wide."""
+    _capi.call("ammc_set_dec_mode", {"auto": 0, "fp32": 1, "tensor": 2}[mode])
+
+
+def attach_planes(t: torch.Tensor, planes: torch.Tensor):
+    """Remember the NHWC bf16 hi/lo planes of `t` (produced for free by the dec epilogue) so the AMFT block can skip its
+    pack kernel.  The tensor's version counter is recorded: any in-place change of `t` invalidates the planes."""
+    t._ammc_planes = (planes, t._version)
+
+
+def planes_of(t: torch.Tensor):
+    rec = getattr(t, "_ammc_planes", None)
+    if rec is None:
+        return None
+    planes, version = rec
+    b, C, h, w = t.shape
+    if version != t._version or tuple(planes.shape) != (2, b, h, w, C) or planes.device != t.device:
+        return None
+    return planes
+
+
+def mem_forward_raw(x, enc_w, enc_b, embed, dec_w, dec_b, k: int, residual: bool, want_stats: bool,
+                    want_planes: bool = False):
     """One fused-module forward.  Returns dict(out, q1[N,D], idx[N,k], z[N,D], sse_frame[b], diff[1], counts, embed_sum)."""
     _require_cuda_f32(x, enc_w, enc_b, embed, dec_w, dec_b, names=("x", "enc.weight", "enc.bias", "embed", "dec.weight", "dec.bias"))
     if x.dim() != 4:
@@ -97,12 +120,18 @@ def mem_forward_raw(x, enc_w, enc_b, embed, dec_w, dec_b, k: int, residual: bool
     counts = torch.empty((M,), dtype=torch.float32, device=dev) if want_stats else None
     esum = torch.empty((D, M), dtype=torch.float32, device=dev) if want_stats else None
     lib = _capi.load()
+    planes = None
+    if want_planes and lib.ammc_mem_dec_uses_tensor(b, h, w, C, D, M, k):
+        planes = torch.empty((2, b, h, w, C), dtype=torch.bfloat16, device=dev)
     ws = _workspace(lib.ammc_mem_workspace_bytes(b, h, w, C, D, M, k), dev)
     with torch.cuda.device(dev):
         _capi.call("ammc_mem_fwd", _p(x), _p(enc_w.contiguous()), _p(enc_b.contiguous()), _p(embed.contiguous()),
                    _p(dec_w.contiguous()), _p(dec_b.contiguous()), _p(out), _p(q1), _p(idx), _p(z), _p(sse), _p(diff),
-                   _p(counts), _p(esum), _p(ws), ws.numel(), b, h, w, C, D, M, k, int(bool(residual)), _stream())
+                   _p(counts), _p(esum), _p(planes), _p(ws), ws.numel(), b, h, w, C, D, M, k, int(bool(residual)),
+                   _stream())
     _count(8 + (2 if want_stats else 0))
+    if planes is not None:
+        attach_planes(out, planes)
     return dict(out=out, q1=q1, idx=idx, z=z, sse_frame=sse, diff=diff, counts=counts, embed_sum=esum, x=x)
 
 
@@ -149,7 +178,7 @@ class MemoryModuleFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, enc_w, enc_b, embed, dec_w, dec_b, k, residual, want_stats):
         r = mem_forward_raw(x, enc_w.reshape(enc_w.shape[0], -1), enc_b, embed, dec_w.reshape(dec_w.shape[0], -1),
-                            dec_b, k, residual, want_stats)
+                            dec_b, k, residual, want_stats, want_planes=not torch.is_grad_enabled())
         b, C, h, w = r["x"].shape
         D, M = embed.shape
         # training: the caller updates the bank in place right after this forward (EMA, unet.py:298-309);

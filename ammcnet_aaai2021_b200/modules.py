@@ -162,8 +162,11 @@ class bridge(nn.Module):
             x = self.O2F.forward_autograd(zy, zx, self.precision)
             y = self.F20.forward_autograd(zx, zy, self.precision)
             return x, y
-        px = F_.pack_nhwc(zx)
-        py = F_.pack_nhwc(zy)
+        # the memory modules' dec epilogue already wrote the NHWC bf16 planes of its output; otherwise pack here
+        px = F_.planes_of(zx)
+        py = F_.planes_of(zy)
+        px = F_.pack_nhwc(zx) if px is None else px
+        py = F_.pack_nhwc(zy) if py is None else py
         x = self.O2F.forward_fused(py, zx, self.precision)
         y = self.F20.forward_fused(px, zy, self.precision)
         return x, y

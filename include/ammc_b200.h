@@ -62,7 +62,14 @@ int ammc_debug_tma_probe(const void* base, const int64_t* dims5, const int64_t* 
  *   sse_frame[b]            per-frame sum of (e_top1 - z)^2   (the per-frame partial of unet.py:310)
  *   diff     [1]            mean over all N*D elements = reference `diff`                    (unet.py:310,329)
  *   counts   [M], embed_sum [D, M]  (both NULL in eval) assignment statistics of unet.py:298-302
+ *   out_planes [2][b,h,w,C] bf16 or NULL: `out` additionally as NHWC hi/lo planes (the AMFT block's operand), written
+ *              by the same epilogue.  Only allowed when ammc_mem_dec_uses_tensor(...) == 1.
+ * `dec` runs as a split-bf16 x3 GEMM on tcgen05 when k*D % 64 == 0, C % 64 == 0 and the feature map tiles into 128-pixel
+ * boxes (w divides 128); otherwise as an exact fp32 gather of precomputed table rows.  ammc_set_dec_mode: 0 auto,
+ * 1 force the fp32 gather, 2 force the tensor-core GEMM.
  * ------------------------------------------------------------------------------------------------- */
+int ammc_mem_dec_uses_tensor(int b, int h, int w, int C, int D, int M, int k);
+int ammc_set_dec_mode(int mode);
 size_t ammc_mem_workspace_bytes(int b, int h, int w, int C, int D, int M, int k);
 
 /* Addressing path (process-wide): 0 = auto (tensor-core filter + exact fp32 refine when D % 64 == 0, 16 <= M <= 65536, k <= 4,
@@ -77,7 +84,7 @@ int ammc_set_addressing_mode(int mode);
 int ammc_mem_fwd(const float* x, const float* enc_w, const float* enc_b, const float* embed,
                  const float* dec_w, const float* dec_b,
                  float* out, float* q1, int64_t* idx, float* z, float* sse_frame, float* diff,
-                 float* counts, float* embed_sum,
+                 float* counts, float* embed_sum, void* out_planes,
                  void* workspace, size_t workspace_bytes,
                  int b, int h, int w, int C, int D, int M, int k, int residual, void* stream);
 

@@ -255,3 +255,70 @@ def test_shipped_module_uses_tensor_path_and_matches_golden(addressing_mode):
         addressing_mode("tensor")
         q = A.Quantize_topk(32, 50, k=3).to(DEV).eval()
         q(torch.zeros(1, 4, 4, 32, device=DEV))
+
+
+# --------------------------------------------------------------------------------------------------
+# dec on the tensor cores (split-bf16 x3 GEMM, fused residual + NHWC planes) vs the exact fp32 table gather
+# --------------------------------------------------------------------------------------------------
+@pytest.fixture
+def dec_mode():
+    yield F_.set_dec_mode
+    F_.set_dec_mode("auto")
+
+
+def test_tensor_dec_matches_fp32_gather_and_golden(dec_mode):
+    c, g = load_golden("mem_shipped")
+    p, x = _inputs(c)
+    outs = {}
+    for mode in ("fp32", "tensor"):
+        dec_mode(mode)
+        m = _module(c, p).eval()
+        with torch.no_grad():
+            out, diff, q1 = m(x.to(DEV))
+        outs[mode] = (out, diff, q1, m.quan.quantize.last_idx.clone(), F_.planes_of(out))
+    F_.check_pipeline_watchdog()
+    assert torch.equal(outs["fp32"][3], outs["tensor"][3]) and torch.equal(outs["fp32"][2], outs["tensor"][2])
+    assert_close(outs["tensor"][0].cpu(), outs["fp32"][0].cpu(), 1e-4, "dec tensor vs fp32")
+    same = (outs["tensor"][3].cpu() == torch.as_tensor(g["idx_topk"], dtype=torch.int64)).all(1).view(c["b"], c["h"], c["w"])
+    assert_close(outs["tensor"][0].cpu().permute(0, 2, 3, 1)[same], torch.as_tensor(g["out"]).permute(0, 2, 3, 1)[same], 1e-3, "dec tensor vs golden")
+    # the epilogue's NHWC planes are exactly what the pack kernel would produce from `out`
+    assert outs["fp32"][4] is None and outs["tensor"][4] is not None
+    assert torch.equal(outs["tensor"][4], F_.pack_nhwc(outs["tensor"][0]))
+    o = outs["tensor"][0]
+    o.add_(1.0)                                          # in-place change -> the attached planes must be dropped
+    assert F_.planes_of(o) is None
+
+
+def test_bridge_consumes_dec_planes_without_repacking(dec_mode):
+    """Whole starred region: memory modules -> AMFT.  Using the planes from the dec epilogue is bit-identical to packing."""
+    C, D, M, k, b = 512, 64, 256, 2, 3
+    p = synth.path_params(4, C, D, M, k)
+    mods = {}
+    for s in ("rgb", "op"):
+        m = A.enc_quan_dec_res_topk(C, D, M, k=k)
+        pre = s + ".vq_down3."
+        m.load_state_dict({kk[len(pre):]: v for kk, v in p.items() if kk.startswith(pre)}, strict=True)
+        mods[s] = m.to(DEV).eval()
+    br = A.bridge(in_c=C)
+    br.load_state_dict({kk[len("bridge."):]: v for kk, v in p.items() if kk.startswith("bridge.")}, strict=True)
+    br = br.to(DEV).eval()
+    xr, xo = synth.features(41, b, C, 32, 32).to(DEV), synth.features(42, b, C, 32, 32).to(DEV)
+    with torch.no_grad():
+        o_r, _, _ = mods["rgb"](xr)
+        o_o, _, _ = mods["op"](xo)
+        assert F_.planes_of(o_r) is not None and F_.planes_of(o_o) is not None
+        br(o_r.clone(), o_o.clone())                    # warm-up: packs the conv weights / folds BN once
+        n0 = F_.LAUNCHES["count"]
+        y1 = br(o_r, o_o)
+        n_fused = F_.LAUNCHES["count"] - n0
+        n0 = F_.LAUNCHES["count"]
+        y2 = br(o_r.clone(), o_o.clone())               # clones carry no planes -> pack kernels run
+        n_packed = F_.LAUNCHES["count"] - n0
+    assert n_packed == n_fused + 2
+    assert torch.equal(y1[0], y2[0]) and torch.equal(y1[1], y2[1])
+    ref = O.path_forward(xr.cpu(), xo.cpu(), *synth.frames(1, b, 3, 8, 8), p, k)
+    same = (mods["rgb"].quan.quantize.last_idx.cpu() == ref["rgb"]["idx_topk"]).all() and \
+           (mods["op"].quan.quantize.last_idx.cpu() == ref["op"]["idx_topk"]).all()
+    if same:
+        assert_close(y1[0].cpu(), ref["amft_rgb"], 1e-3, "path.amft_rgb")
+        assert_close(y1[1].cpu(), ref["amft_op"], 1e-3, "path.amft_op")

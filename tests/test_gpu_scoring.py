@@ -115,3 +115,44 @@ def test_video_scorer_reproduces_reference_loop_semantics():
         assert len(set(np.round(rec["rgb_fea_comm"][4:], 12))) == 3       # one commit value per 16-clip group
     finally:
         torch.backends.cudnn.allow_tf32 = prev
+
+
+def test_graphed_path_matches_eager():
+    """CUDA-graph replay of memory modules + AMFT + PSNR must reproduce the eager results bit for bit."""
+    from ammcnet_aaai2021_b200 import functions as F_
+    C, D, M, k, b = 512, 64, 256, 2, 4
+    p = synth.path_params(6, C, D, M, k)
+    mods = {}
+    for s in ("rgb", "op"):
+        m = A.enc_quan_dec_res_topk(C, D, M, k=k)
+        pre = s + ".vq_down3."
+        m.load_state_dict({kk[len(pre):]: v for kk, v in p.items() if kk.startswith(pre)}, strict=True)
+        mods[s] = m.to(DEV).eval()
+    br = A.bridge(in_c=C)
+    br.load_state_dict({kk[len("bridge."):]: v for kk, v in p.items() if kk.startswith("bridge.")}, strict=True)
+    br = br.to(DEV).eval()
+
+    def step(xr, xo, gen, gt):
+        o_r, _, _ = mods["rgb"](xr)
+        o_o, _, _ = mods["op"](xo)
+        yr, yo = br(o_r, o_o)
+        return yr, yo, F_.psnr_per_frame(gen, gt), mods["rgb"].quan.quantize.last_sse_frame
+
+    ins = [synth.features(51, b, C, 32, 32).to(DEV), synth.features(52, b, C, 32, 32).to(DEV)]
+    ins += [t.to(DEV) for t in synth.frames(53, b, 3, 64, 64)]
+    with torch.no_grad():
+        eager = [t.clone() for t in step(*ins)]
+    g = A.GraphedPath(step, ins)
+    outs = g(*ins)
+    torch.cuda.synchronize()
+    for a, e in zip(outs, eager):
+        assert torch.equal(a, e)
+    ins2 = [synth.features(61, b, C, 32, 32).to(DEV), synth.features(62, b, C, 32, 32).to(DEV)]
+    ins2 += [t.to(DEV) for t in synth.frames(63, b, 3, 64, 64)]
+    with torch.no_grad():
+        eager2 = [t.clone() for t in step(*ins2)]
+    outs2 = g(*ins2)
+    torch.cuda.synchronize()
+    for a, e in zip(outs2, eager2):
+        assert torch.equal(a, e)
+    F_.check_pipeline_watchdog()
