@@ -26,6 +26,7 @@ SIGNATURES = {
     "ammc_mem_fwd": (I, [P] * 6 + [P] * 6 + [P, P, P] + [P, Z] + [I] * 8 + [P]),
     "ammc_mem_dec_uses_tensor": (I, [I] * 7),
     "ammc_set_dec_mode": (I, [I]),
+    "ammc_set_enc_mode": (I, [I]),
     "ammc_addr_padded_items": (I, [I]),
     "ammc_addr_pack_queries": (I, [P, P, P, L, I, P]),
     "ammc_addr_pack_bank": (I, [P] * 6 + [I, I, P]),

@@ -453,9 +453,10 @@ static int launch_filter(const void* zp, const void* bank_hi, AddrParams& p, int
 
 // z fp32 [N][D] (+ optional pre-packed bf16 copy zp), bank_t fp32 [M][D], en2 [M]  ->  outputs as address_kernel.
 // `ws` must provide addr_tc_ws_bytes(); stats[0] += rows that needed the exact fallback.
-int run_address_tc(const float* z, __nv_bfloat16* read_planes, const float* bank_t, const float* en2, float* read,
-                   float* q1, int64_t* idx, float* sse_px, float* counts, float* embed_sum, int* stats, Workspace& ws,
-                   int64_t N, int D, int M, int k, cudaStream_t st) {
+int run_address_tc(const float* z, const __nv_bfloat16* zp_in, const float* znorm2_in, __nv_bfloat16* read_planes,
+                   const float* bank_t, const float* en2, float* read, float* q1, int64_t* idx, float* sse_px,
+                   float* counts, float* embed_sum, int* stats, Workspace& ws, int64_t N, int D, int M, int k,
+                   cudaStream_t st) {
   const long long rps = (long long)N * k * D;
   const int bn = addr_block_n(M);
   const int Mpad = (int)align_up(M, bn);
@@ -468,8 +469,13 @@ int run_address_tc(const float* z, __nv_bfloat16* read_planes, const float* bank
   int* rescan_list = ws.take<int>(N);
   float* emax = ws.take<float>(1);
   if (!ws.ok()) return fail(AMMC_EWORKSPACE, "workspace too small");
-  pack_rows_bf16_kernel<<<ceil_div(N, 8), 256, 0, st>>>(z, zp, znorm2, N, D);
-  AMMC_LAUNCH_CHECK("pack_rows_bf16_kernel");
+  if (zp_in && znorm2_in) {                  // the tensor-core enc epilogue already produced bf16(z) and ||z||^2
+    zp = const_cast<__nv_bfloat16*>(zp_in);
+    znorm2 = const_cast<float*>(znorm2_in);
+  } else {
+    pack_rows_bf16_kernel<<<ceil_div(N, 8), 256, 0, st>>>(z, zp, znorm2, N, D);
+    AMMC_LAUNCH_CHECK("pack_rows_bf16_kernel");
+  }
   AMMC_CUDA_CHECK(cudaMemsetAsync(emax, 0, 4, st));
   bank_pack_kernel<<<Mpad, 128, 0, st>>>(bank_t, en2, bank_hi, en2pad, emax, D, M, Mpad);
   AMMC_LAUNCH_CHECK("bank_pack_kernel");

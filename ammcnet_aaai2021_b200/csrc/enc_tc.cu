@@ -1,0 +1,249 @@
+// `enc` 1x1 convolution of the memory module on the tensor cores, straight from the fp32 NCHW features.
+//
+//   z[n, :] = enc_w . x[n, :] + enc_b        (reference Code/models/unet.py:321,326)    C -> D = 64
+//
+// x is what the cuDNN encoder leaves in HBM: NCHW fp32, i.e. for a pixel tile the *pixels* are contiguous and the
+// contraction axis (channels) is strided -- not a layout tcgen05 can consume as fp32.  Instead of a separate pack pass
+// (read 134 MB + write 134 MB at b=64) the kernel converts on the fly:
+//   warp 0      TMA: fp32 box [64 channels][128 pixels] (no swizzle) + the matching 64-channel slices of the bf16 hi/lo
+//               weight planes [64 d][64 ch] (128B swizzle) per pipeline stage
+//   warps 2-5   converters: thread = pixel; read its 64 staged fp32 values, split x = hi + lo (bf16), write both as rows
+//               of the canonical K-major 128B-swizzled UMMA tile (16-byte chunk index XOR (row & 7)), then
+//               fence.proxy.async + mbarrier arrive
+//   warp 1      MMA: per stage  hi*W_hi + hi*W_lo + lo*W_hi  (M128 x N64 x K16, fp32 accumulate in TMEM)
+//   warps 6-9   epilogue: + bias -> z fp32 [N, D], its bf16 rounding zp (the addressing filter's operand) and ||z||^2
+// Error of the split-bf16 x3 product: ~2^-17 relative (measured on the conv kernel), i.e. z agrees with the fp32 FFMA
+// kernel to ~1e-5; the exact fp32 refine stage then ranks the candidates with that z.
+#include "common.cuh"
+#include "ptx.cuh"
+#include <cuda_bf16.h>
+
+namespace ammc {
+
+constexpr int ENC_THREADS = 320;
+constexpr int ENC_D = 64;                          // output channels handled by this kernel
+constexpr int ENC_BK = 64;                         // channels per stage
+constexpr int ENC_STAGE_X = ENC_BK * 128 * 4;      // fp32 staging [64 ch][128 px]            32 KB
+constexpr int ENC_STAGE_A = 128 * ENC_BK * 2;      // one bf16 A tile [128 px][64 ch]          16 KB
+constexpr int ENC_STAGE_W = ENC_D * ENC_BK * 2;    // one bf16 weight slice [64 d][64 ch]       8 KB
+constexpr int ENC_STAGE = ENC_STAGE_X + 2 * ENC_STAGE_A + 2 * ENC_STAGE_W;   // 80 KB
+constexpr int ENC_STAGES = 2;
+constexpr int ENC_BAR_OFFSET = ENC_STAGES * ENC_STAGE;
+constexpr int ENC_SMEM = ENC_BAR_OFFSET + 256 + 1024;
+
+struct EncParams {
+  int N, HW, C, tiles;
+  const float* bias;
+  float* z;                 // [N][64]
+  __nv_bfloat16* zp;        // [N][64] or null
+  float* znorm2;            // [N] or null
+};
+
+__global__ void __launch_bounds__(ENC_THREADS, 1)
+enc_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const EncParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + ENC_BAR_OFFSET);   // TMA landed (x staging + weight slices)
+  uint64_t* conv_bar = full_bar + ENC_STAGES;                                // converters wrote the A tiles
+  uint64_t* empty_bar = conv_bar + ENC_STAGES;                               // MMAs of the stage retired
+  uint64_t* tmem_full = empty_bar + ENC_STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kb_per_tile = p.C / ENC_BK;
+  const int tiles_per_img = p.HW / 128;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tmX);
+    ptx::prefetch_tensormap(&tmW);
+    for (int s = 0; s < ENC_STAGES; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&conv_bar[s], 128);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tmem_full[a], 1); ptx::mbar_init(&tmem_empty[a], 128); }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, 2 * ENC_D);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
+        const int img = t / tiles_per_img, p0 = (t % tiles_per_img) * 128;
+        for (int kb = 0; kb < kb_per_tile; ++kb) {
+          ptx::mbar_wait(&empty_bar[s], ph ^ 1, 51);
+          ptx::mbar_expect_tx(&full_bar[s], ENC_STAGE_X + 2 * ENC_STAGE_W);
+          uint8_t* base = smem + s * ENC_STAGE;
+          ptx::tma_load_3d(base, &tmX, &full_bar[s], p0, kb * ENC_BK, img);
+          ptx::tma_load_3d(base + ENC_STAGE_X + 2 * ENC_STAGE_A, &tmW, &full_bar[s], kb * ENC_BK, 0, 0);
+          ptx::tma_load_3d(base + ENC_STAGE_X + 2 * ENC_STAGE_A + ENC_STAGE_W, &tmW, &full_bar[s], kb * ENC_BK, 0, 1);
+          if (++s == ENC_STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc(1, 128, ENC_D);
+      int s = 0; uint32_t ph = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < p.tiles; t += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_ph = (it >> 1) & 1;
+        ptx::mbar_wait(&tmem_empty[acc], acc_ph ^ 1, 52);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * ENC_D;
+        for (int kb = 0; kb < kb_per_tile; ++kb) {
+          ptx::mbar_wait(&full_bar[s], ph, 53);      // weight slices landed
+          ptx::mbar_wait(&conv_bar[s], ph, 54);      // A tiles written by the converters
+          ptx::tc_fence_after();
+          const uint32_t base = ptx::smem_u32(smem + s * ENC_STAGE);
+          const uint64_t a_hi = ptx::umma_desc_k_sw128(base + ENC_STAGE_X);
+          const uint64_t a_lo = ptx::umma_desc_k_sw128(base + ENC_STAGE_X + ENC_STAGE_A);
+          const uint64_t w_hi = ptx::umma_desc_k_sw128(base + ENC_STAGE_X + 2 * ENC_STAGE_A);
+          const uint64_t w_lo = ptx::umma_desc_k_sw128(base + ENC_STAGE_X + 2 * ENC_STAGE_A + ENC_STAGE_W);
+#pragma unroll
+          for (int k4 = 0; k4 < ENC_BK / 16; ++k4) {
+            ptx::mma_f16_ss(d_tmem, a_hi + 2 * k4, w_hi + 2 * k4, idesc, (kb | k4) != 0 ? 1u : 0u);
+            ptx::mma_f16_ss(d_tmem, a_hi + 2 * k4, w_lo + 2 * k4, idesc, 1u);
+            ptx::mma_f16_ss(d_tmem, a_lo + 2 * k4, w_hi + 2 * k4, idesc, 1u);
+          }
+          ptx::mma_commit(&empty_bar[s]);
+          if (kb == kb_per_tile - 1) ptx::mma_commit(&tmem_full[acc]);
+          if (++s == ENC_STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp < 6) {
+    // ---------------------------------------------------------------- converters: fp32 staging -> bf16 hi/lo UMMA tiles
+    const int row = (warp - 2) * 32 + lane;                   // pixel within the tile
+    int s = 0; uint32_t ph = 0;
+    for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
+      for (int kb = 0; kb < kb_per_tile; ++kb) {
+        ptx::mbar_wait(&full_bar[s], ph, 55);                 // staging landed (the previous MMAs of this stage retired
+                                                              // before the producer refilled it, so the A tiles are free)
+        uint8_t* base = smem + s * ENC_STAGE;
+        const float* xs = reinterpret_cast<const float*>(base) + row;          // [ch][128 px]
+        uint8_t* a_hi = base + ENC_STAGE_X + row * 128;
+        uint8_t* a_lo = a_hi + ENC_STAGE_A;
+#pragma unroll
+        for (int c8 = 0; c8 < ENC_BK / 8; ++c8) {
+          uint32_t hp[4], lp[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float v0 = xs[(c8 * 8 + 2 * j) * 128], v1 = xs[(c8 * 8 + 2 * j + 1) * 128];
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+            const __nv_bfloat16 l0 = __float2bfloat16_rn(v0 - __bfloat162float(h0));
+            const __nv_bfloat16 l1 = __float2bfloat16_rn(v1 - __bfloat162float(h1));
+            hp[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+            lp[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+          }
+          const int chunk = (c8 ^ (row & 7)) * 16;            // 128B swizzle: 16-byte chunk index XOR (row mod 8)
+          *reinterpret_cast<uint4*>(a_hi + chunk) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+          *reinterpret_cast<uint4*>(a_lo + chunk) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+        }
+        ptx::fence_proxy_async();                             // generic-proxy writes -> visible to the tensor core
+        ptx::mbar_arrive(&conv_bar[s]);
+        if (++s == ENC_STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue: z, bf16(z), ||z||^2
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    int it = 0;
+    for (int t = blockIdx.x; t < p.tiles; t += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_ph = (it >> 1) & 1;
+      const size_t n = (size_t)t * 128 + r;
+      ptx::mbar_wait(&tmem_full[acc], acc_ph, 56);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ENC_D;
+      float zn2 = 0.f;
+#pragma unroll
+      for (int c32 = 0; c32 < ENC_D / 32; ++c32) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32(taddr + c32 * 32, v);
+        ptx::tmem_ld_wait();
+        float* zr = p.z + n * ENC_D + c32 * 32;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + c32 * 32 + 4 * g));
+          float4 o;
+          o.x = __uint_as_float(v[4 * g + 0]) + b4.x; o.y = __uint_as_float(v[4 * g + 1]) + b4.y;
+          o.z = __uint_as_float(v[4 * g + 2]) + b4.z; o.w = __uint_as_float(v[4 * g + 3]) + b4.w;
+          reinterpret_cast<float4*>(zr)[g] = o;
+          zn2 = fmaf(o.x, o.x, zn2); zn2 = fmaf(o.y, o.y, zn2); zn2 = fmaf(o.z, o.z, zn2); zn2 = fmaf(o.w, o.w, zn2);
+          if (p.zp) {
+            const __nv_bfloat162 p0 = __floats2bfloat162_rn(o.x, o.y), p1 = __floats2bfloat162_rn(o.z, o.w);
+            uint2 pk;
+            pk.x = *reinterpret_cast<const uint32_t*>(&p0);
+            pk.y = *reinterpret_cast<const uint32_t*>(&p1);
+            *reinterpret_cast<uint2*>(p.zp + n * ENC_D + c32 * 32 + 4 * g) = pk;
+          }
+        }
+      }
+      if (p.znorm2) p.znorm2[n] = zn2;
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 2 * ENC_D);
+  }
+}
+
+int make_map_generic(CUtensorMap* m, const void* base, int elem_bytes, int rank, const uint64_t* dims,
+                     const uint64_t* strides, const uint32_t* box, int swizzle128);   // amft_conv.cu
+int pack_weights_1x1(const float* w, void* wp, int Cout, int Cin, cudaStream_t st);
+
+bool enc_tc_supported(int b, int HW, int C, int D) { return D == ENC_D && C % ENC_BK == 0 && HW % 128 == 0 && b > 0; }
+
+size_t enc_tc_ws_bytes(int C) { return align_up((size_t)2 * ENC_D * C * 2, 256); }
+
+// x [b][C][HW] fp32, enc_w [64][C] fp32 -> z [N][64] (+ zp, znorm2 when non-null).  wp_ws: enc_tc_ws_bytes(C).
+int run_enc_tc(const float* x, const float* enc_w, const float* enc_b, float* z, __nv_bfloat16* zp, float* znorm2,
+               void* wp_ws, int b, int HW, int C, cudaStream_t st) {
+  if (int rc = pack_weights_1x1(enc_w, wp_ws, ENC_D, C, st)) return rc;
+  CUtensorMap tmX, tmW;
+  {
+    uint64_t dims[3] = {(uint64_t)HW, (uint64_t)C, (uint64_t)b};
+    uint64_t strides[2] = {(uint64_t)HW * 4, (uint64_t)C * HW * 4};
+    uint32_t box[3] = {128, (uint32_t)ENC_BK, 1};
+    if (int rc = make_map_generic(&tmX, x, 4, 3, dims, strides, box, 0)) return rc;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)C, (uint64_t)ENC_D, 2};
+    uint64_t strides[2] = {(uint64_t)C * 2, (uint64_t)ENC_D * C * 2};
+    uint32_t box[3] = {(uint32_t)ENC_BK, (uint32_t)ENC_D, 1};
+    if (int rc = make_map_generic(&tmW, wp_ws, 2, 3, dims, strides, box, 1)) return rc;
+  }
+  EncParams p;
+  p.N = b * HW; p.HW = HW; p.C = C; p.tiles = b * (HW / 128);
+  p.bias = enc_b; p.z = z; p.zp = zp; p.znorm2 = znorm2;
+  static bool configured[64] = {false};
+  int dev = 0;
+  AMMC_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && !configured[dev]) {
+    AMMC_CUDA_CHECK(cudaFuncSetAttribute(enc_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ENC_SMEM));
+    configured[dev] = true;
+  }
+  enc_tc_kernel<<<min(num_sms(), p.tiles), ENC_THREADS, ENC_SMEM, st>>>(tmX, tmW, p);
+  AMMC_LAUNCH_CHECK("enc_tc_kernel");
+  return 0;
+}
+
+AMMC_DEFINE_TIMEOUT_READER(timeout_reader_enc)
+
+}  // namespace ammc

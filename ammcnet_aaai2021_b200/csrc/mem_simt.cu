@@ -574,15 +574,22 @@ __global__ void gdec_w_kernel(const float* __restrict__ G, const float* __restri
 // ------------------------------------------------------------------------------------------------
 struct MemWs {
   int* stats; float* bank_t; float* en2; float* T; float* sse_px; __nv_bfloat16* read_planes;
+  const __nv_bfloat16* zp; const float* znorm2;     // produced by the tensor-core enc epilogue, else null
 };
 
 
 // addr_tc.cu
 size_t addr_tc_ws_bytes(int64_t N, int D, int M);
 bool addr_tc_supported(int64_t N, int D, int M, int k);
-int run_address_tc(const float* z, __nv_bfloat16* read_planes, const float* bank_t, const float* en2, float* read,
-                   float* q1, int64_t* idx, float* sse_px, float* counts, float* embed_sum, int* stats, Workspace& ws,
-                   int64_t N, int D, int M, int k, cudaStream_t st);
+int run_address_tc(const float* z, const __nv_bfloat16* zp_in, const float* znorm2_in, __nv_bfloat16* read_planes,
+                   const float* bank_t, const float* en2, float* read, float* q1, int64_t* idx, float* sse_px,
+                   float* counts, float* embed_sum, int* stats, Workspace& ws, int64_t N, int D, int M, int k,
+                   cudaStream_t st);
+// enc_tc.cu
+bool enc_tc_supported(int b, int HW, int C, int D);
+size_t enc_tc_ws_bytes(int C);
+int run_enc_tc(const float* x, const float* enc_w, const float* enc_b, float* z, __nv_bfloat16* zp, float* znorm2,
+               void* wp_ws, int b, int HW, int C, cudaStream_t st);
 
 // amft_conv.cu
 bool conv_shape_supported(int b, int Cin, int Cout, int h, int w);
@@ -591,6 +598,7 @@ int conv_igemm(const void* xp, const void* wp, const float* scale, const float* 
                float* out_nchw, const float* res_nchw, int b, int Cin, int Cout, int h, int w, int ntaps, int precision,
                int relu, cudaStream_t st);
 
+static int g_enc_mode = 0;    // 0 auto, 1 fp32 FFMA (CUDA cores), 2 tensor-core GEMM (split-bf16 x3, converts NCHW on the fly)
 static int g_dec_mode = 0;    // 0 auto, 1 fp32 table gather (CUDA cores), 2 tensor-core GEMM (split-bf16 x3)
 static int g_addr_mode = 0;   // 0 auto, 1 generic fp32 (CUDA cores), 2 tensor-core filter + exact refine
 
@@ -618,6 +626,7 @@ static size_t mem_ws_bytes(int64_t N, int C, int D, int M, int k, bool with_tabl
     s += align_up((size_t)k * M * C * 4, 256);                       // dec tables (fp32 gather path)
     s += align_up((size_t)N * k * D * 2 * 2, 256);                    // read planes (tensor-core dec)
     s += align_up((size_t)C * k * D * 2 * 2, 256) + align_up((size_t)C * 4, 256);
+    s += enc_tc_ws_bytes(C) + align_up((size_t)N * D * 2, 256) + align_up((size_t)N * 4, 256);   // tensor-core enc
   }
   s += align_up((size_t)N * 4, 256);
   return s;
@@ -626,6 +635,8 @@ static size_t mem_ws_bytes(int64_t N, int C, int D, int M, int k, bool with_tabl
 static int carve(Workspace& ws, MemWs& m, int64_t N, int C, int D, int M, int k, bool with_table) {
   m.stats = ws.take<int>(64);
   m.read_planes = nullptr;
+  m.zp = nullptr;
+  m.znorm2 = nullptr;
   m.bank_t = ws.take<float>((size_t)M * D);
   m.en2 = ws.take<float>(M);
   m.T = with_table ? ws.take<float>((size_t)k * M * C) : nullptr;
@@ -657,8 +668,8 @@ static int run_address(const float* z, const float* embed, const MemWs& m, float
     AMMC_CUDA_CHECK(cudaMemsetAsync(m.stats + 1, path, 1, st));   // low byte of stats[1] (rest zeroed above)
   }
   if (use_tc(N, D, M, k))
-    return run_address_tc(z, m.read_planes, m.bank_t, m.en2, read, q1, idx, m.sse_px, counts, embed_sum, m.stats, ws, N, D,
-                          M, k, st);
+    return run_address_tc(z, m.zp, m.znorm2, m.read_planes, m.bank_t, m.en2, read, q1, idx, m.sse_px, counts, embed_sum,
+                          m.stats, ws, N, D, M, k, st);
   switch (k) {
     case 1: launch_address<1>(z, embed, m, read, q1, idx, counts, embed_sum, (int)N, D, M, st); break;
     case 2: launch_address<2>(z, embed, m, read, q1, idx, counts, embed_sum, (int)N, D, M, st); break;
@@ -740,8 +751,21 @@ extern "C" int ammc_mem_fwd(const float* x, const float* enc_w, const float* enc
     dec_table_kernel<<<dim3(ceil_div(C, 32), ceil_div(M, 32), k), dim3(32, 8), 0, st>>>(dec_w, embed, m.T, C, D, M, k);
     AMMC_LAUNCH_CHECK("dec_table_kernel");
   }
-  enc1x1_kernel<<<dim3(ceil_div(N, 64), ceil_div(D, 64)), 256, 0, st>>>(x, enc_w, enc_b, z, nullptr, (int)N, HW, C, D);
-  AMMC_LAUNCH_CHECK("enc1x1_kernel");
+  const bool tc_enc = g_enc_mode != 1 && enc_tc_supported(b, HW, C, D);
+  if (g_enc_mode == 2 && !tc_enc)
+    return fail(AMMC_EUNSUPPORTED, "tensor-core enc needs embed_dim == 64, C %% 64 == 0 and h*w %% 128 == 0");
+  if (tc_enc) {
+    void* enc_wp = ws.take<__nv_bfloat16>((size_t)2 * D * C);
+    __nv_bfloat16* zp = ws.take<__nv_bfloat16>((size_t)N * D);
+    float* zn2 = ws.take<float>(N);
+    if (!ws.ok()) return fail(AMMC_EWORKSPACE, "workspace too small");
+    if (int rc = run_enc_tc(x, enc_w, enc_b, z, zp, zn2, enc_wp, b, HW, C, st)) return rc;
+    m.zp = zp;
+    m.znorm2 = zn2;
+  } else {
+    enc1x1_kernel<<<dim3(ceil_div(N, 64), ceil_div(D, 64)), 256, 0, st>>>(x, enc_w, enc_b, z, nullptr, (int)N, HW, C, D);
+    AMMC_LAUNCH_CHECK("enc1x1_kernel");
+  }
   if (int rc = run_address(z, embed, m, nullptr, q1, idx, counts, embed_sum, N, D, M, k, st, ws)) return rc;
   if (int rc = run_commit(m, sse_frame, diff, N, HW, D, st)) return rc;
   const float* res = residual ? x : nullptr;
@@ -769,6 +793,12 @@ extern "C" int ammc_mem_fwd(const float* x, const float* enc_w, const float* enc
 extern "C" int ammc_mem_dec_uses_tensor(int b, int h, int w, int C, int D, int M, int k) {
   (void)M;
   return use_tc_dec(b, h, w, C, D, k) ? 1 : 0;
+}
+
+extern "C" int ammc_set_enc_mode(int mode) {
+  AMMC_REQUIRE(mode >= 0 && mode <= 2, "enc mode must be 0 (auto), 1 (fp32 FFMA) or 2 (tensor-core)");
+  g_enc_mode = mode;
+  return 0;
 }
 
 extern "C" int ammc_set_dec_mode(int mode) {

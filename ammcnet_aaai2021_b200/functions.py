@@ -80,6 +80,11 @@ def set_dec_mode(mode: str = "auto"):
     _capi.call("ammc_set_dec_mode", {"auto": 0, "fp32": 1, "tensor": 2}[mode])
 
 
+def set_enc_mode(mode: str = "auto"):
+    """'auto' | 'fp32' (FFMA GEMM on CUDA cores) | 'tensor' (split-bf16 x3 on tcgen05, NCHW converted on the fly)."""
+    _capi.call("ammc_set_enc_mode", {"auto": 0, "fp32": 1, "tensor": 2}[mode])
+
+
 def attach_planes(t: torch.Tensor, planes: torch.Tensor):
     """Remember the NHWC bf16 hi/lo planes of `t` (produced for free by the dec epilogue) so the AMFT block can skip its
     pack kernel.  The tensor's version counter is recorded: any in-place change of `t` invalidates the planes."""

@@ -70,6 +70,10 @@ int ammc_debug_tma_probe(const void* base, const int64_t* dims5, const int64_t* 
  * ------------------------------------------------------------------------------------------------- */
 int ammc_mem_dec_uses_tensor(int b, int h, int w, int C, int D, int M, int k);
 int ammc_set_dec_mode(int mode);
+/* `enc` runs as a split-bf16 x3 GEMM on tcgen05 that converts the fp32 NCHW input on the fly (and emits bf16(z) and
+ * ||z||^2 for the addressing filter) when embed_dim == 64, C % 64 == 0 and h*w % 128 == 0; otherwise as an fp32 FFMA
+ * GEMM.  ammc_set_enc_mode: 0 auto, 1 force fp32 FFMA, 2 force the tensor-core kernel. */
+int ammc_set_enc_mode(int mode);
 size_t ammc_mem_workspace_bytes(int b, int h, int w, int C, int D, int M, int k);
 
 /* Addressing path (process-wide): 0 = auto (tensor-core filter + exact fp32 refine when D % 64 == 0, 16 <= M <= 65536, k <= 4,

@@ -322,3 +322,42 @@ def test_bridge_consumes_dec_planes_without_repacking(dec_mode):
     if same:
         assert_close(y1[0].cpu(), ref["amft_rgb"], 1e-3, "path.amft_rgb")
         assert_close(y1[1].cpu(), ref["amft_op"], 1e-3, "path.amft_op")
+
+
+@pytest.fixture
+def enc_mode():
+    yield F_.set_enc_mode
+    F_.set_enc_mode("auto")
+
+
+@pytest.mark.parametrize("b,h,w", [(2, 8, 16), (3, 32, 32), (1, 16, 8)])
+def test_tensor_enc_matches_fp32_enc(b, h, w, enc_mode):
+    """enc on tcgen05 (fp32 NCHW converted to split-bf16 on the fly) vs the fp32 FFMA kernel."""
+    C, D, M, k = 512, 64, 256, 2
+    p = synth.memory_params(21, C, D, M, k)
+    x = synth.features(22, b, C, h, w)
+    res = {}
+    for mode in ("fp32", "tensor"):
+        enc_mode(mode)
+        m = A.enc_quan_dec_res_topk(C, D, M, k=k)
+        m.load_state_dict({"quan." + kk: v for kk, v in p.items()})
+        m = m.to(DEV).eval()
+        xg = x.to(DEV).requires_grad_(True)
+        out, diff, q1 = m(xg)
+        (out.sum() + 5.0 * diff.sum()).backward()
+        res[mode] = (out.detach(), diff.detach(), q1.detach(), m.quan.quantize.last_idx.clone(), xg.grad.clone(),
+                     m.quan.enc.weight.grad.clone())
+    F_.check_pipeline_watchdog()
+    o = O.memory_module_forward(x, p["enc.weight"], p["enc.bias"], p["quantize.embed"], p["dec.weight"], p["dec.bias"], k)
+    keep = _no_tie_rows(o["dist"].sort(1)[0][:, :3])
+    for mode in ("fp32", "tensor"):
+        assert torch.equal(res[mode][3].cpu()[keep], o["idx_topk"][keep]), mode
+    agree = (res["fp32"][3] == res["tensor"][3]).all(1)
+    assert agree.float().mean() > 0.995
+    assert_close(res["tensor"][1].cpu(), res["fp32"][1].cpu(), 1e-4, "diff")
+    rows = agree.view(b, h, w)
+    assert_close(res["tensor"][0].permute(0, 2, 3, 1)[rows].cpu(), res["fp32"][0].permute(0, 2, 3, 1)[rows].cpu(), 1e-4, "out")
+    # z itself: q1 - (e - z) is not exposed, but diff and the commit-loss gradient both depend on z linearly
+    if bool(agree.all()):
+        assert_close(res["tensor"][4].cpu(), res["fp32"][4].cpu(), 1e-3, "gx")
+        assert_close(res["tensor"][5].cpu(), res["fp32"][5].cpu(), 1e-3, "g_enc_w")
