@@ -32,7 +32,7 @@ struct ConvParams {
   int b, H, W, Cin, Cout;
   int W_box, H_box, B_box, groups_h;
   int tiles_m, tiles_n, ntaps;
-  int n_pass, pass_a[3], pass_b[3];
+  int n_pass;               // 1: hi*hi only; 3: (hi,hi) + (hi,lo) + (lo,hi)
   int relu;
   const float* scale;
   const float* shift;
@@ -93,7 +93,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int img0 = (mt / p.groups_h) * p.B_box, h0 = (mt % p.groups_h) * p.H_box;
         const int n0 = nt * BLOCK_N;
         for (int ps = 0; ps < p.n_pass; ++ps) {
-          const int pa = p.pass_a[ps], pb = p.pass_b[ps];
+          const int pa = ps == 2 ? 1 : 0, pb = ps == 1 ? 1 : 0;   // (hi,hi) (hi,lo) (lo,hi)
           for (int tap = 0; tap < p.ntaps; ++tap) {
             const int dy = p.ntaps == 9 ? tap / 3 - 1 : 0, dx = p.ntaps == 9 ? tap % 3 - 1 : 0;
             for (int cc = 0; cc < p.Cin / BLOCK_K; ++cc) {
@@ -274,7 +274,7 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         const int img0 = (mt / p.groups_h) * p.B_box, h0 = (mt % p.groups_h) * p.H_box;
         const int n0 = nt * PAIR_N + (int)rank * (PAIR_N / 2);
         for (int ps = 0; ps < p.n_pass; ++ps) {
-          const int pa = p.pass_a[ps], pb = p.pass_b[ps];
+          const int pa = ps == 2 ? 1 : 0, pb = ps == 1 ? 1 : 0;   // (hi,hi) (hi,lo) (lo,hi)
           for (int tap = 0; tap < p.ntaps; ++tap) {
             const int dy = p.ntaps == 9 ? tap / 3 - 1 : 0, dx = p.ntaps == 9 ? tap % 3 - 1 : 0;
             for (int cc = 0; cc < p.Cin / BLOCK_K; ++cc) {
@@ -338,57 +338,71 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       const int n0 = nt * PAIR_N + half * HALF_N;
       const size_t obase = ((size_t)img * p.Cout + n0) * hw + (size_t)hh * p.W + ww;
       const bool has_res = valid && p.res_nchw != nullptr;
-      ptx::mbar_wait(&tmem_full[acc], acc_ph, 44);
-      ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * PAIR_N + half * HALF_N;
+      // 16 columns at a time, software-pipelined two chunks deep: the residual loads of chunks c+1 and c+2 are in
+      // flight while chunk c is converted and stored (the loads are the only latency on the epilogue's critical path)
+      float rv0[16], rv1[16];
+      if (has_res) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) rv0[j] = __ldg(p.res_nchw + obase + (size_t)j * hw);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) rv1[j] = __ldg(p.res_nchw + obase + (size_t)(16 + j) * hw);
+      }
+      ptx::mbar_wait(&tmem_full[acc], acc_ph, 44);        // the first residual loads overlap the tail of the MMAs
+      ptx::tc_fence_after();
 #pragma unroll 1
-      for (int c16 = 0; c16 < HALF_N / 16; ++c16) {       // 16 columns at a time: v[16] + rv[16] stay in registers
-        float rv[16];
-        const size_t oc = obase + (size_t)c16 * 16 * hw;
-        if (has_res) {                    // issue the residual loads first: they overlap the TMEM read below
+      for (int c16 = 0; c16 < HALF_N / 16; c16 += 2) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) rv[j] = __ldg(p.res_nchw + oc + (size_t)j * hw);
-        }
-        uint32_t v[16];
-        ptx::tmem_ld_32x16(taddr + c16 * 16, v);
-        ptx::tmem_ld_wait();
-        const int cbase = n0 + c16 * 16;
+        for (int sub = 0; sub < 2; ++sub) {
+          float (&rv)[16] = sub == 0 ? rv0 : rv1;
+          const int cc = c16 + sub;
+          const size_t oc = obase + (size_t)cc * 16 * hw;
+          uint32_t v[16];
+          ptx::tmem_ld_32x16(taddr + cc * 16, v);
+          ptx::tmem_ld_wait();
+          const int cbase = n0 + cc * 16;
 #pragma unroll
-        for (int g4 = 0; g4 < 4; ++g4) {
-          const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + cbase + 4 * g4));
-          const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + cbase + 4 * g4));
-          const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
+          for (int g4 = 0; g4 < 4; ++g4) {
+            const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + cbase + 4 * g4));
+            const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + cbase + 4 * g4));
+            const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float a = fmaf(__uint_as_float(v[4 * g4 + j]), scv[j], shv[j]);
-            a = p.relu ? fmaxf(a, 0.f) : a;
-            v[4 * g4 + j] = __float_as_uint(has_res ? a + rv[4 * g4 + j] : a);
+            for (int j = 0; j < 4; ++j) {
+              float a = fmaf(__uint_as_float(v[4 * g4 + j]), scv[j], shv[j]);
+              a = p.relu ? fmaxf(a, 0.f) : a;
+              v[4 * g4 + j] = __float_as_uint(has_res ? a + rv[4 * g4 + j] : a);
+            }
           }
-        }
-        if (valid) {
-          if (p.out_nchw) {
-            size_t o = oc;
+          if (has_res && cc + 2 < HALF_N / 16) {          // refill this buffer with the chunk two steps ahead
+            const size_t on = obase + (size_t)(cc + 2) * 16 * hw;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) { p.out_nchw[o] = __uint_as_float(v[j]); o += hw; }
+            for (int j = 0; j < 16; ++j) rv[j] = __ldg(p.res_nchw + on + (size_t)j * hw);
           }
-          if (p.out_planes) {
-            const size_t pix = ((size_t)img * p.H + hh) * p.W + ww;
-            __nv_bfloat16* hi = p.out_planes + pix * p.Cout + cbase;
-            __nv_bfloat16* lo = hi + p.out_plane_stride;
+          if (valid) {
+            if (p.out_nchw) {
+              size_t o = oc;
 #pragma unroll
-            for (int g8 = 0; g8 < 2; ++g8) {               // 8 channels (16 B per plane) at a time
-              uint32_t hp[4], lp[4];
+              for (int j = 0; j < 16; ++j) { p.out_nchw[o] = __uint_as_float(v[j]); o += hw; }
+            }
+            if (p.out_planes) {
+              const size_t pix = ((size_t)img * p.H + hh) * p.W + ww;
+              __nv_bfloat16* hi = p.out_planes + pix * p.Cout + cbase;
+              __nv_bfloat16* lo = hi + p.out_plane_stride;
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float y0 = __uint_as_float(v[8 * g8 + 2 * j]), y1 = __uint_as_float(v[8 * g8 + 2 * j + 1]);
-                const __nv_bfloat16 h0 = __float2bfloat16_rn(y0), h1 = __float2bfloat16_rn(y1);
-                const __nv_bfloat16 l0 = __float2bfloat16_rn(y0 - __bfloat162float(h0));
-                const __nv_bfloat16 l1 = __float2bfloat16_rn(y1 - __bfloat162float(h1));
-                hp[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                lp[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+              for (int g8 = 0; g8 < 2; ++g8) {               // 8 channels (16 B per plane) at a time
+                uint32_t hp[4], lp[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float y0 = __uint_as_float(v[8 * g8 + 2 * j]), y1 = __uint_as_float(v[8 * g8 + 2 * j + 1]);
+                  const __nv_bfloat16 h0 = __float2bfloat16_rn(y0), h1 = __float2bfloat16_rn(y1);
+                  const __nv_bfloat16 l0 = __float2bfloat16_rn(y0 - __bfloat162float(h0));
+                  const __nv_bfloat16 l1 = __float2bfloat16_rn(y1 - __bfloat162float(h1));
+                  hp[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                  lp[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                }
+                reinterpret_cast<uint4*>(hi)[g8] = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+                reinterpret_cast<uint4*>(lo)[g8] = make_uint4(lp[0], lp[1], lp[2], lp[3]);
               }
-              reinterpret_cast<uint4*>(hi)[g8] = make_uint4(hp[0], hp[1], hp[2], hp[3]);
-              reinterpret_cast<uint4*>(lo)[g8] = make_uint4(lp[0], lp[1], lp[2], lp[3]);
             }
           }
         }
@@ -585,8 +599,6 @@ int conv_igemm(const void* xp, const void* wp, const float* scale, const float* 
   p.tiles_n = Cout / block_n;
   p.ntaps = ntaps;
   p.n_pass = precision;
-  const int pa[3] = {0, 0, 1}, pb[3] = {0, 1, 0};
-  for (int i = 0; i < 3; ++i) { p.pass_a[i] = pa[i]; p.pass_b[i] = pb[i]; }
   p.relu = relu;
   p.scale = scale; p.shift = shift;
   p.out_planes = (__nv_bfloat16*)out_planes;

@@ -249,7 +249,7 @@ struct WgradParams {
   int rows_per_kb;          // 64 / W
   int kb_per_img;           // H*W / 64
   int tiles_m, tiles_n, splits, imgs_per_split;
-  int n_pass, pass_a[3], pass_b[3];
+  int n_pass;               // 1: hi*hi only; 3: (hi,hi) + (hi,lo) + (lo,hi)
   int block_n;              // input channels actually present in an N tile (Cin may be < 256)
   float* gw;                // [Cout][Cin][9]
 };
@@ -303,7 +303,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int dy = tap / 3 - 1, dx = tap % 3 - 1;
         const int i0 = sp * p.imgs_per_split, i1 = min(p.b, i0 + p.imgs_per_split);
         for (int ps = 0; ps < p.n_pass; ++ps) {
-          const int pa = p.pass_a[ps], pb = p.pass_b[ps];
+          const int pa = ps == 2 ? 1 : 0, pb = ps == 1 ? 1 : 0;   // (hi,hi) (hi,lo) (lo,hi)
           for (int img = i0; img < i1; ++img) {
             for (int kb = 0; kb < p.kb_per_img; ++kb) {
               const int h0 = kb * p.rows_per_kb;
@@ -548,8 +548,6 @@ extern "C" int ammc_conv3x3_wgrad(const void* gy_nhwc_planes, const void* x_nhwc
   p.imgs_per_split = ceil_div(b, p.splits);
   p.splits = ceil_div(b, p.imgs_per_split);
   p.n_pass = precision;
-  const int pa[3] = {0, 0, 1}, pb[3] = {0, 1, 0};
-  for (int i = 0; i < 3; ++i) { p.pass_a[i] = pa[i]; p.pass_b[i] = pb[i]; }
   p.gw = gw;
   AMMC_CUDA_CHECK(cudaMemsetAsync(gw, 0, (size_t)Cout * Cin * 9 * sizeof(float), st));
   CUtensorMap tmA, tmB;
