@@ -224,17 +224,28 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // ------------------------------------------------------------------------------------------------
 constexpr int PAIR_N = 256;
 constexpr int PAIR_B_BYTES = (PAIR_N / 2) * BLOCK_K * 2;      // this CTA's half of the B tile: 16 KB
-constexpr int PAIR_STAGE_BYTES = A_BYTES + PAIR_B_BYTES;       // 32 KB
-constexpr int PAIR_STAGES = 6;
-constexpr int PAIR_BAR_OFFSET = PAIR_STAGES * PAIR_STAGE_BYTES;
+constexpr int PAIR_TILE_BYTES = A_BYTES + PAIR_B_BYTES;        // one (A, B-half) pair of one plane: 32 KB
+constexpr int PAIR_RING_BYTES = 6 * PAIR_TILE_BYTES;           // 192 KB: 6 stages of 32 KB, or 3 fused stages of 64 KB
+constexpr int PAIR_BAR_OFFSET = PAIR_RING_BYTES;
 constexpr int PAIR_SMEM = PAIR_BAR_OFFSET + 256 + 1024;
+// FUSED3 (precision 3): a stage holds the hi AND lo planes of both operands, loaded once and used by the three MMA
+// groups hi*hi, hi*lo, lo*hi -> one third less L2->smem traffic than streaming the K loop three times.
+template <bool FUSED3> struct PairCfg {
+  static constexpr int PLANES = FUSED3 ? 2 : 1;
+  static constexpr int STAGE_BYTES = PLANES * PAIR_TILE_BYTES;
+  static constexpr int STAGES = PAIR_RING_BYTES / STAGE_BYTES;
+};
 constexpr int PAIR_EPI_WARPS = 8;
 constexpr int PAIR_THREADS = 64 + 32 * PAIR_EPI_WARPS;    // warp 0: TMA, warp 1: MMA, warps 2-9: epilogue
 
+template <bool FUSED3>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1)
 conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  using Cfg = PairCfg<FUSED3>;
+  constexpr int PAIR_STAGES = Cfg::STAGES;
+  constexpr int PAIR_STAGE_BYTES = Cfg::STAGE_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + PAIR_BAR_OFFSET);
   uint64_t* empty_bar = full_bar + PAIR_STAGES;
   uint64_t* tmem_full = empty_bar + PAIR_STAGES;
@@ -247,7 +258,7 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   const int pair_tiles_m = (p.tiles_m + 1) >> 1;
   const int num_tiles = pair_tiles_m * p.tiles_n;
   const int kb_per_pass = p.ntaps * (p.Cin / BLOCK_K);
-  const int kb_total = kb_per_pass * p.n_pass;
+  const int kb_total = FUSED3 ? kb_per_pass : kb_per_pass * p.n_pass;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmA);
@@ -273,7 +284,7 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         const int mt = (t / p.tiles_n) * 2 + (int)rank, nt = t % p.tiles_n;
         const int img0 = (mt / p.groups_h) * p.B_box, h0 = (mt % p.groups_h) * p.H_box;
         const int n0 = nt * PAIR_N + (int)rank * (PAIR_N / 2);
-        for (int ps = 0; ps < p.n_pass; ++ps) {
+        for (int ps = 0; ps < (FUSED3 ? 1 : p.n_pass); ++ps) {
           const int pa = ps == 2 ? 1 : 0, pb = ps == 1 ? 1 : 0;   // (hi,hi) (hi,lo) (lo,hi)
           for (int tap = 0; tap < p.ntaps; ++tap) {
             const int dy = p.ntaps == 9 ? tap / 3 - 1 : 0, dx = p.ntaps == 9 ? tap % 3 - 1 : 0;
@@ -281,8 +292,17 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
               ptx::mbar_wait(&empty_bar[s], ph ^ 1, 41);
               if (rank == 0) ptx::mbar_expect_tx(&full_bar[s], 2 * PAIR_STAGE_BYTES);
               uint8_t* a_dst = smem + s * PAIR_STAGE_BYTES;
-              ptx::tma_load_5d_2sm(a_dst, &tmA, &full_bar[s], cc * BLOCK_K, dx, h0 + dy, img0, pa);
-              ptx::tma_load_3d_2sm(a_dst + A_BYTES, &tmB, &full_bar[s], tap * p.Cin + cc * BLOCK_K, n0, pb);
+              if (FUSED3) {
+#pragma unroll
+                for (int pl = 0; pl < 2; ++pl) {       // [A_hi | B_hi | A_lo | B_lo]
+                  ptx::tma_load_5d_2sm(a_dst + pl * PAIR_TILE_BYTES, &tmA, &full_bar[s], cc * BLOCK_K, dx, h0 + dy, img0, pl);
+                  ptx::tma_load_3d_2sm(a_dst + pl * PAIR_TILE_BYTES + A_BYTES, &tmB, &full_bar[s],
+                                       tap * p.Cin + cc * BLOCK_K, n0, pl);
+                }
+              } else {
+                ptx::tma_load_5d_2sm(a_dst, &tmA, &full_bar[s], cc * BLOCK_K, dx, h0 + dy, img0, pa);
+                ptx::tma_load_3d_2sm(a_dst + A_BYTES, &tmB, &full_bar[s], tap * p.Cin + cc * BLOCK_K, n0, pb);
+              }
               if (++s == PAIR_STAGES) { s = 0; ph ^= 1; }
             }
           }
@@ -307,9 +327,20 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           const uint32_t a_addr = ptx::smem_u32(smem + s * PAIR_STAGE_BYTES);
           const uint64_t adesc = ptx::umma_desc_k_sw128(a_addr);
           const uint64_t bdesc = ptx::umma_desc_k_sw128(a_addr + A_BYTES);
+          if (FUSED3) {
+            const uint64_t adesc_lo = ptx::umma_desc_k_sw128(a_addr + PAIR_TILE_BYTES);
+            const uint64_t bdesc_lo = ptx::umma_desc_k_sw128(a_addr + PAIR_TILE_BYTES + A_BYTES);
 #pragma unroll
-          for (int k4 = 0; k4 < BLOCK_K / 16; ++k4)
-            ptx::mma_f16_ss_2sm(d_tmem, adesc + 2 * k4, bdesc + 2 * k4, idesc, (kb | k4) != 0 ? 1u : 0u);
+            for (int k4 = 0; k4 < BLOCK_K / 16; ++k4) {
+              ptx::mma_f16_ss_2sm(d_tmem, adesc + 2 * k4, bdesc + 2 * k4, idesc, (kb | k4) != 0 ? 1u : 0u);
+              ptx::mma_f16_ss_2sm(d_tmem, adesc + 2 * k4, bdesc_lo + 2 * k4, idesc, 1u);
+              ptx::mma_f16_ss_2sm(d_tmem, adesc_lo + 2 * k4, bdesc + 2 * k4, idesc, 1u);
+            }
+          } else {
+#pragma unroll
+            for (int k4 = 0; k4 < BLOCK_K / 16; ++k4)
+              ptx::mma_f16_ss_2sm(d_tmem, adesc + 2 * k4, bdesc + 2 * k4, idesc, (kb | k4) != 0 ? 1u : 0u);
+          }
           ptx::mma_commit_2sm(&empty_bar[s], 3);
           if (kb == kb_total - 1) ptx::mma_commit_2sm(&tmem_full[acc], 3);
           if (++s == PAIR_STAGES) { s = 0; ph ^= 1; }
@@ -558,6 +589,7 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const Con
   return 0;
 }
 
+static int g_conv_fused3 = 1;      // pair kernel, precision 3: load hi+lo planes once per K block (1) or stream K 3x (0)
 static int g_conv_pair_mode = 1;   // 1: CTA-pair kernel when Cout % 256 == 0; 0: single-CTA kernel everywhere
 
 bool conv_shape_supported(int b, int Cin, int Cout, int h, int w) {
@@ -632,12 +664,16 @@ int conv_igemm(const void* xp, const void* wp, const float* scale, const float* 
     int dev = 0;
     AMMC_CUDA_CHECK(cudaGetDevice(&dev));
     if (dev >= 0 && dev < 64 && !configured[dev]) {
-      AMMC_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM));
+      AMMC_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM));
+      AMMC_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM));
       configured[dev] = true;
     }
     const int pair_tiles = ((p.tiles_m + 1) / 2) * p.tiles_n;
     const int clusters = min(num_sms() / 2, pair_tiles);
-    conv_igemm_pair_kernel<<<2 * clusters, PAIR_THREADS, PAIR_SMEM, st>>>(tmA, tmB, p);
+    if (precision == 3 && g_conv_fused3)
+      conv_igemm_pair_kernel<true><<<2 * clusters, PAIR_THREADS, PAIR_SMEM, st>>>(tmA, tmB, p);
+    else
+      conv_igemm_pair_kernel<false><<<2 * clusters, PAIR_THREADS, PAIR_SMEM, st>>>(tmA, tmB, p);
     AMMC_LAUNCH_CHECK("conv_igemm_pair_kernel");
     return 0;
   }
@@ -655,7 +691,8 @@ namespace ammc { AMMC_DEFINE_TIMEOUT_READER(timeout_reader_conv) }
 using namespace ammc;
 
 extern "C" int ammc_set_conv_pair_mode(int on) {
-  g_conv_pair_mode = on ? 1 : 0;
+  g_conv_pair_mode = on ? 1 : 0;       // bit 1 (value 2/3): keep the pair kernel but stream the K loop three times
+  g_conv_fused3 = (on & 2) ? 0 : 1;
   return 0;
 }
 

@@ -151,9 +151,10 @@ def check_pipeline_watchdog():
                            % (rec[0], rec[1], rec[2], rec[3]))
 
 
-def set_conv_pair_mode(on: bool):
-    """CTA-pair (cta_group::2) conv kernel on/off (default on); for A/B measurements only."""
-    _capi.call("ammc_set_conv_pair_mode", int(bool(on)))
+def set_conv_pair_mode(on):
+    """True/1: CTA-pair (cta_group::2) conv kernel with fused hi/lo stages (default); 3: pair kernel streaming K three
+    times (bit-identical to the single-CTA kernel); False/0: single-CTA kernel.  For A/B measurements only."""
+    _capi.call("ammc_set_conv_pair_mode", int(on))
 
 
 def set_addressing_mode(mode: str = "auto"):

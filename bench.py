@@ -203,6 +203,8 @@ def run_ours(args):
     prec = args.precision
     if args.no_pair:
         F_.set_conv_pair_mode(False)
+    if args.pair_unfused:
+        F_.set_conv_pair_mode(3)
 
     # ---- modules with random-init weights of the shipped architecture (replicated on every rank) ----------
     p = synth.path_params(1, C, D, M, K_TOP)
@@ -432,6 +434,7 @@ def main():
     ap.add_argument("--precision", type=int, default=3, choices=[1, 3])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="issue the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--pair-unfused", action="store_true", help="A/B: CTA-pair kernel streaming the K loop three times")
     ap.add_argument("--no-pair", action="store_true", help="A/B: single-CTA conv kernel instead of the CTA-pair one")
     args = ap.parse_args()
     if args.impl == "reference":

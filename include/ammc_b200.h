@@ -168,8 +168,10 @@ int ammc_pack_nhwc(const float* x, void* xp, int b, int C, int h, int w, void* s
 int ammc_conv3x3_bn_relu(const void* xp, const void* wp, const float* scale, const float* shift,
                          void* out_planes, float* out_nchw, const float* res_nchw,
                          int b, int Cin, int Cout, int h, int w, int precision, int relu, void* stream);
-/* 1 (default): convolutions with Cout % 256 == 0 use the CTA-pair (cta_group::2, M=256) kernel; 0: always the
- * single-CTA kernel.  Results are bit-identical; the switch exists for A/B measurements. */
+/* 1 (default): convolutions with Cout % 256 == 0 use the CTA-pair (cta_group::2, M=256) kernel, which at precision 3
+ * loads the hi and lo planes of a K block once and issues hi*hi, hi*lo, lo*hi back to back; 3: CTA-pair kernel that
+ * streams the K loop three times instead (bit-identical to the single-CTA kernel); 0: always the single-CTA kernel.
+ * The variants differ only in fp32 summation order; the switch exists for A/B measurements. */
 int ammc_set_conv_pair_mode(int on);
 /* 1x1 convolution on the same tensor-core engine (a plain [N,Cin] x [Cout,Cin]^T GEMM, no halo):
  *   wp [2 planes][Cout][Cin] bf16 (pack with ammc_pack_conv_weights_1x1). */

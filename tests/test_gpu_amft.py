@@ -83,7 +83,7 @@ def test_cta_pair_kernel_matches_single_cta_kernel():
         scale, shift = torch.rand(cout, generator=g).to(DEV) + 0.5, torch.randn(cout, generator=g).to(DEV)
         outs = []
         try:
-            for pair in (True, False):
+            for pair in (3, False, True):
                 F_.set_conv_pair_mode(pair)
                 outs.append((F_.conv3x3_bn_relu(xp, wp, scale, shift, to_planes=False, precision=3),
                              F_.conv3x3_bn_relu(xp, wp, scale, shift, to_planes=True, precision=1)))
@@ -91,6 +91,8 @@ def test_cta_pair_kernel_matches_single_cta_kernel():
             F_.set_conv_pair_mode(True)
         F_.check_pipeline_watchdog()
         assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+        # default kernel (hi/lo planes fused per K block): same products, different fp32 summation order
+        assert rel_err(outs[2][0].cpu(), outs[1][0].cpu()) < 2e-5 and torch.equal(outs[2][1], outs[1][1])
         ref = torch.relu(torch.nn.functional.conv2d(x.double(), wt.double(), padding=1) * scale.cpu().double().view(1, -1, 1, 1)
                          + shift.cpu().double().view(1, -1, 1, 1))
         assert rel_err(outs[0][0].cpu(), ref) < 5e-5
