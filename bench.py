@@ -26,15 +26,15 @@ sys.path.insert(0, ROOT)
 
 METRIC = "frames/sec (memory+AMFT+score path)"
 UNIT = "frames/s"
-C, D, M, K_TOP, HW = 512, 64, 256, 2, 32
+C, D, M, K_TOP, HW = 512, 64, 256, 2, 32     # M is overridden by --items
 FRAME = (3, 256, 256)
 
 
 def workload_desc(batch, precision):
     return {
         "workload": "BASELINE configs[1]: AMMC-Net ped2-shape inference path on synthetic frames, batch %d per GPU: "
-                    "2 memory modules on [%d,512,32,32] (D=64, M=256, k=2) + AMFT bridge(512) + rgb PSNR on "
-                    "[%d,3,256,256]" % (batch, batch, batch),
+                    "2 memory modules on [%d,512,32,32] (D=64, M=%d, k=2) + AMFT bridge(512) + rgb PSNR on "
+                    "[%d,3,256,256]" % (batch, batch, M, batch),
         "batch_per_gpu": batch,
         "arithmetic": ("split-bf16 x3 tensor-core passes, fp32 accumulate (fp32-parity mode)" if precision == 3
                        else "single bf16 tensor-core pass, fp32 accumulate") + "; memory addressing, PSNR in fp32",
@@ -433,10 +433,13 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--precision", type=int, default=3, choices=[1, 3])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--items", type=int, default=256, help="memory bank size M (BASELINE configs[2] sweeps 256..2000)")
     ap.add_argument("--no-graph", action="store_true", help="issue the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--pair-unfused", action="store_true", help="A/B: CTA-pair kernel streaming the K loop three times")
     ap.add_argument("--no-pair", action="store_true", help="A/B: single-CTA conv kernel instead of the CTA-pair one")
     args = ap.parse_args()
+    global M
+    M = args.items
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -1,0 +1,92 @@
+"""BASELINE configs[3]: joint training step of the two-stream generator, data-parallel (one process per GPU, NCCL).
+
+The hot-path modules run their training kernels (memory: fused forward + closed-form backward + EMA bank update with
+globally all-reduced assignment statistics; AMFT: batch-stat BN, tcgen05 dgrad/wgrad); the U-Net convolutions are stock
+cuDNN layers (unchanged host code).  Losses follow the reference step structure (Code/run_helper/train_helper.py:291-343,
+Code/models/losses/loss_zoo.py:307-350) without the parts that need unavailable weights (FlowNet2-SD, discriminator):
+intensity L2 on the rgb prediction, L1 on the flow prediction, lam_latent * (rgb_diff + op_diff).
+
+    torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/train_step.py --steps 10 --batch 8
+"""
+import argparse, json, os, sys, time
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import ammcnet_aaai2021_b200 as A
+from ammcnet_aaai2021_b200 import dist as adist, functions as F_
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=8)       # per GPU (reference script: batch 8, training_com.sh:21)
+    ap.add_argument("--size", type=int, default=256)
+    args = ap.parse_args()
+    rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        adist.install_stats_allreduce()
+    torch.manual_seed(20200525)                           # same init on every rank (reference seeds at import, unet.py:4)
+    g = A.get_twostream().to(dev).train()
+    opt = torch.optim.Adam(g.parameters(), lr=2e-4)
+    params = [p for p in g.parameters()]
+    gen = torch.Generator().manual_seed(77 + rank)
+    B, S = args.batch, args.size
+    rgb = (torch.rand((B, 5, 3, S, S), generator=gen) * 2 - 1).to(dev)
+    op = (torch.randn((B, 4, 2, S, S), generator=gen) * 0.02).to(dev)
+    rgb_in, rgb_tgt = rgb[:, :-1].flatten(1, 2), rgb[:, -1]
+    op_in, op_tgt = op[:, :-1].flatten(1, 2), op[:, -1]
+    lam_latent = 1.0
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        pr, po, (d_rgb, d_op), _ = g(rgb_in, op_in)
+        loss = (pr - rgb_tgt).pow(2).mean() + 2.0 * (po - op_tgt).abs().mean() + lam_latent * (d_rgb + d_op).sum()
+        loss.backward()
+        adist.allreduce_gradients(params)
+        opt.step()
+        return loss.detach()
+
+    losses = []
+    for _ in range(args.warmup):
+        losses.append(step())
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        losses.append(step())
+    e1.record()
+    torch.cuda.synchronize()
+    F_.check_pipeline_watchdog()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    # consistency: banks and parameters must be identical on every rank after the step
+    bank = g.rgb.vq_down3.quan.quantize.embed.detach().clone()
+    w = g.bridge.O2F.conv[0].weight.detach().clone()
+    bank_max_dev = torch.zeros(1, device=dev, dtype=torch.float64)
+    w_max_dev = torch.zeros(1, device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ref_b, ref_w = bank.clone(), w.clone()
+        dist.broadcast(ref_b, 0); dist.broadcast(ref_w, 0)
+        bank_max_dev = (bank - ref_b).abs().max().double().reshape(1)
+        w_max_dev = (w - ref_w).abs().max().double().reshape(1)
+        dist.all_reduce(bank_max_dev, op=dist.ReduceOp.MAX); dist.all_reduce(w_max_dev, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        ls = [float(l) for l in losses]
+        print(json.dumps({"what": "joint training step (generator fwd+bwd, EMA stats + gradient all-reduce, Adam)",
+                          "n_gpus": world, "batch_per_gpu": B, "steps": args.steps, "ms_per_step": float(ms) / args.steps,
+                          "frames_per_s": world * B * args.steps / (float(ms) * 1e-3), "loss_first": ls[0], "loss_last": ls[-1],
+                          "finite": all(l == l and abs(l) < 1e30 for l in ls),
+                          "bank_max_abs_dev_across_ranks": float(bank_max_dev), "weight_max_abs_dev_across_ranks": float(w_max_dev)}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
