@@ -177,6 +177,22 @@ class ClockSampler:
         return out
 
 
+def ncu_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full`
+    capture of this same command (profiles/, summarised by tools/ncu_summary.py); None when the file is absent."""
+    import csv
+    path = os.path.join(ROOT, "profiles", "r01_ncu_conv_igemm_pair_full_summary.csv")
+    try:
+        rows = list(csv.reader(open(path)))
+        hdr, units = rows[0], rows[1]
+        ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
+        vals = [float(r[ir]) * scale.get(units[ir], 1.0) + float(r[iw]) * scale.get(units[iw], 1.0) for r in rows[2:] if r]
+        return sum(vals) / len(vals) if vals else None
+    except Exception:
+        return None
+
+
 def load_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -400,8 +416,11 @@ def run_ours(args):
             avg = sum(conv_ms) / len(conv_ms)
             ach = conv_flops / (avg * 1e-3) / 1e12
             peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
-            roof = {"kernel": "conv_igemm_kernel<256> (AMFT 3x3 conv, tcgen05)", "bound": "tensor", "achieved": ach,
-                    "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+            roof = {"kernel": "conv_igemm_pair_kernel<FUSED3> (AMFT 3x3 conv, tcgen05 cta_group::2)", "bound": "tensor", "achieved": ach,
+                    "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": ncu_traffic_bytes(),
+                    "traffic_note": "mean DRAM bytes per launch over the two convs of one branch, ncu --set full "
+                                    "(profiles/r01_ncu_conv_igemm_pair_full_summary.csv); algorithmic operand+result bytes "
+                                    "per launch: 2*67 MB planes in + 134 MB out (+134 MB residual) + 9.4 MB weights",
                     "peak_source": peak_src + " bf16_tflops_sustained (kernel timed inside a long step)",
                     "avg_launch_ms": avg, "launches_timed": len(conv_ms),
                     "timing": "CUDA events around each 3x3 conv launch of K eagerly issued steps run right after the "
