@@ -55,6 +55,8 @@ SIGNATURES = {
     "ammc_psnr_workspace_bytes": (Z, [I, L]),
     "ammc_psnr_batch": (I, [P, P, P, P, Z, I, L, P]),
     "ammc_score_workspace_bytes": (Z, [L, I]),
+    "ammc_auc_workspace_bytes": (Z, [L]),
+    "ammc_roc_auc": (I, [P, P, I, P, P, Z, L, P]),
     "ammc_score_reduce": (I, [P, P, P, I, F, F, F, F, P, P, Z, L, P]),
 }
 

@@ -542,3 +542,19 @@ def score_reduce_device(img: torch.Tensor, fea: torch.Tensor, offsets: torch.Ten
                    oml1, l1f, oml2, l2f, _p(out), _p(ws), ws.numel(), T, _stream())
     _count(2)
     return out
+
+
+def roc_auc_device(scores: torch.Tensor, labels: torch.Tensor, pos_label: int = 0) -> torch.Tensor:
+    """ROC-AUC on the GPU (sort + tie-aware rank sum); returns a 0-d float64 device tensor, no host sync."""
+    _require_cuda_f32(scores, names=("scores",))
+    if not labels.is_cuda or labels.dtype != torch.int8 or labels.numel() != scores.numel():
+        raise RuntimeError("ammc_b200: roc_auc labels must be a CUDA int8 tensor of the scores' length")
+    T = scores.numel()
+    out = torch.empty((1,), dtype=torch.float64, device=scores.device)
+    lib = _capi.load()
+    ws = _workspace(lib.ammc_auc_workspace_bytes(T), scores.device)
+    with torch.cuda.device(scores.device):
+        _capi.call("ammc_roc_auc", _p(scores.contiguous()), _p(labels.contiguous()), int(pos_label), _p(out), _p(ws),
+                   ws.numel(), T, _stream())
+    _count(6)
+    return out.reshape(())

@@ -140,7 +140,22 @@ def score_reduce(img_records: Sequence[np.ndarray], fea_records: Sequence[np.nda
     return F_.score_reduce_device(img, fea, offsets, lam).cpu().numpy()
 
 
-def evaluate(eval_type: str, save_file: str, lam=None, gt_labels: Optional[Sequence[np.ndarray]] = None) -> Dict:
+def score_and_auc_device(img_records, fea_records, lam, gt_labels, device=None):
+    """Whole a13 row on the device: regularity scores (ammc_score_reduce) and their ROC-AUC (ammc_roc_auc); one
+    device->host read of the final double.  Returns (scores float32 numpy, auc float)."""
+    device = device or torch.device("cuda", torch.cuda.current_device())
+    lens = np.array([len(r) for r in img_records], dtype=np.int64)
+    offsets = torch.from_numpy(np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)).to(device)
+    img = torch.from_numpy(np.concatenate([np.asarray(r, np.float32) for r in img_records])).to(device)
+    fea = torch.from_numpy(np.concatenate([np.asarray(r, np.float32) for r in fea_records])).to(device)
+    labels = torch.from_numpy(np.concatenate([np.asarray(g)[DECIDABLE_IDX:] for g in gt_labels]).astype(np.int8)).to(device)
+    scores = F_.score_reduce_device(img, fea, offsets, lam)
+    auc = F_.roc_auc_device(scores, labels, pos_label=0)
+    return scores.cpu().numpy(), float(auc.cpu())
+
+
+def evaluate(eval_type: str, save_file: str, lam=None, gt_labels: Optional[Sequence[np.ndarray]] = None,
+             auc_on_gpu: bool = False) -> Dict:
     """eval_metric.evaluate('img_pred_fea_comm_rgb_auc', pickle_or_dir, lam) (eval_metric.py:382-454).
 
     gt_labels: per-video int8 label arrays (what the reference's GroundTruthLoader returns from the dataset's
@@ -149,16 +164,19 @@ def evaluate(eval_type: str, save_file: str, lam=None, gt_labels: Optional[Seque
         raise AssertionError("there is no type of evaluation %s" % eval_type)
     if gt_labels is None:
         raise RuntimeError("ammc_b200.evaluate needs gt_labels (the dataset ground truth is not shipped)")
-    from sklearn import metrics
     files = [save_file] if not os.path.isdir(save_file) else [os.path.join(save_file, f) for f in os.listdir(save_file)]
     best = None
     for f in files:
         with open(f, "rb") as fp:
             res = pickle.load(fp)
-        scores = score_reduce(res["rgb_img_pred_records"], res["rgb_fea_comm_records"], lam)
-        labels = np.concatenate([np.asarray(g)[DECIDABLE_IDX:] for g in gt_labels])
-        fpr, tpr, _ = metrics.roc_curve(labels, scores, pos_label=0)
-        auc = metrics.auc(fpr, tpr)
+        if auc_on_gpu:
+            _, auc = score_and_auc_device(res["rgb_img_pred_records"], res["rgb_fea_comm_records"], lam, gt_labels)
+        else:
+            from sklearn import metrics            # the reference's own host path (eval_metric.py:428-429)
+            scores = score_reduce(res["rgb_img_pred_records"], res["rgb_fea_comm_records"], lam)
+            labels = np.concatenate([np.asarray(g)[DECIDABLE_IDX:] for g in gt_labels])
+            fpr, tpr, _ = metrics.roc_curve(labels, scores, pos_label=0)
+            auc = metrics.auc(fpr, tpr)
         if best is None or auc > best[1]:
             best = (f, auc)
     return {"optimal_loss": "{}".format(best[0]), "auc": round(best[1], 3)}

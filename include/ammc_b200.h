@@ -228,6 +228,13 @@ int ammc_score_reduce(const float* img, const float* fea, const int64_t* offsets
                       float one_minus_lam1, float lam1, float one_minus_lam2, float lam2,
                       float* scores, void* workspace, size_t workspace_bytes, int64_t t_total, void* stream);
 
+/* ROC-AUC of scores against labels (labels[i] == pos_label marks the positive class), the value
+ * sklearn.metrics.auc(roc_curve(labels, scores, pos_label)) returns at reference Code/main/eval_metric.py:428-429:
+ * bitonic sort + tie-aware rank sum, exact in integers, final ratio in fp64.  auc: device double[1]. */
+size_t ammc_auc_workspace_bytes(int64_t T);
+int ammc_roc_auc(const float* scores, const int8_t* labels, int pos_label, double* auc, void* workspace,
+                 size_t workspace_bytes, int64_t T, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -156,3 +156,35 @@ def test_graphed_path_matches_eager():
     for a, e in zip(outs2, eager2):
         assert torch.equal(a, e)
     F_.check_pipeline_watchdog()
+
+
+@pytest.mark.parametrize("ds", ["ped2", "avenue", "shanghaitech"])
+def test_gpu_roc_auc_matches_sklearn_on_reference_records(ds):
+    """Next-row: ROC-AUC on the device equals sklearn's on the reference's recorded score records."""
+    from ammcnet_aaai2021_b200 import functions as F_
+    c, g = load_golden("scores_" + ds)
+    offs = np.concatenate([[0], np.cumsum(g["lengths"])])
+    nv = len(g["lengths"])
+    labels = np.concatenate([g["labels"][offs[i] + 4:offs[i + 1]] for i in range(nv)]).astype(np.int8)
+    scores = torch.from_numpy(g["scores"]).to(DEV)
+    auc = float(F_.roc_auc_device(scores, torch.from_numpy(labels).to(DEV), pos_label=0).cpu())
+    assert abs(auc - float(g["auc"])) < 1e-12, (auc, float(g["auc"]))
+    img = [g["img"][offs[i]:offs[i + 1]] for i in range(nv)]
+    fea = [g["fea"][offs[i]:offs[i + 1]] for i in range(nv)]
+    lab = [g["labels"][offs[i]:offs[i + 1]] for i in range(nv)]
+    s, a = scoring.score_and_auc_device(img, fea, tuple(c["lam"]), lab)
+    assert np.array_equal(s, g["scores"]) and abs(a - float(g["auc"])) < 1e-12
+
+
+@pytest.mark.parametrize("T", [1, 2, 7, 2048, 2049, 5000, 70000])
+def test_gpu_roc_auc_ties_and_sizes(T):
+    from ammcnet_aaai2021_b200 import functions as F_
+    rng = np.random.RandomState(T)
+    scores = np.round(rng.randn(T), 1).astype(np.float32)           # heavy ties, negatives, zeros
+    labels = (rng.rand(T) < 0.4).astype(np.int8)
+    got = float(F_.roc_auc_device(torch.from_numpy(scores).to(DEV), torch.from_numpy(labels).to(DEV), 0).cpu())
+    ref = O.roc_auc(labels, scores, pos_label=0)
+    if np.isnan(ref):
+        assert np.isnan(got)
+    else:
+        assert abs(got - ref) < 1e-12, (got, ref)
