@@ -67,11 +67,20 @@ class VideoScorer:
     `quantize.last_sse_frame`).
     """
 
-    def __init__(self, generator, batch: int = 64, rgb_clip_len: int = 5, op_clip_len: int = 4):
+    def __init__(self, generator, batch: int = 64, rgb_clip_len: int = 5, op_clip_len: int = 4, graph: bool = False):
         self.g = generator
         self.batch = batch
         self.rgb_clip_len = rgb_clip_len
         self.op_clip_len = op_clip_len
+        # graph=True: full batches replay ONE captured CUDA graph of generator + PSNR (cuDNN convolutions included);
+        # the ragged last batch of a video runs eagerly.  Captured lazily per frame size.
+        self.graph = graph
+        self._graphs = {}
+
+    def _batch_scores(self, rgb_in, op_in, target):
+        q_rgb, q_op = self._memories()
+        pred, _op_pred, _diffs, _ = self.g(rgb_in, op_in)
+        return F_.psnr_per_frame(pred, target), q_rgb.last_sse_frame, q_op.last_sse_frame
 
     def _memories(self):
         return self.g.rgb.vq_down3.quan.quantize, self.g.op.vq_down3.quan.quantize
@@ -90,10 +99,17 @@ class VideoScorer:
             rgb_in = torch.stack([rgb_frames[idx + t] for t in range(L - 1)], 1).flatten(1, 2)
             op_in = torch.stack([op_frames[idx + t] for t in range(Lo - 1)], 1).flatten(1, 2)
             target = rgb_frames[idx + (L - 1)]
-            pred, _op_pred, _diffs, _ = self.g(rgb_in, op_in)
-            psnr_parts.append(F_.psnr_per_frame(pred, target))
-            sse_rgb.append(q_rgb.last_sse_frame)
-            sse_op.append(q_op.last_sse_frame)
+            if self.graph and (c1 - c0) == self.batch:
+                key = (tuple(rgb_in.shape), tuple(op_in.shape), rgb_in.device.index)
+                if key not in self._graphs:
+                    from .graphs import GraphedPath
+                    self._graphs[key] = GraphedPath(self._batch_scores, [rgb_in, op_in, target])
+                ps, sr, so = (t.clone() for t in self._graphs[key](rgb_in, op_in, target))
+            else:
+                ps, sr, so = self._batch_scores(rgb_in, op_in, target)
+            psnr_parts.append(ps)
+            sse_rgb.append(sr)
+            sse_op.append(so)
         psnr = torch.cat(psnr_parts)
         elems = q_rgb.last_idx.shape[0] // max(1, sse_rgb[-1].numel()) * q_rgb.dim
         commit_rgb = group_commit_from_frames(torch.cat(sse_rgb), elems)

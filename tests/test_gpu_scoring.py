@@ -89,6 +89,9 @@ def test_video_scorer_reproduces_reference_loop_semantics():
         op = (torch.randn((T - 1, 2, H, H), generator=gen) * 0.02).to(DEV)
         rec = scoring.VideoScorer(g, batch=64).score_video(rgb, op)
         rec7 = scoring.VideoScorer(g, batch=7).score_video(rgb, op)
+        rec_graph = scoring.VideoScorer(g, batch=16, graph=True).score_video(rgb, op)    # 2 replays + 1 eager batch
+        for kk in ("rgb_img_pred", "rgb_fea_comm", "op_fea_comm"):
+            np.testing.assert_allclose(rec_graph[kk], scoring.VideoScorer(g, batch=16).score_video(rgb, op)[kk], rtol=1e-5)
         # the reference's own procedure: batches of 16 clips, psnr_error per frame, the batch-level diff per frame
         n_clips = T - 4
         psnr_ref = np.empty(n_clips, np.float32)
