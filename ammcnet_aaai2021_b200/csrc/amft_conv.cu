@@ -31,6 +31,7 @@ constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;    // 16 KB
 struct ConvParams {
   int b, H, W, Cin, Cout;
   int W_box, H_box, B_box, groups_h;
+  int rows_valid;                // pixels actually covered by one TMA box (<= 128; < 128 when w does not divide 128)
   int tiles_m, tiles_n, ntaps;
   int n_pass;               // 1: hi*hi only; 3: (hi,hi) + (hi,lo) + (lo,hi)
   int relu;
@@ -98,7 +99,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const int dy = p.ntaps == 9 ? tap / 3 - 1 : 0, dx = p.ntaps == 9 ? tap % 3 - 1 : 0;
             for (int cc = 0; cc < p.Cin / BLOCK_K; ++cc) {
               ptx::mbar_wait(&empty_bar[s], ph ^ 1, 1);
-              ptx::mbar_expect_tx(&full_bar[s], S::STAGE_BYTES);
+              ptx::mbar_expect_tx(&full_bar[s], p.rows_valid * 128 + S::B_BYTES);
               uint8_t* a_dst = smem + s * S::STAGE_BYTES;
               ptx::tma_load_5d(a_dst, &tmA, &full_bar[s], cc * BLOCK_K, dx, h0 + dy, img0, pa);
               ptx::tma_load_3d(a_dst + A_BYTES, &tmB, &full_bar[s], tap * p.Cin + cc * BLOCK_K, n0, pb);
@@ -150,7 +151,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int img = (mt / p.groups_h) * p.B_box + r / per_img;
       const int rem = r % per_img;
       const int hh = (mt % p.groups_h) * p.H_box + rem / p.W_box, ww = rem % p.W_box;
-      const bool valid = img < p.b;
+      const bool valid = img < p.b && hh < p.H && r < p.rows_valid;   // rows past the box hold stale smem: never stored
       const int n0 = nt * BLOCK_N;
       ptx::mbar_wait(&tmem_full[acc], acc_ph, 4);
       ptx::tc_fence_after();
@@ -290,7 +291,7 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             const int dy = p.ntaps == 9 ? tap / 3 - 1 : 0, dx = p.ntaps == 9 ? tap % 3 - 1 : 0;
             for (int cc = 0; cc < p.Cin / BLOCK_K; ++cc) {
               ptx::mbar_wait(&empty_bar[s], ph ^ 1, 41);
-              if (rank == 0) ptx::mbar_expect_tx(&full_bar[s], 2 * PAIR_STAGE_BYTES);
+              if (rank == 0) ptx::mbar_expect_tx(&full_bar[s], 2 * Cfg::PLANES * (p.rows_valid * 128 + PAIR_B_BYTES));
               uint8_t* a_dst = smem + s * PAIR_STAGE_BYTES;
               if (FUSED3) {
 #pragma unroll
@@ -365,7 +366,7 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       const int img = (mt / p.groups_h) * p.B_box + r / per_img;
       const int rem = r % per_img;
       const int hh = (mt % p.groups_h) * p.H_box + rem / p.W_box, ww = rem % p.W_box;
-      const bool valid = img < p.b && mt < p.tiles_m;
+      const bool valid = img < p.b && mt < p.tiles_m && hh < p.H && r < p.rows_valid;
       const int n0 = nt * PAIR_N + half * HALF_N;
       const size_t obase = ((size_t)img * p.Cout + n0) * hw + (size_t)hh * p.W + ww;
       const bool has_res = valid && p.res_nchw != nullptr;
@@ -593,10 +594,7 @@ static int g_conv_fused3 = 1;      // pair kernel, precision 3: load hi+lo plane
 static int g_conv_pair_mode = 1;   // 1: CTA-pair kernel when Cout % 256 == 0; 0: single-CTA kernel everywhere
 
 bool conv_shape_supported(int b, int Cin, int Cout, int h, int w) {
-  if (b <= 0 || h <= 0 || w <= 0 || Cin % 64 != 0 || Cout % 64 != 0) return false;
-  if (w > 128 || (128 % w) != 0) return false;
-  const int hb = min(h, 128 / w);
-  return h % hb == 0 && (128 % (w * hb)) == 0;
+  return b > 0 && h > 0 && w > 0 && w <= 128 && Cin % 64 == 0 && Cout % 64 == 0;
 }
 
 // w [Cout][Cin] fp32 -> [2][Cout][Cin] bf16 planes (1x1 conv / plain GEMM weights)
@@ -616,16 +614,16 @@ int conv_igemm(const void* xp, const void* wp, const float* scale, const float* 
   if (precision != 1 && precision != 3) return fail(AMMC_EINVAL, "precision must be 1 or 3 (got %d)", precision);
   if (Cin % 64 != 0 || Cout % 64 != 0)
     return fail(AMMC_EUNSUPPORTED, "tcgen05 conv needs Cin and Cout multiples of 64 (got %d, %d)", Cin, Cout);
-  if (w > 128 || (128 % w) != 0)
-    return fail(AMMC_EUNSUPPORTED, "tcgen05 conv needs a feature-map width that divides 128 (got %d)", w);
+  if (w > 128)
+    return fail(AMMC_EUNSUPPORTED, "tcgen05 conv supports feature maps up to 128 pixels wide (got %d)", w);
   ConvParams p;
   p.b = b; p.H = h; p.W = w; p.Cin = Cin; p.Cout = Cout;
+  // one TMA box = W_box x H_box x B_box pixels <= 128: whole rows, as many as fit; whole images when a full image fits
   p.W_box = w;
   p.H_box = min(h, 128 / w);
-  if (h % p.H_box != 0 || (128 % (w * p.H_box)) != 0)
-    return fail(AMMC_EUNSUPPORTED, "tcgen05 conv cannot tile a %dx%d feature map into 128-pixel boxes", h, w);
-  p.B_box = 128 / (w * p.H_box);
-  p.groups_h = h / p.H_box;
+  p.B_box = (p.H_box == h) ? max(1, 128 / (w * h)) : 1;
+  p.groups_h = ceil_div(h, p.H_box);
+  p.rows_valid = p.W_box * p.H_box * p.B_box;
   p.tiles_m = ceil_div(b, p.B_box) * p.groups_h;
   const int block_n = (Cout % 256 == 0) ? 256 : (Cout % 128 == 0 ? 128 : 64);
   p.tiles_n = Cout / block_n;

@@ -246,8 +246,11 @@ constexpr int WG_SMEM = WG_BAR_OFFSET + 256 + 1024;
 
 struct WgradParams {
   int b, H, W, Cin, Cout;
-  int rows_per_kb;          // 64 / W
-  int kb_per_img;           // H*W / 64
+  int w_box;                // pixels of one row covered by a K block: min(W, 64)
+  int rows_per_kb;          // rows per K block: 64 / W for W <= 64, else 1
+  int chunks_per_row;       // ceil(W / 64): K blocks needed to cover one row (1 for W <= 64)
+  int kb_per_img;           // ceil(H / rows_per_kb) * chunks_per_row
+  int k_bytes;              // bytes one [pixels][64 ch] box really transfers: w_box * rows_per_kb * 128
   int tiles_m, tiles_n, splits, imgs_per_split;
   int n_pass;               // 1: hi*hi only; 3: (hi,hi) + (hi,lo) + (lo,hi)
   int block_n;              // input channels actually present in an N tile (Cin may be < 256)
@@ -278,6 +281,13 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     ptx::tmem_alloc(tmem_slot, 2 * WG_BLOCK_N);
     ptx::tmem_relinquish();
   }
+  // K = pixels: when a box covers fewer than 64 pixels the remaining K rows of every stage are never written by TMA and
+  // must contribute zero -> clear the ring once (generic-proxy writes, made visible to the async proxy by the fence)
+  if (p.k_bytes < WG_BOX_BYTES) {
+    for (int i = threadIdx.x * 16; i < WG_STAGES * WG_STAGE_BYTES; i += WG_THREADS * 16)
+      *reinterpret_cast<uint4*>(smem + i) = make_uint4(0, 0, 0, 0);
+    ptx::fence_proxy_async();
+  }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -306,16 +316,16 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const int pa = ps == 2 ? 1 : 0, pb = ps == 1 ? 1 : 0;   // (hi,hi) (hi,lo) (lo,hi)
           for (int img = i0; img < i1; ++img) {
             for (int kb = 0; kb < p.kb_per_img; ++kb) {
-              const int h0 = kb * p.rows_per_kb;
+              const int h0 = (kb / p.chunks_per_row) * p.rows_per_kb, w0 = (kb % p.chunks_per_row) * 64;
               ptx::mbar_wait(&empty_bar[s], ph ^ 1, 21);
-              ptx::mbar_expect_tx(&full_bar[s], WG_STAGE_BYTES);
+              ptx::mbar_expect_tx(&full_bar[s], (WG_BLOCK_M / 64 + WG_BLOCK_N / 64) * p.k_bytes);
               uint8_t* dst = smem + s * WG_STAGE_BYTES;
 #pragma unroll
               for (int i = 0; i < WG_BLOCK_M / 64; ++i)
-                ptx::tma_load_5d(dst + i * WG_BOX_BYTES, &tmA, &full_bar[s], mt * WG_BLOCK_M + i * 64, 0, h0, img, pa);
+                ptx::tma_load_5d(dst + i * WG_BOX_BYTES, &tmA, &full_bar[s], mt * WG_BLOCK_M + i * 64, w0, h0, img, pa);
 #pragma unroll
               for (int i = 0; i < WG_BLOCK_N / 64; ++i)
-                ptx::tma_load_5d(dst + WG_A_BYTES + i * WG_BOX_BYTES, &tmB, &full_bar[s], nt * WG_BLOCK_N + i * 64, dx,
+                ptx::tma_load_5d(dst + WG_A_BYTES + i * WG_BOX_BYTES, &tmB, &full_bar[s], nt * WG_BLOCK_N + i * 64, w0 + dx,
                                  h0 + dy, img, pb);
               if (++s == WG_STAGES) { s = 0; ph ^= 1; }
             }
@@ -534,12 +544,15 @@ extern "C" int ammc_conv3x3_wgrad(const void* gy_nhwc_planes, const void* x_nhwc
   if (precision != 1 && precision != 3) return fail(AMMC_EINVAL, "precision must be 1 or 3 (got %d)", precision);
   if (Cin % 64 != 0 || Cout % 64 != 0)
     return fail(AMMC_EUNSUPPORTED, "tcgen05 wgrad needs Cin and Cout multiples of 64 (got %d, %d)", Cin, Cout);
-  if (w > 64 || 64 % w != 0 || h % (64 / w) != 0)
-    return fail(AMMC_EUNSUPPORTED, "tcgen05 wgrad cannot tile a %dx%d feature map into 64-pixel runs", h, w);
+  if (w > 128)
+    return fail(AMMC_EUNSUPPORTED, "tcgen05 wgrad supports feature maps up to 128 pixels wide (got %d)", w);
   WgradParams p;
   p.b = b; p.H = h; p.W = w; p.Cin = Cin; p.Cout = Cout;
-  p.rows_per_kb = 64 / w;
-  p.kb_per_img = h * w / 64;
+  p.w_box = min(w, 64);
+  p.rows_per_kb = w <= 64 ? min(h, 64 / w) : 1;
+  p.chunks_per_row = ceil_div(w, 64);
+  p.kb_per_img = ceil_div(h, p.rows_per_kb) * p.chunks_per_row;
+  p.k_bytes = p.w_box * p.rows_per_kb * 128;
   p.tiles_m = ceil_div(Cout, WG_BLOCK_M);
   p.tiles_n = ceil_div(Cin, WG_BLOCK_N);
   p.block_n = min(Cin, WG_BLOCK_N);
@@ -555,14 +568,14 @@ extern "C" int ammc_conv3x3_wgrad(const void* gy_nhwc_planes, const void* x_nhwc
     uint64_t dims[5] = {(uint64_t)Cout, (uint64_t)w, (uint64_t)h, (uint64_t)b, 2};
     uint64_t strides[4] = {(uint64_t)Cout * 2, (uint64_t)w * Cout * 2, (uint64_t)h * w * Cout * 2,
                            (uint64_t)b * h * w * Cout * 2};
-    uint32_t box[5] = {64, (uint32_t)w, (uint32_t)p.rows_per_kb, 1, 1};
+    uint32_t box[5] = {64, (uint32_t)p.w_box, (uint32_t)p.rows_per_kb, 1, 1};
     if (int rc = make_map_bf16(&tmA, gy_nhwc_planes, 5, dims, strides, box)) return rc;
   }
   {
     uint64_t dims[5] = {(uint64_t)Cin, (uint64_t)w, (uint64_t)h, (uint64_t)b, 2};
     uint64_t strides[4] = {(uint64_t)Cin * 2, (uint64_t)w * Cin * 2, (uint64_t)h * w * Cin * 2,
                            (uint64_t)b * h * w * Cin * 2};
-    uint32_t box[5] = {64, (uint32_t)w, (uint32_t)p.rows_per_kb, 1, 1};
+    uint32_t box[5] = {64, (uint32_t)p.w_box, (uint32_t)p.rows_per_kb, 1, 1};
     if (int rc = make_map_bf16(&tmB, x_nhwc_planes, 5, dims, strides, box)) return rc;
   }
   static bool configured[64] = {false};

@@ -64,8 +64,8 @@ int ammc_debug_tma_probe(const void* base, const int64_t* dims5, const int64_t* 
  *   counts   [M], embed_sum [D, M]  (both NULL in eval) assignment statistics of unet.py:298-302
  *   out_planes [2][b,h,w,C] bf16 or NULL: `out` additionally as NHWC hi/lo planes (the AMFT block's operand), written
  *              by the same epilogue.  Only allowed when ammc_mem_dec_uses_tensor(...) == 1.
- * `dec` runs as a split-bf16 x3 GEMM on tcgen05 when k*D % 64 == 0, C % 64 == 0 and the feature map tiles into 128-pixel
- * boxes (w divides 128); otherwise as an exact fp32 gather of precomputed table rows.  ammc_set_dec_mode: 0 auto,
+ * `dec` runs as a split-bf16 x3 GEMM on tcgen05 when k*D % 64 == 0, C % 64 == 0 and the feature map is at most 128
+ * pixels wide; otherwise as an exact fp32 gather of precomputed table rows.  ammc_set_dec_mode: 0 auto,
  * 1 force the fp32 gather, 2 force the tensor-core GEMM.
  * ------------------------------------------------------------------------------------------------- */
 int ammc_mem_dec_uses_tensor(int b, int h, int w, int C, int D, int M, int k);

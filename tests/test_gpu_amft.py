@@ -186,5 +186,84 @@ def test_bridge_eval_mode_with_grad_matches_fused_path():
 
 def test_bridge_rejects_unsupported_shapes():
     m = A.bridge(in_c=64).to(DEV)
-    with torch.no_grad(), pytest.raises(RuntimeError, match="divides 128|128-pixel"):
-        m.eval()(torch.zeros(1, 64, 5, 7, device=DEV), torch.zeros(1, 64, 5, 7, device=DEV))
+    with torch.no_grad(), pytest.raises(RuntimeError, match="128 pixels wide"):
+        m.eval()(torch.zeros(1, 64, 4, 130, device=DEV), torch.zeros(1, 64, 4, 130, device=DEV))
+    m96 = A.bridge(in_c=96).to(DEV)
+    with torch.no_grad(), pytest.raises(RuntimeError, match="multiples of 64"):
+        m96.eval()(torch.zeros(1, 96, 8, 8, device=DEV), torch.zeros(1, 96, 8, 8, device=DEV))
+
+
+def _relu_masks_of_branch(u, w1, g1, b1, w2, g2, b2):
+    """The ReLU activity masks the CUDA path itself uses in training mode (same kernels, same inputs => same bits).
+    ReLU has no derivative at 0: where a pre-activation is within rounding of 0 the fp64 reference may take the other
+    side and the gradients then differ by O(1) at that element, so the reference below is given these masks."""
+    C = u.shape[1]
+    one, zero = torch.ones(C, device=DEV), torch.zeros(C, device=DEV)
+    rm, rv = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
+    d = lambda t: t.to(DEV)
+    y1 = F_.conv3x3_bn_relu(F_.pack_nhwc(d(u)), F_.pack_conv_weights(d(w1)), one, zero, to_planes=False, precision=3,
+                            relu=False)
+    sc1, sh1, _, _ = F_.bn_batch_stats(y1, d(g1), d(b1), rm.clone(), rv.clone(), 0.1, 1e-5, True)
+    a1p, _, a1 = F_.bn_apply(y1, sc1, sh1, relu=True, nhwc=True, f32=True)
+    y2 = F_.conv3x3_bn_relu(a1p, F_.pack_conv_weights(d(w2)), one, zero, to_planes=False, precision=3, relu=False)
+    sc2, sh2, _, _ = F_.bn_batch_stats(y2, d(g2), d(b2), rm.clone(), rv.clone(), 0.1, 1e-5, True)
+    _, _, a2 = F_.bn_apply(y2, sc2, sh2, relu=True, f32=True)
+    return (a1 > 0).cpu(), (a2 > 0).cpu()
+
+
+def _double_conv_ref_with_masks(u, p, prefix, masks):
+    """oracle.double_conv_forward in training mode (unet.py:8-20) with the ReLU side prescribed by `masks`."""
+    for (ci, bi), mask in zip(((0, 1), (3, 4)), masks):
+        u = torch.nn.functional.conv2d(u, p[f"{prefix}.conv.{ci}.weight"], None, padding=1)
+        u = torch.nn.functional.batch_norm(u, None, None, p[f"{prefix}.conv.{bi}.weight"], p[f"{prefix}.conv.{bi}.bias"],
+                                           training=True, eps=1e-5)
+        u = u * mask.to(u.dtype)
+    return u
+
+
+@pytest.mark.parametrize("C,h,w,b", [(64, 5, 7, 3), (128, 12, 20, 2), (64, 9, 100, 1), (256, 28, 28, 2), (64, 3, 128, 2),
+                                     (64, 1, 1, 5)])
+def test_bridge_arbitrary_feature_map_sizes(C, h, w, b):
+    """Any width <= 128 / any height (partial TMA boxes, masked rows): eval forward, train forward and all gradients
+    against the oracle differentiated by torch autograd in float64."""
+    p = synth.amft_params(100 + h * w, C)
+    zx, zy = synth.features(h, b, C, h, w), synth.features(w, b, C, h, w)
+    p64 = {k: (v.double() if v.is_floating_point() else v) for k, v in p.items()}
+    m = A.bridge(in_c=C)
+    m.load_state_dict(p)
+    m = m.to(DEV).eval()
+    with torch.no_grad():
+        x, y = m(zx.to(DEV), zy.to(DEV))
+    ox, oy, _ = O.amft_forward(zx.double(), zy.double(), p64)
+    assert_close(x.cpu(), ox, 1e-3, "odd.eval.x")
+    assert_close(y.cpu(), oy, 1e-3, "odd.eval.y")
+    if b * h * w < 2:
+        return                                           # BatchNorm needs more than one value per channel to train
+    # training mode + gradients
+    m.train()
+    zxg, zyg = zx.to(DEV).requires_grad_(True), zy.to(DEV).requires_grad_(True)
+    tx, ty = m(zxg, zyg)
+    gen = torch.Generator().manual_seed(7)
+    rx, ry = torch.randn(tx.shape, generator=gen), torch.randn(ty.shape, generator=gen)
+    ((tx * rx.to(DEV)).sum() + (ty * ry.to(DEV)).sum()).backward()
+    leaves = {k: v.clone().requires_grad_(True) for k, v in p64.items() if v.is_floating_point() and "running" not in k}
+    pr = dict(p64)
+    pr.update(leaves)
+    zx64, zy64 = zx.double().requires_grad_(True), zy.double().requires_grad_(True)
+    # plain oracle for the forward values; for the gradients the ReLU sides are taken from the CUDA path (see above)
+    otx, oty, _ = O.amft_forward(zx.double(), zy.double(), p64, training=True)
+    assert_close(tx.detach().cpu(), otx, 1e-3, "odd.train.x")
+    assert_close(ty.detach().cpu(), oty, 1e-3, "odd.train.y")
+    br = lambda name: [p[name + k] for k in (".conv.0.weight", ".conv.1.weight", ".conv.1.bias", ".conv.3.weight",
+                                              ".conv.4.weight", ".conv.4.bias")]
+    masks_o = _relu_masks_of_branch(zy, *br("O2F"))
+    masks_f = _relu_masks_of_branch(zx, *br("F20"))
+    rtx = zx64 + _double_conv_ref_with_masks(zy64, pr, "O2F", masks_o)
+    rty = zy64 + _double_conv_ref_with_masks(zx64, pr, "F20", masks_f)
+    assert_close(rtx.detach(), otx, 1e-4, "odd.masked-reference.x")     # the masks only move values within rounding of 0
+    ((rtx * rx.double()).sum() + (rty * ry.double()).sum()).backward()
+    assert_close(zxg.grad.cpu(), zx64.grad, 2e-3, "odd.g_zx")
+    assert_close(zyg.grad.cpu(), zy64.grad, 2e-3, "odd.g_zy")
+    for name, prm in m.named_parameters():
+        assert_close(prm.grad.cpu(), leaves[name].grad, 2e-3, "odd.g_" + name)
+    F_.check_pipeline_watchdog()

@@ -361,3 +361,28 @@ def test_tensor_enc_matches_fp32_enc(b, h, w, enc_mode):
     if bool(agree.all()):
         assert_close(res["tensor"][4].cpu(), res["fp32"][4].cpu(), 1e-3, "gx")
         assert_close(res["tensor"][5].cpu(), res["fp32"][5].cpu(), 1e-3, "g_enc_w")
+
+
+@pytest.mark.parametrize("b,h,w", [(2, 28, 28), (3, 5, 7), (1, 9, 100)])
+def test_memory_module_tensor_dec_on_odd_feature_maps(b, h, w, dec_mode):
+    """The tensor-core dec GEMM (and its fused NHWC planes) on feature maps that do not tile into full 128-pixel boxes."""
+    C, D, M, k = 128, 64, 64, 2
+    p = synth.memory_params(31, C, D, M, k)
+    x = synth.features(32, b, C, h, w)
+    outs = {}
+    for mode in ("fp32", "tensor"):
+        dec_mode(mode)
+        m = A.enc_quan_dec_res_topk(C, D, M, k=k)
+        m.load_state_dict({"quan." + kk: v for kk, v in p.items()})
+        m = m.to(DEV).eval()
+        with torch.no_grad():
+            out, diff, q1 = m(x.to(DEV))
+        outs[mode] = (out, m.quan.quantize.last_idx.clone(), F_.planes_of(out))
+    F_.check_pipeline_watchdog()
+    assert torch.equal(outs["fp32"][1], outs["tensor"][1])
+    assert_close(outs["tensor"][0].cpu(), outs["fp32"][0].cpu(), 1e-4, "odd dec")
+    assert torch.equal(outs["tensor"][2], F_.pack_nhwc(outs["tensor"][0]))
+    o = O.memory_module_forward(x, p["enc.weight"], p["enc.bias"], p["quantize.embed"], p["dec.weight"], p["dec.bias"], k)
+    same = (outs["tensor"][1].cpu() == o["idx_topk"]).all(1).view(b, h, w)
+    assert same.float().mean() > 0.98
+    assert_close(outs["tensor"][0].cpu().permute(0, 2, 3, 1)[same], o["out"].permute(0, 2, 3, 1)[same], 1e-3, "odd dec vs oracle")
