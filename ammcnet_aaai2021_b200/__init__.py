@@ -11,9 +11,10 @@ from .scoring import VideoScorer, assemble_video_records, score_reduce, evaluate
 from .patch import patch_reference, unpatch_reference, swap_modules
 from .host_model import twostream, UNetMem_v7, get_twostream
 from .graphs import GraphedPath
+from .generator import GeneratorEngine
 
 __all__ = [
     "Quantize_topk", "enc_quan_dec_topk", "enc_quan_dec_res_topk", "bridge", "double_conv", "psnr_error",
     "psnr_per_frame", "VideoScorer", "assemble_video_records", "score_reduce", "evaluate", "LAM_MAP",
-    "patch_reference", "unpatch_reference", "swap_modules", "twostream", "UNetMem_v7", "get_twostream", "GraphedPath",
+    "patch_reference", "unpatch_reference", "swap_modules", "twostream", "UNetMem_v7", "get_twostream", "GraphedPath", "GeneratorEngine",
 ]

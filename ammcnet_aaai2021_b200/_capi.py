@@ -14,12 +14,24 @@ LIB_PATH = os.path.join(_PKG, "libammc_b200.so")
 
 P, I, L, F, Z = c_void_p, c_int, c_int64, c_float, c_size_t
 
+class ConvLayer(ctypes.Structure):
+    """`ammc_conv_layer` of include/ammc_b200.h (field order and types must match)."""
+    _fields_ = [("in_planes", c_void_p), ("in_cs", c_int), ("in_c_off", c_int),
+                ("wp", c_void_p), ("taps", c_int),
+                ("scale", c_void_p), ("shift", c_void_p), ("act", c_int),
+                ("out_planes", c_void_p), ("out_cs", c_int), ("out_c_off", c_int),
+                ("out_nchw", c_void_p), ("res_nchw", c_void_p), ("cout_valid", c_int),
+                ("b", c_int), ("h", c_int), ("w", c_int), ("Cin", c_int), ("Cout", c_int),
+                ("up2x", c_int), ("precision", c_int)]
+
+
 # name -> (restype, argtypes); must list every symbol of include/ammc_b200.h (tests/test_capi.py checks it)
 SIGNATURES = {
     "ammc_version": (I, []),
     "ammc_last_error": (c_char_p, []),
     "ammc_device_supported": (I, []),
     "ammc_debug_timeout": (I, [P]),
+    "ammc_debug_desc_probe": (I, [P, P, P, I, I, I, P]),
     "ammc_debug_tma_probe": (I, [P, P, P, P, P, P, I, P]),
     "ammc_mem_workspace_bytes": (Z, [I] * 7),
     "ammc_set_addressing_mode": (I, [I]),
@@ -42,7 +54,14 @@ SIGNATURES = {
     "ammc_pack_conv_weights": (I, [P, P, I, I, P]),
     "ammc_pack_nhwc": (I, [P, P, I, I, I, I, P]),
     "ammc_conv3x3_bn_relu": (I, [P] * 7 + [I] * 7 + [P]),
+    "ammc_conv_layer_run": (I, [ctypes.POINTER(ConvLayer), P]),
+    "ammc_pack_conv_weights_padded": (I, [P, P, I, I, I, I, I, P]),
+    "ammc_pack_convt_weights": (I, [P, P, I, I, P]),
+    "ammc_pack_nhwc_padded": (I, [P, P, I, I, I, I, I, P]),
+    "ammc_maxpool2_planes": (I, [P, I, I, P, I, I, I, I, P]),
+    "ammc_unpack_nhwc": (I, [P, I, I, P, I, I, I, I, P]),
     "ammc_set_conv_pair_mode": (I, [I]),
+    "ammc_set_conv_halo_mode": (I, [I]),
     "ammc_pack_conv_weights_1x1": (I, [P, P, I, I, P]),
     "ammc_conv1x1_bn_relu": (I, [P] * 7 + [I] * 7 + [P]),
     "ammc_bn_batch_stats": (I, [P] * 9 + [P, Z] + [I, I, I, I, F, F, I, P]),

@@ -30,18 +30,30 @@ constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;    // 16 KB
 
 struct ConvParams {
   int b, H, W, Cin, Cout;
-  int W_box, H_box, B_box, groups_h;
+  int W_box, H_box, B_box, groups_h, groups_w;
   int rows_valid;                // pixels actually covered by one TMA box (<= 128; < 128 when w does not divide 128)
   int tiles_m, tiles_n, ntaps;
   int n_pass;               // 1: hi*hi only; 3: (hi,hi) + (hi,lo) + (lo,hi)
-  int relu;
+  int act;                  // 0: none, 1: ReLU, 2: tanh (single-CTA kernel only)
   const float* scale;
   const float* shift;
-  __nv_bfloat16* out_planes;     // [2][b][H][W][Cout] or null
+  __nv_bfloat16* out_planes;     // [2][b][Ho][Wo][out_cs] (channels out_c_off .. of a possibly wider buffer) or null
   long long out_plane_stride;    // elements between the hi and lo plane
-  float* out_nchw;               // [b][Cout][H][W] or null
+  int out_cs, out_c_off;
+  int up2x, up_cout;             // transposed 2x2/stride-2 conv: column n = (dy*2+dx)*up_cout + co lands on pixel (2h+dy, 2w+dx)
+  float* out_nchw;               // [b][cout_valid][H][W] or null
   const float* res_nchw;         // same shape or null
+  int cout_valid;                // channels of out_nchw / res_nchw (< Cout when the weights were zero-padded)
 };
+
+// m-tile index -> first image / row / column of its TMA box
+__device__ __forceinline__ void tile_origin(int mt, int groups_w, int groups_h, int W_box, int H_box, int B_box,
+                                            int& img0, int& h0, int& w0) {
+  const int wg = mt % groups_w, t2 = mt / groups_w;
+  w0 = wg * W_box;
+  h0 = (t2 % groups_h) * H_box;
+  img0 = (t2 / groups_h) * B_box;
+}
 
 template <int BLOCK_N>
 struct ConvSmem {
@@ -91,7 +103,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int s = 0; uint32_t ph = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const int mt = t / p.tiles_n, nt = t % p.tiles_n;
-        const int img0 = (mt / p.groups_h) * p.B_box, h0 = (mt % p.groups_h) * p.H_box;
+        int img0, h0, w0;
+        tile_origin(mt, p.groups_w, p.groups_h, p.W_box, p.H_box, p.B_box, img0, h0, w0);
         const int n0 = nt * BLOCK_N;
         for (int ps = 0; ps < p.n_pass; ++ps) {
           const int pa = ps == 2 ? 1 : 0, pb = ps == 1 ? 1 : 0;   // (hi,hi) (hi,lo) (lo,hi)
@@ -101,7 +114,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               ptx::mbar_wait(&empty_bar[s], ph ^ 1, 1);
               ptx::mbar_expect_tx(&full_bar[s], p.rows_valid * 128 + S::B_BYTES);
               uint8_t* a_dst = smem + s * S::STAGE_BYTES;
-              ptx::tma_load_5d(a_dst, &tmA, &full_bar[s], cc * BLOCK_K, dx, h0 + dy, img0, pa);
+              ptx::tma_load_5d(a_dst, &tmA, &full_bar[s], cc * BLOCK_K, w0 + dx, h0 + dy, img0, pa);
               ptx::tma_load_3d(a_dst + A_BYTES, &tmB, &full_bar[s], tap * p.Cin + cc * BLOCK_K, n0, pb);
               if (++s == S::STAGES) { s = 0; ph ^= 1; }
             }
@@ -148,10 +161,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const int acc = it & 1;
       const uint32_t acc_ph = (it >> 1) & 1;
       const int mt = t / p.tiles_n, nt = t % p.tiles_n;
-      const int img = (mt / p.groups_h) * p.B_box + r / per_img;
+      int img0, h0, w0;
+      tile_origin(mt, p.groups_w, p.groups_h, p.W_box, p.H_box, p.B_box, img0, h0, w0);
+      const int img = img0 + r / per_img;
       const int rem = r % per_img;
-      const int hh = (mt % p.groups_h) * p.H_box + rem / p.W_box, ww = rem % p.W_box;
-      const bool valid = img < p.b && hh < p.H && r < p.rows_valid;   // rows past the box hold stale smem: never stored
+      const int hh = h0 + rem / p.W_box, ww = w0 + rem % p.W_box;
+      // rows past the box hold stale smem, columns past the row are TMA zero fill: never stored
+      const bool valid = img < p.b && hh < p.H && ww < p.W && r < p.rows_valid;
       const int n0 = nt * BLOCK_N;
       ptx::mbar_wait(&tmem_full[acc], acc_ph, 4);
       ptx::tc_fence_after();
@@ -164,27 +180,46 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int cbase = n0 + c32 * 32;
         float y[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float a = __uint_as_float(v[j]);
-          a = fmaf(a, __ldg(p.scale + cbase + j), __ldg(p.shift + cbase + j));
-          y[j] = p.relu ? fmaxf(a, 0.f) : a;
+        for (int g4 = 0; g4 < 8; ++g4) {
+          const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + cbase) + g4);
+          const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + cbase) + g4);
+          y[4 * g4 + 0] = fmaf(__uint_as_float(v[4 * g4 + 0]), sc.x, sh.x);
+          y[4 * g4 + 1] = fmaf(__uint_as_float(v[4 * g4 + 1]), sc.y, sh.y);
+          y[4 * g4 + 2] = fmaf(__uint_as_float(v[4 * g4 + 2]), sc.z, sh.z);
+          y[4 * g4 + 3] = fmaf(__uint_as_float(v[4 * g4 + 3]), sc.w, sh.w);
+        }
+        if (p.act == 2) {                 // tanh is ~25 instructions per element: keep it off the common path
+#pragma unroll
+          for (int j = 0; j < 32; ++j) y[j] = tanhf(y[j]);
+        } else if (p.act == 1) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j], 0.f);
         }
         if (valid) {
           const size_t hw = (size_t)p.H * p.W;
-          const size_t o0 = ((size_t)img * p.Cout + cbase) * hw + (size_t)hh * p.W + ww;
+          const size_t o0 = ((size_t)img * p.cout_valid + cbase) * hw + (size_t)hh * p.W + ww;
+          const int nv = p.cout_valid - cbase;       // channels of this chunk that exist in the NCHW tensors
           if (p.res_nchw) {                      // residual first: both output forms carry it
             size_t o = o0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) { y[j] += __ldg(p.res_nchw + o); o += hw; }
+            for (int j = 0; j < 32; ++j) { if (j < nv) y[j] += __ldg(p.res_nchw + o); o += hw; }
           }
           if (p.out_nchw) {
             size_t o = o0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) { p.out_nchw[o] = y[j]; o += hw; }
+            for (int j = 0; j < 32; ++j) { if (j < nv) p.out_nchw[o] = y[j]; o += hw; }
           }
           if (p.out_planes) {
-            const size_t pix = ((size_t)img * p.H + hh) * p.W + ww;
-            __nv_bfloat16* hi = p.out_planes + pix * p.Cout + cbase;
+            size_t pix;
+            int oc = cbase;
+            if (p.up2x) {
+              const int q4 = cbase / p.up_cout;
+              oc = cbase - q4 * p.up_cout;
+              pix = ((size_t)img * (2 * p.H) + 2 * hh + (q4 >> 1)) * (2 * p.W) + 2 * ww + (q4 & 1);
+            } else {
+              pix = ((size_t)img * p.H + hh) * p.W + ww;
+            }
+            __nv_bfloat16* hi = p.out_planes + pix * p.out_cs + p.out_c_off + oc;
             __nv_bfloat16* lo = hi + p.out_plane_stride;
             uint32_t hp[16], lp[16];
 #pragma unroll
@@ -283,7 +318,8 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       int s = 0; uint32_t ph = 0;
       for (int t = cluster_id; t < num_tiles; t += num_clusters) {
         const int mt = (t / p.tiles_n) * 2 + (int)rank, nt = t % p.tiles_n;
-        const int img0 = (mt / p.groups_h) * p.B_box, h0 = (mt % p.groups_h) * p.H_box;
+        int img0, h0, w0;
+        tile_origin(mt, p.groups_w, p.groups_h, p.W_box, p.H_box, p.B_box, img0, h0, w0);
         const int n0 = nt * PAIR_N + (int)rank * (PAIR_N / 2);
         for (int ps = 0; ps < (FUSED3 ? 1 : p.n_pass); ++ps) {
           const int pa = ps == 2 ? 1 : 0, pb = ps == 1 ? 1 : 0;   // (hi,hi) (hi,lo) (lo,hi)
@@ -296,12 +332,12 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
               if (FUSED3) {
 #pragma unroll
                 for (int pl = 0; pl < 2; ++pl) {       // [A_hi | B_hi | A_lo | B_lo]
-                  ptx::tma_load_5d_2sm(a_dst + pl * PAIR_TILE_BYTES, &tmA, &full_bar[s], cc * BLOCK_K, dx, h0 + dy, img0, pl);
+                  ptx::tma_load_5d_2sm(a_dst + pl * PAIR_TILE_BYTES, &tmA, &full_bar[s], cc * BLOCK_K, w0 + dx, h0 + dy, img0, pl);
                   ptx::tma_load_3d_2sm(a_dst + pl * PAIR_TILE_BYTES + A_BYTES, &tmB, &full_bar[s],
                                        tap * p.Cin + cc * BLOCK_K, n0, pl);
                 }
               } else {
-                ptx::tma_load_5d_2sm(a_dst, &tmA, &full_bar[s], cc * BLOCK_K, dx, h0 + dy, img0, pa);
+                ptx::tma_load_5d_2sm(a_dst, &tmA, &full_bar[s], cc * BLOCK_K, w0 + dx, h0 + dy, img0, pa);
                 ptx::tma_load_3d_2sm(a_dst + A_BYTES, &tmB, &full_bar[s], tap * p.Cin + cc * BLOCK_K, n0, pb);
               }
               if (++s == PAIR_STAGES) { s = 0; ph ^= 1; }
@@ -363,11 +399,18 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       const int acc = it & 1;
       const uint32_t acc_ph = (it >> 1) & 1;
       const int mt = (t / p.tiles_n) * 2 + (int)rank, nt = t % p.tiles_n;
-      const int img = (mt / p.groups_h) * p.B_box + r / per_img;
+      int img0, h0, w0;
+      tile_origin(mt, p.groups_w, p.groups_h, p.W_box, p.H_box, p.B_box, img0, h0, w0);
+      const int img = img0 + r / per_img;
       const int rem = r % per_img;
-      const int hh = (mt % p.groups_h) * p.H_box + rem / p.W_box, ww = rem % p.W_box;
-      const bool valid = img < p.b && mt < p.tiles_m && hh < p.H && r < p.rows_valid;
+      const int hh = h0 + rem / p.W_box, ww = w0 + rem % p.W_box;
+      const bool valid = img < p.b && mt < p.tiles_m && hh < p.H && ww < p.W && r < p.rows_valid;
       const int n0 = nt * PAIR_N + half * HALF_N;
+      // NHWC destination of this thread's pixel; a transposed conv scatters the (dy,dx) group of this 128-column half
+      const int q4 = p.up2x ? n0 / p.up_cout : 0;
+      const size_t opix = p.up2x ? ((size_t)img * (2 * p.H) + 2 * hh + (q4 >> 1)) * (2 * p.W) + 2 * ww + (q4 & 1)
+                                 : ((size_t)img * p.H + hh) * p.W + ww;
+      __nv_bfloat16* const oplane = p.out_planes + opix * p.out_cs + p.out_c_off - q4 * p.up_cout;
       const size_t obase = ((size_t)img * p.Cout + n0) * hw + (size_t)hh * p.W + ww;
       const bool has_res = valid && p.res_nchw != nullptr;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * PAIR_N + half * HALF_N;
@@ -401,7 +444,7 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               float a = fmaf(__uint_as_float(v[4 * g4 + j]), scv[j], shv[j]);
-              a = p.relu ? fmaxf(a, 0.f) : a;
+              a = p.act ? fmaxf(a, 0.f) : a;
               v[4 * g4 + j] = __float_as_uint(has_res ? a + rv[4 * g4 + j] : a);
             }
           }
@@ -417,8 +460,7 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
               for (int j = 0; j < 16; ++j) { p.out_nchw[o] = __uint_as_float(v[j]); o += hw; }
             }
             if (p.out_planes) {
-              const size_t pix = ((size_t)img * p.H + hh) * p.W + ww;
-              __nv_bfloat16* hi = p.out_planes + pix * p.Cout + cbase;
+              __nv_bfloat16* hi = oplane + cbase;
               __nv_bfloat16* lo = hi + p.out_plane_stride;
 #pragma unroll
               for (int g8 = 0; g8 < 2; ++g8) {               // 8 channels (16 B per plane) at a time
@@ -594,7 +636,7 @@ static int g_conv_fused3 = 1;      // pair kernel, precision 3: load hi+lo plane
 static int g_conv_pair_mode = 1;   // 1: CTA-pair kernel when Cout % 256 == 0; 0: single-CTA kernel everywhere
 
 bool conv_shape_supported(int b, int Cin, int Cout, int h, int w) {
-  return b > 0 && h > 0 && w > 0 && w <= 128 && Cin % 64 == 0 && Cout % 64 == 0;
+  return b > 0 && h > 0 && w > 0 && Cin % 64 == 0 && Cout % 64 == 0;
 }
 
 // w [Cout][Cin] fp32 -> [2][Cout][Cin] bf16 planes (1x1 conv / plain GEMM weights)
@@ -605,59 +647,82 @@ int pack_weights_1x1(const float* w, void* wp, int Cout, int Cin, cudaStream_t s
   return 0;
 }
 
-// Shared by the 3x3 (ntaps = 9) and 1x1 (ntaps = 1) entry points.
-int conv_igemm(const void* xp, const void* wp, const float* scale, const float* shift, void* out_planes,
-               float* out_nchw, const float* res_nchw, int b, int Cin, int Cout, int h, int w, int ntaps,
-               int precision, int relu, cudaStream_t st) {
-  AMMC_REQUIRE(xp && wp && scale && shift && (out_planes || out_nchw), "null pointer argument");
+bool halo_conv_applies(const ammc_conv_layer& L);
+int halo_conv_run(const ammc_conv_layer& L, cudaStream_t st);
+
+// The one launch path of the engine: every public conv entry point fills an ammc_conv_layer and lands here.
+int conv_run(const ammc_conv_layer& L, cudaStream_t st) {
+  const int b = L.b, h = L.h, w = L.w, Cin = L.Cin, Cout = L.Cout, ntaps = L.taps;
+  AMMC_REQUIRE(L.in_planes && L.wp && L.scale && L.shift && (L.out_planes || L.out_nchw), "null pointer argument");
   AMMC_REQUIRE(b > 0 && h > 0 && w > 0, "bad shape b=%d h=%d w=%d", b, h, w);
-  if (precision != 1 && precision != 3) return fail(AMMC_EINVAL, "precision must be 1 or 3 (got %d)", precision);
+  AMMC_REQUIRE(ntaps == 9 || ntaps == 1, "taps must be 9 (3x3) or 1 (1x1), got %d", ntaps);
+  if (L.precision != 1 && L.precision != 3) return fail(AMMC_EINVAL, "precision must be 1 or 3 (got %d)", L.precision);
   if (Cin % 64 != 0 || Cout % 64 != 0)
     return fail(AMMC_EUNSUPPORTED, "tcgen05 conv needs Cin and Cout multiples of 64 (got %d, %d)", Cin, Cout);
-  if (w > 128)
-    return fail(AMMC_EUNSUPPORTED, "tcgen05 conv supports feature maps up to 128 pixels wide (got %d)", w);
+  const int in_cs = L.in_cs > 0 ? L.in_cs : Cin;
+  const int cout_valid = L.cout_valid > 0 ? L.cout_valid : Cout;
+  AMMC_REQUIRE(in_cs % 8 == 0 && L.in_c_off % 8 == 0 && L.in_c_off >= 0 && L.in_c_off + Cin <= in_cs,
+               "input channel window [%d, %d) does not fit a %d-channel buffer (8-channel alignment)", L.in_c_off,
+               L.in_c_off + Cin, in_cs);
+  AMMC_REQUIRE(cout_valid <= Cout, "cout_valid %d > Cout %d", cout_valid, Cout);
+  AMMC_REQUIRE(L.act >= 0 && L.act <= 2, "act must be 0 (none), 1 (ReLU) or 2 (tanh)");
+  const int up_cout = L.up2x ? Cout / 4 : Cout;
+  if (L.up2x) {
+    AMMC_REQUIRE(ntaps == 1 && !L.out_nchw && !L.res_nchw && L.out_planes && cout_valid == Cout,
+                 "a transposed 2x2 conv is a 1x1 GEMM with NHWC plane output only");
+    AMMC_REQUIRE(Cout % 4 == 0 && up_cout % 32 == 0, "transposed conv needs Cout (=4*channels) with channels %% 32 == 0");
+  }
+  const int out_cs = L.out_cs > 0 ? L.out_cs : up_cout;
+  AMMC_REQUIRE(!L.out_planes || (out_cs % 8 == 0 && L.out_c_off % 8 == 0 && L.out_c_off >= 0 &&
+                                 L.out_c_off + (L.up2x ? up_cout : cout_valid) <= out_cs),
+               "output channel window does not fit a %d-channel buffer (8-channel alignment)", out_cs);
+  AMMC_REQUIRE(!L.out_planes || cout_valid == Cout, "NHWC plane output needs cout_valid == Cout");
+  if (halo_conv_applies(L)) return halo_conv_run(L, st);     // wide, shallow layers: tap operands from one halo tile
   ConvParams p;
   p.b = b; p.H = h; p.W = w; p.Cin = Cin; p.Cout = Cout;
-  // one TMA box = W_box x H_box x B_box pixels <= 128: whole rows, as many as fit; whole images when a full image fits
-  p.W_box = w;
-  p.H_box = min(h, 128 / w);
-  p.B_box = (p.H_box == h) ? max(1, 128 / (w * h)) : 1;
+  // one TMA box = W_box x H_box x B_box pixels <= 128: whole rows, as many as fit; whole images when a full image
+  // fits; rows wider than 128 pixels are cut into 128-pixel segments (the last one zero-filled past the row end)
+  p.W_box = min(w, 128);
+  p.groups_w = ceil_div(w, p.W_box);
+  p.H_box = p.groups_w == 1 ? min(h, 128 / w) : 1;
+  p.B_box = (p.groups_w == 1 && p.H_box == h) ? max(1, 128 / (w * h)) : 1;
   p.groups_h = ceil_div(h, p.H_box);
   p.rows_valid = p.W_box * p.H_box * p.B_box;
-  p.tiles_m = ceil_div(b, p.B_box) * p.groups_h;
+  p.tiles_m = ceil_div(b, p.B_box) * p.groups_h * p.groups_w;
   const int block_n = (Cout % 256 == 0) ? 256 : (Cout % 128 == 0 ? 128 : 64);
   p.tiles_n = Cout / block_n;
   p.ntaps = ntaps;
-  p.n_pass = precision;
-  p.relu = relu;
-  p.scale = scale; p.shift = shift;
-  p.out_planes = (__nv_bfloat16*)out_planes;
-  p.out_plane_stride = (long long)b * h * w * Cout;
-  p.out_nchw = out_nchw;
-  p.res_nchw = res_nchw;
+  p.n_pass = L.precision;
+  p.act = L.act;
+  p.scale = L.scale; p.shift = L.shift;
+  p.out_planes = (__nv_bfloat16*)L.out_planes;
+  p.out_cs = out_cs; p.out_c_off = L.out_c_off;
+  p.up2x = L.up2x ? 1 : 0; p.up_cout = up_cout;
+  p.out_plane_stride = (long long)b * h * w * (L.up2x ? 4 : 1) * out_cs;
+  p.out_nchw = L.out_nchw;
+  p.res_nchw = L.res_nchw;
+  p.cout_valid = cout_valid;
 
   CUtensorMap tmA, tmB;
   {
     cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)b, 2};
-    cuuint64_t strides[4] = {(cuuint64_t)Cin * 2, (cuuint64_t)w * Cin * 2, (cuuint64_t)h * w * Cin * 2,
-                             (cuuint64_t)b * h * w * Cin * 2};
+    cuuint64_t strides[4] = {(cuuint64_t)in_cs * 2, (cuuint64_t)w * in_cs * 2, (cuuint64_t)h * w * in_cs * 2,
+                             (cuuint64_t)b * h * w * in_cs * 2};
     cuuint32_t box[5] = {64, (cuuint32_t)p.W_box, (cuuint32_t)p.H_box, (cuuint32_t)p.B_box, 1};
-    if (int rc = make_map(&tmA, xp, 5, dims, strides, box)) return rc;
+    if (int rc = make_map(&tmA, (const __nv_bfloat16*)L.in_planes + L.in_c_off, 5, dims, strides, box)) return rc;
   }
+  // the pair epilogue maps each 128-column half to ONE (dy,dx) group of a transposed conv
+  const bool pair = block_n == 256 && g_conv_pair_mode && L.act != 2 && cout_valid == Cout &&
+                    (!L.up2x || up_cout % 128 == 0);
   {
-    const cuuint64_t K = (cuuint64_t)ntaps * Cin;
-    cuuint64_t dims[3] = {K, (cuuint64_t)Cout, 2};
-    cuuint64_t strides[2] = {K * 2, (cuuint64_t)Cout * K * 2};
-    cuuint32_t box[3] = {64, (cuuint32_t)block_n, 1};
-    if (int rc = make_map(&tmB, wp, 3, dims, strides, box)) return rc;
-  }
-  if (block_n == 256 && g_conv_pair_mode) {
     // B boxes are per-CTA halves (128 channels) in the pair kernel
     const cuuint64_t K = (cuuint64_t)ntaps * Cin;
     cuuint64_t dims[3] = {K, (cuuint64_t)Cout, 2};
     cuuint64_t strides[2] = {K * 2, (cuuint64_t)Cout * K * 2};
-    cuuint32_t box[3] = {64, (cuuint32_t)(PAIR_N / 2), 1};
-    if (int rc = make_map(&tmB, wp, 3, dims, strides, box)) return rc;
+    cuuint32_t box[3] = {64, (cuuint32_t)(pair ? PAIR_N / 2 : block_n), 1};
+    if (int rc = make_map(&tmB, L.wp, 3, dims, strides, box)) return rc;
+  }
+  if (pair) {
     static bool configured[64] = {false};
     int dev = 0;
     AMMC_CUDA_CHECK(cudaGetDevice(&dev));
@@ -668,7 +733,7 @@ int conv_igemm(const void* xp, const void* wp, const float* scale, const float* 
     }
     const int pair_tiles = ((p.tiles_m + 1) / 2) * p.tiles_n;
     const int clusters = min(num_sms() / 2, pair_tiles);
-    if (precision == 3 && g_conv_fused3)
+    if (L.precision == 3 && g_conv_fused3)
       conv_igemm_pair_kernel<true><<<2 * clusters, PAIR_THREADS, PAIR_SMEM, st>>>(tmA, tmB, p);
     else
       conv_igemm_pair_kernel<false><<<2 * clusters, PAIR_THREADS, PAIR_SMEM, st>>>(tmA, tmB, p);
@@ -682,11 +747,27 @@ int conv_igemm(const void* xp, const void* wp, const float* scale, const float* 
   }
 }
 
+// Shared by the plain 3x3 (ntaps = 9) and 1x1 (ntaps = 1) entry points.
+int conv_igemm(const void* xp, const void* wp, const float* scale, const float* shift, void* out_planes,
+               float* out_nchw, const float* res_nchw, int b, int Cin, int Cout, int h, int w, int ntaps,
+               int precision, int relu, cudaStream_t st) {
+  ammc_conv_layer L = {};
+  L.in_planes = xp; L.wp = wp; L.taps = ntaps; L.scale = scale; L.shift = shift; L.act = relu ? 1 : 0;
+  L.out_planes = out_planes; L.out_nchw = out_nchw; L.res_nchw = res_nchw;
+  L.b = b; L.h = h; L.w = w; L.Cin = Cin; L.Cout = Cout; L.precision = precision;
+  return conv_run(L, st);
+}
+
 }  // namespace ammc
 
 namespace ammc { AMMC_DEFINE_TIMEOUT_READER(timeout_reader_conv) }
 
 using namespace ammc;
+
+extern "C" int ammc_conv_layer_run(const ammc_conv_layer* layer, void* stream) {
+  AMMC_REQUIRE(layer != nullptr, "null layer descriptor");
+  return conv_run(*layer, (cudaStream_t)stream);
+}
 
 extern "C" int ammc_set_conv_pair_mode(int on) {
   g_conv_pair_mode = on ? 1 : 0;       // bit 1 (value 2/3): keep the pair kernel but stream the K loop three times

@@ -69,7 +69,7 @@ def _count(n):
 
 
 # optional CUDA-event bracketing of the dominant kernel (bench.py's roofline measurement, live in the timed region)
-PROFILE = {"on": False, "events": []}
+PROFILE = {"on": False, "events": [], "tags": []}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -155,6 +155,12 @@ def set_conv_pair_mode(on):
     """True/1: CTA-pair (cta_group::2) conv kernel with fused hi/lo stages (default); 3: pair kernel streaming K three
     times (bit-identical to the single-CTA kernel); False/0: single-CTA kernel.  For A/B measurements only."""
     _capi.call("ammc_set_conv_pair_mode", int(on))
+
+
+def set_conv_halo_mode(on: bool):
+    """True (default): wide 3x3 layers with Cout 64/128 use the halo kernel (tap operands as shifted descriptors over
+    one halo tile); False: always the generic implicit GEMM.  For A/B measurements only."""
+    _capi.call("ammc_set_conv_halo_mode", int(bool(on)))
 
 
 def set_addressing_mode(mode: str = "auto"):
@@ -375,6 +381,106 @@ def conv3x3_bn_relu(xp, wp, scale, shift, *, to_planes: bool, residual: Optional
             PROFILE["events"].append((ev0, ev1))
     _count(1)
     return out_p if to_planes else out_n
+
+
+# --------------------------------------------------------------------------------------------------
+# general layer form of the conv engine (U-Net encoder / decoder)
+# --------------------------------------------------------------------------------------------------
+def conv_layer(in_planes, wp, scale, shift, *, taps: int = 9, act: int = 1, Cin: Optional[int] = None, in_c_off: int = 0,
+               out_planes=None, out_c_off: int = 0, out_nchw=None, residual=None, cout_valid: int = 0,
+               up2x: bool = False, precision: int = 3):
+    """One launch of `ammc_conv_layer_run`.  in_planes [2,b,h,w,in_cs] bf16 (channel window [in_c_off, +Cin));
+    wp [2,Cout,taps*Cin]; out_planes [2,b,ho,wo,out_cs] (written at out_c_off) and/or out_nchw [b,cout_valid,h,w]."""
+    _, b, h, w, in_cs = in_planes.shape
+    Cout = wp.shape[1]
+    Cin = wp.shape[2] // taps if Cin is None else Cin
+    dev = in_planes.device
+    _check_device(dev)
+    L = _capi.ConvLayer()
+    L.in_planes, L.in_cs, L.in_c_off = in_planes.data_ptr(), in_cs, in_c_off
+    L.wp, L.taps = wp.data_ptr(), taps
+    L.scale, L.shift, L.act = scale.data_ptr(), shift.data_ptr(), int(act)
+    if out_planes is not None:
+        ho, wo = (2 * h, 2 * w) if up2x else (h, w)
+        if tuple(out_planes.shape[:4]) != (2, b, ho, wo) or out_planes.dtype != torch.bfloat16:
+            raise RuntimeError("ammc_b200: out_planes must be bf16 [2,%d,%d,%d,cs], got %s" % (b, ho, wo, tuple(out_planes.shape)))
+        L.out_planes, L.out_cs, L.out_c_off = out_planes.data_ptr(), out_planes.shape[4], out_c_off
+    if out_nchw is not None:
+        _require_cuda_f32(out_nchw, names=("out_nchw",))
+        L.out_nchw = out_nchw.data_ptr()
+    if residual is not None:
+        _require_cuda_f32(residual, names=("residual",))
+        residual = residual.contiguous()
+        L.res_nchw = residual.data_ptr()
+    L.cout_valid = cout_valid
+    L.b, L.h, L.w, L.Cin, L.Cout = b, h, w, Cin, Cout
+    L.up2x, L.precision = int(bool(up2x)), int(precision)
+    with torch.cuda.device(dev):
+        if PROFILE["on"]:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+        _capi.call("ammc_conv_layer_run", ctypes.byref(L), _stream())
+        if PROFILE["on"]:
+            ev1.record()
+            PROFILE["events"].append((ev0, ev1))
+            PROFILE["tags"].append(dict(b=b, h=h, w=w, Cin=Cin, Cout=Cout, taps=taps, up2x=bool(up2x), precision=precision))
+    _count(1)
+
+
+def pack_conv_weights_padded(w: torch.Tensor, cout_pad: int, cin_pad: int) -> torch.Tensor:
+    """[Cout,Cin,3,3] or [Cout,Cin,1,1] fp32 -> [2,cout_pad,taps*cin_pad] bf16 planes, zero-padded."""
+    _require_cuda_f32(w, names=("conv weight",))
+    Cout, Cin = w.shape[0], w.shape[1]
+    taps = w.shape[2] * w.shape[3]
+    wp = torch.empty((2, cout_pad, taps * cin_pad), dtype=torch.bfloat16, device=w.device)
+    with torch.cuda.device(w.device):
+        _capi.call("ammc_pack_conv_weights_padded", _p(w.contiguous()), _p(wp), Cout, Cin, cout_pad, cin_pad, taps, _stream())
+    _count(1)
+    return wp
+
+
+def pack_convT_weights(w: torch.Tensor) -> torch.Tensor:
+    """ConvTranspose2d(k=2, s=2) weight [Cin,Cout,2,2] -> [2, 4*Cout, Cin] bf16 planes (row (dy*2+dx)*Cout + co)."""
+    _require_cuda_f32(w, names=("ConvTranspose2d weight",))
+    Cin, Cout = w.shape[0], w.shape[1]
+    if tuple(w.shape[2:]) != (2, 2):
+        raise RuntimeError("ammc_b200: only the 2x2 / stride-2 transposed conv of unet.py:46 is supported")
+    wp = torch.empty((2, 4 * Cout, Cin), dtype=torch.bfloat16, device=w.device)
+    with torch.cuda.device(w.device):
+        _capi.call("ammc_pack_convt_weights", _p(w.contiguous()), _p(wp), Cin, Cout, _stream())
+    _count(1)
+    return wp
+
+
+def pack_nhwc_padded(x: torch.Tensor, c_pad: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _require_cuda_f32(x, names=("activation",))
+    b, C, h, w = x.shape
+    xp = torch.empty((2, b, h, w, c_pad), dtype=torch.bfloat16, device=x.device) if out is None else out
+    with torch.cuda.device(x.device):
+        _capi.call("ammc_pack_nhwc_padded", _p(x.contiguous()), _p(xp), b, C, c_pad, h, w, _stream())
+    _count(1)
+    return xp
+
+
+def maxpool2_planes(in_planes: torch.Tensor, C: int, in_c_off: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """MaxPool2d(2) on the channel window [in_c_off, +C) of NHWC planes -> dense [2,b,h/2,w/2,C] planes."""
+    _, b, h, w, cs = in_planes.shape
+    o = torch.empty((2, b, h // 2, w // 2, C), dtype=torch.bfloat16, device=in_planes.device) if out is None else out
+    with torch.cuda.device(in_planes.device):
+        _capi.call("ammc_maxpool2_planes", _p(in_planes), cs, in_c_off, _p(o), b, h, w, C, _stream())
+    _count(1)
+    return o
+
+
+def unpack_nhwc(planes: torch.Tensor, C: Optional[int] = None, c_off: int = 0) -> torch.Tensor:
+    """NHWC hi/lo planes (channel window) -> fp32 NCHW tensor."""
+    _, b, h, w, cs = planes.shape
+    C = cs - c_off if C is None else C
+    x = torch.empty((b, C, h, w), dtype=torch.float32, device=planes.device)
+    with torch.cuda.device(planes.device):
+        _capi.call("ammc_unpack_nhwc", _p(planes), cs, c_off, _p(x), b, C, h, w, _stream())
+    _count(1)
+    return x
 
 
 def bn_batch_stats(y, gamma, beta, running_mean, running_var, momentum: float, eps: float, training: bool):

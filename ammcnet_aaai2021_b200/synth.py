@@ -87,6 +87,66 @@ def path_params(seed: int, C: int = 512, D: int = 64, M: int = 256, k: int = 2) 
     return p
 
 
+def double_conv_params(prefix: str, in_c: int, out_c: int, g: torch.Generator,
+                       trained_bn: bool = True) -> Dict[str, torch.Tensor]:
+    """Parameters and buffers of one `double_conv(in_c, out_c)` (reference unet.py:8-16) under `prefix`.conv.*"""
+    p: Dict[str, torch.Tensor] = {}
+    for (ci, bi), (cin, cout) in zip(((0, 1), (3, 4)), ((in_c, out_c), (out_c, out_c))):
+        w, _ = conv_default_init(cout, cin, 3, g, bias=False)
+        p[f"{prefix}.conv.{ci}.weight"] = w
+        if trained_bn:
+            p[f"{prefix}.conv.{bi}.weight"] = 0.5 + torch.rand((cout,), generator=g)
+            p[f"{prefix}.conv.{bi}.bias"] = 0.2 * torch.randn((cout,), generator=g)
+            p[f"{prefix}.conv.{bi}.running_mean"] = 0.1 * torch.randn((cout,), generator=g)
+            p[f"{prefix}.conv.{bi}.running_var"] = 0.05 + 0.2 * torch.rand((cout,), generator=g)
+        else:
+            p[f"{prefix}.conv.{bi}.weight"] = torch.ones(cout)
+            p[f"{prefix}.conv.{bi}.bias"] = torch.zeros(cout)
+            p[f"{prefix}.conv.{bi}.running_mean"] = torch.zeros(cout)
+            p[f"{prefix}.conv.{bi}.running_var"] = torch.ones(cout)
+        p[f"{prefix}.conv.{bi}.num_batches_tracked"] = torch.zeros((), dtype=torch.long)
+    return p
+
+
+def unet_params(seed: int, in_c: int, out_c: int, D: int = 64, M: int = 256, k: int = 2,
+                prefix: str = "") -> Dict[str, torch.Tensor]:
+    """Every parameter/buffer of one `UNetMem_v7` stream (reference unet.py:908-922) under the state_dict names."""
+    g = _gen(seed)
+    p: Dict[str, torch.Tensor] = {}
+    p.update(double_conv_params(prefix + "inc.conv", in_c, 64, g))
+    for name, (ci, co) in (("down1", (64, 128)), ("down2", (128, 256)), ("down3", (256, 512))):
+        p.update(double_conv_params(f"{prefix}{name}.mpconv.1", ci, co, g))
+    for name, (ci, co) in (("up1", (512, 256)), ("up2", (256, 128)), ("up3", (128, 64))):
+        # ConvTranspose2d(ci, ci//2, 2, stride=2): weight [ci, ci//2, 2, 2]; torch's fan_in for it is (ci//2)*4
+        bound = 1.0 / math.sqrt((ci // 2) * 4)
+        p[f"{prefix}{name}.up.weight"] = _uniform((ci, ci // 2, 2, 2), bound, g)
+        p[f"{prefix}{name}.up.bias"] = _uniform((ci // 2,), bound, g)
+        p.update(double_conv_params(f"{prefix}{name}.conv", ci, co, g))
+    w, b = conv_default_init(out_c, 64, 3, g)
+    p[prefix + "outc.weight"], p[prefix + "outc.bias"] = w, b
+    p.update(memory_params(seed * 10 + 1, 512, D, M, k, prefix=prefix + "vq_down3.quan."))
+    return p
+
+
+def generator_params(seed: int, in_channel=(12, 6), out_channel=(3, 2), D: int = 64, M: int = 256,
+                     k: int = 2) -> Dict[str, torch.Tensor]:
+    """state_dict of the shipped `twostream` generator (reference unet.py:967-979, 1241-1249): 222 entries."""
+    p = {}
+    p.update(unet_params(seed * 7 + 1, in_channel[0], out_channel[0], D, M, k, prefix="rgb."))
+    p.update(unet_params(seed * 7 + 2, in_channel[1], out_channel[1], D, M, k, prefix="op."))
+    p.update(amft_params(seed * 7 + 3, 512, prefix="bridge."))
+    return p
+
+
+def generator_inputs(seed: int, b: int, h: int = 256, w: int = 256, in_channel=(12, 6)):
+    """(rgb_input, op_input) with the loader's value ranges (two_stream_dataset.py:94-95,503-506)."""
+    g = _gen(seed)
+    rgb = _uniform((b, in_channel[0], h, w), 1.0, g)
+    op = torch.randn((b, in_channel[1], h, w), generator=g, dtype=torch.float32) * (4.0 / 256.0)
+    op[:, 1::2] = op[:, 0::2] / 256.0
+    return rgb, op
+
+
 def features(seed: int, b: int, C: int = 512, h: int = 32, w: int = 32) -> torch.Tensor:
     """ReLU(N(0,1)) bottleneck features, NCHW fp32."""
     return torch.relu(torch.randn((b, C, h, w), generator=_gen(seed), dtype=torch.float32))

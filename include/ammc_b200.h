@@ -43,6 +43,8 @@ int ammc_device_supported(void);
  * instead of hanging the GPU.  Returns 0 when no wait timed out since the last call, 1 with out4 = {kernel family
  * (1 conv, 2 addressing, 3 training), wait tag, block, thread} otherwise, negative on CUDA errors.  Synchronises. */
 int ammc_debug_timeout(int* out4);
+/* Debug aid: UMMA K-major SWIZZLE_128B descriptor starting at an arbitrary 128-byte row (see csrc/halo_conv.cu) */
+int ammc_debug_desc_probe(const void* a, const void* b, float* out, int rows, int row_off, int base_off, void* stream);
 /* Debug aid: TMA-load one 5-D bf16 box (128B swizzle, zero OOB fill) and dump the raw shared-memory bytes to `out`. */
 int ammc_debug_tma_probe(const void* base, const int64_t* dims5, const int64_t* strides4_bytes, const int* box5,
                          const int* coords5, void* out, int out_bytes, void* stream);
@@ -168,11 +170,50 @@ int ammc_pack_nhwc(const float* x, void* xp, int b, int C, int h, int w, void* s
 int ammc_conv3x3_bn_relu(const void* xp, const void* wp, const float* scale, const float* shift,
                          void* out_planes, float* out_nchw, const float* res_nchw,
                          int b, int Cin, int Cout, int h, int w, int precision, int relu, void* stream);
+/* ---- general layer form of the same engine (the U-Net encoder/decoder around the path,
+ *      reference Code/models/unet.py:8-59 double_conv / inconv / down / up, 908-937 UNetMem_v7) --------------------------
+ * One descriptor covers: 3x3 conv + folded BN + ReLU (unet.py:11-16), the 1x1 GEMMs, the transposed 2x2 / stride-2
+ * conv of `up` (unet.py:46, a 1x1 GEMM with 4*Cout columns whose epilogue scatters column (dy*2+dx)*Cout + co to pixel
+ * (2h+dy, 2w+dx)), the final 3x3 conv + bias + tanh (unet.py:918,936), reads from / writes into a channel window of a
+ * wider NHWC buffer (so torch.cat([skip, up], 1) at unet.py:58 never copies), and rows wider than 128 pixels. */
+typedef struct ammc_conv_layer {
+  const void* in_planes;   /* [2][b,h,w,in_cs] bf16 hi/lo planes; the layer reads channels [in_c_off, in_c_off + Cin) */
+  int in_cs, in_c_off;     /* in_cs = 0 means Cin */
+  const void* wp;          /* [2][Cout][taps*Cin] bf16 planes (ammc_pack_conv_weights* / ammc_pack_convt_weights) */
+  int taps;                /* 9 (3x3, padding 1) or 1 */
+  const float* scale;      /* [Cout] */
+  const float* shift;      /* [Cout]  y = act(acc*scale + shift) */
+  int act;                 /* 0 none, 1 ReLU, 2 tanh */
+  void* out_planes;        /* [2][b,ho,wo,out_cs] bf16 planes or NULL; channels written at out_c_off */
+  int out_cs, out_c_off;   /* out_cs = 0 means dense */
+  float* out_nchw;         /* [b,cout_valid,h,w] fp32 or NULL */
+  const float* res_nchw;   /* added before both outputs, or NULL */
+  int cout_valid;          /* 0 = Cout; < Cout when the weights/scale/shift were zero-padded to a multiple of 64 */
+  int b, h, w, Cin, Cout;  /* input feature map; Cin, Cout multiples of 64 */
+  int up2x;                /* 1: transposed 2x2 stride-2 conv (taps = 1, Cout = 4*channels, output 2h x 2w) */
+  int precision;           /* 3: split-bf16 x3 (fp32 parity); 1: single bf16 pass */
+} ammc_conv_layer;
+int ammc_conv_layer_run(const ammc_conv_layer* layer, void* stream);
+/* w [Cout,Cin,3,3] (taps=9) or [Cout,Cin] (taps=1) -> wp [2][Cout_pad][taps*Cin_pad], zero-padded rows/columns */
+int ammc_pack_conv_weights_padded(const float* w, void* wp, int Cout, int Cin, int Cout_pad, int Cin_pad, int taps,
+                                  void* stream);
+/* ConvTranspose2d weight [Cin,Cout,2,2] -> wp [2][4*Cout][Cin], row (dy*2+dx)*Cout + co */
+int ammc_pack_convt_weights(const float* w, void* wp, int Cin, int Cout, void* stream);
+/* x [b,C,h,w] fp32 -> planes [2][b,h,w,C_pad] (channels C..C_pad-1 zero) */
+int ammc_pack_nhwc_padded(const float* x, void* xp, int b, int C, int C_pad, int h, int w, void* stream);
+/* MaxPool2d(2) (unet.py:33) on NHWC planes: in [2][b,h,w,in_cs] channels [in_c_off, in_c_off+C) -> out [2][b,h/2,w/2,C] */
+int ammc_maxpool2_planes(const void* in_planes, int in_cs, int in_c_off, void* out_planes, int b, int h, int w, int C,
+                         void* stream);
+/* planes [2][b,h,w,cs] channels [c_off, c_off+C) -> fp32 NCHW [b,C,h,w] (hi + lo) */
+int ammc_unpack_nhwc(const void* xp, int cs, int c_off, float* x, int b, int C, int h, int w, void* stream);
 /* 1 (default): convolutions with Cout % 256 == 0 use the CTA-pair (cta_group::2, M=256) kernel, which at precision 3
  * loads the hi and lo planes of a K block once and issues hi*hi, hi*lo, lo*hi back to back; 3: CTA-pair kernel that
  * streams the K loop three times instead (bit-identical to the single-CTA kernel); 0: always the single-CTA kernel.
  * The variants differ only in fp32 summation order; the switch exists for A/B measurements. */
 int ammc_set_conv_pair_mode(int on);
+/* 1 (default): 3x3 layers with Cout 64 / 128 on maps >= 64 pixels wide use the halo kernel (one halo tile per 64-channel
+ * block, nine shifted tap descriptors over it); 0: always the generic implicit GEMM.  For A/B measurements. */
+int ammc_set_conv_halo_mode(int on);
 /* 1x1 convolution on the same tensor-core engine (a plain [N,Cin] x [Cout,Cin]^T GEMM, no halo):
  *   wp [2 planes][Cout][Cin] bf16 (pack with ammc_pack_conv_weights_1x1). */
 int ammc_pack_conv_weights_1x1(const float* w, void* wp, int Cout, int Cin, void* stream);

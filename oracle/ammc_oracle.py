@@ -247,6 +247,51 @@ def roc_auc(labels: np.ndarray, scores: np.ndarray, pos_label: int = 0) -> float
 # --------------------------------------------------------------------------------------------------
 # whole path (one "step" of the metric): both memory modules + AMFT + rgb PSNR
 # --------------------------------------------------------------------------------------------------
+# --------------------------------------------------------------------------------------------------
+# the U-Net encoder / decoder around the path, eval mode
+# --------------------------------------------------------------------------------------------------
+def unet_encode(x, p: Dict[str, torch.Tensor], s: str):
+    """inc / down1-3 of UNetMem_v7 (Code/models/unet.py:924-928; inconv 23-30, down 33-42): x1, x2, x3, x4."""
+    x1, _ = double_conv_forward(x, p, s + "inc.conv")
+    x2, _ = double_conv_forward(F.max_pool2d(x1, 2), p, s + "down1.mpconv.1")
+    x3, _ = double_conv_forward(F.max_pool2d(x2, 2), p, s + "down2.mpconv.1")
+    x4, _ = double_conv_forward(F.max_pool2d(x3, 2), p, s + "down3.mpconv.1")
+    return x1, x2, x3, x4
+
+
+def unet_up(x1, x2, p: Dict[str, torch.Tensor], prefix: str):
+    """up.forward, Code/models/unet.py:50-59: ConvTranspose2d(2, stride 2), pad to the skip, cat([skip, up]), double_conv."""
+    x1 = F.conv_transpose2d(x1, p[prefix + ".up.weight"], p[prefix + ".up.bias"], stride=2)
+    dy, dx = x2.shape[2] - x1.shape[2], x2.shape[3] - x1.shape[3]
+    x1 = F.pad(x1, (dx // 2, dx - dx // 2, dy // 2, dy - dy // 2))
+    out, _ = double_conv_forward(torch.cat([x2, x1], dim=1), p, prefix + ".conv")
+    return out
+
+
+def unet_decode(x4, x3, x2, x1, p: Dict[str, torch.Tensor], s: str):
+    """up1-3 + outc of UNetMem_v7 (Code/models/unet.py:930-933); the caller applies tanh (unet.py:937)."""
+    x = unet_up(x4, x3, p, s + "up1")
+    x = unet_up(x, x2, p, s + "up2")
+    x = unet_up(x, x1, p, s + "up3")
+    return F.conv2d(x, p[s + "outc.weight"], p[s + "outc.bias"], padding=1)
+
+
+def twostream_forward(rgb_x, op_x, p: Dict[str, torch.Tensor], k: int):
+    """twostream.forward in eval mode, Code/models/unet.py:981-1007.
+    Returns (tanh rgb, tanh op, (rgb_diff, op_diff), (rgb_q1, op_q1))."""
+    enc, mem = {}, {}
+    for s, x in (("rgb", rgb_x), ("op", op_x)):
+        enc[s] = unet_encode(x, p, s + ".")
+        pre = f"{s}.vq_down3.quan."
+        mem[s] = memory_module_forward(enc[s][3], p[pre + "enc.weight"], p[pre + "enc.bias"], p[pre + "quantize.embed"],
+                                       p[pre + "dec.weight"], p[pre + "dec.bias"], k)
+    r4, o4, _ = amft_forward(mem["rgb"]["out"], mem["op"]["out"], p, "bridge")
+    rgb_y = unet_decode(r4, enc["rgb"][2], enc["rgb"][1], enc["rgb"][0], p, "rgb.")
+    op_y = unet_decode(o4, enc["op"][2], enc["op"][1], enc["op"][0], p, "op.")
+    return (torch.tanh(rgb_y), torch.tanh(op_y), (mem["rgb"]["diff"], mem["op"]["diff"]),
+            (mem["rgb"]["quantize"], mem["op"]["quantize"]))
+
+
 def path_forward(x_rgb, x_op, gen, gt, params: Dict[str, torch.Tensor], k: int):
     """The starred region of twostream.forward (Code/models/unet.py:985-994) followed by the per-frame rgb
     PSNR of test_helper.py:445-452.  `params` uses the reference state_dict key names

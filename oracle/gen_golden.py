@@ -268,6 +268,30 @@ def gen_records():
              for v in range(len(lengths))})
 
 
+GEN_CASES = {
+    # the shipped twostream generator (12/6 -> 3/2 channels, D=64, M=256, k=2) on small frames
+    "gen_64": dict(b=2, h=64, w=64, seed=31),
+    "gen_96x160": dict(b=1, h=96, w=160, seed=32),      # non-square, 160 = one full + one partial 128-pixel segment
+}
+
+
+def gen_generator(ref_unet):
+    """Whole twostream generator, eval mode: reference vs the oracle's functional restatement (unet.py:981-1007)."""
+    for name, c in GEN_CASES.items():
+        p = synth.generator_params(c["seed"])
+        ref = ref_unet.twostream(12, 3, 6, 2, embed_dim=64, n_embed=256, k=2)
+        ref.load_state_dict({k: v.clone() for k, v in p.items()}, strict=True)
+        ref.eval()
+        rgb, op = synth.generator_inputs(c["seed"] + 500, c["b"], c["h"], c["w"])
+        with torch.no_grad():
+            ry, oy, (rd, od), (rq, oq) = ref(rgb, op)
+            ary, aoy, (ard, aod), (arq, aoq) = O.twostream_forward(rgb, op, p, 2)
+        for a, b_, what in ((ary, ry, "rgb_y"), (aoy, oy, "op_y"), (ard, rd, "rgb_diff"), (aod, od, "op_diff"),
+                            (arq, rq, "rgb_q1"), (aoq, oq, "op_q1")):
+            _close(a, b_, 1e-6, f"{name}.{what}")
+        _save(name, dict(kind="generator", **c), rgb_y=ry, op_y=oy, rgb_diff=rd, op_diff=od, rgb_q1=rq, op_q1=oq)
+
+
 def main():
     torch.set_num_threads(os.cpu_count())
     ref_unet, ref_utils, ref_eval = ref_harness.import_reference()
@@ -276,6 +300,7 @@ def main():
     gen_psnr(ref_utils)
     gen_scores(ref_eval)
     gen_records()
+    gen_generator(ref_unet)
     print("all fixtures written to", GOLD)
 
 

@@ -185,12 +185,20 @@ def test_bridge_eval_mode_with_grad_matches_fused_path():
 
 
 def test_bridge_rejects_unsupported_shapes():
-    m = A.bridge(in_c=64).to(DEV)
-    with torch.no_grad(), pytest.raises(RuntimeError, match="128 pixels wide"):
-        m.eval()(torch.zeros(1, 64, 4, 130, device=DEV), torch.zeros(1, 64, 4, 130, device=DEV))
     m96 = A.bridge(in_c=96).to(DEV)
     with torch.no_grad(), pytest.raises(RuntimeError, match="multiples of 64"):
         m96.eval()(torch.zeros(1, 96, 8, 8, device=DEV), torch.zeros(1, 96, 8, 8, device=DEV))
+    # rows wider than 128 pixels: inference works (128-pixel segments), the weight-gradient kernel does not cover them
+    m = A.bridge(in_c=64).to(DEV)
+    z = torch.randn(1, 64, 4, 130, device=DEV)
+    with torch.no_grad():
+        x, _ = m.eval()(z, z)
+    ref, _, _ = O.amft_forward(z.cpu().double(), z.cpu().double(), {k: (v.double().cpu() if v.is_floating_point() else v.cpu())
+                                                                     for k, v in m.state_dict().items()})
+    assert_close(x.cpu(), ref, 1e-3, "bridge.w130")
+    with pytest.raises(RuntimeError, match="128 pixels wide"):
+        out, _ = m.train()(z.requires_grad_(True), z)
+        out.sum().backward()
 
 
 def _relu_masks_of_branch(u, w1, g1, b1, w2, g2, b2):

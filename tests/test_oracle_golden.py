@@ -117,3 +117,19 @@ def test_record_assembly():
         ogroups = np.array([op_fea[3 + 16 * i] for i in range((n_clips + 15) // 16)], np.float32)
         img2, fea2 = O.assemble_video_records(op_img[3:3 + n_clips], ogroups, clip_len=4, tail_copy=True)
         assert np.array_equal(fea2, op_fea) and np.array_equal(img2, op_img)
+
+
+@pytest.mark.parametrize("name", ["gen_64", "gen_96x160"])
+def test_generator_oracle_vs_reference_golden(name):
+    """The oracle's functional restatement of twostream.forward (unet.py:981-1007) against the live reference's outputs;
+    also pins synth.generator_params to the reference's state_dict layout (222 entries, loaded strict by gen_golden)."""
+    import torch
+    from ammcnet_aaai2021_b200 import synth, host_model
+    c, g = load_golden(name)
+    p = synth.generator_params(c["seed"])
+    assert set(p) == set(host_model.get_twostream().state_dict()) and len(p) == 222
+    rgb, op = synth.generator_inputs(c["seed"] + 500, c["b"], c["h"], c["w"])
+    with torch.no_grad():
+        ry, oy, (rd, od), (rq, oq) = O.twostream_forward(rgb, op, p, 2)
+    for a, key in ((ry, "rgb_y"), (oy, "op_y"), (rd, "rgb_diff"), (od, "op_diff"), (rq, "rgb_q1"), (oq, "op_q1")):
+        assert_close(a, g[key], 1e-5, key)
