@@ -123,8 +123,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ------------------------------------------------------------------ MMA issuer
+    {
+      // ------------------------------------------------------------------ MMA issuer: the whole warp runs the loop
+      // converged on warp-uniform values and one elected lane issues (see ptx::mma_f16_ss_warp); with short MMAs
+      // (N <= 128) a single-lane issue loop, not the tensor core, was the bound
       constexpr uint32_t idesc = ptx::umma_idesc(1, BLOCK_M, BLOCK_N);
       int s = 0; uint32_t ph = 0;
       int it = 0;
@@ -143,10 +145,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
           for (int k4 = 0; k4 < BLOCK_K / 16; ++k4) {
             // advance 16 elements (32 B) along K inside the swizzled row: +2 in the (>>4) address field
-            ptx::mma_f16_ss(d_tmem, adesc + 2 * k4, bdesc + 2 * k4, idesc, (kb | k4) != 0 ? 1u : 0u);
+            ptx::mma_f16_ss_warp(d_tmem, adesc + 2 * k4, bdesc + 2 * k4, idesc, (kb | k4) != 0 ? 1u : 0u);
           }
-          ptx::mma_commit(&empty_bar[s]);
-          if (kb == kb_total - 1) ptx::mma_commit(&tmem_full[acc]);
+          ptx::mma_commit_warp(&empty_bar[s]);
+          if (kb == kb_total - 1) ptx::mma_commit_warp(&tmem_full[acc]);
           if (++s == S::STAGES) { s = 0; ph ^= 1; }
         }
       }

@@ -73,6 +73,10 @@ class GeneratorEngine:
         self._key = None
         self._packs = None
 
+    def __getattr__(self, name):
+        # attribute passthrough (rgb, op, bridge, ...) so the engine can stand in for the module, e.g. in VideoScorer
+        return getattr(self.__dict__["model"], name)
+
     # -- weights ----------------------------------------------------------------------------------
     def _ensure_packed(self):
         tensors = list(self.model.parameters()) + list(self.model.buffers())

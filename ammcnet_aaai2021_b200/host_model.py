@@ -1,11 +1,16 @@
 """Host-side two-stream generator wiring (row a8 of SURVEY.md section 8): the caller of the hot path.
 
-The encoder / decoder convolutions are NOT part of the accelerated path -- they are stock torch.nn layers that run
-on cuDNN exactly as in the reference (north-star: "the conv encoder/decoder (left on cuDNN) ... unchanged").  This
-file only exists so the package can be exercised end to end without the reference tree (which is absent on the GPU
-box): it mirrors the layer names of reference Code/models/unet.py (`inconv/down/up` 23-59, `UNetMem_v7` 908-937,
-`twostream` 967-1007) so a reference checkpoint loads with strict=True, and places this package's memory modules
-and AMFT block in the starred region (unet.py:985-994).
+The encoder / decoder layers are stock torch.nn modules with the reference's names (reference Code/models/unet.py
+`inconv/down/up` 23-59, `UNetMem_v7` 908-937, `twostream` 967-1007), so a reference checkpoint loads with strict=True;
+this package's memory modules and AMFT block sit in the starred region (unet.py:985-994).  The file exists so the
+package can be exercised end to end without the reference tree (absent on the GPU box).
+
+Two execution routes for `twostream.forward`:
+* training / autograd: the torch.nn layers run on cuDNN exactly as in the reference (north-star: "the conv
+  encoder/decoder (left on cuDNN) ... unchanged"), the path's modules run this package's kernels;
+* eval + no_grad on a CUDA device (`engine = "tcgen05"`, the default): the whole forward runs on the tcgen05 conv engine
+  through `generator.GeneratorEngine`.  Set `model.engine = "cudnn"` to keep the layers on
+  cuDNN.
 """
 from __future__ import annotations
 
@@ -83,8 +88,16 @@ class twostream(nn.Module):
         self.rgb = UNetMem_v7(rgb_in_c, rgb_out_c, embed_dim, n_embed, k, layer_nums, features_root)
         self.op = UNetMem_v7(op_in_c, op_out_c, embed_dim, n_embed, k, layer_nums, features_root)
         self.bridge = bridge(in_c=512)
+        self.engine = "tcgen05"
+        object.__setattr__(self, "_engine_obj", None)
 
     def forward(self, rgb_x, op_x):
+        if (self.engine == "tcgen05" and not self.training and not torch.is_grad_enabled() and rgb_x.is_cuda
+                and rgb_x.shape[2] % 8 == 0 and rgb_x.shape[3] % 8 == 0):
+            if self._engine_obj is None:
+                from .generator import GeneratorEngine
+                object.__setattr__(self, "_engine_obj", GeneratorEngine(self))
+            return self._engine_obj(rgb_x, op_x)
         r1, r2, r3, r4 = self.rgb.encode(rgb_x)
         r4, rgb_diff, rgb_q = self.rgb.vq_down3(r4)
         o1, o2, o3, o4 = self.op.encode(op_x)

@@ -163,11 +163,16 @@ def test_generator_engine_matches_module_forward_and_oracle():
     ry, oy, (rd, od), _ = eng(rgb.to(DEV), op.to(DEV))
     prev = torch.backends.cudnn.allow_tf32
     torch.backends.cudnn.allow_tf32 = False
+    m.engine = "cudnn"                       # the module's own layers (stock torch.nn on cuDNN, fp32)
     try:
         with torch.no_grad():
             my, mo, (md, mod_), _ = m(rgb.to(DEV), op.to(DEV))
     finally:
         torch.backends.cudnn.allow_tf32 = prev
+        m.engine = "tcgen05"
+    with torch.no_grad():
+        dy = m(rgb.to(DEV), op.to(DEV))[0]   # default route of the module in eval + no_grad = the engine
+    assert torch.equal(dy, ry)
     assert_close(ry.cpu(), my.cpu(), 1e-3, "engine-vs-module.rgb")
     assert_close(oy.cpu(), mo.cpu(), 1e-3, "engine-vs-module.op")
     assert_close(rd.cpu(), md.cpu(), 1e-3, "engine-vs-module.diff")
@@ -190,6 +195,27 @@ def test_generator_engine_refuses_what_it_does_not_cover():
     with pytest.raises(RuntimeError, match="CUDA"):
         m.eval()
         eng(torch.zeros(1, 12, 64, 64), torch.zeros(1, 6, 64, 64))
+
+
+def test_generator_engine_under_cuda_graph_and_in_video_scorer():
+    _, m = _engine_model(45)
+    eng = A.GeneratorEngine(m)
+    rgb, op = (t.to(DEV) for t in synth.generator_inputs(6, 2, 64, 64))
+    eager = [t.clone() for t in (eng(rgb, op)[0], eng(rgb, op)[1])]
+    g = A.GraphedPath(eng, [rgb, op])
+    rgb2, op2 = (t.to(DEV) for t in synth.generator_inputs(7, 2, 64, 64))
+    g(rgb2, op2)
+    out = g(rgb, op)
+    assert torch.equal(out[0], eager[0]) and torch.equal(out[1], eager[1])
+    # the engine stands in for the module wherever a generator is expected
+    frames = torch.rand(9, 3, 64, 64, device=DEV) * 2 - 1
+    flows = torch.randn(8, 2, 64, 64, device=DEV) * 0.02
+    rec_e = A.VideoScorer(eng, batch=4).score_video(frames, flows)
+    m.engine = "cudnn"
+    rec_m = A.VideoScorer(m, batch=4).score_video(frames, flows)
+    for k in ("rgb_img_pred", "rgb_fea_comm", "op_fea_comm"):
+        assert_close(rec_e[k], rec_m[k], 1e-3, "scorer." + k)
+    F_.check_pipeline_watchdog()
 
 
 def test_generator_engine_tracks_weight_updates():

@@ -45,6 +45,9 @@ def timed(fn, label, extra=None):
 with torch.no_grad():
     eng3 = A.GeneratorEngine(m, precision=3)
     y3 = timed(lambda: eng3(rgb, op), "tcgen05 engine, split-bf16 x3 (fp32 parity)")
+    g3 = A.GraphedPath(eng3, [rgb, op])
+    timed(lambda: g3.replay(), "tcgen05 engine, split-bf16 x3, CUDA-graph replay")
+    m.engine = "cudnn"
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     yf = timed(lambda: m(rgb, op), "cuDNN fp32 U-Net + this package's path")
