@@ -105,7 +105,8 @@ template <int BLOCK_N>
 __global__ void __launch_bounds__(HALO_THREADS, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const HaloParams p) {
   constexpr int B_TILE = BLOCK_N * 128;
-  constexpr int NB = HALO_B_BYTES / B_TILE;
+  constexpr int NB = HALO_B_BYTES / B_TILE;       // resident mode: one slot per (plane, tap)
+  constexpr int NBS = NB / 3;                     // streaming mode: stages of three tiles
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_b = smem + HALO_A_STAGES * HALO_A_STAGE;
@@ -165,17 +166,20 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             ptx::tma_load_3d(smem_b + slot * B_TILE, &tmB, &b_full[slot], tap * p.Cin, 0, pl);
           }
       } else {
+        // streamed weights: one stage = the three taps of one kernel row of one plane (3 tiles, one barrier round trip)
         int s = 0; uint32_t ph = 0;
         for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x)
           for (int cc = 0; cc < ncc; ++cc)
             for (int pl = 0; pl < n_planes; ++pl)
-              for (int tap = 0; tap < 9; ++tap) {
+              for (int dyg = 0; dyg < 3; ++dyg) {
                 const int nb = (pl == 0 && n_planes == 2) ? 2 : 1;
                 for (int bp = 0; bp < nb; ++bp) {
                   ptx::mbar_wait(&b_empty[s], ph ^ 1, 62);
-                  ptx::mbar_expect_tx(&b_full[s], B_TILE);
-                  ptx::tma_load_3d(smem_b + s * B_TILE, &tmB, &b_full[s], tap * p.Cin + cc * 64, 0, bp);
-                  if (++s == NB) { s = 0; ph ^= 1; }
+                  ptx::mbar_expect_tx(&b_full[s], 3 * B_TILE);
+#pragma unroll
+                  for (int dx = 0; dx < 3; ++dx)
+                    ptx::tma_load_3d(smem_b + (s * 3 + dx) * B_TILE, &tmB, &b_full[s], (dyg * 3 + dx) * p.Cin + cc * 64, 0, bp);
+                  if (++s == NBS) { s = 0; ph ^= 1; }
                 }
               }
       }
@@ -225,20 +229,23 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 }
               }
             } else {
-#pragma unroll
-              for (int tap = 0; tap < 9; ++tap) {
-                const uint64_t ad = adesc0 + ((((tap / 3) * HALO_WP + tap % 3) * 128) >> 4);
+              for (int dyg = 0; dyg < 3; ++dyg) {
+                const uint64_t ad0 = adesc0 + (uint64_t)((dyg * HALO_WP * 128) >> 4);
                 for (int bp = 0; bp < (two ? 2 : 1); ++bp) {
                   ptx::mbar_wait(&b_full[sb], phb, 66);
                   ptx::tc_fence_after();
-                  const uint64_t bd = bdesc_ring + (uint64_t)((sb * B_TILE) >> 4);
+                  const uint64_t bd0 = bdesc_ring + (uint64_t)((sb * 3 * B_TILE) >> 4);
 #pragma unroll
-                  for (int k4 = 0; k4 < 4; ++k4) {
-                    ptx::mma_f16_ss_warp(d_tmem, ad + 2 * k4, bd + 2 * k4, idesc, accum);
-                    accum = 1;
+                  for (int dx = 0; dx < 3; ++dx) {
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4) {
+                      ptx::mma_f16_ss_warp(d_tmem, ad0 + ((dx * 128) >> 4) + 2 * k4, bd0 + ((dx * B_TILE) >> 4) + 2 * k4, idesc,
+                                           accum);
+                      accum = 1;
+                    }
                   }
                   ptx::mma_commit_warp(&b_empty[sb]);
-                  if (++sb == NB) { sb = 0; phb ^= 1; }
+                  if (++sb == NBS) { sb = 0; phb ^= 1; }
                 }
               }
             }
@@ -266,10 +273,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N;
 #pragma unroll 1
       for (int c32 = 0; c32 < BLOCK_N / 32; ++c32) {
+        const int cbase = c32 * 32;
+        if (!p.out_planes && cbase >= p.cout_valid) break;      // zero-padded output channels (outc): nothing to store
         uint32_t v[32];
         ptx::tmem_ld_32x32(taddr + c32 * 32, v);
         ptx::tmem_ld_wait();
-        const int cbase = c32 * 32;
         float y[32];
 #pragma unroll
         for (int g4 = 0; g4 < 8; ++g4) {
@@ -281,8 +289,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           y[4 * g4 + 3] = fmaf(__uint_as_float(v[4 * g4 + 3]), sc.w, sh.w);
         }
         if (p.act == 2) {                 // tanh is ~25 instructions per element: keep it off the common path
+          const int nt = p.out_planes ? 32 : p.cout_valid - cbase;     // and off the zero-padded channels
 #pragma unroll
-          for (int j = 0; j < 32; ++j) y[j] = tanhf(y[j]);
+          for (int j = 0; j < 32; ++j)
+            if (j < nt) y[j] = tanhf(y[j]);
         } else if (p.act == 1) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j], 0.f);
