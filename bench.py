@@ -438,9 +438,52 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
+        if world == 1 and not args.no_generator:
+            line["generator"] = generator_leg(dev)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def generator_leg(dev, batch=16, steps=5):
+    """SURVEY section 8(f) rank 1, reported beside the path's metric (never part of `value`): eval-mode forward of the
+    whole twostream generator on 256x256 frames, tcgen05 conv engine vs the same module with its U-Net layers on cuDNN."""
+    import ammcnet_aaai2021_b200 as A
+    from ammcnet_aaai2021_b200 import synth
+    m = A.get_twostream()
+    m.load_state_dict(synth.generator_params(3))
+    m = m.to(dev).eval()
+    rgb, op = (t.to(dev) for t in synth.generator_inputs(9, batch, 256, 256))
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return batch * steps / (e0.elapsed_time(e1) * 1e-3)
+
+    with torch.no_grad():
+        eng = A.GeneratorEngine(m)
+        graph = A.GraphedPath(eng, [rgb, op])
+        ours = timed(graph.replay)
+        m.engine = "cudnn"
+        tf32 = torch.backends.cudnn.allow_tf32
+        torch.backends.cudnn.allow_tf32 = True
+        cudnn_tf32 = timed(lambda: m(rgb, op))
+        torch.backends.cudnn.allow_tf32 = False
+        cudnn_fp32 = timed(lambda: m(rgb, op))
+        torch.backends.cudnn.allow_tf32 = tf32
+    del graph, eng, m
+    torch.cuda.empty_cache()
+    return {"value": ours, "unit": "frames/s", "workload": "whole twostream generator (unet.py:981-1007), eval, 256x256 "
+            "frames, batch %d, split-bf16 x3 (fp32 parity), CUDA-graph replay, inputs resident" % batch,
+            "algorithmic_tflops": ours * 187.4e9 / 1e12,
+            "same_module_unet_on_cudnn_tf32": cudnn_tf32, "same_module_unet_on_cudnn_fp32": cudnn_fp32}
 
 
 def main():
@@ -452,6 +495,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--precision", type=int, default=3, choices=[1, 3])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-generator", action="store_true", help="skip the whole-generator leg (SURVEY 8(f) rank 1)")
     ap.add_argument("--items", type=int, default=256, help="memory bank size M (BASELINE configs[2] sweeps 256..2000)")
     ap.add_argument("--no-graph", action="store_true", help="issue the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--pair-unfused", action="store_true", help="A/B: CTA-pair kernel streaming the K loop three times")
