@@ -12,9 +12,10 @@ from .patch import patch_reference, unpatch_reference, swap_modules
 from .host_model import twostream, UNetMem_v7, get_twostream
 from .graphs import GraphedPath
 from .generator import GeneratorEngine
+from .preprocess import preprocess_frames, preprocess_flow, load_video
 
 __all__ = [
     "Quantize_topk", "enc_quan_dec_topk", "enc_quan_dec_res_topk", "bridge", "double_conv", "psnr_error",
     "psnr_per_frame", "VideoScorer", "assemble_video_records", "score_reduce", "evaluate", "LAM_MAP",
-    "patch_reference", "unpatch_reference", "swap_modules", "twostream", "UNetMem_v7", "get_twostream", "GraphedPath", "GeneratorEngine",
+    "patch_reference", "unpatch_reference", "swap_modules", "twostream", "UNetMem_v7", "get_twostream", "GraphedPath", "GeneratorEngine", "preprocess_frames", "preprocess_flow", "load_video",
 ]

@@ -71,6 +71,8 @@ SIGNATURES = {
     "ammc_pack_conv_weights_dgrad": (I, [P, P, I, I, P]),
     "ammc_conv3x3_wgrad": (I, [P, P, P, I, I, I, I, I, I, P]),
     "ammc_bn_fold": (I, [P] * 4 + [F] + [P, P, I, P]),
+    "ammc_preprocess_frames_u8": (I, [P, P, I, I, I, I, I, P]),
+    "ammc_preprocess_flow": (I, [P, P, I, I, I, I, I, P]),
     "ammc_psnr_workspace_bytes": (Z, [I, L]),
     "ammc_psnr_batch": (I, [P, P, P, P, Z, I, L, P]),
     "ammc_score_workspace_bytes": (Z, [L, I]),

@@ -147,6 +147,26 @@ def generator_inputs(seed: int, b: int, h: int = 256, w: int = 256, in_channel=(
     return rgb, op
 
 
+# source (h, w) -> target (W, H) cases of the frame / flow preprocessing fixtures: the three datasets' native frame
+# sizes plus ragged and degenerate ones (tests/golden/preprocess.npz, oracle/gen_golden.py)
+PREPROCESS_CASES = {
+    "ped2": ((240, 360), (256, 256)), "avenue": ((360, 640), (256, 256)), "shanghaitech": ((480, 856), (256, 256)),
+    "same": ((256, 256), (256, 256)), "up_small": ((37, 53), (64, 48)), "down_odd": ((97, 131), (40, 24)),
+    "one_row": ((1, 9), (16, 8)), "one_px": ((1, 1), (8, 8)),
+}
+
+
+def preprocess_inputs(seed: int = 20200525):
+    """Yields (name, bgr uint8 [h,w,3], flow float32 [h,w,2], (W, H)) for every PREPROCESS_CASES entry, in order, from
+    one numpy Generator stream (decoded frames as TurboJPEG/cv2.imread return them; .flo payloads)."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    for name, ((h0, w0), size) in PREPROCESS_CASES.items():
+        bgr = rng.integers(0, 256, (h0, w0, 3), dtype=np.uint8)
+        flow = (rng.standard_normal((h0, w0, 2)) * 3).astype(np.float32)
+        yield name, bgr, flow, size
+
+
 def features(seed: int, b: int, C: int = 512, h: int = 32, w: int = 32) -> torch.Tensor:
     """ReLU(N(0,1)) bottleneck features, NCHW fp32."""
     return torch.relu(torch.randn((b, C, h, w), generator=_gen(seed), dtype=torch.float32))

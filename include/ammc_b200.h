@@ -276,6 +276,16 @@ size_t ammc_auc_workspace_bytes(int64_t T);
 int ammc_roc_auc(const float* scores, const int8_t* labels, int pos_label, double* auc, void* workspace,
                  size_t workspace_bytes, int64_t T, void* stream);
 
+/* ---- frame / flow preprocessing in front of the generator --------------------------------
+ * Replaces the per-frame CPU work of Code/dataset/two_stream_dataset.py:72-99 after decoding (cv2.cvtColor + cv2.resize +
+ * ToTensor + Normalize, resp. cv2.resize + the flow scaling), bit-exactly:
+ *   ammc_preprocess_frames_u8  decoded BGR uint8 [n,h0,w0,3] -> fp32 RGB [n,3,H,W] in (-1,1)
+ *   ammc_preprocess_flow       .flo payload fp32 [n,h0,w0,2]  -> fp32 [n,2,H,W]; ch0 = resized u / H, ch1 = ch0 / W (the
+ *                              loader derives channel 1 from channel 0, two_stream_dataset.py:94-95)
+ * The host uploads uint8 frames (a quarter of the bytes of the fp32 tensors). */
+int ammc_preprocess_frames_u8(const uint8_t* frames_bgr, float* out, int n, int h0, int w0, int H, int W, void* stream);
+int ammc_preprocess_flow(const float* flow, float* out, int n, int h0, int w0, int H, int W, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

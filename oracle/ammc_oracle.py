@@ -292,6 +292,85 @@ def twostream_forward(rgb_x, op_x, p: Dict[str, torch.Tensor], k: int):
             (mem["rgb"]["quantize"], mem["op"]["quantize"]))
 
 
+# --------------------------------------------------------------------------------------------------
+# frame / flow preprocessing in front of the generator
+# --------------------------------------------------------------------------------------------------
+# The reference resizes with cv2.resize (default INTER_LINEAR; opencv-python==4.1.1.26, Code/environment.yaml:78), a
+# third-party dependency that is not under /root/reference.  Its published algorithm (modules/imgproc/src/resize.cpp,
+# resizeGeneric_ / HResizeLinear / VResizeLinear) is restated here and pinned bit-exactly against the cv2 of this image
+# and against the reference's own _load_frame / _load_op by oracle/gen_golden.py.
+def _linear_taps(src: int, dst: int, clamp_weights: bool):
+    """Source indices and float32 weights of cv2's bilinear resize along one axis.
+    scale = 1 / (dst / src) in double; f = float((d + 0.5) * scale - 0.5); s = floor(f); f -= s.  Along x the weights are
+    clamped at the borders (f = 0), along y only the row indices are (resize.cpp: xofs/alpha vs. yofs/beta + clip)."""
+    scale = 1.0 / (float(dst) / float(src))
+    i0 = np.empty(dst, np.int64)
+    i1 = np.empty(dst, np.int64)
+    wgt = np.empty((dst, 2), np.float32)
+    for d in range(dst):
+        f = np.float32((d + 0.5) * scale - 0.5)
+        s = int(np.floor(f))
+        f = np.float32(f - np.float32(s))
+        if clamp_weights:
+            if s < 0:
+                f, s = np.float32(0), 0
+            if s >= src - 1:
+                f, s = np.float32(0), src - 1
+        wgt[d, 0] = np.float32(1.0) - f
+        wgt[d, 1] = f
+        i0[d] = min(max(s, 0), src - 1)
+        i1[d] = min(max(s + 1, 0), src - 1)
+    return i0, i1, wgt
+
+
+def resize_linear_u8(img: np.ndarray, width: int, height: int) -> np.ndarray:
+    """cv2.resize(img, (width, height)) for uint8 [h, w, c]: 11-bit fixed-point weights (cvRound(w * 2048)), integer
+    horizontal pass, vertical pass ((b0*(S0>>4))>>16) + ((b1*(S1>>4))>>16) + 2) >> 2."""
+    h0, w0 = img.shape[:2]
+    x0, x1, ax = _linear_taps(w0, width, True)
+    y0, y1, ay = _linear_taps(h0, height, False)
+    iax = np.rint(ax * np.float32(2048)).astype(np.int64)
+    iay = np.rint(ay * np.float32(2048)).astype(np.int64)
+    src = img.astype(np.int64).reshape(h0, w0, -1)
+    rows = src[:, x0, :] * iax[:, 0][None, :, None] + src[:, x1, :] * iax[:, 1][None, :, None]
+    s0, s1 = rows[y0], rows[y1]
+    b0, b1 = iay[:, 0][:, None, None], iay[:, 1][:, None, None]
+    out = (((b0 * (s0 >> 4)) >> 16) + ((b1 * (s1 >> 4)) >> 16) + 2) >> 2
+    return np.clip(out, 0, 255).astype(np.uint8).reshape((height, width) + img.shape[2:])
+
+
+def resize_linear_f32(img: np.ndarray, width: int, height: int) -> np.ndarray:
+    """cv2.resize for float32 [h, w, c]: float32 weights, separate multiply and add (no FMA), horizontal then vertical."""
+    h0, w0 = img.shape[:2]
+    x0, x1, ax = _linear_taps(w0, width, True)
+    y0, y1, ay = _linear_taps(h0, height, False)
+    src = img.astype(np.float32).reshape(h0, w0, -1)
+    rows = (src[:, x0, :] * ax[:, 0][None, :, None]).astype(np.float32) + (src[:, x1, :] * ax[:, 1][None, :, None]).astype(np.float32)
+    s0, s1 = rows[y0], rows[y1]
+    out = (s0 * ay[:, 0][:, None, None]).astype(np.float32) + (s1 * ay[:, 1][:, None, None]).astype(np.float32)
+    return out.astype(np.float32).reshape((height, width) + img.shape[2:])
+
+
+def preprocess_frame(bgr_u8: np.ndarray, size=(256, 256)) -> np.ndarray:
+    """_load_frame with the test transform (Code/dataset/two_stream_dataset.py:72-84, 501-505): BGR->RGB, resize,
+    ToTensor (uint8 HWC -> float32 CHW / 255), Normalize(0.5, 0.5).  Returns float32 [3, H, W]."""
+    width, height = size
+    rgb = resize_linear_u8(bgr_u8[:, :, ::-1], width, height)
+    x = rgb.astype(np.float32) / np.float32(255)
+    x = (x - np.float32(0.5)) / np.float32(0.5)
+    return np.ascontiguousarray(x.transpose(2, 0, 1))
+
+
+def preprocess_flow(flow: np.ndarray, size=(256, 256)) -> np.ndarray:
+    """_load_op (Code/dataset/two_stream_dataset.py:86-99): resize, ch0 = ch0 * 1.0 / H, ch1 = (scaled ch0) / W --
+    the loader's quirk: channel 1 is derived from channel 0, the resized v component is discarded.  float32 [2, H, W]."""
+    width, height = size
+    r = resize_linear_f32(flow.astype(np.float32), width, height)
+    c0 = (r[:, :, 0] * np.float32(1.0)) / np.float32(height)
+    c1 = c0 / np.float32(width)
+    return np.stack([c0, c1]).astype(np.float32)
+
+
 def path_forward(x_rgb, x_op, gen, gt, params: Dict[str, torch.Tensor], k: int):
     """The starred region of twostream.forward (Code/models/unet.py:985-994) followed by the per-frame rgb
     PSNR of test_helper.py:445-452.  `params` uses the reference state_dict key names

@@ -292,6 +292,44 @@ def gen_generator(ref_unet):
         _save(name, dict(kind="generator", **c), rgb_y=ry, op_y=oy, rgb_diff=rd, op_diff=od, rgb_q1=rq, op_q1=oq)
 
 
+def gen_preprocess():
+    """Frame / flow loaders of the reference (two_stream_dataset._load_frame / _load_op) on synthetic decoded inputs.
+    The JPEG decoder is replaced by the synthetic BGR array (decoding is not part of the restated path); .flo files are
+    written to a temp dir and read back by the reference's own readFlow."""
+    import hashlib
+    import tempfile
+    import torchvision.transforms as T
+    import cv2
+    ref_harness.import_reference()            # installs the stub modules and puts the reference on sys.path
+    import Code.dataset.two_stream_dataset as ds
+    tf_rgb = T.Compose([T.ToTensor(), T.Normalize([0.5, 0.5, 0.5], [0.5, 0.5, 0.5])])      # two_stream_dataset.py:501-505
+    out, meta = {}, {}
+    tmp = tempfile.mkdtemp()
+    for name, bgr, flow, (W, H) in synth.preprocess_inputs(20200525):
+        h0, w0 = bgr.shape[:2]
+        ds.img_decode = lambda path, _a=bgr: _a.copy()
+        ref_rgb = ds._load_frame("synthetic.jpg", img_size=(W, H), transform=tf_rgb).numpy()
+        flo = os.path.join(tmp, name + ".flo")
+        with open(flo, "wb") as f:
+            np.array([202021.25], np.float32).tofile(f)
+            np.array([w0, h0], np.int32).tofile(f)
+            flow.tofile(f)
+        ref_op = ds._load_op(flo, img_size=(W, H)).numpy()
+        mine_rgb, mine_op = O.preprocess_frame(bgr, (W, H)), O.preprocess_flow(flow, (W, H))
+        assert np.array_equal(mine_rgb, ref_rgb), f"oracle != reference _load_frame for {name}"
+        assert np.array_equal(mine_op, ref_op), f"oracle != reference _load_op for {name}"
+        assert np.array_equal(O.resize_linear_u8(bgr, W, H), cv2.resize(bgr, (W, H)))
+        assert np.array_equal(O.resize_linear_f32(flow, W, H), cv2.resize(flow, (W, H)))
+        meta[name] = dict(src=[h0, w0], dst=[W, H])
+        if h0 * w0 <= 20000:                      # small cases: the arrays themselves
+            out[name + "_bgr"], out[name + "_flow"] = bgr, flow
+            out[name + "_rgb_out"], out[name + "_op_out"] = ref_rgb, ref_op
+        else:                                     # dataset sizes: inputs come from the seed, outputs are pinned by digest
+            meta[name]["rgb_sha256"] = hashlib.sha256(ref_rgb.tobytes()).hexdigest()
+            meta[name]["op_sha256"] = hashlib.sha256(ref_op.tobytes()).hexdigest()
+    _save("preprocess", dict(kind="preprocess", seed=20200525, cases=meta, cv2=cv2.__version__), **out)
+
+
 def main():
     torch.set_num_threads(os.cpu_count())
     ref_unet, ref_utils, ref_eval = ref_harness.import_reference()
@@ -301,6 +339,7 @@ def main():
     gen_scores(ref_eval)
     gen_records()
     gen_generator(ref_unet)
+    gen_preprocess()
     print("all fixtures written to", GOLD)
 
 

@@ -133,3 +133,25 @@ def test_generator_oracle_vs_reference_golden(name):
         ry, oy, (rd, od), (rq, oq) = O.twostream_forward(rgb, op, p, 2)
     for a, key in ((ry, "rgb_y"), (oy, "op_y"), (rd, "rgb_diff"), (od, "op_diff"), (rq, "rgb_q1"), (oq, "op_q1")):
         assert_close(a, g[key], 1e-5, key)
+
+
+def test_preprocess_oracle_vs_reference_loaders():
+    """cv2.resize restatement + the loaders' arithmetic (two_stream_dataset.py:72-99) against what the reference's own
+    _load_frame / _load_op returned for the same decoded inputs: bit-exact, arrays for small cases, digests for the
+    datasets' native sizes."""
+    import hashlib
+    c, g = load_golden("preprocess")
+    n = 0
+    for name, bgr, flow, size in synth.preprocess_inputs(c["seed"]):
+        rgb, op = O.preprocess_frame(bgr, size), O.preprocess_flow(flow, size)
+        meta = c["cases"][name]
+        if "rgb_sha256" in meta:
+            assert hashlib.sha256(rgb.tobytes()).hexdigest() == meta["rgb_sha256"], name
+            assert hashlib.sha256(op.tobytes()).hexdigest() == meta["op_sha256"], name
+        else:
+            assert np.array_equal(bgr, g[name + "_bgr"]) and np.array_equal(flow, g[name + "_flow"]), name
+            assert np.array_equal(rgb, g[name + "_rgb_out"]), name
+            assert np.array_equal(op, g[name + "_op_out"]), name
+        assert rgb.dtype == np.float32 and rgb.shape == (3, size[1], size[0]) and op.shape == (2, size[1], size[0])
+        n += 1
+    assert n == len(synth.PREPROCESS_CASES) == 8
