@@ -2,5 +2,5 @@
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 python -m ammcnet_aaai2021_b200.build 2>&1 | tail -1
-timeout 900 python -m pytest tests/test_gpu_preprocess.py -m gpu -x -q 2>&1 | tail -12
-timeout 300 python tools/preprocess_bench.py 2>&1 | tee gpurun_out/preprocess_bench.jsonl | cut -c1-220
+timeout 900 python tools/score_dataset.py --dataset ped2 --native --batch 64 2>&1 | tail -1 | tee gpurun_out/score_dataset_ped2_native_n1.json | cut -c1-600
+timeout 900 python tools/score_dataset.py --dataset ped2 --native --batch 64 --graph 2>&1 | tail -1 | tee gpurun_out/score_dataset_ped2_native_graph_n1.json | cut -c1-600
