@@ -60,6 +60,45 @@ def _workspace(nbytes: int, device: torch.device) -> torch.Tensor:
     return ws
 
 
+_side_streams: Dict[Tuple[int, int], "torch.cuda.Stream"] = {}
+
+
+def concurrently(*fns):
+    """Run independent pieces of the path on separate CUDA streams and join them on the current stream.
+
+    The appearance and the motion memory module do not depend on each other until the AMFT block (reference
+    unet.py:985-994), and neither does the PSNR of the previous prediction; their many short kernels (bank preparation,
+    per-frame reductions) and the tails of the large ones overlap when issued on different streams.  fns[0] runs on the
+    current stream, the others on per-device side streams; works eagerly and under CUDA-graph capture (fork/join).
+    Returns the list of results."""
+    cur = torch.cuda.current_stream()
+    dev = cur.device
+    results = [None] * len(fns)
+    sides = []
+    for i in range(1, len(fns)):
+        key = (dev.index, i)
+        st = _side_streams.get(key)
+        if st is None:
+            st = torch.cuda.Stream(device=dev)
+            _side_streams[key] = st
+        st.wait_stream(cur)
+        with torch.cuda.stream(st):
+            results[i] = fns[i]()
+        sides.append(st)
+    results[0] = fns[0]()
+    for st in sides:
+        cur.wait_stream(st)
+    if not torch.cuda.is_current_stream_capturing():     # a captured graph owns its memory pool: nothing is ever reused
+        for r in results[1:]:                             # tensors produced on a side stream are consumed on this one
+            for t in (r if isinstance(r, (tuple, list)) else (r,)):
+                if isinstance(t, torch.Tensor):
+                    t.record_stream(cur)
+                    planes = getattr(t, "_ammc_planes", None)
+                    if planes is not None:
+                        planes[0].record_stream(cur)
+    return results
+
+
 # launch counter: bench.py reports how many of OUR kernels ran in the timed region
 LAUNCHES = {"count": 0}
 

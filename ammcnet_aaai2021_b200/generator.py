@@ -152,15 +152,17 @@ class GeneratorEngine:
                                "both streams, got %s / %s" % (tuple(rgb_x.shape), tuple(op_x.shape)))
         self._ensure_packed()
         pr, po = self._packs["rgb"], self._packs["op"]
-        cats_r, r4 = self._encode(pr, rgb_x)
-        r4, rgb_diff, rgb_q = m.rgb.vq_down3(r4)
-        cats_o, o4 = self._encode(po, op_x)
-        o4, op_diff, op_q = m.op.vq_down3(o4)
+        def stream_front(pk, unet, x):                         # encoder + memory module of one stream
+            cats, x4 = self._encode(pk, x)
+            return (cats,) + tuple(unet.vq_down3(x4))
+
+        # the appearance and motion streams are independent up to the AMFT block and again after it (unet.py:981-1003)
+        (cats_r, r4, rgb_diff, rgb_q), (cats_o, o4, op_diff, op_q) = F_.concurrently(
+            lambda: stream_front(pr, m.rgb, rgb_x), lambda: stream_front(po, m.op, op_x))
         px, py = F_.planes_of(r4), F_.planes_of(o4)
         px = F_.pack_nhwc(r4) if px is None else px
         py = F_.pack_nhwc(o4) if py is None else py
         r4p = self._amft_branch(m.bridge.O2F, py, r4)          # x' = zx + O2F(zy)   (unet.py:963)
         o4p = self._amft_branch(m.bridge.F20, px, o4)          # y' = zy + F20(zx)   (unet.py:964)
-        rgb_y = self._decode(pr, r4p, cats_r)
-        op_y = self._decode(po, o4p, cats_o)
+        rgb_y, op_y = F_.concurrently(lambda: self._decode(pr, r4p, cats_r), lambda: self._decode(po, o4p, cats_o))
         return rgb_y, op_y, (rgb_diff, op_diff), (rgb_q, op_q)

@@ -236,10 +236,12 @@ def run_ours(args):
 
     def local_step(xr, xo, gen, gt):
         with torch.no_grad():
-            o_r, d_r, _ = mem["rgb"](xr)
-            o_o, d_o, _ = mem["op"](xo)
+            if args.no_streams:
+                (o_r, d_r, _), (o_o, d_o, _), ps = mem["rgb"](xr), mem["op"](xo), F_.psnr_per_frame(gen, gt)
+            else:       # the two memory modules and the PSNR are independent until the AMFT block: three streams
+                (o_r, d_r, _), (o_o, d_o, _), ps = F_.concurrently(lambda: mem["rgb"](xr), lambda: mem["op"](xo),
+                                                                   lambda: F_.psnr_per_frame(gen, gt))
             yr, yo = amft(o_r, o_o)
-            ps = F_.psnr_per_frame(gen, gt)
             commit = mem["rgb"].quan.quantize.last_sse_frame
             scores = torch.stack([ps, commit])                    # per-frame (psnr, commit partial)
         return yr, yo, scores
@@ -499,6 +501,7 @@ def main():
     ap.add_argument("--items", type=int, default=256, help="memory bank size M (BASELINE configs[2] sweeps 256..2000)")
     ap.add_argument("--no-graph", action="store_true", help="issue the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--pair-unfused", action="store_true", help="A/B: CTA-pair kernel streaming the K loop three times")
+    ap.add_argument("--no-streams", action="store_true", help="A/B: issue the two memory modules and the PSNR on one stream")
     ap.add_argument("--no-pair", action="store_true", help="A/B: single-CTA conv kernel instead of the CTA-pair one")
     args = ap.parse_args()
     global M
