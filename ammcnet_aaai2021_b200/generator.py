@@ -75,7 +75,10 @@ class GeneratorEngine:
 
     def __getattr__(self, name):
         # attribute passthrough (rgb, op, bridge, ...) so the engine can stand in for the module, e.g. in VideoScorer
-        return getattr(self.__dict__["model"], name)
+        model = self.__dict__.get("model")
+        if model is None or name.startswith("__"):
+            raise AttributeError(name)
+        return getattr(model, name)
 
     # -- weights ----------------------------------------------------------------------------------
     def _ensure_packed(self):
