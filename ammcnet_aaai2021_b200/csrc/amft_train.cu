@@ -522,6 +522,14 @@ extern "C" int ammc_bn_backward(const float* g, const float* y, const float* sca
   return launch_apply(a, b, C, h, w, st);
 }
 
+namespace ammc {
+int pack_planes_f32(const float* x, void* xp, long long n, cudaStream_t st) {
+  pack_planes_kernel<<<ceil_div(n, 256), 256, 0, st>>>(x, (__nv_bfloat16*)xp, n);
+  AMMC_LAUNCH_CHECK("pack_planes_kernel");
+  return 0;
+}
+}  // namespace ammc
+
 extern "C" int ammc_pack_planes(const float* x, void* xp, int64_t n, void* stream) {
   AMMC_REQUIRE(x && xp && n > 0, "bad argument");
   pack_planes_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)xp, n);

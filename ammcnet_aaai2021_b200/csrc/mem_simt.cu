@@ -491,6 +491,63 @@ __global__ void __launch_bounds__(256) genc_w_kernel(const float* __restrict__ g
   }
 }
 
+// Same reduction with a per-block private table in shared memory: a block owns 32 channels and PRIV_PX pixels, adds every
+// (pixel, j) row into table[j*M + idx][32] with shared-memory atomics (lane = channel = bank: conflict-free) and flushes the
+// table to G once -- 67 M contended global atomics become N*k*C / PRIV_PX * ... ~ 8 M spread ones (523 -> ~60 us at b=64).
+constexpr int PRIV_PX = 2048;
+template <int K>
+__global__ void __launch_bounds__(256) gdec_scatter_priv_kernel(const float* __restrict__ g_out,
+                                                                 const int64_t* __restrict__ idx, float* __restrict__ G,
+                                                                 float* __restrict__ g_dec_b, int N, int HW, int C, int M) {
+  extern __shared__ float table[];             // [K*M][32]
+  __shared__ float tile[32][33];               // [ch][px]
+  __shared__ int idx_s[32][K];
+  const int lane = threadIdx.x & 31, wv = threadIdx.x >> 5;
+  const int c0 = blockIdx.y * 32;
+  const int n_beg = blockIdx.x * PRIV_PX, n_end = min(N, n_beg + PRIV_PX);
+  for (int e = threadIdx.x; e < K * M * 32; e += 256) table[e] = 0.f;
+  float bsum[4] = {0.f, 0.f, 0.f, 0.f};
+  __syncthreads();
+  for (int n0 = n_beg; n0 < n_end; n0 += 32) {
+    for (int e = threadIdx.x; e < 32 * K; e += 256) {
+      const int p = e / K, j = e % K;
+      idx_s[p][j] = (n0 + p < n_end) ? (int)idx[(size_t)(n0 + p) * K + j] : 0;
+    }
+    const int n = n0 + lane;
+    const bool nvalid = n < n_end;
+    const int img = nvalid ? n / HW : 0, pp = nvalid ? n % HW : 0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int ch = wv * 4 + r, c = c0 + ch;
+      const float v = (nvalid && c < C) ? g_out[((size_t)img * C + c) * HW + pp] : 0.f;
+      tile[ch][lane] = v;
+      bsum[r] += v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int p = wv * 4 + r;
+      if (n0 + p < n_end) {
+        const float v = tile[lane][p];
+#pragma unroll
+        for (int j = 0; j < K; ++j) atomicAdd(&table[(j * M + idx_s[p][j]) * 32 + lane], v);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const float s = warp_sum(bsum[r]);
+    const int c = c0 + wv * 4 + r;
+    if (lane == 0 && c < C) atomicAdd(&g_dec_b[c], s);
+  }
+  if (c0 + lane < C)
+    for (int row = wv; row < K * M; row += 8) {
+      const float v = table[row * 32 + lane];
+      if (v != 0.f) atomicAdd(&G[(size_t)row * C + c0 + lane], v);
+    }
+}
+
 // G[j][idx_j(n)][c] += g_out[img,c,p] ;  g_dec_b[c] += sum_n g_out
 template <int K>
 __global__ void __launch_bounds__(256) gdec_scatter_kernel(const float* __restrict__ g_out,
@@ -593,6 +650,7 @@ int run_enc_tc(const float* x, const float* enc_w, const float* enc_b, float* z,
 
 // amft_conv.cu
 bool conv_shape_supported(int b, int Cin, int Cout, int h, int w);
+int pack_planes_f32(const float* x, void* xp, long long n, cudaStream_t st);
 int pack_weights_1x1(const float* w, void* wp, int Cout, int Cin, cudaStream_t st);
 int conv_igemm(const void* xp, const void* wp, const float* scale, const float* shift, void* out_planes,
                float* out_nchw, const float* res_nchw, int b, int Cin, int Cout, int h, int w, int ntaps, int precision,
@@ -874,7 +932,10 @@ extern "C" int ammc_ema_update(float* embed, float* cluster_size, float* embed_a
 
 extern "C" size_t ammc_mem_bwd_workspace_bytes(int b, int h, int w, int C, int D, int M, int k) {
   int64_t N = (int64_t)b * h * w;
-  return align_up((size_t)M * D * 4, 256) + align_up((size_t)N * D * 4, 256) + align_up((size_t)k * M * C * 4, 256);
+  // + tensor-core gx: bf16 hi/lo planes of g_z, packed enc_w^T, unit scale / zero shift vectors
+  return align_up((size_t)M * D * 4, 256) + align_up((size_t)N * D * 4, 256) + align_up((size_t)k * M * C * 4, 256) +
+         align_up((size_t)2 * N * D * 2, 256) + align_up((size_t)2 * C * D * 2, 256) + 2 * align_up((size_t)C * 4, 256) +
+         align_up((size_t)C * D * 4, 256);
 }
 
 extern "C" int ammc_mem_bwd(const float* x, const float* enc_w, const float* embed, const int64_t* idx,
@@ -903,8 +964,28 @@ extern "C" int ammc_mem_bwd(const float* x, const float* enc_w, const float* emb
   gz_kernel<<<ceil_div(N, 64), 256, (size_t)D * 4, st>>>(z, bank_t, idx, g_diff, g_q1, gz, g_enc_b, (int)N, D, k,
                                                         1.0 / ((double)N * (double)D));
   AMMC_LAUNCH_CHECK("gz_kernel");
-  gx_kernel<<<dim3(ceil_div(N, 64), ceil_div(C, 64)), 256, 0, st>>>(gz, enc_w, g_out, gx, (int)N, HW, C, D, residual);
-  AMMC_LAUNCH_CHECK("gx_kernel");
+  if (g_dec_mode != 1 && D % 64 == 0 && C % 64 == 0) {        // ammc_set_dec_mode(1) keeps every 1x1 GEMM on CUDA cores
+    // gx = (residual ? g_out : 0) + g_z . enc_w  as a split-bf16 x3 1x1 GEMM on tcgen05 (the conv engine with K = D):
+    // operands = NHWC planes of g_z and enc_w^T [C][D]; the residual add and the NCHW store are its epilogue
+    __nv_bfloat16* gzp = ws.take<__nv_bfloat16>((size_t)2 * N * D);
+    __nv_bfloat16* wtp = ws.take<__nv_bfloat16>((size_t)2 * C * D);
+    float* ones = ws.take<float>(C);
+    float* zeros = ws.take<float>(C);
+    float* wt = ws.take<float>((size_t)C * D);
+    if (!ws.ok()) return fail(AMMC_EWORKSPACE, "workspace too small");
+    if (int rc = pack_planes_f32(gz, gzp, (long long)N * D, st)) return rc;
+    bank_transpose_kernel<<<dim3(ceil_div(C, 32), ceil_div(D, 32)), dim3(32, 8), 0, st>>>(enc_w, wt, D, C);   // [D][C] -> [C][D]
+    AMMC_LAUNCH_CHECK("bank_transpose_kernel");
+    if (int rc = pack_weights_1x1(wt, wtp, C, D, st)) return rc;
+    fill_kernel<<<ceil_div(C, 256), 256, 0, st>>>(ones, 1.f, C);
+    fill_kernel<<<ceil_div(C, 256), 256, 0, st>>>(zeros, 0.f, C);
+    AMMC_LAUNCH_CHECK("fill_kernel");
+    if (int rc = conv_igemm(gzp, wtp, ones, zeros, nullptr, gx, residual ? g_out : nullptr, b, D, C, h, w, 1, 3, 0, st))
+      return rc;
+  } else {
+    gx_kernel<<<dim3(ceil_div(N, 64), ceil_div(C, 64)), 256, 0, st>>>(gz, enc_w, g_out, gx, (int)N, HW, C, D, residual);
+    AMMC_LAUNCH_CHECK("gx_kernel");
+  }
   {
     int tiles = ceil_div(D, 64) * ceil_div(C, 64);
     int splits = max(1, min((int)ceil_div(N, 256), ceil_div(4 * num_sms(), tiles)));
@@ -913,7 +994,23 @@ extern "C" int ammc_mem_bwd(const float* x, const float* enc_w, const float* emb
     genc_w_kernel<<<dim3(ceil_div(D, 64), ceil_div(C, 64), splits), 256, 0, st>>>(gz, x, g_enc_w, (int)N, HW, C, D, per);
     AMMC_LAUNCH_CHECK("genc_w_kernel");
   }
-  {
+  const size_t priv_bytes = (size_t)k * M * 32 * sizeof(float);
+  if (priv_bytes <= 160 * 1024) {
+    // private shared-memory tables (shipped shapes: k*M = 512 rows -> 64 KB)
+    dim3 grid(ceil_div(N, PRIV_PX), ceil_div(C, 32));
+    switch (k) {
+#define AMMC_SP_CASE(KK)                                                                                              \
+  case KK:                                                                                                            \
+    AMMC_CUDA_CHECK(cudaFuncSetAttribute(gdec_scatter_priv_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                         160 * 1024));                                                                \
+    gdec_scatter_priv_kernel<KK><<<grid, 256, priv_bytes, st>>>(g_out, idx, G, g_dec_b, (int)N, HW, C, M);            \
+    break;
+      AMMC_SP_CASE(1) AMMC_SP_CASE(2) AMMC_SP_CASE(3) AMMC_SP_CASE(4)
+      AMMC_SP_CASE(5) AMMC_SP_CASE(6) AMMC_SP_CASE(7) AMMC_SP_CASE(8)
+#undef AMMC_SP_CASE
+    }
+    AMMC_LAUNCH_CHECK("gdec_scatter_priv_kernel");
+  } else {
     const int chunks = 4;
     dim3 grid(ceil_div(N, 32), ceil_div(ceil_div(C, 32), chunks));
     switch (k) {
