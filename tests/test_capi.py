@@ -37,6 +37,13 @@ def test_ops_refuse_cpu_tensors():
     q = A.Quantize_topk(16, 8, k=2)
     with pytest.raises(RuntimeError, match="CUDA"):
         q(torch.zeros(1, 4, 4, 16))
+    # the widened rows (generator engine, preprocessing) follow the same rule
+    with pytest.raises(RuntimeError, match="CUDA"):
+        A.GeneratorEngine(A.get_twostream().eval())(torch.zeros(1, 12, 64, 64), torch.zeros(1, 6, 64, 64))
+    with pytest.raises(RuntimeError, match="CUDA uint8"):
+        A.preprocess_frames(torch.zeros(1, 8, 8, 3, dtype=torch.uint8))
+    with pytest.raises(RuntimeError, match="CUDA float32"):
+        A.preprocess_flow(torch.zeros(1, 8, 8, 2))
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
