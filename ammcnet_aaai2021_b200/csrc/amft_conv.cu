@@ -226,11 +226,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             uint32_t hp[16], lp[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              __nv_bfloat16 h0 = __float2bfloat16_rn(y[2 * j]), h1 = __float2bfloat16_rn(y[2 * j + 1]);
-              __nv_bfloat16 l0 = __float2bfloat16_rn(y[2 * j] - __bfloat162float(h0));
-              __nv_bfloat16 l1 = __float2bfloat16_rn(y[2 * j + 1] - __bfloat162float(h1));
-              hp[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-              lp[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+              ptx::split_pack_bf16x2(y[2 * j], y[2 * j + 1], hp[j], lp[j]);
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -469,12 +465,7 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                 uint32_t hp[4], lp[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                  const float y0 = __uint_as_float(v[8 * g8 + 2 * j]), y1 = __uint_as_float(v[8 * g8 + 2 * j + 1]);
-                  const __nv_bfloat16 h0 = __float2bfloat16_rn(y0), h1 = __float2bfloat16_rn(y1);
-                  const __nv_bfloat16 l0 = __float2bfloat16_rn(y0 - __bfloat162float(h0));
-                  const __nv_bfloat16 l1 = __float2bfloat16_rn(y1 - __bfloat162float(h1));
-                  hp[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                  lp[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                  ptx::split_pack_bf16x2(__uint_as_float(v[8 * g8 + 2 * j]), __uint_as_float(v[8 * g8 + 2 * j + 1]), hp[j], lp[j]);
                 }
                 reinterpret_cast<uint4*>(hi)[g8] = make_uint4(hp[0], hp[1], hp[2], hp[3]);
                 reinterpret_cast<uint4*>(lo)[g8] = make_uint4(lp[0], lp[1], lp[2], lp[3]);

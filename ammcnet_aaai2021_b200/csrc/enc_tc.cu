@@ -7,11 +7,11 @@
 // (read 134 MB + write 134 MB at b=64) the kernel converts on the fly:
 //   warp 0      TMA: fp32 box [64 channels][128 pixels] (no swizzle) + the matching 64-channel slices of the bf16 hi/lo
 //               weight planes [64 d][64 ch] (128B swizzle) per pipeline stage
-//   warps 2-5   converters: thread = pixel; read its 64 staged fp32 values, split x = hi + lo (bf16), write both as rows
+//   warps 2-9   converters: thread = pixel x channel half; read its 32 staged fp32 values, split x = hi + lo (bf16), write both as rows
 //               of the canonical K-major 128B-swizzled UMMA tile (16-byte chunk index XOR (row & 7)), then
 //               fence.proxy.async + mbarrier arrive
 //   warp 1      MMA: per stage  hi*W_hi + hi*W_lo + lo*W_hi  (M128 x N64 x K16, fp32 accumulate in TMEM)
-//   warps 6-9   epilogue: + bias -> z fp32 [N, D], its bf16 rounding zp (the addressing filter's operand) and ||z||^2
+//   warps 10-13 epilogue: + bias -> z fp32 [N, D], its bf16 rounding zp (the addressing filter's operand) and ||z||^2
 // Error of the split-bf16 x3 product: ~2^-17 relative (measured on the conv kernel), i.e. z agrees with the fp32 FFMA
 // kernel to ~1e-5; the exact fp32 refine stage then ranks the candidates with that z.
 #include "common.cuh"
@@ -20,15 +20,19 @@
 
 namespace ammc {
 
-constexpr int ENC_THREADS = 320;
+constexpr int ENC_THREADS = 448;                   // warp 0 TMA, 1 MMA, 2-9 converters, 10-13 epilogue
 constexpr int ENC_D = 64;                          // output channels handled by this kernel
 constexpr int ENC_BK = 64;                         // channels per stage
 constexpr int ENC_STAGE_X = ENC_BK * 128 * 4;      // fp32 staging [64 ch][128 px]            32 KB
 constexpr int ENC_STAGE_A = 128 * ENC_BK * 2;      // one bf16 A tile [128 px][64 ch]          16 KB
 constexpr int ENC_STAGE_W = ENC_D * ENC_BK * 2;    // one bf16 weight slice [64 d][64 ch]       8 KB
-constexpr int ENC_STAGE = ENC_STAGE_X + 2 * ENC_STAGE_A + 2 * ENC_STAGE_W;   // 80 KB
-constexpr int ENC_STAGES = 2;
-constexpr int ENC_BAR_OFFSET = ENC_STAGES * ENC_STAGE;
+// two rings: the fp32 staging buffers are released as soon as the converters have read them (3 deep, so TMA runs ahead
+// of the conversion), the bf16 operand buffers (A hi/lo written by the converters + the weight slices) when their MMAs retire
+constexpr int ENC_X_STAGES = 3;
+constexpr int ENC_AW_STAGE = 2 * ENC_STAGE_A + 2 * ENC_STAGE_W;              // 48 KB
+constexpr int ENC_AW_STAGES = 2;
+constexpr int ENC_AW_OFFSET = ENC_X_STAGES * ENC_STAGE_X;                   // 96 KB
+constexpr int ENC_BAR_OFFSET = ENC_AW_OFFSET + ENC_AW_STAGES * ENC_AW_STAGE;   // 192 KB
 constexpr int ENC_SMEM = ENC_BAR_OFFSET + 256 + 1024;
 
 struct EncParams {
@@ -43,10 +47,12 @@ __global__ void __launch_bounds__(ENC_THREADS, 1)
 enc_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const EncParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + ENC_BAR_OFFSET);   // TMA landed (x staging + weight slices)
-  uint64_t* conv_bar = full_bar + ENC_STAGES;                                // converters wrote the A tiles
-  uint64_t* empty_bar = conv_bar + ENC_STAGES;                               // MMAs of the stage retired
-  uint64_t* tmem_full = empty_bar + ENC_STAGES;
+  uint64_t* x_full = reinterpret_cast<uint64_t*>(smem + ENC_BAR_OFFSET);     // TMA landed an fp32 staging buffer
+  uint64_t* x_empty = x_full + ENC_X_STAGES;                                 // the 128 converter threads have read it
+  uint64_t* w_full = x_empty + ENC_X_STAGES;                                 // TMA landed the weight slices of an operand stage
+  uint64_t* conv_bar = w_full + ENC_AW_STAGES;                               // converters wrote the A tiles
+  uint64_t* aw_free = conv_bar + ENC_AW_STAGES;                              // MMAs of the operand stage retired
+  uint64_t* tmem_full = aw_free + ENC_AW_STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
@@ -57,10 +63,11 @@ enc_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmX);
     ptx::prefetch_tensormap(&tmW);
-    for (int s = 0; s < ENC_STAGES; ++s) {
-      ptx::mbar_init(&full_bar[s], 1);
-      ptx::mbar_init(&conv_bar[s], 128);
-      ptx::mbar_init(&empty_bar[s], 1);
+    for (int s = 0; s < ENC_X_STAGES; ++s) { ptx::mbar_init(&x_full[s], 1); ptx::mbar_init(&x_empty[s], 256); }
+    for (int s = 0; s < ENC_AW_STAGES; ++s) {
+      ptx::mbar_init(&w_full[s], 1);
+      ptx::mbar_init(&conv_bar[s], 256);
+      ptx::mbar_init(&aw_free[s], 1);
     }
     for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tmem_full[a], 1); ptx::mbar_init(&tmem_empty[a], 128); }
     ptx::fence_mbar_init();
@@ -76,22 +83,27 @@ enc_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
 
   if (warp == 0) {
     if (lane == 0) {
-      int s = 0; uint32_t ph = 0;
+      int sx = 0; uint32_t phx = 0;
+      int sa = 0; uint32_t pha = 0;
       for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
         const int img = t / tiles_per_img, p0 = (t % tiles_per_img) * 128;
         for (int kb = 0; kb < kb_per_tile; ++kb) {
-          ptx::mbar_wait(&empty_bar[s], ph ^ 1, 51);
-          ptx::mbar_expect_tx(&full_bar[s], ENC_STAGE_X + 2 * ENC_STAGE_W);
-          uint8_t* base = smem + s * ENC_STAGE;
-          ptx::tma_load_3d(base, &tmX, &full_bar[s], p0, kb * ENC_BK, img);
-          ptx::tma_load_3d(base + ENC_STAGE_X + 2 * ENC_STAGE_A, &tmW, &full_bar[s], kb * ENC_BK, 0, 0);
-          ptx::tma_load_3d(base + ENC_STAGE_X + 2 * ENC_STAGE_A + ENC_STAGE_W, &tmW, &full_bar[s], kb * ENC_BK, 0, 1);
-          if (++s == ENC_STAGES) { s = 0; ph ^= 1; }
+          ptx::mbar_wait(&x_empty[sx], phx ^ 1, 51);
+          ptx::mbar_expect_tx(&x_full[sx], ENC_STAGE_X);
+          ptx::tma_load_3d(smem + sx * ENC_STAGE_X, &tmX, &x_full[sx], p0, kb * ENC_BK, img);
+          if (++sx == ENC_X_STAGES) { sx = 0; phx ^= 1; }
+          ptx::mbar_wait(&aw_free[sa], pha ^ 1, 57);
+          ptx::mbar_expect_tx(&w_full[sa], 2 * ENC_STAGE_W);
+          uint8_t* wdst = smem + ENC_AW_OFFSET + sa * ENC_AW_STAGE + 2 * ENC_STAGE_A;
+          ptx::tma_load_3d(wdst, &tmW, &w_full[sa], kb * ENC_BK, 0, 0);
+          ptx::tma_load_3d(wdst + ENC_STAGE_W, &tmW, &w_full[sa], kb * ENC_BK, 0, 1);
+          if (++sa == ENC_AW_STAGES) { sa = 0; pha ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
+      // whole warp converged, one elected lane issues (ptx::mma_f16_ss_warp): N = 64 MMAs are short, the issue loop counts
       constexpr uint32_t idesc = ptx::umma_idesc(1, 128, ENC_D);
       int s = 0; uint32_t ph = 0;
       int it = 0;
@@ -102,57 +114,66 @@ enc_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * ENC_D;
         for (int kb = 0; kb < kb_per_tile; ++kb) {
-          ptx::mbar_wait(&full_bar[s], ph, 53);      // weight slices landed
+          ptx::mbar_wait(&w_full[s], ph, 53);        // weight slices landed
           ptx::mbar_wait(&conv_bar[s], ph, 54);      // A tiles written by the converters
           ptx::tc_fence_after();
-          const uint32_t base = ptx::smem_u32(smem + s * ENC_STAGE);
-          const uint64_t a_hi = ptx::umma_desc_k_sw128(base + ENC_STAGE_X);
-          const uint64_t a_lo = ptx::umma_desc_k_sw128(base + ENC_STAGE_X + ENC_STAGE_A);
-          const uint64_t w_hi = ptx::umma_desc_k_sw128(base + ENC_STAGE_X + 2 * ENC_STAGE_A);
-          const uint64_t w_lo = ptx::umma_desc_k_sw128(base + ENC_STAGE_X + 2 * ENC_STAGE_A + ENC_STAGE_W);
+          const uint32_t base = ptx::smem_u32(smem + ENC_AW_OFFSET + s * ENC_AW_STAGE);
+          const uint64_t a_hi = ptx::umma_desc_k_sw128(base);
+          const uint64_t a_lo = ptx::umma_desc_k_sw128(base + ENC_STAGE_A);
+          const uint64_t w_hi = ptx::umma_desc_k_sw128(base + 2 * ENC_STAGE_A);
+          const uint64_t w_lo = ptx::umma_desc_k_sw128(base + 2 * ENC_STAGE_A + ENC_STAGE_W);
 #pragma unroll
           for (int k4 = 0; k4 < ENC_BK / 16; ++k4) {
-            ptx::mma_f16_ss(d_tmem, a_hi + 2 * k4, w_hi + 2 * k4, idesc, (kb | k4) != 0 ? 1u : 0u);
-            ptx::mma_f16_ss(d_tmem, a_hi + 2 * k4, w_lo + 2 * k4, idesc, 1u);
-            ptx::mma_f16_ss(d_tmem, a_lo + 2 * k4, w_hi + 2 * k4, idesc, 1u);
+            ptx::mma_f16_ss_warp(d_tmem, a_hi + 2 * k4, w_hi + 2 * k4, idesc, (kb | k4) != 0 ? 1u : 0u);
+            ptx::mma_f16_ss_warp(d_tmem, a_hi + 2 * k4, w_lo + 2 * k4, idesc, 1u);
+            ptx::mma_f16_ss_warp(d_tmem, a_lo + 2 * k4, w_hi + 2 * k4, idesc, 1u);
           }
-          ptx::mma_commit(&empty_bar[s]);
-          if (kb == kb_per_tile - 1) ptx::mma_commit(&tmem_full[acc]);
-          if (++s == ENC_STAGES) { s = 0; ph ^= 1; }
+          ptx::mma_commit_warp(&aw_free[s]);
+          if (kb == kb_per_tile - 1) ptx::mma_commit_warp(&tmem_full[acc]);
+          if (++s == ENC_AW_STAGES) { s = 0; ph ^= 1; }
         }
       }
     }
-  } else if (warp < 6) {
+  } else if (warp < 10) {
     // ---------------------------------------------------------------- converters: fp32 staging -> bf16 hi/lo UMMA tiles
-    const int row = (warp - 2) * 32 + lane;                   // pixel within the tile
-    int s = 0; uint32_t ph = 0;
+    // eight warps: two per 32-pixel group, each converting 32 of the stage's 64 channels (one converter warp per
+    // scheduler was the bound: ~450 dependent instructions per thread and k-block)
+    const int row = ((warp - 2) & 3) * 32 + lane;             // pixel within the tile
+    const int c8_0 = ((warp - 2) >> 2) * (ENC_BK / 16);       // first 8-channel chunk of this warp's half
+    int sx = 0; uint32_t phx = 0;
+    int sa = 0; uint32_t pha = 0;
     for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
       for (int kb = 0; kb < kb_per_tile; ++kb) {
-        ptx::mbar_wait(&full_bar[s], ph, 55);                 // staging landed (the previous MMAs of this stage retired
-                                                              // before the producer refilled it, so the A tiles are free)
-        uint8_t* base = smem + s * ENC_STAGE;
-        const float* xs = reinterpret_cast<const float*>(base) + row;          // [ch][128 px]
-        uint8_t* a_hi = base + ENC_STAGE_X + row * 128;
-        uint8_t* a_lo = a_hi + ENC_STAGE_A;
+        ptx::mbar_wait(&x_full[sx], phx, 55);                 // fp32 staging landed
+        ptx::mbar_wait(&aw_free[sa], pha ^ 1, 58);            // the MMAs that last read these A tiles have retired
+        // explicit shared-space accesses (the generic pointer derived from the aligned base would compile to LD.E/ST.E)
+        const uint32_t xs = ptx::smem_u32(smem + sx * ENC_STAGE_X) + row * 4;                     // [ch][128 px] fp32
+        const uint32_t a_hi = ptx::smem_u32(smem + ENC_AW_OFFSET + sa * ENC_AW_STAGE) + row * 128;
+        const uint32_t a_lo = a_hi + ENC_STAGE_A;
 #pragma unroll
-        for (int c8 = 0; c8 < ENC_BK / 8; ++c8) {
+        for (int c8 = c8_0; c8 < c8_0 + ENC_BK / 16; ++c8) {
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = ptx::lds_f32(xs + (c8 * 8 + j) * 512);
           uint32_t hp[4], lp[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const float v0 = xs[(c8 * 8 + 2 * j) * 128], v1 = xs[(c8 * 8 + 2 * j + 1) * 128];
-            const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
-            const __nv_bfloat16 l0 = __float2bfloat16_rn(v0 - __bfloat162float(h0));
-            const __nv_bfloat16 l1 = __float2bfloat16_rn(v1 - __bfloat162float(h1));
-            hp[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-            lp[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+            // packed conversions: one F2FP per pair; float(hi) is a 16-bit shift of its bit pattern
+            const uint32_t h = ptx::pack_bf16x2(v[2 * j], v[2 * j + 1]);
+            const float r0 = v[2 * j] - __uint_as_float(h << 16);
+            const float r1 = v[2 * j + 1] - __uint_as_float(h & 0xffff0000u);
+            hp[j] = h;
+            lp[j] = ptx::pack_bf16x2(r0, r1);
           }
-          const int chunk = (c8 ^ (row & 7)) * 16;            // 128B swizzle: 16-byte chunk index XOR (row mod 8)
-          *reinterpret_cast<uint4*>(a_hi + chunk) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
-          *reinterpret_cast<uint4*>(a_lo + chunk) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+          const uint32_t chunk = (uint32_t)((c8 ^ (row & 7)) * 16);   // 128B swizzle: 16-byte chunk index XOR (row mod 8)
+          ptx::sts_v4(a_hi + chunk, hp[0], hp[1], hp[2], hp[3]);
+          ptx::sts_v4(a_lo + chunk, lp[0], lp[1], lp[2], lp[3]);
         }
+        ptx::mbar_arrive(&x_empty[sx]);                       // staging buffer read: TMA may refill it
         ptx::fence_proxy_async();                             // generic-proxy writes -> visible to the tensor core
-        ptx::mbar_arrive(&conv_bar[s]);
-        if (++s == ENC_STAGES) { s = 0; ph ^= 1; }
+        ptx::mbar_arrive(&conv_bar[sa]);
+        if (++sx == ENC_X_STAGES) { sx = 0; phx ^= 1; }
+        if (++sa == ENC_AW_STAGES) { sa = 0; pha ^= 1; }
       }
     }
   } else {

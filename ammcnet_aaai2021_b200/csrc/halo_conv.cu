@@ -312,11 +312,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             uint32_t hp[16], lp[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              __nv_bfloat16 h0 = __float2bfloat16_rn(y[2 * j]), h1 = __float2bfloat16_rn(y[2 * j + 1]);
-              __nv_bfloat16 l0 = __float2bfloat16_rn(y[2 * j] - __bfloat162float(h0));
-              __nv_bfloat16 l1 = __float2bfloat16_rn(y[2 * j + 1] - __bfloat162float(h1));
-              hp[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-              lp[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+              ptx::split_pack_bf16x2(y[2 * j], y[2 * j + 1], hp[j], lp[j]);
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {

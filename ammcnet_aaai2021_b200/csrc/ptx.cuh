@@ -58,6 +58,28 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
   }
 }
 
+// ---------------------------------------------------------------- explicit shared-memory accesses / packed conversion
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+// {lo 16 bits = bf16_rn(a), hi 16 bits = bf16_rn(b)} in one F2FP
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+// split two fp32 values into bf16 hi / lo parts (x = hi + lo), each pair packed into one 32-bit word: two F2FP, two shifts
+// and two subtractions instead of four scalar conversions plus repacking
+__device__ __forceinline__ void split_pack_bf16x2(float y0, float y1, uint32_t& hi, uint32_t& lo) {
+  hi = pack_bf16x2(y0, y1);
+  lo = pack_bf16x2(y0 - __uint_as_float(hi << 16), y1 - __uint_as_float(hi & 0xffff0000u));
+}
+
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
