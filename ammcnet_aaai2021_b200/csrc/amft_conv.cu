@@ -409,6 +409,8 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       const size_t opix = p.up2x ? ((size_t)img * (2 * p.H) + 2 * hh + (q4 >> 1)) * (2 * p.W) + 2 * ww + (q4 & 1)
                                  : ((size_t)img * p.H + hh) * p.W + ww;
       __nv_bfloat16* const oplane = p.out_planes + opix * p.out_cs + p.out_c_off - q4 * p.up_cout;
+      // 32-byte aligned plane rows (every shipped layout): STG.256
+      const bool planes32 = ((reinterpret_cast<uintptr_t>(oplane) | (uintptr_t)(p.out_plane_stride * 2)) & 31) == 0;
       const size_t obase = ((size_t)img * p.Cout + n0) * hw + (size_t)hh * p.W + ww;
       const bool has_res = valid && p.res_nchw != nullptr;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * PAIR_N + half * HALF_N;
@@ -460,15 +462,19 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             if (p.out_planes) {
               __nv_bfloat16* hi = oplane + cbase;
               __nv_bfloat16* lo = hi + p.out_plane_stride;
+              uint32_t hp[8], lp[8];
 #pragma unroll
-              for (int g8 = 0; g8 < 2; ++g8) {               // 8 channels (16 B per plane) at a time
-                uint32_t hp[4], lp[4];
+              for (int j = 0; j < 8; ++j)
+                ptx::split_pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]), hp[j], lp[j]);
+              if (planes32) {                                  // 16 channels = one 32-byte sector per plane: one request
+                ptx::stg_v8(hi, hp);
+                ptx::stg_v8(lo, lp);
+              } else {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  ptx::split_pack_bf16x2(__uint_as_float(v[8 * g8 + 2 * j]), __uint_as_float(v[8 * g8 + 2 * j + 1]), hp[j], lp[j]);
+                for (int g8 = 0; g8 < 2; ++g8) {
+                  reinterpret_cast<uint4*>(hi)[g8] = make_uint4(hp[4 * g8], hp[4 * g8 + 1], hp[4 * g8 + 2], hp[4 * g8 + 3]);
+                  reinterpret_cast<uint4*>(lo)[g8] = make_uint4(lp[4 * g8], lp[4 * g8 + 1], lp[4 * g8 + 2], lp[4 * g8 + 3]);
                 }
-                reinterpret_cast<uint4*>(hi)[g8] = make_uint4(hp[0], hp[1], hp[2], hp[3]);
-                reinterpret_cast<uint4*>(lo)[g8] = make_uint4(lp[0], lp[1], lp[2], lp[3]);
               }
             }
           }

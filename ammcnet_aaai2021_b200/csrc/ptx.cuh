@@ -73,6 +73,12 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
   return r;
 }
+// 256-bit global store (sm_100: STG.E.256): one request per 32-byte sector instead of two 16-byte ones
+__device__ __forceinline__ void stg_v8(void* ptr, const uint32_t (&w)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(w[0]), "r"(w[1]), "r"(w[2]),
+               "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+               : "memory");
+}
 // split two fp32 values into bf16 hi / lo parts (x = hi + lo), each pair packed into one 32-bit word: two F2FP, two shifts
 // and two subtractions instead of four scalar conversions plus repacking
 __device__ __forceinline__ void split_pack_bf16x2(float y0, float y1, uint32_t& hi, uint32_t& lo) {
