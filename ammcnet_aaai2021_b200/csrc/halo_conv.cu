@@ -314,10 +314,20 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int j = 0; j < 16; ++j) {
               ptx::split_pack_bf16x2(y[2 * j], y[2 * j + 1], hp[j], lp[j]);
             }
+            if (((reinterpret_cast<uintptr_t>(hi) | reinterpret_cast<uintptr_t>(lo)) & 31) == 0) {
+              // 32 channels = two 32-byte sectors per plane: STG.256, one request per sector
+              const uint32_t (&h8)[2][8] = *reinterpret_cast<const uint32_t (*)[2][8]>(hp);
+              const uint32_t (&l8)[2][8] = *reinterpret_cast<const uint32_t (*)[2][8]>(lp);
+              ptx::stg_v8(hi, h8[0]);
+              ptx::stg_v8(hi + 16, h8[1]);
+              ptx::stg_v8(lo, l8[0]);
+              ptx::stg_v8(lo + 16, l8[1]);
+            } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              reinterpret_cast<uint4*>(hi)[j] = make_uint4(hp[4 * j], hp[4 * j + 1], hp[4 * j + 2], hp[4 * j + 3]);
-              reinterpret_cast<uint4*>(lo)[j] = make_uint4(lp[4 * j], lp[4 * j + 1], lp[4 * j + 2], lp[4 * j + 3]);
+              for (int j = 0; j < 4; ++j) {
+                reinterpret_cast<uint4*>(hi)[j] = make_uint4(hp[4 * j], hp[4 * j + 1], hp[4 * j + 2], hp[4 * j + 3]);
+                reinterpret_cast<uint4*>(lo)[j] = make_uint4(lp[4 * j], lp[4 * j + 1], lp[4 * j + 2], lp[4 * j + 3]);
+              }
             }
           }
         }
