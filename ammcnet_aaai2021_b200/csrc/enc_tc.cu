@@ -194,22 +194,27 @@ enc_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         uint32_t v[32];
         ptx::tmem_ld_32x32(taddr + c32 * 32, v);
         ptx::tmem_ld_wait();
+        // 32-byte stores (STG.256): one request per sector; a row of z is 256 B, of zp 128 B, both 32-byte aligned
         float* zr = p.z + n * ENC_D + c32 * 32;
+        uint32_t zb[16];
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + c32 * 32 + 4 * g));
-          float4 o;
-          o.x = __uint_as_float(v[4 * g + 0]) + b4.x; o.y = __uint_as_float(v[4 * g + 1]) + b4.y;
-          o.z = __uint_as_float(v[4 * g + 2]) + b4.z; o.w = __uint_as_float(v[4 * g + 3]) + b4.w;
-          reinterpret_cast<float4*>(zr)[g] = o;
-          zn2 = fmaf(o.x, o.x, zn2); zn2 = fmaf(o.y, o.y, zn2); zn2 = fmaf(o.z, o.z, zn2); zn2 = fmaf(o.w, o.w, zn2);
-          if (p.zp) {
-            const __nv_bfloat162 p0 = __floats2bfloat162_rn(o.x, o.y), p1 = __floats2bfloat162_rn(o.z, o.w);
-            uint2 pk;
-            pk.x = *reinterpret_cast<const uint32_t*>(&p0);
-            pk.y = *reinterpret_cast<const uint32_t*>(&p1);
-            *reinterpret_cast<uint2*>(p.zp + n * ENC_D + c32 * 32 + 4 * g) = pk;
+        for (int g = 0; g < 4; ++g) {
+          uint32_t o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float zv = __uint_as_float(v[8 * g + j]) + __ldg(p.bias + c32 * 32 + 8 * g + j);
+            zn2 = fmaf(zv, zv, zn2);
+            o[j] = __float_as_uint(zv);
           }
+          ptx::stg_v8(zr + 8 * g, o);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) zb[4 * g + j] = ptx::pack_bf16x2(__uint_as_float(o[2 * j]), __uint_as_float(o[2 * j + 1]));
+        }
+        if (p.zp) {
+          __nv_bfloat16* zpr = p.zp + n * ENC_D + c32 * 32;
+          const uint32_t (&z8)[2][8] = *reinterpret_cast<const uint32_t (*)[2][8]>(zb);
+          ptx::stg_v8(zpr, z8[0]);
+          ptx::stg_v8(zpr + 16, z8[1]);
         }
       }
       if (p.znorm2) p.znorm2[n] = zn2;
