@@ -61,6 +61,7 @@ def _workspace(nbytes: int, device: torch.device) -> torch.Tensor:
 
 
 _side_streams: Dict[Tuple[int, int], "torch.cuda.Stream"] = {}
+CONCURRENCY = {"on": True}       # False: `concurrently` runs its pieces one after the other on the current stream (per-kernel timing)
 
 
 def concurrently(*fns):
@@ -71,6 +72,8 @@ def concurrently(*fns):
     per-frame reductions) and the tails of the large ones overlap when issued on different streams.  fns[0] runs on the
     current stream, the others on per-device side streams; works eagerly and under CUDA-graph capture (fork/join).
     Returns the list of results."""
+    if not CONCURRENCY["on"]:
+        return [fn() for fn in fns]
     cur = torch.cuda.current_stream()
     dev = cur.device
     results = [None] * len(fns)

@@ -13,6 +13,7 @@ m = A.get_twostream(); m.load_state_dict(synth.generator_params(3)); m = m.to(de
 m.bridge.precision = args.precision
 rgb, op = (t.to(dev) for t in synth.generator_inputs(9, args.batch, 256, 256))
 eng = A.GeneratorEngine(m, precision=args.precision)
+F_.CONCURRENCY["on"] = False      # one stream: the events around a launch must not see the other network stream's kernels
 for _ in range(3): eng(rgb, op)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -68,8 +68,17 @@ def main():
         row["cudnn_fp32_ms"] = timed(step(ref))
         step(ours)(); g_ours = ours.O2F.conv[0].weight.grad.clone(); gx_ours = zx.grad.clone()
         step(ref)(); g_ref = ref.O2F.conv[0].weight.grad.clone(); gx_ref = zx.grad.clone()
-        row["wgrad_rel_err_vs_cudnn_fp32"] = float((g_ours - g_ref).abs().max() / g_ref.abs().max())
-        row["gx_rel_err_vs_cudnn_fp32"] = float((gx_ours - gx_ref).abs().max() / gx_ref.abs().max())
+        # ReLU has no derivative at 0: a pre-activation within rounding of 0 may take the other side in the other
+        # implementation and changes the gradients by O(1) in its 3x3 neighbourhood, so the max error is dominated by those
+        # isolated elements; report the fraction of elements outside 1e-3 next to it, and cuDNN TF32 for calibration
+        def cmp(a, r):
+            d = (a - r).abs()
+            return {"max_rel": float(d.max() / r.abs().max()), "frac_outside_1e-3": float((d > 1e-3 * r.abs().max()).float().mean())}
+        row["wgrad_vs_cudnn_fp32"] = cmp(g_ours, g_ref)
+        row["gx_vs_cudnn_fp32"] = cmp(gx_ours, gx_ref)
+        torch.backends.cudnn.allow_tf32 = True
+        step(ref)(); row["cudnn_tf32_gx_vs_cudnn_fp32"] = cmp(zx.grad.clone(), gx_ref)
+        torch.backends.cudnn.allow_tf32 = False
         F_.check_pipeline_watchdog()
         res.append(row)
         print(json.dumps(row), flush=True)
