@@ -70,6 +70,7 @@ SIGNATURES = {
     "ammc_pack_planes": (I, [P, P, L, P]),
     "ammc_pack_conv_weights_dgrad": (I, [P, P, I, I, P]),
     "ammc_conv3x3_wgrad": (I, [P, P, P, I, I, I, I, I, I, P]),
+    "ammc_conv1x1_wgrad": (I, [P, P, P, I, I, I, I, I, I, P]),
     "ammc_bn_fold": (I, [P] * 4 + [F] + [P, P, I, P]),
     "ammc_preprocess_frames_u8": (I, [P, P, I, I, I, I, I, P]),
     "ammc_preprocess_flow": (I, [P, P, I, I, I, I, I, P]),

@@ -254,7 +254,8 @@ struct WgradParams {
   int tiles_m, tiles_n, splits, imgs_per_split;
   int n_pass;               // 1: hi*hi only; 3: (hi,hi) + (hi,lo) + (lo,hi)
   int block_n;              // input channels actually present in an N tile (Cin may be < 256)
-  float* gw;                // [Cout][Cin][9]
+  int ntaps;                // 9: 3x3 conv; 1: 1x1 conv (a plain [Cout x pixels] . [pixels x Cin] GEMM)
+  float* gw;                // [Cout][Cin][ntaps]
 };
 
 __global__ void __launch_bounds__(WG_THREADS, 1)
@@ -268,7 +269,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int work_items = p.tiles_m * p.tiles_n * 9 * p.splits;
+  const int work_items = p.tiles_m * p.tiles_n * p.ntaps * p.splits;
+  const int ntaps = p.ntaps;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmA);
@@ -302,7 +304,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     int w_ = (wi_);                                    \
     mt_ = w_ % tiles_m; w_ /= tiles_m;                 \
     nt_ = w_ % tiles_n; w_ /= tiles_n;                 \
-    tap_ = w_ % 9;      sp_ = w_ / 9;                  \
+    tap_ = w_ % ntaps;  sp_ = w_ / ntaps;              \
   }
 
   if (warp == 0) {
@@ -310,7 +312,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int s = 0; uint32_t ph = 0;
       for (int wi = blockIdx.x; wi < work_items; wi += gridDim.x) {
         WG_DECODE(wi, mt, nt, tap, sp)
-        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+        const int dy = ntaps == 9 ? tap / 3 - 1 : 0, dx = ntaps == 9 ? tap % 3 - 1 : 0;
         const int i0 = sp * p.imgs_per_split, i1 = min(p.b, i0 + p.imgs_per_split);
         for (int ps = 0; ps < p.n_pass; ++ps) {
           const int pa = ps == 2 ? 1 : 0, pb = ps == 1 ? 1 : 0;   // (hi,hi) (hi,lo) (lo,hi)
@@ -388,7 +390,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const int ci0 = nt * WG_BLOCK_N + c32 * 32;
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (ci0 + j < p.Cin) atomicAdd(&p.gw[((size_t)co * p.Cin + ci0 + j) * 9 + tap], __uint_as_float(v[j]));
+            if (ci0 + j < p.Cin) atomicAdd(&p.gw[((size_t)co * p.Cin + ci0 + j) * ntaps + tap], __uint_as_float(v[j]));
         }
       }
       ptx::tc_fence_before();
@@ -545,10 +547,13 @@ extern "C" int ammc_pack_conv_weights_dgrad(const float* w, void* wp, int Cout, 
   return 0;
 }
 
-extern "C" int ammc_conv3x3_wgrad(const void* gy_nhwc_planes, const void* x_nhwc_planes, float* gw, int b, int Cin,
-                                  int Cout, int h, int w, int precision, void* stream) {
-  cudaStream_t st = (cudaStream_t)stream;
+namespace ammc {
+// gw [Cout][Cin][ntaps] = sum over pixels of gy[px][Cout] (x) x[px + tap][Cin]; operands are NHWC bf16 hi/lo planes.
+// Channel counts need not fill the 128 x 256 tile: TMA zero-fills the channel boxes past Cout / Cin.
+int conv_wgrad_run(const void* gy_nhwc_planes, const void* x_nhwc_planes, float* gw, int b, int Cin, int Cout, int h, int w,
+                   int ntaps, int precision, cudaStream_t st) {
   AMMC_REQUIRE(gy_nhwc_planes && x_nhwc_planes && gw && b > 0, "bad argument");
+  AMMC_REQUIRE(ntaps == 9 || ntaps == 1, "ntaps must be 9 or 1");
   if (precision != 1 && precision != 3) return fail(AMMC_EINVAL, "precision must be 1 or 3 (got %d)", precision);
   if (Cin % 64 != 0 || Cout % 64 != 0)
     return fail(AMMC_EUNSUPPORTED, "tcgen05 wgrad needs Cin and Cout multiples of 64 (got %d, %d)", Cin, Cout);
@@ -564,13 +569,14 @@ extern "C" int ammc_conv3x3_wgrad(const void* gy_nhwc_planes, const void* x_nhwc
   p.tiles_m = ceil_div(Cout, WG_BLOCK_M);
   p.tiles_n = ceil_div(Cin, WG_BLOCK_N);
   p.block_n = min(Cin, WG_BLOCK_N);
-  const int base_items = p.tiles_m * p.tiles_n * 9;
+  p.ntaps = ntaps;
+  const int base_items = p.tiles_m * p.tiles_n * ntaps;
   p.splits = max(1, min(b, ceil_div(2 * num_sms(), base_items)));
   p.imgs_per_split = ceil_div(b, p.splits);
   p.splits = ceil_div(b, p.imgs_per_split);
   p.n_pass = precision;
   p.gw = gw;
-  AMMC_CUDA_CHECK(cudaMemsetAsync(gw, 0, (size_t)Cout * Cin * 9 * sizeof(float), st));
+  AMMC_CUDA_CHECK(cudaMemsetAsync(gw, 0, (size_t)Cout * Cin * ntaps * sizeof(float), st));
   CUtensorMap tmA, tmB;
   {
     uint64_t dims[5] = {(uint64_t)Cout, (uint64_t)w, (uint64_t)h, (uint64_t)b, 2};
@@ -597,4 +603,15 @@ extern "C" int ammc_conv3x3_wgrad(const void* gy_nhwc_planes, const void* x_nhwc
   conv_wgrad_kernel<<<min(num_sms(), items), WG_THREADS, WG_SMEM, st>>>(tmA, tmB, p);
   AMMC_LAUNCH_CHECK("conv_wgrad_kernel");
   return 0;
+}
+}  // namespace ammc
+
+extern "C" int ammc_conv3x3_wgrad(const void* gy_nhwc_planes, const void* x_nhwc_planes, float* gw, int b, int Cin,
+                                  int Cout, int h, int w, int precision, void* stream) {
+  return conv_wgrad_run(gy_nhwc_planes, x_nhwc_planes, gw, b, Cin, Cout, h, w, 9, precision, (cudaStream_t)stream);
+}
+
+extern "C" int ammc_conv1x1_wgrad(const void* gy_nhwc_planes, const void* x_nhwc_planes, float* gw, int b, int Cin,
+                                  int Cout, int h, int w, int precision, void* stream) {
+  return conv_wgrad_run(gy_nhwc_planes, x_nhwc_planes, gw, b, Cin, Cout, h, w, 1, precision, (cudaStream_t)stream);
 }

@@ -592,6 +592,81 @@ __global__ void __launch_bounds__(256) gdec_scatter_kernel(const float* __restri
   }
 }
 
+// ---- operands of the tensor-core weight-gradient GEMMs (K = pixels) -------------------------------------------------
+// g [b][C][HW] fp32 -> NHWC bf16 hi/lo planes [2][b][HW][C].  A block transposes a [64 ch][32 px] tile through shared
+// memory: coalesced 128-byte row loads, then every thread emits 8 channels of one pixel as one 16-byte store per plane.
+__global__ void __launch_bounds__(256) pack_nhwc64_kernel(const float* __restrict__ g, __nv_bfloat16* __restrict__ gp, int C,
+                                                           int HW, long long plane_stride) {
+  __shared__ float tile[64][33];
+  const int img = blockIdx.z, c0 = blockIdx.y * 64, p0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int r = ty; r < 64; r += 8) {
+    const int c = c0 + r, pp = p0 + tx;
+    tile[r][tx] = (c < C && pp < HW) ? g[((size_t)img * C + c) * HW + pp] : 0.f;
+  }
+  __syncthreads();
+  const int px = threadIdx.x >> 3, cg = threadIdx.x & 7;         // pixel within the tile, 8-channel group
+  const int pp = p0 + px, c = c0 + cg * 8;
+  if (pp < HW && c < C) {                                        // C is a multiple of 8 on this path
+    uint32_t hp[4], lp[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float v0 = tile[cg * 8 + 2 * j][px], v1 = tile[cg * 8 + 2 * j + 1][px];
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+      const __nv_bfloat16 l0 = __float2bfloat16_rn(v0 - __bfloat162float(h0));
+      const __nv_bfloat16 l1 = __float2bfloat16_rn(v1 - __bfloat162float(h1));
+      hp[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+      lp[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    }
+    __nv_bfloat16* dst = gp + ((size_t)img * HW + pp) * C + c;
+    *reinterpret_cast<uint4*>(dst) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+    *reinterpret_cast<uint4*>(dst + plane_stride) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+  }
+}
+
+// colsum[c] += sum over images and pixels of g [b][C][HW]  (g_dec_b): one block per (channel, image group)
+__global__ void __launch_bounds__(256) channel_sum_kernel(const float* __restrict__ g, float* __restrict__ colsum, int b,
+                                                           int C, int HW, int imgs_per_block) {
+  __shared__ float red[33];
+  const int c = blockIdx.x;
+  const int i0 = blockIdx.y * imgs_per_block, i1 = min(b, i0 + imgs_per_block);
+  float acc = 0.f;
+  for (int img = i0; img < i1; ++img) {
+    const float* row = g + ((size_t)img * C + c) * HW;
+    for (int i = threadIdx.x; i < HW; i += 256) acc += row[i];
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) atomicAdd(&colsum[c], acc);
+}
+
+// read[n][j*D + d] = bank_t[idx[n][j]][d] as bf16 hi/lo planes [2][N][k*D] (what the forward's refine kernel wrote)
+__global__ void __launch_bounds__(256) read_planes_kernel(const int64_t* __restrict__ idx, const float* __restrict__ bank_t,
+                                                           __nv_bfloat16* __restrict__ rp, long long N, int D, int k,
+                                                           long long plane_stride) {
+  const long long total = N * k * (D / 4);
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int d4 = (int)(e % (D / 4));
+    const long long nj = e / (D / 4);
+    const float4 v = __ldg(reinterpret_cast<const float4*>(bank_t + (size_t)idx[nj] * D) + d4);
+    const float vv[4] = {v.x, v.y, v.z, v.w};
+    __nv_bfloat16 h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      h[i] = __float2bfloat16_rn(vv[i]);
+      l[i] = __float2bfloat16_rn(vv[i] - __bfloat162float(h[i]));
+    }
+    uint2 ph, pl;
+    ph.x = (uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16);
+    ph.y = (uint32_t)__bfloat16_as_ushort(h[2]) | ((uint32_t)__bfloat16_as_ushort(h[3]) << 16);
+    pl.x = (uint32_t)__bfloat16_as_ushort(l[0]) | ((uint32_t)__bfloat16_as_ushort(l[1]) << 16);
+    pl.y = (uint32_t)__bfloat16_as_ushort(l[2]) | ((uint32_t)__bfloat16_as_ushort(l[3]) << 16);
+    __nv_bfloat16* dst = rp + (size_t)nj * D + 4 * d4;
+    *reinterpret_cast<uint2*>(dst) = ph;
+    *reinterpret_cast<uint2*>(dst + plane_stride) = pl;
+  }
+}
+
 // g_dec_w[c][j*D + d] = sum_m G[j][m][c] * embed[d][m]
 __global__ void gdec_w_kernel(const float* __restrict__ G, const float* __restrict__ embed,
                               float* __restrict__ g_dec_w, int C, int D, int M, int k) {
@@ -651,6 +726,8 @@ int run_enc_tc(const float* x, const float* enc_w, const float* enc_b, float* z,
 // amft_conv.cu
 bool conv_shape_supported(int b, int Cin, int Cout, int h, int w);
 int pack_planes_f32(const float* x, void* xp, long long n, cudaStream_t st);
+int conv_wgrad_run(const void* gy_nhwc_planes, const void* x_nhwc_planes, float* gw, int b, int Cin, int Cout, int h, int w,
+                   int ntaps, int precision, cudaStream_t st);
 int pack_weights_1x1(const float* w, void* wp, int Cout, int Cin, cudaStream_t st);
 int conv_igemm(const void* xp, const void* wp, const float* scale, const float* shift, void* out_planes,
                float* out_nchw, const float* res_nchw, int b, int Cin, int Cout, int h, int w, int ntaps, int precision,
@@ -935,7 +1012,10 @@ extern "C" size_t ammc_mem_bwd_workspace_bytes(int b, int h, int w, int C, int D
   // + tensor-core gx: bf16 hi/lo planes of g_z, packed enc_w^T, unit scale / zero shift vectors
   return align_up((size_t)M * D * 4, 256) + align_up((size_t)N * D * 4, 256) + align_up((size_t)k * M * C * 4, 256) +
          align_up((size_t)2 * N * D * 2, 256) + align_up((size_t)2 * C * D * 2, 256) + 2 * align_up((size_t)C * 4, 256) +
-         align_up((size_t)C * D * 4, 256);
+         align_up((size_t)C * D * 4, 256) +
+         // tensor-core weight gradients: NHWC planes of x and g_out, planes of the gathered read, g_dec_w^T
+         2 * align_up((size_t)2 * N * C * 2, 256) + align_up((size_t)2 * N * k * D * 2, 256) +
+         align_up((size_t)k * D * C * 4, 256);
 }
 
 extern "C" int ammc_mem_bwd(const float* x, const float* enc_w, const float* embed, const int64_t* idx,
@@ -982,6 +1062,31 @@ extern "C" int ammc_mem_bwd(const float* x, const float* enc_w, const float* emb
     AMMC_LAUNCH_CHECK("fill_kernel");
     if (int rc = conv_igemm(gzp, wtp, ones, zeros, nullptr, gx, residual ? g_out : nullptr, b, D, C, h, w, 1, 3, 0, st))
       return rc;
+    if (w <= 128 && b <= 65535) {
+      // both weight gradients are GEMMs with K = pixels: the tcgen05 weight-gradient kernel (amft_train.cu) on NHWC bf16
+      // hi/lo planes.   g_enc_w [D][C] = g_z^T . x ;   g_dec_w^T [kD][C] = read^T . g_out ;   g_dec_b from the pack pass
+      __nv_bfloat16* xpl = ws.take<__nv_bfloat16>((size_t)2 * N * C);
+      __nv_bfloat16* gopl = ws.take<__nv_bfloat16>((size_t)2 * N * C);
+      __nv_bfloat16* rdpl = ws.take<__nv_bfloat16>((size_t)2 * N * k * D);
+      float* gdwT = ws.take<float>((size_t)k * D * C);
+      if (!ws.ok()) return fail(AMMC_EWORKSPACE, "workspace too small");
+      const dim3 pgrid(ceil_div(HW, 32), ceil_div(C, 64), b);
+      pack_nhwc64_kernel<<<pgrid, 256, 0, st>>>(x, xpl, C, HW, (long long)N * C);
+      pack_nhwc64_kernel<<<pgrid, 256, 0, st>>>(g_out, gopl, C, HW, (long long)N * C);
+      AMMC_LAUNCH_CHECK("pack_nhwc64_kernel");
+      {
+        const int per = max(1, b / 8);
+        channel_sum_kernel<<<dim3(C, ceil_div(b, per)), 256, 0, st>>>(g_out, g_dec_b, b, C, HW, per);
+        AMMC_LAUNCH_CHECK("channel_sum_kernel");
+      }
+      read_planes_kernel<<<num_sms() * 8, 256, 0, st>>>(idx, bank_t, rdpl, (long long)N, D, k, (long long)N * k * D);
+      AMMC_LAUNCH_CHECK("read_planes_kernel");
+      if (int rc = conv_wgrad_run(gzp, xpl, g_enc_w, b, C, D, h, w, 1, 3, st)) return rc;
+      if (int rc = conv_wgrad_run(rdpl, gopl, gdwT, b, C, k * D, h, w, 1, 3, st)) return rc;
+      bank_transpose_kernel<<<dim3(ceil_div(C, 32), ceil_div(k * D, 32)), dim3(32, 8), 0, st>>>(gdwT, g_dec_w, k * D, C);
+      AMMC_LAUNCH_CHECK("bank_transpose_kernel");
+      return 0;
+    }
   } else {
     gx_kernel<<<dim3(ceil_div(N, 64), ceil_div(C, 64)), 256, 0, st>>>(gz, enc_w, g_out, gx, (int)N, HW, C, D, residual);
     AMMC_LAUNCH_CHECK("gx_kernel");

@@ -233,7 +233,9 @@ int ammc_conv1x1_bn_relu(const void* xp, const void* wp, const float* scale, con
  * ammc_pack_conv_weights_dgrad   w [Cout,Cin,3,3] -> [2][Cin][9*Cout] (taps flipped): ammc_conv3x3_bn_relu on gradient
  *                       planes with these weights is the data gradient of the convolution.
  * ammc_conv3x3_wgrad    gw [Cout,Cin,3,3] = sum_pixels gy x x(shifted) on tcgen05; operands are the NHWC bf16 planes of
- *                       the output gradient [2][b,h,w,Cout] and of the conv input [2][b,h,w,Cin] (MN-major UMMA). */
+ *                       the output gradient [2][b,h,w,Cout] and of the conv input [2][b,h,w,Cin] (MN-major UMMA).
+ * ammc_conv1x1_wgrad    same for a 1x1 conv: gw [Cout,Cin] = gy^T . x, a GEMM whose K axis is the pixels (also used inside
+ *                       ammc_mem_bwd for the enc / dec weight gradients). */
 int ammc_bn_batch_stats(const float* y, const float* gamma, const float* beta, float* running_mean, float* running_var,
                         float* scale, float* shift, float* mean, float* invstd, void* workspace, size_t workspace_bytes,
                         int b, int C, int h, int w, float momentum, float eps, int training, void* stream);
@@ -248,6 +250,8 @@ int ammc_pack_conv_weights_dgrad(const float* w, void* wp, int Cout, int Cin, vo
 int ammc_conv3x3_wgrad(const void* gy_nhwc_planes, const void* x_nhwc_planes, float* gw, int b, int Cin, int Cout,
                        int h, int w, int precision, void* stream);
 /* BatchNorm (eval) folding: scale/shift [C] from gamma, beta, running_mean, running_var. */
+int ammc_conv1x1_wgrad(const void* gy_nhwc_planes, const void* x_nhwc_planes, float* gw, int b, int Cin, int Cout, int h,
+                       int w, int precision, void* stream);
 int ammc_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, float eps,
                  float* scale, float* shift, int C, void* stream);
 
