@@ -625,6 +625,13 @@ __global__ void __launch_bounds__(256) pack_nhwc64_kernel(const float* __restric
   }
 }
 
+int pack_nhwc64(const float* x, void* xp, int b, int C, int HW, cudaStream_t st) {     // C % 8 == 0
+  pack_nhwc64_kernel<<<dim3(ceil_div(HW, 32), ceil_div(C, 64), b), 256, 0, st>>>(x, (__nv_bfloat16*)xp, C, HW,
+                                                                                  (long long)b * HW * C);
+  AMMC_LAUNCH_CHECK("pack_nhwc64_kernel");
+  return 0;
+}
+
 // colsum[c] += sum over images and pixels of g [b][C][HW]  (g_dec_b): one block per (channel, image group)
 __global__ void __launch_bounds__(256) channel_sum_kernel(const float* __restrict__ g, float* __restrict__ colsum, int b,
                                                            int C, int HW, int imgs_per_block) {

@@ -63,26 +63,35 @@ __global__ void __launch_bounds__(256) maxpool2_planes_kernel(const __nv_bfloat1
   }
 }
 
-// x [b][C][HW] fp32 -> xp [2][b][HW][C_pad] bf16, zero in the pad channels.  32x32 (c, p) tiles through shared memory.
+// x [b][C][HW] fp32 -> xp [2][b][HW][C_pad] bf16, zero in the pad channels.  A block transposes a [64 ch][32 px] tile
+// through shared memory (coalesced row loads of the real channels only); every thread then emits 8 channels of one pixel as
+// one 16-byte store per plane.  C_pad must be a multiple of 8.
 __global__ void __launch_bounds__(256) pack_nhwc_padded_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ xp,
                                                                 int C, int C_pad, int HW, long long plane_stride) {
-  __shared__ float tile[32][33];
-  const int img = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  __shared__ float tile[64][33];
+  const int img = blockIdx.z, c0 = blockIdx.y * 64, p0 = blockIdx.x * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  for (int r = ty; r < 32; r += 8) {
+#pragma unroll
+  for (int r = ty; r < 64; r += 8) {
     const int c = c0 + r, pp = p0 + tx;
     tile[r][tx] = (c < C && pp < HW) ? x[((size_t)img * C + c) * HW + pp] : 0.f;
   }
   __syncthreads();
-  for (int r = ty; r < 32; r += 8) {
-    const int pp = p0 + r, c = c0 + tx;
-    if (pp < HW && c < C_pad) {
-      __nv_bfloat16 hi, lo;
-      split2(tile[tx][r], hi, lo);
-      const size_t o = ((size_t)img * HW + pp) * C_pad + c;
-      xp[o] = hi;
-      xp[o + plane_stride] = lo;
+  const int px = threadIdx.x >> 3, cg = threadIdx.x & 7;
+  const int pp = p0 + px, c = c0 + cg * 8;
+  if (pp < HW && c < C_pad) {
+    uint32_t hp[4], lp[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      __nv_bfloat16 h0, l0, h1, l1;
+      split2(tile[cg * 8 + 2 * j][px], h0, l0);
+      split2(tile[cg * 8 + 2 * j + 1][px], h1, l1);
+      hp[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+      lp[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
     }
+    __nv_bfloat16* dst = xp + ((size_t)img * HW + pp) * C_pad + c;
+    *reinterpret_cast<uint4*>(dst) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+    *reinterpret_cast<uint4*>(dst + plane_stride) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
   }
 }
 
@@ -160,9 +169,10 @@ extern "C" int ammc_maxpool2_planes(const void* in_planes, int in_cs, int in_c_o
 
 extern "C" int ammc_pack_nhwc_padded(const float* x, void* xp, int b, int C, int C_pad, int h, int w, void* stream) {
   AMMC_REQUIRE(x && xp && b > 0 && C > 0 && C_pad >= C && h > 0 && w > 0, "bad argument");
+  AMMC_REQUIRE(C_pad % 8 == 0, "C_pad must be a multiple of 8 (got %d)", C_pad);
   AMMC_REQUIRE(b <= 65535, "batch %d too large for one pack launch", b);
   const int HW = h * w;
-  pack_nhwc_padded_kernel<<<dim3(ceil_div(HW, 32), ceil_div(C_pad, 32), b), 256, 0, (cudaStream_t)stream>>>(
+  pack_nhwc_padded_kernel<<<dim3(ceil_div(HW, 32), ceil_div(C_pad, 64), b), 256, 0, (cudaStream_t)stream>>>(
       x, (__nv_bfloat16*)xp, C, C_pad, HW, (long long)b * HW * C_pad);
   AMMC_LAUNCH_CHECK("pack_nhwc_padded_kernel");
   return 0;
