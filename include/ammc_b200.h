@@ -290,6 +290,16 @@ int ammc_roc_auc(const float* scores, const int8_t* labels, int pos_label, doubl
 int ammc_preprocess_frames_u8(const uint8_t* frames_bgr, float* out, int n, int h0, int w0, int H, int W, void* stream);
 int ammc_preprocess_flow(const float* flow, float* out, int n, int h0, int w0, int H, int W, void* stream);
 
+/* ---- image-space generator losses (Code/models/losses/losses_utils.py:17-59,124-129) --------
+ * out2[0] = Intensity_Loss(l_num=2): mean over (b,h,w) of the channel-wise L2 norm of gen - gt;
+ * out2[1] = Gradient_Loss(alpha=1):  mean of |dx| + |dy| of the channel-summed difference (zero padding left / top).
+ * bwd: grad_gen = g_int * d out2[0]/d gen + g_gd * d out2[1]/d gen; g_int / g_gd are device scalars (either may be NULL). */
+size_t ammc_frame_losses_workspace_bytes(int n, int H, int W);
+int ammc_frame_losses_fwd(const float* gen, const float* gt, float* out2, void* workspace, size_t workspace_bytes, int n, int C,
+                          int H, int W, void* stream);
+int ammc_frame_losses_bwd(const float* gen, const float* gt, const float* g_int, const float* g_gd, float* grad_gen, int n,
+                          int C, int H, int W, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -371,6 +371,29 @@ def preprocess_flow(flow: np.ndarray, size=(256, 256)) -> np.ndarray:
     return np.stack([c0, c1]).astype(np.float32)
 
 
+# --------------------------------------------------------------------------------------------------
+# image-space generator losses (the part that needs no external weights)
+# --------------------------------------------------------------------------------------------------
+def intensity_loss(gen: torch.Tensor, gt: torch.Tensor) -> torch.Tensor:
+    """Intensity_Loss(l_num=2) -> L2, Code/models/losses/losses_utils.py:17-28,124-129: the L2 norm over the channel axis,
+    averaged over batch and pixels."""
+    return torch.norm(gen - gt, p=2, dim=1).mean()
+
+
+def gradient_loss(gen: torch.Tensor, gt: torch.Tensor, alpha: int = 1) -> torch.Tensor:
+    """Gradient_Loss, losses_utils.py:30-59: the [-1, 1] difference filters are [1, C, 1, 2] / [1, C, 2, 1] conv weights, i.e.
+    they SUM over the channels (one output channel); zero padding on the left / top; mean of |d_x|^a + |d_y|^a."""
+    C = gen.shape[1]
+    filt = torch.tensor([[-1.0, 1.0]], dtype=gen.dtype, device=gen.device)
+    fx = filt.view(1, 1, 1, 2).repeat(1, C, 1, 1)
+    fy = filt.view(1, 1, 2, 1).repeat(1, C, 1, 1)
+    gen_dx = F.conv2d(F.pad(gen, (1, 0, 0, 0)), fx)
+    gen_dy = F.conv2d(F.pad(gen, (0, 0, 1, 0)), fy)
+    gt_dx = F.conv2d(F.pad(gt, (1, 0, 0, 0)), fx)
+    gt_dy = F.conv2d(F.pad(gt, (0, 0, 1, 0)), fy)
+    return torch.mean(torch.abs(gt_dx - gen_dx) ** alpha + torch.abs(gt_dy - gen_dy) ** alpha)
+
+
 def path_forward(x_rgb, x_op, gen, gt, params: Dict[str, torch.Tensor], k: int):
     """The starred region of twostream.forward (Code/models/unet.py:985-994) followed by the per-frame rgb
     PSNR of test_helper.py:445-452.  `params` uses the reference state_dict key names

@@ -330,6 +330,48 @@ def gen_preprocess():
     _save("preprocess", dict(kind="preprocess", seed=20200525, cases=meta, cv2=cv2.__version__), **out)
 
 
+LOSS_CASES = {"loss_rgb_small": dict(b=2, C=3, h=16, w=20, seed=41), "loss_op_small": dict(b=3, C=2, h=9, w=7, seed=42),
+              "loss_rgb_256": dict(b=2, C=3, h=256, w=256, seed=43)}
+
+
+def gen_losses():
+    """Intensity_Loss / Gradient_Loss of the reference (losses_utils.py:17-59) with autograd gradients.  The module reads
+    the training configuration at import and moves its filters with .cuda(): a stub `const` and an identity Tensor.cuda
+    stand in for both here (the reference file itself is imported unmodified)."""
+    import types
+    ref_harness.import_reference()
+    stub = types.ModuleType("Code.main.constant_train")
+    stub.const = types.SimpleNamespace(gpu_idx="0")
+    sys.modules["Code.main.constant_train"] = stub
+    import Code.models.losses.losses_utils as LU
+    cuda_orig = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        out = {}
+        for name, c in LOSS_CASES.items():
+            gen_f, gt_f = synth.frames(c["seed"], c["b"], c["C"], c["h"], c["w"])
+            gen_f.requires_grad_(True)
+            li = LU.Intensity_Loss()(gen_f, gt_f)
+            lg = LU.Gradient_Loss(channels=c["C"])(gen_f, gt_f)
+            (gi,) = torch.autograd.grad(li, gen_f, retain_graph=True)
+            (gg,) = torch.autograd.grad(lg, gen_f)
+            g2 = gen_f.detach().clone().requires_grad_(True)
+            oi, og = O.intensity_loss(g2, gt_f), O.gradient_loss(g2, gt_f)
+            _close(oi, li, 1e-6, name + ".intensity")
+            _close(og, lg, 1e-6, name + ".gradient")
+            _close(torch.autograd.grad(oi, g2, retain_graph=True)[0], gi, 1e-6, name + ".d_intensity")
+            _close(torch.autograd.grad(og, g2)[0], gg, 1e-6, name + ".d_gradient")
+            out[name + "_int"], out[name + "_gd"] = li.detach(), lg.detach()
+            if c["h"] * c["w"] <= 1024:
+                out[name + "_g_int"], out[name + "_g_gd"] = gi, gg
+            else:                                                       # large case: gradients pinned by two projections
+                out[name + "_g_int_sum"] = (gi.double() * gt_f.double()).sum()
+                out[name + "_g_gd_sum"] = (gg.double() * gt_f.double()).sum()
+    finally:
+        torch.Tensor.cuda = cuda_orig
+    _save("losses", dict(kind="losses", cases=LOSS_CASES), **out)
+
+
 def main():
     torch.set_num_threads(os.cpu_count())
     ref_unet, ref_utils, ref_eval = ref_harness.import_reference()
@@ -340,6 +382,7 @@ def main():
     gen_records()
     gen_generator(ref_unet)
     gen_preprocess()
+    gen_losses()
     print("all fixtures written to", GOLD)
 
 

@@ -155,3 +155,22 @@ def test_preprocess_oracle_vs_reference_loaders():
         assert rgb.dtype == np.float32 and rgb.shape == (3, size[1], size[0]) and op.shape == (2, size[1], size[0])
         n += 1
     assert n == len(synth.PREPROCESS_CASES) == 8
+
+
+def test_frame_losses_oracle_vs_reference():
+    """Intensity_Loss / Gradient_Loss restatement (losses_utils.py:17-59) against the reference's values and autograd."""
+    c, g = load_golden("losses")
+    for name, cs in c["cases"].items():
+        gen, gt = synth.frames(cs["seed"], cs["b"], cs["C"], cs["h"], cs["w"])
+        gen.requires_grad_(True)
+        li, lg = O.intensity_loss(gen, gt), O.gradient_loss(gen, gt)
+        assert_close(li.detach(), g[name + "_int"], 1e-6, name + ".int")
+        assert_close(lg.detach(), g[name + "_gd"], 1e-6, name + ".gd")
+        gi = torch.autograd.grad(li, gen, retain_graph=True)[0]
+        gg = torch.autograd.grad(lg, gen)[0]
+        if name + "_g_int" in g:
+            assert_close(gi, g[name + "_g_int"], 1e-6, name + ".g_int")
+            assert_close(gg, g[name + "_g_gd"], 1e-6, name + ".g_gd")
+        else:
+            assert_close((gi.double() * gt.double()).sum(), g[name + "_g_int_sum"], 1e-6, name + ".g_int_sum")
+            assert_close((gg.double() * gt.double()).sum(), g[name + "_g_gd_sum"], 1e-6, name + ".g_gd_sum")
