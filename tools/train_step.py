@@ -45,7 +45,11 @@ def main():
     def step():
         opt.zero_grad(set_to_none=True)
         pr, po, (d_rgb, d_op), _ = g(rgb_in, op_in)
-        loss = (pr - rgb_tgt).pow(2).mean() + 2.0 * (po - op_tgt).abs().mean() + lam_latent * (d_rgb + d_op).sum()
+        # the reference's generator objective without the adversarial / FlowNet terms (loss_zoo.py:124-126, 190-192): intensity +
+        # gradient loss on the frame, intensity loss on the flow, commit terms -- the image-space losses from the fused kernels
+        l_int, l_gd = A.frame_losses(pr, rgb_tgt)
+        l_int_op, _ = A.frame_losses(po, op_tgt)
+        loss = l_int + l_gd + 2.0 * l_int_op + lam_latent * (d_rgb + d_op).sum()
         loss.backward()
         adist.allreduce_gradients(params)
         opt.step()
