@@ -589,7 +589,7 @@ static int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t
   return 0;
 }
 
-// Any element size (2 = bf16, 4 = fp32), with or without the 128B swizzle.
+// Any element size (1 = bytes / fp8, 2 = bf16 / fp16, 4 = fp32), with or without the 128B swizzle.
 int make_map_generic(CUtensorMap* m, const void* base, int elem_bytes, int rank, const uint64_t* dims,
                      const uint64_t* strides, const uint32_t* box, int swizzle128) {
   EncodeTiledFn fn = encode_fn();
@@ -598,7 +598,9 @@ int make_map_generic(CUtensorMap* m, const void* base, int elem_bytes, int rank,
   cuuint32_t bx[5], estr[5] = {1, 1, 1, 1, 1};
   for (int i = 0; i < rank; ++i) { d[i] = dims[i]; bx[i] = box[i]; }
   for (int i = 0; i + 1 < rank; ++i) s[i] = strides[i];
-  CUresult r = fn(m, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank,
+  const CUtensorMapDataType dt = elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                 : (elem_bytes == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+  CUresult r = fn(m, dt, (cuuint32_t)rank,
                   const_cast<void*>(base), d, s, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -43,6 +43,9 @@ int ammc_device_supported(void);
  * instead of hanging the GPU.  Returns 0 when no wait timed out since the last call, 1 with out4 = {kernel family
  * (1 conv, 2 addressing, 3 training), wait tag, block, thread} otherwise, negative on CUDA errors.  Synchronises. */
 int ammc_debug_timeout(int* out4);
+/* Debug aid: kind::f8f6f4 (e4m3) MMAs chained into kind::f16 MMAs through scale-input-d on one 128x64 tile (csrc/probes.cu):
+ * mode 0: out = (a8.b8^T) * 2^-12 + a16.b16^T; mode 1: out = a8.b8^T; mode 2: out = a16.b16^T. */
+int ammc_debug_fp8_probe(const void* a8, const void* b8, const void* a16, const void* b16, float* out, int mode, void* stream);
 /* Debug aid: UMMA K-major SWIZZLE_128B descriptor starting at an arbitrary 128-byte row (see csrc/halo_conv.cu) */
 int ammc_debug_desc_probe(const void* a, const void* b, float* out, int rows, int row_off, int base_off, void* stream);
 /* Debug aid: TMA-load one 5-D bf16 box (128B swizzle, zero OOB fill) and dump the raw shared-memory bytes to `out`. */
