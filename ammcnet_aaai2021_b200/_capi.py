@@ -31,6 +31,7 @@ SIGNATURES = {
     "ammc_last_error": (c_char_p, []),
     "ammc_device_supported": (I, []),
     "ammc_debug_timeout": (I, [P]),
+    "ammc_debug_mma_rate": (I, [P, I, I, I, P]),
     "ammc_debug_fp8_probe": (I, [P, P, P, P, P, I, P]),
     "ammc_debug_desc_probe": (I, [P, P, P, I, I, I, P]),
     "ammc_debug_tma_probe": (I, [P, P, P, P, P, P, I, P]),

@@ -94,6 +94,48 @@ __global__ void __launch_bounds__(128) fp8_probe_kernel(const __grid_constant__ 
   if (warp == 0) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem, 64); }
 }
 
+// MMA issue-to-retire rate of one SM: `iters` groups of 4 back-to-back MMAs (M = 128, N = n) on whatever bytes sit in
+// shared memory, kind::f16 (K = 16) or kind::f8f6f4 (K = 32); cycles[0] = clock64 ticks from first issue to commit arrival.
+__global__ void __launch_bounds__(128) mma_rate_kernel(long long* cycles, int fp8, int n, int iters) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* done = reinterpret_cast<uint64_t*>(smem + 49152);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(done + 1);
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x * 16; i < 49152; i += 128 * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0, 0, 0, 0);
+  ptx::fence_proxy_async();
+  if (threadIdx.x == 0) { ptx::mbar_init(done, 1); ptx::fence_mbar_init(); }
+  if (warp == 0) { ptx::tmem_alloc(slot, 256); ptx::tmem_relinquish(); }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *slot;
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = (1u << 4) | (fp8 ? 0u : ((1u << 7) | (1u << 10))) | (((uint32_t)n >> 3) << 17) | ((128u >> 4) << 24);
+    const uint64_t da = ptx::umma_desc_k_sw128(ptx::smem_u32(smem)), db = ptx::umma_desc_k_sw128(ptx::smem_u32(smem + 16384));
+    const uint32_t zero = 0;
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (fp8)
+          asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                       "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}" ::"r"(tmem),
+                       "l"(da + 2 * k), "l"(db + 2 * k), "r"(idesc), "r"(1u), "r"(zero), "r"(zero), "r"(zero), "r"(zero)
+                       : "memory");
+        else
+          ptx::mma_f16_ss(tmem, da + 2 * k, db + 2 * k, idesc, 1u);
+      }
+    }
+    ptx::mma_commit(done);
+    ptx::mbar_wait(done, 0, 94);
+    cycles[0] = clock64() - t0;
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem, 256); }
+}
+
 AMMC_DEFINE_TIMEOUT_READER(timeout_reader_probe)
 
 }  // namespace ammc
@@ -130,5 +172,15 @@ extern "C" int ammc_debug_fp8_probe(const void* a8, const void* b8, const void* 
   AMMC_CUDA_CHECK(cudaFuncSetAttribute(fp8_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   fp8_probe_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(mA8, mB8, mA16, mB16, out, mode);
   AMMC_LAUNCH_CHECK("fp8_probe_kernel");
+  return 0;
+}
+
+// cycles: device long long[1].  fp8 = 0: kind::f16 on bf16 (K = 16 per MMA); 1: kind::f8f6f4 on e4m3 (K = 32 per MMA).
+extern "C" int ammc_debug_mma_rate(long long* cycles, int fp8, int n, int iters, void* stream) {
+  AMMC_REQUIRE(cycles && (n == 64 || n == 128 || n == 256) && iters > 0 && iters <= 100000, "bad argument");
+  const int smem = 49152 + 256 + 1024;
+  AMMC_CUDA_CHECK(cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  mma_rate_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(cycles, fp8, n, iters);
+  AMMC_LAUNCH_CHECK("mma_rate_kernel");
   return 0;
 }

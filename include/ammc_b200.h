@@ -45,6 +45,9 @@ int ammc_device_supported(void);
 int ammc_debug_timeout(int* out4);
 /* Debug aid: kind::f8f6f4 (e4m3) MMAs chained into kind::f16 MMAs through scale-input-d on one 128x64 tile (csrc/probes.cu):
  * mode 0: out = (a8.b8^T) * 2^-12 + a16.b16^T; mode 1: out = a8.b8^T; mode 2: out = a16.b16^T. */
+/* Debug aid: clock64 ticks for `iters` x 4 back-to-back MMAs (M = 128, N = n) of kind::f16 / bf16 (fp8 = 0, K = 16) or
+ * kind::f8f6f4 / e4m3 (fp8 = 1, K = 32) on one SM. */
+int ammc_debug_mma_rate(long long* cycles, int fp8, int n, int iters, void* stream);
 int ammc_debug_fp8_probe(const void* a8, const void* b8, const void* a16, const void* b16, float* out, int mode, void* stream);
 /* Debug aid: UMMA K-major SWIZZLE_128B descriptor starting at an arbitrary 128-byte row (see csrc/halo_conv.cu) */
 int ammc_debug_desc_probe(const void* a, const void* b, float* out, int rows, int row_off, int base_off, void* stream);

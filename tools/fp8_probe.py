@@ -24,3 +24,15 @@ for mode in (2, 1, 0):
     o = out.cpu()
     print(f"mode {mode} ({names[mode]}): exact = {bool(torch.equal(o, want[mode]))}, max abs diff = {float((o - want[mode]).abs().max()):.3e}", flush=True)
 check_pipeline_watchdog()
+
+# issue-to-retire rate of the two kinds on one SM (cycles per MMA; an fp8 MMA covers K = 32, a bf16 one K = 16)
+cyc = torch.zeros(1, dtype=torch.int64, device=dev)
+for n in (64, 128, 256):
+    row = {}
+    for fp8 in (0, 1):
+        for _ in range(2):
+            _capi.call("ammc_debug_mma_rate", P(cyc), fp8, n, 2000, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+            torch.cuda.synchronize()
+        row["e4m3 K=32" if fp8 else "bf16 K=16"] = round(int(cyc.item()) / 8000.0, 1)
+    print(f"M=128 N={n}: clock64 ticks per MMA {row}", flush=True)
+check_pipeline_watchdog()
