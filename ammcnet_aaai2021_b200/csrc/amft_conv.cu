@@ -15,8 +15,12 @@
 //                  accumulator -> ~2^-17 relative error, the fp32-parity mode.
 //   epilogue       TMEM -> registers (tcgen05.ld 32x32b), y = relu(acc*scale[c] + shift[c]) and either
 //                  (a) NHWC bf16 hi/lo planes (the next conv's A operand) or (b) + residual -> NCHW fp32.
-//   roles          warp 0 lane 0: TMA producer; warp 1 lane 0: MMA issuer (warp 1 owns TMEM alloc/dealloc);
-//                  warps 2-5: epilogue (one TMEM lane quarter each).  Persistent over tiles, one CTA per SM.
+//   roles          warp 0 lane 0: TMA producer; warp 1: MMA issuer (the warp runs converged, one elected lane issues;
+//                  it also owns TMEM alloc/dealloc); warps 2-5: epilogue (one TMEM lane quarter each, bf16 planes stored
+//                  with 256-bit st.global.v8).  Persistent over tiles, one CTA per SM.
+//   general form   ammc_conv_layer (include/ammc_b200.h): channel windows on both sides, rows wider than 128 pixels,
+//                  transposed 2x2 conv as a scattering epilogue, zero-padded channel counts, tanh; wide shallow layers are
+//                  routed to halo_conv.cu.
 #include "common.cuh"
 #include "ptx.cuh"
 #include <cuda_bf16.h>

@@ -14,7 +14,9 @@
 //        (dec is linear and the read is a concatenation of bank rows, so dec(read_n) is a sum of k rows of
 //         the precomputed tables: the N x kD x C contraction becomes a gather)
 //   sse_frame_kernel / diff_kernel            deterministic per-frame and global commit reductions (unet.py:310)
-//   backward: gz_kernel, gx_kernel, genc_w_kernel, gdec_scatter_kernel, gdec_w_kernel
+//   backward: gz_kernel, then on tcgen05 when D, C % 64 == 0 (1x1 conv engine for the input gradient, weight-gradient
+//             kernel of amft_train.cu for both weight gradients; pack_nhwc64 / read_planes / channel_sum prepare operands),
+//             else gx_kernel, genc_w_kernel, gdec_scatter_priv_kernel (gdec_scatter_kernel for huge banks), gdec_w_kernel
 //   ema_*                                     unet.py:298-309
 #include "common.cuh"
 #include "topk.cuh"
