@@ -22,7 +22,7 @@ class ConvLayer(ctypes.Structure):
                 ("out_planes", c_void_p), ("out_cs", c_int), ("out_c_off", c_int),
                 ("out_nchw", c_void_p), ("res_nchw", c_void_p), ("cout_valid", c_int),
                 ("b", c_int), ("h", c_int), ("w", c_int), ("Cin", c_int), ("Cout", c_int),
-                ("up2x", c_int), ("precision", c_int)]
+                ("up2x", c_int), ("precision", c_int), ("in_fmt", c_int), ("out_fmt", c_int)]
 
 
 # name -> (restype, argtypes); must list every symbol of include/ammc_b200.h (tests/test_capi.py checks it)
@@ -37,7 +37,7 @@ SIGNATURES = {
     "ammc_debug_tma_probe": (I, [P, P, P, P, P, P, I, P]),
     "ammc_mem_workspace_bytes": (Z, [I] * 7),
     "ammc_set_addressing_mode": (I, [I]),
-    "ammc_mem_fwd": (I, [P] * 6 + [P] * 6 + [P, P, P] + [P, Z] + [I] * 8 + [P]),
+    "ammc_mem_fwd": (I, [P] * 6 + [P] * 6 + [P, P, P, I] + [P, Z] + [I] * 8 + [P]),
     "ammc_mem_dec_uses_tensor": (I, [I] * 7),
     "ammc_set_dec_mode": (I, [I]),
     "ammc_set_enc_mode": (I, [I]),
@@ -55,6 +55,10 @@ SIGNATURES = {
     "ammc_mem_bwd": (I, [P] * 8 + [P] * 5 + [P, Z] + [I] * 8 + [P]),
     "ammc_pack_conv_weights": (I, [P, P, I, I, P]),
     "ammc_pack_nhwc": (I, [P, P, I, I, I, I, P]),
+    "ammc_q_act_bytes": (Z, [L]),
+    "ammc_q_weight_bytes": (Z, [I, I]),
+    "ammc_pack_nhwc_q": (I, [P, P, I, I, I, I, P]),
+    "ammc_pack_conv_weights_q": (I, [P, P, I, I, I, P]),
     "ammc_conv3x3_bn_relu": (I, [P] * 7 + [I] * 7 + [P]),
     "ammc_conv_layer_run": (I, [ctypes.POINTER(ConvLayer), P]),
     "ammc_pack_conv_weights_padded": (I, [P, P, I, I, I, I, I, P]),

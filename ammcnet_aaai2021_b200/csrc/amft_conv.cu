@@ -24,6 +24,7 @@
 #include "common.cuh"
 #include "ptx.cuh"
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 namespace ammc {
 
@@ -48,6 +49,14 @@ struct ConvParams {
   float* out_nchw;               // [b][cout_valid][H][W] or null
   const float* res_nchw;         // same shape or null
   int cout_valid;                // channels of out_nchw / res_nchw (< Cout when the weights were zero-padded)
+  // mixed fp16 + e4m3 operand format "q" (pair kernel only; ptx.cuh split_pack_q)
+  int out_fmt;                   // 0: out_planes are bf16 hi/lo planes; 1: q planes (out_q16 / out_q8)
+  __half* out_q16;               // [b][H][W][Cout] fp16
+  uint8_t* out_q8;               // [2][b][H][W][Cout] e4m3 (h8, l8)
+  long long out_q8_stride;       // bytes between the h8 and l8 plane
+  const float* out_qs;           // device scalar: power-of-two scale of the q output
+  const float* in_qs;            // device scalars: scales of the q input and the q weights (PAIR_Q mode), else null
+  const float* w_qs;
 };
 
 // m-tile index -> first image / row / column of its TMA box
@@ -276,22 +285,32 @@ constexpr int PAIR_TILE_BYTES = A_BYTES + PAIR_B_BYTES;        // one (A, B-half
 constexpr int PAIR_RING_BYTES = 6 * PAIR_TILE_BYTES;           // 192 KB: 6 stages of 32 KB, or 3 fused stages of 64 KB
 constexpr int PAIR_BAR_OFFSET = PAIR_RING_BYTES;
 constexpr int PAIR_SMEM = PAIR_BAR_OFFSET + 256 + 1024;
-// FUSED3 (precision 3): a stage holds the hi AND lo planes of both operands, loaded once and used by the three MMA
+// PAIR_FUSED3 (precision 3): a stage holds the hi AND lo planes of both operands, loaded once and used by the three MMA
 // groups hi*hi, hi*lo, lo*hi -> one third less L2->smem traffic than streaming the K loop three times.
-template <bool FUSED3> struct PairCfg {
-  static constexpr int PLANES = FUSED3 ? 2 : 1;
+// PAIR_Q (precision 2): mixed fp16 + e4m3 operands, two pass-equivalents instead of three.  The K loop runs twice per tile
+// over 128-channel blocks of 64 KB stages: phase 0 streams the e4m3 planes [A_h8 | A_l8 | B_h8 | B_l8] and issues the
+// cross terms h8.l8 + l8.h8 as kind::f8f6f4 MMAs (K = 32 each: twice the MACs per tensor-core cycle), phase 1 streams
+// the fp16 planes [A_0 | A_1 | B_0 | B_1] (two 64-channel halves) and issues h16.h16; the first fp16 MMA rescales the
+// cross-term sum by 2^-4 through scale-input-d, so one TMEM accumulator holds the whole product.  Each plane is read
+// from L2 exactly once.
+enum { PAIR_STREAM = 0, PAIR_FUSED3 = 1, PAIR_Q = 2 };
+template <int MODE> struct PairCfg {
+  static constexpr int PLANES = MODE == PAIR_STREAM ? 1 : 2;
   static constexpr int STAGE_BYTES = PLANES * PAIR_TILE_BYTES;
   static constexpr int STAGES = PAIR_RING_BYTES / STAGE_BYTES;
 };
 constexpr int PAIR_EPI_WARPS = 8;
 constexpr int PAIR_THREADS = 64 + 32 * PAIR_EPI_WARPS;    // warp 0: TMA, warp 1: MMA, warps 2-9: epilogue
 
-template <bool FUSED3>
+template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1)
-conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
+conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                       const __grid_constant__ CUtensorMap tmA8, const __grid_constant__ CUtensorMap tmB8, const ConvParams p) {
+  constexpr bool FUSED3 = MODE == PAIR_FUSED3;
+  constexpr bool QMODE = MODE == PAIR_Q;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  using Cfg = PairCfg<FUSED3>;
+  using Cfg = PairCfg<MODE>;
   constexpr int PAIR_STAGES = Cfg::STAGES;
   constexpr int PAIR_STAGE_BYTES = Cfg::STAGE_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + PAIR_BAR_OFFSET);
@@ -306,11 +325,13 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   const int pair_tiles_m = (p.tiles_m + 1) >> 1;
   const int num_tiles = pair_tiles_m * p.tiles_n;
   const int kb_per_pass = p.ntaps * (p.Cin / BLOCK_K);
-  const int kb_total = FUSED3 ? kb_per_pass : kb_per_pass * p.n_pass;
+  const int kb_q = p.ntaps * (p.Cin / 128);                  // PAIR_Q: 128-channel blocks, walked twice (e4m3, fp16)
+  const int kb_total = QMODE ? 2 * kb_q : (FUSED3 ? kb_per_pass : kb_per_pass * p.n_pass);
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmA);
     ptx::prefetch_tensormap(&tmB);
+    if (QMODE) { ptx::prefetch_tensormap(&tmA8); ptx::prefetch_tensormap(&tmB8); }
     for (int s = 0; s < PAIR_STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
     for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tmem_full[a], 1); ptx::mbar_init(&tmem_empty[a], 2 * 32 * PAIR_EPI_WARPS); }
     ptx::fence_mbar_init();
@@ -333,6 +354,32 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         int img0, h0, w0;
         tile_origin(mt, p.groups_w, p.groups_h, p.W_box, p.H_box, p.B_box, img0, h0, w0);
         const int n0 = nt * PAIR_N + (int)rank * (PAIR_N / 2);
+        if (QMODE) {
+          for (int phase = 0; phase < 2; ++phase) {
+            for (int tap = 0; tap < p.ntaps; ++tap) {
+              const int dy = p.ntaps == 9 ? tap / 3 - 1 : 0, dx = p.ntaps == 9 ? tap % 3 - 1 : 0;
+              for (int cc = 0; cc < p.Cin / 128; ++cc) {
+                ptx::mbar_wait(&empty_bar[s], ph ^ 1, 41);
+                if (rank == 0) ptx::mbar_expect_tx(&full_bar[s], 2 * 2 * (p.rows_valid * 128 + PAIR_B_BYTES));
+                uint8_t* a_dst = smem + s * PAIR_STAGE_BYTES;
+                const int c0 = cc * 128, k0 = tap * p.Cin + cc * 128;
+                if (phase == 0) {                       // [A_h8 | A_l8 | B_h8 | B_l8]: 128 rows x 128 e4m3 each
+                  ptx::tma_load_5d_2sm(a_dst, &tmA8, &full_bar[s], c0, w0 + dx, h0 + dy, img0, 0);
+                  ptx::tma_load_5d_2sm(a_dst + A_BYTES, &tmA8, &full_bar[s], c0, w0 + dx, h0 + dy, img0, 1);
+                  ptx::tma_load_3d_2sm(a_dst + 2 * A_BYTES, &tmB8, &full_bar[s], k0, n0, 0);
+                  ptx::tma_load_3d_2sm(a_dst + 2 * A_BYTES + PAIR_B_BYTES, &tmB8, &full_bar[s], k0, n0, 1);
+                } else {                                // [A_0 | A_1 | B_0 | B_1]: two 64-channel fp16 halves
+                  ptx::tma_load_5d_2sm(a_dst, &tmA, &full_bar[s], c0, w0 + dx, h0 + dy, img0, 0);
+                  ptx::tma_load_5d_2sm(a_dst + A_BYTES, &tmA, &full_bar[s], c0 + 64, w0 + dx, h0 + dy, img0, 0);
+                  ptx::tma_load_3d_2sm(a_dst + 2 * A_BYTES, &tmB, &full_bar[s], k0, n0, 0);
+                  ptx::tma_load_3d_2sm(a_dst + 2 * A_BYTES + PAIR_B_BYTES, &tmB, &full_bar[s], k0 + 64, n0, 0);
+                }
+                if (++s == PAIR_STAGES) { s = 0; ph ^= 1; }
+              }
+            }
+          }
+          continue;
+        }
         for (int ps = 0; ps < (FUSED3 ? 1 : p.n_pass); ++ps) {
           const int pa = ps == 2 ? 1 : 0, pb = ps == 1 ? 1 : 0;   // (hi,hi) (hi,lo) (lo,hi)
           for (int tap = 0; tap < p.ntaps; ++tap) {
@@ -374,6 +421,30 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           ptx::mbar_wait(&full_bar[s], ph, 43);
           ptx::tc_fence_after();
           const uint32_t a_addr = ptx::smem_u32(smem + s * PAIR_STAGE_BYTES);
+          if (QMODE) {
+            constexpr uint32_t idesc_q = ptx::umma_idesc(0, 2 * BLOCK_M, PAIR_N);    // format 0 = F16 resp. E4M3
+            const uint64_t a0 = ptx::umma_desc_k_sw128(a_addr), a1 = ptx::umma_desc_k_sw128(a_addr + A_BYTES);
+            const uint64_t b0 = ptx::umma_desc_k_sw128(a_addr + 2 * A_BYTES);
+            const uint64_t b1 = ptx::umma_desc_k_sw128(a_addr + 2 * A_BYTES + PAIR_B_BYTES);
+            if (kb < kb_q) {                            // cross terms: h8.l8 + l8.h8, four K = 32 steps per 128-byte row
+#pragma unroll
+              for (int k4 = 0; k4 < 4; ++k4) {
+                ptx::mma_f8_ss_2sm(d_tmem, a0 + 2 * k4, b1 + 2 * k4, idesc_q, (kb | k4) != 0 ? 1u : 0u);
+                ptx::mma_f8_ss_2sm(d_tmem, a1 + 2 * k4, b0 + 2 * k4, idesc_q, 1u);
+              }
+            } else {                                    // main product; its first MMA folds the cross terms in (x 2^-4)
+              if (kb == kb_q) ptx::mma_f16_ss_2sm_scaled<ptx::Q_SHIFT>(d_tmem, a0, b0, idesc_q);
+              else ptx::mma_f16_ss_2sm(d_tmem, a0, b0, idesc_q, 1u);
+#pragma unroll
+              for (int k4 = 1; k4 < 4; ++k4) ptx::mma_f16_ss_2sm(d_tmem, a0 + 2 * k4, b0 + 2 * k4, idesc_q, 1u);
+#pragma unroll
+              for (int k4 = 0; k4 < 4; ++k4) ptx::mma_f16_ss_2sm(d_tmem, a1 + 2 * k4, b1 + 2 * k4, idesc_q, 1u);
+            }
+            ptx::mma_commit_2sm(&empty_bar[s], 3);
+            if (kb == kb_total - 1) ptx::mma_commit_2sm(&tmem_full[acc], 3);
+            if (++s == PAIR_STAGES) { s = 0; ph ^= 1; }
+            continue;
+          }
           const uint64_t adesc = ptx::umma_desc_k_sw128(a_addr);
           const uint64_t bdesc = ptx::umma_desc_k_sw128(a_addr + A_BYTES);
           if (FUSED3) {
@@ -427,6 +498,11 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       const bool planes32 = ((reinterpret_cast<uintptr_t>(oplane) | (uintptr_t)(p.out_plane_stride * 2)) & 31) == 0;
       const size_t obase = ((size_t)img * p.Cout + n0) * hw + (size_t)hh * p.W + ww;
       const bool has_res = valid && p.res_nchw != nullptr;
+      // q operands carry power-of-two scales: the accumulator holds (x.w) * s16x * s16w
+      const float acc_inv = QMODE ? 1.f / (__ldg(p.in_qs) * __ldg(p.w_qs)) : 1.f;
+      const float oq = p.out_fmt == 1 ? __ldg(p.out_qs) : 1.f;
+      __half* const oq16 = p.out_q16 + opix * p.out_cs + p.out_c_off;
+      uint8_t* const oq8 = p.out_q8 + opix * p.out_cs + p.out_c_off;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * PAIR_N + half * HALF_N;
       // 16 columns at a time, software-pipelined two chunks deep: the residual loads of chunks c+1 and c+2 are in
       // flight while chunk c is converted and stored (the loads are the only latency on the epilogue's critical path)
@@ -457,7 +533,7 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, shv[4] = {sh.x, sh.y, sh.z, sh.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              float a = fmaf(__uint_as_float(v[4 * g4 + j]), scv[j], shv[j]);
+              float a = fmaf(QMODE ? __uint_as_float(v[4 * g4 + j]) * acc_inv : __uint_as_float(v[4 * g4 + j]), scv[j], shv[j]);
               a = p.act ? fmaxf(a, 0.f) : a;
               v[4 * g4 + j] = __float_as_uint(has_res ? a + rv[4 * g4 + j] : a);
             }
@@ -473,7 +549,18 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 #pragma unroll
               for (int j = 0; j < 16; ++j) { p.out_nchw[o] = __uint_as_float(v[j]); o += hw; }
             }
-            if (p.out_planes) {
+            if (p.out_fmt == 1) {
+              // q planes: 16 channels = 32 B of fp16 + 16 B of h8 + 16 B of l8
+              uint32_t h16[8], h8[8], l8[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                ptx::split_pack_q(__uint_as_float(v[2 * j]) * oq, __uint_as_float(v[2 * j + 1]) * oq, h16[j], h8[j], l8[j]);
+              ptx::stg_v8(oq16 + cbase, h16);
+              *reinterpret_cast<uint4*>(oq8 + cbase) =
+                  make_uint4(h8[0] | (h8[1] << 16), h8[2] | (h8[3] << 16), h8[4] | (h8[5] << 16), h8[6] | (h8[7] << 16));
+              *reinterpret_cast<uint4*>(oq8 + p.out_q8_stride + cbase) =
+                  make_uint4(l8[0] | (l8[1] << 16), l8[2] | (l8[3] << 16), l8[4] | (l8[5] << 16), l8[6] | (l8[7] << 16));
+            } else if (p.out_planes) {
               __nv_bfloat16* hi = oplane + cbase;
               __nv_bfloat16* lo = hi + p.out_plane_stride;
               uint32_t hp[8], lp[8];
@@ -560,6 +647,98 @@ __global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __r
   float s = gamma[c] / sqrtf(var[c] + eps);
   scale[c] = s;
   shift[c] = beta[c] - mean[c] * s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// q-format (fp16 + e4m3) packers and scales.  Buffer layouts (n = element count):
+//   activations  [n fp16][n e4m3 h8][n e4m3 l8][float s16 @ 4n]                     NHWC, 4n + 16 bytes
+//   weights      [n fp16][n h8][n l8][Cout floats: sum_k |w_ck| @ 4n][float s16 @ 4n + 4 Cout]   4n + 4 Cout + 16 bytes
+// ------------------------------------------------------------------------------------------------
+// max |x| as the bit pattern of a non-negative float (monotone under unsigned compare); *out must be zeroed first
+__global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ x, long long n, unsigned* __restrict__ out) {
+  float m = 0.f;
+  const long long n4 = n >> 2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+    m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+  }
+  if (blockIdx.x == 0)
+    for (long long i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, fabsf(x[i]));
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));
+}
+__global__ void qscale_from_absmax_kernel(const unsigned* __restrict__ amax_bits, float* __restrict__ qs) {
+  if (threadIdx.x == 0) qs[0] = q_scale_for_bound(__uint_as_float(amax_bits[0]));
+}
+// scale of a conv output written as q planes: bound_c = |scale_c| * L1_c * X + |shift_c|, X = 2^15 / s16(input) >= max|x|
+__global__ void __launch_bounds__(256) qscale_conv_out_kernel(const float* __restrict__ l1, const float* __restrict__ scale,
+                                                              const float* __restrict__ shift, const float* __restrict__ in_qs,
+                                                              int Cout, float* __restrict__ out_qs) {
+  __shared__ float red[8];
+  const float X = 32768.f / in_qs[0];
+  float m = 0.f;
+  for (int c = threadIdx.x; c < Cout; c += blockDim.x) m = fmaxf(m, fabsf(scale[c]) * l1[c] * X * 1.01f + fabsf(shift[c]));
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+    out_qs[0] = q_scale_for_bound(m);
+  }
+}
+// weights: one block per output channel; w [Cout][Cin][taps] -> q planes with k = tap*Cin + cin, L1 row sums
+__global__ void __launch_bounds__(256) pack_weights_q_kernel(const float* __restrict__ w, uint8_t* __restrict__ wq, int Cout,
+                                                             int Cin, int taps, const unsigned* __restrict__ amax_bits) {
+  __shared__ float red[33];
+  const int co = blockIdx.x;
+  const long long K = (long long)taps * Cin, n = (long long)Cout * K;
+  // weights sit with their maximum in (2^7, 2^8]: fp16 and e4m3 planes share one scale (no 2^-7 between them)
+  const float s = q_scale_for_bound(__uint_as_float(amax_bits[0])) * 0.0078125f;
+  __half* w16 = reinterpret_cast<__half*>(wq);
+  uint8_t* h8 = wq + 2 * n;
+  uint8_t* l8 = wq + 3 * n;
+  float l1 = 0.f;
+  for (long long e = threadIdx.x; e < K; e += blockDim.x) {
+    const int cin = (int)(e % Cin), tap = (int)(e / Cin);
+    const float v = w[((size_t)co * Cin + cin) * taps + tap];
+    l1 += fabsf(v);
+    const float t = v * s;
+    const __half hh = __float2half_rn(t);
+    w16[co * K + e] = hh;
+    h8[co * K + e] = (uint8_t)(ptx::pack_e4m3x2(t, 0.f) & 0xff);
+    l8[co * K + e] = (uint8_t)(ptx::pack_e4m3x2((t - __half2float(hh)) * 2048.f, 0.f) & 0xff);
+  }
+  l1 = block_sum(l1, red);
+  if (threadIdx.x == 0) {
+    reinterpret_cast<float*>(wq + 4 * n)[co] = l1;
+    if (co == 0) reinterpret_cast<float*>(wq + 4 * n + 4 * (long long)Cout)[0] = s;
+  }
+}
+// activations: x [b][C][HW] fp32 -> q planes [b][HW][C]; 32 x 32 (channel, pixel) tiles through shared memory
+__global__ void __launch_bounds__(256) pack_nhwc_q_kernel(const float* __restrict__ x, uint8_t* __restrict__ xq, int C, int HW,
+                                                          long long n, const float* __restrict__ qs) {
+  __shared__ float tile[32][33];
+  const int img = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const float s = qs[0];
+  for (int r = ty; r < 32; r += 8) {
+    const int c = c0 + r, pp = p0 + tx;
+    tile[r][tx] = (c < C && pp < HW) ? x[((size_t)img * C + c) * HW + pp] : 0.f;
+  }
+  __syncthreads();
+  __half* x16 = reinterpret_cast<__half*>(xq);
+  for (int r = ty; r < 32; r += 8) {
+    const int pp = p0 + r, c = c0 + tx;
+    if (pp < HW && c < C) {
+      const float t = tile[tx][r] * s;
+      uint32_t h16, h8, l8;
+      ptx::split_pack_q(t, 0.f, h16, h8, l8);
+      const size_t o = ((size_t)img * HW + pp) * C + c;
+      x16[o] = __ushort_as_half((unsigned short)(h16 & 0xffff));
+      xq[2 * n + o] = (uint8_t)(h8 & 0xff);
+      xq[3 * n + o] = (uint8_t)(l8 & 0xff);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -671,7 +850,10 @@ int conv_run(const ammc_conv_layer& L, cudaStream_t st) {
   AMMC_REQUIRE(L.in_planes && L.wp && L.scale && L.shift && (L.out_planes || L.out_nchw), "null pointer argument");
   AMMC_REQUIRE(b > 0 && h > 0 && w > 0, "bad shape b=%d h=%d w=%d", b, h, w);
   AMMC_REQUIRE(ntaps == 9 || ntaps == 1, "taps must be 9 (3x3) or 1 (1x1), got %d", ntaps);
-  if (L.precision != 1 && L.precision != 3) return fail(AMMC_EINVAL, "precision must be 1 or 3 (got %d)", L.precision);
+  if (L.precision < 1 || L.precision > 3) return fail(AMMC_EINVAL, "precision must be 1, 2 or 3 (got %d)", L.precision);
+  AMMC_REQUIRE(L.in_fmt == (L.precision == 2 ? 1 : 0), "precision 2 takes q-format operands (in_fmt = 1), 1 and 3 take "
+               "bf16 hi/lo planes (in_fmt = 0); got precision %d, in_fmt %d", L.precision, L.in_fmt);
+  AMMC_REQUIRE(L.out_fmt == 0 || L.out_fmt == 1, "out_fmt must be 0 (bf16 hi/lo planes) or 1 (q planes)");
   if (Cin % 64 != 0 || Cout % 64 != 0)
     return fail(AMMC_EUNSUPPORTED, "tcgen05 conv needs Cin and Cout multiples of 64 (got %d, %d)", Cin, Cout);
   const int in_cs = L.in_cs > 0 ? L.in_cs : Cin;
@@ -692,7 +874,7 @@ int conv_run(const ammc_conv_layer& L, cudaStream_t st) {
                                  L.out_c_off + (L.up2x ? up_cout : cout_valid) <= out_cs),
                "output channel window does not fit a %d-channel buffer (8-channel alignment)", out_cs);
   AMMC_REQUIRE(!L.out_planes || cout_valid == Cout, "NHWC plane output needs cout_valid == Cout");
-  if (halo_conv_applies(L)) return halo_conv_run(L, st);     // wide, shallow layers: tap operands from one halo tile
+  if (L.precision != 2 && L.out_fmt == 0 && halo_conv_applies(L)) return halo_conv_run(L, st);   // wide, shallow layers
   ConvParams p;
   p.b = b; p.H = h; p.W = w; p.Cin = Cin; p.Cout = Cout;
   // one TMA box = W_box x H_box x B_box pixels <= 128: whole rows, as many as fit; whole images when a full image
@@ -717,9 +899,55 @@ int conv_run(const ammc_conv_layer& L, cudaStream_t st) {
   p.out_nchw = L.out_nchw;
   p.res_nchw = L.res_nchw;
   p.cout_valid = cout_valid;
+  p.out_fmt = 0; p.out_q16 = nullptr; p.out_q8 = nullptr; p.out_q8_stride = 0; p.out_qs = nullptr;
+  p.in_qs = nullptr; p.w_qs = nullptr;
+  const bool qmode = L.precision == 2;
+  const long long n_out = (long long)b * h * w * out_cs, n_in = (long long)b * h * w * in_cs, n_w = (long long)Cout * ntaps * Cin;
+  if (L.out_fmt == 1) {
+    AMMC_REQUIRE(L.out_planes && !L.up2x && out_cs % 16 == 0 && L.out_c_off % 16 == 0 && cout_valid == Cout,
+                 "q-format output needs a plain conv writing 16-channel aligned windows");
+    p.out_fmt = 1;
+    p.out_planes = nullptr;
+    p.out_q16 = (__half*)L.out_planes;
+    p.out_q8 = (uint8_t*)L.out_planes + 2 * n_out;
+    p.out_q8_stride = n_out;
+    p.out_qs = (const float*)((const uint8_t*)L.out_planes + 4 * n_out);
+  }
+  if (qmode) {
+    AMMC_REQUIRE(Cin % 128 == 0 && Cout % 256 == 0 && !L.up2x && L.act != 2 && cout_valid == Cout && in_cs == Cin,
+                 "precision 2 (fp16 + e4m3) needs Cin %% 128 == 0, Cout %% 256 == 0, dense input planes, act 0/1 (got Cin=%d Cout=%d)",
+                 Cin, Cout);
+    p.in_qs = (const float*)((const uint8_t*)L.in_planes + 4 * n_in);
+    p.w_qs = (const float*)((const uint8_t*)L.wp + 4 * n_w + 4 * (long long)Cout);
+    if (L.out_fmt == 1) {
+      // scale of the q output from a rigorous bound: |y_c| <= |scale_c| * sum_k |w_ck| * max|x| + |shift_c|
+      qscale_conv_out_kernel<<<1, 256, 0, st>>>((const float*)((const uint8_t*)L.wp + 4 * n_w), L.scale, L.shift, p.in_qs,
+                                                Cout, const_cast<float*>(p.out_qs));
+      AMMC_LAUNCH_CHECK("qscale_conv_out_kernel");
+    }
+  }
 
-  CUtensorMap tmA, tmB;
-  {
+  CUtensorMap tmA, tmB, tmA8, tmB8;
+  if (qmode) {
+    // fp16 plane (one plane, 64-channel boxes) and the two e4m3 planes (128-channel boxes = 128-byte rows)
+    uint64_t dims[5] = {(uint64_t)Cin, (uint64_t)w, (uint64_t)h, (uint64_t)b, 1};
+    uint64_t st16[4] = {(uint64_t)Cin * 2, (uint64_t)w * Cin * 2, (uint64_t)h * w * Cin * 2, (uint64_t)b * h * w * Cin * 2};
+    uint32_t box16[5] = {64, (uint32_t)p.W_box, (uint32_t)p.H_box, (uint32_t)p.B_box, 1};
+    if (int rc = make_map_generic(&tmA, L.in_planes, 2, 5, dims, st16, box16, 1)) return rc;
+    dims[4] = 2;
+    uint64_t st8[4] = {(uint64_t)Cin, (uint64_t)w * Cin, (uint64_t)h * w * Cin, (uint64_t)n_in};
+    uint32_t box8[5] = {128, (uint32_t)p.W_box, (uint32_t)p.H_box, (uint32_t)p.B_box, 1};
+    if (int rc = make_map_generic(&tmA8, (const uint8_t*)L.in_planes + 2 * n_in, 1, 5, dims, st8, box8, 1)) return rc;
+    const uint64_t K = (uint64_t)ntaps * Cin;
+    uint64_t wd[3] = {K, (uint64_t)Cout, 1}, ws16[2] = {K * 2, (uint64_t)Cout * K * 2};
+    uint32_t wb16[3] = {64, (uint32_t)(PAIR_N / 2), 1};
+    if (int rc = make_map_generic(&tmB, L.wp, 2, 3, wd, ws16, wb16, 1)) return rc;
+    wd[2] = 2;
+    uint64_t ws8[2] = {K, (uint64_t)Cout * K};
+    uint32_t wb8[3] = {128, (uint32_t)(PAIR_N / 2), 1};
+    if (int rc = make_map_generic(&tmB8, (const uint8_t*)L.wp + 2 * n_w, 1, 3, wd, ws8, wb8, 1)) return rc;
+  }
+  if (!qmode) {
     cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)b, 2};
     cuuint64_t strides[4] = {(cuuint64_t)in_cs * 2, (cuuint64_t)w * in_cs * 2, (cuuint64_t)h * w * in_cs * 2,
                              (cuuint64_t)b * h * w * in_cs * 2};
@@ -727,9 +955,10 @@ int conv_run(const ammc_conv_layer& L, cudaStream_t st) {
     if (int rc = make_map(&tmA, (const __nv_bfloat16*)L.in_planes + L.in_c_off, 5, dims, strides, box)) return rc;
   }
   // the pair epilogue maps each 128-column half to ONE (dy,dx) group of a transposed conv
-  const bool pair = block_n == 256 && g_conv_pair_mode && L.act != 2 && cout_valid == Cout &&
+  const bool pair = block_n == 256 && (g_conv_pair_mode || qmode || L.out_fmt == 1) && L.act != 2 && cout_valid == Cout &&
                     (!L.up2x || up_cout % 128 == 0);
-  {
+  AMMC_REQUIRE(pair || (!qmode && L.out_fmt == 0), "q-format operands need the CTA-pair kernel (Cout %% 256 == 0)");
+  if (!qmode) {
     // B boxes are per-CTA halves (128 channels) in the pair kernel
     const cuuint64_t K = (cuuint64_t)ntaps * Cin;
     cuuint64_t dims[3] = {K, (cuuint64_t)Cout, 2};
@@ -742,16 +971,19 @@ int conv_run(const ammc_conv_layer& L, cudaStream_t st) {
     int dev = 0;
     AMMC_CUDA_CHECK(cudaGetDevice(&dev));
     if (dev >= 0 && dev < 64 && !configured[dev]) {
-      AMMC_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM));
-      AMMC_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM));
+      AMMC_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_pair_kernel<PAIR_STREAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM));
+      AMMC_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_pair_kernel<PAIR_FUSED3>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM));
+      AMMC_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_pair_kernel<PAIR_Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM));
       configured[dev] = true;
     }
     const int pair_tiles = ((p.tiles_m + 1) / 2) * p.tiles_n;
     const int clusters = min(num_sms() / 2, pair_tiles);
-    if (L.precision == 3 && g_conv_fused3)
-      conv_igemm_pair_kernel<true><<<2 * clusters, PAIR_THREADS, PAIR_SMEM, st>>>(tmA, tmB, p);
+    if (qmode)
+      conv_igemm_pair_kernel<PAIR_Q><<<2 * clusters, PAIR_THREADS, PAIR_SMEM, st>>>(tmA, tmB, tmA8, tmB8, p);
+    else if (L.precision == 3 && g_conv_fused3)
+      conv_igemm_pair_kernel<PAIR_FUSED3><<<2 * clusters, PAIR_THREADS, PAIR_SMEM, st>>>(tmA, tmB, tmA, tmB, p);
     else
-      conv_igemm_pair_kernel<false><<<2 * clusters, PAIR_THREADS, PAIR_SMEM, st>>>(tmA, tmB, p);
+      conv_igemm_pair_kernel<PAIR_STREAM><<<2 * clusters, PAIR_THREADS, PAIR_SMEM, st>>>(tmA, tmB, tmA, tmB, p);
     AMMC_LAUNCH_CHECK("conv_igemm_pair_kernel");
     return 0;
   }
@@ -762,6 +994,13 @@ int conv_run(const ammc_conv_layer& L, cudaStream_t st) {
   }
 }
 
+int absmax_f32(const float* x, long long n, unsigned* out_bits, cudaStream_t st) {
+  AMMC_CUDA_CHECK(cudaMemsetAsync(out_bits, 0, 4, st));
+  absmax_kernel<<<min(ceil_div(n, 1024), 1184), 256, 0, st>>>(x, n, out_bits);
+  AMMC_LAUNCH_CHECK("absmax_kernel");
+  return 0;
+}
+
 // Shared by the plain 3x3 (ntaps = 9) and 1x1 (ntaps = 1) entry points.
 int conv_igemm(const void* xp, const void* wp, const float* scale, const float* shift, void* out_planes,
                float* out_nchw, const float* res_nchw, int b, int Cin, int Cout, int h, int w, int ntaps,
@@ -770,6 +1009,8 @@ int conv_igemm(const void* xp, const void* wp, const float* scale, const float* 
   L.in_planes = xp; L.wp = wp; L.taps = ntaps; L.scale = scale; L.shift = shift; L.act = relu ? 1 : 0;
   L.out_planes = out_planes; L.out_nchw = out_nchw; L.res_nchw = res_nchw;
   L.b = b; L.h = h; L.w = w; L.Cin = Cin; L.Cout = Cout; L.precision = precision;
+  L.in_fmt = precision == 2 ? 1 : 0;          // precision 2: q operands in, q planes out (the next conv's operand)
+  L.out_fmt = precision == 2 ? 1 : 0;
   return conv_run(L, st);
 }
 
@@ -782,6 +1023,38 @@ using namespace ammc;
 extern "C" int ammc_conv_layer_run(const ammc_conv_layer* layer, void* stream) {
   AMMC_REQUIRE(layer != nullptr, "null layer descriptor");
   return conv_run(*layer, (cudaStream_t)stream);
+}
+
+extern "C" size_t ammc_q_act_bytes(int64_t n) { return (size_t)(4 * n + 16); }
+extern "C" size_t ammc_q_weight_bytes(int Cout, int K) { return (size_t)(4 * (int64_t)Cout * K + 4 * (int64_t)Cout + 16); }
+
+extern "C" int ammc_pack_conv_weights_q(const float* w, void* wq, int Cout, int Cin, int taps, void* stream) {
+  AMMC_REQUIRE(w && wq && Cout > 0 && Cin > 0 && (taps == 9 || taps == 1), "bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long n = (long long)Cout * Cin * taps;
+  unsigned* amax = reinterpret_cast<unsigned*>((uint8_t*)wq + 4 * n + 4 * (long long)Cout + 4);   // scratch word of the tail
+  AMMC_CUDA_CHECK(cudaMemsetAsync(amax, 0, 4, st));
+  absmax_kernel<<<min(ceil_div(n, 1024), 1184), 256, 0, st>>>(w, n, amax);
+  AMMC_LAUNCH_CHECK("absmax_kernel");
+  pack_weights_q_kernel<<<Cout, 256, 0, st>>>(w, (uint8_t*)wq, Cout, Cin, taps, amax);
+  AMMC_LAUNCH_CHECK("pack_weights_q_kernel");
+  return 0;
+}
+
+extern "C" int ammc_pack_nhwc_q(const float* x, void* xq, int b, int C, int h, int w, void* stream) {
+  AMMC_REQUIRE(x && xq && b > 0 && C > 0 && h > 0 && w > 0 && b <= 65535, "bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long n = (long long)b * C * h * w;
+  float* qs = reinterpret_cast<float*>((uint8_t*)xq + 4 * n);
+  unsigned* amax = reinterpret_cast<unsigned*>(qs + 1);
+  AMMC_CUDA_CHECK(cudaMemsetAsync(amax, 0, 4, st));
+  absmax_kernel<<<min(ceil_div(n, 1024), 1184), 256, 0, st>>>(x, n, amax);
+  AMMC_LAUNCH_CHECK("absmax_kernel");
+  qscale_from_absmax_kernel<<<1, 32, 0, st>>>(amax, qs);
+  AMMC_LAUNCH_CHECK("qscale_from_absmax_kernel");
+  pack_nhwc_q_kernel<<<dim3(ceil_div(h * w, 32), ceil_div(C, 32), b), 256, 0, st>>>(x, (uint8_t*)xq, C, h * w, n, qs);
+  AMMC_LAUNCH_CHECK("pack_nhwc_q_kernel");
+  return 0;
 }
 
 extern "C" int ammc_set_conv_pair_mode(int on) {

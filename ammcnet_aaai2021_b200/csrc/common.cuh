@@ -54,6 +54,17 @@ struct Workspace {
 
 int num_sms();
 
+// largest power of two s with bound * s < 2^15 (s = 1 for bound == 0 or non-finite)
+__host__ __device__ __forceinline__ float q_scale_for_bound(float bound) {
+  if (!(bound > 0.f) || !(bound < 3.0e38f)) return 1.f;
+  int e;
+  frexpf(bound, &e);                 // bound = m * 2^e, m in [0.5, 1)
+  int se = 15 - e;
+  se = se > 100 ? 100 : (se < -100 ? -100 : se);
+  return ldexpf(1.f, se);
+}
+
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

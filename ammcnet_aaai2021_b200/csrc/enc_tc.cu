@@ -41,8 +41,10 @@ struct EncParams {
   float* z;                 // [N][64]
   __nv_bfloat16* zp;        // [N][64] or null
   float* znorm2;            // [N] or null
+  unsigned* amax_bits;      // AMAX: max |x| over the whole input as the bits of a non-negative float (atomicMax; zeroed by the host)
 };
 
+template <bool AMAX>
 __global__ void __launch_bounds__(ENC_THREADS, 1)
 enc_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, const EncParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -142,6 +144,7 @@ enc_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     const int c8_0 = ((warp - 2) >> 2) * (ENC_BK / 16);       // first 8-channel chunk of this warp's half
     int sx = 0; uint32_t phx = 0;
     int sa = 0; uint32_t pha = 0;
+    float amax = 0.f;                                         // AMAX: the values pass through registers here anyway
     for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
       for (int kb = 0; kb < kb_per_tile; ++kb) {
         ptx::mbar_wait(&x_full[sx], phx, 55);                 // fp32 staging landed
@@ -155,6 +158,10 @@ enc_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
           float v[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) v[j] = ptx::lds_f32(xs + (c8 * 8 + j) * 512);
+          if (AMAX) {
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) amax = fmaxf(amax, fmaxf(fabsf(v[j]), fabsf(v[j + 1])));
+          }
           uint32_t hp[4], lp[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -175,6 +182,10 @@ enc_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         if (++sx == ENC_X_STAGES) { sx = 0; phx ^= 1; }
         if (++sa == ENC_AW_STAGES) { sa = 0; pha ^= 1; }
       }
+    }
+    if (AMAX) {
+      amax = warp_max(amax);
+      if (lane == 0 && amax > 0.f) atomicMax(p.amax_bits, __float_as_uint(amax));
     }
   } else {
     // ---------------------------------------------------------------- epilogue: z, bf16(z), ||z||^2
@@ -240,7 +251,7 @@ size_t enc_tc_ws_bytes(int C) { return align_up((size_t)2 * ENC_D * C * 2, 256);
 
 // x [b][C][HW] fp32, enc_w [64][C] fp32 -> z [N][64] (+ zp, znorm2 when non-null).  wp_ws: enc_tc_ws_bytes(C).
 int run_enc_tc(const float* x, const float* enc_w, const float* enc_b, float* z, __nv_bfloat16* zp, float* znorm2,
-               void* wp_ws, int b, int HW, int C, cudaStream_t st) {
+               void* wp_ws, unsigned* amax_bits, int b, int HW, int C, cudaStream_t st) {
   if (int rc = pack_weights_1x1(enc_w, wp_ws, ENC_D, C, st)) return rc;
   CUtensorMap tmX, tmW;
   {
@@ -257,15 +268,21 @@ int run_enc_tc(const float* x, const float* enc_w, const float* enc_b, float* z,
   }
   EncParams p;
   p.N = b * HW; p.HW = HW; p.C = C; p.tiles = b * (HW / 128);
-  p.bias = enc_b; p.z = z; p.zp = zp; p.znorm2 = znorm2;
+  p.bias = enc_b; p.z = z; p.zp = zp; p.znorm2 = znorm2; p.amax_bits = amax_bits;
   static bool configured[64] = {false};
   int dev = 0;
   AMMC_CUDA_CHECK(cudaGetDevice(&dev));
   if (dev >= 0 && dev < 64 && !configured[dev]) {
-    AMMC_CUDA_CHECK(cudaFuncSetAttribute(enc_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ENC_SMEM));
+    AMMC_CUDA_CHECK(cudaFuncSetAttribute(enc_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ENC_SMEM));
+    AMMC_CUDA_CHECK(cudaFuncSetAttribute(enc_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ENC_SMEM));
     configured[dev] = true;
   }
-  enc_tc_kernel<<<min(num_sms(), p.tiles), ENC_THREADS, ENC_SMEM, st>>>(tmX, tmW, p);
+  if (amax_bits) {
+    AMMC_CUDA_CHECK(cudaMemsetAsync(amax_bits, 0, 4, st));
+    enc_tc_kernel<true><<<min(num_sms(), p.tiles), ENC_THREADS, ENC_SMEM, st>>>(tmX, tmW, p);
+  } else {
+    enc_tc_kernel<false><<<min(num_sms(), p.tiles), ENC_THREADS, ENC_SMEM, st>>>(tmX, tmW, p);
+  }
   AMMC_LAUNCH_CHECK("enc_tc_kernel");
   return 0;
 }

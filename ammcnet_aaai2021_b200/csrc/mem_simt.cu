@@ -730,7 +730,7 @@ int run_address_tc(const float* z, const __nv_bfloat16* zp_in, const float* znor
 bool enc_tc_supported(int b, int HW, int C, int D);
 size_t enc_tc_ws_bytes(int C);
 int run_enc_tc(const float* x, const float* enc_w, const float* enc_b, float* z, __nv_bfloat16* zp, float* znorm2,
-               void* wp_ws, int b, int HW, int C, cudaStream_t st);
+               void* wp_ws, unsigned* amax_bits, int b, int HW, int C, cudaStream_t st);
 
 // amft_conv.cu
 bool conv_shape_supported(int b, int Cin, int Cout, int h, int w);
@@ -741,6 +741,44 @@ int pack_weights_1x1(const float* w, void* wp, int Cout, int Cin, cudaStream_t s
 int conv_igemm(const void* xp, const void* wp, const float* scale, const float* shift, void* out_planes,
                float* out_nchw, const float* res_nchw, int b, int Cin, int Cout, int h, int w, int ntaps, int precision,
                int relu, cudaStream_t st);
+int conv_run(const ammc_conv_layer& L, cudaStream_t st);
+int absmax_f32(const float* x, long long n, unsigned* out_bits, cudaStream_t st);
+
+// Power-of-two scale of the module output written as q planes (precision-2 operand of the AMFT block), from a rigorous
+// bound:  |out_c| <= max|x| (residual) + sum_j ||dec_w[c, jD:(j+1)D]||_2 * max_m ||e_m||_2 + |dec_b[c]|   (Cauchy-Schwarz)
+__global__ void __launch_bounds__(256) mem_out_qscale_kernel(const unsigned* __restrict__ amax_bits, const float* __restrict__ dec_w,
+                                                             const float* __restrict__ dec_b, const float* __restrict__ en2,
+                                                             int C, int D, int M, int k, int residual, float* __restrict__ qs) {
+  __shared__ float red[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float e2 = 0.f;
+  for (int m = threadIdx.x; m < M; m += blockDim.x) e2 = fmaxf(e2, en2[m]);
+  e2 = warp_max(e2);
+  if (lane == 0) red[warp] = e2;
+  __syncthreads();
+  e2 = red[0];
+  for (int i = 1; i < 8; ++i) e2 = fmaxf(e2, red[i]);
+  const float emax = sqrtf(e2);
+  __syncthreads();
+  float best = 0.f;
+  for (int c = warp; c < C; c += 8) {
+    float bound = 0.f;
+    for (int j = 0; j < k; ++j) {
+      float ss = 0.f;
+      for (int d = lane; d < D; d += 32) { const float wv = dec_w[(size_t)c * k * D + j * D + d]; ss = fmaf(wv, wv, ss); }
+      ss = warp_sum(ss);
+      bound += sqrtf(ss);
+    }
+    best = fmaxf(best, bound * emax * 1.01f + fabsf(dec_b[c]));
+  }
+  if (lane == 0) red[warp] = best;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 8; ++i) best = fmaxf(best, red[i]);
+    const float xmax = residual ? __uint_as_float(amax_bits[0]) : 0.f;
+    qs[0] = q_scale_for_bound(xmax + best);
+  }
+}
 
 static int g_enc_mode = 0;    // 0 auto, 1 fp32 FFMA (CUDA cores), 2 tensor-core GEMM (split-bf16 x3, converts NCHW on the fly)
 static int g_dec_mode = 0;    // 0 auto, 1 fp32 table gather (CUDA cores), 2 tensor-core GEMM (split-bf16 x3)
@@ -798,7 +836,7 @@ static void launch_address(const float* z, const float* embed, const MemWs& m, f
 
 static int run_address(const float* z, const float* embed, const MemWs& m, float* read, float* q1, int64_t* idx,
                        float* counts, float* embed_sum, int64_t N, int D, int M, int k, cudaStream_t st, Workspace& ws) {
-  AMMC_CUDA_CHECK(cudaMemsetAsync(m.stats, 0, 256, st));
+  AMMC_CUDA_CHECK(cudaMemsetAsync(m.stats, 0, 32, st));   // words 0-7; word 8 = max|x| bits of the enc pass
   bank_transpose_kernel<<<dim3(ceil_div(M, 32), ceil_div(D, 32)), dim3(32, 8), 0, st>>>(embed, m.bank_t, D, M);
   AMMC_LAUNCH_CHECK("bank_transpose_kernel");
   bank_norms_kernel<<<ceil_div(M, 128), 128, 0, st>>>(embed, m.en2, D, M);
@@ -868,8 +906,8 @@ static int check_dims(int64_t N, int C, int D, int M, int k) {
 extern "C" int ammc_mem_fwd(const float* x, const float* enc_w, const float* enc_b, const float* embed,
                             const float* dec_w, const float* dec_b, float* out, float* q1, int64_t* idx, float* z,
                             float* sse_frame, float* diff, float* counts, float* embed_sum, void* out_planes,
-                            void* workspace, size_t workspace_bytes, int b, int h, int w, int C, int D, int M, int k,
-                            int residual, void* stream) {
+                            int planes_fmt, void* workspace, size_t workspace_bytes, int b, int h, int w, int C, int D,
+                            int M, int k, int residual, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t N = (int64_t)b * h * w;
   const int HW = h * w;
@@ -884,6 +922,10 @@ extern "C" int ammc_mem_fwd(const float* x, const float* enc_w, const float* enc
     return fail(AMMC_EUNSUPPORTED, "tensor-core dec needs k*D %% 64 == 0, C %% 64 == 0 and a feature map the conv engine tiles");
   AMMC_REQUIRE(!out_planes || tc_dec, "out_planes requested but the tensor-core dec path is not in use "
                                       "(query ammc_mem_dec_uses_tensor first)");
+  AMMC_REQUIRE(planes_fmt == 0 || planes_fmt == 1, "planes_fmt must be 0 (bf16 hi/lo) or 1 (q)");
+  const bool q_planes = out_planes && planes_fmt == 1;
+  AMMC_REQUIRE(!q_planes || C % 256 == 0, "q-format planes need C %% 256 == 0");
+  unsigned* amax_bits = reinterpret_cast<unsigned*>(m.stats + 8);     // word 8 of the stats block
   __nv_bfloat16* dec_wp = nullptr;
   float* ones = nullptr;
   if (tc_dec) {
@@ -903,12 +945,16 @@ extern "C" int ammc_mem_fwd(const float* x, const float* enc_w, const float* enc
     __nv_bfloat16* zp = ws.take<__nv_bfloat16>((size_t)N * D);
     float* zn2 = ws.take<float>(N);
     if (!ws.ok()) return fail(AMMC_EWORKSPACE, "workspace too small");
-    if (int rc = run_enc_tc(x, enc_w, enc_b, z, zp, zn2, enc_wp, b, HW, C, st)) return rc;
+    // the converters see every input value: max|x| (for the q planes' scale) comes out of the same pass
+    if (int rc = run_enc_tc(x, enc_w, enc_b, z, zp, zn2, enc_wp, (q_planes && residual) ? amax_bits : nullptr, b, HW, C, st))
+      return rc;
     m.zp = zp;
     m.znorm2 = zn2;
   } else {
     enc1x1_kernel<<<dim3(ceil_div(N, 64), ceil_div(D, 64)), 256, 0, st>>>(x, enc_w, enc_b, z, nullptr, (int)N, HW, C, D);
     AMMC_LAUNCH_CHECK("enc1x1_kernel");
+    if (q_planes && residual)
+      if (int rc = absmax_f32(x, (long long)N * C, amax_bits, st)) return rc;
   }
   if (int rc = run_address(z, embed, m, nullptr, q1, idx, counts, embed_sum, N, D, M, k, st, ws)) return rc;
   if (int rc = run_commit(m, sse_frame, diff, N, HW, D, st)) return rc;
@@ -919,7 +965,17 @@ extern "C" int ammc_mem_fwd(const float* x, const float* enc_w, const float* enc
     if (int rc = pack_weights_1x1(dec_w, dec_wp, C, k * D, st)) return rc;
     fill_kernel<<<ceil_div(C, 256), 256, 0, st>>>(ones, 1.f, C);
     AMMC_LAUNCH_CHECK("fill_kernel");
-    return conv_igemm(m.read_planes, dec_wp, ones, dec_b, out_planes, out, res, b, k * D, C, h, w, 1, 3, 0, st);
+    ammc_conv_layer L = {};
+    L.in_planes = m.read_planes; L.wp = dec_wp; L.taps = 1; L.scale = ones; L.shift = dec_b; L.act = 0;
+    L.out_planes = out_planes; L.out_nchw = out; L.res_nchw = res;
+    L.b = b; L.h = h; L.w = w; L.Cin = k * D; L.Cout = C; L.precision = 3;
+    if (q_planes) {
+      float* qs = reinterpret_cast<float*>((uint8_t*)out_planes + 4 * N * C);
+      mem_out_qscale_kernel<<<1, 256, 0, st>>>(amax_bits, dec_w, dec_b, m.en2, C, D, M, k, residual, qs);
+      AMMC_LAUNCH_CHECK("mem_out_qscale_kernel");
+      L.out_fmt = 1;
+    }
+    return conv_run(L, st);
   }
   const int chunks = 4;
   dim3 grid(ceil_div(N, 32), ceil_div(ceil_div(C, 32), chunks));

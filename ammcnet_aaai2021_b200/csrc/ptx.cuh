@@ -35,25 +35,26 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a pipeline bug must never hang the GPU.  On timeout the waiter records (tag, block, thread) in
-// g_ammc_timeout, poisons all later waits (they return immediately) and lets the kernel drain; the host reads the
-// record with ammc_debug_timeout() and raises.  Results of a poisoned launch are garbage by construction.
-static __device__ int g_ammc_timeout[4];   // per translation unit: [0] poisoned flag, [1] tag, [2] block, [3] thread
+// Bounded wait: a pipeline bug must never hang the GPU, and must never go unnoticed.  After ~10 s of spinning (2e10
+// clocks; far beyond any legitimate wait, including time-sliced or debugger-preempted contexts) the waiter records
+// (tag, block, thread) in g_ammc_timeout and executes `trap`: the launch fails, the context carries a sticky error and
+// every later CUDA call of the process -- hence every later ammc_* call -- returns AMMC_ECUDA.  No launch can continue
+// past a broken wait and no later launch can silently skip its waits.
+static __device__ int g_ammc_timeout[4];   // per translation unit: [0] flag, [1] tag, [2] block, [3] thread
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 63u) != 0) continue;                        // keep the hot loop free of global-memory traffic
-    if (*reinterpret_cast<volatile int*>(&g_ammc_timeout[0])) return;
-    if (clock64() - t0 > 1000000000LL) {
+    if ((++spins & 1023u) != 0) continue;                      // keep the hot loop free of clock reads
+    if (clock64() - t0 > 20000000000LL) {
       if (atomicCAS(&g_ammc_timeout[0], 0, 1) == 0) {
         g_ammc_timeout[1] = tag;
         g_ammc_timeout[2] = (int)blockIdx.x;
         g_ammc_timeout[3] = (int)threadIdx.x;
-        __threadfence();
+        __threadfence_system();
       }
-      return;
+      asm volatile("trap;");
     }
   }
 }
@@ -261,6 +262,58 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta)
       : "memory");
 }
 
+// ---------------------------------------------------------------- mixed fp16 + e4m3 scheme (precision 2)
+// kind::f8f6f4 on e4m3 operands (K = 32 per MMA, same 128B-swizzled K-major descriptors, +2 per K step), CTA pair
+__device__ __forceinline__ void mma_f8_ss_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// D = D * 2^-SHIFT + A.B  (scale-input-d immediate; joins the e4m3 cross terms with the fp16 main product)
+template <int SHIFT>
+__device__ __forceinline__ void mma_f16_ss_2sm_scaled(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, 1, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p, %4;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "n"(SHIFT)
+      : "memory");
+}
+// {lo 16 bits = f16_rn(a), hi 16 bits = f16_rn(b)}, saturating to the largest finite value
+__device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+// {lo byte = e4m3_rn(a), hi byte = e4m3_rn(b)}, saturating at +-448
+__device__ __forceinline__ uint32_t pack_e4m3x2(float a, float b) {
+  uint16_t r;
+  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(r) : "f"(b), "f"(a));
+  return (uint32_t)r;
+}
+__device__ __forceinline__ float2 unpack_f16x2(uint32_t h) {
+  float2 f;
+  asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tcvt.f32.f16 %0, lo;\n\tcvt.f32.f16 %1, hi;\n\t}"
+      : "=f"(f.x), "=f"(f.y)
+      : "r"(h));
+  return f;
+}
+// Mixed-precision operand format "q" of one tensor t scaled by a power of two s16 (|t*s16| <= 2^15):
+//   h16 = fp16(t*s16)            the main operand
+//   h8  = e4m3(t*s16 * 2^-7)     the same value at 4 bits, for the cross terms
+//   l8  = e4m3((t*s16 - h16) * 2^4)   the fp16 rounding residual, scaled by 2^11 * 2^-7
+// sum over k of  h16.h16 + 2^-4 (h8.l8 + l8.h8)  ==  (x.w) s16x s16w  up to ~2^-14 relative per product.
+constexpr int Q_SHIFT = 4;           // scale-input-d that joins the cross-term accumulator with the main one
+__device__ __forceinline__ void split_pack_q(float t0, float t1, uint32_t& h16, uint32_t& h8, uint32_t& l8) {
+  h16 = pack_f16x2(t0, t1);
+  const float2 f = unpack_f16x2(h16);
+  h8 = pack_e4m3x2(t0 * 0.0078125f, t1 * 0.0078125f);
+  l8 = pack_e4m3x2((t0 - f.x) * 16.f, (t1 - f.y) * 16.f);
+}
 // ---------------------------------------------------------------- UMMA descriptors
 // K-major operand tile stored as rows of 128 bytes with the 128B swizzle (what TMA SWIZZLE_128B writes):
 // 8-row groups are 1024 B apart (SBO); LBO is unused for swizzled K-major layouts (encoded 1 like CUTLASS).

@@ -98,7 +98,7 @@ def concurrently(*fns):
                     t.record_stream(cur)
                     planes = getattr(t, "_ammc_planes", None)
                     if planes is not None:
-                        planes[0].record_stream(cur)
+                        planes[0].record_stream(cur)           # bf16 planes tensor or QPlanes
     return results
 
 
@@ -127,26 +127,70 @@ def set_enc_mode(mode: str = "auto"):
     _capi.call("ammc_set_enc_mode", {"auto": 0, "fp32": 1, "tensor": 2}[mode])
 
 
-def attach_planes(t: torch.Tensor, planes: torch.Tensor):
-    """Remember the NHWC bf16 hi/lo planes of `t` (produced for free by the dec epilogue) so the AMFT block can skip its
-    pack kernel.  The tensor's version counter is recorded: any in-place change of `t` invalidates the planes."""
+class QPlanes:
+    """q-format operand buffer of an NHWC activation [b,h,w,C] (include/ammc_b200.h, precision 2): fp16 plane, two e4m3
+    planes and the power-of-two scale in one uint8 tensor."""
+    __slots__ = ("buf", "shape")
+
+    def __init__(self, buf: torch.Tensor, shape):
+        self.buf, self.shape = buf, tuple(shape)          # shape = (b, h, w, C)
+
+    @staticmethod
+    def empty(b, h, w, C, device):
+        n = b * h * w * C
+        return QPlanes(torch.empty((4 * n + 16,), dtype=torch.uint8, device=device), (b, h, w, C))
+
+    @property
+    def device(self):
+        return self.buf.device
+
+    def data_ptr(self):
+        return self.buf.data_ptr()
+
+    def record_stream(self, st):
+        self.buf.record_stream(st)
+
+    def scale(self) -> torch.Tensor:
+        n = self.buf.numel() - 16
+        return self.buf[n:n + 4].view(torch.float32)
+
+    def dequantize(self) -> torch.Tensor:
+        """fp32 NCHW value of the fp16 plane + residual plane (tests / debugging)."""
+        b, h, w, C = self.shape
+        n = b * h * w * C
+        h16 = self.buf[:2 * n].view(torch.float16).float()
+        l8 = self.buf[3 * n:4 * n].view(torch.float8_e4m3fn).float()
+        return ((h16 + l8 / 16.0) / self.scale()).view(b, h, w, C).permute(0, 3, 1, 2).contiguous()
+
+
+def attach_planes(t: torch.Tensor, planes):
+    """Remember the NHWC operand planes of `t` (bf16 hi/lo tensor or QPlanes, produced for free by the dec epilogue) so the
+    AMFT block can skip its pack kernel.  The tensor's version counter is recorded: any in-place change of `t`
+    invalidates the planes."""
     t._ammc_planes = (planes, t._version)
 
 
-def planes_of(t: torch.Tensor):
+def planes_of(t: torch.Tensor, fmt: str = "bf16"):
+    """The attached operand planes of `t` in format `fmt` ('bf16' | 'q'), or None."""
     rec = getattr(t, "_ammc_planes", None)
     if rec is None:
         return None
     planes, version = rec
     b, C, h, w = t.shape
-    if version != t._version or tuple(planes.shape) != (2, b, h, w, C) or planes.device != t.device:
+    if version != t._version or planes.device != t.device:
+        return None
+    if isinstance(planes, QPlanes):
+        return planes if fmt == "q" and planes.shape == (b, h, w, C) else None
+    if fmt != "bf16" or tuple(planes.shape) != (2, b, h, w, C):
         return None
     return planes
 
 
 def mem_forward_raw(x, enc_w, enc_b, embed, dec_w, dec_b, k: int, residual: bool, want_stats: bool,
-                    want_planes: bool = False):
-    """One fused-module forward.  Returns dict(out, q1[N,D], idx[N,k], z[N,D], sse_frame[b], diff[1], counts, embed_sum)."""
+                    want_planes=False):
+    """One fused-module forward.  Returns dict(out, q1[N,D], idx[N,k], z[N,D], sse_frame[b], diff[1], counts, embed_sum).
+    want_planes: False | 'bf16' (True) | 'q' -- also emit `out` as the AMFT block's NHWC operand in that format."""
+    want_planes = "bf16" if want_planes is True else want_planes
     _require_cuda_f32(x, enc_w, enc_b, embed, dec_w, dec_b, names=("x", "enc.weight", "enc.bias", "embed", "dec.weight", "dec.bias"))
     if x.dim() != 4:
         raise RuntimeError("ammc_b200: memory module input must be [b, C, h, w], got %s" % (tuple(x.shape),))
@@ -169,14 +213,17 @@ def mem_forward_raw(x, enc_w, enc_b, embed, dec_w, dec_b, k: int, residual: bool
     lib = _capi.load()
     planes = None
     if want_planes and lib.ammc_mem_dec_uses_tensor(b, h, w, C, D, M, k):
-        planes = torch.empty((2, b, h, w, C), dtype=torch.bfloat16, device=dev)
+        if want_planes == "q" and C % 256 == 0:
+            planes = QPlanes.empty(b, h, w, C, dev)
+        else:
+            planes = torch.empty((2, b, h, w, C), dtype=torch.bfloat16, device=dev)
     ws = _workspace(lib.ammc_mem_workspace_bytes(b, h, w, C, D, M, k), dev)
     with torch.cuda.device(dev):
         _capi.call("ammc_mem_fwd", _p(x), _p(enc_w.contiguous()), _p(enc_b.contiguous()), _p(embed.contiguous()),
                    _p(dec_w.contiguous()), _p(dec_b.contiguous()), _p(out), _p(q1), _p(idx), _p(z), _p(sse), _p(diff),
-                   _p(counts), _p(esum), _p(planes), _p(ws), ws.numel(), b, h, w, C, D, M, k, int(bool(residual)),
-                   _stream())
-    _count(8 + (2 if want_stats else 0))
+                   _p(counts), _p(esum), _p(planes), int(isinstance(planes, QPlanes)), _p(ws), ws.numel(), b, h, w, C, D, M,
+                   k, int(bool(residual)), _stream())
+    _count(8 + (2 if want_stats else 0) + (1 if isinstance(planes, QPlanes) else 0))
     if planes is not None:
         attach_planes(out, planes)
     return dict(out=out, q1=q1, idx=idx, z=z, sse_frame=sse, diff=diff, counts=counts, embed_sum=esum, x=x)
@@ -230,9 +277,10 @@ class MemoryModuleFn(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, x, enc_w, enc_b, embed, dec_w, dec_b, k, residual, want_stats):
+    def forward(ctx, x, enc_w, enc_b, embed, dec_w, dec_b, k, residual, want_stats, want_planes=False):
+        # want_planes is decided by the caller: grad mode is always off inside Function.forward
         r = mem_forward_raw(x, enc_w.reshape(enc_w.shape[0], -1), enc_b, embed, dec_w.reshape(dec_w.shape[0], -1),
-                            dec_b, k, residual, want_stats, want_planes=not torch.is_grad_enabled())
+                            dec_b, k, residual, want_stats, want_planes=want_planes)
         b, C, h, w = r["x"].shape
         D, M = embed.shape
         # training: the caller updates the bank in place right after this forward (EMA, unet.py:298-309);
@@ -269,7 +317,7 @@ class MemoryModuleFn(torch.autograd.Function):
                        _p(g_dec_b), _p(ws), ws.numel(), b, h, w, C, D, M, k, int(residual), _stream())
         _count(10)
         es, ds = ctx.wshapes
-        return gx, g_enc_w.view(es), g_enc_b, None, g_dec_w.view(ds), g_dec_b, None, None, None
+        return gx, g_enc_w.view(es), g_enc_b, None, g_dec_w.view(ds), g_dec_b, None, None, None, None
 
 
 class QuantizeFn(torch.autograd.Function):
@@ -375,6 +423,36 @@ def pack_conv_weights(w: torch.Tensor) -> torch.Tensor:
     return wp
 
 
+def q_conv_supported(Cin: int, Cout: int) -> bool:
+    """Shapes the fp16 + e4m3 (precision 2) conv kernel serves; others run precision 3."""
+    return Cin % 128 == 0 and Cout % 256 == 0
+
+
+def pack_conv_weights_q(w: torch.Tensor) -> torch.Tensor:
+    """[Cout, Cin, 3, 3] / [Cout, Cin, 1, 1] fp32 -> q weight buffer (uint8; include/ammc_b200.h)."""
+    _require_cuda_f32(w, names=("conv weight",))
+    Cout, Cin = w.shape[0], w.shape[1]
+    taps = w[0, 0].numel()
+    if taps not in (1, 9):
+        raise RuntimeError("ammc_b200: only 3x3 and 1x1 conv weights are supported")
+    wq = torch.empty((int(_capi.load().ammc_q_weight_bytes(Cout, taps * Cin)),), dtype=torch.uint8, device=w.device)
+    with torch.cuda.device(w.device):
+        _capi.call("ammc_pack_conv_weights_q", _p(w.contiguous()), _p(wq), Cout, Cin, taps, _stream())
+    _count(2)
+    return wq
+
+
+def pack_nhwc_q(x: torch.Tensor) -> QPlanes:
+    """[b, C, h, w] fp32 NCHW -> q operand buffer (max|x| reduction + pack)."""
+    _require_cuda_f32(x, names=("activation",))
+    b, C, h, w = x.shape
+    q = QPlanes.empty(b, h, w, C, x.device)
+    with torch.cuda.device(x.device):
+        _capi.call("ammc_pack_nhwc_q", _p(x.contiguous()), _p(q.buf), b, C, h, w, _stream())
+    _count(3)
+    return q
+
+
 def bn_fold(gamma, beta, mean, var, eps: float):
     _require_cuda_f32(gamma, beta, mean, var)
     C = gamma.numel()
@@ -400,14 +478,27 @@ def pack_nhwc(x: torch.Tensor) -> torch.Tensor:
 
 def conv3x3_bn_relu(xp, wp, scale, shift, *, to_planes: bool, residual: Optional[torch.Tensor] = None,
                     precision: int = 3, relu: bool = True):
-    """One implicit-GEMM conv.  xp [2,b,h,w,Cin] bf16, wp [2,Cout,9Cin] bf16.
-    to_planes=True -> [2,b,h,w,Cout] bf16 planes; else fp32 NCHW [b,Cout,h,w] (+ residual)."""
-    _, b, h, w, Cin = xp.shape
-    Cout = wp.shape[1]
-    taps = wp.shape[2] // Cin
+    """One implicit-GEMM conv.  precision 1/3: xp [2,b,h,w,Cin] bf16, wp [2,Cout,9Cin] bf16; precision 2: xp a QPlanes,
+    wp a q weight buffer.  to_planes=True -> operand planes of the same format ([2,b,h,w,Cout] bf16 or QPlanes);
+    else fp32 NCHW [b,Cout,h,w] (+ residual)."""
+    if precision == 2:
+        if not isinstance(xp, QPlanes):
+            raise RuntimeError("ammc_b200: precision 2 takes q-format operands (pack_nhwc_q / pack_conv_weights_q)")
+        b, h, w, Cin = xp.shape
+        Cout = scale.numel()
+        taps = (wp.numel() - 16 - 4 * Cout) // (4 * Cout * Cin)
+    else:
+        _, b, h, w, Cin = xp.shape
+        Cout = wp.shape[1]
+        taps = wp.shape[2] // Cin
     dev = xp.device
     _check_device(dev)
-    out_p = torch.empty((2, b, h, w, Cout), dtype=torch.bfloat16, device=dev) if to_planes else None
+    if not to_planes:
+        out_p = None
+    elif precision == 2:
+        out_p = QPlanes.empty(b, h, w, Cout, dev)
+    else:
+        out_p = torch.empty((2, b, h, w, Cout), dtype=torch.bfloat16, device=dev)
     out_n = None if to_planes else torch.empty((b, Cout, h, w), dtype=torch.float32, device=dev)
     if residual is not None:
         _require_cuda_f32(residual, names=("residual",))
@@ -421,7 +512,7 @@ def conv3x3_bn_relu(xp, wp, scale, shift, *, to_planes: bool, residual: Optional
         if PROFILE["on"]:
             ev1.record()
             PROFILE["events"].append((ev0, ev1))
-    _count(1)
+    _count(2 if (precision == 2 and to_planes) else 1)
     return out_p if to_planes else out_n
 
 
@@ -433,16 +524,28 @@ def conv_layer(in_planes, wp, scale, shift, *, taps: int = 9, act: int = 1, Cin:
                up2x: bool = False, precision: int = 3):
     """One launch of `ammc_conv_layer_run`.  in_planes [2,b,h,w,in_cs] bf16 (channel window [in_c_off, +Cin));
     wp [2,Cout,taps*Cin]; out_planes [2,b,ho,wo,out_cs] (written at out_c_off) and/or out_nchw [b,cout_valid,h,w]."""
-    _, b, h, w, in_cs = in_planes.shape
-    Cout = wp.shape[1]
-    Cin = wp.shape[2] // taps if Cin is None else Cin
+    q_in = isinstance(in_planes, QPlanes)
+    if q_in != (precision == 2):
+        raise RuntimeError("ammc_b200: precision 2 <=> q-format input planes")
+    if q_in:
+        b, h, w, in_cs = in_planes.shape
+        Cout = scale.numel()
+        Cin = in_cs
+    else:
+        _, b, h, w, in_cs = in_planes.shape
+        Cout = wp.shape[1]
+        Cin = wp.shape[2] // taps if Cin is None else Cin
     dev = in_planes.device
     _check_device(dev)
     L = _capi.ConvLayer()
     L.in_planes, L.in_cs, L.in_c_off = in_planes.data_ptr(), in_cs, in_c_off
     L.wp, L.taps = wp.data_ptr(), taps
     L.scale, L.shift, L.act = scale.data_ptr(), shift.data_ptr(), int(act)
-    if out_planes is not None:
+    if isinstance(out_planes, QPlanes):
+        if out_planes.shape[:3] != (b, h, w) or up2x:
+            raise RuntimeError("ammc_b200: q-format out_planes must be [%d,%d,%d,cs]" % (b, h, w))
+        L.out_planes, L.out_cs, L.out_c_off, L.out_fmt = out_planes.data_ptr(), out_planes.shape[3], out_c_off, 1
+    elif out_planes is not None:
         ho, wo = (2 * h, 2 * w) if up2x else (h, w)
         if tuple(out_planes.shape[:4]) != (2, b, ho, wo) or out_planes.dtype != torch.bfloat16:
             raise RuntimeError("ammc_b200: out_planes must be bf16 [2,%d,%d,%d,cs], got %s" % (b, ho, wo, tuple(out_planes.shape)))
@@ -456,7 +559,7 @@ def conv_layer(in_planes, wp, scale, shift, *, taps: int = 9, act: int = 1, Cin:
         L.res_nchw = residual.data_ptr()
     L.cout_valid = cout_valid
     L.b, L.h, L.w, L.Cin, L.Cout = b, h, w, Cin, Cout
-    L.up2x, L.precision = int(bool(up2x)), int(precision)
+    L.up2x, L.precision, L.in_fmt = int(bool(up2x)), int(precision), int(q_in)
     with torch.cuda.device(dev):
         if PROFILE["on"]:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

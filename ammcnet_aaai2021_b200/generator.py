@@ -116,14 +116,15 @@ class GeneratorEngine:
         self._conv(pk, "down3.1", mid, out_nchw=x4)            # the memory module's `enc` reads fp32 NCHW
         return cats, x4
 
-    def _amft_branch(self, dc, src_planes, residual):
-        w1, s1, b1 = dc.packed(0, 1)
-        w2, s2, b2 = dc.packed(3, 4)
-        _, b, h, w, c = src_planes.shape
-        mid = _planes(b, h, w, c, src_planes.device)
-        F_.conv_layer(src_planes, w1, s1, b1, out_planes=mid, precision=self.model.bridge.precision)
-        out = _planes(b, h, w, c, src_planes.device)
-        F_.conv_layer(mid, w2, s2, b2, out_planes=out, residual=residual, precision=self.model.bridge.precision)
+    def _amft_branch(self, dc, src_planes, residual, prec):
+        q = prec == 2
+        w1, s1, b1 = dc.packed(0, 1, q)
+        w2, s2, b2 = dc.packed(3, 4, q)
+        b, h, w, c = src_planes.shape if q else src_planes.shape[1:]
+        mid = F_.QPlanes.empty(b, h, w, c, src_planes.device) if q else _planes(b, h, w, c, src_planes.device)
+        F_.conv_layer(src_planes, w1, s1, b1, out_planes=mid, precision=prec)
+        out = _planes(b, h, w, c, src_planes.device)           # up1's transposed conv reads bf16 hi/lo planes
+        F_.conv_layer(mid, w2, s2, b2, out_planes=out, residual=residual, precision=prec)
         return out
 
     def _decode(self, pk, x4p, cats):
@@ -157,15 +158,18 @@ class GeneratorEngine:
         pr, po = self._packs["rgb"], self._packs["op"]
         def stream_front(pk, unet, x):                         # encoder + memory module of one stream
             cats, x4 = self._encode(pk, x)
-            return (cats,) + tuple(unet.vq_down3(x4))
+            return (cats,) + tuple(unet.vq_down3(x4)) + (x4,)
 
         # the appearance and motion streams are independent up to the AMFT block and again after it (unet.py:981-1003)
-        (cats_r, r4, rgb_diff, rgb_q), (cats_o, o4, op_diff, op_q) = F_.concurrently(
+        (cats_r, r4, rgb_diff, rgb_q, r4_in), (cats_o, o4, op_diff, op_q, _) = F_.concurrently(
             lambda: stream_front(pr, m.rgb, rgb_x), lambda: stream_front(po, m.op, op_x))
-        px, py = F_.planes_of(r4), F_.planes_of(o4)
-        px = F_.pack_nhwc(r4) if px is None else px
-        py = F_.pack_nhwc(o4) if py is None else py
-        r4p = self._amft_branch(m.bridge.O2F, py, r4)          # x' = zx + O2F(zy)   (unet.py:963)
-        o4p = self._amft_branch(m.bridge.F20, px, o4)          # y' = zy + F20(zx)   (unet.py:964)
+        m.quant_befor, m.quant_after = r4_in, r4             # side attributes of the reference forward (unet.py:986,988)
+        prec = m.bridge.eval_precision(r4.shape[1])
+        fmt, pack = ("q", F_.pack_nhwc_q) if prec == 2 else ("bf16", F_.pack_nhwc)
+        px, py = F_.planes_of(r4, fmt), F_.planes_of(o4, fmt)
+        px = pack(r4) if px is None else px
+        py = pack(o4) if py is None else py
+        r4p = self._amft_branch(m.bridge.O2F, py, r4, prec)    # x' = zx + O2F(zy)   (unet.py:963)
+        o4p = self._amft_branch(m.bridge.F20, px, o4, prec)    # y' = zy + F20(zx)   (unet.py:964)
         rgb_y, op_y = F_.concurrently(lambda: self._decode(pr, r4p, cats_r), lambda: self._decode(po, o4p, cats_o))
         return rgb_y, op_y, (rgb_diff, op_diff), (rgb_q, op_q)

@@ -99,7 +99,9 @@ class twostream(nn.Module):
                 object.__setattr__(self, "_engine_obj", GeneratorEngine(self))
             return self._engine_obj(rgb_x, op_x)
         r1, r2, r3, r4 = self.rgb.encode(rgb_x)
+        self.quant_befor = r4                                   # side attributes the reference keeps (unet.py:986,988)
         r4, rgb_diff, rgb_q = self.rgb.vq_down3(r4)
+        self.quant_after = r4
         o1, o2, o3, o4 = self.op.encode(op_x)
         o4, op_diff, op_q = self.op.vq_down3(o4)
         r4, o4 = self.bridge(r4, o4)

@@ -70,10 +70,16 @@ class enc_quan_dec_topk(nn.Module):
         self.quantize = Quantize_topk(dim=embed_dim, n_embed=n_embed, k=k)
         self.dec = nn.Conv2d(embed_dim * k, in_c, 1)
 
+    # operand format in which eval / no-grad forwards also emit `out` for the AMFT block (free in the dec epilogue):
+    # 'q' = fp16 + e4m3 (bridge precision 2, the default), 'bf16' = hi/lo planes (precision 1 / 3), None = off
+    planes_format = "q"
+
     def _run(self, x, residual):
         q = self.quantize
+        want_planes = False if (self.training or torch.is_grad_enabled()) else (self.planes_format or False)
         out, diff, q1, idx, sse, counts, esum = F_.MemoryModuleFn.apply(
-            x, self.enc.weight, self.enc.bias, q.embed, self.dec.weight, self.dec.bias, q.k, residual, self.training)
+            x, self.enc.weight, self.enc.bias, q.embed, self.dec.weight, self.dec.bias, q.k, residual, self.training,
+            want_planes)
         q.last_idx, q.last_sse_frame = idx, sse
         if self.training:
             q._ema(counts, esum)
@@ -108,17 +114,18 @@ class double_conv(nn.Module):
                                   nn.ReLU(inplace=True))
         self._packed = {}
 
-    def packed(self, ci, bi):
-        """(weight planes, scale, shift) of conv `ci` / BN `bi`, re-packed only when a tensor changed."""
+    def packed(self, ci, bi, q=False):
+        """(weight planes, scale, shift) of conv `ci` / BN `bi`, re-packed only when a tensor changed.  q: the fp16 + e4m3
+        weight buffer of precision 2 instead of bf16 hi/lo planes."""
         conv, bn = self.conv[ci], self.conv[bi]
         src = (conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var)
         key = tuple((t.data_ptr(), t._version) for t in src)
-        hit = self._packed.get(ci)
+        hit = self._packed.get((ci, q))
         if hit is None or hit[0] != key:
-            wp = F_.pack_conv_weights(conv.weight.detach())
+            wp = (F_.pack_conv_weights_q if q else F_.pack_conv_weights)(conv.weight.detach())
             scale, shift = F_.bn_fold(bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var, bn.eps)
             hit = (key, wp, scale, shift)
-            self._packed[ci] = hit
+            self._packed[(ci, q)] = hit
         return hit[1], hit[2], hit[3]
 
     def forward_autograd(self, u, residual, precision):
@@ -135,8 +142,9 @@ class double_conv(nn.Module):
         return out
 
     def forward_fused(self, xp, residual, precision):
-        w1, s1, b1 = self.packed(0, 1)
-        w2, s2, b2 = self.packed(3, 4)
+        q = precision == 2
+        w1, s1, b1 = self.packed(0, 1, q)
+        w2, s2, b2 = self.packed(3, 4, q)
         mid = F_.conv3x3_bn_relu(xp, w1, s1, b1, to_planes=True, precision=precision)
         return F_.conv3x3_bn_relu(mid, w2, s2, b2, to_planes=False, residual=residual, precision=precision)
 
@@ -144,31 +152,40 @@ class double_conv(nn.Module):
 class bridge(nn.Module):
     """AMFT: x' = zx + O2F(zy), y' = zy + F20(zx) (reference unet.py:956-965).
 
-    `precision` = 3 (default): split-bf16 three-pass tensor-core convolution, fp32-parity numerics;
+    `precision` = 2 (default): fp16 main product + e4m3 cross terms on tcgen05, fp32-parity numerics at two tensor-core
+                  pass-equivalents (eval / no-grad forward, channels % 256 == 0; other cases run precision 3);
+    `precision` = 3: split-bf16 three-pass convolution, fp32-parity numerics (also the training / autograd path);
     `precision` = 1: single bf16 pass (the "bf16 variant", stated separately in every report).
     """
 
-    def __init__(self, in_c=64, precision: int = 3):
+    def __init__(self, in_c=64, precision: int = 2):
         super().__init__()
         self.O2F = double_conv(in_c, in_c)
         self.F20 = double_conv(in_c, in_c)
         self.precision = precision
+
+    def eval_precision(self, C: int) -> int:
+        """Precision the fused eval path runs at for C channels (2 needs shapes the q kernel serves)."""
+        return 3 if (self.precision == 2 and not F_.q_conv_supported(C, C)) else self.precision
 
     def forward(self, zx, zy):
         needs_graph = torch.is_grad_enabled() and (zx.requires_grad or zy.requires_grad or
                                                    any(p.requires_grad for p in self.parameters()))
         if self.training or needs_graph:
             # batch-statistic BN and/or autograd: unfused pipeline (raw conv -> BN stats -> apply), tcgen05 dgrad/wgrad
-            x = self.O2F.forward_autograd(zy, zx, self.precision)
-            y = self.F20.forward_autograd(zx, zy, self.precision)
+            prec = 3 if self.precision == 2 else self.precision
+            x = self.O2F.forward_autograd(zy, zx, prec)
+            y = self.F20.forward_autograd(zx, zy, prec)
             return x, y
-        # the memory modules' dec epilogue already wrote the NHWC bf16 planes of its output; otherwise pack here
-        px = F_.planes_of(zx)
-        py = F_.planes_of(zy)
-        px = F_.pack_nhwc(zx) if px is None else px
-        py = F_.pack_nhwc(zy) if py is None else py
-        x = self.O2F.forward_fused(py, zx, self.precision)
-        y = self.F20.forward_fused(px, zy, self.precision)
+        # the memory modules' dec epilogue already wrote the NHWC operand planes of its output; otherwise pack here
+        prec = self.eval_precision(zx.shape[1])
+        fmt, pack = ("q", F_.pack_nhwc_q) if prec == 2 else ("bf16", F_.pack_nhwc)
+        px = F_.planes_of(zx, fmt)
+        py = F_.planes_of(zy, fmt)
+        px = pack(zx) if px is None else px
+        py = pack(zy) if py is None else py
+        x = self.O2F.forward_fused(py, zx, prec)
+        y = self.F20.forward_fused(px, zy, prec)
         return x, y
 
 

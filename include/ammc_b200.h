@@ -70,8 +70,10 @@ int ammc_debug_tma_probe(const void* base, const int64_t* dims5, const int64_t* 
  *   sse_frame[b]            per-frame sum of (e_top1 - z)^2   (the per-frame partial of unet.py:310)
  *   diff     [1]            mean over all N*D elements = reference `diff`                    (unet.py:310,329)
  *   counts   [M], embed_sum [D, M]  (both NULL in eval) assignment statistics of unet.py:298-302
- *   out_planes [2][b,h,w,C] bf16 or NULL: `out` additionally as NHWC hi/lo planes (the AMFT block's operand), written
- *              by the same epilogue.  Only allowed when ammc_mem_dec_uses_tensor(...) == 1.
+ *   out_planes NULL, or `out` additionally as the AMFT block's NHWC operand, written by the same epilogue:
+ *              planes_fmt 0: [2][b,h,w,C] bf16 hi/lo planes; planes_fmt 1: a q buffer (ammc_q_act_bytes(N*C); its scale is
+ *              derived on the device from max|x| -- reduced inside the enc kernel -- and a Cauchy-Schwarz bound on dec(read)).
+ *              Only allowed when ammc_mem_dec_uses_tensor(...) == 1.
  * `dec` runs as a split-bf16 x3 GEMM on tcgen05 when k*D % 64 == 0, C % 64 == 0 and the feature map is at most 128
  * pixels wide; otherwise as an exact fp32 gather of precomputed table rows.  ammc_set_dec_mode: 0 auto,
  * 1 force the fp32 gather, 2 force the tensor-core GEMM.
@@ -96,7 +98,7 @@ int ammc_set_addressing_mode(int mode);
 int ammc_mem_fwd(const float* x, const float* enc_w, const float* enc_b, const float* embed,
                  const float* dec_w, const float* dec_b,
                  float* out, float* q1, int64_t* idx, float* z, float* sse_frame, float* diff,
-                 float* counts, float* embed_sum, void* out_planes,
+                 float* counts, float* embed_sum, void* out_planes, int planes_fmt,
                  void* workspace, size_t workspace_bytes,
                  int b, int h, int w, int C, int D, int M, int k, int residual, void* stream);
 
@@ -162,7 +164,8 @@ int ammc_mem_bwd(const float* x, const float* enc_w, const float* embed, const i
  * AMFT.  Replaces bridge.forward (unet.py:962-965) = two double_conv stacks (unet.py:8-20) + residuals.
  * The block is run as four 3x3 implicit-GEMM convolutions on tcgen05 tensor cores over NHWC bf16
  * operand planes.  `precision`: 1 = single bf16 pass; 3 = three-pass split-bf16 (hi*hi + hi*lo + lo*hi,
- * fp32 accumulate, ~2^-17 relative error: the fp32-parity mode).
+ * fp32 accumulate, ~2^-17 relative error: the fp32-parity mode); 2 = fp16 main product + e4m3 cross terms on q buffers
+ * (below): the same parity bar at two pass-equivalents -- xp / wp / out_planes are then q buffers.
  *
  * ammc_pack_conv_weights:   w [Cout, Cin, 3, 3] fp32  ->  wp [2 planes][Cout][9*Cin] bf16 (k = tap*Cin+cin)
  * ammc_pack_nhwc:           x [b, C, h, w] fp32 NCHW  ->  xp [2 planes][b, h, w, C] bf16   (hi, lo)
@@ -173,6 +176,20 @@ int ammc_mem_bwd(const float* x, const float* enc_w, const float* embed, const i
  * ------------------------------------------------------------------------------------------------- */
 int ammc_pack_conv_weights(const float* w, void* wp, int Cout, int Cin, void* stream);
 int ammc_pack_nhwc(const float* x, void* xp, int b, int C, int h, int w, void* stream);
+/* ---- precision 2: the "q" operand format (fp32 parity at two tensor-core pass-equivalents instead of three) ----------
+ * A tensor t with a power-of-two scale s16 (|t*s16| < 2^15, derived on the device from max|t| or from a rigorous bound)
+ * is stored as  h16 = fp16(t*s16),  h8 = e4m3(t*s16 / 128),  l8 = e4m3((t*s16 - h16) * 16).  The conv accumulates the
+ * cross terms h8.l8 + l8.h8 with kind::f8f6f4 MMAs (K = 32: twice the MACs per cycle) and then h16.h16 with kind::f16
+ * MMAs whose first instruction rescales the cross-term sum by 2^-4 (scale-input-d) -- one TMEM accumulator, each
+ * operand byte read once, ~5e-5 relative error per conv (tests/test_precision_schemes.py models it on the CPU).
+ *   activation buffer (n = b*h*w*C, NHWC):  [n fp16][n h8][n l8][float s16]                    ammc_q_act_bytes(n)
+ *   weight buffer (n = Cout*K, K = taps*Cin, k = tap*Cin + cin): [n fp16][n h8][n l8][Cout floats sum_k|w|][float s16]
+ * ammc_pack_nhwc_q: x [b,C,h,w] fp32 NCHW -> q buffer (max|x| reduction + pack).  ammc_pack_conv_weights_q: w
+ * [Cout,Cin,3,3] (taps 9) or [Cout,Cin] (taps 1) -> q weight buffer. */
+size_t ammc_q_act_bytes(int64_t n);
+size_t ammc_q_weight_bytes(int Cout, int K);
+int ammc_pack_nhwc_q(const float* x, void* xq, int b, int C, int h, int w, void* stream);
+int ammc_pack_conv_weights_q(const float* w, void* wq, int Cout, int Cin, int taps, void* stream);
 int ammc_conv3x3_bn_relu(const void* xp, const void* wp, const float* scale, const float* shift,
                          void* out_planes, float* out_nchw, const float* res_nchw,
                          int b, int Cin, int Cout, int h, int w, int precision, int relu, void* stream);
@@ -197,7 +214,11 @@ typedef struct ammc_conv_layer {
   int cout_valid;          /* 0 = Cout; < Cout when the weights/scale/shift were zero-padded to a multiple of 64 */
   int b, h, w, Cin, Cout;  /* input feature map; Cin, Cout multiples of 64 */
   int up2x;                /* 1: transposed 2x2 stride-2 conv (taps = 1, Cout = 4*channels, output 2h x 2w) */
-  int precision;           /* 3: split-bf16 x3 (fp32 parity); 1: single bf16 pass */
+  int precision;           /* 3: split-bf16 x3 (fp32 parity); 2: fp16 + e4m3 cross terms (fp32 parity at two pass-
+                              equivalents, q operands); 1: single bf16 pass */
+  int in_fmt;              /* 0: in_planes / wp are bf16 hi/lo planes; 1: q buffers (required by precision 2) */
+  int out_fmt;             /* 0: out_planes are bf16 hi/lo planes; 1: a q buffer.  With precision 2 the layer derives the
+                              output scale itself; with precision 1/3 the caller stores it at byte 4*n beforehand */
 } ammc_conv_layer;
 int ammc_conv_layer_run(const ammc_conv_layer* layer, void* stream);
 /* w [Cout,Cin,3,3] (taps=9) or [Cout,Cin] (taps=1) -> wp [2][Cout_pad][taps*Cin_pad], zero-padded rows/columns */

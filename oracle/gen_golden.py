@@ -22,6 +22,7 @@ sys.path.insert(0, HERE)
 
 import ammc_oracle as O                      # noqa: E402
 import ref_harness                           # noqa: E402
+import digest                                # noqa: E402
 from ammcnet_aaai2021_b200 import synth     # noqa: E402
 
 GOLD = os.path.join(ROOT, "tests", "golden")
@@ -154,9 +155,12 @@ def gen_amft(ref_unet):
         for kname, v in stats.items():
             _close(v, sdt[kname], 1e-5, name + ".train." + kname)
         extra = {}
-        if c["C"] <= 64:      # weight grads only for the small case (fixture size)
-            for pn, pv in mt.named_parameters():
+        for i, (pn, pv) in enumerate(mt.named_parameters()):
+            if c["C"] <= 64 or pv.grad.dim() == 1:      # full gradients: small case, and every BatchNorm vector
                 extra["g_" + pn] = pv.grad
+            else:                                       # shipped C=512 conv weights: reduced forms (oracle/digest.py)
+                for dk, dv in digest.weight_grad_digest(pv.grad, c["seed"] + 4000 + i).items():
+                    extra["gd_%s_%s" % (dk, pn)] = dv
         _save(name, dict(kind="amft", **c), x=yx, y=yy, train_x=tx, train_y=ty,
               g_zx=zxg.grad, g_zy=zyg.grad,
               **{"stat_" + k: sdt[k] for k in stats}, **extra)
@@ -375,15 +379,14 @@ def gen_losses():
 def main():
     torch.set_num_threads(os.cpu_count())
     ref_unet, ref_utils, ref_eval = ref_harness.import_reference()
-    gen_memory(ref_unet)
-    gen_amft(ref_unet)
-    gen_psnr(ref_utils)
-    gen_scores(ref_eval)
-    gen_records()
-    gen_generator(ref_unet)
-    gen_preprocess()
-    gen_losses()
-    print("all fixtures written to", GOLD)
+    only = set(sys.argv[1:])                    # e.g. `python oracle/gen_golden.py amft` rewrites one family
+    steps = [("memory", lambda: gen_memory(ref_unet)), ("amft", lambda: gen_amft(ref_unet)),
+             ("psnr", lambda: gen_psnr(ref_utils)), ("scores", lambda: gen_scores(ref_eval)), ("records", gen_records),
+             ("generator", lambda: gen_generator(ref_unet)), ("preprocess", gen_preprocess), ("losses", gen_losses)]
+    for name, fn in steps:
+        if not only or name in only:
+            fn()
+    print("fixtures written to", GOLD)
 
 
 if __name__ == "__main__":

@@ -6,7 +6,7 @@ import torch
 import ammc_oracle as O
 import ammcnet_aaai2021_b200 as A
 from ammcnet_aaai2021_b200 import synth
-from conftest import load_golden, assert_close
+from conftest import load_golden, assert_close, rel_err
 
 pytestmark = pytest.mark.gpu
 MEM = ["mem_shipped", "mem_cfg1", "mem_k3", "mem_k1"]
@@ -273,10 +273,22 @@ def test_tensor_dec_matches_fp32_gather_and_golden(dec_mode):
     for mode in ("fp32", "tensor"):
         dec_mode(mode)
         m = _module(c, p).eval()
+        m.quan.planes_format = "bf16"
         with torch.no_grad():
             out, diff, q1 = m(x.to(DEV))
         outs[mode] = (out, diff, q1, m.quan.quantize.last_idx.clone(), F_.planes_of(out))
     F_.check_pipeline_watchdog()
+    # default operand format of the module: q planes (fp16 + e4m3, precision 2 of the AMFT block) from the same epilogue
+    mq = _module(c, p).eval()
+    with torch.no_grad():
+        out_q, _, _ = mq(x.to(DEV))
+    assert torch.equal(out_q, outs["tensor"][0])
+    qp = F_.planes_of(out_q, "q")
+    assert qp is not None and F_.planes_of(out_q) is None
+    s16 = float(qp.scale())
+    assert s16 == 2.0 ** round(np.log2(s16)) and float(out_q.abs().max()) * s16 < 2 ** 15      # bound holds, power of two
+    assert float(out_q.abs().max()) * s16 >= 2 ** 9                                              # and is not absurdly loose
+    assert (qp.dequantize() - out_q).abs().max() <= 2.0 ** -13 * out_q.abs().max()
     assert torch.equal(outs["fp32"][3], outs["tensor"][3]) and torch.equal(outs["fp32"][2], outs["tensor"][2])
     assert_close(outs["tensor"][0].cpu(), outs["fp32"][0].cpu(), 1e-4, "dec tensor vs fp32")
     same = (outs["tensor"][3].cpu() == torch.as_tensor(g["idx_topk"], dtype=torch.int64)).all(1).view(c["b"], c["h"], c["w"])
@@ -299,23 +311,29 @@ def test_bridge_consumes_dec_planes_without_repacking(dec_mode):
         pre = s + ".vq_down3."
         m.load_state_dict({kk[len(pre):]: v for kk, v in p.items() if kk.startswith(pre)}, strict=True)
         mods[s] = m.to(DEV).eval()
-    br = A.bridge(in_c=C)
-    br.load_state_dict({kk[len("bridge."):]: v for kk, v in p.items() if kk.startswith("bridge.")}, strict=True)
-    br = br.to(DEV).eval()
     xr, xo = synth.features(41, b, C, 32, 32).to(DEV), synth.features(42, b, C, 32, 32).to(DEV)
-    with torch.no_grad():
-        o_r, _, _ = mods["rgb"](xr)
-        o_o, _, _ = mods["op"](xo)
-        assert F_.planes_of(o_r) is not None and F_.planes_of(o_o) is not None
-        br(o_r.clone(), o_o.clone())                    # warm-up: packs the conv weights / folds BN once
-        n0 = F_.LAUNCHES["count"]
-        y1 = br(o_r, o_o)
-        n_fused = F_.LAUNCHES["count"] - n0
-        n0 = F_.LAUNCHES["count"]
-        y2 = br(o_r.clone(), o_o.clone())               # clones carry no planes -> pack kernels run
-        n_packed = F_.LAUNCHES["count"] - n0
-    assert n_packed == n_fused + 2
-    assert torch.equal(y1[0], y2[0]) and torch.equal(y1[1], y2[1])
+    for prec, fmt, pack_launches in ((3, "bf16", 1), (2, "q", 3)):
+        br = A.bridge(in_c=C, precision=prec)
+        br.load_state_dict({kk[len("bridge."):]: v for kk, v in p.items() if kk.startswith("bridge.")}, strict=True)
+        br = br.to(DEV).eval()
+        with torch.no_grad():
+            for m in mods.values():
+                m.quan.planes_format = fmt
+            o_r, _, _ = mods["rgb"](xr)
+            o_o, _, _ = mods["op"](xo)
+            assert F_.planes_of(o_r, fmt) is not None and F_.planes_of(o_o, fmt) is not None
+            br(o_r.clone(), o_o.clone())                    # warm-up: packs the conv weights / folds BN once
+            n0 = F_.LAUNCHES["count"]
+            y1 = br(o_r, o_o)
+            n_fused = F_.LAUNCHES["count"] - n0
+            n0 = F_.LAUNCHES["count"]
+            y2 = br(o_r.clone(), o_o.clone())               # clones carry no planes -> pack kernels run
+            n_packed = F_.LAUNCHES["count"] - n0
+        assert n_packed == n_fused + 2 * pack_launches
+        if prec == 3:
+            assert torch.equal(y1[0], y2[0]) and torch.equal(y1[1], y2[1])
+        else:       # q: the epilogue's scale comes from a bound, the packer's from the exact maximum -> different rounding
+            assert rel_err(y1[0].cpu(), y2[0].cpu()) < 1e-4 and rel_err(y1[1].cpu(), y2[1].cpu()) < 1e-4
     ref = O.path_forward(xr.cpu(), xo.cpu(), *synth.frames(1, b, 3, 8, 8), p, k)
     same = (mods["rgb"].quan.quantize.last_idx.cpu() == ref["rgb"]["idx_topk"]).all() and \
            (mods["op"].quan.quantize.last_idx.cpu() == ref["op"]["idx_topk"]).all()
