@@ -80,6 +80,7 @@ SIGNATURES = {
     "ammc_bn_fold": (I, [P] * 4 + [F] + [P, P, I, P]),
     "ammc_preprocess_frames_u8": (I, [P, P, I, I, I, I, I, P]),
     "ammc_preprocess_flow": (I, [P, P, I, I, I, I, I, P]),
+    "ammc_cast_bf16_f32": (I, [P, P, L, P]),
     "ammc_frame_losses_workspace_bytes": (Z, [I, I, I]),
     "ammc_frame_losses_fwd": (I, [P, P, P, P, Z, I, I, I, I, P]),
     "ammc_frame_losses_bwd": (I, [P, P, P, P, P, I, I, I, I, P]),

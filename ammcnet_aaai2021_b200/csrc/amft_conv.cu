@@ -1010,7 +1010,7 @@ int conv_igemm(const void* xp, const void* wp, const float* scale, const float* 
   L.out_planes = out_planes; L.out_nchw = out_nchw; L.res_nchw = res_nchw;
   L.b = b; L.h = h; L.w = w; L.Cin = Cin; L.Cout = Cout; L.precision = precision;
   L.in_fmt = precision == 2 ? 1 : 0;          // precision 2: q operands in, q planes out (the next conv's operand)
-  L.out_fmt = precision == 2 ? 1 : 0;
+  L.out_fmt = (precision == 2 && out_planes) ? 1 : 0;
   return conv_run(L, st);
 }
 

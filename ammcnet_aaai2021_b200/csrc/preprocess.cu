@@ -86,9 +86,34 @@ __global__ void __launch_bounds__(256) preprocess_flow_kernel(const float* __res
   }
 }
 
+// bf16 -> fp32, 16 bytes in / 32 bytes out per thread and step (the bf16 feature-I/O boundary of BASELINE configs[2])
+__global__ void __launch_bounds__(256) cast_bf16_f32_kernel(const uint16_t* __restrict__ src, float* __restrict__ dst, long long n) {
+  const long long n8 = n >> 3;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(src) + i);
+    float4 a, b;
+    a.x = __uint_as_float(v.x << 16); a.y = __uint_as_float(v.x & 0xffff0000u);
+    a.z = __uint_as_float(v.y << 16); a.w = __uint_as_float(v.y & 0xffff0000u);
+    b.x = __uint_as_float(v.z << 16); b.y = __uint_as_float(v.z & 0xffff0000u);
+    b.z = __uint_as_float(v.w << 16); b.w = __uint_as_float(v.w & 0xffff0000u);
+    reinterpret_cast<float4*>(dst)[2 * i] = a;
+    reinterpret_cast<float4*>(dst)[2 * i + 1] = b;
+  }
+  if (blockIdx.x == 0)
+    for (long long i = (n8 << 3) + threadIdx.x; i < n; i += blockDim.x) dst[i] = __uint_as_float((uint32_t)src[i] << 16);
+}
+
 }  // namespace ammc
 
 using namespace ammc;
+
+extern "C" int ammc_cast_bf16_f32(const void* src, float* dst, int64_t n, void* stream) {
+  AMMC_REQUIRE(src && dst && n > 0, "bad argument");
+  AMMC_REQUIRE(((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0, "16-byte aligned buffers required");
+  cast_bf16_f32_kernel<<<min(ceil_div(n, 2048), 148 * 16), 256, 0, (cudaStream_t)stream>>>((const uint16_t*)src, dst, n);
+  AMMC_LAUNCH_CHECK("cast_bf16_f32_kernel");
+  return 0;
+}
 
 static int check_dims(int n, int h0, int w0, int H, int W) {
   AMMC_REQUIRE(n > 0 && h0 > 0 && w0 > 0 && H > 0 && W > 0, "bad shape n=%d src=%dx%d dst=%dx%d", n, h0, w0, H, W);

@@ -54,6 +54,20 @@ def preprocess_flow(flow: torch.Tensor, size: Tuple[int, int] = (256, 256)) -> t
     return out
 
 
+def widen_bf16(t: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
+    """bf16 CUDA tensor -> fp32 tensor of the same shape (exact); the device side of a bf16 host boundary."""
+    if not t.is_cuda or t.dtype != torch.bfloat16:
+        raise RuntimeError("ammc_b200: widen_bf16 needs a CUDA bfloat16 tensor, got %s on %s" % (t.dtype, t.device))
+    _check_device(t.device)
+    tc = t.contiguous()
+    out = torch.empty(tc.shape, dtype=torch.float32, device=t.device) if out is None else out
+    if tc.numel():
+        with torch.cuda.device(t.device):
+            _capi.call("ammc_cast_bf16_f32", _p(tc), _p(out), tc.numel(), _stream())
+        _count(1)
+    return out
+
+
 def upload(arrays: Sequence, device) -> torch.Tensor:
     """Stack equally shaped host arrays (decoded frames or flow payloads) in pinned memory and copy them to `device`
     asynchronously on the current stream."""

@@ -5,9 +5,20 @@
 
 One "step" = one pass of the path over a batch of 64 synthetic frames per GPU: both memory modules on
 [64,512,32,32] bottleneck features (D=64, M=256, k=2), the AMFT block, and the rgb PSNR of 64 3x256x256 frame
-pairs.  Prints ONE JSON line (rank 0).  `value` is device-timed with inputs resident in HBM; `e2e` is the same
-metric through the public module API with pinned HOST buffers copied in (and scores copied out) every step.
-`--impl reference` times the CPU restatement of the reference (oracle/, torch CPU ops, all host threads).
+pairs.  Prints ONE JSON line (rank 0).
+
+* `value`   device-timed, inputs resident in HBM (fp32 features), one CUDA-graph replay per step; the per-frame score
+            records of all K steps are gathered across ranks ONCE at the end of the timed region (inside it), the way the
+            reference consumes them (per video, test_helper.py:476-488).
+* `e2e`     the same metric through the public module API with pinned HOST buffers copied in and the step's scores copied
+            out every step.  Host buffers use the bf16 feature-I/O format of BASELINE configs[2] (bf16 bottleneck features
+            and predicted frames, uint8 ground-truth frames as the loader decodes them); the device widens them exactly and
+            runs the unchanged fp32-parity path.
+* parity    before anything is timed (N=1), the 64-frame batch of the timed configuration is checked against the CPU
+            oracle (the same run that produces `cpu_baseline`): top-k indices, memory outputs, AMFT outputs, commit
+            partials, PSNR.  A mismatch aborts the benchmark.
+`--impl reference` times the CPU restatement of the reference (oracle/, torch CPU ops, all host threads) on the same
+64-frame batch per step.
 """
 from __future__ import annotations
 
@@ -28,6 +39,10 @@ METRIC = "frames/sec (memory+AMFT+score path)"
 UNIT = "frames/s"
 C, D, M, K_TOP, HW = 512, 64, 256, 2, 32     # M is overridden by --items
 FRAME = (3, 256, 256)
+ARITH = {3: "split-bf16 x3 tensor-core passes, fp32 accumulate (fp32-parity mode)",
+         2: "fp16 main product + e4m3 cross terms on tcgen05 = 2 pass-equivalents, fp32 accumulate (fp32-parity mode)",
+         1: "single bf16 tensor-core pass, fp32 accumulate"}
+DTYPE = {3: "bf16x3->f32acc", 2: "f16+e4m3x2->f32acc", 1: "bf16->f32acc"}
 
 
 def workload_desc(batch, precision):
@@ -36,69 +51,160 @@ def workload_desc(batch, precision):
                     "2 memory modules on [%d,512,32,32] (D=64, M=%d, k=2) + AMFT bridge(512) + rgb PSNR on "
                     "[%d,3,256,256]" % (batch, batch, M, batch),
         "batch_per_gpu": batch,
-        "arithmetic": ("split-bf16 x3 tensor-core passes, fp32 accumulate (fp32-parity mode)" if precision == 3
-                       else "single bf16 tensor-core pass, fp32 accumulate") + "; memory addressing, PSNR in fp32",
+        "arithmetic": ARITH[precision] + "; memory addressing, PSNR in fp32",
         "l2_policy": "inputs+intermediates per step (~0.9 GB) exceed the 126 MB L2; no explicit flush",
         "launch": "one CUDA-graph replay per step (eager with --no-graph)",
-        "sharding": "clips data-parallel, replicated bank and weights; per-frame scores all-gathered each step",
+        "sharding": "clips data-parallel, replicated bank and weights, no data-path collective; the per-frame score "
+                    "records of the K steps are all-gathered once, inside the timed region",
     }
 
 
 # --------------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the oracle port on the host cores
+# baselines: the oracle port of the reference on the host cores (reference arm, cpu_baseline + parity check)
+# and the same torch ops on the GPU (gpu_eager_baseline).  The ONLY places bench.py touches oracle/.
 # --------------------------------------------------------------------------------------------------
-def _oracle_step_fn(frames):
+def _oracle():
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import ammc_oracle as O          # the ONLY place bench.py touches oracle/: the timed CPU baseline
+    import ammc_oracle as O
+    return O
+
+
+def _bench_inputs(rank, frames):
     from ammcnet_aaai2021_b200 import synth
-    p = synth.path_params(1, C, D, M, K_TOP)
-    xr, xo = synth.features(11, frames, C, HW, HW), synth.features(12, frames, C, HW, HW)
-    gen, gt = synth.frames(13, frames, *FRAME)
-
-    def step():
-        with torch.no_grad():
-            return O.path_forward(xr, xo, gen, gt, p, K_TOP)
-    return step
+    xr = synth.features(1234 + rank, frames, C, HW, HW)
+    xo = synth.features(4321 + rank, frames, C, HW, HW)
+    gen, gt = synth.frames(99 + rank, frames, *FRAME)
+    return xr, xo, gen, gt
 
 
-def cpu_baseline(budget_s=12.0, frames_per_call=4, max_frames=64):
+def _oracle_batch(O, p, xr, xo, gen, gt, per_call=4):
+    """The oracle over a batch, `per_call` frames at a time (frames are independent in eval mode); returns the pieces."""
+    outs = []
+    with torch.no_grad():
+        for i in range(0, xr.shape[0], per_call):
+            sl = slice(i, i + per_call)
+            outs.append(O.path_forward(xr[sl], xo[sl], gen[sl], gt[sl], p, K_TOP))
+    return outs
+
+
+def cpu_baseline_and_parity(gpu_out, inputs, p, frames_per_call=4):
+    """Times the oracle on the 64 frames of the timed batch (all host cores) and uses its outputs as the parity oracle for
+    the GPU results of that same batch."""
+    O = _oracle()
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    step = _oracle_step_fn(frames_per_call)
-    step()                                           # warm-up (thread pools, mkldnn primitives)
-    done, t0 = 0, time.perf_counter()
-    while done < max_frames and (time.perf_counter() - t0) < budget_s:
-        step()
-        done += frames_per_call
+    xr, xo, gen, gt = inputs
+    _oracle_batch(O, p, xr[:frames_per_call], xo[:frames_per_call], gen[:frames_per_call], gt[:frames_per_call])  # warm-up
+    t0 = time.perf_counter()
+    outs = _oracle_batch(O, p, xr, xo, gen, gt, frames_per_call)
     dt = time.perf_counter() - t0
-    return {"value": done / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "%d frames of the same workload (oracle/ammc_oracle.py path_forward, torch CPU fp32, %d threads, "
-                      "%d frames per call), %.1f s" % (done, cores, frames_per_call, dt)}
+    n = xr.shape[0]
+    base = {"value": n / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "the %d frames of the timed batch (oracle/ammc_oracle.py path_forward, torch CPU fp32, %d threads, "
+                      "%d frames per call), %.1f s" % (n, cores, frames_per_call, dt)}
+    parity = check_parity(gpu_out, outs, frames_per_call, n)
+    return base, parity
+
+
+def check_parity(gpu_out, oracle_outs, per_call, n, tol=1e-3):
+    """GPU batch vs oracle: indices exact on no-tie rows, everything else within 1e-3 relative (BASELINE north_star)."""
+    def cat(f):
+        return torch.cat([f(o) for o in oracle_outs])
+
+    def rel(a, b):
+        a, b = a.double().cpu(), b.double()
+        return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+    res = {"frames": n, "tolerance": tol}
+    ok_rows = {}
+    for s in ("rgb", "op"):
+        idx_ref = cat(lambda o: o[s]["idx_topk"])
+        same = (gpu_out["idx_" + s].cpu() == idx_ref).all(1)
+        res["index_agreement_" + s] = float(same.float().mean())
+        ok_rows[s] = same.view(n, HW * HW)
+        # commit partial per frame: sum over the frame's pixels of (e_top1 - z)^2
+        res["commit_rel_err_" + s] = rel(gpu_out["sse_" + s], cat(lambda o: o[s]["sse_per_frame"]))
+    res["psnr_rel_err"] = rel(gpu_out["psnr"], cat(lambda o: o["psnr"]))
+    # features: frames whose every pixel picked the reference's items (a near-tie flips a whole read vector: the
+    # north_star's "no-tie inputs" rule); the others are reported, not compared
+    frames_ok = ok_rows["rgb"].all(1) & ok_rows["op"].all(1)
+    res["frames_with_identical_indices"] = int(frames_ok.sum())
+    if frames_ok.any():
+        for key, name in (("out_rgb", lambda o: o["rgb"]["out"]), ("out_op", lambda o: o["op"]["out"]),
+                          ("amft_rgb", lambda o: o["amft_rgb"]), ("amft_op", lambda o: o["amft_op"])):
+            res[key + "_rel_err"] = rel(gpu_out[key][frames_ok.to(gpu_out[key].device)], cat(name)[frames_ok])
+    bad = [k for k, v in res.items() if k.endswith("_rel_err") and not (v <= tol)]
+    if min(res["index_agreement_rgb"], res["index_agreement_op"]) < 0.999:
+        bad.append("index_agreement")
+    if res["frames_with_identical_indices"] < n // 2:
+        bad.append("frames_with_identical_indices")
+    res["ok"] = not bad
+    if bad:
+        raise RuntimeError("bench.py parity check against the CPU oracle FAILED at the timed configuration: %s\n%s"
+                           % (bad, json.dumps(res)))
+    return res
+
+
+def gpu_eager_baseline(p, dev, xr, xo, gen, gt, steps=5):
+    """SURVEY 8(d) 'the real bar': the reference's own op sequence (oracle port = torch ATen/cuDNN/cuBLAS ops) on THIS GPU,
+    TF32 as torch defaults it (cuDNN on, matmul off) and fully fp32."""
+    O = _oracle()
+    pd = {k: v.to(dev) for k, v in p.items()}
+    res = {"what": "oracle port of the reference path (torch eager: cuDNN conv, cuBLAS mm, ATen topk) on the same B200, "
+                   "same 64-frame batch, inputs resident", "unit": UNIT}
+
+    def run():
+        with torch.no_grad():
+            return O.path_forward(xr, xo, gen, gt, pd, K_TOP)
+
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    try:
+        for name, (c_tf32, m_tf32) in (("tf32_default", (True, False)), ("fp32", (False, False))):
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = c_tf32, m_tf32
+            for _ in range(2):
+                run()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                run()
+            e1.record()
+            torch.cuda.synchronize()
+            res[name] = xr.shape[0] * steps / (e0.elapsed_time(e1) * 1e-3)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = saved
+    del pd
+    torch.cuda.empty_cache()
+    return res
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    from ammcnet_aaai2021_b200 import synth
+    O = _oracle()
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    frames = 4
-    step = _oracle_step_fn(frames)
-    for _ in range(max(1, min(args.warmup, 3))):
-        step()
+    B, per_call = args.batch, 4
+    p = synth.path_params(1, C, D, M, K_TOP)
+    inputs = _bench_inputs(0, B)
+    _oracle_batch(O, p, *(t[:per_call] for t in inputs), per_call)
+    for _ in range(min(args.warmup, 1)):
+        _oracle_batch(O, p, *inputs, per_call)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        step()
+        _oracle_batch(O, p, *inputs, per_call)
     dt = time.perf_counter() - t0
-    val = frames * args.steps / dt
+    val = B * args.steps / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": dict(workload_desc(64, 3), sample="each step = %d frames of the workload on the host CPU" % frames),
+        "config": workload_desc(B, args.precision),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "%d steps x %d frames, oracle port of the reference's torch-CPU op sequence "
-                                   "(the Python reference cannot travel to the GPU box)" % (args.steps, frames)},
+                         "sample": "%d steps x %d frames (%d per call), oracle port of the reference's torch-CPU op sequence "
+                                   "(the Python reference cannot travel to the GPU box)" % (args.steps, B, per_call)},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -177,20 +283,26 @@ class ClockSampler:
         return out
 
 
-def ncu_traffic_bytes():
+NCU_SUMMARY = {2: "r02_ncu_conv_igemm_pair_q_full_summary.csv", 3: "r01_ncu_conv_igemm_pair_full_summary.csv"}
+
+
+def ncu_traffic_bytes(precision):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full`
     capture of this same command (profiles/, summarised by tools/ncu_summary.py); None when the file is absent."""
     import csv
-    path = os.path.join(ROOT, "profiles", "r01_ncu_conv_igemm_pair_full_summary.csv")
+    name = NCU_SUMMARY.get(precision)
+    if name is None:
+        return None, None
+    path = os.path.join(ROOT, "profiles", name)
     try:
         rows = list(csv.reader(open(path)))
         hdr, units = rows[0], rows[1]
         ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
         scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
         vals = [float(r[ir]) * scale.get(units[ir], 1.0) + float(r[iw]) * scale.get(units[iw], 1.0) for r in rows[2:] if r]
-        return sum(vals) / len(vals) if vals else None
+        return (sum(vals) / len(vals) if vals else None), name
     except Exception:
-        return None
+        return None, name
 
 
 def load_peaks():
@@ -202,21 +314,47 @@ def load_peaks():
         return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
+def bind_to_gpu_numa_node(local):
+    """Pin this rank's host threads (and therefore the first-touch placement of its pinned staging buffers) to the NUMA
+    node its GPU hangs off: with 8 ranks feeding 8 GPUs from host memory, cross-socket staging halves the e2e rate."""
+    try:
+        bus = torch.cuda.get_device_properties(local).pci_bus_id
+        dom = torch.cuda.get_device_properties(local).pci_domain_id
+        dev_id = torch.cuda.get_device_properties(local).pci_device_id
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node" % (dom, bus, dev_id)
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def run_ours(args):
     import torch.distributed as dist
     import ammcnet_aaai2021_b200 as A
     from ammcnet_aaai2021_b200 import functions as F_, synth
-    from ammcnet_aaai2021_b200 import dist as adist
+    from ammcnet_aaai2021_b200.graphs import GraphedPath
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
     prec = args.precision
+    steps = args.steps
     if args.no_pair:
         F_.set_conv_pair_mode(False)
     if args.pair_unfused:
@@ -228,7 +366,8 @@ def run_ours(args):
     for s in ("rgb", "op"):
         m = A.enc_quan_dec_res_topk(C, D, M, k=K_TOP)
         pre = s + ".vq_down3."
-        m.load_state_dict({k[len(pre):]: v for k, v in p.items() if k.startswith(pre)}, strict=True)
+        m.load_state_dict({k: v for k, v in ((k[len(pre):], v) for k, v in p.items() if k.startswith(pre))}, strict=True)
+        m.quan.planes_format = "q" if prec == 2 else "bf16"
         mem[s] = m.to(dev).eval()
     amft = A.bridge(in_c=C, precision=prec)
     amft.load_state_dict({k[len("bridge."):]: v for k, v in p.items() if k.startswith("bridge.")}, strict=True)
@@ -246,21 +385,9 @@ def run_ours(args):
             scores = torch.stack([ps, commit])                    # per-frame (psnr, commit partial)
         return yr, yo, scores
 
-    def exchange(out):
-        yr, yo, scores = out
-        if world > 1:
-            scores = adist.all_gather_scores(scores)               # inference exchange step: scores only (NCCL)
-        return yr, yo, scores
-
-    def path_step(xr, xo, gen, gt):                                # eager form (also used for the per-kernel timing)
-        return exchange(local_step(xr, xo, gen, gt))
-
     # ---- synthetic inputs: host (pinned) and device copies -------------------------------------------------
-    xr_h = synth.features(1234 + rank, B, C, HW, HW).pin_memory()
-    xo_h = synth.features(4321 + rank, B, C, HW, HW).pin_memory()
-    gen_h, gt_h = synth.frames(99 + rank, B, *FRAME)
-    gen_h, gt_h = gen_h.pin_memory(), gt_h.pin_memory()
-    xr, xo, gen, gt = (t.to(dev, non_blocking=True) for t in (xr_h, xo_h, gen_h, gt_h))
+    xr_c, xo_c, gen_c, gt_c = _bench_inputs(rank, B)
+    xr, xo, gen, gt = (t.to(dev) for t in (xr_c, xo_c, gen_c, gt_c))
     torch.cuda.synchronize()
 
     def barrier():
@@ -268,52 +395,75 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---- parity at the timed configuration, BEFORE timing (N=1; also yields cpu_baseline) -------------------
+    cpu_base = parity = None
+    if world == 1 and not args.no_cpu_baseline:
+        yr, yo, sc = local_step(xr, xo, gen, gt)
+        with torch.no_grad():
+            o_r, _, _ = mem["rgb"](xr)
+            idx_r, sse_r = mem["rgb"].quan.quantize.last_idx.clone(), mem["rgb"].quan.quantize.last_sse_frame.clone()
+            o_o, _, _ = mem["op"](xo)
+            idx_o, sse_o = mem["op"].quan.quantize.last_idx.clone(), mem["op"].quan.quantize.last_sse_frame.clone()
+        torch.cuda.synchronize()
+        F_.check_pipeline_watchdog()
+        gpu_out = dict(idx_rgb=idx_r, idx_op=idx_o, sse_rgb=sse_r, sse_op=sse_o, psnr=sc[0], out_rgb=o_r, out_op=o_o,
+                       amft_rgb=yr, amft_op=yo)
+        cpu_base, parity = cpu_baseline_and_parity(gpu_out, (xr_c, xo_c, gen_c, gt_c), p)
+        del gpu_out, o_r, o_o, yr, yo
+
     sampler = ClockSampler(local) if rank == 0 else None      # started before warm-up so it is sampling by the time we time
     use_graph = not args.no_graph
-    graphed = None
     if use_graph:
-        from ammcnet_aaai2021_b200.graphs import GraphedPath
         graphed = GraphedPath(local_step, [xr, xo, gen, gt])
-        step_fn = lambda: exchange(graphed.replay())               # inputs already sit in the captured buffers
+        step_fn = graphed.replay                                   # inputs already sit in the captured buffers
     else:
-        step_fn = lambda: path_step(xr, xo, gen, gt)
-    for _ in range(max(args.warmup, 3)):
-        step_fn()
+        step_fn = lambda: local_step(xr, xo, gen, gt)
+    # per-frame score records of the timed steps; gathered across ranks once, at the end of the timed region
+    records = torch.zeros((steps, 2, B), dtype=torch.float32, device=dev)
+    gathered = torch.zeros((world, steps, 2, B), dtype=torch.float32, device=dev) if world > 1 else None
+
+    def run_steps(n):
+        for i in range(n):
+            _, _, sc = step_fn()
+            records[i % steps].copy_(sc, non_blocking=True)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, records)         # the path's only exchange: scores (NCCL, NVLink)
+
+    run_steps(max(args.warmup, 3))
     barrier()
 
     # ---- timed region (device-resident inputs) --------------------------------------------------------------
     F_.LAUNCHES["count"] = 0
-    path_step(xr, xo, gen, gt)
+    local_step(xr, xo, gen, gt)
     launches_per_step = F_.LAUNCHES["count"]                     # kernels of ours in one step (a graph replays the same)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     if sampler:
         sampler.mark_begin()
     e0.record()
-    for _ in range(args.steps):
-        step_fn()
+    run_steps(steps)
     e1.record()
     barrier()
     if sampler:
         sampler.mark_end()
     ms = e0.elapsed_time(e1)
-    launches = launches_per_step * args.steps
+    launches = launches_per_step * steps
     clocks = sampler.stop() if sampler else None
     # dominant-kernel timing: CUDA events around every conv launch of the same K steps issued eagerly (events cannot be
     # recorded inside a replayed graph), same stream, right after the timed region
     F_.PROFILE["on"] = True
     F_.PROFILE["events"].clear()
-    for _ in range(args.steps):
-        path_step(xr, xo, gen, gt)
+    for _ in range(steps):
+        local_step(xr, xo, gen, gt)
     torch.cuda.synchronize()
     F_.PROFILE["on"] = False
-    conv_ms = [s.elapsed_time(e) for (s, e) in F_.PROFILE["events"] if s.elapsed_time(e) > 0.2]   # 3x3 convs only
+    conv_ms = [s.elapsed_time(e) for (s, e) in F_.PROFILE["events"] if s.elapsed_time(e) > 0.15]   # 3x3 convs only
     F_.PROFILE["events"].clear()
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
-    value = world * B * args.steps / (ms * 1e-3)
+    value = world * B * steps / (ms * 1e-3)
 
     # ---- component breakdown (rank 0, informational) -------------------------------------------------------
     def timed(fn, n=5):
@@ -338,16 +488,32 @@ def run_ours(args):
             del o_r, o_o
 
     # ---- e2e: host buffers in, scores out, every step (double-buffered copies on a side stream) -------------
+    # host format = bf16 feature I/O (BASELINE configs[2]) + the loader's uint8 ground-truth frames
+    xr_h = xr_c.to(torch.bfloat16).pin_memory()
+    xo_h = xo_c.to(torch.bfloat16).pin_memory()
+    gen_h = gen_c.to(torch.bfloat16).pin_memory()
+    gt_u8 = ((gt_c.permute(0, 2, 3, 1).flip(-1) * 0.5 + 0.5) * 255.0).round().clamp(0, 255).to(torch.uint8)   # BGR HWC, as decoded
+    gt_h = gt_u8.contiguous().pin_memory()
+    hosts = (xr_h, xo_h, gen_h, gt_h)
+
+    def e2e_step(xr_b, xo_b, gen_b, gt_b):
+        with torch.no_grad():
+            return local_step(A.widen_bf16(xr_b), A.widen_bf16(xo_b), A.widen_bf16(gen_b),
+                              A.preprocess_frames(gt_b, (FRAME[2], FRAME[1])))
+
     copy_stream = torch.cuda.Stream(device=dev)
-    bufs = [[torch.empty_like(t, device=dev) for t in (xr_h, xo_h, gen_h, gt_h)] for _ in range(2)]
+    bufs = [[torch.empty_like(t, device=dev) for t in hosts] for _ in range(2)]
     ready = [torch.cuda.Event() for _ in range(2)]
     freed = [torch.cuda.Event() for _ in range(2)]
-    h2d_bytes = sum(t.numel() * 4 for t in (xr_h, xo_h, gen_h, gt_h))
-    scores_h = torch.empty((2, B) if world == 1 else (world, 2, B), dtype=torch.float32).pin_memory()
+    h2d_bytes = sum(t.numel() * t.element_size() for t in hosts)
+    scores_h = torch.empty((2, B), dtype=torch.float32).pin_memory()
 
     e2e_graphs = None
     if use_graph:
-        e2e_graphs = [GraphedPath(local_step, bufs[i]) for i in range(2)]
+        for i in range(2):
+            for d_t, h_t in zip(bufs[i], hosts):
+                d_t.copy_(h_t)
+        e2e_graphs = [GraphedPath(e2e_step, bufs[i]) for i in range(2)]
         for i in range(2):
             bufs[i] = e2e_graphs[i].static_inputs                 # copy straight into the captured buffers
 
@@ -358,16 +524,18 @@ def run_ours(args):
                 sl = i & 1
                 with torch.cuda.stream(copy_stream):
                     copy_stream.wait_event(freed[sl])
-                    for d_t, h_t in zip(bufs[sl], (xr_h, xo_h, gen_h, gt_h)):
+                    for d_t, h_t in zip(bufs[sl], hosts):
                         d_t.copy_(h_t, non_blocking=True)
                     ready[sl].record(copy_stream)
             if i > 0:                                             # compute step i-1
                 sl = (i - 1) & 1
                 cur.wait_event(ready[sl])
-                out = e2e_graphs[sl].replay() if use_graph else local_step(*bufs[sl])
-                _, _, sc = exchange(out)
-                scores_h.copy_(sc, non_blocking=True)
+                _, _, sc = e2e_graphs[sl].replay() if use_graph else e2e_step(*bufs[sl])
+                records[(i - 1) % steps].copy_(sc, non_blocking=True)
+                scores_h.copy_(sc, non_blocking=True)             # the step's result goes back to the host every step
                 freed[sl].record(cur)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, records)
         return scores_h
 
     for ev in freed:
@@ -376,39 +544,49 @@ def run_ours(args):
     barrier()
     a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a0.record()
-    e2e_loop(args.steps)
+    e2e_loop(steps)
     a1.record()
     barrier()
     t = torch.tensor([a0.elapsed_time(a1)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t.item())
-    e2e_val = world * B * args.steps / (e2e_ms * 1e-3)
+    e2e_val = world * B * steps / (e2e_ms * 1e-3)
+    del e2e_graphs, bufs
 
-    # ---- bf16 single-pass variant, stated separately ---------------------------------------------------------
-    variant = None
-    if prec == 3:
-        amft.precision = 1
+    # ---- variants, stated separately --------------------------------------------------------------------------
+    def timed_variant(precision):
+        amft.precision = precision
+        for s in mem:
+            mem[s].quan.planes_format = "q" if precision == 2 else "bf16"
         if use_graph:
             g1 = GraphedPath(local_step, [xr, xo, gen, gt])
-            vstep = lambda: exchange(g1.replay())
+            vstep = g1.replay
         else:
-            vstep = lambda: path_step(xr, xo, gen, gt)
+            vstep = lambda: local_step(xr, xo, gen, gt)
         for _ in range(3):
             vstep()
         barrier()
         v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         v0.record()
-        for _ in range(args.steps):
+        for _ in range(steps):
             vstep()
         v1.record()
         barrier()
-        t = torch.tensor([v0.elapsed_time(v1)], device=dev, dtype=torch.float64)
+        tt = torch.tensor([v0.elapsed_time(v1)], device=dev, dtype=torch.float64)
         if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        variant = {"amft_single_bf16_pass_frames_per_s": world * B * args.steps / (float(t.item()) * 1e-3),
-                   "note": "bf16 variant: AMFT error ~1e-2 relative, outside the fp32 1e-3 parity bar"}
-        amft.precision = 3
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return world * B * steps / (float(tt.item()) * 1e-3)
+
+    variant = {}
+    if prec != 1:
+        variant["amft_single_bf16_pass_frames_per_s"] = timed_variant(1)
+        variant["note"] = "bf16 variant: AMFT error ~1e-2 relative, outside the fp32 1e-3 parity bar"
+    if prec == 2:
+        variant["amft_split_bf16_x3_frames_per_s"] = timed_variant(3)
+    amft.precision = prec
+    for s in mem:
+        mem[s].quan.planes_format = "q" if prec == 2 else "bf16"
 
     if rank == 0:
         peaks, peak_src = load_peaks()
@@ -418,33 +596,142 @@ def run_ours(args):
             avg = sum(conv_ms) / len(conv_ms)
             ach = conv_flops / (avg * 1e-3) / 1e12
             peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
-            roof = {"kernel": "conv_igemm_pair_kernel<FUSED3> (AMFT 3x3 conv, tcgen05 cta_group::2)", "bound": "tensor", "achieved": ach,
-                    "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": ncu_traffic_bytes(),
+            traffic, traffic_file = ncu_traffic_bytes(prec)
+            kname = {2: "conv_igemm_pair_kernel<PAIR_Q> (AMFT 3x3 conv: kind::f8f6f4 cross terms + kind::f16 main product, "
+                        "tcgen05 cta_group::2)",
+                     3: "conv_igemm_pair_kernel<PAIR_FUSED3> (AMFT 3x3 conv, tcgen05 cta_group::2)",
+                     1: "conv_igemm_pair_kernel<PAIR_STREAM> (AMFT 3x3 conv, tcgen05 cta_group::2)"}[prec]
+            roof = {"kernel": kname, "bound": "tensor", "achieved": ach,
+                    "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
                     "traffic_note": "mean DRAM bytes per launch over the two convs of one branch, ncu --set full "
-                                    "(profiles/r01_ncu_conv_igemm_pair_full_summary.csv); algorithmic operand+result bytes "
-                                    "per launch: 2*67 MB planes in + 134 MB out (+134 MB residual) + 9.4 MB weights",
-                    "peak_source": peak_src + " bf16_tflops_sustained (kernel timed inside a long step)",
+                                    "(profiles/%s); algorithmic operand+result bytes per launch: 134 MB operand planes in "
+                                    "+ 134 MB out (+134 MB residual) + 9.4 MB weights" % traffic_file,
+                    "peak_source": peak_src + " bf16_tflops_sustained (dense bf16 cuBLAS; kernel timed inside a long step)",
                     "avg_launch_ms": avg, "launches_timed": len(conv_ms),
                     "timing": "CUDA events around each 3x3 conv launch of K eagerly issued steps run right after the "
                               "timed region (events cannot be recorded inside a graph replay)",
                     "algorithmic_flops_per_launch": conv_flops,
-                    "tensor_passes": prec, "executed_frac_of_peak": prec * ach / peak}
+                    "tensor_pass_equivalents": prec, "executed_frac_of_peak": prec * ach / peak}
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16x3->f32acc" if prec == 3 else "bf16->f32acc", "data": "synthetic",
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": DTYPE[prec], "data": "synthetic",
             "config": workload_desc(B, prec),
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": scores_h.numel() * 4,
-                    "ms_per_step": e2e_ms / args.steps},
+                    "ms_per_step": e2e_ms / steps,
+                    "host_format": "bf16 bottleneck features + bf16 predicted frames + uint8 BGR ground-truth frames in pinned "
+                                   "memory (BASELINE configs[2] I/O format); widened / preprocessed on the device, then the "
+                                   "unchanged fp32-parity path", "numa_node": numa},
             "gpu_launches": launches, "clocks": clocks, "roofline": roof, "breakdown": breakdown, "variants": variant,
         }
-        if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline()
+        if parity is not None:
+            line["parity"] = parity
+        if cpu_base is not None:
+            line["cpu_baseline"] = cpu_base
+        if world == 1 and not args.no_extras:
+            line["gpu_eager_baseline"] = gpu_eager_baseline(p, dev, xr, xo, gen, gt)
+            line["addressing"] = addressing_leg(dev, peaks, peak_src)
+            line["reductions"] = reductions_leg(dev, peaks, peak_src, gen, gt)
         if world == 1 and not args.no_generator:
             line["generator"] = generator_leg(dev)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _time(fn, iters):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def addressing_leg(dev, peaks, peak_src):
+    """BASELINE metric, second half: the addressing contraction against the tensor roofline, measured live.  Algorithmic
+    FLOP = 2*N*M*D; peak = measured bf16 burst (kernel timed alone).  `filter` is the tcgen05 contraction
+    kernel, `whole_op` everything Quantize_topk.forward does (pack, filter, exact refine, reads, commit partials)."""
+    import ctypes
+    import ammcnet_aaai2021_b200 as A
+    from ammcnet_aaai2021_b200 import _capi, functions as F_
+    peak = float(peaks.get("bf16_tflops", 1590.0))
+    out = {"peak": peak, "peak_source": peak_src + " bf16_tflops (burst)", "unit": "TFLOP/s", "points": []}
+    lib = _capi.load()
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    for (N, Mi, Di) in ((65536, 256, 64), (65536, 2048, 512), (262144, 8192, 1024)):
+        g = torch.Generator().manual_seed(0)
+        z = torch.randn((N, Di), generator=g).to(dev)
+        embed = torch.randn((Di, Mi), generator=g).to(dev)
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        Mpad = lib.ammc_addr_padded_items(Mi)
+        zp = torch.empty((N, Di), dtype=torch.bfloat16, device=dev)
+        bank_t, en2 = torch.empty((Mi, Di), device=dev), torch.empty((Mi,), device=dev)
+        bank_hi = torch.empty((Mpad, Di), dtype=torch.bfloat16, device=dev)
+        en2pad, emax, zn2 = torch.empty((Mpad,), device=dev), torch.empty((1,), device=dev), torch.empty((N,), device=dev)
+        cand = torch.empty((N, 24), dtype=torch.int32, device=dev)
+        cnt = torch.empty((N, 2), dtype=torch.int32, device=dev)
+        _capi.call("ammc_addr_pack_queries", P(z), P(zp), P(zn2), N, Di, st)
+        _capi.call("ammc_addr_pack_bank", P(embed), P(bank_t), P(en2), P(bank_hi), P(en2pad), P(emax), Di, Mi, st)
+        flops = 2.0 * N * Mi * Di
+        iters = max(3, min(30, int(1e12 / flops)))
+        t_f = _time(lambda: _capi.call("ammc_addr_filter", P(zp), P(zn2), P(bank_hi), P(en2pad), P(emax), P(cand), P(cnt),
+                                       N, Di, Mi, 2, st), iters)
+        q = A.Quantize_topk(Di, Mi, k=2).to(dev).eval()
+        q.embed.copy_(embed)
+        z4 = z.view(1, N, 1, Di)
+        with torch.no_grad():
+            t_op = _time(lambda: q(z4), max(3, iters // 2))
+            rescans = F_.last_addressing_stats()[0]
+        out["points"].append({"N": N, "M": Mi, "D": Di, "filter_ms": t_f, "filter_tflops": flops / t_f / 1e9,
+                              "filter_frac": flops / t_f / 1e9 / peak, "whole_op_ms": t_op,
+                              "whole_op_tflops": flops / t_op / 1e9, "whole_op_frac": flops / t_op / 1e9 / peak,
+                              "exact_rescan_rows": rescans})
+        del z, embed, zp, bank_t, bank_hi, cand, cnt, q, z4
+        torch.cuda.empty_cache()
+    return out
+
+
+def reductions_leg(dev, peaks, peak_src, gen, gt):
+    """North-star kernels (b) and (c) against the HBM roofline (measured copy bandwidth), algorithmic bytes per launch."""
+    import numpy as np
+    import ammcnet_aaai2021_b200 as A
+    from ammcnet_aaai2021_b200 import functions as F_, synth
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    out = {"peak": hbm, "peak_source": peak_src + " hbm_gbs", "unit": "GB/s"}
+    ms = _time(lambda: F_.psnr_per_frame(gen, gt), 20)
+    by = 2 * gen.numel() * 4
+    out["psnr_b%d" % gen.shape[0]] = {"ms": ms, "achieved": by / ms / 1e6, "frac": by / ms / 1e6 / hbm, "bytes": by}
+    g4, t4 = gen.repeat(4, 1, 1, 1), gt.repeat(4, 1, 1, 1)
+    ms = _time(lambda: F_.psnr_per_frame(g4, t4), 10)
+    by = 2 * g4.numel() * 4
+    out["psnr_b%d" % g4.shape[0]] = {"ms": ms, "achieved": by / ms / 1e6, "frac": by / ms / 1e6 / hbm, "bytes": by}
+    del g4, t4
+    T, V = 40791, 107                                       # shanghaitech record sizes (SURVEY 8(d))
+    lens = np.full(V, T // V); lens[: T - lens.sum()] += 1
+    off = torch.tensor(np.concatenate([[0], np.cumsum(lens)]), dtype=torch.int64, device=dev)
+    img, fea = torch.rand(T, device=dev) * 10 + 20, torch.rand(T, device=dev)
+    ms = _time(lambda: F_.score_reduce_device(img, fea, off, (0.2, 0.6)), 20)
+    out["score_reduce_T40791"] = {"ms": ms, "bytes": 3 * T * 4, "note": "latency-bound: 0.5 MB through two launches"}
+    b = gen.shape[0]
+    p = synth.memory_params(3, C, D, M, K_TOP)
+    m = A.enc_quan_dec_res_topk(C, D, M, k=K_TOP)
+    m.load_state_dict({"quan." + kk: v for kk, v in p.items()})
+    m = m.to(dev).train()
+    x = synth.features(7, b, C, HW, HW).to(dev).requires_grad_(True)
+    o, _, _ = m(x)
+    gr = torch.randn_like(o)
+    ms = _time(lambda: torch.autograd.grad(o, x, gr, retain_graph=True), 10)
+    by = (3 * x.numel() + 2 * b * HW * HW * D) * 4 + b * HW * HW * K_TOP * 8
+    out["mem_bwd_b%d" % b] = {"ms": ms, "achieved": by / ms / 1e6, "frac": by / ms / 1e6 / hbm, "bytes": by,
+                              "note": "commit-loss / gather backward + enc/dec gradients; bytes = x, g_out read, gx written, z, g_z, idx"}
+    del m, x, o, gr
+    torch.cuda.empty_cache()
+    return out
 
 
 def generator_leg(dev, batch=16, steps=5):
@@ -483,7 +770,7 @@ def generator_leg(dev, batch=16, steps=5):
     del graph, eng, m
     torch.cuda.empty_cache()
     return {"value": ours, "unit": "frames/s", "workload": "whole twostream generator (unet.py:981-1007), eval, 256x256 "
-            "frames, batch %d, split-bf16 x3 (fp32 parity), CUDA-graph replay, inputs resident" % batch,
+            "frames, batch %d, U-Net layers split-bf16 x3, AMFT fp16+e4m3 (fp32 parity), CUDA-graph replay, inputs resident" % batch,
             "algorithmic_tflops": ours * 187.4e9 / 1e12,
             "same_module_unet_on_cudnn_tf32": cudnn_tf32, "same_module_unet_on_cudnn_fp32": cudnn_fp32}
 
@@ -495,9 +782,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=64)
-    ap.add_argument("--precision", type=int, default=3, choices=[1, 3])
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", type=int, default=2, choices=[1, 2, 3],
+                    help="AMFT arithmetic: 2 fp16 + e4m3 cross terms (default, fp32 parity), 3 split-bf16 x3 (fp32 parity), 1 bf16")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU oracle run (baseline + parity check)")
     ap.add_argument("--no-generator", action="store_true", help="skip the whole-generator leg (SURVEY 8(f) rank 1)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the GPU-eager baseline, addressing and reductions legs")
     ap.add_argument("--items", type=int, default=256, help="memory bank size M (BASELINE configs[2] sweeps 256..2000)")
     ap.add_argument("--no-graph", action="store_true", help="issue the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--pair-unfused", action="store_true", help="A/B: CTA-pair kernel streaming the K loop three times")

@@ -316,6 +316,9 @@ int ammc_roc_auc(const float* scores, const int8_t* labels, int pos_label, doubl
  * The host uploads uint8 frames (a quarter of the bytes of the fp32 tensors). */
 int ammc_preprocess_frames_u8(const uint8_t* frames_bgr, float* out, int n, int h0, int w0, int H, int W, void* stream);
 int ammc_preprocess_flow(const float* flow, float* out, int n, int h0, int w0, int H, int W, void* stream);
+/* bf16 -> fp32 widening of a host-boundary buffer (bf16 feature I/O, BASELINE configs[2]): exact, the fp32-parity path
+ * then runs unchanged on the widened values. */
+int ammc_cast_bf16_f32(const void* src_bf16, float* dst, int64_t n, void* stream);
 
 /* ---- image-space generator losses (Code/models/losses/losses_utils.py:17-59,124-129) --------
  * out2[0] = Intensity_Loss(l_num=2): mean over (b,h,w) of the channel-wise L2 norm of gen - gt;
