@@ -57,6 +57,7 @@ struct ConvParams {
   const float* out_qs;           // device scalar: power-of-two scale of the q output
   const float* in_qs;            // device scalars: scales of the q input and the q weights (PAIR_Q mode), else null
   const float* w_qs;
+  int a_reuse;                   // PAIR_Q, 3x3: one (H_box+2)-row A tile per (dx, channel block) serves the three dy taps
 };
 
 // m-tile index -> first image / row / column of its TMA box
@@ -294,6 +295,17 @@ constexpr int PAIR_SMEM = PAIR_BAR_OFFSET + 256 + 1024;
 // cross-term sum by 2^-4 through scale-input-d, so one TMEM accumulator holds the whole product.  Each plane is read
 // from L2 exactly once.
 enum { PAIR_STREAM = 0, PAIR_FUSED3 = 1, PAIR_Q = 2 };
+// PAIR_Q shared memory: an A ring (2 stages of two 24 KB planes: up to 192 pixel rows of 128 bytes) and a B ring (3 stages
+// of two 16 KB planes).  With a_reuse the A tile of a (dx, channel block) carries H_box + 2 image rows and the three dy
+// taps are the same tile with the UMMA descriptor advanced by W_box rows -- A traffic from L2 drops from 9 to 3 tiles per
+// channel block (the kernel is bound by L2 -> shared-memory bandwidth: 64 KB per 1024 tensor-core cycles and SM otherwise).
+constexpr int Q_A_PLANE = 192 * 128;                 // 24 KB
+constexpr int Q_A_STAGE = 2 * Q_A_PLANE;             // 48 KB
+constexpr int Q_A_STAGES = 2;
+constexpr int Q_B_STAGE = 2 * PAIR_B_BYTES;          // 32 KB
+constexpr int Q_B_STAGES = 3;
+constexpr int Q_B_RING = Q_A_STAGES * Q_A_STAGE;     // 96 KB
+static_assert(Q_B_RING + Q_B_STAGES * Q_B_STAGE == PAIR_RING_BYTES, "q rings fill the pair kernel's ring");
 template <int MODE> struct PairCfg {
   static constexpr int PLANES = MODE == PAIR_STREAM ? 1 : 2;
   static constexpr int STAGE_BYTES = PLANES * PAIR_TILE_BYTES;
@@ -315,7 +327,12 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   constexpr int PAIR_STAGE_BYTES = Cfg::STAGE_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + PAIR_BAR_OFFSET);
   uint64_t* empty_bar = full_bar + PAIR_STAGES;
-  uint64_t* tmem_full = empty_bar + PAIR_STAGES;
+  // PAIR_Q: [a_full 2][a_empty 2][b_full 3][b_empty 3] instead of [full][empty]
+  uint64_t* a_full = full_bar;
+  uint64_t* a_empty = a_full + Q_A_STAGES;
+  uint64_t* b_full = a_empty + Q_A_STAGES;
+  uint64_t* b_empty = b_full + Q_B_STAGES;
+  uint64_t* tmem_full = QMODE ? b_empty + Q_B_STAGES : empty_bar + PAIR_STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
@@ -325,14 +342,17 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   const int pair_tiles_m = (p.tiles_m + 1) >> 1;
   const int num_tiles = pair_tiles_m * p.tiles_n;
   const int kb_per_pass = p.ntaps * (p.Cin / BLOCK_K);
-  const int kb_q = p.ntaps * (p.Cin / 128);                  // PAIR_Q: 128-channel blocks, walked twice (e4m3, fp16)
-  const int kb_total = QMODE ? 2 * kb_q : (FUSED3 ? kb_per_pass : kb_per_pass * p.n_pass);
+  const int kb_total = FUSED3 ? kb_per_pass : kb_per_pass * p.n_pass;      // PAIR_Q walks its own loops
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmA);
     ptx::prefetch_tensormap(&tmB);
     if (QMODE) { ptx::prefetch_tensormap(&tmA8); ptx::prefetch_tensormap(&tmB8); }
-    for (int s = 0; s < PAIR_STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
+    if (QMODE) {
+      for (int s = 0; s < 2 * Q_A_STAGES + 2 * Q_B_STAGES; ++s) ptx::mbar_init(&a_full[s], 1);
+    } else {
+      for (int s = 0; s < PAIR_STAGES; ++s) { ptx::mbar_init(&full_bar[s], 1); ptx::mbar_init(&empty_bar[s], 1); }
+    }
     for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tmem_full[a], 1); ptx::mbar_init(&tmem_empty[a], 2 * 32 * PAIR_EPI_WARPS); }
     ptx::fence_mbar_init();
   }
@@ -349,32 +369,48 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     if (lane == 0) {
       // ------------------------------------------------------------------ TMA producer (both CTAs)
       int s = 0; uint32_t ph = 0;
+      int sa = 0, sb = 0; uint32_t pha = 0, phb = 0;       // PAIR_Q rings
       for (int t = cluster_id; t < num_tiles; t += num_clusters) {
         const int mt = (t / p.tiles_n) * 2 + (int)rank, nt = t % p.tiles_n;
         int img0, h0, w0;
         tile_origin(mt, p.groups_w, p.groups_h, p.W_box, p.H_box, p.B_box, img0, h0, w0);
         const int n0 = nt * PAIR_N + (int)rank * (PAIR_N / 2);
         if (QMODE) {
+          // A groups: with a_reuse one tile per (dx, channel block) feeding the three dy taps, else one tile per tap
+          const int ngroups = p.a_reuse ? 3 : p.ntaps, nsub = p.a_reuse ? 3 : 1;
+          const int rows_a = p.a_reuse ? p.W_box * (p.H_box + 2) * p.B_box : p.rows_valid;
           for (int phase = 0; phase < 2; ++phase) {
-            for (int tap = 0; tap < p.ntaps; ++tap) {
-              const int dy = p.ntaps == 9 ? tap / 3 - 1 : 0, dx = p.ntaps == 9 ? tap % 3 - 1 : 0;
+            for (int g = 0; g < ngroups; ++g) {
+              const int dx = p.a_reuse ? g - 1 : (p.ntaps == 9 ? g % 3 - 1 : 0);
+              const int dy0 = p.a_reuse ? -1 : (p.ntaps == 9 ? g / 3 - 1 : 0);
               for (int cc = 0; cc < p.Cin / 128; ++cc) {
-                ptx::mbar_wait(&empty_bar[s], ph ^ 1, 41);
-                if (rank == 0) ptx::mbar_expect_tx(&full_bar[s], 2 * 2 * (p.rows_valid * 128 + PAIR_B_BYTES));
-                uint8_t* a_dst = smem + s * PAIR_STAGE_BYTES;
-                const int c0 = cc * 128, k0 = tap * p.Cin + cc * 128;
-                if (phase == 0) {                       // [A_h8 | A_l8 | B_h8 | B_l8]: 128 rows x 128 e4m3 each
-                  ptx::tma_load_5d_2sm(a_dst, &tmA8, &full_bar[s], c0, w0 + dx, h0 + dy, img0, 0);
-                  ptx::tma_load_5d_2sm(a_dst + A_BYTES, &tmA8, &full_bar[s], c0, w0 + dx, h0 + dy, img0, 1);
-                  ptx::tma_load_3d_2sm(a_dst + 2 * A_BYTES, &tmB8, &full_bar[s], k0, n0, 0);
-                  ptx::tma_load_3d_2sm(a_dst + 2 * A_BYTES + PAIR_B_BYTES, &tmB8, &full_bar[s], k0, n0, 1);
-                } else {                                // [A_0 | A_1 | B_0 | B_1]: two 64-channel fp16 halves
-                  ptx::tma_load_5d_2sm(a_dst, &tmA, &full_bar[s], c0, w0 + dx, h0 + dy, img0, 0);
-                  ptx::tma_load_5d_2sm(a_dst + A_BYTES, &tmA, &full_bar[s], c0 + 64, w0 + dx, h0 + dy, img0, 0);
-                  ptx::tma_load_3d_2sm(a_dst + 2 * A_BYTES, &tmB, &full_bar[s], k0, n0, 0);
-                  ptx::tma_load_3d_2sm(a_dst + 2 * A_BYTES + PAIR_B_BYTES, &tmB, &full_bar[s], k0 + 64, n0, 0);
+                const int c0 = cc * 128;
+                ptx::mbar_wait(&a_empty[sa], pha ^ 1, 41);
+                if (rank == 0) ptx::mbar_expect_tx(&a_full[sa], 2 * 2 * rows_a * 128);
+                uint8_t* a_dst = smem + sa * Q_A_STAGE;
+                if (phase == 0) {                       // [A_h8 | A_l8]: rows of 128 e4m3
+                  ptx::tma_load_5d_2sm(a_dst, &tmA8, &a_full[sa], c0, w0 + dx, h0 + dy0, img0, 0);
+                  ptx::tma_load_5d_2sm(a_dst + Q_A_PLANE, &tmA8, &a_full[sa], c0, w0 + dx, h0 + dy0, img0, 1);
+                } else {                                // [A_0 | A_1]: two 64-channel fp16 halves
+                  ptx::tma_load_5d_2sm(a_dst, &tmA, &a_full[sa], c0, w0 + dx, h0 + dy0, img0, 0);
+                  ptx::tma_load_5d_2sm(a_dst + Q_A_PLANE, &tmA, &a_full[sa], c0 + 64, w0 + dx, h0 + dy0, img0, 0);
                 }
-                if (++s == PAIR_STAGES) { s = 0; ph ^= 1; }
+                if (++sa == Q_A_STAGES) { sa = 0; pha ^= 1; }
+                for (int sub = 0; sub < nsub; ++sub) {
+                  const int tap = p.a_reuse ? sub * 3 + g : g;
+                  const int k0 = tap * p.Cin + c0;
+                  ptx::mbar_wait(&b_empty[sb], phb ^ 1, 45);
+                  if (rank == 0) ptx::mbar_expect_tx(&b_full[sb], 2 * Q_B_STAGE);
+                  uint8_t* b_dst = smem + Q_B_RING + sb * Q_B_STAGE;
+                  if (phase == 0) {                     // [B_h8 | B_l8]
+                    ptx::tma_load_3d_2sm(b_dst, &tmB8, &b_full[sb], k0, n0, 0);
+                    ptx::tma_load_3d_2sm(b_dst + PAIR_B_BYTES, &tmB8, &b_full[sb], k0, n0, 1);
+                  } else {                              // [B_0 | B_1]
+                    ptx::tma_load_3d_2sm(b_dst, &tmB, &b_full[sb], k0, n0, 0);
+                    ptx::tma_load_3d_2sm(b_dst + PAIR_B_BYTES, &tmB, &b_full[sb], k0 + 64, n0, 0);
+                  }
+                  if (++sb == Q_B_STAGES) { sb = 0; phb ^= 1; }
+                }
               }
             }
           }
@@ -410,6 +446,7 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       // ------------------------------------------------------------------ MMA issuer (leader only)
       constexpr uint32_t idesc = ptx::umma_idesc(1, 2 * BLOCK_M, PAIR_N);
       int s = 0; uint32_t ph = 0;
+      int sa = 0, sb = 0; uint32_t pha = 0, phb = 0;       // PAIR_Q rings
       int it = 0;
       for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
         const int acc = it & 1;
@@ -417,34 +454,50 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         ptx::mbar_wait(&tmem_empty[acc], acc_ph ^ 1, 42);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * PAIR_N;
+        if (QMODE) {
+          constexpr uint32_t idesc_q = ptx::umma_idesc(0, 2 * BLOCK_M, PAIR_N);    // format 0 = F16 resp. E4M3
+          const int ngroups = p.a_reuse ? 3 : p.ntaps, nsub = p.a_reuse ? 3 : 1;
+          const int ncc = p.Cin / 128;
+          for (int phase = 0; phase < 2; ++phase) {
+            for (int gc = 0; gc < ngroups * ncc; ++gc) {
+              ptx::mbar_wait(&a_full[sa], pha, 43);
+              const uint32_t a_base = ptx::smem_u32(smem + sa * Q_A_STAGE);
+              for (int sub = 0; sub < nsub; ++sub) {
+                ptx::mbar_wait(&b_full[sb], phb, 46);
+                ptx::tc_fence_after();
+                const uint32_t a_addr = a_base + (p.a_reuse ? sub * p.W_box * 128 : 0);    // dy tap = W_box rows further
+                const uint32_t b_addr = ptx::smem_u32(smem + Q_B_RING + sb * Q_B_STAGE);
+                const uint64_t a0 = ptx::umma_desc_k_sw128(a_addr), a1 = ptx::umma_desc_k_sw128(a_addr + Q_A_PLANE);
+                const uint64_t b0 = ptx::umma_desc_k_sw128(b_addr), b1 = ptx::umma_desc_k_sw128(b_addr + PAIR_B_BYTES);
+                if (phase == 0) {                       // cross terms: h8.l8 + l8.h8, four K = 32 steps per 128-byte row
+                  const uint32_t first = (gc | sub) == 0 ? 0u : 1u;
+#pragma unroll
+                  for (int k4 = 0; k4 < 4; ++k4) {
+                    ptx::mma_f8_ss_2sm(d_tmem, a0 + 2 * k4, b1 + 2 * k4, idesc_q, k4 == 0 ? first : 1u);
+                    ptx::mma_f8_ss_2sm(d_tmem, a1 + 2 * k4, b0 + 2 * k4, idesc_q, 1u);
+                  }
+                } else {                                // main product; its first MMA folds the cross terms in (x 2^-4)
+                  if ((gc | sub) == 0) ptx::mma_f16_ss_2sm_scaled<ptx::Q_SHIFT>(d_tmem, a0, b0, idesc_q);
+                  else ptx::mma_f16_ss_2sm(d_tmem, a0, b0, idesc_q, 1u);
+#pragma unroll
+                  for (int k4 = 1; k4 < 4; ++k4) ptx::mma_f16_ss_2sm(d_tmem, a0 + 2 * k4, b0 + 2 * k4, idesc_q, 1u);
+#pragma unroll
+                  for (int k4 = 0; k4 < 4; ++k4) ptx::mma_f16_ss_2sm(d_tmem, a1 + 2 * k4, b1 + 2 * k4, idesc_q, 1u);
+                }
+                ptx::mma_commit_2sm(&b_empty[sb], 3);
+                if (++sb == Q_B_STAGES) { sb = 0; phb ^= 1; }
+              }
+              ptx::mma_commit_2sm(&a_empty[sa], 3);
+              if (++sa == Q_A_STAGES) { sa = 0; pha ^= 1; }
+            }
+          }
+          ptx::mma_commit_2sm(&tmem_full[acc], 3);
+          continue;
+        }
         for (int kb = 0; kb < kb_total; ++kb) {
           ptx::mbar_wait(&full_bar[s], ph, 43);
           ptx::tc_fence_after();
           const uint32_t a_addr = ptx::smem_u32(smem + s * PAIR_STAGE_BYTES);
-          if (QMODE) {
-            constexpr uint32_t idesc_q = ptx::umma_idesc(0, 2 * BLOCK_M, PAIR_N);    // format 0 = F16 resp. E4M3
-            const uint64_t a0 = ptx::umma_desc_k_sw128(a_addr), a1 = ptx::umma_desc_k_sw128(a_addr + A_BYTES);
-            const uint64_t b0 = ptx::umma_desc_k_sw128(a_addr + 2 * A_BYTES);
-            const uint64_t b1 = ptx::umma_desc_k_sw128(a_addr + 2 * A_BYTES + PAIR_B_BYTES);
-            if (kb < kb_q) {                            // cross terms: h8.l8 + l8.h8, four K = 32 steps per 128-byte row
-#pragma unroll
-              for (int k4 = 0; k4 < 4; ++k4) {
-                ptx::mma_f8_ss_2sm(d_tmem, a0 + 2 * k4, b1 + 2 * k4, idesc_q, (kb | k4) != 0 ? 1u : 0u);
-                ptx::mma_f8_ss_2sm(d_tmem, a1 + 2 * k4, b0 + 2 * k4, idesc_q, 1u);
-              }
-            } else {                                    // main product; its first MMA folds the cross terms in (x 2^-4)
-              if (kb == kb_q) ptx::mma_f16_ss_2sm_scaled<ptx::Q_SHIFT>(d_tmem, a0, b0, idesc_q);
-              else ptx::mma_f16_ss_2sm(d_tmem, a0, b0, idesc_q, 1u);
-#pragma unroll
-              for (int k4 = 1; k4 < 4; ++k4) ptx::mma_f16_ss_2sm(d_tmem, a0 + 2 * k4, b0 + 2 * k4, idesc_q, 1u);
-#pragma unroll
-              for (int k4 = 0; k4 < 4; ++k4) ptx::mma_f16_ss_2sm(d_tmem, a1 + 2 * k4, b1 + 2 * k4, idesc_q, 1u);
-            }
-            ptx::mma_commit_2sm(&empty_bar[s], 3);
-            if (kb == kb_total - 1) ptx::mma_commit_2sm(&tmem_full[acc], 3);
-            if (++s == PAIR_STAGES) { s = 0; ph ^= 1; }
-            continue;
-          }
           const uint64_t adesc = ptx::umma_desc_k_sw128(a_addr);
           const uint64_t bdesc = ptx::umma_desc_k_sw128(a_addr + A_BYTES);
           if (FUSED3) {
@@ -828,6 +881,7 @@ static int launch_conv(const CUtensorMap& tmA, const CUtensorMap& tmB, const Con
 
 static int g_conv_fused3 = 1;      // pair kernel, precision 3: load hi+lo planes once per K block (1) or stream K 3x (0)
 static int g_conv_pair_mode = 1;   // 1: CTA-pair kernel when Cout % 256 == 0; 0: single-CTA kernel everywhere
+static int g_conv_q_reuse = 1;     // precision 2: A tiles with dy halo rows shared by three taps (0: one A tile per tap)
 
 bool conv_shape_supported(int b, int Cin, int Cout, int h, int w) {
   return b > 0 && h > 0 && w > 0 && Cin % 64 == 0 && Cout % 64 == 0;
@@ -902,6 +956,8 @@ int conv_run(const ammc_conv_layer& L, cudaStream_t st) {
   p.out_fmt = 0; p.out_q16 = nullptr; p.out_q8 = nullptr; p.out_q8_stride = 0; p.out_qs = nullptr;
   p.in_qs = nullptr; p.w_qs = nullptr;
   const bool qmode = L.precision == 2;
+  p.a_reuse = (qmode && ntaps == 9 && g_conv_q_reuse && p.B_box == 1 && p.groups_w == 1 && p.W_box % 8 == 0 &&
+               p.W_box * (p.H_box + 2) <= 192) ? 1 : 0;
   const long long n_out = (long long)b * h * w * out_cs, n_in = (long long)b * h * w * in_cs, n_w = (long long)Cout * ntaps * Cin;
   if (L.out_fmt == 1) {
     AMMC_REQUIRE(L.out_planes && !L.up2x && out_cs % 16 == 0 && L.out_c_off % 16 == 0 && cout_valid == Cout,
@@ -932,11 +988,12 @@ int conv_run(const ammc_conv_layer& L, cudaStream_t st) {
     // fp16 plane (one plane, 64-channel boxes) and the two e4m3 planes (128-channel boxes = 128-byte rows)
     uint64_t dims[5] = {(uint64_t)Cin, (uint64_t)w, (uint64_t)h, (uint64_t)b, 1};
     uint64_t st16[4] = {(uint64_t)Cin * 2, (uint64_t)w * Cin * 2, (uint64_t)h * w * Cin * 2, (uint64_t)b * h * w * Cin * 2};
-    uint32_t box16[5] = {64, (uint32_t)p.W_box, (uint32_t)p.H_box, (uint32_t)p.B_box, 1};
+    const uint32_t hb = (uint32_t)(p.a_reuse ? p.H_box + 2 : p.H_box);       // a_reuse: the tile carries its dy halo rows
+    uint32_t box16[5] = {64, (uint32_t)p.W_box, hb, (uint32_t)p.B_box, 1};
     if (int rc = make_map_generic(&tmA, L.in_planes, 2, 5, dims, st16, box16, 1)) return rc;
     dims[4] = 2;
     uint64_t st8[4] = {(uint64_t)Cin, (uint64_t)w * Cin, (uint64_t)h * w * Cin, (uint64_t)n_in};
-    uint32_t box8[5] = {128, (uint32_t)p.W_box, (uint32_t)p.H_box, (uint32_t)p.B_box, 1};
+    uint32_t box8[5] = {128, (uint32_t)p.W_box, hb, (uint32_t)p.B_box, 1};
     if (int rc = make_map_generic(&tmA8, (const uint8_t*)L.in_planes + 2 * n_in, 1, 5, dims, st8, box8, 1)) return rc;
     const uint64_t K = (uint64_t)ntaps * Cin;
     uint64_t wd[3] = {K, (uint64_t)Cout, 1}, ws16[2] = {K * 2, (uint64_t)Cout * K * 2};
@@ -1060,6 +1117,7 @@ extern "C" int ammc_pack_nhwc_q(const float* x, void* xq, int b, int C, int h, i
 extern "C" int ammc_set_conv_pair_mode(int on) {
   g_conv_pair_mode = on ? 1 : 0;       // bit 1 (value 2/3): keep the pair kernel but stream the K loop three times
   g_conv_fused3 = (on & 2) ? 0 : 1;
+  g_conv_q_reuse = (on & 4) ? 0 : 1;   // bit 2 (value 5): precision 2 without the dy-halo A tiles (A/B measurement)
   return 0;
 }
 

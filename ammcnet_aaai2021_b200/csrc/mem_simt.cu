@@ -746,9 +746,11 @@ int absmax_f32(const float* x, long long n, unsigned* out_bits, cudaStream_t st)
 
 // Power-of-two scale of the module output written as q planes (precision-2 operand of the AMFT block), from a rigorous
 // bound:  |out_c| <= max|x| (residual) + sum_j ||dec_w[c, jD:(j+1)D]||_2 * max_m ||e_m||_2 + |dec_b[c]|   (Cauchy-Schwarz)
-__global__ void __launch_bounds__(256) mem_out_qscale_kernel(const unsigned* __restrict__ amax_bits, const float* __restrict__ dec_w,
-                                                             const float* __restrict__ dec_b, const float* __restrict__ en2,
-                                                             int C, int D, int M, int k, int residual, float* __restrict__ qs) {
+// One warp per output channel (a single block walking all C channels was latency-bound: 150 us); the per-channel bounds
+// meet in an atomicMax on the bit pattern, a one-thread kernel turns the sum into the scale.
+__global__ void __launch_bounds__(256) dec_bound_kernel(const float* __restrict__ dec_w, const float* __restrict__ dec_b,
+                                                        const float* __restrict__ en2, int C, int D, int M, int k,
+                                                        unsigned* __restrict__ bound_bits) {
   __shared__ float red[8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float e2 = 0.f;
@@ -759,25 +761,20 @@ __global__ void __launch_bounds__(256) mem_out_qscale_kernel(const unsigned* __r
   e2 = red[0];
   for (int i = 1; i < 8; ++i) e2 = fmaxf(e2, red[i]);
   const float emax = sqrtf(e2);
-  __syncthreads();
-  float best = 0.f;
-  for (int c = warp; c < C; c += 8) {
-    float bound = 0.f;
-    for (int j = 0; j < k; ++j) {
-      float ss = 0.f;
-      for (int d = lane; d < D; d += 32) { const float wv = dec_w[(size_t)c * k * D + j * D + d]; ss = fmaf(wv, wv, ss); }
-      ss = warp_sum(ss);
-      bound += sqrtf(ss);
-    }
-    best = fmaxf(best, bound * emax * 1.01f + fabsf(dec_b[c]));
+  const int c = blockIdx.x * 8 + warp;
+  if (c >= C) return;
+  float bound = 0.f;
+  for (int j = 0; j < k; ++j) {
+    float ss = 0.f;
+    for (int d = lane; d < D; d += 32) { const float wv = dec_w[(size_t)c * k * D + j * D + d]; ss = fmaf(wv, wv, ss); }
+    bound += sqrtf(warp_sum(ss));
   }
-  if (lane == 0) red[warp] = best;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int i = 1; i < 8; ++i) best = fmaxf(best, red[i]);
-    const float xmax = residual ? __uint_as_float(amax_bits[0]) : 0.f;
-    qs[0] = q_scale_for_bound(xmax + best);
-  }
+  if (lane == 0) atomicMax(bound_bits, __float_as_uint(bound * emax * 1.01f + fabsf(dec_b[c])));
+}
+__global__ void mem_out_qscale_kernel(const unsigned* __restrict__ amax_bits, const unsigned* __restrict__ bound_bits,
+                                      int residual, float* __restrict__ qs) {
+  if (threadIdx.x == 0)
+    qs[0] = q_scale_for_bound((residual ? __uint_as_float(amax_bits[0]) : 0.f) + __uint_as_float(bound_bits[0]));
 }
 
 static int g_enc_mode = 0;    // 0 auto, 1 fp32 FFMA (CUDA cores), 2 tensor-core GEMM (split-bf16 x3, converts NCHW on the fly)
@@ -971,7 +968,11 @@ extern "C" int ammc_mem_fwd(const float* x, const float* enc_w, const float* enc
     L.b = b; L.h = h; L.w = w; L.Cin = k * D; L.Cout = C; L.precision = 3;
     if (q_planes) {
       float* qs = reinterpret_cast<float*>((uint8_t*)out_planes + 4 * N * C);
-      mem_out_qscale_kernel<<<1, 256, 0, st>>>(amax_bits, dec_w, dec_b, m.en2, C, D, M, k, residual, qs);
+      unsigned* bound_bits = amax_bits + 1;                                 // word 9 of the stats block
+      AMMC_CUDA_CHECK(cudaMemsetAsync(bound_bits, 0, 4, st));
+      dec_bound_kernel<<<ceil_div(C, 8), 256, 0, st>>>(dec_w, dec_b, m.en2, C, D, M, k, bound_bits);
+      AMMC_LAUNCH_CHECK("dec_bound_kernel");
+      mem_out_qscale_kernel<<<1, 32, 0, st>>>(amax_bits, bound_bits, residual, qs);
       AMMC_LAUNCH_CHECK("mem_out_qscale_kernel");
       L.out_fmt = 1;
     }
