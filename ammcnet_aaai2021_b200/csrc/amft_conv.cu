@@ -303,9 +303,11 @@ constexpr int Q_A_PLANE = 192 * 128;                 // 24 KB
 constexpr int Q_A_STAGE = 2 * Q_A_PLANE;             // 48 KB
 constexpr int Q_A_STAGES = 2;
 constexpr int Q_B_STAGE = 2 * PAIR_B_BYTES;          // 32 KB
-constexpr int Q_B_STAGES = 3;
+constexpr int Q_B_STAGES = 4;
 constexpr int Q_B_RING = Q_A_STAGES * Q_A_STAGE;     // 96 KB
-static_assert(Q_B_RING + Q_B_STAGES * Q_B_STAGE == PAIR_RING_BYTES, "q rings fill the pair kernel's ring");
+constexpr int Q_RING_BYTES = Q_B_RING + Q_B_STAGES * Q_B_STAGE;      // 224 KB
+constexpr int Q_SMEM = Q_RING_BYTES + 256 + 1024;
+static_assert(Q_SMEM <= 232448, "q rings exceed the 227 KB of shared memory a CTA can have");
 template <int MODE> struct PairCfg {
   static constexpr int PLANES = MODE == PAIR_STREAM ? 1 : 2;
   static constexpr int STAGE_BYTES = PLANES * PAIR_TILE_BYTES;
@@ -325,7 +327,7 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   using Cfg = PairCfg<MODE>;
   constexpr int PAIR_STAGES = Cfg::STAGES;
   constexpr int PAIR_STAGE_BYTES = Cfg::STAGE_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + PAIR_BAR_OFFSET);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (QMODE ? Q_RING_BYTES : PAIR_BAR_OFFSET));
   uint64_t* empty_bar = full_bar + PAIR_STAGES;
   // PAIR_Q: [a_full 2][a_empty 2][b_full 3][b_empty 3] instead of [full][empty]
   uint64_t* a_full = full_bar;
@@ -1030,13 +1032,13 @@ int conv_run(const ammc_conv_layer& L, cudaStream_t st) {
     if (dev >= 0 && dev < 64 && !configured[dev]) {
       AMMC_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_pair_kernel<PAIR_STREAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM));
       AMMC_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_pair_kernel<PAIR_FUSED3>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM));
-      AMMC_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_pair_kernel<PAIR_Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM));
+      AMMC_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_pair_kernel<PAIR_Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM));
       configured[dev] = true;
     }
     const int pair_tiles = ((p.tiles_m + 1) / 2) * p.tiles_n;
     const int clusters = min(num_sms() / 2, pair_tiles);
     if (qmode)
-      conv_igemm_pair_kernel<PAIR_Q><<<2 * clusters, PAIR_THREADS, PAIR_SMEM, st>>>(tmA, tmB, tmA8, tmB8, p);
+      conv_igemm_pair_kernel<PAIR_Q><<<2 * clusters, PAIR_THREADS, Q_SMEM, st>>>(tmA, tmB, tmA8, tmB8, p);
     else if (L.precision == 3 && g_conv_fused3)
       conv_igemm_pair_kernel<PAIR_FUSED3><<<2 * clusters, PAIR_THREADS, PAIR_SMEM, st>>>(tmA, tmB, tmA, tmB, p);
     else

@@ -169,7 +169,7 @@ class GeneratorEngine:
         px, py = F_.planes_of(r4, fmt), F_.planes_of(o4, fmt)
         px = pack(r4) if px is None else px
         py = pack(o4) if py is None else py
-        r4p = self._amft_branch(m.bridge.O2F, py, r4, prec)    # x' = zx + O2F(zy)   (unet.py:963)
-        o4p = self._amft_branch(m.bridge.F20, px, o4, prec)    # y' = zy + F20(zx)   (unet.py:964)
+        r4p, o4p = F_.concurrently(lambda: self._amft_branch(m.bridge.O2F, py, r4, prec),     # x' = zx + O2F(zy)   (unet.py:963)
+                                   lambda: self._amft_branch(m.bridge.F20, px, o4, prec))     # y' = zy + F20(zx)   (unet.py:964)
         rgb_y, op_y = F_.concurrently(lambda: self._decode(pr, r4p, cats_r), lambda: self._decode(po, o4p, cats_o))
         return rgb_y, op_y, (rgb_diff, op_diff), (rgb_q, op_q)

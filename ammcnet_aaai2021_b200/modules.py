@@ -184,8 +184,9 @@ class bridge(nn.Module):
         py = F_.planes_of(zy, fmt)
         px = pack(zx) if px is None else px
         py = pack(zy) if py is None else py
-        x = self.O2F.forward_fused(py, zx, prec)
-        y = self.F20.forward_fused(px, zy, prec)
+        # the two branches are independent: issued on two CUDA streams, the persistent conv kernels of one branch take over
+        # the SMs the other branch's kernel frees at its tail (no idle SMs between launches, ~3 % of the block)
+        x, y = F_.concurrently(lambda: self.O2F.forward_fused(py, zx, prec), lambda: self.F20.forward_fused(px, zy, prec))
         return x, y
 
 

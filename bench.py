@@ -453,9 +453,11 @@ def run_ours(args):
     # recorded inside a replayed graph), same stream, right after the timed region
     F_.PROFILE["on"] = True
     F_.PROFILE["events"].clear()
+    F_.CONCURRENCY["on"] = False          # one stream: the events of a launch must not bracket a neighbour's kernel
     for _ in range(steps):
         local_step(xr, xo, gen, gt)
     torch.cuda.synchronize()
+    F_.CONCURRENCY["on"] = True
     F_.PROFILE["on"] = False
     conv_ms = [s.elapsed_time(e) for (s, e) in F_.PROFILE["events"] if s.elapsed_time(e) > 0.15]   # 3x3 convs only
     F_.PROFILE["events"].clear()
@@ -608,8 +610,9 @@ def run_ours(args):
                                     "+ 134 MB out (+134 MB residual) + 9.4 MB weights" % traffic_file,
                     "peak_source": peak_src + " bf16_tflops_sustained (dense bf16 cuBLAS; kernel timed inside a long step)",
                     "avg_launch_ms": avg, "launches_timed": len(conv_ms),
-                    "timing": "CUDA events around each 3x3 conv launch of K eagerly issued steps run right after the "
-                              "timed region (events cannot be recorded inside a graph replay)",
+                    "timing": "CUDA events around each 3x3 conv launch of K steps issued eagerly on ONE stream right after the "
+                              "timed region (events cannot be recorded inside a graph replay; in the timed region the two AMFT "
+                              "branches run on two streams and overlap their tails)",
                     "algorithmic_flops_per_launch": conv_flops,
                     "tensor_pass_equivalents": prec, "executed_frac_of_peak": prec * ach / peak}
         line = {

@@ -60,6 +60,11 @@ def main():
         ms = timed(fn)
         out[name + "_ms"] = ms
         out[name + "_algorithmic_tflops"] = flops / ms / 1e9
+    F_.set_conv_pair_mode(5)              # precision 2 without the dy-halo A tiles (one A tile per tap)
+    y2n = F_.conv3x3_bn_relu(xq, wq, scale, shift, to_planes=False, precision=2)
+    out["p2_noreuse_vs_reuse_rel"] = float((y2n - y2).abs().max() / y2.abs().max())
+    out["p2_noreuse_planes_ms"] = timed(lambda: F_.conv3x3_bn_relu(xq, wq, scale, shift, to_planes=True, precision=2))
+    F_.set_conv_pair_mode(1)
     out["batch"] = b
     print(json.dumps(out))
 
