@@ -37,7 +37,10 @@ SIGNATURES = {
     "ammc_debug_tma_probe": (I, [P, P, P, P, P, P, I, P]),
     "ammc_mem_workspace_bytes": (Z, [I] * 7),
     "ammc_set_addressing_mode": (I, [I]),
-    "ammc_mem_fwd": (I, [P] * 6 + [P] * 6 + [P, P, P, I] + [P, Z] + [I] * 8 + [P]),
+    "ammc_mem_fwd": (I, [P] * 6 + [P] * 6 + [P, P, P, I, P] + [P, Z] + [I] * 8 + [P]),
+    "ammc_mem_prep_bytes": (Z, [I] * 4),
+    "ammc_mem_prepare": (I, [P] * 5 + [Z] + [I] * 7 + [P]),
+    "ammc_set_front_mode": (I, [I]),
     "ammc_mem_dec_uses_tensor": (I, [I] * 7),
     "ammc_set_dec_mode": (I, [I]),
     "ammc_set_enc_mode": (I, [I]),

@@ -15,7 +15,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libammc_b200.so")
 STAMP = os.path.join(PKG, "csrc", ".build_stamp")
-SOURCES = ["core.cu", "mem_simt.cu", "addr_tc.cu", "enc_tc.cu", "score.cu", "auc.cu", "amft_conv.cu", "amft_train.cu", "unet_ops.cu", "halo_conv.cu", "preprocess.cu", "losses.cu", "probes.cu"]
+SOURCES = ["core.cu", "mem_simt.cu", "addr_tc.cu", "enc_tc.cu", "mem_front.cu", "score.cu", "auc.cu", "amft_conv.cu", "amft_train.cu", "unet_ops.cu", "halo_conv.cu", "preprocess.cu", "losses.cu", "probes.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 

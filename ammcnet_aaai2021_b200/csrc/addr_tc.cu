@@ -503,6 +503,33 @@ int run_address_tc(const float* z, const __nv_bfloat16* zp_in, const float* znor
   return 0;
 }
 
+// exact re-scan of the rows the fused front kernel (mem_front.cu) queued: stats[2] rows listed in rescan_list
+int run_rescan(const float* z, const float* bank_t, const float* en2, float* q1, int64_t* idx, float* sse_px, int* stats,
+               int* rescan_list, __nv_bfloat16* read_planes, long long read_plane_stride, int D, int M, int k,
+               cudaStream_t st) {
+  switch (k) {
+#define AMMC_RS_CASE(KK)                                                                                                  \
+  case KK:                                                                                                                \
+    rescan_kernel<KK><<<2 * num_sms(), 256, 0, st>>>(z, bank_t, en2, nullptr, q1, idx, sse_px, nullptr, nullptr, stats,   \
+                                                     rescan_list, read_planes, read_plane_stride, D, M);                  \
+    break;
+    AMMC_RS_CASE(1) AMMC_RS_CASE(2) AMMC_RS_CASE(3) AMMC_RS_CASE(4)
+#undef AMMC_RS_CASE
+    default: return fail(AMMC_EUNSUPPORTED, "re-scan supports k <= 4");
+  }
+  AMMC_LAUNCH_CHECK("rescan_kernel");
+  return 0;
+}
+
+// bank_t [M][D], en2 [M] -> bank_hi [Mpad][D] bf16, en2pad [Mpad], emax (max ||e||) for a caller-chosen padding
+int pack_bank_padded(const float* bank_t, const float* en2, void* bank_hi, float* en2pad, float* emax, int D, int M, int Mpad,
+                     cudaStream_t st) {
+  AMMC_CUDA_CHECK(cudaMemsetAsync(emax, 0, 4, st));
+  bank_pack_kernel<<<Mpad, 128, 0, st>>>(bank_t, en2, (__nv_bfloat16*)bank_hi, en2pad, emax, D, M, Mpad);
+  AMMC_LAUNCH_CHECK("bank_pack_kernel");
+  return 0;
+}
+
 // mem_simt.cu
 __global__ void bank_transpose_kernel(const float* __restrict__ embed, float* __restrict__ bank_t, int D, int M);
 __global__ void bank_norms_kernel(const float* __restrict__ embed, float* __restrict__ en2, int D, int M);

@@ -251,8 +251,9 @@ size_t enc_tc_ws_bytes(int C) { return align_up((size_t)2 * ENC_D * C * 2, 256);
 
 // x [b][C][HW] fp32, enc_w [64][C] fp32 -> z [N][64] (+ zp, znorm2 when non-null).  wp_ws: enc_tc_ws_bytes(C).
 int run_enc_tc(const float* x, const float* enc_w, const float* enc_b, float* z, __nv_bfloat16* zp, float* znorm2,
-               void* wp_ws, unsigned* amax_bits, int b, int HW, int C, cudaStream_t st) {
-  if (int rc = pack_weights_1x1(enc_w, wp_ws, ENC_D, C, st)) return rc;
+               void* wp_ws, bool wp_ready, unsigned* amax_bits, int b, int HW, int C, cudaStream_t st) {
+  if (!wp_ready)
+    if (int rc = pack_weights_1x1(enc_w, wp_ws, ENC_D, C, st)) return rc;
   CUtensorMap tmX, tmW;
   {
     uint64_t dims[3] = {(uint64_t)HW, (uint64_t)C, (uint64_t)b};

@@ -715,6 +715,7 @@ __global__ void gdec_w_kernel(const float* __restrict__ G, const float* __restri
 // ------------------------------------------------------------------------------------------------
 struct MemWs {
   int* stats; float* bank_t; float* en2; float* T; float* sse_px; __nv_bfloat16* read_planes;
+  bool own_bank;                                    // bank_t / en2 live in the workspace and are (re)derived per call
   const __nv_bfloat16* zp; const float* znorm2;     // produced by the tensor-core enc epilogue, else null
 };
 
@@ -726,11 +727,21 @@ int run_address_tc(const float* z, const __nv_bfloat16* zp_in, const float* znor
                    const float* bank_t, const float* en2, float* read, float* q1, int64_t* idx, float* sse_px,
                    float* counts, float* embed_sum, int* stats, Workspace& ws, int64_t N, int D, int M, int k,
                    cudaStream_t st);
+int run_rescan(const float* z, const float* bank_t, const float* en2, float* q1, int64_t* idx, float* sse_px, int* stats,
+               int* rescan_list, __nv_bfloat16* read_planes, long long read_plane_stride, int D, int M, int k, cudaStream_t st);
+int pack_bank_padded(const float* bank_t, const float* en2, void* bank_hi, float* en2pad, float* emax, int D, int M, int Mpad,
+                     cudaStream_t st);
+// mem_front.cu
+bool mem_front_supported(int b, int HW, int C, int D, int M, int k);
+int run_mem_front(const float* x, const void* enc_wp, const float* enc_b, const void* bank_hi, const float* bank_t,
+                  const float* en2, const float* en2pad, const float* emax, float* z, float* q1, int64_t* idx, float* sse_px,
+                  __nv_bfloat16* read_planes, int* stats, int* rescan_list, unsigned* amax_bits, int b, int HW, int C, int M,
+                  int k, cudaStream_t st);
 // enc_tc.cu
 bool enc_tc_supported(int b, int HW, int C, int D);
 size_t enc_tc_ws_bytes(int C);
 int run_enc_tc(const float* x, const float* enc_w, const float* enc_b, float* z, __nv_bfloat16* zp, float* znorm2,
-               void* wp_ws, unsigned* amax_bits, int b, int HW, int C, cudaStream_t st);
+               void* wp_ws, bool wp_ready, unsigned* amax_bits, int b, int HW, int C, cudaStream_t st);
 
 // amft_conv.cu
 bool conv_shape_supported(int b, int Cin, int Cout, int h, int w);
@@ -777,7 +788,40 @@ __global__ void mem_out_qscale_kernel(const unsigned* __restrict__ amax_bits, co
     qs[0] = q_scale_for_bound((residual ? __uint_as_float(amax_bits[0]) : 0.f) + __uint_as_float(bound_bits[0]));
 }
 
-static int g_enc_mode = 0;    // 0 auto, 1 fp32 FFMA (CUDA cores), 2 tensor-core GEMM (split-bf16 x3, converts NCHW on the fly)
+// Everything the forward derives from the parameters alone (constant between optimizer / EMA steps): packed once by
+// ammc_mem_prepare into a caller-owned buffer and reused by every ammc_mem_fwd until a parameter changes.
+struct MemPrep {
+  __nv_bfloat16* enc_wp;     // [2][D][C]   bf16 hi/lo planes of enc.weight
+  __nv_bfloat16* dec_wp;     // [2][C][kD]  bf16 hi/lo planes of dec.weight
+  float* bank_t;             // [M][D]      items as rows
+  float* en2;                // [M]         ||e||^2
+  __nv_bfloat16* bank_hi;    // [256][D]    bf16 items, zero rows beyond M (fused front kernel)
+  float* en2pad;             // [256]       ||e||^2, +inf beyond M
+  float* emax;               // [1]         max ||e||
+  float* ones;               // [C]
+  unsigned* dec_bound;       // [1]         bits of max_c (sum_j ||dec_w[c,j]|| max||e|| + |dec_b[c]|): q-plane scale bound
+};
+static size_t prep_bytes(int C, int D, int M, int k) {
+  return align_up((size_t)2 * D * C * 2, 256) + align_up((size_t)2 * C * k * D * 2, 256) + align_up((size_t)M * D * 4, 256) +
+         align_up((size_t)M * 4, 256) + align_up((size_t)256 * D * 2, 256) + align_up((size_t)256 * 4, 256) + 256 +
+         align_up((size_t)C * 4, 256) + 256;
+}
+static int carve_prep(Workspace& ws, MemPrep& pr, int C, int D, int M, int k) {
+  pr.enc_wp = ws.take<__nv_bfloat16>((size_t)2 * D * C);
+  pr.dec_wp = ws.take<__nv_bfloat16>((size_t)2 * C * k * D);
+  pr.bank_t = ws.take<float>((size_t)M * D);
+  pr.en2 = ws.take<float>(M);
+  pr.bank_hi = ws.take<__nv_bfloat16>((size_t)256 * D);
+  pr.en2pad = ws.take<float>(256);
+  pr.emax = ws.take<float>(1);
+  pr.ones = ws.take<float>(C);
+  pr.dec_bound = ws.take<unsigned>(1);
+  if (!ws.ok()) return fail(AMMC_EWORKSPACE, "prepared-parameter buffer too small");
+  return 0;
+}
+
+static int g_enc_mode = 0;
+static int g_front_mode = 1;  // 1: fused enc + addressing kernel (mem_front.cu) when the shape allows; 0: staged kernels    // 0 auto, 1 fp32 FFMA (CUDA cores), 2 tensor-core GEMM (split-bf16 x3, converts NCHW on the fly)
 static int g_dec_mode = 0;    // 0 auto, 1 fp32 table gather (CUDA cores), 2 tensor-core GEMM (split-bf16 x3)
 static int g_addr_mode = 0;   // 0 auto, 1 generic fp32 (CUDA cores), 2 tensor-core filter + exact refine
 
@@ -802,6 +846,7 @@ static size_t mem_ws_bytes(int64_t N, int C, int D, int M, int k, bool with_tabl
   s += align_up((size_t)M * D * 4, 256);
   s += align_up((size_t)M * 4, 256);
   if (with_table) {
+    s += prep_bytes(C, D, M, k) + align_up((size_t)N * 4, 256);      // prepared parameters (when not cached), re-scan list
     s += align_up((size_t)k * M * C * 4, 256);                       // dec tables (fp32 gather path)
     s += align_up((size_t)N * k * D * 2 * 2, 256);                    // read planes (tensor-core dec)
     s += align_up((size_t)C * k * D * 2 * 2, 256) + align_up((size_t)C * 4, 256);
@@ -816,8 +861,9 @@ static int carve(Workspace& ws, MemWs& m, int64_t N, int C, int D, int M, int k,
   m.read_planes = nullptr;
   m.zp = nullptr;
   m.znorm2 = nullptr;
-  m.bank_t = ws.take<float>((size_t)M * D);
-  m.en2 = ws.take<float>(M);
+  m.own_bank = !with_table;                         // the module path takes both from the prepared-parameter buffer
+  m.bank_t = with_table ? nullptr : ws.take<float>((size_t)M * D);
+  m.en2 = with_table ? nullptr : ws.take<float>(M);
   m.T = with_table ? ws.take<float>((size_t)k * M * C) : nullptr;
   m.sse_px = ws.take<float>(N);
   if (!ws.ok()) return fail(AMMC_EWORKSPACE, "workspace too small");
@@ -834,10 +880,12 @@ static void launch_address(const float* z, const float* embed, const MemWs& m, f
 static int run_address(const float* z, const float* embed, const MemWs& m, float* read, float* q1, int64_t* idx,
                        float* counts, float* embed_sum, int64_t N, int D, int M, int k, cudaStream_t st, Workspace& ws) {
   AMMC_CUDA_CHECK(cudaMemsetAsync(m.stats, 0, 32, st));   // words 0-7; word 8 = max|x| bits of the enc pass
-  bank_transpose_kernel<<<dim3(ceil_div(M, 32), ceil_div(D, 32)), dim3(32, 8), 0, st>>>(embed, m.bank_t, D, M);
-  AMMC_LAUNCH_CHECK("bank_transpose_kernel");
-  bank_norms_kernel<<<ceil_div(M, 128), 128, 0, st>>>(embed, m.en2, D, M);
-  AMMC_LAUNCH_CHECK("bank_norms_kernel");
+  if (m.own_bank) {                                       // Quantize_topk on its own: items as rows + norms derived here
+    bank_transpose_kernel<<<dim3(ceil_div(M, 32), ceil_div(D, 32)), dim3(32, 8), 0, st>>>(embed, m.bank_t, D, M);
+    AMMC_LAUNCH_CHECK("bank_transpose_kernel");
+    bank_norms_kernel<<<ceil_div(M, 128), 128, 0, st>>>(embed, m.en2, D, M);
+    AMMC_LAUNCH_CHECK("bank_norms_kernel");
+  }
   if (counts) AMMC_CUDA_CHECK(cudaMemsetAsync(counts, 0, (size_t)M * 4, st));
   if (embed_sum) AMMC_CUDA_CHECK(cudaMemsetAsync(embed_sum, 0, (size_t)D * M * 4, st));
   if (g_addr_mode == 2 && !addr_tc_supported(N, D, M, k))
@@ -900,11 +948,52 @@ static int check_dims(int64_t N, int C, int D, int M, int k) {
   return 0;
 }
 
+// Derive everything that depends on the parameters only (see MemPrep).
+static int run_prepare(const MemPrep& pr, const float* enc_w, const float* embed, const float* dec_w, const float* dec_b,
+                       int C, int D, int M, int k, bool tc_enc, bool tc_dec, cudaStream_t st) {
+  bank_transpose_kernel<<<dim3(ceil_div(M, 32), ceil_div(D, 32)), dim3(32, 8), 0, st>>>(embed, pr.bank_t, D, M);
+  AMMC_LAUNCH_CHECK("bank_transpose_kernel");
+  bank_norms_kernel<<<ceil_div(M, 128), 128, 0, st>>>(embed, pr.en2, D, M);
+  AMMC_LAUNCH_CHECK("bank_norms_kernel");
+  if (M <= 256)
+    if (int rc = pack_bank_padded(pr.bank_t, pr.en2, pr.bank_hi, pr.en2pad, pr.emax, D, M, 256, st)) return rc;
+  if (tc_enc)
+    if (int rc = pack_weights_1x1(enc_w, pr.enc_wp, D, C, st)) return rc;
+  if (tc_dec) {
+    if (int rc = pack_weights_1x1(dec_w, pr.dec_wp, C, k * D, st)) return rc;
+    fill_kernel<<<ceil_div(C, 256), 256, 0, st>>>(pr.ones, 1.f, C);
+    AMMC_LAUNCH_CHECK("fill_kernel");
+  }
+  AMMC_CUDA_CHECK(cudaMemsetAsync(pr.dec_bound, 0, 4, st));
+  dec_bound_kernel<<<ceil_div(C, 8), 256, 0, st>>>(dec_w, dec_b, pr.en2, C, D, M, k, pr.dec_bound);
+  AMMC_LAUNCH_CHECK("dec_bound_kernel");
+  return 0;
+}
+
+extern "C" size_t ammc_mem_prep_bytes(int C, int D, int M, int k) { return prep_bytes(C, D, M, k); }
+
+extern "C" int ammc_mem_prepare(const float* enc_w, const float* embed, const float* dec_w, const float* dec_b, void* prep,
+                                size_t prep_bytes_given, int b, int h, int w, int C, int D, int M, int k, void* stream) {
+  AMMC_REQUIRE(enc_w && embed && dec_w && dec_b && prep, "null pointer argument");
+  if (int rc = check_dims((int64_t)b * h * w, C, D, M, k)) return rc;
+  Workspace ws(prep, prep_bytes_given);
+  MemPrep pr;
+  if (int rc = carve_prep(ws, pr, C, D, M, k)) return rc;
+  const bool tc_dec = use_tc_dec(b, h, w, C, D, k);
+  const bool tc_enc = g_enc_mode != 1 && enc_tc_supported(b, h * w, C, D);
+  return run_prepare(pr, enc_w, embed, dec_w, dec_b, C, D, M, k, tc_enc, tc_dec, (cudaStream_t)stream);
+}
+
+extern "C" int ammc_set_front_mode(int on) {
+  g_front_mode = on ? 1 : 0;
+  return 0;
+}
+
 extern "C" int ammc_mem_fwd(const float* x, const float* enc_w, const float* enc_b, const float* embed,
                             const float* dec_w, const float* dec_b, float* out, float* q1, int64_t* idx, float* z,
                             float* sse_frame, float* diff, float* counts, float* embed_sum, void* out_planes,
-                            int planes_fmt, void* workspace, size_t workspace_bytes, int b, int h, int w, int C, int D,
-                            int M, int k, int residual, void* stream) {
+                            int planes_fmt, const void* prep, void* workspace, size_t workspace_bytes, int b, int h, int w,
+                            int C, int D, int M, int k, int residual, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t N = (int64_t)b * h * w;
   const int HW = h * w;
@@ -923,56 +1012,73 @@ extern "C" int ammc_mem_fwd(const float* x, const float* enc_w, const float* enc
   const bool q_planes = out_planes && planes_fmt == 1;
   AMMC_REQUIRE(!q_planes || C % 256 == 0, "q-format planes need C %% 256 == 0");
   unsigned* amax_bits = reinterpret_cast<unsigned*>(m.stats + 8);     // word 8 of the stats block
-  __nv_bfloat16* dec_wp = nullptr;
-  float* ones = nullptr;
+  const bool tc_enc = g_enc_mode != 1 && enc_tc_supported(b, HW, C, D);
+  if (g_enc_mode == 2 && !tc_enc)
+    return fail(AMMC_EUNSUPPORTED, "tensor-core enc needs embed_dim == 64, C %% 64 == 0 and h*w %% 128 == 0");
+  // parameters-only quantities: from the caller's prepared buffer, else derived here into the workspace
+  MemPrep pr;
+  if (prep) {
+    Workspace pws(const_cast<void*>(prep), prep_bytes(C, D, M, k));
+    if (int rc = carve_prep(pws, pr, C, D, M, k)) return rc;
+  } else {
+    if (int rc = carve_prep(ws, pr, C, D, M, k)) return rc;
+    if (int rc = run_prepare(pr, enc_w, embed, dec_w, dec_b, C, D, M, k, tc_enc, tc_dec, st)) return rc;
+  }
+  m.bank_t = pr.bank_t;
+  m.en2 = pr.en2;
   if (tc_dec) {
     m.read_planes = ws.take<__nv_bfloat16>((size_t)N * k * D * 2);
-    dec_wp = ws.take<__nv_bfloat16>((size_t)C * k * D * 2);
-    ones = ws.take<float>(C);
     if (!ws.ok()) return fail(AMMC_EWORKSPACE, "workspace too small");
   } else {
     dec_table_kernel<<<dim3(ceil_div(C, 32), ceil_div(M, 32), k), dim3(32, 8), 0, st>>>(dec_w, embed, m.T, C, D, M, k);
     AMMC_LAUNCH_CHECK("dec_table_kernel");
   }
-  const bool tc_enc = g_enc_mode != 1 && enc_tc_supported(b, HW, C, D);
-  if (g_enc_mode == 2 && !tc_enc)
-    return fail(AMMC_EUNSUPPORTED, "tensor-core enc needs embed_dim == 64, C %% 64 == 0 and h*w %% 128 == 0");
-  if (tc_enc) {
-    void* enc_wp = ws.take<__nv_bfloat16>((size_t)2 * D * C);
-    __nv_bfloat16* zp = ws.take<__nv_bfloat16>((size_t)N * D);
-    float* zn2 = ws.take<float>(N);
+  // fused enc + addressing (eval): z, candidates and scores never leave the SM
+  const bool front = g_front_mode && tc_enc && tc_dec && !counts && !embed_sum && g_addr_mode != 1 &&
+                     mem_front_supported(b, HW, C, D, M, k);
+  if (front) {
+    int* rescan_list = ws.take<int>(N);
     if (!ws.ok()) return fail(AMMC_EWORKSPACE, "workspace too small");
-    // the converters see every input value: max|x| (for the q planes' scale) comes out of the same pass
-    if (int rc = run_enc_tc(x, enc_w, enc_b, z, zp, zn2, enc_wp, (q_planes && residual) ? amax_bits : nullptr, b, HW, C, st))
+    AMMC_CUDA_CHECK(cudaMemsetAsync(m.stats, 0, 32, st));
+    AMMC_CUDA_CHECK(cudaMemsetAsync(m.stats + 1, 3, 1, st));            // path id 3: fused front kernel
+    if (int rc = run_mem_front(x, pr.enc_wp, enc_b, pr.bank_hi, pr.bank_t, pr.en2, pr.en2pad, pr.emax, z, q1, idx, m.sse_px,
+                               m.read_planes, m.stats, rescan_list, (q_planes && residual) ? amax_bits : nullptr, b, HW, C,
+                               M, k, st))
       return rc;
-    m.zp = zp;
-    m.znorm2 = zn2;
+    if (int rc = run_rescan(z, pr.bank_t, pr.en2, q1, idx, m.sse_px, m.stats, rescan_list, m.read_planes,
+                            (long long)N * k * D, D, M, k, st))
+      return rc;
   } else {
-    enc1x1_kernel<<<dim3(ceil_div(N, 64), ceil_div(D, 64)), 256, 0, st>>>(x, enc_w, enc_b, z, nullptr, (int)N, HW, C, D);
-    AMMC_LAUNCH_CHECK("enc1x1_kernel");
-    if (q_planes && residual)
-      if (int rc = absmax_f32(x, (long long)N * C, amax_bits, st)) return rc;
+    if (tc_enc) {
+      __nv_bfloat16* zp = ws.take<__nv_bfloat16>((size_t)N * D);
+      float* zn2 = ws.take<float>(N);
+      if (!ws.ok()) return fail(AMMC_EWORKSPACE, "workspace too small");
+      // the converters see every input value: max|x| (for the q planes' scale) comes out of the same pass
+      if (int rc = run_enc_tc(x, enc_w, enc_b, z, zp, zn2, pr.enc_wp, true, (q_planes && residual) ? amax_bits : nullptr, b,
+                              HW, C, st))
+        return rc;
+      m.zp = zp;
+      m.znorm2 = zn2;
+    } else {
+      enc1x1_kernel<<<dim3(ceil_div(N, 64), ceil_div(D, 64)), 256, 0, st>>>(x, enc_w, enc_b, z, nullptr, (int)N, HW, C, D);
+      AMMC_LAUNCH_CHECK("enc1x1_kernel");
+      if (q_planes && residual)
+        if (int rc = absmax_f32(x, (long long)N * C, amax_bits, st)) return rc;
+    }
+    if (int rc = run_address(z, embed, m, nullptr, q1, idx, counts, embed_sum, N, D, M, k, st, ws)) return rc;
   }
-  if (int rc = run_address(z, embed, m, nullptr, q1, idx, counts, embed_sum, N, D, M, k, st, ws)) return rc;
   if (int rc = run_commit(m, sse_frame, diff, N, HW, D, st)) return rc;
   const float* res = residual ? x : nullptr;
   if (tc_dec) {
     // dec(read) as a [N, kD] x [kD, C] GEMM on tcgen05 (split-bf16 x3); bias, residual and -- when asked -- the NHWC
-    // bf16 planes of `out` (the AMFT block's operand) all come out of the same epilogue
-    if (int rc = pack_weights_1x1(dec_w, dec_wp, C, k * D, st)) return rc;
-    fill_kernel<<<ceil_div(C, 256), 256, 0, st>>>(ones, 1.f, C);
-    AMMC_LAUNCH_CHECK("fill_kernel");
+    // operand planes of `out` (the AMFT block's input) all come out of the same epilogue
     ammc_conv_layer L = {};
-    L.in_planes = m.read_planes; L.wp = dec_wp; L.taps = 1; L.scale = ones; L.shift = dec_b; L.act = 0;
+    L.in_planes = m.read_planes; L.wp = pr.dec_wp; L.taps = 1; L.scale = pr.ones; L.shift = dec_b; L.act = 0;
     L.out_planes = out_planes; L.out_nchw = out; L.res_nchw = res;
     L.b = b; L.h = h; L.w = w; L.Cin = k * D; L.Cout = C; L.precision = 3;
     if (q_planes) {
       float* qs = reinterpret_cast<float*>((uint8_t*)out_planes + 4 * N * C);
-      unsigned* bound_bits = amax_bits + 1;                                 // word 9 of the stats block
-      AMMC_CUDA_CHECK(cudaMemsetAsync(bound_bits, 0, 4, st));
-      dec_bound_kernel<<<ceil_div(C, 8), 256, 0, st>>>(dec_w, dec_b, m.en2, C, D, M, k, bound_bits);
-      AMMC_LAUNCH_CHECK("dec_bound_kernel");
-      mem_out_qscale_kernel<<<1, 32, 0, st>>>(amax_bits, bound_bits, residual, qs);
+      mem_out_qscale_kernel<<<1, 32, 0, st>>>(amax_bits, pr.dec_bound, residual, qs);
       AMMC_LAUNCH_CHECK("mem_out_qscale_kernel");
       L.out_fmt = 1;
     }

@@ -186,8 +186,29 @@ def planes_of(t: torch.Tensor, fmt: str = "bf16"):
     return planes
 
 
+def set_front_mode(on: bool = True):
+    """True (default): eval forwards at the shipped shapes run enc + addressing + exact refine as one persistent kernel
+    (csrc/mem_front.cu); False: the staged kernels.  For A/B measurements; process-wide."""
+    _capi.call("ammc_set_front_mode", int(bool(on)))
+
+
+def mem_prepare(enc_w, embed, dec_w, dec_b, b: int, h: int, w: int, k: int) -> torch.Tensor:
+    """Parameter-only quantities of the memory module (packed weights, bank rows / norms / bf16 copy, q-scale bound) in one
+    buffer; valid until one of the four tensors changes.  `enc_w` [D,C], `dec_w` [C,kD] as 2-D views."""
+    _require_cuda_f32(enc_w, embed, dec_w, dec_b, names=("enc.weight", "embed", "dec.weight", "dec.bias"))
+    D, M = embed.shape
+    C = dec_w.shape[0]
+    lib = _capi.load()
+    prep = torch.empty((int(lib.ammc_mem_prep_bytes(C, D, M, k)),), dtype=torch.uint8, device=embed.device)
+    with torch.cuda.device(embed.device):
+        _capi.call("ammc_mem_prepare", _p(enc_w.contiguous()), _p(embed.contiguous()), _p(dec_w.contiguous()),
+                   _p(dec_b.contiguous()), _p(prep), prep.numel(), b, h, w, C, D, M, k, _stream())
+    _count(8)
+    return prep
+
+
 def mem_forward_raw(x, enc_w, enc_b, embed, dec_w, dec_b, k: int, residual: bool, want_stats: bool,
-                    want_planes=False):
+                    want_planes=False, prep: Optional[torch.Tensor] = None):
     """One fused-module forward.  Returns dict(out, q1[N,D], idx[N,k], z[N,D], sse_frame[b], diff[1], counts, embed_sum).
     want_planes: False | 'bf16' (True) | 'q' -- also emit `out` as the AMFT block's NHWC operand in that format."""
     want_planes = "bf16" if want_planes is True else want_planes
@@ -221,9 +242,10 @@ def mem_forward_raw(x, enc_w, enc_b, embed, dec_w, dec_b, k: int, residual: bool
     with torch.cuda.device(dev):
         _capi.call("ammc_mem_fwd", _p(x), _p(enc_w.contiguous()), _p(enc_b.contiguous()), _p(embed.contiguous()),
                    _p(dec_w.contiguous()), _p(dec_b.contiguous()), _p(out), _p(q1), _p(idx), _p(z), _p(sse), _p(diff),
-                   _p(counts), _p(esum), _p(planes), int(isinstance(planes, QPlanes)), _p(ws), ws.numel(), b, h, w, C, D, M,
-                   k, int(bool(residual)), _stream())
-    _count(8 + (2 if want_stats else 0) + (1 if isinstance(planes, QPlanes) else 0))
+                   _p(counts), _p(esum), _p(planes), int(isinstance(planes, QPlanes)), _p(prep), _p(ws), ws.numel(), b, h,
+                   w, C, D, M, k, int(bool(residual)), _stream())
+    # front kernel + rescan + 2 commit kernels + dec (+ q scale) when prepared and fused; the staged path launches more
+    _count((5 if prep is not None else 13) + (2 if want_stats else 0) + (1 if isinstance(planes, QPlanes) else 0))
     if planes is not None:
         attach_planes(out, planes)
     return dict(out=out, q1=q1, idx=idx, z=z, sse_frame=sse, diff=diff, counts=counts, embed_sum=esum, x=x)
@@ -277,10 +299,10 @@ class MemoryModuleFn(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, x, enc_w, enc_b, embed, dec_w, dec_b, k, residual, want_stats, want_planes=False):
+    def forward(ctx, x, enc_w, enc_b, embed, dec_w, dec_b, k, residual, want_stats, want_planes=False, prep=None):
         # want_planes is decided by the caller: grad mode is always off inside Function.forward
         r = mem_forward_raw(x, enc_w.reshape(enc_w.shape[0], -1), enc_b, embed, dec_w.reshape(dec_w.shape[0], -1),
-                            dec_b, k, residual, want_stats, want_planes=want_planes)
+                            dec_b, k, residual, want_stats, want_planes=want_planes, prep=prep)
         b, C, h, w = r["x"].shape
         D, M = embed.shape
         # training: the caller updates the bank in place right after this forward (EMA, unet.py:298-309);
@@ -317,7 +339,7 @@ class MemoryModuleFn(torch.autograd.Function):
                        _p(g_dec_b), _p(ws), ws.numel(), b, h, w, C, D, M, k, int(residual), _stream())
         _count(10)
         es, ds = ctx.wshapes
-        return gx, g_enc_w.view(es), g_enc_b, None, g_dec_w.view(ds), g_dec_b, None, None, None, None
+        return gx, g_enc_w.view(es), g_enc_b, None, g_dec_w.view(ds), g_dec_b, None, None, None, None, None
 
 
 class QuantizeFn(torch.autograd.Function):
@@ -403,6 +425,8 @@ def ema_update_(embed, cluster_size, embed_avg, counts, embed_sum, decay: float,
         _capi.call("ammc_ema_update", _p(embed), _p(cluster_size), _p(embed_avg), _p(counts.contiguous()),
                    _p(embed_sum.contiguous()), D, M, float(decay), float(eps), _stream())
     _count(2)
+    for t in (embed, cluster_size, embed_avg):        # mutated through raw pointers: tell autograd and the caches
+        torch.autograd.graph.increment_version(t)     # keyed on tensor versions (prepared parameters, packed weights)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -639,6 +663,9 @@ def bn_batch_stats(y, gamma, beta, running_mean, running_var, momentum: float, e
                    _p(running_var), _p(scale), _p(shift), _p(mean), _p(invstd), _p(ws), ws.numel(), b, C, h, w,
                    float(momentum), float(eps), int(bool(training)), _stream())
     _count(3 if training else 1)
+    if training:                                      # running statistics were updated in place by the kernel
+        torch.autograd.graph.increment_version(running_mean)
+        torch.autograd.graph.increment_version(running_var)
     return scale, shift, mean, invstd
 
 

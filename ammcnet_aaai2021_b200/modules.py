@@ -74,12 +74,28 @@ class enc_quan_dec_topk(nn.Module):
     # 'q' = fp16 + e4m3 (bridge precision 2, the default), 'bf16' = hi/lo planes (precision 1 / 3), None = off
     planes_format = "q"
 
+    def prepared(self, x):
+        """Parameter-only quantities of the forward (ammc_mem_prepare), re-derived only when a parameter or the bank
+        changed (eval: once; training: the EMA step bumps the bank's version every iteration)."""
+        q = self.quantize
+        src = (self.enc.weight, q.embed, self.dec.weight, self.dec.bias)
+        key = tuple((t.data_ptr(), t._version) for t in src) + (tuple(x.shape[2:]), x.shape[0] > 0, x.device)
+        hit = getattr(self, "_prep", None)
+        if hit is None or hit[0] != key:
+            D = q.embed.shape[0]
+            prep = F_.mem_prepare(self.enc.weight.detach().reshape(D, -1), q.embed, self.dec.weight.detach().reshape(
+                self.dec.weight.shape[0], -1), self.dec.bias.detach(), x.shape[0], x.shape[2], x.shape[3], q.k)
+            hit = (key, prep)
+            object.__setattr__(self, "_prep", hit)
+        return hit[1]
+
     def _run(self, x, residual):
         q = self.quantize
         want_planes = False if (self.training or torch.is_grad_enabled()) else (self.planes_format or False)
+        prep = self.prepared(x) if (x.is_cuda and x.dim() == 4 and not self.training) else None
         out, diff, q1, idx, sse, counts, esum = F_.MemoryModuleFn.apply(
             x, self.enc.weight, self.enc.bias, q.embed, self.dec.weight, self.dec.bias, q.k, residual, self.training,
-            want_planes)
+            want_planes, prep)
         q.last_idx, q.last_sse_frame = idx, sse
         if self.training:
             q._ema(counts, esum)

@@ -79,6 +79,19 @@ int ammc_debug_tma_probe(const void* base, const int64_t* dims5, const int64_t* 
  * 1 force the fp32 gather, 2 force the tensor-core GEMM.
  * ------------------------------------------------------------------------------------------------- */
 int ammc_mem_dec_uses_tensor(int b, int h, int w, int C, int D, int M, int k);
+/* Everything ammc_mem_fwd derives from the parameters alone -- packed bf16 planes of enc.weight / dec.weight, the bank as
+ * rows with its norms and bf16 copy, the bound behind the q-plane scale -- can be prepared once per parameter version:
+ * ammc_mem_prepare fills a caller-owned buffer of ammc_mem_prep_bytes(C, D, M, k) bytes (b, h, w select the same kernel
+ * paths as the forward that will use it); passing it as `prep` to ammc_mem_fwd skips those launches.  prep == NULL keeps
+ * the forward self-contained (the same quantities are derived into the workspace).  The reference re-derives them on
+ * every call too (embed.t(), unet.py:316; the conv weights are cuDNN's business there).
+ * With embed_dim == 64, n_embed <= 256, h*w % 128 == 0 and the tensor-core enc / dec paths in use, the eval forward runs
+ * enc + addressing + exact refine as ONE persistent kernel (csrc/mem_front.cu); ammc_set_front_mode(0) restores the staged
+ * kernels (A/B measurements). */
+size_t ammc_mem_prep_bytes(int C, int D, int M, int k);
+int ammc_mem_prepare(const float* enc_w, const float* embed, const float* dec_w, const float* dec_b, void* prep,
+                     size_t prep_bytes, int b, int h, int w, int C, int D, int M, int k, void* stream);
+int ammc_set_front_mode(int on);
 int ammc_set_dec_mode(int mode);
 /* `enc` runs as a split-bf16 x3 GEMM on tcgen05 that converts the fp32 NCHW input on the fly (and emits bf16(z) and
  * ||z||^2 for the addressing filter) when embed_dim == 64, C % 64 == 0 and h*w % 128 == 0; otherwise as an fp32 FFMA
@@ -98,7 +111,7 @@ int ammc_set_addressing_mode(int mode);
 int ammc_mem_fwd(const float* x, const float* enc_w, const float* enc_b, const float* embed,
                  const float* dec_w, const float* dec_b,
                  float* out, float* q1, int64_t* idx, float* z, float* sse_frame, float* diff,
-                 float* counts, float* embed_sum, void* out_planes, int planes_fmt,
+                 float* counts, float* embed_sum, void* out_planes, int planes_fmt, const void* prep,
                  void* workspace, size_t workspace_bytes,
                  int b, int h, int w, int C, int D, int M, int k, int residual, void* stream);
 

@@ -245,7 +245,7 @@ def test_shipped_module_uses_tensor_path_and_matches_golden(addressing_mode):
         with torch.no_grad():
             out, diff, q1 = m(x.to(DEV))
         res[mode] = (m.quan.quantize.last_idx.clone(), out.clone(), diff.clone(), F_.last_addressing_stats())
-    assert res["auto"][3][1] == 2 and res["fp32"][3][1] == 1
+    assert res["auto"][3][1] == 3 and res["fp32"][3][1] == 1      # auto = the fused enc + addressing kernel (path 3)
     for mode in ("tensor", "auto"):
         assert torch.equal(res[mode][0], res["fp32"][0]) and torch.equal(res[mode][1], res["fp32"][1])
         assert torch.equal(res[mode][2], res["fp32"][2])
@@ -255,6 +255,95 @@ def test_shipped_module_uses_tensor_path_and_matches_golden(addressing_mode):
         addressing_mode("tensor")
         q = A.Quantize_topk(32, 50, k=3).to(DEV).eval()
         q(torch.zeros(1, 4, 4, 32, device=DEV))
+
+
+# --------------------------------------------------------------------------------------------------
+# fused front kernel (enc + similarity + exact refine in one persistent kernel) vs the staged kernels
+# --------------------------------------------------------------------------------------------------
+@pytest.fixture
+def front_mode():
+    yield F_.set_front_mode
+    F_.set_front_mode(True)
+
+
+def _adversarial_memory_params(seed, C, D, M, k):
+    """Bank of 16 clusters of near-duplicates plus one exact duplicate: candidate lists overflow, the fused kernel must
+    hand those rows to the exact re-scan and still return the fp32 kernel's indices."""
+    p = synth.memory_params(seed, C, D, M, k)
+    g = torch.Generator().manual_seed(seed)
+    base = torch.randn((D, 16), generator=g)
+    emb = base.repeat(1, (M + 15) // 16)[:, :M] + 1e-3 * torch.randn((D, M), generator=g)
+    emb[:, 5] = emb[:, 4]
+    p["quantize.embed"] = emb
+    p["quantize.embed_avg"] = emb.clone()
+    return p
+
+
+@pytest.mark.parametrize("b,C,h,w,M,k,adversarial", [(3, 512, 32, 32, 256, 2, False), (2, 512, 8, 16, 256, 2, False),
+                                                      (2, 128, 16, 16, 100, 1, False), (1, 192, 8, 32, 37, 3, False),
+                                                      (2, 256, 16, 8, 256, 4, False), (2, 512, 16, 16, 256, 2, True),
+                                                      (5, 64, 8, 16, 200, 2, False)])
+def test_fused_front_kernel_bit_identical_to_staged_kernels(b, C, h, w, M, k, adversarial, front_mode, addressing_mode):
+    D = 64
+    p = (_adversarial_memory_params if adversarial else synth.memory_params)(50 + M + k, C, D, M, k)
+    x = synth.features(60 + C, b, C, h, w)
+    if adversarial:       # queries sitting (almost) on items: every cluster member is a candidate
+        pass
+    outs = {}
+    for name, front, amode in (("fused", True, "auto"), ("staged", False, "auto"), ("fp32", False, "fp32")):
+        front_mode(front)
+        addressing_mode(amode)
+        m = A.enc_quan_dec_res_topk(C, D, M, k=k)
+        m.load_state_dict({"quan." + kk: v for kk, v in p.items()})
+        m = m.to(DEV).eval()
+        with torch.no_grad():
+            out, diff, q1 = m(x.to(DEV))
+        st = F_.last_addressing_stats()
+        outs[name] = (m.quan.quantize.last_idx.clone(), q1.clone(), m.quan.quantize.last_sse_frame.clone(), diff.clone(),
+                      out.clone(), st, F_.planes_of(out, "q") is not None)
+    F_.check_pipeline_watchdog()
+    assert outs["fused"][5][1] == 3 and outs["staged"][5][1] == 2 and outs["fp32"][5][1] == 1, [o[5] for o in outs.values()]
+    for other in ("staged", "fp32"):
+        for i, what in enumerate(("indices", "q1", "per-frame SSE", "commit", "out")):
+            assert torch.equal(outs["fused"][i], outs[other][i]), "%s differs between the fused and the %s path" % (what, other)
+    if adversarial:
+        print("adversarial bank: fused front re-scanned", outs["fused"][5][0], "of", b * h * w, "rows")
+        assert outs["fused"][5][0] > 0
+    o = O.memory_module_forward(x, p["enc.weight"], p["enc.bias"], p["quantize.embed"], p["dec.weight"], p["dec.bias"], k)
+    same = (outs["fused"][0].cpu() == o["idx_topk"]).all(1).view(b, h, w)
+    if not adversarial:
+        assert same.float().mean() > 0.98
+        assert_close(outs["fused"][4].cpu().permute(0, 2, 3, 1)[same], o["out"].permute(0, 2, 3, 1)[same], 1e-3, "fused vs oracle")
+
+
+def test_prepared_parameters_follow_parameter_updates():
+    """The cached parameter-only buffer must be re-derived when a weight or the bank changes (including the in-place EMA
+    step of a training forward, which mutates the bank through a raw pointer)."""
+    C, D, M, k = 128, 64, 64, 2
+    p = synth.memory_params(71, C, D, M, k)
+    x = synth.features(72, 2, C, 8, 16).to(DEV)
+    m = A.enc_quan_dec_res_topk(C, D, M, k=k)
+    m.load_state_dict({"quan." + kk: v for kk, v in p.items()})
+    m = m.to(DEV).eval()
+
+    def fresh():
+        f = A.enc_quan_dec_res_topk(C, D, M, k=k).to(DEV).eval()
+        f.load_state_dict(m.state_dict())
+        with torch.no_grad():
+            return f(x)[0]
+
+    with torch.no_grad():
+        o0 = m(x)[0]
+        prep0 = m.quan._prep[1]
+        assert m(x)[0] is not None and m.quan._prep[1] is prep0           # unchanged parameters: same buffer
+        m.quan.dec.weight.mul_(1.5)
+        o1 = m(x)[0]
+        assert m.quan._prep[1] is not prep0 and not torch.equal(o0, o1) and torch.equal(o1, fresh())
+    m.train()
+    m(x)                                                                   # EMA step: bank mutated by the kernel
+    m.eval()
+    with torch.no_grad():
+        assert torch.equal(m(x)[0], fresh())
 
 
 # --------------------------------------------------------------------------------------------------
