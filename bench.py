@@ -103,7 +103,33 @@ def cpu_baseline_and_parity(gpu_out, inputs, p, frames_per_call=4):
             "sample": "the %d frames of the timed batch (oracle/ammc_oracle.py path_forward, torch CPU fp32, %d threads, "
                       "%d frames per call), %.1f s" % (n, cores, frames_per_call, dt)}
     parity = check_parity(gpu_out, outs, frames_per_call, n)
-    return base, parity
+    return base, parity, outs
+
+
+def bf16_io_report(idx, outs, yr, yo, scores, oracle_outs, n):
+    """bf16-rounded inputs vs the fp32 oracle on the exact inputs (north_star: 'bf16 variants stated separately')."""
+    def cat(f):
+        return torch.cat([f(o) for o in oracle_outs])
+
+    def rel(a, b):
+        a, b = a.double().cpu(), b.double()
+        return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+    rep = {"what": "same fp32-parity device path, inputs rounded to bf16 at the host boundary; reference = fp32 oracle on "
+                   "the unrounded inputs"}
+    ok = None
+    for s in ("rgb", "op"):
+        same = (idx[s].cpu() == cat(lambda o: o[s]["idx_topk"])).all(1)
+        rep["index_agreement_" + s] = float(same.float().mean())
+        fr = same.view(n, -1).all(1)
+        ok = fr if ok is None else (ok & fr)
+        rep["out_%s_rel_err_all_frames" % s] = rel(outs[s], cat(lambda o: o[s]["out"]))
+    rep["frames_with_identical_indices"] = int(ok.sum())
+    if ok.any():
+        rep["amft_rgb_rel_err_identical_index_frames"] = rel(yr[ok.to(yr.device)], cat(lambda o: o["amft_rgb"])[ok])
+        rep["amft_op_rel_err_identical_index_frames"] = rel(yo[ok.to(yo.device)], cat(lambda o: o["amft_op"])[ok])
+    rep["psnr_rel_err"] = rel(scores[0], cat(lambda o: o["psnr"]))
+    return rep
 
 
 def check_parity(gpu_out, oracle_outs, per_call, n, tol=1e-3):
@@ -408,8 +434,20 @@ def run_ours(args):
         F_.check_pipeline_watchdog()
         gpu_out = dict(idx_rgb=idx_r, idx_op=idx_o, sse_rgb=sse_r, sse_op=sse_o, psnr=sc[0], out_rgb=o_r, out_op=o_o,
                        amft_rgb=yr, amft_op=yo)
-        cpu_base, parity = cpu_baseline_and_parity(gpu_out, (xr_c, xo_c, gen_c, gt_c), p)
+        cpu_base, parity, oracle_outs = cpu_baseline_and_parity(gpu_out, (xr_c, xo_c, gen_c, gt_c), p)
         del gpu_out, o_r, o_o, yr, yo
+        # bf16 feature I/O (BASELINE configs[2]), stated separately: the same device path fed with the bf16 rounding of
+        # the inputs, against the fp32 oracle on the unrounded inputs -- index agreement and relative errors, not a gate
+        with torch.no_grad():
+            xr16, xo16 = xr.to(torch.bfloat16).float(), xo.to(torch.bfloat16).float()
+            yr16, yo16, sc16 = local_step(xr16, xo16, gen.to(torch.bfloat16).float(), gt)
+            i16 = {s: mem[s].quan.quantize.last_idx.clone() for s in ("rgb", "op")}     # rgb ran last on its own module
+            o16 = {}
+            for s, xin in (("rgb", xr16), ("op", xo16)):
+                o16[s] = mem[s](xin)[0]
+                i16[s] = mem[s].quan.quantize.last_idx.clone()
+        parity["bf16_io_variant"] = bf16_io_report(i16, o16, yr16, yo16, sc16, oracle_outs, B)
+        del xr16, xo16, yr16, yo16, o16, oracle_outs
 
     sampler = ClockSampler(local) if rank == 0 else None      # started before warm-up so it is sampling by the time we time
     use_graph = not args.no_graph
