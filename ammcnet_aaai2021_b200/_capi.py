@@ -76,6 +76,8 @@ SIGNATURES = {
     "ammc_bn_batch_stats": (I, [P] * 9 + [P, Z] + [I, I, I, I, F, F, I, P]),
     "ammc_bn_apply": (I, [P, P, P, I, P, P, P, P, I, I, I, I, P]),
     "ammc_bn_backward": (I, [P] * 6 + [I, I] + [P] * 4 + [P, Z] + [I, I, I, I, P]),
+    "ammc_bn_batch_stats_staged": (I, [P] * 9 + [P, Z] + [I, I, I, I, F, F, I, I, c_double, P]),
+    "ammc_bn_backward_staged": (I, [P] * 6 + [I, I] + [P] * 4 + [P, Z] + [I, I, I, I, I, c_double, P]),
     "ammc_pack_planes": (I, [P, P, L, P]),
     "ammc_pack_conv_weights_dgrad": (I, [P, P, I, I, P]),
     "ammc_conv3x3_wgrad": (I, [P, P, P, I, I, I, I, I, I, P]),

@@ -453,12 +453,32 @@ extern "C" int ammc_debug_tma_probe(const void* base, const int64_t* dims5, cons
   return 0;
 }
 
+extern "C" int ammc_bn_batch_stats_staged(const float* y, const float* gamma, const float* beta, float* running_mean,
+                                          float* running_var, float* scale, float* shift, float* mean, float* invstd,
+                                          void* workspace, size_t workspace_bytes, int b, int C, int h, int w,
+                                          float momentum, float eps, int training, int stage, double count_total,
+                                          void* stream);
+
 extern "C" int ammc_bn_batch_stats(const float* y, const float* gamma, const float* beta, float* running_mean,
                                    float* running_var, float* scale, float* shift, float* mean, float* invstd,
                                    void* workspace, size_t workspace_bytes, int b, int C, int h, int w, float momentum,
                                    float eps, int training, void* stream) {
+  return ammc_bn_batch_stats_staged(y, gamma, beta, running_mean, running_var, scale, shift, mean, invstd, workspace,
+                                    workspace_bytes, b, C, h, w, momentum, eps, training, 0, 0.0, stream);
+}
+
+// stage 0: everything in one call (per-rank statistics).  Data-parallel training with GLOBAL-batch statistics (what a
+// single-GPU run of the reference computes, unet.py:11-16): stage 1 leaves the per-channel (sum, sum of squares) as 2*C
+// doubles in the workspace, the caller all-reduces them, stage 2 finishes with `count_total` = elements per channel over
+// all ranks.
+extern "C" int ammc_bn_batch_stats_staged(const float* y, const float* gamma, const float* beta, float* running_mean,
+                                          float* running_var, float* scale, float* shift, float* mean, float* invstd,
+                                          void* workspace, size_t workspace_bytes, int b, int C, int h, int w,
+                                          float momentum, float eps, int training, int stage, double count_total,
+                                          void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   AMMC_REQUIRE(gamma && beta && running_mean && running_var && scale && shift && mean && invstd && C > 0, "bad argument");
+  AMMC_REQUIRE(stage >= 0 && stage <= 2, "stage must be 0 (all), 1 (local sums) or 2 (finalize)");
   if (!training) {
     bn_eval_params_kernel<<<ceil_div(C, 128), 128, 0, st>>>(gamma, beta, running_mean, running_var, scale, shift, mean,
                                                             invstd, C, eps);
@@ -468,13 +488,18 @@ extern "C" int ammc_bn_batch_stats(const float* y, const float* gamma, const flo
   AMMC_REQUIRE(y && b > 0 && h > 0 && w > 0, "bad argument");
   if (!workspace || workspace_bytes < (size_t)2 * C * sizeof(double)) return fail(AMMC_EWORKSPACE, "workspace too small");
   double* sums = (double*)workspace;
-  AMMC_CUDA_CHECK(cudaMemsetAsync(sums, 0, (size_t)2 * C * sizeof(double), st));
-  const int splits = max(1, min(b, ceil_div(4 * num_sms(), C)));
-  const int per = ceil_div(b, splits);
-  bn_stats_kernel<<<dim3(C, ceil_div(b, per)), 256, 0, st>>>(y, sums, b, C, h * w, per);
-  AMMC_LAUNCH_CHECK("bn_stats_kernel");
+  if (stage != 2) {
+    AMMC_CUDA_CHECK(cudaMemsetAsync(sums, 0, (size_t)2 * C * sizeof(double), st));
+    const int splits = max(1, min(b, ceil_div(4 * num_sms(), C)));
+    const int per = ceil_div(b, splits);
+    bn_stats_kernel<<<dim3(C, ceil_div(b, per)), 256, 0, st>>>(y, sums, b, C, h * w, per);
+    AMMC_LAUNCH_CHECK("bn_stats_kernel");
+    if (stage == 1) return 0;
+  }
+  const double count = stage == 2 ? count_total : (double)b * h * w;
+  AMMC_REQUIRE(count >= 1.0, "count_total must be the number of elements per channel over all ranks");
   bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(sums, gamma, beta, running_mean, running_var, scale, shift, mean,
-                                                       invstd, C, (double)b * h * w, momentum, eps, 1);
+                                                       invstd, C, count, momentum, eps, 1);
   AMMC_LAUNCH_CHECK("bn_finalize_kernel");
   return 0;
 }
@@ -498,26 +523,48 @@ extern "C" int ammc_bn_apply(const float* y, const float* scale, const float* sh
   return launch_apply(a, b, C, h, w, (cudaStream_t)stream);
 }
 
+extern "C" int ammc_bn_backward_staged(const float* g, const float* y, const float* scale, const float* shift,
+                                       const float* mean, const float* invstd, int relu, int training, void* gy_nhwc_planes,
+                                       void* gy_nchw_planes, float* g_gamma, float* g_beta, void* workspace,
+                                       size_t workspace_bytes, int b, int C, int h, int w, int stage, double count_total,
+                                       void* stream);
+
 extern "C" int ammc_bn_backward(const float* g, const float* y, const float* scale, const float* shift, const float* mean,
                                 const float* invstd, int relu, int training, void* gy_nhwc_planes, void* gy_nchw_planes,
                                 float* g_gamma, float* g_beta, void* workspace, size_t workspace_bytes, int b, int C, int h,
                                 int w, void* stream) {
+  return ammc_bn_backward_staged(g, y, scale, shift, mean, invstd, relu, training, gy_nhwc_planes, gy_nchw_planes, g_gamma,
+                                 g_beta, workspace, workspace_bytes, b, C, h, w, 0, 0.0, stream);
+}
+
+// stage 0: one call.  Global-batch statistics: stage 1 reduces this rank's (sum g', sum g' * yhat) into the workspace and
+// writes the LOCAL parameter gradients (they are all-reduced with the other gradients); the caller all-reduces the 2*C
+// doubles; stage 2 applies the BatchNorm backward with the global sums and `count_total`.
+extern "C" int ammc_bn_backward_staged(const float* g, const float* y, const float* scale, const float* shift,
+                                       const float* mean, const float* invstd, int relu, int training, void* gy_nhwc_planes,
+                                       void* gy_nchw_planes, float* g_gamma, float* g_beta, void* workspace,
+                                       size_t workspace_bytes, int b, int C, int h, int w, int stage, double count_total,
+                                       void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   AMMC_REQUIRE(g && y && scale && shift && mean && invstd && g_gamma && g_beta && (gy_nhwc_planes || gy_nchw_planes),
                "bad argument");
+  AMMC_REQUIRE(stage >= 0 && stage <= 2, "stage must be 0 (all), 1 (local sums) or 2 (apply)");
   if (!workspace || workspace_bytes < (size_t)2 * C * sizeof(double)) return fail(AMMC_EWORKSPACE, "workspace too small");
   double* sums = (double*)workspace;
-  AMMC_CUDA_CHECK(cudaMemsetAsync(sums, 0, (size_t)2 * C * sizeof(double), st));
-  const int splits = max(1, min(b, ceil_div(4 * num_sms(), C)));
-  const int per = ceil_div(b, splits);
-  bn_bwd_reduce_kernel<<<dim3(C, ceil_div(b, per)), 256, 0, st>>>(g, y, scale, shift, mean, invstd, relu, sums, b, C, h * w,
-                                                                  per);
-  AMMC_LAUNCH_CHECK("bn_bwd_reduce_kernel");
-  bn_param_grads_kernel<<<ceil_div(C, 128), 128, 0, st>>>(sums, g_gamma, g_beta, C);
-  AMMC_LAUNCH_CHECK("bn_param_grads_kernel");
+  if (stage != 2) {
+    AMMC_CUDA_CHECK(cudaMemsetAsync(sums, 0, (size_t)2 * C * sizeof(double), st));
+    const int splits = max(1, min(b, ceil_div(4 * num_sms(), C)));
+    const int per = ceil_div(b, splits);
+    bn_bwd_reduce_kernel<<<dim3(C, ceil_div(b, per)), 256, 0, st>>>(g, y, scale, shift, mean, invstd, relu, sums, b, C,
+                                                                    h * w, per);
+    AMMC_LAUNCH_CHECK("bn_bwd_reduce_kernel");
+    bn_param_grads_kernel<<<ceil_div(C, 128), 128, 0, st>>>(sums, g_gamma, g_beta, C);
+    AMMC_LAUNCH_CHECK("bn_param_grads_kernel");
+    if (stage == 1) return 0;
+  }
   ApplyArgs a{};
   a.y = y; a.g = g; a.scale = scale; a.shift = shift; a.mean = mean; a.invstd = invstd; a.bsums = sums;
-  a.inv_count = 1.0 / ((double)b * h * w);
+  a.inv_count = 1.0 / (stage == 2 ? count_total : (double)b * h * w);
   a.mode = training ? 1 : 2; a.relu = relu;
   a.nhwc = (__nv_bfloat16*)gy_nhwc_planes; a.nchw = (__nv_bfloat16*)gy_nchw_planes;
   a.plane_stride = (long long)b * C * h * w;

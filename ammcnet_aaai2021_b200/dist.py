@@ -88,6 +88,47 @@ def uninstall_stats_allreduce():
     _modules._Hooks.stats_allreduce = None
 
 
+def install_sync_bn(model=None, group=None):
+    """GLOBAL-batch BatchNorm statistics under data parallelism -- the semantics of the reference's single-GPU step
+    (BatchNorm inside `double_conv`, unet.py:11-16; step structure train_helper.py:291-343):
+
+    * the AMFT block's own kernels: the per-channel sums of the forward statistics and of the BatchNorm backward are
+      sum-all-reduced between the two stages of ammc_bn_batch_stats_staged / ammc_bn_backward_staged;
+    * the stock torch.nn.BatchNorm2d layers of the U-Net encoder / decoder (left on cuDNN for training): converted to
+      torch.nn.SyncBatchNorm when `model` is given.  Returns the (possibly converted) model.
+    Without this call every rank normalises with its own batch (stated as per-rank BN in DESIGN.md)."""
+    from . import functions as _F
+
+    def allreduce(sums):
+        if dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+            return dist.get_world_size(group)
+        return 1
+
+    _F.BN_SYNC["allreduce"] = allreduce
+    if model is not None and dist.is_initialized() and dist.get_world_size(group) > 1:
+        bridge = getattr(model, "bridge", None)
+        # the bridge's BatchNorm2d modules are parameter containers of our own kernels: keep them as they are
+        keep = {id(m) for m in bridge.modules()} if bridge is not None else set()
+
+        def convert(mod):
+            for name, child in list(mod.named_children()):
+                if id(child) in keep:
+                    continue
+                if isinstance(child, torch.nn.BatchNorm2d):
+                    setattr(mod, name, torch.nn.SyncBatchNorm.convert_sync_batchnorm(child, group))
+                else:
+                    convert(child)
+            return mod
+        model = convert(model)
+    return model
+
+
+def uninstall_sync_bn():
+    from . import functions as _F
+    _F.BN_SYNC["allreduce"] = None
+
+
 def allreduce_gradients(params, group=None, average: bool = True):
     """One flat all-reduce of all gradients (25 M fp32 = 100 MB for the whole generator; sub-millisecond class on NVLink 5)."""
     grads = [p.grad for p in params if p.grad is not None]

@@ -652,16 +652,31 @@ def unpack_nhwc(planes: torch.Tensor, C: Optional[int] = None, c_off: int = 0) -
     return x
 
 
+# optional data-parallel hook: callable(sums[2C] float64 CUDA tensor) -> world size; all-reduces (SUM) the per-channel
+# BatchNorm sums in place so that statistics are those of the GLOBAL batch (installed by ammcnet_aaai2021_b200.dist)
+BN_SYNC = {"allreduce": None}
+
+
 def bn_batch_stats(y, gamma, beta, running_mean, running_var, momentum: float, eps: float, training: bool):
     """(scale, shift, mean, invstd) of a BatchNorm2d over y [b,C,h,w]; updates the running stats in place when training."""
     b, C, h, w = y.shape
     dev = y.device
     scale, shift, mean, invstd = (torch.empty((C,), dtype=torch.float32, device=dev) for _ in range(4))
-    ws = _workspace(2 * C * 8, dev)
-    with torch.cuda.device(dev):
-        _capi.call("ammc_bn_batch_stats", _p(y), _p(gamma.contiguous()), _p(beta.contiguous()), _p(running_mean),
-                   _p(running_var), _p(scale), _p(shift), _p(mean), _p(invstd), _p(ws), ws.numel(), b, C, h, w,
-                   float(momentum), float(eps), int(bool(training)), _stream())
+    sync = BN_SYNC["allreduce"] if training else None
+    if sync is None:
+        ws = _workspace(2 * C * 8, dev)
+        with torch.cuda.device(dev):
+            _capi.call("ammc_bn_batch_stats", _p(y), _p(gamma.contiguous()), _p(beta.contiguous()), _p(running_mean),
+                       _p(running_var), _p(scale), _p(shift), _p(mean), _p(invstd), _p(ws), ws.numel(), b, C, h, w,
+                       float(momentum), float(eps), int(bool(training)), _stream())
+    else:
+        sums = torch.empty((2 * C,), dtype=torch.float64, device=dev)
+        args = (_p(y), _p(gamma.contiguous()), _p(beta.contiguous()), _p(running_mean), _p(running_var), _p(scale), _p(shift),
+                _p(mean), _p(invstd), _p(sums), sums.numel() * 8, b, C, h, w, float(momentum), float(eps), 1)
+        with torch.cuda.device(dev):
+            _capi.call("ammc_bn_batch_stats_staged", *args, 1, 0.0, _stream())
+            world = int(sync(sums))
+            _capi.call("ammc_bn_batch_stats_staged", *args, 2, float(world) * b * h * w, _stream())
     _count(3 if training else 1)
     if training:                                      # running statistics were updated in place by the kernel
         torch.autograd.graph.increment_version(running_mean)
@@ -691,11 +706,22 @@ def bn_backward(g, y, scale, shift, mean, invstd, *, relu=True, training=True):
     gy_nchw = None
     gg = torch.empty((C,), dtype=torch.float32, device=dev)
     gb = torch.empty((C,), dtype=torch.float32, device=dev)
-    ws = _workspace(2 * C * 8, dev)
-    with torch.cuda.device(dev):
-        _capi.call("ammc_bn_backward", _p(g.contiguous()), _p(y), _p(scale), _p(shift), _p(mean), _p(invstd),
-                   int(bool(relu)), int(bool(training)), _p(gy_nhwc), _p(gy_nchw), _p(gg), _p(gb), _p(ws), ws.numel(),
-                   b, C, h, w, _stream())
+    sync = BN_SYNC["allreduce"] if training else None
+    if sync is None:
+        ws = _workspace(2 * C * 8, dev)
+        with torch.cuda.device(dev):
+            _capi.call("ammc_bn_backward", _p(g.contiguous()), _p(y), _p(scale), _p(shift), _p(mean), _p(invstd),
+                       int(bool(relu)), int(bool(training)), _p(gy_nhwc), _p(gy_nchw), _p(gg), _p(gb), _p(ws), ws.numel(),
+                       b, C, h, w, _stream())
+    else:
+        sums = torch.empty((2 * C,), dtype=torch.float64, device=dev)
+        gc = g.contiguous()
+        args = (_p(gc), _p(y), _p(scale), _p(shift), _p(mean), _p(invstd), int(bool(relu)), 1, _p(gy_nhwc), _p(gy_nchw),
+                _p(gg), _p(gb), _p(sums), sums.numel() * 8, b, C, h, w)
+        with torch.cuda.device(dev):
+            _capi.call("ammc_bn_backward_staged", *args, 1, 0.0, _stream())
+            world = int(sync(sums))
+            _capi.call("ammc_bn_backward_staged", *args, 2, float(world) * b * h * w, _stream())
     _count(4)
     return gy_nhwc, gg, gb
 

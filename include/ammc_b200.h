@@ -285,6 +285,19 @@ int ammc_bn_backward(const float* g, const float* y, const float* scale, const f
                      const float* invstd, int relu, int training, void* gy_nhwc_planes, void* gy_nchw_planes,
                      float* g_gamma, float* g_beta, void* workspace, size_t workspace_bytes, int b, int C, int h, int w,
                      void* stream);
+/* Staged forms for data-parallel training with GLOBAL-batch BatchNorm statistics (what one GPU running the reference on the
+ * whole batch computes): stage 1 leaves this rank's per-channel sums as 2*C doubles at the start of the workspace, the
+ * caller all-reduces them (NCCL, SUM), stage 2 finishes with count_total = elements per channel over all ranks.  stage 0 =
+ * the single-call forms above.  The backward's stage 1 also writes the LOCAL g_gamma / g_beta (reduced with the other
+ * parameter gradients). */
+int ammc_bn_batch_stats_staged(const float* y, const float* gamma, const float* beta, float* running_mean,
+                               float* running_var, float* scale, float* shift, float* mean, float* invstd, void* workspace,
+                               size_t workspace_bytes, int b, int C, int h, int w, float momentum, float eps, int training,
+                               int stage, double count_total, void* stream);
+int ammc_bn_backward_staged(const float* g, const float* y, const float* scale, const float* shift, const float* mean,
+                            const float* invstd, int relu, int training, void* gy_nhwc_planes, void* gy_nchw_planes,
+                            float* g_gamma, float* g_beta, void* workspace, size_t workspace_bytes, int b, int C, int h, int w,
+                            int stage, double count_total, void* stream);
 int ammc_pack_planes(const float* x, void* xp, int64_t n, void* stream);
 int ammc_pack_conv_weights_dgrad(const float* w, void* wp, int Cout, int Cin, void* stream);
 int ammc_conv3x3_wgrad(const void* gy_nhwc_planes, const void* x_nhwc_planes, float* gw, int b, int Cin, int Cout,

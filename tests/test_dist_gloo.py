@@ -66,6 +66,20 @@ def _worker(rank, world, port, out_dir):
         adist.allreduce_gradients(list(lin.parameters()))
         for p in lin.parameters():
             assert torch.allclose(p.grad, torch.full_like(p, (world - 1) / 2.0))
+        # global-batch BatchNorm: the hook sums the per-channel statistics over ranks and reports the world size; stock
+        # BatchNorm2d layers outside the AMFT block become SyncBatchNorm, the block's own parameter containers stay
+        import ammcnet_aaai2021_b200 as A
+        from ammcnet_aaai2021_b200 import functions as F_
+        net = torch.nn.Module()
+        net.enc = torch.nn.Sequential(torch.nn.Conv2d(3, 4, 3), torch.nn.BatchNorm2d(4))
+        net.bridge = A.bridge(in_c=64)
+        net = adist.install_sync_bn(net)
+        assert isinstance(net.enc[1], torch.nn.SyncBatchNorm) and type(net.bridge.O2F.conv[1]) is torch.nn.BatchNorm2d
+        sums = torch.arange(6, dtype=torch.float64) * (rank + 1)
+        assert F_.BN_SYNC["allreduce"](sums) == world
+        assert torch.equal(sums, torch.arange(6, dtype=torch.float64) * tot)
+        adist.uninstall_sync_bn()
+        assert F_.BN_SYNC["allreduce"] is None
         sc = adist.all_gather_scores(torch.full((2, 5), float(rank)))
         assert sc.shape == (world, 2, 5) and float(sc[1].mean()) == 1.0
         open(os.path.join(out_dir, "ok%d" % rank), "w").write("ok")

@@ -373,3 +373,34 @@ def test_bridge_training_gradients_at_shipped_shape_vs_float64():
         assert_close(prm.grad.cpu(), leaves[name].grad, 1e-3, "c512.g_" + name)
         n += 1
     assert n == 12
+
+
+def test_staged_batchnorm_statistics_equal_single_call():
+    """Global-batch BatchNorm plumbing (ammc_bn_*_staged): with a stand-in all-reduce that doubles the per-channel sums and
+    reports two ranks -- the statistics of the batch seen twice -- forward, gradients and running means must equal the
+    single-call per-rank path (the unbiased running variance differs by the n/(n-1) factor of the doubled count)."""
+    c, g = load_golden("amft_c64")
+    p, zx, zy = _inputs(c)
+    res = {}
+    for mode in ("local", "staged"):
+        m = A.bridge(in_c=c["C"], precision=3)
+        m.load_state_dict({k: v.clone() for k, v in p.items()}, strict=True)
+        m = m.to(DEV).train()
+        F_.BN_SYNC["allreduce"] = (lambda sums: (sums.mul_(2.0), 2)[1]) if mode == "staged" else None
+        try:
+            zxg, zyg = zx.to(DEV).requires_grad_(True), zy.to(DEV).requires_grad_(True)
+            tx, ty = m(zxg, zyg)
+            (tx.sum() + (ty * ty).sum()).backward()
+        finally:
+            F_.BN_SYNC["allreduce"] = None
+        res[mode] = (tx.detach(), ty.detach(), zxg.grad, zyg.grad, [q.grad for q in m.parameters()],
+                     m.O2F.conv[1].running_mean.clone(), m.O2F.conv[1].running_var.clone())
+    a, b = res["local"], res["staged"]
+    for i in range(4):
+        assert torch.equal(a[i], b[i]), i
+    for ga, gb in zip(a[4], b[4]):
+        assert torch.equal(ga, gb)
+    assert torch.equal(a[5], b[5])
+    n = c["b"] * c["h"] * c["w"]
+    assert_close(b[6] - 0.9 * p["O2F.conv.1.running_var"].to(DEV), (a[6] - 0.9 * p["O2F.conv.1.running_var"].to(DEV)) *
+                 ((2 * n) / (2 * n - 1.0)) / (n / (n - 1.0)), 1e-5, "running_var with the doubled count")

@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=8)       # per GPU (reference script: batch 8, training_com.sh:21)
     ap.add_argument("--size", type=int, default=256)
+    ap.add_argument("--sync-bn", action="store_true", help="global-batch BatchNorm statistics (single-GPU semantics)")
     args = ap.parse_args()
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
     torch.cuda.set_device(local)
@@ -32,6 +33,8 @@ def main():
         adist.install_stats_allreduce()
     torch.manual_seed(20200525)                           # same init on every rank (reference seeds at import, unet.py:4)
     g = A.get_twostream().to(dev).train()
+    if args.sync_bn:
+        g = adist.install_sync_bn(g)
     opt = torch.optim.Adam(g.parameters(), lr=2e-4)
     params = [p for p in g.parameters()]
     gen = torch.Generator().manual_seed(77 + rank)
@@ -84,7 +87,7 @@ def main():
     if rank == 0:
         ls = [float(l) for l in losses]
         print(json.dumps({"what": "joint training step (generator fwd+bwd, EMA stats + gradient all-reduce, Adam)",
-                          "n_gpus": world, "batch_per_gpu": B, "steps": args.steps, "ms_per_step": float(ms) / args.steps,
+                          "n_gpus": world, "batch_per_gpu": B, "batch_norm": "global batch (all-reduced sums)" if args.sync_bn else "per rank", "steps": args.steps, "ms_per_step": float(ms) / args.steps,
                           "frames_per_s": world * B * args.steps / (float(ms) * 1e-3), "loss_first": ls[0], "loss_last": ls[-1],
                           "finite": all(l == l and abs(l) < 1e30 for l in ls),
                           "bank_max_abs_dev_across_ranks": float(bank_max_dev), "weight_max_abs_dev_across_ranks": float(w_max_dev)}))
