@@ -2,14 +2,18 @@
 // similarity matrix living only in TMEM.
 //
 // Exactness scheme ("filter + refine"): the reference ranks fp32 distances (Code/models/unet.py:283-293).  tcgen05 has
-// no fp32 MMA, so the N x M x D contraction runs ONCE in bf16 as a *filter* that keeps, per query, the CAND = 8 items
-// with the smallest approximate score  a~_j = ||e_j||^2 - 2 z~.e~_j  (||z||^2 is rank-irrelevant).  `refine_kernel` then
-// recomputes the exact fp32 distance of those 8 items with the SAME arithmetic as the generic fp32 path (mem_simt.cu)
-// and ranks them.  A rigorous bound makes this safe:  |a~_j - a_j| <= 2 eps,  eps = 2^-8 * 1.02 * ||z|| * max_j ||e_j||
-// (bf16 rounding of both operands + Cauchy-Schwarz).  Every item that was filtered out has a~ >= tau (the worst kept
-// score), hence a >= tau - 2 eps; if the exact k-th best is below that, no filtered item can belong to the top-k.
-// Rows that fail the test (near-degenerate neighbourhoods) are re-scanned exactly over all M items in place, so the
-// indices are bit-identical to the fp32 path for every input; the number of such rows is reported in the stats block.
+// no fp32 MMA, so the N x M x D contraction runs ONCE in fp16 as a *filter*: queries are scaled per row and the bank per
+// tensor by powers of two (max component -> [2^14, 2^15), so neither overflow nor lost small rows can occur), rounded to
+// fp16 (u = 2^-11) and multiplied on the tensor cores; the epilogue forms the approximate score
+//   a~_j = ||e_j||^2 - 2 (z~.e~_j) / (s_n t)          (||z||^2 is rank-irrelevant)
+// and keeps every item within a margin of the k-th smallest.  |a~_j - a_j| <= 2 (2u + u^2) ||z|| ||e_j|| (rounding of both
+// operands, Cauchy-Schwarz), so with margin = 8 u (1 + 1%) ||z|| max||e|| (+ fp32 accumulation slack) the kept set is a
+// superset of the exact top-k.  fp16 instead of bf16 shrinks that margin -- and with it the candidate lists -- eightfold:
+// at D = 1024, M = 8192 the bf16 margin admitted ~11 items per column half (lists of 12 overflowed on 6 % of the rows,
+// each paying an exact scan of the whole bank), the fp16 margin ~2-3.  `refine_kernel` then recomputes the candidates'
+// exact fp32 distances with the SAME arithmetic as the generic fp32 path (mem_simt.cu) and ranks them; rows whose list
+// still overflowed (near-degenerate neighbourhoods) are re-scanned exactly over all M items, so the indices are
+// bit-identical to the fp32 path for every input; the number of such rows is reported in the stats block.
 //
 //   addr_tc_kernel<BLOCK_N>   persistent; per 128-query tile loops over item tiles; TMA (128B swizzle) -> smem ->
 //                             tcgen05.mma (M128 x N BLOCK_N x K16, fp32 accum in TMEM, 2 accumulator buffers);
@@ -21,6 +25,7 @@
 #include "topk.cuh"
 #include "addr_tail.cuh"
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <float.h>
 
 namespace ammc {
@@ -36,8 +41,8 @@ struct AddrParams {
   int N, D, M, Mpad;
   int tiles_q, tiles_i;
   const float* en2pad;  // [Mpad], +inf beyond M
-  const float* znorm2;  // [N]  ||z_n||^2 (fp32)
-  const float* emax;    // [1]  max_j ||e_j||
+  const float2* zmeta;  // [N]  (||z_n||^2, 1 / s_n): fp32 norm and the inverse of the row's power-of-two fp16 scale
+  const float* emax;    // [2]  max_j ||e_j||, 1 / t (inverse of the bank's power-of-two fp16 scale)
   int* cand;            // [N][ADDR_CAND]
   int* cand_cnt;        // [N][2]  entries used per half; > ADDR_CAPH means overflow -> exact re-scan
 };
@@ -128,7 +133,7 @@ addr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = ptx::umma_idesc(1, 128, BLOCK_N);
+      constexpr uint32_t idesc = ptx::umma_idesc(0, 128, BLOCK_N);      // fp16 operands
       int s = 0; uint32_t ph = 0;
       int it = 0;
       for (int tq = blockIdx.x; tq < p.tiles_q; tq += gridDim.x) {
@@ -164,14 +169,17 @@ addr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     constexpr int CHUNKS = HALF_N / 32;
     float* lv = list_val + (size_t)((warp - 2) * 32 + lane) * ADDR_CAPH;
     uint16_t* li = list_idx + (size_t)((warp - 2) * 32 + lane) * ADDR_CAPH;
-    const float emax = __ldg(p.emax);
+    const float emax = __ldg(p.emax), tinv = __ldg(p.emax + 1);
     int it = 0;
     for (int tq = blockIdx.x; tq < p.tiles_q; tq += gridDim.x) {
       const int n = tq * 128 + q * 32 + lane;
-      const float zn2 = n < p.N ? __ldg(p.znorm2 + n) : 0.f;
-      // |a~ - a| <= 2 eps with eps = 2^-8 * 1.02 * ||z|| * max||e||; candidates within 4 eps (+ fp32 slack) of the
-      // KSEL-th smallest approximate score are a superset of the exact top-KSEL (see file header).
-      const float margin = 4.f * 0.00390625f * 1.02f * sqrtf(zn2) * emax + 1e-5f * (zn2 + emax * emax) + 1e-30f;
+      const float2 zm = n < p.N ? __ldg(p.zmeta + n) : make_float2(0.f, 0.f);
+      const float zn2 = zm.x;
+      const float cs = -2.f * zm.y * tinv;           // a~ = ||e||^2 + cs * (z~.e~): undoes the two power-of-two scales
+      // |a~ - a| <= 4u(1+u) ||z|| ||e||, u = 2^-11 (fp16 rounding of both operands, Cauchy-Schwarz); candidates within
+      // twice that (+ fp32 accumulation slack) of the KSEL-th smallest approximate score are a superset of the exact
+      // top-KSEL (see file header).
+      const float margin = 8.f * 0.00048828125f * 1.01f * sqrtf(zn2) * emax + 1e-5f * (zn2 + emax * emax) + 1e-30f;
       float m[KSEL];
 #pragma unroll
       for (int i = 0; i < KSEL; ++i) m[i] = INFINITY;
@@ -199,10 +207,10 @@ addr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 e = __ldg(e4 + j);
-            sel_insert<KSEL>(ma[0], fmaf(-2.f, __uint_as_float(v[4 * j + 0]), e.x));
-            sel_insert<KSEL>(ma[1], fmaf(-2.f, __uint_as_float(v[4 * j + 1]), e.y));
-            sel_insert<KSEL>(ma[2], fmaf(-2.f, __uint_as_float(v[4 * j + 2]), e.z));
-            sel_insert<KSEL>(ma[3], fmaf(-2.f, __uint_as_float(v[4 * j + 3]), e.w));
+            sel_insert<KSEL>(ma[0], fmaf(cs, __uint_as_float(v[4 * j + 0]), e.x));
+            sel_insert<KSEL>(ma[1], fmaf(cs, __uint_as_float(v[4 * j + 1]), e.y));
+            sel_insert<KSEL>(ma[2], fmaf(cs, __uint_as_float(v[4 * j + 2]), e.z));
+            sel_insert<KSEL>(ma[3], fmaf(cs, __uint_as_float(v[4 * j + 3]), e.w));
           }
 #pragma unroll
           for (int g = 0; g < 4; ++g)
@@ -221,16 +229,16 @@ addr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 e = __ldg(e4 + j);
-            hits |= (fmaf(-2.f, __uint_as_float(v[4 * j + 0]), e.x) <= thr ? 1u : 0u) << (4 * j + 0);
-            hits |= (fmaf(-2.f, __uint_as_float(v[4 * j + 1]), e.y) <= thr ? 1u : 0u) << (4 * j + 1);
-            hits |= (fmaf(-2.f, __uint_as_float(v[4 * j + 2]), e.z) <= thr ? 1u : 0u) << (4 * j + 2);
-            hits |= (fmaf(-2.f, __uint_as_float(v[4 * j + 3]), e.w) <= thr ? 1u : 0u) << (4 * j + 3);
+            hits |= (fmaf(cs, __uint_as_float(v[4 * j + 0]), e.x) <= thr ? 1u : 0u) << (4 * j + 0);
+            hits |= (fmaf(cs, __uint_as_float(v[4 * j + 1]), e.y) <= thr ? 1u : 0u) << (4 * j + 1);
+            hits |= (fmaf(cs, __uint_as_float(v[4 * j + 2]), e.z) <= thr ? 1u : 0u) << (4 * j + 2);
+            hits |= (fmaf(cs, __uint_as_float(v[4 * j + 3]), e.w) <= thr ? 1u : 0u) << (4 * j + 3);
           }
           while (hits) {
             const int j = __ffs(hits) - 1;
             hits &= hits - 1;
             const int col = col0 + c * 32 + j;
-            const float av = fmaf(-2.f, __uint_as_float(select32(v, j)), __ldg(p.en2pad + col));
+            const float av = fmaf(cs, __uint_as_float(select32(v, j)), __ldg(p.en2pad + col));
             if (cnt == ADDR_CAPH) {            // full: drop entries that the tightened threshold no longer admits
               int w = 0;
               for (int i = 0; i < ADDR_CAPH; ++i) {
@@ -270,34 +278,52 @@ addr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // ------------------------------------------------------------------------------------------------
 // operand prep
 // ------------------------------------------------------------------------------------------------
-// z [N][D] fp32 -> zp bf16 (round to nearest) and ||z_n||^2; one warp per query row
-__global__ void __launch_bounds__(256) pack_rows_bf16_kernel(const float* __restrict__ z, __nv_bfloat16* __restrict__ zp,
-                                                              float* __restrict__ znorm2, long long N, int D) {
+// z [N][D] fp32 -> zp fp16 of the row scaled by a power of two s_n (max component -> [2^14, 2^15)) and
+// zmeta[n] = (||z_n||^2, 1 / s_n); one warp per query row
+__global__ void __launch_bounds__(256) pack_rows_f16_kernel(const float* __restrict__ z, __half* __restrict__ zp,
+                                                             float2* __restrict__ zmeta, long long N, int D) {
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= N) return;
   const float* zr = z + row * D;
-  __nv_bfloat16* zo = zp + row * D;
-  float s = 0.f;
+  __half* zo = zp + row * D;
+  float s = 0.f, mx = 0.f;
   for (int d = lane * 2; d < D; d += 64) {      // D is a multiple of 64
     const float2 v = __ldg(reinterpret_cast<const float2*>(zr + d));
     s = fmaf(v.x, v.x, fmaf(v.y, v.y, s));
-    *reinterpret_cast<__nv_bfloat162*>(zo + d) = __floats2bfloat162_rn(v.x, v.y);
+    mx = fmaxf(mx, fmaxf(fabsf(v.x), fabsf(v.y)));
   }
   s = warp_sum(s);
-  if (lane == 0) znorm2[row] = s;
+  const float sc = q_scale_for_bound(warp_max(mx));
+  for (int d = lane * 2; d < D; d += 64) {
+    const float2 v = __ldg(reinterpret_cast<const float2*>(zr + d));
+    *reinterpret_cast<uint32_t*>(zo + d) = ptx::pack_f16x2(v.x * sc, v.y * sc);
+  }
+  if (lane == 0) zmeta[row] = make_float2(s, 1.f / sc);
 }
 
-// bank_t [M][D] fp32 -> bank_hi [Mpad][D] bf16 (zero rows beyond M); en2pad [Mpad] (+inf beyond M); emax = max ||e||
+// max |bank| as the bits of a non-negative float (atomicMax); *out zeroed by the host
+__global__ void __launch_bounds__(256) bank_absmax_kernel(const float* __restrict__ bank_t, long long n, unsigned* __restrict__ out) {
+  float m = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(bank_t[i]));
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));
+}
+
+// bank_t [M][D] fp32 -> bank_hi [Mpad][D] fp16 of the bank scaled by one power of two t (zero rows beyond M);
+// en2pad [Mpad] (+inf beyond M); emax[0] = max ||e||, emax[1] = 1 / t.  amax_bits = max |bank| from bank_absmax_kernel.
 __global__ void bank_pack_kernel(const float* __restrict__ bank_t, const float* __restrict__ en2,
-                                 __nv_bfloat16* __restrict__ bank_hi, float* __restrict__ en2pad,
-                                 float* __restrict__ emax, int D, int M, int Mpad) {
+                                 __half* __restrict__ bank_hi, float* __restrict__ en2pad,
+                                 float* __restrict__ emax, const unsigned* __restrict__ amax_bits, int D, int M, int Mpad) {
   const int m = blockIdx.x;
+  const float t = q_scale_for_bound(__uint_as_float(amax_bits[0]));
   for (int d = threadIdx.x; d < D; d += blockDim.x)
-    bank_hi[(size_t)m * D + d] = m < M ? __float2bfloat16_rn(bank_t[(size_t)m * D + d]) : __float2bfloat16_rn(0.f);
+    bank_hi[(size_t)m * D + d] = __float2half_rn(m < M ? bank_t[(size_t)m * D + d] * t : 0.f);
   if (threadIdx.x == 0) {
     en2pad[m] = m < M ? en2[m] : INFINITY;
     if (m < M) atomicMax(reinterpret_cast<int*>(emax), __float_as_int(sqrtf(en2[m])));  // non-negative floats order as ints
+    if (m == 0) emax[1] = 1.f / t;
   }
 }
 
@@ -407,14 +433,17 @@ __global__ void __launch_bounds__(256) rescan_kernel(
 int make_map_2d_bf16(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, uint32_t box_inner,
                      uint32_t box_outer);   // amft_conv.cu
 
+int pack_bank_padded(const float* bank_t, const float* en2, void* bank_hi, float* en2pad, float* emax4, int D, int M, int Mpad,
+                     cudaStream_t st);
+
 int addr_block_n(int M) { return M >= 192 ? 256 : (M >= 96 ? 128 : 64); }
 
 size_t addr_tc_ws_bytes(int64_t N, int D, int M) {
   const int bn = addr_block_n(M);
   const int Mpad = (int)align_up(M, bn);
   return align_up((size_t)N * D * 2, 256) + align_up((size_t)Mpad * D * 2, 256) + align_up((size_t)Mpad * 4, 256) +
-         align_up((size_t)N * ADDR_CAND * 4, 256) + align_up((size_t)N * 2 * 4, 256) + 2 * align_up((size_t)N * 4, 256) +
-         256;
+         align_up((size_t)N * ADDR_CAND * 4, 256) + align_up((size_t)N * 2 * 4, 256) + align_up((size_t)N * 8, 256) +
+         align_up((size_t)N * 4, 256) + 512;
 }
 
 bool addr_tc_supported(int64_t N, int D, int M, int k) {
@@ -453,38 +482,36 @@ static int launch_filter(const void* zp, const void* bank_hi, AddrParams& p, int
 
 // z fp32 [N][D] (+ optional pre-packed bf16 copy zp), bank_t fp32 [M][D], en2 [M]  ->  outputs as address_kernel.
 // `ws` must provide addr_tc_ws_bytes(); stats[0] += rows that needed the exact fallback.
-int run_address_tc(const float* z, const __nv_bfloat16* zp_in, const float* znorm2_in, __nv_bfloat16* read_planes,
+int run_address_tc(const float* z, const void* zp_in, const float* zmeta_in, __nv_bfloat16* read_planes,
                    const float* bank_t, const float* en2, float* read, float* q1, int64_t* idx, float* sse_px,
                    float* counts, float* embed_sum, int* stats, Workspace& ws, int64_t N, int D, int M, int k,
                    cudaStream_t st) {
   const long long rps = (long long)N * k * D;
   const int bn = addr_block_n(M);
   const int Mpad = (int)align_up(M, bn);
-  __nv_bfloat16* zp = ws.take<__nv_bfloat16>((size_t)N * D);
-  __nv_bfloat16* bank_hi = ws.take<__nv_bfloat16>((size_t)Mpad * D);
+  __half* zp = ws.take<__half>((size_t)N * D);
+  __half* bank_hi = ws.take<__half>((size_t)Mpad * D);
   float* en2pad = ws.take<float>(Mpad);
   int* cand = ws.take<int>((size_t)N * ADDR_CAND);
   int* cand_cnt = ws.take<int>((size_t)N * 2);
-  float* znorm2 = ws.take<float>(N);
+  float2* zmeta = ws.take<float2>(N);
   int* rescan_list = ws.take<int>(N);
-  float* emax = ws.take<float>(1);
+  float* emax = ws.take<float>(4);
   if (!ws.ok()) return fail(AMMC_EWORKSPACE, "workspace too small");
-  if (zp_in && znorm2_in) {                  // the tensor-core enc epilogue already produced bf16(z) and ||z||^2
-    zp = const_cast<__nv_bfloat16*>(zp_in);
-    znorm2 = const_cast<float*>(znorm2_in);
+  if (zp_in && zmeta_in) {                  // the tensor-core enc epilogue already produced the scaled fp16 rows and norms
+    zp = reinterpret_cast<__half*>(const_cast<void*>(zp_in));
+    zmeta = reinterpret_cast<float2*>(const_cast<float*>(zmeta_in));
   } else {
-    pack_rows_bf16_kernel<<<ceil_div(N, 8), 256, 0, st>>>(z, zp, znorm2, N, D);
-    AMMC_LAUNCH_CHECK("pack_rows_bf16_kernel");
+    pack_rows_f16_kernel<<<ceil_div(N, 8), 256, 0, st>>>(z, zp, zmeta, N, D);
+    AMMC_LAUNCH_CHECK("pack_rows_f16_kernel");
   }
-  AMMC_CUDA_CHECK(cudaMemsetAsync(emax, 0, 4, st));
-  bank_pack_kernel<<<Mpad, 128, 0, st>>>(bank_t, en2, bank_hi, en2pad, emax, D, M, Mpad);
-  AMMC_LAUNCH_CHECK("bank_pack_kernel");
+  if (int rc = pack_bank_padded(bank_t, en2, bank_hi, en2pad, emax, D, M, Mpad, st)) return rc;
 
   AddrParams p;
   p.N = (int)N; p.D = D; p.M = M; p.Mpad = Mpad;
   p.tiles_q = ceil_div(N, 128);
   p.tiles_i = Mpad / bn;
-  p.en2pad = en2pad; p.znorm2 = znorm2; p.emax = emax; p.cand = cand; p.cand_cnt = cand_cnt;
+  p.en2pad = en2pad; p.zmeta = zmeta; p.emax = emax; p.cand = cand; p.cand_cnt = cand_cnt;
   if (int rc = launch_filter(zp, bank_hi, p, bn, k, st)) return rc;
   const int blocks = ceil_div(N, 64);
   switch (k) {
@@ -521,11 +548,14 @@ int run_rescan(const float* z, const float* bank_t, const float* en2, float* q1,
   return 0;
 }
 
-// bank_t [M][D], en2 [M] -> bank_hi [Mpad][D] bf16, en2pad [Mpad], emax (max ||e||) for a caller-chosen padding
-int pack_bank_padded(const float* bank_t, const float* en2, void* bank_hi, float* en2pad, float* emax, int D, int M, int Mpad,
+// bank_t [M][D], en2 [M] -> bank_hi [Mpad][D] fp16 (power-of-two scaled), en2pad [Mpad], emax4 = {max ||e||, 1 / t, scratch}
+int pack_bank_padded(const float* bank_t, const float* en2, void* bank_hi, float* en2pad, float* emax4, int D, int M, int Mpad,
                      cudaStream_t st) {
-  AMMC_CUDA_CHECK(cudaMemsetAsync(emax, 0, 4, st));
-  bank_pack_kernel<<<Mpad, 128, 0, st>>>(bank_t, en2, (__nv_bfloat16*)bank_hi, en2pad, emax, D, M, Mpad);
+  AMMC_CUDA_CHECK(cudaMemsetAsync(emax4, 0, 16, st));
+  unsigned* amax = reinterpret_cast<unsigned*>(emax4 + 2);
+  bank_absmax_kernel<<<min(ceil_div((long long)M * D, 256), 592), 256, 0, st>>>(bank_t, (long long)M * D, amax);
+  AMMC_LAUNCH_CHECK("bank_absmax_kernel");
+  bank_pack_kernel<<<Mpad, 128, 0, st>>>(bank_t, en2, (__half*)bank_hi, en2pad, emax4, amax, D, M, Mpad);
   AMMC_LAUNCH_CHECK("bank_pack_kernel");
   return 0;
 }
@@ -543,10 +573,10 @@ using namespace ammc;
 // ---- staged entry points (what ammc_quantize_fwd / ammc_mem_fwd compose internally; used by the cfg5 microbench) ----
 extern "C" int ammc_addr_padded_items(int M) { return (int)align_up(M, addr_block_n(M)); }
 
-extern "C" int ammc_addr_pack_queries(const float* z, void* zp, float* znorm2, int64_t N, int D, void* stream) {
-  AMMC_REQUIRE(z && zp && znorm2 && N > 0 && D > 0 && D % 64 == 0, "bad argument (D must be a multiple of 64)");
-  pack_rows_bf16_kernel<<<ceil_div(N, 8), 256, 0, (cudaStream_t)stream>>>(z, (__nv_bfloat16*)zp, znorm2, N, D);
-  AMMC_LAUNCH_CHECK("pack_rows_bf16_kernel");
+extern "C" int ammc_addr_pack_queries(const float* z, void* zp, float* zmeta, int64_t N, int D, void* stream) {
+  AMMC_REQUIRE(z && zp && zmeta && N > 0 && D > 0 && D % 64 == 0, "bad argument (D must be a multiple of 64)");
+  pack_rows_f16_kernel<<<ceil_div(N, 8), 256, 0, (cudaStream_t)stream>>>(z, (__half*)zp, (float2*)zmeta, N, D);
+  AMMC_LAUNCH_CHECK("pack_rows_f16_kernel");
   return 0;
 }
 
@@ -559,16 +589,13 @@ extern "C" int ammc_addr_pack_bank(const float* embed, float* bank_t, float* en2
   AMMC_LAUNCH_CHECK("bank_transpose_kernel");
   bank_norms_kernel<<<ceil_div(M, 128), 128, 0, st>>>(embed, en2, D, M);
   AMMC_LAUNCH_CHECK("bank_norms_kernel");
-  AMMC_CUDA_CHECK(cudaMemsetAsync(emax, 0, 4, st));
-  bank_pack_kernel<<<Mpad, 128, 0, st>>>(bank_t, en2, (__nv_bfloat16*)bank_hi, en2pad, emax, D, M, Mpad);
-  AMMC_LAUNCH_CHECK("bank_pack_kernel");
-  return 0;
+  return pack_bank_padded(bank_t, en2, bank_hi, en2pad, emax, D, M, Mpad, st);
 }
 
-extern "C" int ammc_addr_filter(const void* zp, const float* znorm2, const void* bank_hi, const float* en2pad,
+extern "C" int ammc_addr_filter(const void* zp, const float* zmeta, const void* bank_hi, const float* en2pad,
                                 const float* emax, int* cand, int* cand_cnt, int64_t N, int D, int M, int k,
                                 void* stream) {
-  AMMC_REQUIRE(zp && znorm2 && bank_hi && en2pad && emax && cand && cand_cnt, "null pointer argument");
+  AMMC_REQUIRE(zp && zmeta && bank_hi && en2pad && emax && cand && cand_cnt, "null pointer argument");
   if (!addr_tc_supported(N, D, M, k))
     return fail(AMMC_EUNSUPPORTED, "tensor-core addressing needs D %% 64 == 0, 16 <= M <= 65536, k <= 4 (got D=%d M=%d k=%d)", D, M, k);
   AMMC_REQUIRE(N < (1LL << 31), "N too large");
@@ -577,6 +604,6 @@ extern "C" int ammc_addr_filter(const void* zp, const float* znorm2, const void*
   p.N = (int)N; p.D = D; p.M = M; p.Mpad = ammc_addr_padded_items(M);
   p.tiles_q = ceil_div(N, 128);
   p.tiles_i = p.Mpad / bn;
-  p.en2pad = en2pad; p.znorm2 = znorm2; p.emax = emax; p.cand = cand; p.cand_cnt = cand_cnt;
+  p.en2pad = en2pad; p.zmeta = reinterpret_cast<const float2*>(zmeta); p.emax = emax; p.cand = cand; p.cand_cnt = cand_cnt;
   return launch_filter(zp, bank_hi, p, bn, k, (cudaStream_t)stream);
 }

@@ -11,7 +11,7 @@
 //               of the canonical K-major 128B-swizzled UMMA tile (16-byte chunk index XOR (row & 7)), then
 //               fence.proxy.async + mbarrier arrive
 //   warp 1      MMA: per stage  hi*W_hi + hi*W_lo + lo*W_hi  (M128 x N64 x K16, fp32 accumulate in TMEM)
-//   warps 10-13 epilogue: + bias -> z fp32 [N, D], its bf16 rounding zp (the addressing filter's operand) and ||z||^2
+//   warps 10-13 epilogue: + bias -> z fp32 [N, D], its row-scaled fp16 rounding zp (the addressing filter's operand), ||z||^2
 // Error of the split-bf16 x3 product: ~2^-17 relative (measured on the conv kernel), i.e. z agrees with the fp32 FFMA
 // kernel to ~1e-5; the exact fp32 refine stage then ranks the candidates with that z.
 #include "common.cuh"
@@ -39,8 +39,8 @@ struct EncParams {
   int N, HW, C, tiles;
   const float* bias;
   float* z;                 // [N][64]
-  __nv_bfloat16* zp;        // [N][64] or null
-  float* znorm2;            // [N] or null
+  __nv_bfloat16* zp;        // [N][64] fp16 bits of z * s_n (s_n: per-row power of two), or null
+  float* znorm2;            // [N][2] (||z_n||^2, 1 / s_n), or null
   unsigned* amax_bits;      // AMAX: max |x| over the whole input as the bits of a non-negative float (atomicMax; zeroed by the host)
 };
 
@@ -199,6 +199,19 @@ enc_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
       ptx::mbar_wait(&tmem_full[acc], acc_ph, 56);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * ENC_D;
+      // pass 1: the row's largest component fixes its power-of-two fp16 scale (addressing filter operand, addr_tc.cu)
+      float zmax = 0.f;
+      if (p.zp) {
+#pragma unroll
+        for (int c32 = 0; c32 < ENC_D / 32; ++c32) {
+          uint32_t v[32];
+          ptx::tmem_ld_32x32(taddr + c32 * 32, v);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) zmax = fmaxf(zmax, fabsf(__uint_as_float(v[j]) + __ldg(p.bias + c32 * 32 + j)));
+        }
+      }
+      const float zsc = q_scale_for_bound(zmax);
       float zn2 = 0.f;
 #pragma unroll
       for (int c32 = 0; c32 < ENC_D / 32; ++c32) {
@@ -219,7 +232,8 @@ enc_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
           }
           ptx::stg_v8(zr + 8 * g, o);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) zb[4 * g + j] = ptx::pack_bf16x2(__uint_as_float(o[2 * j]), __uint_as_float(o[2 * j + 1]));
+          for (int j = 0; j < 4; ++j)
+            zb[4 * g + j] = ptx::pack_f16x2(__uint_as_float(o[2 * j]) * zsc, __uint_as_float(o[2 * j + 1]) * zsc);
         }
         if (p.zp) {
           __nv_bfloat16* zpr = p.zp + n * ENC_D + c32 * 32;
@@ -228,7 +242,7 @@ enc_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
           ptx::stg_v8(zpr + 16, z8[1]);
         }
       }
-      if (p.znorm2) p.znorm2[n] = zn2;
+      if (p.znorm2) reinterpret_cast<float2*>(p.znorm2)[n] = make_float2(zn2, 1.f / zsc);
       ptx::tc_fence_before();
       ptx::mbar_arrive(&tmem_empty[acc]);
     }

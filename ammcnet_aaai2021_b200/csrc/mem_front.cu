@@ -12,10 +12,10 @@
 //   warps 2-9     converters: staged fp32 -> bf16 hi/lo rows of the K-major 128B-swizzled UMMA A tiles (as enc_tc.cu);
 //                 max|x| for the q-plane scale falls out of the same pass
 //   warp 1        MMA: enc (hi.Whi + hi.Wlo + lo.Whi, M128 x N64 x K16) into one of two 64-column accumulators, and for
-//                 the PREVIOUS tile the similarity  S = bf16(z) . bank^T  (M128 x N256 x K16 x 4) into a 256-column
+//                 the PREVIOUS tile the similarity  S = fp16(z s_n) . fp16(bank t)^T  (M128 x N256 x K16 x 4) into a 256-column
 //                 accumulator -- issued two K blocks into the next tile so the tensor core never waits for the epilogue
 //   warps 10-13   epilogue, thread = pixel.  P1: z = acc + bias -> HBM (fp32, for backward / the rare exact re-scan),
-//                 bf16(z) -> the swizzled A tile of the similarity MMA, ||z||^2 with the summation tree of the fp32 kernel.
+//                 row-scaled fp16(z) -> the swizzled A tile of the similarity MMA, ||z||^2 with the summation tree of the fp32 kernel.
 //                 P2: approximate scores from TMEM, k smallest + every column within a rigorous bf16 error margin
 //                 (the filter of addr_tc.cu), then the EXACT fp32 distance of those few candidates with z re-read from
 //                 its TMEM accumulator -- same fmaf chain as the generic kernel, so the indices are bit-identical --
@@ -60,7 +60,7 @@ struct FrontParams {
   const float* bank_t;      // [M][64] fp32
   const float* en2;         // [M]
   const float* en2pad;      // [256], +inf beyond M
-  const float* emax;        // [1] max ||e||
+  const float* emax;        // [2] max ||e||, 1 / t (inverse power-of-two fp16 scale of the bank)
   float* z;                 // [N][64]
   float* q1;                // [N][64]
   int64_t* idx;             // [N][K]
@@ -163,7 +163,7 @@ mem_front_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (warp converged, one lane issues)
     constexpr uint32_t idesc_enc = ptx::umma_idesc(1, 128, MF_D);
-    constexpr uint32_t idesc_sim = ptx::umma_idesc(1, 128, MF_MPAD);
+    constexpr uint32_t idesc_sim = ptx::umma_idesc(0, 128, MF_MPAD);      // fp16 operands
     const uint32_t s_tmem = tmem_base + 256;
     const uint64_t zp_desc = ptx::umma_desc_k_sw128(ptx::smem_u32(smem + MF_ZP_OFFSET));
     const uint64_t bank_desc = ptx::umma_desc_k_sw128(ptx::smem_u32(smem + MF_BANK_OFFSET));
@@ -256,7 +256,7 @@ mem_front_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     uint16_t* list = reinterpret_cast<uint16_t*>(smem + MF_LIST_OFFSET) + r * MF_CAP;
     const uint32_t zp_row = ptx::smem_u32(smem + MF_ZP_OFFSET) + r * 128;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-    const float emax = __ldg(p.emax);
+    const float emax = __ldg(p.emax), tinv = __ldg(p.emax + 1);
     int it = 0;
     for (int t = blockIdx.x; t < p.tiles; t += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -266,6 +266,16 @@ mem_front_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       // ---- P1: z, bf16(z), ||z||^2
       ptx::mbar_wait(&tmem_full[acc], acc_ph, 70);
       ptx::tc_fence_after();
+      float zmax = 0.f;                            // pass 1: the row's power-of-two fp16 scale (filter operand)
+#pragma unroll
+      for (int c32 = 0; c32 < 2; ++c32) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32(z_tmem + c32 * 32, v);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) zmax = fmaxf(zmax, fabsf(__uint_as_float(v[j]) + bias_s[c32 * 32 + j]));
+      }
+      const float zsc = q_scale_for_bound(zmax);
       float zs[4] = {0.f, 0.f, 0.f, 0.f};          // partial sums over d = part (mod 4): the tree of team_zn2
 #pragma unroll
       for (int c32 = 0; c32 < 2; ++c32) {
@@ -285,10 +295,10 @@ mem_front_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           ptx::stg_v8(zr + 8 * g, o);
           const int c8 = c32 * 4 + g;
           ptx::sts_v4(zp_row + (uint32_t)((c8 ^ (r & 7)) * 16),
-                      ptx::pack_bf16x2(__uint_as_float(o[0]), __uint_as_float(o[1])),
-                      ptx::pack_bf16x2(__uint_as_float(o[2]), __uint_as_float(o[3])),
-                      ptx::pack_bf16x2(__uint_as_float(o[4]), __uint_as_float(o[5])),
-                      ptx::pack_bf16x2(__uint_as_float(o[6]), __uint_as_float(o[7])));
+                      ptx::pack_f16x2(__uint_as_float(o[0]) * zsc, __uint_as_float(o[1]) * zsc),
+                      ptx::pack_f16x2(__uint_as_float(o[2]) * zsc, __uint_as_float(o[3]) * zsc),
+                      ptx::pack_f16x2(__uint_as_float(o[4]) * zsc, __uint_as_float(o[5]) * zsc),
+                      ptx::pack_f16x2(__uint_as_float(o[6]) * zsc, __uint_as_float(o[7]) * zsc));
         }
       }
       const float zn2 = (zs[0] + zs[1]) + (zs[2] + zs[3]);
@@ -298,9 +308,10 @@ mem_front_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       ptx::mbar_wait(s_full, (uint32_t)(it & 1), 71);
       ptx::tc_fence_after();
       const uint32_t s_tmem = lane_base + 256;
-      // |a~ - a| <= 4u(1+u) ||z|| ||e||, u = 2^-8 (bf16 rounding of both operands, Cauchy-Schwarz); everything within
-      // twice that of the KSEL-th smallest approximate score is a superset of the exact top-KSEL
-      const float margin = 8.f * 0.00390625f * 1.01f * sqrtf(zn2) * emax + 1e-5f * (zn2 + emax * emax) + 1e-30f;
+      // |a~ - a| <= 4u(1+u) ||z|| ||e||, u = 2^-11 (fp16 rounding of both scaled operands, Cauchy-Schwarz); everything
+      // within twice that of the KSEL-th smallest approximate score is a superset of the exact top-KSEL (addr_tc.cu)
+      const float margin = 8.f * 0.00048828125f * 1.01f * sqrtf(zn2) * emax + 1e-5f * (zn2 + emax * emax) + 1e-30f;
+      const float cs = -2.f * tinv / zsc;          // a~ = ||e||^2 + cs * (z~.e~): undoes the two power-of-two scales
       float m[KSEL];
 #pragma unroll
       for (int i = 0; i < KSEL; ++i) m[i] = INFINITY;
@@ -316,7 +327,7 @@ mem_front_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           for (int i = 0; i < KSEL; ++i) ma[g][i] = INFINITY;
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-          mf_sel_insert<KSEL>(ma[j & 3], fmaf(-2.f, __uint_as_float(v[j]), en2pad_s[c * 32 + j]));
+          mf_sel_insert<KSEL>(ma[j & 3], fmaf(cs, __uint_as_float(v[j]), en2pad_s[c * 32 + j]));
 #pragma unroll
         for (int g = 0; g < 4; ++g)
 #pragma unroll
@@ -332,7 +343,7 @@ mem_front_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         uint32_t hits = 0;
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-          hits |= (fmaf(-2.f, __uint_as_float(v[j]), en2pad_s[c * 32 + j]) <= thr ? 1u : 0u) << j;
+          hits |= (fmaf(cs, __uint_as_float(v[j]), en2pad_s[c * 32 + j]) <= thr ? 1u : 0u) << j;
         while (hits) {
           const int j = __ffs(hits) - 1;
           hits &= hits - 1;

@@ -723,7 +723,7 @@ struct MemWs {
 // addr_tc.cu
 size_t addr_tc_ws_bytes(int64_t N, int D, int M);
 bool addr_tc_supported(int64_t N, int D, int M, int k);
-int run_address_tc(const float* z, const __nv_bfloat16* zp_in, const float* znorm2_in, __nv_bfloat16* read_planes,
+int run_address_tc(const float* z, const void* zp_in, const float* zmeta_in, __nv_bfloat16* read_planes,
                    const float* bank_t, const float* en2, float* read, float* q1, int64_t* idx, float* sse_px,
                    float* counts, float* embed_sum, int* stats, Workspace& ws, int64_t N, int D, int M, int k,
                    cudaStream_t st);
@@ -795,9 +795,9 @@ struct MemPrep {
   __nv_bfloat16* dec_wp;     // [2][C][kD]  bf16 hi/lo planes of dec.weight
   float* bank_t;             // [M][D]      items as rows
   float* en2;                // [M]         ||e||^2
-  __nv_bfloat16* bank_hi;    // [256][D]    bf16 items, zero rows beyond M (fused front kernel)
+  __nv_bfloat16* bank_hi;    // [256][D]    fp16 bits of the scaled items, zero rows beyond M (fused front kernel)
   float* en2pad;             // [256]       ||e||^2, +inf beyond M
-  float* emax;               // [1]         max ||e||
+  float* emax;               // [4]         max ||e||, 1 / t (inverse power-of-two fp16 scale of the bank), scratch
   float* ones;               // [C]
   unsigned* dec_bound;       // [1]         bits of max_c (sum_j ||dec_w[c,j]|| max||e|| + |dec_b[c]|): q-plane scale bound
 };
@@ -813,7 +813,7 @@ static int carve_prep(Workspace& ws, MemPrep& pr, int C, int D, int M, int k) {
   pr.en2 = ws.take<float>(M);
   pr.bank_hi = ws.take<__nv_bfloat16>((size_t)256 * D);
   pr.en2pad = ws.take<float>(256);
-  pr.emax = ws.take<float>(1);
+  pr.emax = ws.take<float>(4);          // max ||e||, 1 / fp16 scale of the bank, scratch
   pr.ones = ws.take<float>(C);
   pr.dec_bound = ws.take<unsigned>(1);
   if (!ws.ok()) return fail(AMMC_EWORKSPACE, "prepared-parameter buffer too small");
@@ -850,7 +850,7 @@ static size_t mem_ws_bytes(int64_t N, int C, int D, int M, int k, bool with_tabl
     s += align_up((size_t)k * M * C * 4, 256);                       // dec tables (fp32 gather path)
     s += align_up((size_t)N * k * D * 2 * 2, 256);                    // read planes (tensor-core dec)
     s += align_up((size_t)C * k * D * 2 * 2, 256) + align_up((size_t)C * 4, 256);
-    s += enc_tc_ws_bytes(C) + align_up((size_t)N * D * 2, 256) + align_up((size_t)N * 4, 256);   // tensor-core enc
+    s += enc_tc_ws_bytes(C) + align_up((size_t)N * D * 2, 256) + align_up((size_t)N * 8, 256);   // tensor-core enc
   }
   s += align_up((size_t)N * 4, 256);
   return s;
@@ -1051,7 +1051,7 @@ extern "C" int ammc_mem_fwd(const float* x, const float* enc_w, const float* enc
   } else {
     if (tc_enc) {
       __nv_bfloat16* zp = ws.take<__nv_bfloat16>((size_t)N * D);
-      float* zn2 = ws.take<float>(N);
+      float* zn2 = ws.take<float>(2 * N);                // (||z||^2, 1 / row scale) pairs
       if (!ws.ok()) return fail(AMMC_EWORKSPACE, "workspace too small");
       // the converters see every input value: max|x| (for the q planes' scale) comes out of the same pass
       if (int rc = run_enc_tc(x, enc_w, enc_b, z, zp, zn2, pr.enc_wp, true, (q_planes && residual) ? amax_bits : nullptr, b,

@@ -717,7 +717,7 @@ def addressing_leg(dev, peaks, peak_src):
         zp = torch.empty((N, Di), dtype=torch.bfloat16, device=dev)
         bank_t, en2 = torch.empty((Mi, Di), device=dev), torch.empty((Mi,), device=dev)
         bank_hi = torch.empty((Mpad, Di), dtype=torch.bfloat16, device=dev)
-        en2pad, emax, zn2 = torch.empty((Mpad,), device=dev), torch.empty((1,), device=dev), torch.empty((N,), device=dev)
+        en2pad, emax, zn2 = torch.empty((Mpad,), device=dev), torch.empty((4,), device=dev), torch.empty((N, 2), device=dev)
         cand = torch.empty((N, 24), dtype=torch.int32, device=dev)
         cnt = torch.empty((N, 2), dtype=torch.int32, device=dev)
         _capi.call("ammc_addr_pack_queries", P(z), P(zp), P(zn2), N, Di, st)

@@ -101,8 +101,9 @@ size_t ammc_mem_workspace_bytes(int b, int h, int w, int C, int D, int M, int k)
 
 /* Addressing path (process-wide): 0 = auto (tensor-core filter + exact fp32 refine when D % 64 == 0, 16 <= M <= 65536, k <= 4,
  * else the generic fp32 CUDA-core kernel), 1 = force the generic fp32 kernel, 2 = force the tensor-core path (calls
- * with unsupported shapes then fail).  Both paths return bit-identical indices: the bf16 tensor-core pass only
- * pre-selects candidates (every item within a rigorous error margin of the k-th best approximate score), which are
+ * with unsupported shapes then fail).  Both paths return bit-identical indices: the fp16 tensor-core pass (operands scaled
+ * by powers of two, per query row / per bank) only pre-selects candidates (every item within a rigorous error margin of the
+ * k-th best approximate score), which are
  * re-ranked with the exact fp32 arithmetic of the generic kernel; queries whose candidate list overflowed are
  * re-scanned exactly.  After ammc_mem_fwd / ammc_quantize_fwd the
  * first 8 bytes of the workspace hold two int32: [0] queries that needed the exact re-scan, [1] path used (1 or 2). */
@@ -118,17 +119,20 @@ int ammc_mem_fwd(const float* x, const float* enc_w, const float* enc_b, const f
 /* Staged form of the tensor-core addressing filter (composed internally by ammc_mem_fwd / ammc_quantize_fwd; exposed
  * for the addressing microbench of BASELINE configs[4]):
  *   ammc_addr_padded_items(M)   items after padding to the MMA N tile (Mpad)
- *   ammc_addr_pack_queries      z [N,D] fp32 -> zp [N,D] bf16, znorm2 [N] = ||z_n||^2
- *   ammc_addr_pack_bank         embed [D,M] -> bank_t [M,D] fp32, en2 [M], bank_hi [Mpad,D] bf16, en2pad [Mpad], emax [1]
- *   ammc_addr_filter            zp x bank_hi on tcgen05 -> cand [N,24] int32 (-1 = empty slot; a guaranteed superset
- *                               of the exact top-k unless a half overflowed), cand_cnt [N,2] (hits per column half;
- *                               > 12 = overflow -> the refine stage re-scans that query exactly) */
+ *   ammc_addr_pack_queries      z [N,D] fp32 -> zp [N,D] fp16 of the row scaled by a power of two s_n (max component in
+ *                               [2^14, 2^15): no overflow, no lost small rows), zmeta [N,2] = (||z_n||^2, 1 / s_n)
+ *   ammc_addr_pack_bank         embed [D,M] -> bank_t [M,D] fp32, en2 [M], bank_hi [Mpad,D] fp16 of the bank scaled by one power
+ *                               of two t, en2pad [Mpad], emax [4] = {max ||e||, 1 / t, scratch, -}
+ *   ammc_addr_filter            zp x bank_hi on tcgen05 (kind::f16, fp32 accumulate) -> cand [N,24] int32 (-1 = empty slot; a
+ *                               guaranteed superset of the exact top-k unless a half overflowed: every item whose approximate
+ *                               score lies within 8 * 2^-11 * ||z|| max||e|| of the k-th smallest), cand_cnt [N,2] (hits per
+ *                               column half; > 12 = overflow -> the refine stage re-scans that query exactly) */
 #define AMMC_ADDR_CAND 24
 int ammc_addr_padded_items(int M);
-int ammc_addr_pack_queries(const float* z, void* zp, float* znorm2, int64_t N, int D, void* stream);
+int ammc_addr_pack_queries(const float* z, void* zp, float* zmeta, int64_t N, int D, void* stream);
 int ammc_addr_pack_bank(const float* embed, float* bank_t, float* en2, void* bank_hi, float* en2pad, float* emax,
                         int D, int M, void* stream);
-int ammc_addr_filter(const void* zp, const float* znorm2, const void* bank_hi, const float* en2pad, const float* emax,
+int ammc_addr_filter(const void* zp, const float* zmeta, const void* bank_hi, const float* en2pad, const float* emax,
                      int* cand, int* cand_cnt, int64_t N, int D, int M, int k, void* stream);
 
 /* Quantize_topk.forward on its own (unet.py:282-313): z [N, D] contiguous (N = frames*rows_per_frame).

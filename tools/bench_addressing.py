@@ -53,10 +53,10 @@ def point(N, M, D, k=2, seed=0):
     en2 = torch.empty((M,), device=DEV)
     bank_hi = torch.empty((Mpad, D), dtype=torch.bfloat16, device=DEV)
     en2pad = torch.empty((Mpad,), device=DEV)
-    emax = torch.empty((1,), device=DEV)
+    emax = torch.empty((4,), device=DEV)
     cand = torch.empty((N, 24), dtype=torch.int32, device=DEV)
     cnt = torch.empty((N, 2), dtype=torch.int32, device=DEV)
-    zn2 = torch.empty((N,), device=DEV)
+    zn2 = torch.empty((N, 2), device=DEV)
     _capi.call("ammc_addr_pack_queries", P(z), P(zp), P(zn2), N, D, st)
     _capi.call("ammc_addr_pack_bank", P(embed), P(bank_t), P(en2), P(bank_hi), P(en2pad), P(emax), D, M, st)
     flops = 2.0 * N * M * D

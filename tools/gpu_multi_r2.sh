@@ -5,12 +5,12 @@ cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 N=$(nvidia-smi -L | wc -l)
 run() { python -m torch.distributed.run --nnodes=1 --nproc-per-node $1 --master-addr 127.0.0.1 --master-port $2 "${@:3}"; }
-timeout 600 python bench.py --steps 30 --warmup 5 --no-generator --no-extras 2>gpurun_out/r2_scale_n1.err | tail -1 > gpurun_out/r2_scale_n1.json
-for n in 2 4 8; do
-  [ $n -le $N ] && timeout 600 bash -c "$(declare -f run); run $n $((29510+n)) bench.py --gpus $n --steps 30 --warmup 5" 2>gpurun_out/r2_scale_n$n.err | tail -1 > gpurun_out/r2_scale_n$n.json
+timeout 600 python bench.py --steps 20 --warmup 5 --no-generator --no-extras 2>gpurun_out/r2_scale_n1.err | tail -1 > gpurun_out/r2_scale_n1.json
+for n in ${SCALE_NS:-2 4 8}; do
+  [ $n -le $N ] && timeout 600 bash -c "$(declare -f run); run $n $((29510+n)) bench.py --gpus $n --steps 20 --warmup 5" 2>gpurun_out/r2_scale_n$n.err | tail -1 > gpurun_out/r2_scale_n$n.json
 done
 for m in 512 1000 2000; do
-  timeout 600 bash -c "$(declare -f run); run $N $((29540+m%7)) bench.py --gpus $N --steps 30 --warmup 5 --items $m" 2>gpurun_out/r2_items_${m}_n$N.err | tail -1 > gpurun_out/r2_items_${m}_n$N.json
+  timeout 600 bash -c "$(declare -f run); run $N $((29540+m%7)) bench.py --gpus $N --steps 20 --warmup 5 --items $m" 2>gpurun_out/r2_items_${m}_n$N.err | tail -1 > gpurun_out/r2_items_${m}_n$N.json
 done
 timeout 300 python bench.py --steps 20 --warmup 5 --items 2000 --no-generator --no-extras 2>gpurun_out/r2_items_2000_n1.err | tail -1 > gpurun_out/r2_items_2000_n1.json
 timeout 600 python tools/train_step.py --steps 10 --warmup 3 --batch 8 2>&1 | tail -1 > gpurun_out/r2_train_n1.json
