@@ -36,8 +36,19 @@ __device__ __forceinline__ float exact_dot(const float* __restrict__ zr, const f
   if ((D & 3) == 0) {
     const float4* z4 = reinterpret_cast<const float4*>(zr);
     const float4* e4 = reinterpret_cast<const float4*>(er);
-#pragma unroll 4
-    for (int i = 0; i < (D >> 2); ++i) {
+    const int n4 = D >> 2;
+    int i = 0;
+    for (; i + 8 <= n4; i += 8) {       // 16 loads in flight per lane, the fmaf chain itself is unchanged (ascending d)
+      float4 a[8], b[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { a[j] = __ldg(z4 + i + j); b[j] = __ldg(e4 + i + j); }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        acc = fmaf(a[j].x, b[j].x, acc); acc = fmaf(a[j].y, b[j].y, acc);
+        acc = fmaf(a[j].z, b[j].z, acc); acc = fmaf(a[j].w, b[j].w, acc);
+      }
+    }
+    for (; i < n4; ++i) {
       const float4 a = __ldg(z4 + i), b = __ldg(e4 + i);
       acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
     }

@@ -47,7 +47,15 @@ __global__ void bank_norms_kernel(const float* __restrict__ embed, float* __rest
   int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= M) return;
   float acc = 0.f;
-  for (int d = 0; d < D; ++d) {
+  int d = 0;
+  for (; d + 8 <= D; d += 8) {          // eight loads in flight, same ascending fmaf chain (M threads only: latency-bound)
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = embed[(size_t)(d + j) * M + m];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc = fmaf(v[j], v[j], acc);
+  }
+  for (; d < D; ++d) {
     float v = embed[(size_t)d * M + m];
     acc = fmaf(v, v, acc);
   }
@@ -250,7 +258,17 @@ __global__ void sse_frame_kernel(const float* __restrict__ sse_px, float* __rest
   __shared__ float red[33];
   const float* p = sse_px + (size_t)blockIdx.x * rows;
   float s = 0.f;
-  for (int64_t i = threadIdx.x; i < rows; i += blockDim.x) s += p[i];
+  if ((rows & 3) == 0 && (((uintptr_t)p) & 15) == 0) {       // 16-byte loads, four in flight (one block per frame)
+    const float4* p4 = reinterpret_cast<const float4*>(p);
+    const int64_t n4 = rows >> 2;
+#pragma unroll 4
+    for (int64_t i = threadIdx.x; i < n4; i += blockDim.x) {
+      const float4 v = __ldg(p4 + i);
+      s += (v.x + v.y) + (v.z + v.w);
+    }
+  } else {
+    for (int64_t i = threadIdx.x; i < rows; i += blockDim.x) s += p[i];
+  }
   s = block_sum(s, red);
   if (threadIdx.x == 0) sse_frame[blockIdx.x] = s;
 }
