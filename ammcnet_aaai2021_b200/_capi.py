@@ -30,11 +30,7 @@ SIGNATURES = {
     "ammc_version": (I, []),
     "ammc_last_error": (c_char_p, []),
     "ammc_device_supported": (I, []),
-    "ammc_debug_timeout": (I, [P]),
-    "ammc_debug_mma_rate": (I, [P, I, I, I, P]),
-    "ammc_debug_fp8_probe": (I, [P, P, P, P, P, I, P]),
-    "ammc_debug_desc_probe": (I, [P, P, P, I, I, I, P]),
-    "ammc_debug_tma_probe": (I, [P, P, P, P, P, P, I, P]),
+    "ammc_pipeline_check": (I, [P]),
     "ammc_mem_workspace_bytes": (Z, [I] * 7),
     "ammc_set_addressing_mode": (I, [I]),
     "ammc_mem_fwd": (I, [P] * 6 + [P] * 6 + [P, P, P, I, P] + [P, Z] + [I] * 8 + [P]),

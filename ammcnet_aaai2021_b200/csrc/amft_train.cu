@@ -409,6 +409,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 int make_map_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
                   const uint32_t* box);   // amft_conv.cu
 
+#ifdef AMMC_DEBUG_PROBES
 // Debug: load ONE 5-D box into shared memory with TMA and dump the raw bytes (layout / fault investigations).
 __global__ void tma_probe_kernel(const __grid_constant__ CUtensorMap tm, int c0, int c1, int c2, int c3, int c4,
                                  uint32_t box_bytes, uint8_t* out, uint32_t out_bytes) {
@@ -428,6 +429,7 @@ __global__ void tma_probe_kernel(const __grid_constant__ CUtensorMap tm, int c0,
   __syncthreads();
   for (uint32_t i = threadIdx.x; i < out_bytes; i += blockDim.x) out[i] = smem[i];
 }
+#endif  // AMMC_DEBUG_PROBES
 
 }  // namespace ammc
 
@@ -435,6 +437,7 @@ namespace ammc { AMMC_DEFINE_TIMEOUT_READER(timeout_reader_train) }
 
 using namespace ammc;
 
+#ifdef AMMC_DEBUG_PROBES
 extern "C" int ammc_debug_tma_probe(const void* base, const int64_t* dims5, const int64_t* strides4_bytes,
                                     const int* box5, const int* coords5, void* out, int out_bytes, void* stream) {
   uint64_t d[5], s[4];
@@ -452,6 +455,7 @@ extern "C" int ammc_debug_tma_probe(const void* base, const int64_t* dims5, cons
   AMMC_LAUNCH_CHECK("tma_probe_kernel");
   return 0;
 }
+#endif  // AMMC_DEBUG_PROBES
 
 extern "C" int ammc_bn_batch_stats_staged(const float* y, const float* gamma, const float* beta, float* running_mean,
                                           float* running_var, float* scale, float* shift, float* mean, float* invstd,

@@ -37,20 +37,20 @@ int timeout_reader_addr(int*);
 int timeout_reader_train(int*);
 int timeout_reader_enc(int*);
 int timeout_reader_halo(int*);
-int timeout_reader_probe(int*);
 int timeout_reader_front(int*);
 }
 
-// Debug aid: did any tcgen05 pipeline wait time out since the last call?  Synchronises the device.
-// Returns 0 if not; otherwise 1 and out4 = {kernel family (1 conv, 2 addressing, 3 training, 4 enc, 5 halo conv, 6 probes), tag, block, thread}.
-extern "C" int ammc_debug_timeout(int* out4) {
+// Synchronises the device and reports whether a tcgen05 pipeline wait hit its bound.  A wait that does executes `trap`
+// (ptx.cuh): the synchronise below then fails and this returns AMMC_ECUDA -- the normal way a broken pipeline surfaces.
+// Return 1 with out4 = {kernel family (1 conv, 2 addressing, 3 training, 4 enc, 5 halo conv, 6 fused memory front), tag,
+// block, thread} is kept for the case that the record could still be read; 0 = all pipelines healthy.
+extern "C" int ammc_pipeline_check(int* out4) {
   if (cudaDeviceSynchronize() != cudaSuccess) return ammc::fail(AMMC_ECUDA, "device synchronize failed: %s",
                                                                cudaGetErrorString(cudaGetLastError()));
   int rec[4];
-  int (*readers[7])(int*) = {ammc::timeout_reader_conv, ammc::timeout_reader_addr, ammc::timeout_reader_train,
-                             ammc::timeout_reader_enc, ammc::timeout_reader_halo, ammc::timeout_reader_probe,
-                             ammc::timeout_reader_front};
-  for (int i = 0; i < 7; ++i) {
+  int (*readers[6])(int*) = {ammc::timeout_reader_conv, ammc::timeout_reader_addr, ammc::timeout_reader_train,
+                             ammc::timeout_reader_enc, ammc::timeout_reader_halo, ammc::timeout_reader_front};
+  for (int i = 0; i < 6; ++i) {
     if (readers[i](rec) != 0) return ammc::fail(AMMC_ECUDA, "cannot read the watchdog record");
     if (rec[0]) {
       if (out4) { out4[0] = i + 1; out4[1] = rec[1]; out4[2] = rec[2]; out4[3] = rec[3]; }

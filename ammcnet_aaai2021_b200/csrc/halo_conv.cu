@@ -11,6 +11,7 @@ namespace ammc {
 int make_map_2d_bf16(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, uint32_t box_inner,
                      uint32_t box_outer);
 
+#ifdef AMMC_DEBUG_PROBES
 // ------------------------------------------------------------------------------------------------
 // probe: does a K-major SWIZZLE_128B operand descriptor work when it starts at an arbitrary 128-byte row of a tile that
 // TMA wrote 1024-byte aligned?  out[m][n] = sum_k A[row_off + m][k] * B[n][k],  m < 128, n < 64, k < 64.
@@ -63,6 +64,7 @@ __global__ void __launch_bounds__(128) desc_probe_kernel(const __grid_constant__
   __syncthreads();
   if (warp == 0) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem, 64); }
 }
+#endif  // AMMC_DEBUG_PROBES
 
 
 // ------------------------------------------------------------------------------------------------
@@ -411,6 +413,7 @@ AMMC_DEFINE_TIMEOUT_READER(timeout_reader_halo)
 
 using namespace ammc;
 
+#ifdef AMMC_DEBUG_PROBES
 extern "C" int ammc_debug_desc_probe(const void* a, const void* b, float* out, int rows, int row_off, int base_off,
                                      void* stream) {
   AMMC_REQUIRE(a && b && out && rows >= 128 && rows <= 256 && row_off >= 0 && row_off + 128 <= rows, "bad argument");
@@ -423,6 +426,7 @@ extern "C" int ammc_debug_desc_probe(const void* a, const void* b, float* out, i
   AMMC_LAUNCH_CHECK("desc_probe_kernel");
   return 0;
 }
+#endif  // AMMC_DEBUG_PROBES
 
 extern "C" int ammc_set_conv_halo_mode(int on) {
   g_halo_mode = on ? 1 : 0;

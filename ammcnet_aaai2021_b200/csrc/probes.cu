@@ -1,4 +1,5 @@
-// Hardware-behaviour probes for designs that are not built yet (debug entry points only, never on the product path).
+// Hardware-behaviour probes behind the kernel designs (debug entry points; compiled ONLY into libammc_b200_debug.so --
+// `python -m ammcnet_aaai2021_b200.build --debug` -- never into the product library).
 //
 // ammc_debug_fp8_probe: the mixed-precision chain proposed in DESIGN.md section 8 for the dominant conv kernel --
 //   D  = A8 . B8^T                 kind::f8f6f4 (e4m3 x e4m3, K = 32 per MMA, 128-byte swizzled K-major rows of 128 elements)
@@ -6,8 +7,10 @@
 // checks on a 128 x 64 tile that (i) sm_100a executes the plain (non block-scaled) fp8 kind with the same shared-memory
 // descriptors as bf16, (ii) a descriptor advance of +2 (32 bytes) is the K step for 8-bit operands as well, (iii)
 // scale-input-d rescales the accumulator exactly as documented.
+#ifdef AMMC_DEBUG_PROBES
 #include "common.cuh"
 #include "ptx.cuh"
+#include "../../include/ammc_b200_debug.h"
 
 namespace ammc {
 
@@ -136,7 +139,6 @@ __global__ void __launch_bounds__(128) mma_rate_kernel(long long* cycles, int fp
   if (warp == 0) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem, 256); }
 }
 
-AMMC_DEFINE_TIMEOUT_READER(timeout_reader_probe)
 
 }  // namespace ammc
 
@@ -184,3 +186,4 @@ extern "C" int ammc_debug_mma_rate(long long* cycles, int fp8, int n, int iters,
   AMMC_LAUNCH_CHECK("mma_rate_kernel");
   return 0;
 }
+#endif  // AMMC_DEBUG_PROBES

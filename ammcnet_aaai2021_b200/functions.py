@@ -252,11 +252,12 @@ def mem_forward_raw(x, enc_w, enc_b, embed, dec_w, dec_b, k: int, residual: bool
 
 
 def check_pipeline_watchdog():
-    """Synchronise and raise if any tcgen05 pipeline wait timed out (a kernel bug, never expected in production)."""
+    """Synchronise and raise if a tcgen05 pipeline wait hit its bound (a kernel bug, never expected in production; the
+    waiting thread traps, so the failure also surfaces on the next CUDA call of any kind)."""
     rec = (ctypes.c_int * 4)()
-    rc = _capi.load().ammc_debug_timeout(rec)
+    rc = _capi.load().ammc_pipeline_check(rec)
     if rc < 0:
-        _capi.check(rc, "ammc_debug_timeout")
+        _capi.check(rc, "ammc_pipeline_check")
     if rc == 1:
         raise RuntimeError("ammc_b200: tcgen05 pipeline wait timed out: family=%d tag=%d block=%d thread=%d"
                            % (rec[0], rec[1], rec[2], rec[3]))

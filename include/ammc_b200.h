@@ -39,21 +39,13 @@ int ammc_version(void);
 const char* ammc_last_error(void);
 /* 1 when the current device is sm_100 (B200); the library refuses to run anywhere else. */
 int ammc_device_supported(void);
-/* Debug aid: every mbarrier wait in the tcgen05 kernels is bounded; a pipeline that stalls records where and drains
- * instead of hanging the GPU.  Returns 0 when no wait timed out since the last call, 1 with out4 = {kernel family
- * (1 conv, 2 addressing, 3 training), wait tag, block, thread} otherwise, negative on CUDA errors.  Synchronises. */
-int ammc_debug_timeout(int* out4);
-/* Debug aid: kind::f8f6f4 (e4m3) MMAs chained into kind::f16 MMAs through scale-input-d on one 128x64 tile (csrc/probes.cu):
- * mode 0: out = (a8.b8^T) * 2^-12 + a16.b16^T; mode 1: out = a8.b8^T; mode 2: out = a16.b16^T. */
-/* Debug aid: clock64 ticks for `iters` x 4 back-to-back MMAs (M = 128, N = n) of kind::f16 / bf16 (fp8 = 0, K = 16) or
- * kind::f8f6f4 / e4m3 (fp8 = 1, K = 32) on one SM. */
-int ammc_debug_mma_rate(long long* cycles, int fp8, int n, int iters, void* stream);
-int ammc_debug_fp8_probe(const void* a8, const void* b8, const void* a16, const void* b16, float* out, int mode, void* stream);
-/* Debug aid: UMMA K-major SWIZZLE_128B descriptor starting at an arbitrary 128-byte row (see csrc/halo_conv.cu) */
-int ammc_debug_desc_probe(const void* a, const void* b, float* out, int rows, int row_off, int base_off, void* stream);
-/* Debug aid: TMA-load one 5-D bf16 box (128B swizzle, zero OOB fill) and dump the raw shared-memory bytes to `out`. */
-int ammc_debug_tma_probe(const void* base, const int64_t* dims5, const int64_t* strides4_bytes, const int* box5,
-                         const int* coords5, void* out, int out_bytes, void* stream);
+/* Every mbarrier wait in the tcgen05 kernels is bounded (~10 s of spinning, far beyond any legitimate wait): a pipeline that
+ * stalls records where and executes `trap`, so the launch fails, the CUDA context carries a sticky error and every later
+ * ammc_* call returns AMMC_ECUDA -- a broken pipeline can neither hang the GPU nor let later launches run on garbage.
+ * ammc_pipeline_check synchronises the device and returns 0 when healthy, AMMC_ECUDA after a trap (1 with out4 = {kernel
+ * family, wait tag, block, thread} if the record could still be read).  Hardware-behaviour probes live in
+ * include/ammc_b200_debug.h and are compiled only into the separate debug library. */
+int ammc_pipeline_check(int* out4);
 
 /* ---------------------------------------------------------------------------------------------------
  * Memory module.  Replaces enc_quan_dec_topk.forward / enc_quan_dec_res_topk.forward

@@ -1,7 +1,7 @@
 """Import the UNMODIFIED reference (/root/reference) in-process, for fixture generation only.
 
 TEST INFRASTRUCTURE -- not product code.  Only `oracle/gen_golden.py` and the container-only
-tests (`tests/test_oracle_vs_reference.py`) use this file.  `/root/reference` does not exist on the
+the host-logic test that patches the live reference (`tests/test_host_logic.py`) use this file.  `/root/reference` does not exist on the
 GPU box, so nothing under `-m gpu`, `smoke()` or `bench.py` may import it.
 
 Recipe follows SURVEY.md Appendix B: the reference imports a handful of packages that are not

@@ -1,7 +1,7 @@
 """Does an SW128 K-major UMMA descriptor accept a start address at any 128-byte row?  (prerequisite of the halo conv)"""
 import ctypes, os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from ammcnet_aaai2021_b200 import _capi
+from ammcnet_aaai2021_b200 import _capi_debug as _capi
 from ammcnet_aaai2021_b200.functions import check_pipeline_watchdog
 dev = "cuda:0"
 rows = 200

@@ -2,7 +2,7 @@
 scale-input-d.  Exact small-integer inputs, so every mode must reproduce the torch result bit for bit."""
 import ctypes, os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from ammcnet_aaai2021_b200 import _capi
+from ammcnet_aaai2021_b200 import _capi_debug as _capi
 from ammcnet_aaai2021_b200.functions import check_pipeline_watchdog
 dev = "cuda:0"
 g = torch.Generator().manual_seed(0)

@@ -3,7 +3,7 @@ import ctypes, os, sys
 import numpy as np
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from ammcnet_aaai2021_b200 import _capi, functions as F_
+from ammcnet_aaai2021_b200 import _capi_debug as _capi, functions as F_
 
 def probe(W, H, C, B, box, coords, tag):
     lib = _capi.load()
