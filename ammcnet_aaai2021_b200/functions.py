@@ -48,13 +48,18 @@ def _check_device(dev: torch.device):
 
 
 _workspaces: Dict[Tuple[int, int], torch.Tensor] = {}
+_retired_workspaces = []          # outgrown buffers stay alive: a captured CUDA graph may still hold their address
 
 
 def _workspace(nbytes: int, device: torch.device) -> torch.Tensor:
-    """Grow-only scratch buffer per (device, stream), owned by PyTorch's caching allocator."""
+    """Grow-only scratch buffer per (device, stream), owned by PyTorch's caching allocator.  A buffer that is outgrown
+    is retired, never freed: CUDA graphs captured earlier (GraphedPath, VideoScorer(graph=True)) replay launches that
+    carry its raw address."""
     key = (device.index, torch.cuda.current_stream(device).cuda_stream)
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
+        if ws is not None:
+            _retired_workspaces.append(ws)
         ws = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
         _workspaces[key] = ws
     return ws
@@ -92,13 +97,20 @@ def concurrently(*fns):
     for st in sides:
         cur.wait_stream(st)
     if not torch.cuda.is_current_stream_capturing():     # a captured graph owns its memory pool: nothing is ever reused
-        for r in results[1:]:                             # tensors produced on a side stream are consumed on this one
-            for t in (r if isinstance(r, (tuple, list)) else (r,)):
-                if isinstance(t, torch.Tensor):
-                    t.record_stream(cur)
-                    planes = getattr(t, "_ammc_planes", None)
-                    if planes is not None:
-                        planes[0].record_stream(cur)           # bf16 planes tensor or QPlanes
+        def mark(obj):                                    # tensors produced on a side stream are consumed on this one
+            if isinstance(obj, (torch.Tensor, QPlanes)):
+                obj.record_stream(cur)
+                planes = getattr(obj, "_ammc_planes", None)
+                if planes is not None:
+                    planes[0].record_stream(cur)           # bf16 planes tensor or QPlanes
+            elif isinstance(obj, (tuple, list)):
+                for o in obj:
+                    mark(o)
+            elif isinstance(obj, dict):
+                for o in obj.values():
+                    mark(o)
+        for r in results[1:]:
+            mark(r)
     return results
 
 
