@@ -38,6 +38,7 @@ constexpr int MF_D = 64;
 constexpr int MF_BK = 64;                          // channels per enc K block
 constexpr int MF_MPAD = 256;                       // items, padded (zero rows, +inf norms)
 constexpr int MF_CAP = 16;                         // exact-refine candidates per pixel
+constexpr int MF_GS = 4;                           // candidates refined together (shared z reads, independent chains)
 constexpr int MF_X_STAGE = 32 * 128 * 4;           // fp32 staging box [32 ch][128 px]          16 KB
 constexpr int MF_X_STAGES = 4;                     // stages h, h + 2 belong to channel half h
 constexpr int MF_STAGE_A = 128 * MF_BK * 2;        // one bf16 A tile [128 px][64 ch]           16 KB
@@ -356,27 +357,44 @@ mem_front_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       TopK<K> top;
       top.init();
       const int ncand_max = __reduce_max_sync(0xffffffffu, ncand);
-      for (int i = 0; i < ncand_max; ++i) {
-        const bool live = i < ncand;
-        const int col = live ? (int)list[i] : 0;
-        const float4* e4 = reinterpret_cast<const float4*>(p.bank_t + (size_t)col * MF_D);
-        float dot = 0.f;
+      // exact distances, MF_GS candidates at a time: one TMEM read of a z chunk serves all of them, their bank rows are
+      // 4 x MF_GS independent 16-byte loads in flight and MF_GS independent fmaf chains (each still ascending in d)
+      for (int base = 0; base < ncand_max; base += MF_GS) {
+        const float4* e4[MF_GS];
+        int col[MF_GS];
+        float dot[MF_GS];
+#pragma unroll
+        for (int u = 0; u < MF_GS; ++u) {
+          col[u] = base + u < ncand ? (int)list[base + u] : 0;
+          e4[u] = reinterpret_cast<const float4*>(p.bank_t + (size_t)col[u] * MF_D);
+          dot[u] = 0.f;
+        }
 #pragma unroll
         for (int c16 = 0; c16 < 4; ++c16) {
+          float4 e[MF_GS][4];
+#pragma unroll
+          for (int u = 0; u < MF_GS; ++u)
+#pragma unroll
+            for (int g = 0; g < 4; ++g) e[u][g] = __ldg(e4[u] + c16 * 4 + g);
           uint32_t zc[16];
           ptx::tmem_ld_32x16(z_tmem + c16 * 16, zc);
           ptx::tmem_ld_wait();
+          float zb[16];
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const float4 e = __ldg(e4 + c16 * 4 + g);
-            const int d = c16 * 16 + g * 4;
-            dot = fmaf(__uint_as_float(zc[g * 4 + 0]) + bias_s[d + 0], e.x, dot);
-            dot = fmaf(__uint_as_float(zc[g * 4 + 1]) + bias_s[d + 1], e.y, dot);
-            dot = fmaf(__uint_as_float(zc[g * 4 + 2]) + bias_s[d + 2], e.z, dot);
-            dot = fmaf(__uint_as_float(zc[g * 4 + 3]) + bias_s[d + 3], e.w, dot);
-          }
+          for (int d = 0; d < 16; ++d) zb[d] = __uint_as_float(zc[d]) + bias_s[c16 * 16 + d];
+#pragma unroll
+          for (int u = 0; u < MF_GS; ++u)
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              dot[u] = fmaf(zb[g * 4 + 0], e[u][g].x, dot[u]);
+              dot[u] = fmaf(zb[g * 4 + 1], e[u][g].y, dot[u]);
+              dot[u] = fmaf(zb[g * 4 + 2], e[u][g].z, dot[u]);
+              dot[u] = fmaf(zb[g * 4 + 3], e[u][g].w, dot[u]);
+            }
         }
-        if (live) top.insert(exact_dist(zn2, dot, __ldg(p.en2 + col)), col);
+#pragma unroll
+        for (int u = 0; u < MF_GS; ++u)
+          if (base + u < ncand) top.insert(exact_dist(zn2, dot[u], __ldg(p.en2 + col[u])), col[u]);
       }
 #pragma unroll
       for (int i = 0; i < K; ++i) top.id[i] = min(top.id[i], p.M - 1);
@@ -384,7 +402,6 @@ mem_front_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         atomicAdd(&p.stats[0], 1);
         p.rescan_list[atomicAdd(&p.stats[2], 1)] = (int)n;
       } else {
-        // ---- outputs of the row (arithmetic of team_emit_row, one thread instead of a 4-lane team)
         if (K == 2) {
           *reinterpret_cast<longlong2*>(p.idx + n * 2) = make_longlong2((long long)top.id[0], (long long)top.id[1]);
         } else {
@@ -392,24 +409,34 @@ mem_front_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           for (int i = 0; i < K; ++i) p.idx[n * K + i] = (int64_t)top.id[i];
         }
       }
-      // gathers: warp-collective TMEM loads, so rescan rows walk along with dummy stores masked off
+      // outputs of the row (arithmetic of team_emit_row, one thread instead of a 4-lane team), one pass over d: per 16
+      // components one TMEM read of z, the K winning rows (L1-resident: they were candidates a moment ago), q1 + SSE from
+      // the nearest, bf16 hi/lo planes of all K (A operand of the dec GEMM).  TMEM loads are warp-collective: re-scan rows
+      // walk along with their stores masked off.
       {
-        const float4* e1 = reinterpret_cast<const float4*>(p.bank_t + (size_t)top.id[0] * MF_D);
+        const float4* er[K];
+#pragma unroll
+        for (int j = 0; j < K; ++j) er[j] = reinterpret_cast<const float4*>(p.bank_t + (size_t)top.id[j] * MF_D);
         float sp[4] = {0.f, 0.f, 0.f, 0.f};        // team_emit_row: lane `part` owns the float4 chunks i = part (mod 4)
         float* q1r = p.q1 + n * MF_D;
+        const bool planes = !rescan && p.read_planes != nullptr;
 #pragma unroll
         for (int c16 = 0; c16 < 4; ++c16) {
+          float4 ev[K][4];
+#pragma unroll
+          for (int j = 0; j < K; ++j)
+#pragma unroll
+            for (int g = 0; g < 4; ++g) ev[j][g] = __ldg(er[j] + c16 * 4 + g);
           uint32_t zc[16];
           ptx::tmem_ld_32x16(z_tmem + c16 * 16, zc);
           ptx::tmem_ld_wait();
           uint32_t o[16];
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            const float4 ev = __ldg(e1 + c16 * 4 + g);
             const int d = c16 * 16 + g * 4;
             const float z0 = __uint_as_float(zc[g * 4 + 0]) + bias_s[d + 0], z1 = __uint_as_float(zc[g * 4 + 1]) + bias_s[d + 1];
             const float z2 = __uint_as_float(zc[g * 4 + 2]) + bias_s[d + 2], z3 = __uint_as_float(zc[g * 4 + 3]) + bias_s[d + 3];
-            const float d0 = ev.x - z0, d1 = ev.y - z1, d2 = ev.z - z2, d3 = ev.w - z3;
+            const float d0 = ev[0][g].x - z0, d1 = ev[0][g].y - z1, d2 = ev[0][g].z - z2, d3 = ev[0][g].w - z3;
             o[g * 4 + 0] = __float_as_uint(z0 + d0); o[g * 4 + 1] = __float_as_uint(z1 + d1);
             o[g * 4 + 2] = __float_as_uint(z2 + d2); o[g * 4 + 3] = __float_as_uint(z3 + d3);
             float s = sp[g];                       // chunk index i = c16 * 4 + g  ->  part = g
@@ -421,30 +448,25 @@ mem_front_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             ptx::stg_v8(q1r + c16 * 16, o8[0]);
             ptx::stg_v8(q1r + c16 * 16 + 8, o8[1]);
           }
+          if (planes) {
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+              uint32_t h[8], l[8];
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                ptx::split_pack_bf16x2(ev[j][g].x, ev[j][g].y, h[2 * g], l[2 * g]);
+                ptx::split_pack_bf16x2(ev[j][g].z, ev[j][g].w, h[2 * g + 1], l[2 * g + 1]);
+              }
+              __nv_bfloat16* hp = p.read_planes + (n * K + j) * MF_D + c16 * 16;
+              ptx::stg_v8(hp, h);
+              ptx::stg_v8(hp + p.read_plane_stride, l);
+            }
+          }
         }
         if (!rescan) p.sse_px[n] = (sp[0] + sp[1]) + (sp[2] + sp[3]);
       }
       ptx::tc_fence_before();
       ptx::mbar_arrive(&tmem_empty[acc]);           // z accumulator free (P2 re-read it)
-      if (!rescan && p.read_planes) {               // bf16 hi/lo split of the K gathered rows: A operand of the dec GEMM
-#pragma unroll
-        for (int j = 0; j < K; ++j) {
-          const float4* er = reinterpret_cast<const float4*>(p.bank_t + (size_t)top.id[j] * MF_D);
-          __nv_bfloat16* hp = p.read_planes + (n * K + j) * MF_D;
-#pragma unroll
-          for (int g8 = 0; g8 < 4; ++g8) {          // 16 values = 32 bytes per plane and store
-            uint32_t h[8], l[8];
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const float4 v = __ldg(er + g8 * 4 + g);
-              ptx::split_pack_bf16x2(v.x, v.y, h[2 * g], l[2 * g]);
-              ptx::split_pack_bf16x2(v.z, v.w, h[2 * g + 1], l[2 * g + 1]);
-            }
-            ptx::stg_v8(hp + g8 * 16, h);
-            ptx::stg_v8(hp + p.read_plane_stride + g8 * 16, l);
-          }
-        }
-      }
     }
   }
   ptx::tc_fence_before();

@@ -13,7 +13,7 @@
 //   dec_gather_kernel out[n,:] = sum_j T_j[idx_j(n)] + dec_b (+ x[n,:])  NCHW out         (unet.py:328-330,386)
 //        (dec is linear and the read is a concatenation of bank rows, so dec(read_n) is a sum of k rows of
 //         the precomputed tables: the N x kD x C contraction becomes a gather)
-//   sse_frame_kernel / diff_kernel            deterministic per-frame and global commit reductions (unet.py:310)
+//   sse_frame_kernel                          deterministic per-frame and global commit reductions (unet.py:310), q-plane scale
 //   backward: gz_kernel, then on tcgen05 when D, C % 64 == 0 (1x1 conv engine for the input gradient, weight-gradient
 //             kernel of amft_train.cu for both weight gradients; pack_nhwc64 / read_planes / channel_sum prepare operands),
 //             else gx_kernel, genc_w_kernel, gdec_scatter_priv_kernel (gdec_scatter_kernel for huge banks), gdec_w_kernel
@@ -254,8 +254,16 @@ __global__ void __launch_bounds__(256) address_kernel(
                    read, q1, idx, sse_px, counts, embed_sum, read_planes, (long long)N * K * D);
 }
 
-__global__ void sse_frame_kernel(const float* __restrict__ sse_px, float* __restrict__ sse_frame, int64_t rows) {
+// One block per frame: per-frame commit partial (unet.py:310 summed over the frame's pixels).  The block that finishes
+// last (ticket counter) also produces what used to be two more launches: `diff`, the batch mean over all N*D elements
+// (frames summed in index order by one warp-strided loop: deterministic), and -- when asked -- the power-of-two scale of
+// the module's q-plane output from max|x| and the prepared dec bound (see dec_bound_kernel).
+__global__ void sse_frame_kernel(const float* __restrict__ sse_px, float* __restrict__ sse_frame, int64_t rows,
+                                 float* __restrict__ diff, double inv_count, unsigned* __restrict__ ticket,
+                                 const unsigned* __restrict__ amax_bits, const unsigned* __restrict__ bound_bits,
+                                 int residual, float* __restrict__ qs) {
   __shared__ float red[33];
+  __shared__ bool last;
   const float* p = sse_px + (size_t)blockIdx.x * rows;
   float s = 0.f;
   if ((rows & 3) == 0 && (((uintptr_t)p) & 15) == 0) {       // 16-byte loads, four in flight (one block per frame)
@@ -270,15 +278,22 @@ __global__ void sse_frame_kernel(const float* __restrict__ sse_px, float* __rest
     for (int64_t i = threadIdx.x; i < rows; i += blockDim.x) s += p[i];
   }
   s = block_sum(s, red);
-  if (threadIdx.x == 0) sse_frame[blockIdx.x] = s;
-}
-
-__global__ void diff_kernel(const float* __restrict__ sse_frame, float* __restrict__ diff, int frames, double inv_count) {
-  __shared__ float red[33];
-  float s = 0.f;
-  for (int i = threadIdx.x; i < frames; i += blockDim.x) s += sse_frame[i];
-  s = block_sum(s, red);
-  if (threadIdx.x == 0) diff[0] = (float)((double)s * inv_count);
+  if (threadIdx.x == 0) {
+    sse_frame[blockIdx.x] = s;
+    __threadfence();
+    last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  float t = 0.f;
+  for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) t += __ldcg(sse_frame + i);
+  t = block_sum(t, red);
+  if (threadIdx.x == 0) {
+    diff[0] = (float)((double)t * inv_count);
+    *ticket = 0;                                             // ready for the next call on this workspace
+    if (qs) qs[0] = q_scale_for_bound((residual ? __uint_as_float(amax_bits[0]) : 0.f) + __uint_as_float(bound_bits[0]));
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -800,11 +815,6 @@ __global__ void __launch_bounds__(256) dec_bound_kernel(const float* __restrict_
   }
   if (lane == 0) atomicMax(bound_bits, __float_as_uint(bound * emax * 1.01f + fabsf(dec_b[c])));
 }
-__global__ void mem_out_qscale_kernel(const unsigned* __restrict__ amax_bits, const unsigned* __restrict__ bound_bits,
-                                      int residual, float* __restrict__ qs) {
-  if (threadIdx.x == 0)
-    qs[0] = q_scale_for_bound((residual ? __uint_as_float(amax_bits[0]) : 0.f) + __uint_as_float(bound_bits[0]));
-}
 
 // Everything the forward derives from the parameters alone (constant between optimizer / EMA steps): packed once by
 // ammc_mem_prepare into a caller-owned buffer and reused by every ammc_mem_fwd until a parameter changes.
@@ -931,12 +941,13 @@ static int run_address(const float* z, const float* embed, const MemWs& m, float
 }
 
 static int run_commit(const MemWs& m, float* sse_frame, float* diff, int64_t N, int64_t rows_per_frame, int D,
-                      cudaStream_t st) {
+                      cudaStream_t st, const unsigned* amax_bits = nullptr, const unsigned* bound_bits = nullptr,
+                      int residual = 0, float* qs = nullptr) {
   int frames = (int)(N / rows_per_frame);
-  sse_frame_kernel<<<frames, 256, 0, st>>>(m.sse_px, sse_frame, rows_per_frame);
+  unsigned* ticket = reinterpret_cast<unsigned*>(m.stats + 3);       // word 3 of the stats block (zeroed with it)
+  sse_frame_kernel<<<frames, 256, 0, st>>>(m.sse_px, sse_frame, rows_per_frame, diff, 1.0 / ((double)N * (double)D), ticket,
+                                           amax_bits, bound_bits, residual, qs);
   AMMC_LAUNCH_CHECK("sse_frame_kernel");
-  diff_kernel<<<1, 256, 0, st>>>(sse_frame, diff, frames, 1.0 / ((double)N * (double)D));
-  AMMC_LAUNCH_CHECK("diff_kernel");
   return 0;
 }
 
@@ -1085,7 +1096,10 @@ extern "C" int ammc_mem_fwd(const float* x, const float* enc_w, const float* enc
     }
     if (int rc = run_address(z, embed, m, nullptr, q1, idx, counts, embed_sum, N, D, M, k, st, ws)) return rc;
   }
-  if (int rc = run_commit(m, sse_frame, diff, N, HW, D, st)) return rc;
+  {
+    float* qs = q_planes ? reinterpret_cast<float*>((uint8_t*)out_planes + 4 * N * C) : nullptr;   // scale slot of the q buffer
+    if (int rc = run_commit(m, sse_frame, diff, N, HW, D, st, amax_bits, pr.dec_bound, residual, qs)) return rc;
+  }
   const float* res = residual ? x : nullptr;
   if (tc_dec) {
     // dec(read) as a [N, kD] x [kD, C] GEMM on tcgen05 (split-bf16 x3); bias, residual and -- when asked -- the NHWC
@@ -1094,12 +1108,7 @@ extern "C" int ammc_mem_fwd(const float* x, const float* enc_w, const float* enc
     L.in_planes = m.read_planes; L.wp = pr.dec_wp; L.taps = 1; L.scale = pr.ones; L.shift = dec_b; L.act = 0;
     L.out_planes = out_planes; L.out_nchw = out; L.res_nchw = res;
     L.b = b; L.h = h; L.w = w; L.Cin = k * D; L.Cout = C; L.precision = 3;
-    if (q_planes) {
-      float* qs = reinterpret_cast<float*>((uint8_t*)out_planes + 4 * N * C);
-      mem_out_qscale_kernel<<<1, 32, 0, st>>>(amax_bits, pr.dec_bound, residual, qs);
-      AMMC_LAUNCH_CHECK("mem_out_qscale_kernel");
-      L.out_fmt = 1;
-    }
+    if (q_planes) L.out_fmt = 1;        // its scale was written by the commit kernel above
     return conv_run(L, st);
   }
   const int chunks = 4;

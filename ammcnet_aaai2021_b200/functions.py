@@ -256,8 +256,8 @@ def mem_forward_raw(x, enc_w, enc_b, embed, dec_w, dec_b, k: int, residual: bool
                    _p(dec_w.contiguous()), _p(dec_b.contiguous()), _p(out), _p(q1), _p(idx), _p(z), _p(sse), _p(diff),
                    _p(counts), _p(esum), _p(planes), int(isinstance(planes, QPlanes)), _p(prep), _p(ws), ws.numel(), b, h,
                    w, C, D, M, k, int(bool(residual)), _stream())
-    # front kernel + rescan + 2 commit kernels + dec (+ q scale) when prepared and fused; the staged path launches more
-    _count((5 if prep is not None else 13) + (2 if want_stats else 0) + (1 if isinstance(planes, QPlanes) else 0))
+    # fused front kernel + re-scan + commit + dec when prepared; otherwise + 8 parameter-prep launches (staged kernels: more)
+    _count((4 if prep is not None else 12) + (2 if want_stats else 0))
     if planes is not None:
         attach_planes(out, planes)
     return dict(out=out, q1=q1, idx=idx, z=z, sse_frame=sse, diff=diff, counts=counts, embed_sum=esum, x=x)
