@@ -58,6 +58,8 @@ struct ConvParams {
   const float* in_qs;            // device scalars: scales of the q input and the q weights (PAIR_Q mode), else null
   const float* w_qs;
   int a_reuse;                   // PAIR_Q, 3x3: one (H_box+2)-row A tile per (dx, channel block) serves the three dy taps
+  const float* out_l1;           // PAIR_Q with q output: per-output-channel sum_k |w| -- the kernel derives the output scale itself
+  float* out_qs_store;           // ... and CTA 0 stores it for the consumer
 };
 
 // m-tile index -> first image / row / column of its TMA box
@@ -532,6 +534,24 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     const int per_img = p.W_box * p.H_box;
     constexpr int HALF_N = PAIR_N / 2;
     const size_t hw = (size_t)p.H * p.W;
+    // PAIR_Q writing q planes: the power-of-two scale of the output follows from a rigorous bound,
+    //   |y_c| <= |scale_c| * sum_k |w_ck| * max|x| + |shift_c|,   max|x| <= 2^15 / s16(input),
+    // evaluated here by the (otherwise idle) epilogue warps of every CTA while the first tile's MMAs run -- no extra launch
+    float oq_self = 1.f;
+    if (QMODE && p.out_l1 != nullptr) {
+      float* red = reinterpret_cast<float*>(tmem_slot + 4);          // 8 floats of the barrier block's slack
+      const float X = 32768.f / __ldg(p.in_qs);
+      float m = 0.f;
+      for (int c = threadIdx.x - 64; c < p.Cout; c += 32 * PAIR_EPI_WARPS)
+        m = fmaxf(m, fabsf(__ldg(p.scale + c)) * __ldg(p.out_l1 + c) * X * 1.01f + fabsf(__ldg(p.shift + c)));
+      m = warp_max(m);
+      if (lane == 0) red[warp - 2] = m;
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * PAIR_EPI_WARPS) : "memory");
+#pragma unroll
+      for (int i = 0; i < PAIR_EPI_WARPS; ++i) m = fmaxf(m, red[i]);
+      oq_self = q_scale_for_bound(m);
+      if (blockIdx.x == 0 && threadIdx.x == 64) *p.out_qs_store = oq_self;
+    }
     int it = 0;
     for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
       const int acc = it & 1;
@@ -555,7 +575,7 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       const bool has_res = valid && p.res_nchw != nullptr;
       // q operands carry power-of-two scales: the accumulator holds (x.w) * s16x * s16w
       const float acc_inv = QMODE ? 1.f / (__ldg(p.in_qs) * __ldg(p.w_qs)) : 1.f;
-      const float oq = p.out_fmt == 1 ? __ldg(p.out_qs) : 1.f;
+      const float oq = p.out_fmt == 1 ? ((QMODE && p.out_l1 != nullptr) ? oq_self : __ldg(p.out_qs)) : 1.f;
       __half* const oq16 = p.out_q16 + opix * p.out_cs + p.out_c_off;
       uint8_t* const oq8 = p.out_q8 + opix * p.out_cs + p.out_c_off;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * PAIR_N + half * HALF_N;
@@ -724,22 +744,6 @@ __global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ x
 }
 __global__ void qscale_from_absmax_kernel(const unsigned* __restrict__ amax_bits, float* __restrict__ qs) {
   if (threadIdx.x == 0) qs[0] = q_scale_for_bound(__uint_as_float(amax_bits[0]));
-}
-// scale of a conv output written as q planes: bound_c = |scale_c| * L1_c * X + |shift_c|, X = 2^15 / s16(input) >= max|x|
-__global__ void __launch_bounds__(256) qscale_conv_out_kernel(const float* __restrict__ l1, const float* __restrict__ scale,
-                                                              const float* __restrict__ shift, const float* __restrict__ in_qs,
-                                                              int Cout, float* __restrict__ out_qs) {
-  __shared__ float red[8];
-  const float X = 32768.f / in_qs[0];
-  float m = 0.f;
-  for (int c = threadIdx.x; c < Cout; c += blockDim.x) m = fmaxf(m, fabsf(scale[c]) * l1[c] * X * 1.01f + fabsf(shift[c]));
-  m = warp_max(m);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
-    out_qs[0] = q_scale_for_bound(m);
-  }
 }
 // weights: one block per output channel; w [Cout][Cin][taps] -> q planes with k = tap*Cin + cin, L1 row sums
 __global__ void __launch_bounds__(256) pack_weights_q_kernel(const float* __restrict__ w, uint8_t* __restrict__ wq, int Cout,
@@ -956,7 +960,7 @@ int conv_run(const ammc_conv_layer& L, cudaStream_t st) {
   p.res_nchw = L.res_nchw;
   p.cout_valid = cout_valid;
   p.out_fmt = 0; p.out_q16 = nullptr; p.out_q8 = nullptr; p.out_q8_stride = 0; p.out_qs = nullptr;
-  p.in_qs = nullptr; p.w_qs = nullptr;
+  p.in_qs = nullptr; p.w_qs = nullptr; p.out_l1 = nullptr; p.out_qs_store = nullptr;
   const bool qmode = L.precision == 2;
   p.a_reuse = (qmode && ntaps == 9 && g_conv_q_reuse && p.B_box == 1 && p.groups_w == 1 && p.W_box % 8 == 0 &&
                p.W_box * (p.H_box + 2) <= 192) ? 1 : 0;
@@ -977,11 +981,9 @@ int conv_run(const ammc_conv_layer& L, cudaStream_t st) {
                  Cin, Cout);
     p.in_qs = (const float*)((const uint8_t*)L.in_planes + 4 * n_in);
     p.w_qs = (const float*)((const uint8_t*)L.wp + 4 * n_w + 4 * (long long)Cout);
-    if (L.out_fmt == 1) {
-      // scale of the q output from a rigorous bound: |y_c| <= |scale_c| * sum_k |w_ck| * max|x| + |shift_c|
-      qscale_conv_out_kernel<<<1, 256, 0, st>>>((const float*)((const uint8_t*)L.wp + 4 * n_w), L.scale, L.shift, p.in_qs,
-                                                Cout, const_cast<float*>(p.out_qs));
-      AMMC_LAUNCH_CHECK("qscale_conv_out_kernel");
+    if (L.out_fmt == 1) {       // the kernel's epilogue warps derive the output scale from the weights' L1 row sums
+      p.out_l1 = (const float*)((const uint8_t*)L.wp + 4 * n_w);
+      p.out_qs_store = const_cast<float*>(p.out_qs);
     }
   }
 

@@ -549,7 +549,7 @@ def conv3x3_bn_relu(xp, wp, scale, shift, *, to_planes: bool, residual: Optional
         if PROFILE["on"]:
             ev1.record()
             PROFILE["events"].append((ev0, ev1))
-    _count(2 if (precision == 2 and to_planes) else 1)
+    _count(1)
     return out_p if to_planes else out_n
 
 
