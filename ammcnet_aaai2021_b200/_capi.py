@@ -10,7 +10,7 @@ import os
 from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_size_t, c_void_p
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libammc_b200.so")
+LIB_PATH = os.environ.get("AMMC_B200_LIB") or os.path.join(_PKG, "libammc_b200.so")     # override: A/B builds only
 
 P, I, L, F, Z = c_void_p, c_int, c_int64, c_float, c_size_t
 
