@@ -78,7 +78,16 @@ def main():
         row["gx_vs_cudnn_fp32"] = cmp(gx_ours, gx_ref)
         torch.backends.cudnn.allow_tf32 = True
         step(ref)(); row["cudnn_tf32_gx_vs_cudnn_fp32"] = cmp(zx.grad.clone(), gx_ref)
+        row["cudnn_tf32_wgrad_vs_cudnn_fp32"] = cmp(ref.O2F.conv[0].weight.grad.clone(), g_ref)
         torch.backends.cudnn.allow_tf32 = False
+        # reduced-precision variant, stated separately: one bf16 tensor-core pass for every convolution of the step
+        # (forward, data gradient, weight gradient) -- 8 significant bits per operand against TF32's 10
+        ours.precision = 1
+        row["ours_single_bf16_pass_ms"] = timed(step(ours))
+        step(ours)()
+        row["single_bf16_pass_wgrad_vs_cudnn_fp32"] = cmp(ours.O2F.conv[0].weight.grad.clone(), g_ref)
+        row["single_bf16_pass_gx_vs_cudnn_fp32"] = cmp(zx.grad.clone(), gx_ref)
+        ours.precision = 2
         F_.check_pipeline_watchdog()
         res.append(row)
         print(json.dumps(row), flush=True)
