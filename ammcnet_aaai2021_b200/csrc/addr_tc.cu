@@ -43,8 +43,10 @@ struct AddrParams {
   const float* en2pad;  // [Mpad], +inf beyond M
   const float2* zmeta;  // [N]  (||z_n||^2, 1 / s_n): fp32 norm and the inverse of the row's power-of-two fp16 scale
   const float* emax;    // [2]  max_j ||e_j||, 1 / t (inverse of the bank's power-of-two fp16 scale)
-  int* cand;            // [N][ADDR_CAND]
-  int* cand_cnt;        // [N][2]  entries used per half; > ADDR_CAPH means overflow -> exact re-scan
+  int k;                // items wanted per query (<= KSEL of the instantiation)
+  int* cand;            // [N][ADDR_CAND]  merged candidate list of the query (both column halves)
+  int* cand_cnt;        // [N][2]  [0] entries used (> ADDR_CAND: a list overflowed -> exact re-scan), [1] 1 when the
+                        //         filter alone decided the row: cand[0..k) are the final indices in rank order
 };
 
 template <int BLOCK_N>
@@ -53,7 +55,8 @@ struct AddrSmem {
   static constexpr int STAGE_BYTES = ADDR_A_BYTES + B_BYTES;
   static constexpr int STAGES = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8);
   static constexpr int LIST_OFFSET = STAGES * STAGE_BYTES;         // float [256 threads][CAPH] + uint16 [256][CAPH]
-  static constexpr int BAR_OFFSET = LIST_OFFSET + 256 * ADDR_CAPH * 6;
+  static constexpr int XCH_OFFSET = LIST_OFFSET + 256 * ADDR_CAPH * 6;   // float [128 rows][4] + int [128]: half 1 -> half 0
+  static constexpr int BAR_OFFSET = XCH_OFFSET + 128 * 4 * 4 + 128 * 4;
   static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
 };
 
@@ -90,6 +93,8 @@ addr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   float* list_val = reinterpret_cast<float*>(smem + S::LIST_OFFSET);
   uint16_t* list_idx = reinterpret_cast<uint16_t*>(smem + S::LIST_OFFSET + 256 * ADDR_CAPH * 4);
+  float* xch_m = reinterpret_cast<float*>(smem + S::XCH_OFFSET);             // [128][4] best scores of column half 1
+  int* xch_cnt = reinterpret_cast<int*>(smem + S::XCH_OFFSET + 128 * 4 * 4);  // [128] its list length, -1 = overflowed
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFFSET);
   uint64_t* empty_bar = full_bar + S::STAGES;
   uint64_t* tmem_full = empty_bar + S::STAGES;
@@ -177,9 +182,14 @@ addr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const float zn2 = zm.x;
       const float cs = -2.f * zm.y * tinv;           // a~ = ||e||^2 + cs * (z~.e~): undoes the two power-of-two scales
       // |a~ - a| <= 4u(1+u) ||z|| ||e||, u = 2^-11 (fp16 rounding of both operands, Cauchy-Schwarz); candidates within
-      // twice that (+ fp32 accumulation slack) of the KSEL-th smallest approximate score are a superset of the exact
-      // top-KSEL (see file header).
-      const float margin = 8.f * 0.00048828125f * 1.01f * sqrtf(zn2) * emax + 1e-5f * (zn2 + emax * emax) + 1e-30f;
+      // twice that of the KSEL-th smallest approximate score are a superset of the exact top-KSEL (see file header).
+      // The second term bounds, again worst case, what fp32 evaluation adds on both sides (u32 = 2^-24): the D-term
+      // accumulations of the MMA and of the exact kernel's dot product (2 * 2 * D u32 ||z|| ||e||), of ||e||^2
+      // (D u32 ||e||^2) and the roundings of the three-term distance (3 u32 (||z|| + ||e||)^2) -- doubled like the first.
+      const float zn = sqrtf(zn2);
+      const float margin = 8.f * 0.00048828125f * 1.01f * zn * emax +
+                           1.1920929e-7f * (4.f * (float)p.D * zn * emax + (float)p.D * emax * emax +
+                                            3.f * (zn + emax) * (zn + emax)) + 1e-30f;
       float m[KSEL];
 #pragma unroll
       for (int i = 0; i < KSEL; ++i) m[i] = INFINITY;
@@ -255,16 +265,60 @@ addr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         ptx::tc_fence_before();
         ptx::mbar_arrive(&tmem_empty[acc]);
       }
-      if (n < p.N) {
-        // final prune against the final threshold, then publish
-        const float thr_final = fminf(m[KSEL - 1] + margin, FLT_MAX);
-        int* dst = p.cand + (size_t)n * ADDR_CAND + half * ADDR_CAPH;
-        int w = 0;
-        for (int i = 0; i < cnt; ++i)
-          if (lv[i] <= thr_final) dst[w++] = (int)li[i];
-        for (int i = w; i < ADDR_CAPH; ++i) dst[i] = -1;
-        p.cand_cnt[(size_t)n * 2 + half] = overflow ? ADDR_CAPH + 1 : w;
+      // ---- merge the two column halves of the row and decide.  Half 1 hands its best scores and list over in shared
+      // memory; the half-0 thread prunes both lists against the row's final threshold, and -- new in round 2 -- checks
+      // whether the approximate ranking is already PROVEN: every candidate's approximate score is within margin / 2 of
+      // the fp32 distance the exact kernel would compute, so k candidates whose consecutive scores (and the next one, if
+      // any survived) lie more than `margin` apart are in their final order and need no exact distance at all.
+      const int row = q * 32 + lane;
+      if (half == 1) {
+#pragma unroll
+        for (int i = 0; i < KSEL; ++i) xch_m[row * 4 + i] = m[i];
+        xch_cnt[row] = overflow ? -1 : cnt;
       }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (half == 0 && n < p.N) {
+#pragma unroll
+        for (int i = 0; i < KSEL; ++i) sel_insert<KSEL>(m, xch_m[row * 4 + i]);
+        const float thr_final = fminf(m[KSEL - 1] + margin, FLT_MAX);
+        const int ocnt = xch_cnt[row];
+        const bool ovf = overflow || ocnt < 0;
+        const float* olv = lv + (size_t)4 * 32 * ADDR_CAPH;      // the partner warp (warp + 4) holds the other half
+        const uint16_t* oli = li + (size_t)4 * 32 * ADDR_CAPH;
+        int* dst = p.cand + (size_t)n * ADDR_CAND;
+        float sv[KSEL + 1];
+        int si[KSEL + 1];
+#pragma unroll
+        for (int i = 0; i <= KSEL; ++i) { sv[i] = INFINITY; si[i] = 0; }
+        int w = 0;
+        auto take = [&](float x, int c) {
+          if (x <= thr_final) {
+            dst[w++] = c;
+#pragma unroll
+            for (int i = 0; i <= KSEL; ++i) {
+              const bool lt = x < sv[i];
+              const float tx = lt ? sv[i] : x; const int tc = lt ? si[i] : c;
+              sv[i] = lt ? x : sv[i]; si[i] = lt ? c : si[i];
+              x = tx; c = tc;
+            }
+          }
+        };
+        for (int i = 0; i < cnt; ++i) take(lv[i], (int)li[i]);
+        for (int i = 0; i < ocnt; ++i) take(olv[i], (int)oli[i]);
+        bool decided = !ovf;
+#pragma unroll
+        for (int i = 0; i < KSEL; ++i)
+          if (i < p.k) decided = decided && (sv[i + 1] - sv[i] > margin);      // inf - inf = NaN -> undecided
+        if (decided) {
+#pragma unroll
+          for (int i = 0; i < KSEL; ++i)
+            if (i < p.k) dst[i] = si[i];
+          w = p.k;
+        }
+        p.cand_cnt[(size_t)n * 2] = ovf ? ADDR_CAND + 1 : w;
+        p.cand_cnt[(size_t)n * 2 + 1] = decided ? 1 : 0;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // the lists are free for the next query tile
     }
   }
   ptx::tc_fence_before();
@@ -363,8 +417,8 @@ __global__ void __launch_bounds__(256) refine_kernel(
   TopK<K> top;
   top.init();
   if (valid) {
-    const int c0 = cand_cnt[(size_t)n * 2], c1 = cand_cnt[(size_t)n * 2 + 1];
-    const bool rescan = c0 > ADDR_CAPH || c1 > ADDR_CAPH || (c0 + c1) < K;       // uniform within the 4-lane team
+    const int c0 = cand_cnt[(size_t)n * 2];
+    const bool rescan = c0 > ADDR_CAND || c0 < K;                                 // uniform within the 4-lane team
     if (rescan) {
       if (part == 0) {
         atomicAdd(&stats[0], 1);
@@ -377,10 +431,6 @@ __global__ void __launch_bounds__(256) refine_kernel(
         const int j = cr[c];
         top.insert(exact_dist(zn2, exact_dot(zr, bank_t + (size_t)j * D, D), en2[j]), j);
       }
-      for (int c = part; c < c1; c += 4) {
-        const int j = cr[ADDR_CAPH + c];
-        top.insert(exact_dist(zn2, exact_dot(zr, bank_t + (size_t)j * D, D), en2[j]), j);
-      }
     }
   }
   team_merge<K>(top);
@@ -388,6 +438,182 @@ __global__ void __launch_bounds__(256) refine_kernel(
   for (int i = 0; i < K; ++i) top.id[i] = min(top.id[i], M - 1);
   team_emit_row<K>(zr, bank_t, top.id, (int64_t)n, D, M, part, valid, read, q1, idx, sse_px, counts, embed_sum,
                    read_planes, read_plane_stride);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Tail for D >= 128: ONE WARP PER QUERY, every global access a coalesced 16-byte-per-lane row segment.
+//   * rows the filter decided (cand_cnt[n][1] == 1): no distance is computed; the warp streams z and the k item rows
+//     and writes q1 / read / idx / the commit partial -- a pure gather at HBM speed.
+//   * ambiguous rows: z and up to TAIL_CM candidate rows pass through shared memory in 128-element segments (coalesced
+//     loads, the next segment in flight while this one is used); lane c then walks candidate c's fmaf chain in
+//     ascending d and every lane the ||z||^2 chain of its component (lane & 3), i.e. exactly the arithmetic of
+//     exact_dot / team_zn2 above, so the ranking is bit-identical to refine_kernel and to the fp32 kernel.
+// The commit partial keeps the summation tree of team_emit_row (four interleaved chains over the 16-byte chunks, then
+// (s0 + s1) + (s2 + s3)): a chain crosses the lanes in order, eight hops per 512 elements.
+// ------------------------------------------------------------------------------------------------
+constexpr int TAIL_CM = 4;      // candidate rows chained per pass (one lane each)
+constexpr int TAIL_ROW4 = 33;   // staged segment pitch in 16-byte units: 32 + 1 shifts the banks row to row
+
+__device__ __forceinline__ float chain4(float acc, const float4& a, const float4& b) {
+  acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
+  return acc;
+}
+
+template <int K>
+__global__ void __launch_bounds__(512, 2) addr_tail_kernel(
+    const float* __restrict__ z, const int* __restrict__ cand, const int* __restrict__ cand_cnt,
+    const float* __restrict__ bank_t, const float* __restrict__ en2,
+    float* __restrict__ read, float* __restrict__ q1, int64_t* __restrict__ idx, float* __restrict__ sse_px,
+    float* __restrict__ counts, float* __restrict__ embed_sum, int* __restrict__ stats, int* __restrict__ rescan_list,
+    __nv_bfloat16* __restrict__ read_planes, long long read_plane_stride, int N, int D, int M) {
+  __shared__ float4 tail_smem[16 * (1 + TAIL_CM) * TAIL_ROW4];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  float4* sz4 = tail_smem + warp * (1 + TAIL_CM) * TAIL_ROW4;   // this warp's staged 128-element segment of z ...
+  float4* se4 = sz4 + TAIL_ROW4;                                 // ... and of up to TAIL_CM candidate rows
+  const int chunks = D >> 2;
+  const int part = lane & 3;
+  for (int n = blockIdx.x * wpb + warp; n < N; n += gridDim.x * wpb) {
+    const int cnt = __ldg(cand_cnt + (size_t)n * 2);
+    const int decided = __ldg(cand_cnt + (size_t)n * 2 + 1);
+    if (cnt > ADDR_CAND || cnt < K) {                       // a list overflowed (or M < K items scored): exact re-scan
+      if (lane == 0) {
+        atomicAdd(&stats[0], 1);
+        rescan_list[atomicAdd(&stats[2], 1)] = n;
+      }
+      continue;
+    }
+    const int* cr = cand + (size_t)n * ADDR_CAND;
+    const float4* z4 = reinterpret_cast<const float4*>(z + (size_t)n * D);
+    int ids[K];
+    if (decided) {
+#pragma unroll
+      for (int i = 0; i < K; ++i) ids[i] = __ldg(cr + i);
+    } else {
+      TopK<K> top;
+      top.init();
+      float zn2 = 0.f;
+      for (int c0 = 0; c0 < cnt; c0 += TAIL_CM) {
+        const int nc = min(TAIL_CM, cnt - c0);
+        const bool dotl = lane < nc;
+        const int jme = dotl ? __ldg(cr + c0 + lane) : 0;
+        const float4* e4[TAIL_CM];
+#pragma unroll
+        for (int c = 0; c < TAIL_CM; ++c)
+          e4[c] = reinterpret_cast<const float4*>(bank_t + (size_t)__shfl_sync(0xffffffffu, jme, c) * D);
+        const float4* er4 = se4 + (dotl ? lane : 0) * TAIL_ROW4;   // lane c < nc chains candidate c (the others idle on row 0)
+        float acc = 0.f, zacc = 0.f;
+        // segments of 128 elements: the next one is fetched (coalesced, 512 bytes per row) while this one is chained
+        float4 pz, pe[TAIL_CM];
+        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        pz = lane < chunks ? __ldg(z4 + lane) : zero4;
+#pragma unroll
+        for (int c = 0; c < TAIL_CM; ++c) pe[c] = (c < nc && lane < chunks) ? __ldg(e4[c] + lane) : zero4;
+        for (int s0 = 0; s0 < chunks; s0 += 32) {
+          sz4[lane] = pz;
+#pragma unroll
+          for (int c = 0; c < TAIL_CM; ++c) se4[c * TAIL_ROW4 + lane] = pe[c];
+          __syncwarp();
+          const int nx = s0 + 32 + lane;
+          pz = nx < chunks ? __ldg(z4 + nx) : zero4;
+#pragma unroll
+          for (int c = 0; c < TAIL_CM; ++c) pe[c] = (c < nc && nx < chunks) ? __ldg(e4[c] + nx) : zero4;
+          const int lim = min(32, chunks - s0);
+          // candidate chain + (same pass, same shared-memory read of z) the ||z||^2 chain of component `part`; shared
+          // memory wavefronts, not instruction issue, bound this loop (ncu), hence selects instead of a second read
+#pragma unroll 4
+          for (int i = 0; i < lim; ++i) {
+            const float4 a = sz4[i];
+            acc = chain4(acc, a, er4[i]);
+            const float c = (part & 1) ? ((part & 2) ? a.w : a.y) : ((part & 2) ? a.z : a.x);
+            zacc = fmaf(c, c, zacc);
+          }
+          __syncwarp();
+        }
+        if (c0 == 0) {
+          const float s0 = __shfl_sync(0xffffffffu, zacc, 0), s1 = __shfl_sync(0xffffffffu, zacc, 1);
+          const float s2 = __shfl_sync(0xffffffffu, zacc, 2), s3 = __shfl_sync(0xffffffffu, zacc, 3);
+          zn2 = (s0 + s1) + (s2 + s3);
+        }
+        const float dme = dotl ? exact_dist(zn2, acc, __ldg(en2 + jme)) : INFINITY;
+        for (int c = 0; c < nc; ++c) top.insert(__shfl_sync(0xffffffffu, dme, c), __shfl_sync(0xffffffffu, jme, c));
+      }
+#pragma unroll
+      for (int i = 0; i < K; ++i) ids[i] = top.id[i];
+    }
+#pragma unroll
+    for (int i = 0; i < K; ++i) ids[i] = min(ids[i], M - 1);
+    // ---- outputs
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < K; ++i) idx[(size_t)n * K + i] = (int64_t)ids[i];
+      if (counts) atomicAdd(&counts[ids[0]], 1.f);
+    }
+    const float4* e1 = reinterpret_cast<const float4*>(bank_t + (size_t)ids[0] * D);
+    float4* q4 = reinterpret_cast<float4*>(q1 + (size_t)n * D);
+    float carry = 0.f;                                      // chain `part` of the commit partial, replicated per part
+    for (int g = 0; g < chunks; g += 128) {                 // 4 chunks per lane and pass
+      float4 zv[4], ev[4];
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int i = g + 32 * jj + lane;
+        const bool ok = i < chunks;
+        zv[jj] = ok ? __ldg(z4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        ev[jj] = ok ? __ldg(e1 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int i = g + 32 * jj + lane;
+        const bool ok = i < chunks;
+        const float4 df = make_float4(ev[jj].x - zv[jj].x, ev[jj].y - zv[jj].y, ev[jj].z - zv[jj].z, ev[jj].w - zv[jj].w);
+        if (ok) {
+          q4[i] = make_float4(zv[jj].x + df.x, zv[jj].y + df.y, zv[jj].z + df.z, zv[jj].w + df.w);
+          if (read) reinterpret_cast<float4*>(read + ((size_t)n * K) * D)[i] = ev[jj];
+          if (embed_sum) {
+            atomicAdd(&embed_sum[(size_t)(4 * i + 0) * M + ids[0]], zv[jj].x);
+            atomicAdd(&embed_sum[(size_t)(4 * i + 1) * M + ids[0]], zv[jj].y);
+            atomicAdd(&embed_sum[(size_t)(4 * i + 2) * M + ids[0]], zv[jj].z);
+            atomicAdd(&embed_sum[(size_t)(4 * i + 3) * M + ids[0]], zv[jj].w);
+          }
+        }
+        if (g + 32 * jj < chunks) {                          // uniform: this group of 32 chunks exists
+#pragma unroll
+          for (int l = 0; l < 8; ++l) {
+            const float nv = chain4(carry, df, df);
+            const float pass = ((lane >> 2) == l && ok) ? nv : carry;
+            carry = __shfl_sync(0xffffffffu, pass, 4 * l + part);
+          }
+        }
+      }
+    }
+    {
+      float s = carry + __shfl_xor_sync(0xffffffffu, carry, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      if (lane == 0) sse_px[n] = s;
+    }
+    if (read) {
+#pragma unroll
+      for (int j = 1; j < K; ++j) {
+        const float4* er = reinterpret_cast<const float4*>(bank_t + (size_t)ids[j] * D);
+        float4* rr = reinterpret_cast<float4*>(read + ((size_t)n * K + j) * D);
+        for (int i = lane; i < chunks; i += 32) rr[i] = __ldg(er + i);
+      }
+    }
+    if (read_planes) {                                      // bf16 hi/lo split of the read: A operand of the `dec` GEMM
+#pragma unroll
+      for (int j = 0; j < K; ++j) {
+        const float4* er = reinterpret_cast<const float4*>(bank_t + (size_t)ids[j] * D);
+        __nv_bfloat16* hp = read_planes + ((size_t)n * K + j) * D;
+        for (int i = lane; i < chunks; i += 32) {
+          const float4 v = __ldg(er + i);
+          uint2 ph, pl;
+          ptx::split_pack_bf16x2(v.x, v.y, ph.x, pl.x);
+          ptx::split_pack_bf16x2(v.z, v.w, ph.y, pl.y);
+          *reinterpret_cast<uint2*>(hp + 4 * i) = ph;
+          *reinterpret_cast<uint2*>(hp + read_plane_stride + 4 * i) = pl;
+        }
+      }
+    }
+  }
 }
 
 // Exact scan over all M items for the (rare) rows whose candidate list overflowed: one warp per row.
@@ -511,14 +737,23 @@ int run_address_tc(const float* z, const void* zp_in, const float* zmeta_in, __n
   p.N = (int)N; p.D = D; p.M = M; p.Mpad = Mpad;
   p.tiles_q = ceil_div(N, 128);
   p.tiles_i = Mpad / bn;
-  p.en2pad = en2pad; p.zmeta = zmeta; p.emax = emax; p.cand = cand; p.cand_cnt = cand_cnt;
+  p.en2pad = en2pad; p.zmeta = zmeta; p.emax = emax; p.cand = cand; p.cand_cnt = cand_cnt; p.k = k;
   if (int rc = launch_filter(zp, bank_hi, p, bn, k, st)) return rc;
   const int blocks = ceil_div(N, 64);
+  const bool tail = D >= 128;                      // warp-per-query tail; below that a 4-lane team per query is denser
+  const int tail_blocks = min(ceil_div(N, 16), 2 * num_sms());
   switch (k) {
 #define AMMC_RF_CASE(KK)                                                                                      \
   case KK:                                                                                                    \
-    refine_kernel<KK><<<blocks, 256, 0, st>>>(z, cand, cand_cnt, bank_t, en2, read, q1, idx, sse_px, counts,  \
-                                              embed_sum, stats, rescan_list, read_planes, rps, (int)N, D, M); \
+    if (tail) {                                                                                               \
+      addr_tail_kernel<KK><<<tail_blocks, 512, 0, st>>>(                                                      \
+          z, cand, cand_cnt, bank_t, en2, read, q1, idx, sse_px, counts, embed_sum, stats, rescan_list,       \
+          read_planes, rps, (int)N, D, M);                                                                    \
+    } else {                                                                                                  \
+      refine_kernel<KK><<<blocks, 256, 0, st>>>(z, cand, cand_cnt, bank_t, en2, read, q1, idx, sse_px, counts, \
+                                                embed_sum, stats, rescan_list, read_planes, rps, (int)N, D, M); \
+    }                                                                                                         \
+    AMMC_LAUNCH_CHECK("refine_kernel / addr_tail_kernel");                                                    \
     rescan_kernel<KK><<<2 * num_sms(), 256, 0, st>>>(z, bank_t, en2, read, q1, idx, sse_px, counts, embed_sum, \
                                                      stats, rescan_list, read_planes, rps, D, M);             \
     break;
@@ -526,7 +761,7 @@ int run_address_tc(const float* z, const void* zp_in, const float* zmeta_in, __n
 #undef AMMC_RF_CASE
     default: return fail(AMMC_EUNSUPPORTED, "tensor-core addressing supports k <= 4");
   }
-  AMMC_LAUNCH_CHECK("refine_kernel");
+  AMMC_LAUNCH_CHECK("rescan_kernel");
   return 0;
 }
 
@@ -587,7 +822,7 @@ extern "C" int ammc_addr_pack_bank(const float* embed, float* bank_t, float* en2
   const int Mpad = ammc_addr_padded_items(M);
   bank_transpose_kernel<<<dim3(ceil_div(M, 32), ceil_div(D, 32)), dim3(32, 8), 0, st>>>(embed, bank_t, D, M);
   AMMC_LAUNCH_CHECK("bank_transpose_kernel");
-  bank_norms_kernel<<<ceil_div(M, 128), 128, 0, st>>>(embed, en2, D, M);
+  bank_norms_kernel<<<ceil_div(M, 32), dim3(32, 8), 0, st>>>(embed, en2, D, M);
   AMMC_LAUNCH_CHECK("bank_norms_kernel");
   return pack_bank_padded(bank_t, en2, bank_hi, en2pad, emax, D, M, Mpad, st);
 }
@@ -605,5 +840,6 @@ extern "C" int ammc_addr_filter(const void* zp, const float* zmeta, const void* 
   p.tiles_q = ceil_div(N, 128);
   p.tiles_i = p.Mpad / bn;
   p.en2pad = en2pad; p.zmeta = reinterpret_cast<const float2*>(zmeta); p.emax = emax; p.cand = cand; p.cand_cnt = cand_cnt;
+  p.k = k;
   return launch_filter(zp, bank_hi, p, bn, k, (cudaStream_t)stream);
 }

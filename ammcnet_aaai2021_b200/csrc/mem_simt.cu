@@ -43,23 +43,35 @@ __global__ void bank_transpose_kernel(const float* __restrict__ embed, float* __
   }
 }
 
-__global__ void bank_norms_kernel(const float* __restrict__ embed, float* __restrict__ en2, int D, int M) {
-  int m = blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= M) return;
+// ||e_m||^2 for every item.  Block = 32 items x 8 interleaved partial sums (d = g, g + 8, ...: independent coalesced
+// loads, 16 in flight per thread), combined in a fixed order -- deterministic, and the ONE source of the norms every
+// addressing path (fp32, tensor-core, fused front) ranks with.  Launch with dim3(32, 8) threads.
+__global__ void __launch_bounds__(256) bank_norms_kernel(const float* __restrict__ embed, float* __restrict__ en2, int D, int M) {
+  __shared__ float part[8][33];
+  const int m = blockIdx.x * 32 + threadIdx.x, g = threadIdx.y;
   float acc = 0.f;
-  int d = 0;
-  for (; d + 8 <= D; d += 8) {          // eight loads in flight, same ascending fmaf chain (M threads only: latency-bound)
-    float v[8];
+  if (m < M) {
+    int d = g;
+    for (; d + 8 * 15 < D; d += 8 * 16) {
+      float v[16];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = embed[(size_t)(d + j) * M + m];
+      for (int j = 0; j < 16; ++j) v[j] = embed[(size_t)(d + 8 * j) * M + m];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc = fmaf(v[j], v[j], acc);
+      for (int j = 0; j < 16; ++j) acc = fmaf(v[j], v[j], acc);
+    }
+    for (; d < D; d += 8) {
+      const float v = embed[(size_t)d * M + m];
+      acc = fmaf(v, v, acc);
+    }
   }
-  for (; d < D; ++d) {
-    float v = embed[(size_t)d * M + m];
-    acc = fmaf(v, v, acc);
+  part[g][threadIdx.x] = acc;
+  __syncthreads();
+  if (g == 0 && m < M) {
+    float s = part[0][threadIdx.x];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) s += part[i][threadIdx.x];
+    en2[m] = s;
   }
-  en2[m] = acc;
 }
 
 // T[j][m][c] = sum_d dec_w[c][j*D + d] * embed[d][m]
@@ -911,7 +923,7 @@ static int run_address(const float* z, const float* embed, const MemWs& m, float
   if (m.own_bank) {                                       // Quantize_topk on its own: items as rows + norms derived here
     bank_transpose_kernel<<<dim3(ceil_div(M, 32), ceil_div(D, 32)), dim3(32, 8), 0, st>>>(embed, m.bank_t, D, M);
     AMMC_LAUNCH_CHECK("bank_transpose_kernel");
-    bank_norms_kernel<<<ceil_div(M, 128), 128, 0, st>>>(embed, m.en2, D, M);
+    bank_norms_kernel<<<ceil_div(M, 32), dim3(32, 8), 0, st>>>(embed, m.en2, D, M);
     AMMC_LAUNCH_CHECK("bank_norms_kernel");
   }
   if (counts) AMMC_CUDA_CHECK(cudaMemsetAsync(counts, 0, (size_t)M * 4, st));
@@ -982,7 +994,7 @@ static int run_prepare(const MemPrep& pr, const float* enc_w, const float* embed
                        int C, int D, int M, int k, bool tc_enc, bool tc_dec, cudaStream_t st) {
   bank_transpose_kernel<<<dim3(ceil_div(M, 32), ceil_div(D, 32)), dim3(32, 8), 0, st>>>(embed, pr.bank_t, D, M);
   AMMC_LAUNCH_CHECK("bank_transpose_kernel");
-  bank_norms_kernel<<<ceil_div(M, 128), 128, 0, st>>>(embed, pr.en2, D, M);
+  bank_norms_kernel<<<ceil_div(M, 32), dim3(32, 8), 0, st>>>(embed, pr.en2, D, M);
   AMMC_LAUNCH_CHECK("bank_norms_kernel");
   if (M <= 256)
     if (int rc = pack_bank_padded(pr.bank_t, pr.en2, pr.bank_hi, pr.en2pad, pr.emax, D, M, 256, st)) return rc;

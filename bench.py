@@ -711,7 +711,8 @@ def _time(fn, iters):
 def addressing_leg(dev, peaks, peak_src):
     """BASELINE metric, second half: the addressing contraction against the tensor roofline, measured live.  Algorithmic
     FLOP = 2*N*M*D; peak = measured bf16 burst (kernel timed alone).  `filter` is the tcgen05 contraction
-    kernel, `whole_op` everything Quantize_topk.forward does (pack, filter, exact refine, reads, commit partials)."""
+    kernel, `whole_op` everything Quantize_topk.forward does (bank + query pack, filter, exact distances of the rows the
+    filter could not decide, the gathers read / q1, indices, commit partials)."""
     import ctypes
     import ammcnet_aaai2021_b200 as A
     from ammcnet_aaai2021_b200 import _capi, functions as F_
@@ -739,14 +740,15 @@ def addressing_leg(dev, peaks, peak_src):
                                        N, Di, Mi, 2, st), iters)
         q = A.Quantize_topk(Di, Mi, k=2).to(dev).eval()
         q.embed.copy_(embed)
-        z4 = z.view(1, N, 1, Di)
+        decided = float(cnt[:, 1].float().mean())
+        z4 = z.view(N // 1024, 32, 32, Di)                     # frames of 32x32 queries, as the shipped feature map
         with torch.no_grad():
             t_op = _time(lambda: q(z4), max(3, iters // 2))
             rescans = F_.last_addressing_stats()[0]
         out["points"].append({"N": N, "M": Mi, "D": Di, "filter_ms": t_f, "filter_tflops": flops / t_f / 1e9,
                               "filter_frac": flops / t_f / 1e9 / peak, "whole_op_ms": t_op,
                               "whole_op_tflops": flops / t_op / 1e9, "whole_op_frac": flops / t_op / 1e9 / peak,
-                              "exact_rescan_rows": rescans})
+                              "rows_decided_by_filter": decided, "exact_rescan_rows": rescans})
         del z, embed, zp, bank_t, bank_hi, cand, cnt, q, z4
         torch.cuda.empty_cache()
     return out

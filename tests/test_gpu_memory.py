@@ -207,7 +207,8 @@ def _quantize_both(z, embed, k, addressing_mode):
 
 
 @pytest.mark.parametrize("N,D,M,k", [(4096, 64, 256, 2), (1000, 64, 16, 1), (777, 128, 100, 3), (2048, 256, 1000, 4),
-                                      (130, 64, 2000, 2), (4096, 512, 300, 2), (65536, 64, 256, 2)])
+                                      (130, 64, 2000, 2), (4096, 512, 300, 2), (65536, 64, 256, 2),
+                                      (3000, 192, 500, 2), (2048, 1024, 600, 2), (5000, 128, 64, 1), (4100, 320, 2100, 3)])
 def test_tensor_path_bit_identical_to_fp32_path(N, D, M, k, addressing_mode):
     g = torch.Generator().manual_seed(N + D + M)
     z = torch.randn((1, N, 1, D), generator=g).to(DEV)
@@ -233,6 +234,84 @@ def test_tensor_path_adversarial_banks(addressing_mode):
     assert torch.equal(o["fp32"][0], o["tensor"][0])
     assert torch.equal(o["fp32"][1], o["tensor"][1])
     print("adversarial bank: exact re-scans", o["tensor"][5][0], "of", N)
+
+
+def test_tensor_path_adversarial_banks_wide_rows(addressing_mode):
+    """D >= 128 takes the warp-per-query tail: rows the filter decides alone (no exact distance), ambiguous rows with more
+    candidates than one staging pass holds (clusters of near-duplicates), exact duplicates (index tie-break)."""
+    g = torch.Generator().manual_seed(11)
+    D, M, N, k = 256, 512, 6000, 2
+    base = torch.randn((D, 64), generator=g)
+    embed = base.repeat(1, 8) + 1e-3 * torch.randn((D, M), generator=g)       # 64 clusters of 8 near-duplicates
+    embed[:, 9] = embed[:, 8]
+    z = embed.t()[torch.randint(0, M, (N,), generator=g)] + 1e-4 * torch.randn((N, D), generator=g)
+    z[:100] *= 1e3
+    z[100:3000] = torch.randn((2900, D), generator=g)                          # well separated rows: decided by the filter
+    o = _quantize_both(z.view(6, N // 6, 1, D).to(DEV), embed.to(DEV), k, addressing_mode)
+    a, b = o["fp32"], o["tensor"]
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[3], b[3])
+    assert torch.equal(a[4], b[4]) and torch.equal(a[2], b[2])                 # per-frame SSE and the commit scalar
+
+
+def test_filter_decides_separated_rows(addressing_mode):
+    """The staged filter entry point reports which rows it ranked without any exact distance; on random data at
+    D = 512 that is the majority, and their indices are the fp32 kernel's."""
+    import ctypes
+    from ammcnet_aaai2021_b200 import _capi
+    g = torch.Generator().manual_seed(5)
+    N, D, M, k = 8192, 512, 2048, 2
+    z = torch.randn((N, D), generator=g).to(DEV)
+    embed = torch.randn((D, M), generator=g).to(DEV)
+    lib = _capi.load()
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    Mpad = lib.ammc_addr_padded_items(M)
+    zp = torch.empty((N, D), dtype=torch.float16, device=DEV)
+    zmeta = torch.empty((N, 2), device=DEV)
+    bank_t, en2 = torch.empty((M, D), device=DEV), torch.empty((M,), device=DEV)
+    bank_hi = torch.empty((Mpad, D), dtype=torch.float16, device=DEV)
+    en2pad, emax = torch.empty((Mpad,), device=DEV), torch.empty((4,), device=DEV)
+    cand = torch.full((N, 24), -7, dtype=torch.int32, device=DEV)
+    cnt = torch.empty((N, 2), dtype=torch.int32, device=DEV)
+    _capi.call("ammc_addr_pack_queries", P(z), P(zp), P(zmeta), N, D, st)
+    _capi.call("ammc_addr_pack_bank", P(embed), P(bank_t), P(en2), P(bank_hi), P(en2pad), P(emax), D, M, st)
+    _capi.call("ammc_addr_filter", P(zp), P(zmeta), P(bank_hi), P(en2pad), P(emax), P(cand), P(cnt), N, D, M, k, st)
+    addressing_mode("fp32")
+    q = A.Quantize_topk(D, M, k=k).to(DEV).eval()
+    q.embed.copy_(embed)
+    with torch.no_grad():
+        q(z.view(8, 32, 32, D))
+    ref = q.last_idx
+    decided = cnt[:, 1] == 1
+    frac = float(decided.float().mean())
+    assert 0.3 < frac < 1.0, frac
+    assert bool((cnt[decided, 0] == k).all())
+    assert torch.equal(cand[decided][:, :k].long(), ref[decided])
+    und = ~decided
+    assert bool((cnt[und, 0] >= k).all()) and bool((cnt[und, 0] <= 24).all())
+    # every undecided row still lists the exact top-k among its candidates
+    c = cand[und].long()
+    valid = torch.arange(24, device=DEV)[None, :] < cnt[und, 0:1]
+    for j in range(k):
+        assert bool(((c == ref[und][:, j:j + 1]) & valid).any(1).all())
+
+
+def test_ema_statistics_equal_on_both_paths_wide_rows(addressing_mode):
+    g = torch.Generator().manual_seed(21)
+    N, D, M, k = 4096, 128, 300, 2
+    z = torch.randn((4, N // 4, 1, D), generator=g).to(DEV)
+    embed = torch.randn((D, M), generator=g).to(DEV)
+    res = {}
+    for mode in ("fp32", "tensor"):
+        addressing_mode(mode)
+        q = A.Quantize_topk(D, M, k=k).to(DEV).train()
+        q.embed.copy_(embed); q.embed_avg.copy_(embed)
+        q(z)
+        res[mode] = (q.last_idx.clone(), q.cluster_size.clone(), q.embed_avg.clone(), q.embed.clone())
+    assert torch.equal(res["fp32"][0], res["tensor"][0])
+    assert torch.equal(res["fp32"][1], res["tensor"][1])
+    assert_close(res["tensor"][2].cpu(), res["fp32"][2].cpu(), 1e-5, "embed_avg")
+    assert_close(res["tensor"][3].cpu(), res["fp32"][3].cpu(), 1e-5, "embed")
 
 
 def test_shipped_module_uses_tensor_path_and_matches_golden(addressing_mode):

@@ -63,12 +63,13 @@ def point(N, M, D, k=2, seed=0):
     iters = max(3, min(50, int(2e12 / flops)))
     t_filter = time_fn(lambda: _capi.call("ammc_addr_filter", P(zp), P(zn2), P(bank_hi), P(en2pad), P(emax), P(cand),
                                           P(cnt), N, D, M, k, st), iters)
-    res_cand = float((cand >= 0).sum(1).float().mean())
+    res_cand = float(cnt[:, 0].clamp(max=24).float().mean())
+    decided = float(cnt[:, 1].float().mean())
     q = A.Quantize_topk(D, M, k=k).to(DEV).eval()
     q.embed.copy_(embed)
-    z4 = z.view(1, N, 1, D)
+    z4 = z.view(N // 1024, 32, 32, D) if N % 1024 == 0 else z.view(1, N, 1, D)   # frames of 32x32 queries, as shipped
     res = {"N": N, "M": M, "D": D, "k": k, "filter_ms": t_filter, "filter_tflops": flops / t_filter / 1e9,
-           "mean_candidates": res_cand}
+           "mean_candidates": res_cand, "rows_decided_by_filter": decided}
     with torch.no_grad():
         F_.set_addressing_mode("tensor")
         res["op_tensor_ms"] = time_fn(lambda: q(z4), max(3, iters // 2))
@@ -90,8 +91,11 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--out", default=None)
+    ap.add_argument("--points", default=None, help="N,M,D;N,M,D;... instead of a built-in grid")
     args = ap.parse_args()
-    if args.quick:
+    if args.points:
+        grid = [tuple(int(v) for v in pt.split(",")) for pt in args.points.split(";")]
+    elif args.quick:
         grid = [(65536, 256, 64), (65536, 2000, 64), (262144, 1024, 128), (65536, 8192, 256), (65536, 2048, 512)]
     else:
         grid = []
