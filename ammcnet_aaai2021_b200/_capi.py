@@ -22,7 +22,7 @@ class ConvLayer(ctypes.Structure):
                 ("out_planes", c_void_p), ("out_cs", c_int), ("out_c_off", c_int),
                 ("out_nchw", c_void_p), ("res_nchw", c_void_p), ("cout_valid", c_int),
                 ("b", c_int), ("h", c_int), ("w", c_int), ("Cin", c_int), ("Cout", c_int),
-                ("up2x", c_int), ("precision", c_int), ("in_fmt", c_int), ("out_fmt", c_int)]
+                ("up2x", c_int), ("precision", c_int), ("in_fmt", c_int), ("out_fmt", c_int), ("io_bf16", c_int)]
 
 
 # name -> (restype, argtypes); must list every symbol of include/ammc_b200.h (tests/test_capi.py checks it)
@@ -34,6 +34,9 @@ SIGNATURES = {
     "ammc_mem_workspace_bytes": (Z, [I] * 7),
     "ammc_set_addressing_mode": (I, [I]),
     "ammc_mem_fwd": (I, [P] * 6 + [P] * 6 + [P, P, P, I, P] + [P, Z] + [I] * 8 + [P]),
+    "ammc_mem_io16_supported": (I, [I] * 7),
+    "ammc_mem_fwd_io16": (I, [P] * 6 + [P] * 6 + [P, I, P] + [P, Z] + [I] * 8 + [P]),
+    "ammc_cast_f32_bf16": (I, [P, P, L, P]),
     "ammc_mem_prep_bytes": (Z, [I] * 4),
     "ammc_mem_prepare": (I, [P] * 5 + [Z] + [I] * 7 + [P]),
     "ammc_set_front_mode": (I, [I]),

@@ -57,6 +57,7 @@ struct ConvParams {
   const float* out_qs;           // device scalar: power-of-two scale of the q output
   const float* in_qs;            // device scalars: scales of the q input and the q weights (PAIR_Q mode), else null
   const float* w_qs;
+  int io_bf16;                   // pair kernel: out_nchw / res_nchw point to bf16 NCHW tensors (bf16 feature-I/O variant)
   int a_reuse;                   // PAIR_Q, 3x3: one (H_box+2)-row A tile per (dx, channel block) serves the three dy taps
   const float* out_l1;           // PAIR_Q with q output: per-output-channel sum_k |w| -- the kernel derives the output scale itself
   float* out_qs_store;           // ... and CTA 0 stores it for the consumer
@@ -582,11 +583,16 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       // 16 columns at a time, software-pipelined two chunks deep: the residual loads of chunks c+1 and c+2 are in
       // flight while chunk c is converted and stored (the loads are the only latency on the epilogue's critical path)
       float rv0[16], rv1[16];
+      const bool io16 = p.io_bf16 != 0;
+      const unsigned short* const res16 = reinterpret_cast<const unsigned short*>(p.res_nchw);
+      auto load_res = [&](size_t i) -> float {
+        return io16 ? __uint_as_float((uint32_t)__ldg(res16 + i) << 16) : __ldg(p.res_nchw + i);
+      };
       if (has_res) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) rv0[j] = __ldg(p.res_nchw + obase + (size_t)j * hw);
+        for (int j = 0; j < 16; ++j) rv0[j] = load_res(obase + (size_t)j * hw);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) rv1[j] = __ldg(p.res_nchw + obase + (size_t)(16 + j) * hw);
+        for (int j = 0; j < 16; ++j) rv1[j] = load_res(obase + (size_t)(16 + j) * hw);
       }
       ptx::mbar_wait(&tmem_full[acc], acc_ph, 44);        // the first residual loads overlap the tail of the MMAs
       ptx::tc_fence_after();
@@ -616,13 +622,19 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           if (has_res && cc + 2 < HALF_N / 16) {          // refill this buffer with the chunk two steps ahead
             const size_t on = obase + (size_t)(cc + 2) * 16 * hw;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) rv[j] = __ldg(p.res_nchw + on + (size_t)j * hw);
+            for (int j = 0; j < 16; ++j) rv[j] = load_res(on + (size_t)j * hw);
           }
           if (valid) {
             if (p.out_nchw) {
               size_t o = oc;
+              if (io16) {                                       // the operand planes below keep the unrounded fp32 value
+                __nv_bfloat16* const o16 = reinterpret_cast<__nv_bfloat16*>(p.out_nchw);
 #pragma unroll
-              for (int j = 0; j < 16; ++j) { p.out_nchw[o] = __uint_as_float(v[j]); o += hw; }
+                for (int j = 0; j < 16; ++j) { o16[o] = __float2bfloat16_rn(__uint_as_float(v[j])); o += hw; }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { p.out_nchw[o] = __uint_as_float(v[j]); o += hw; }
+              }
             }
             if (p.out_fmt == 1) {
               // q planes: 16 channels = 32 B of fp16 + 16 B of h8 + 16 B of l8
@@ -934,7 +946,7 @@ int conv_run(const ammc_conv_layer& L, cudaStream_t st) {
                                  L.out_c_off + (L.up2x ? up_cout : cout_valid) <= out_cs),
                "output channel window does not fit a %d-channel buffer (8-channel alignment)", out_cs);
   AMMC_REQUIRE(!L.out_planes || cout_valid == Cout, "NHWC plane output needs cout_valid == Cout");
-  if (L.precision != 2 && L.out_fmt == 0 && halo_conv_applies(L)) return halo_conv_run(L, st);   // wide, shallow layers
+  if (L.precision != 2 && L.out_fmt == 0 && !L.io_bf16 && halo_conv_applies(L)) return halo_conv_run(L, st);   // wide, shallow layers
   ConvParams p;
   p.b = b; p.H = h; p.W = w; p.Cin = Cin; p.Cout = Cout;
   // one TMA box = W_box x H_box x B_box pixels <= 128: whole rows, as many as fit; whole images when a full image
@@ -958,6 +970,7 @@ int conv_run(const ammc_conv_layer& L, cudaStream_t st) {
   p.out_plane_stride = (long long)b * h * w * (L.up2x ? 4 : 1) * out_cs;
   p.out_nchw = L.out_nchw;
   p.res_nchw = L.res_nchw;
+  p.io_bf16 = L.io_bf16 ? 1 : 0;
   p.cout_valid = cout_valid;
   p.out_fmt = 0; p.out_q16 = nullptr; p.out_q8 = nullptr; p.out_q8_stride = 0; p.out_qs = nullptr;
   p.in_qs = nullptr; p.w_qs = nullptr; p.out_l1 = nullptr; p.out_qs_store = nullptr;
@@ -1019,6 +1032,8 @@ int conv_run(const ammc_conv_layer& L, cudaStream_t st) {
   const bool pair = block_n == 256 && (g_conv_pair_mode || qmode || L.out_fmt == 1) && L.act != 2 && cout_valid == Cout &&
                     (!L.up2x || up_cout % 128 == 0);
   AMMC_REQUIRE(pair || (!qmode && L.out_fmt == 0), "q-format operands need the CTA-pair kernel (Cout %% 256 == 0)");
+  if (L.io_bf16 && !pair)
+    return fail(AMMC_EUNSUPPORTED, "bf16 NCHW output / residual needs the CTA-pair kernel (Cout %% 256 == 0, act 0/1)");
   if (!qmode) {
     // B boxes are per-CTA halves (128 channels) in the pair kernel
     const cuuint64_t K = (cuuint64_t)ntaps * Cin;

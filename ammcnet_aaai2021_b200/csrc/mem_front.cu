@@ -84,7 +84,10 @@ __device__ __forceinline__ void mf_sel_insert(float (&m)[KSEL], float x) {
   }
 }
 
-template <int K, bool AMAX>
+// XBF16: x arrives as bf16 NCHW (the bf16 feature-I/O variant, BASELINE configs[2]).  The staging boxes are half as large,
+// the converters copy the values into the hi tile unchanged (x = hi exactly, lo = 0) and the lo.Whi MMA is skipped -- it
+// would add exact zeros, so z and everything after it is bit-identical to the fp32 kernel fed the widened tensor.
+template <int K, bool AMAX, bool XBF16>
 __global__ void __launch_bounds__(MF_THREADS, 1)
 mem_front_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                  const __grid_constant__ CUtensorMap tmBank, const FrontParams p) {
@@ -149,7 +152,7 @@ mem_front_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           for (int h = 0; h < 2; ++h, ++kx) {
             const int sx = kx & 3;
             ptx::mbar_wait(&x_empty[sx], ((kx >> 2) & 1) ^ 1, 61);
-            ptx::mbar_expect_tx(&x_full[sx], MF_X_STAGE);
+            ptx::mbar_expect_tx(&x_full[sx], XBF16 ? MF_X_STAGE / 2 : MF_X_STAGE);
             ptx::tma_load_3d(smem + sx * MF_X_STAGE, &tmX, &x_full[sx], p0, kb * MF_BK + 32 * h, img);
           }
           ptx::mbar_wait(&aw_free[sa], pha ^ 1, 62);
@@ -200,7 +203,7 @@ mem_front_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         for (int k4 = 0; k4 < MF_BK / 16; ++k4) {
           ptx::mma_f16_ss_warp(d_tmem, a_hi + 2 * k4, w_hi + 2 * k4, idesc_enc, (kb | k4) != 0 ? 1u : 0u);
           ptx::mma_f16_ss_warp(d_tmem, a_hi + 2 * k4, w_lo + 2 * k4, idesc_enc, 1u);
-          ptx::mma_f16_ss_warp(d_tmem, a_lo + 2 * k4, w_hi + 2 * k4, idesc_enc, 1u);
+          if (!XBF16) ptx::mma_f16_ss_warp(d_tmem, a_lo + 2 * k4, w_hi + 2 * k4, idesc_enc, 1u);
         }
         ptx::mma_commit_warp(&aw_free[s]);
         if (kb == kb_per_tile - 1) ptx::mma_commit_warp(&tmem_full[acc]);
@@ -220,25 +223,36 @@ mem_front_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         const int sx = half + 2 * (kx & 1);
         ptx::mbar_wait(&x_full[sx], (uint32_t)((kx >> 1) & 1), 68);
         ptx::mbar_wait(&aw_free[sa], pha ^ 1, 69);
-        const uint32_t xs = ptx::smem_u32(smem + sx * MF_X_STAGE) + row * 4;                     // [32 ch][128 px] fp32
+        const uint32_t xs = ptx::smem_u32(smem + sx * MF_X_STAGE) + row * (XBF16 ? 2 : 4);   // [32 ch][128 px]
         const uint32_t a_hi = ptx::smem_u32(smem + MF_AW_OFFSET + sa * MF_AW_STAGE) + row * 128;
         const uint32_t a_lo = a_hi + MF_STAGE_A;
 #pragma unroll
         for (int c8l = 0; c8l < 4; ++c8l) {
-          float v[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = ptx::lds_f32(xs + (c8l * 8 + j) * 512);
-          if (AMAX) {
-#pragma unroll
-            for (int j = 0; j < 8; j += 2) amax = fmaxf(amax, fmaxf(fabsf(v[j]), fabsf(v[j + 1])));
-          }
-          uint32_t hp[4], lp[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) ptx::split_pack_bf16x2(v[2 * j], v[2 * j + 1], hp[j], lp[j]);
           const int c8 = half * 4 + c8l;                               // 16-byte chunk of the 128-byte row
           const uint32_t chunk = (uint32_t)((c8 ^ (row & 7)) * 16);   // 128B swizzle
-          ptx::sts_v4(a_hi + chunk, hp[0], hp[1], hp[2], hp[3]);
-          ptx::sts_v4(a_lo + chunk, lp[0], lp[1], lp[2], lp[3]);
+          if (XBF16) {
+            uint32_t b[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) b[j] = ptx::lds_u16(xs + (c8l * 8 + j) * 256);
+            if (AMAX) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) amax = fmaxf(amax, fabsf(__uint_as_float(b[j] << 16)));
+            }
+            ptx::sts_v4(a_hi + chunk, b[0] | (b[1] << 16), b[2] | (b[3] << 16), b[4] | (b[5] << 16), b[6] | (b[7] << 16));
+          } else {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = ptx::lds_f32(xs + (c8l * 8 + j) * 512);
+            if (AMAX) {
+#pragma unroll
+              for (int j = 0; j < 8; j += 2) amax = fmaxf(amax, fmaxf(fabsf(v[j]), fabsf(v[j + 1])));
+            }
+            uint32_t hp[4], lp[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) ptx::split_pack_bf16x2(v[2 * j], v[2 * j + 1], hp[j], lp[j]);
+            ptx::sts_v4(a_hi + chunk, hp[0], hp[1], hp[2], hp[3]);
+            ptx::sts_v4(a_lo + chunk, lp[0], lp[1], lp[2], lp[3]);
+          }
         }
         ptx::mbar_arrive(&x_empty[sx]);
         ptx::fence_proxy_async();
@@ -485,18 +499,19 @@ bool mem_front_supported(int b, int HW, int C, int D, int M, int k) {
          k <= M;
 }
 
-// x [b][C][HW] fp32; enc_wp [2][64][C] bf16 planes; bank_hi [256][64] bf16 (zero rows beyond M); en2pad [256]; others as
+// x [b][C][HW] fp32 (x_bf16 = 0) or bf16 (1); enc_wp [2][64][C] bf16 planes; bank_hi [256][64] bf16 (zero rows beyond M); en2pad [256]; others as
 // FrontParams.  stats[0], stats[2] must be zero on entry.
-int run_mem_front(const float* x, const void* enc_wp, const float* enc_b, const void* bank_hi, const float* bank_t,
+int run_mem_front(const void* x, int x_bf16, const void* enc_wp, const float* enc_b, const void* bank_hi, const float* bank_t,
                   const float* en2, const float* en2pad, const float* emax, float* z, float* q1, int64_t* idx, float* sse_px,
                   __nv_bfloat16* read_planes, int* stats, int* rescan_list, unsigned* amax_bits, int b, int HW, int C, int M,
                   int k, cudaStream_t st) {
   CUtensorMap tmX, tmW, tmBank;
   {
     uint64_t dims[3] = {(uint64_t)HW, (uint64_t)C, (uint64_t)b};
-    uint64_t strides[2] = {(uint64_t)HW * 4, (uint64_t)C * HW * 4};
+    const uint64_t eb = x_bf16 ? 2 : 4;
+    uint64_t strides[2] = {(uint64_t)HW * eb, (uint64_t)C * HW * eb};
     uint32_t box[3] = {128, 32, 1};
-    if (int rc = make_map_generic(&tmX, x, 4, 3, dims, strides, box, 0)) return rc;
+    if (int rc = make_map_generic(&tmX, x, (int)eb, 3, dims, strides, box, 0)) return rc;
   }
   {
     uint64_t dims[3] = {(uint64_t)C, (uint64_t)MF_D, 2};
@@ -521,27 +536,29 @@ int run_mem_front(const float* x, const void* enc_wp, const float* enc_b, const 
   int dev = 0;
   AMMC_CUDA_CHECK(cudaGetDevice(&dev));
   const int grid = min(num_sms(), p.tiles);
-#define AMMC_MF_LAUNCH(KK, AM) mem_front_kernel<KK, AM><<<grid, MF_THREADS, MF_SMEM, st>>>(tmX, tmW, tmBank, p)
+#define AMMC_MF_LAUNCH(KK, AM, XB) mem_front_kernel<KK, AM, XB><<<grid, MF_THREADS, MF_SMEM, st>>>(tmX, tmW, tmBank, p)
+#define AMMC_MF_ATTR(KK, AM, XB)                                                                                          \
+  AMMC_CUDA_CHECK(cudaFuncSetAttribute(mem_front_kernel<KK, AM, XB>, cudaFuncAttributeMaxDynamicSharedMemorySize, MF_SMEM))
   // the attribute must be set for every instantiation that may run on this device: set all of them once
   if (dev >= 0 && dev < 64 && !configured[dev]) {
-    AMMC_CUDA_CHECK(cudaFuncSetAttribute(mem_front_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MF_SMEM));
-    AMMC_CUDA_CHECK(cudaFuncSetAttribute(mem_front_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MF_SMEM));
-    AMMC_CUDA_CHECK(cudaFuncSetAttribute(mem_front_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MF_SMEM));
-    AMMC_CUDA_CHECK(cudaFuncSetAttribute(mem_front_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MF_SMEM));
-    AMMC_CUDA_CHECK(cudaFuncSetAttribute(mem_front_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MF_SMEM));
-    AMMC_CUDA_CHECK(cudaFuncSetAttribute(mem_front_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MF_SMEM));
-    AMMC_CUDA_CHECK(cudaFuncSetAttribute(mem_front_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MF_SMEM));
-    AMMC_CUDA_CHECK(cudaFuncSetAttribute(mem_front_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MF_SMEM));
+    AMMC_MF_ATTR(1, false, false); AMMC_MF_ATTR(1, true, false); AMMC_MF_ATTR(2, false, false); AMMC_MF_ATTR(2, true, false);
+    AMMC_MF_ATTR(3, false, false); AMMC_MF_ATTR(3, true, false); AMMC_MF_ATTR(4, false, false); AMMC_MF_ATTR(4, true, false);
+    AMMC_MF_ATTR(1, false, true); AMMC_MF_ATTR(1, true, true); AMMC_MF_ATTR(2, false, true); AMMC_MF_ATTR(2, true, true);
+    AMMC_MF_ATTR(3, false, true); AMMC_MF_ATTR(3, true, true); AMMC_MF_ATTR(4, false, true); AMMC_MF_ATTR(4, true, true);
     configured[dev] = true;
   }
   const bool am = amax_bits != nullptr;
+#define AMMC_MF_CASE(KK)                                                                        \
+  case KK:                                                                                      \
+    if (x_bf16) { if (am) AMMC_MF_LAUNCH(KK, true, true); else AMMC_MF_LAUNCH(KK, false, true); } \
+    else { if (am) AMMC_MF_LAUNCH(KK, true, false); else AMMC_MF_LAUNCH(KK, false, false); }     \
+    break;
   switch (k) {
-    case 1: if (am) AMMC_MF_LAUNCH(1, true); else AMMC_MF_LAUNCH(1, false); break;
-    case 2: if (am) AMMC_MF_LAUNCH(2, true); else AMMC_MF_LAUNCH(2, false); break;
-    case 3: if (am) AMMC_MF_LAUNCH(3, true); else AMMC_MF_LAUNCH(3, false); break;
-    case 4: if (am) AMMC_MF_LAUNCH(4, true); else AMMC_MF_LAUNCH(4, false); break;
+    AMMC_MF_CASE(1) AMMC_MF_CASE(2) AMMC_MF_CASE(3) AMMC_MF_CASE(4)
     default: return fail(AMMC_EUNSUPPORTED, "fused memory front supports k <= 4");
   }
+#undef AMMC_MF_CASE
+#undef AMMC_MF_ATTR
 #undef AMMC_MF_LAUNCH
   AMMC_LAUNCH_CHECK("mem_front_kernel");
   return 0;

@@ -778,7 +778,7 @@ int pack_bank_padded(const float* bank_t, const float* en2, void* bank_hi, float
                      cudaStream_t st);
 // mem_front.cu
 bool mem_front_supported(int b, int HW, int C, int D, int M, int k);
-int run_mem_front(const float* x, const void* enc_wp, const float* enc_b, const void* bank_hi, const float* bank_t,
+int run_mem_front(const void* x, int x_bf16, const void* enc_wp, const float* enc_b, const void* bank_hi, const float* bank_t,
                   const float* en2, const float* en2pad, const float* emax, float* z, float* q1, int64_t* idx, float* sse_px,
                   __nv_bfloat16* read_planes, int* stats, int* rescan_list, unsigned* amax_bits, int b, int HW, int C, int M,
                   int k, cudaStream_t st);
@@ -1030,11 +1030,14 @@ extern "C" int ammc_set_front_mode(int on) {
   return 0;
 }
 
-extern "C" int ammc_mem_fwd(const float* x, const float* enc_w, const float* enc_b, const float* embed,
-                            const float* dec_w, const float* dec_b, float* out, float* q1, int64_t* idx, float* z,
-                            float* sse_frame, float* diff, float* counts, float* embed_sum, void* out_planes,
-                            int planes_fmt, const void* prep, void* workspace, size_t workspace_bytes, int b, int h, int w,
-                            int C, int D, int M, int k, int residual, void* stream) {
+// io16: x_any / out_any are bf16 NCHW (ammc_mem_fwd_io16), else fp32
+static int mem_fwd_impl(const void* x_any, const float* enc_w, const float* enc_b, const float* embed,
+                        const float* dec_w, const float* dec_b, void* out_any, float* q1, int64_t* idx, float* z,
+                        float* sse_frame, float* diff, float* counts, float* embed_sum, void* out_planes,
+                        int planes_fmt, const void* prep, void* workspace, size_t workspace_bytes, int b, int h, int w,
+                        int C, int D, int M, int k, int residual, int io16, void* stream) {
+  const float* x = reinterpret_cast<const float*>(x_any);     // only dereferenced as fp32 when io16 == 0
+  float* out = reinterpret_cast<float*>(out_any);
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t N = (int64_t)b * h * w;
   const int HW = h * w;
@@ -1077,12 +1080,15 @@ extern "C" int ammc_mem_fwd(const float* x, const float* enc_w, const float* enc
   // fused enc + addressing (eval): z, candidates and scores never leave the SM
   const bool front = g_front_mode && tc_enc && tc_dec && !counts && !embed_sum && g_addr_mode != 1 &&
                      mem_front_supported(b, HW, C, D, M, k);
+  if (io16 && !front)
+    return fail(AMMC_EUNSUPPORTED, "bf16 feature I/O runs on the fused front kernel + tensor-core dec only "
+                                   "(embed_dim 64, n_embed <= 256, h*w %% 128 == 0, eval); widen the input instead");
   if (front) {
     int* rescan_list = ws.take<int>(N);
     if (!ws.ok()) return fail(AMMC_EWORKSPACE, "workspace too small");
     AMMC_CUDA_CHECK(cudaMemsetAsync(m.stats, 0, 32, st));
     AMMC_CUDA_CHECK(cudaMemsetAsync(m.stats + 1, 3, 1, st));            // path id 3: fused front kernel
-    if (int rc = run_mem_front(x, pr.enc_wp, enc_b, pr.bank_hi, pr.bank_t, pr.en2, pr.en2pad, pr.emax, z, q1, idx, m.sse_px,
+    if (int rc = run_mem_front(x_any, io16, pr.enc_wp, enc_b, pr.bank_hi, pr.bank_t, pr.en2, pr.en2pad, pr.emax, z, q1, idx, m.sse_px,
                                m.read_planes, m.stats, rescan_list, (q_planes && residual) ? amax_bits : nullptr, b, HW, C,
                                M, k, st))
       return rc;
@@ -1120,6 +1126,7 @@ extern "C" int ammc_mem_fwd(const float* x, const float* enc_w, const float* enc
     L.in_planes = m.read_planes; L.wp = pr.dec_wp; L.taps = 1; L.scale = pr.ones; L.shift = dec_b; L.act = 0;
     L.out_planes = out_planes; L.out_nchw = out; L.res_nchw = res;
     L.b = b; L.h = h; L.w = w; L.Cin = k * D; L.Cout = C; L.precision = 3;
+    L.io_bf16 = io16;                   // residual x and `out` as bf16 NCHW
     if (q_planes) L.out_fmt = 1;        // its scale was written by the commit kernel above
     return conv_run(L, st);
   }
@@ -1134,6 +1141,34 @@ extern "C" int ammc_mem_fwd(const float* x, const float* enc_w, const float* enc
   }
   AMMC_LAUNCH_CHECK("dec_gather_kernel");
   return 0;
+}
+
+extern "C" int ammc_mem_fwd(const float* x, const float* enc_w, const float* enc_b, const float* embed,
+                            const float* dec_w, const float* dec_b, float* out, float* q1, int64_t* idx, float* z,
+                            float* sse_frame, float* diff, float* counts, float* embed_sum, void* out_planes,
+                            int planes_fmt, const void* prep, void* workspace, size_t workspace_bytes, int b, int h, int w,
+                            int C, int D, int M, int k, int residual, void* stream) {
+  return mem_fwd_impl(x, enc_w, enc_b, embed, dec_w, dec_b, out, q1, idx, z, sse_frame, diff, counts, embed_sum, out_planes,
+                      planes_fmt, prep, workspace, workspace_bytes, b, h, w, C, D, M, k, residual, 0, stream);
+}
+
+extern "C" int ammc_mem_io16_supported(int b, int h, int w, int C, int D, int M, int k) {
+  if (b <= 0 || h <= 0 || w <= 0 || C <= 0 || D <= 0 || M <= 0 || k <= 0) return 0;
+  const bool tc_enc = g_enc_mode != 1 && enc_tc_supported(b, h * w, C, D);
+  return (g_front_mode && tc_enc && use_tc_dec(b, h, w, C, D, k) && g_addr_mode != 1 && C % 256 == 0 &&
+          mem_front_supported(b, h * w, C, D, M, k)) ? 1 : 0;
+}
+
+extern "C" int ammc_mem_fwd_io16(const void* x_bf16, const float* enc_w, const float* enc_b, const float* embed,
+                                 const float* dec_w, const float* dec_b, void* out_bf16, float* q1, int64_t* idx, float* z,
+                                 float* sse_frame, float* diff, void* out_planes, int planes_fmt, const void* prep,
+                                 void* workspace, size_t workspace_bytes, int b, int h, int w, int C, int D, int M, int k,
+                                 int residual, void* stream) {
+  if (!ammc_mem_io16_supported(b, h, w, C, D, M, k))
+    return fail(AMMC_EUNSUPPORTED, "bf16 feature I/O needs embed_dim 64, n_embed <= 256, C %% 256 == 0, h*w %% 128 == 0 "
+                                   "(got C=%d D=%d M=%d h*w=%d); widen the input and call ammc_mem_fwd", C, D, M, h * w);
+  return mem_fwd_impl(x_bf16, enc_w, enc_b, embed, dec_w, dec_b, out_bf16, q1, idx, z, sse_frame, diff, nullptr, nullptr,
+                      out_planes, planes_fmt, prep, workspace, workspace_bytes, b, h, w, C, D, M, k, residual, 1, stream);
 }
 
 extern "C" int ammc_mem_dec_uses_tensor(int b, int h, int w, int C, int D, int M, int k) {

@@ -263,6 +263,56 @@ def mem_forward_raw(x, enc_w, enc_b, embed, dec_w, dec_b, k: int, residual: bool
     return dict(out=out, q1=q1, idx=idx, z=z, sse_frame=sse, diff=diff, counts=counts, embed_sum=esum, x=x)
 
 
+def mem_forward_io16(x, enc_w, enc_b, embed, dec_w, dec_b, k: int, residual: bool, want_planes=False,
+                     prep: Optional[torch.Tensor] = None):
+    """bf16 feature-I/O variant of the module forward (BASELINE configs[2]; eval): x, out bf16 NCHW, everything else as
+    mem_forward_raw.  Shapes the fused front kernel serves run natively (`ammc_mem_fwd_io16`: x enters the enc GEMM as its
+    own bf16 hi plane, residual + bias summed in fp32, one rounding at the store); other shapes widen / narrow around the
+    fp32 kernels.  Either way idx, q1, z, diff and the operand planes equal the fp32 path's on the widened input."""
+    from .preprocess import widen_bf16, narrow_bf16
+    if not x.is_cuda or x.dtype != torch.bfloat16 or x.dim() != 4:
+        raise RuntimeError("ammc_b200: mem_forward_io16 needs a CUDA bfloat16 [b, C, h, w] tensor")
+    want_planes = "bf16" if want_planes is True else want_planes
+    _require_cuda_f32(enc_w, enc_b, embed, dec_w, dec_b, names=("enc.weight", "enc.bias", "embed", "dec.weight", "dec.bias"))
+    _check_device(x.device)
+    x = x.contiguous()
+    b, C, h, w = x.shape
+    D, M = embed.shape
+    lib = _capi.load()
+    if not lib.ammc_mem_io16_supported(b, h, w, C, D, M, k):
+        r = mem_forward_raw(widen_bf16(x), enc_w, enc_b, embed, dec_w, dec_b, k, residual, False, want_planes=want_planes,
+                            prep=prep)
+        out = narrow_bf16(r["out"])
+        planes = planes_of(r["out"], "q") or planes_of(r["out"], "bf16")
+        if planes is not None:
+            attach_planes(out, planes)
+        r["out"], r["x"] = out, x
+        return r
+    if enc_w.shape[0] != D or enc_w.shape[1] != C or dec_w.shape[0] != C or dec_w.shape[1] != k * D:
+        raise RuntimeError("ammc_b200: inconsistent memory-module parameter shapes")
+    N = b * h * w
+    dev = x.device
+    out = torch.empty_like(x)
+    q1 = torch.empty((N, D), dtype=torch.float32, device=dev)
+    idx = torch.empty((N, k), dtype=torch.int64, device=dev)
+    z = torch.empty((N, D), dtype=torch.float32, device=dev)
+    sse = torch.empty((b,), dtype=torch.float32, device=dev)
+    diff = torch.empty((1,), dtype=torch.float32, device=dev)
+    planes = None
+    if want_planes:
+        planes = QPlanes.empty(b, h, w, C, dev) if want_planes == "q" else torch.empty((2, b, h, w, C), dtype=torch.bfloat16, device=dev)
+    ws = _workspace(lib.ammc_mem_workspace_bytes(b, h, w, C, D, M, k), dev)
+    with torch.cuda.device(dev):
+        _capi.call("ammc_mem_fwd_io16", _p(x), _p(enc_w.contiguous()), _p(enc_b.contiguous()), _p(embed.contiguous()),
+                   _p(dec_w.contiguous()), _p(dec_b.contiguous()), _p(out), _p(q1), _p(idx), _p(z), _p(sse), _p(diff),
+                   _p(planes), int(isinstance(planes, QPlanes)), _p(prep), _p(ws), ws.numel(), b, h, w, C, D, M, k,
+                   int(bool(residual)), _stream())
+    _count(4 if prep is not None else 12)
+    if planes is not None:
+        attach_planes(out, planes)
+    return dict(out=out, q1=q1, idx=idx, z=z, sse_frame=sse, diff=diff, counts=None, embed_sum=None, x=x)
+
+
 def check_pipeline_watchdog():
     """Synchronise and raise if a tcgen05 pipeline wait hit its bound (a kernel bug, never expected in production; the
     waiting thread traps, so the failure also surfaces on the next CUDA call of any kind)."""
@@ -536,6 +586,18 @@ def conv3x3_bn_relu(xp, wp, scale, shift, *, to_planes: bool, residual: Optional
         out_p = QPlanes.empty(b, h, w, Cout, dev)
     else:
         out_p = torch.empty((2, b, h, w, Cout), dtype=torch.bfloat16, device=dev)
+    if residual is not None and residual.dtype == torch.bfloat16 and not to_planes:
+        # bf16 feature-I/O variant: bf16 residual in, bf16 NCHW out (fp32 sum, one rounding at the store)
+        if not residual.is_cuda:
+            raise RuntimeError("ammc_b200: residual must live on a CUDA device (there is no CPU path)")
+        if Cout % 256 == 0:
+            out16 = torch.empty((b, Cout, h, w), dtype=torch.bfloat16, device=dev)
+            conv_layer(xp, wp, scale, shift, taps=taps, act=int(bool(relu)), out_nchw=out16, residual=residual.contiguous(),
+                       precision=precision, io_bf16=True)
+            return out16
+        from .preprocess import widen_bf16, narrow_bf16
+        return narrow_bf16(conv3x3_bn_relu(xp, wp, scale, shift, to_planes=False, residual=widen_bf16(residual),
+                                           precision=precision, relu=relu))
     out_n = None if to_planes else torch.empty((b, Cout, h, w), dtype=torch.float32, device=dev)
     if residual is not None:
         _require_cuda_f32(residual, names=("residual",))
@@ -558,8 +620,8 @@ def conv3x3_bn_relu(xp, wp, scale, shift, *, to_planes: bool, residual: Optional
 # --------------------------------------------------------------------------------------------------
 def conv_layer(in_planes, wp, scale, shift, *, taps: int = 9, act: int = 1, Cin: Optional[int] = None, in_c_off: int = 0,
                out_planes=None, out_c_off: int = 0, out_nchw=None, residual=None, cout_valid: int = 0,
-               up2x: bool = False, precision: int = 3):
-    """One launch of `ammc_conv_layer_run`.  in_planes [2,b,h,w,in_cs] bf16 (channel window [in_c_off, +Cin));
+               up2x: bool = False, precision: int = 3, io_bf16: bool = False):
+    """One launch of `ammc_conv_layer_run`.  io_bf16: out_nchw / residual are bf16 NCHW tensors (CTA-pair kernel only).  in_planes [2,b,h,w,in_cs] bf16 (channel window [in_c_off, +Cin));
     wp [2,Cout,taps*Cin]; out_planes [2,b,ho,wo,out_cs] (written at out_c_off) and/or out_nchw [b,cout_valid,h,w]."""
     q_in = isinstance(in_planes, QPlanes)
     if q_in != (precision == 2):
@@ -587,13 +649,16 @@ def conv_layer(in_planes, wp, scale, shift, *, taps: int = 9, act: int = 1, Cin:
         if tuple(out_planes.shape[:4]) != (2, b, ho, wo) or out_planes.dtype != torch.bfloat16:
             raise RuntimeError("ammc_b200: out_planes must be bf16 [2,%d,%d,%d,cs], got %s" % (b, ho, wo, tuple(out_planes.shape)))
         L.out_planes, L.out_cs, L.out_c_off = out_planes.data_ptr(), out_planes.shape[4], out_c_off
+    want = torch.bfloat16 if io_bf16 else torch.float32
+    for nm, t in (("out_nchw", out_nchw), ("residual", residual)):
+        if t is not None and (not t.is_cuda or t.dtype != want):
+            raise RuntimeError("ammc_b200: %s must be a CUDA %s tensor, got %s on %s" % (nm, want, t.dtype, t.device))
     if out_nchw is not None:
-        _require_cuda_f32(out_nchw, names=("out_nchw",))
         L.out_nchw = out_nchw.data_ptr()
     if residual is not None:
-        _require_cuda_f32(residual, names=("residual",))
         residual = residual.contiguous()
         L.res_nchw = residual.data_ptr()
+    L.io_bf16 = int(bool(io_bf16))
     L.cout_valid = cout_valid
     L.b, L.h, L.w, L.Cin, L.Cout = b, h, w, Cin, Cout
     L.up2x, L.precision, L.in_fmt = int(bool(up2x)), int(precision), int(q_in)
@@ -822,6 +887,10 @@ class AmftBranchFn(torch.autograd.Function):
 # --------------------------------------------------------------------------------------------------
 def psnr_per_frame(gen: torch.Tensor, gt: torch.Tensor) -> torch.Tensor:
     """[n, ...] x 2 -> psnr[n]; the batched form of the reference's per-frame psnr_error calls."""
+    if gen.is_cuda and gen.dtype == torch.bfloat16 or gt.is_cuda and gt.dtype == torch.bfloat16:
+        from .preprocess import widen_bf16           # bf16 frame I/O: widened exactly, PSNR itself in fp32
+        gen = widen_bf16(gen) if gen.dtype == torch.bfloat16 else gen
+        gt = widen_bf16(gt) if gt.dtype == torch.bfloat16 else gt
     _require_cuda_f32(gen, gt, names=("gen_frames", "gt_frames"))
     if gen.shape != gt.shape:
         raise RuntimeError("ammc_b200: psnr needs equal shapes, got %s vs %s (the reference's broadcasting op-stream "

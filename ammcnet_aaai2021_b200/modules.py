@@ -50,6 +50,9 @@ class Quantize_topk(nn.Module):
         F_.ema_update_(self.embed, self.cluster_size, self.embed_avg, counts, embed_sum, self.decay, self.eps)
 
     def forward(self, input):
+        if input.dtype == torch.bfloat16 and input.is_cuda and not self.training:
+            from .preprocess import widen_bf16        # bf16 feature I/O: queries widened exactly, outputs stay fp32
+            input = widen_bf16(input)
         read, diff, q1, idx, sse, counts, esum = F_.QuantizeFn.apply(input, self.embed, self.k, self.training)
         self.last_idx, self.last_sse_frame = idx, sse
         if self.training:
@@ -89,7 +92,23 @@ class enc_quan_dec_topk(nn.Module):
             object.__setattr__(self, "_prep", hit)
         return hit[1]
 
+    def _run_io16(self, x, residual):
+        """bf16 feature I/O (BASELINE configs[2]): bf16 NCHW in, bf16 NCHW out; eval / no-grad only."""
+        q = self.quantize
+        if self.training or (torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))):
+            raise RuntimeError("ammc_b200: bfloat16 feature I/O is an inference variant; train with float32 tensors "
+                               "(or under torch.no_grad() / with frozen parameters)")
+        D = q.embed.shape[0]
+        r = F_.mem_forward_io16(x, self.enc.weight.detach().reshape(D, -1), self.enc.bias.detach(), q.embed,
+                                self.dec.weight.detach().reshape(self.dec.weight.shape[0], -1), self.dec.bias.detach(),
+                                q.k, residual, want_planes=self.planes_format or False, prep=self.prepared(x))
+        q.last_idx, q.last_sse_frame = r["idx"], r["sse_frame"]
+        b, _, h, w = x.shape
+        return r["out"], r["diff"], r["q1"].view(b, h, w, D)
+
     def _run(self, x, residual):
+        if x.dtype == torch.bfloat16 and x.is_cuda and x.dim() == 4:
+            return self._run_io16(x, residual)
         q = self.quantize
         want_planes = False if (self.training or torch.is_grad_enabled()) else (self.planes_format or False)
         prep = self.prepared(x) if (x.is_cuda and x.dim() == 4 and not self.training) else None
@@ -187,6 +206,14 @@ class bridge(nn.Module):
     def forward(self, zx, zy):
         needs_graph = torch.is_grad_enabled() and (zx.requires_grad or zy.requires_grad or
                                                    any(p.requires_grad for p in self.parameters()))
+        io16 = zx.dtype == torch.bfloat16 or zy.dtype == torch.bfloat16
+        if io16:
+            # bf16 feature I/O (BASELINE configs[2]): operand planes as usual (written unrounded by the memory modules' dec
+            # epilogue when attached), residuals read and results written as bf16 NCHW by the last conv's epilogue
+            if zx.dtype != zy.dtype:
+                raise RuntimeError("ammc_b200: bridge inputs must share one dtype, got %s and %s" % (zx.dtype, zy.dtype))
+            if self.training or needs_graph:
+                raise RuntimeError("ammc_b200: bfloat16 feature I/O is an inference variant; train with float32 tensors")
         if self.training or needs_graph:
             # batch-statistic BN and/or autograd: unfused pipeline (raw conv -> BN stats -> apply), tcgen05 dgrad/wgrad
             prec = 3 if self.precision == 2 else self.precision
@@ -198,6 +225,10 @@ class bridge(nn.Module):
         fmt, pack = ("q", F_.pack_nhwc_q) if prec == 2 else ("bf16", F_.pack_nhwc)
         px = F_.planes_of(zx, fmt)
         py = F_.planes_of(zy, fmt)
+        if io16 and (px is None or py is None):
+            from .preprocess import widen_bf16
+            px = pack(widen_bf16(zx)) if px is None else px
+            py = pack(widen_bf16(zy)) if py is None else py
         px = pack(zx) if px is None else px
         py = pack(zy) if py is None else py
         # the two branches are independent: issued on two CUDA streams, the persistent conv kernels of one branch take over

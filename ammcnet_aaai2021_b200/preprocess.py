@@ -68,6 +68,20 @@ def widen_bf16(t: torch.Tensor, out: torch.Tensor = None) -> torch.Tensor:
     return out
 
 
+def narrow_bf16(t: torch.Tensor) -> torch.Tensor:
+    """fp32 CUDA tensor -> bf16 tensor of the same shape (round to nearest even)."""
+    if not t.is_cuda or t.dtype != torch.float32:
+        raise RuntimeError("ammc_b200: narrow_bf16 needs a CUDA float32 tensor, got %s on %s" % (t.dtype, t.device))
+    _check_device(t.device)
+    tc = t.contiguous()
+    out = torch.empty(tc.shape, dtype=torch.bfloat16, device=t.device)
+    if tc.numel():
+        with torch.cuda.device(t.device):
+            _capi.call("ammc_cast_f32_bf16", _p(tc), _p(out), tc.numel(), _stream())
+        _count(1)
+    return out
+
+
 def upload(arrays: Sequence, device) -> torch.Tensor:
     """Stack equally shaped host arrays (decoded frames or flow payloads) in pinned memory and copy them to `device`
     asynchronously on the current stream."""

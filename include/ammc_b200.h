@@ -108,6 +108,21 @@ int ammc_mem_fwd(const float* x, const float* enc_w, const float* enc_b, const f
                  void* workspace, size_t workspace_bytes,
                  int b, int h, int w, int C, int D, int M, int k, int residual, void* stream);
 
+/* bf16 feature-I/O variant of the module (BASELINE configs[2]; the reference module is dtype-agnostic, unet.py:318-331,
+ * 379-387): x and out are bf16 NCHW, everything else as ammc_mem_fwd.  x enters the enc GEMM exactly (bf16 is its own hi
+ * plane), the residual sum is formed in fp32 and rounded once when `out` is stored, so indices, q1, z, diff and the
+ * operand planes are bit-identical to ammc_mem_fwd on the widened tensor and out == bf16(its out).  Runs on the fused
+ * front kernel + tensor-core dec only (ammc_mem_io16_supported); eval (counts == embed_sum == NULL). */
+int ammc_mem_io16_supported(int b, int h, int w, int C, int D, int M, int k);
+int ammc_mem_fwd_io16(const void* x_bf16, const float* enc_w, const float* enc_b, const float* embed,
+                      const float* dec_w, const float* dec_b,
+                      void* out_bf16, float* q1, int64_t* idx, float* z, float* sse_frame, float* diff,
+                      void* out_planes, int planes_fmt, const void* prep,
+                      void* workspace, size_t workspace_bytes,
+                      int b, int h, int w, int C, int D, int M, int k, int residual, void* stream);
+/* fp32 -> bf16 (round to nearest even), the inverse direction of ammc_cast_bf16_f32 */
+int ammc_cast_f32_bf16(const float* src, void* dst_bf16, int64_t n, void* stream);
+
 /* Staged form of the tensor-core addressing filter (composed internally by ammc_mem_fwd / ammc_quantize_fwd; exposed
  * for the addressing microbench of BASELINE configs[4]):
  *   ammc_addr_padded_items(M)   items after padding to the MMA N tile (Mpad)
@@ -228,6 +243,9 @@ typedef struct ammc_conv_layer {
   int in_fmt;              /* 0: in_planes / wp are bf16 hi/lo planes; 1: q buffers (required by precision 2) */
   int out_fmt;             /* 0: out_planes are bf16 hi/lo planes; 1: a q buffer.  With precision 2 the layer derives the
                               output scale itself; with precision 1/3 the caller stores it at byte 4*n beforehand */
+  int io_bf16;             /* 1: out_nchw / res_nchw point to bf16 NCHW tensors (bf16 feature-I/O variant, BASELINE
+                              configs[2]); the sum is formed in fp32 and rounded once at the store.  CTA-pair kernel only
+                              (Cout % 256 == 0, act 0/1) */
 } ammc_conv_layer;
 int ammc_conv_layer_run(const ammc_conv_layer* layer, void* stream);
 /* w [Cout,Cin,3,3] (taps=9) or [Cout,Cin] (taps=1) -> wp [2][Cout_pad][taps*Cin_pad], zero-padded rows/columns */
