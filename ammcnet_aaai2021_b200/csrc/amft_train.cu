@@ -113,31 +113,50 @@ struct ApplyArgs {
   long long plane_stride;
 };
 
+// Tile = 64 channels x 32 pixels.  Phase 1 walks the NCHW side (lane = pixel: 128-byte coalesced reads of y / g / res and
+// writes of out_f32 / the NCHW planes); phase 2 walks the NHWC side with one (pixel, 8-channel group) per thread: 16-byte
+// stores, 128 contiguous bytes per 8 lanes (round 1 stored 2 bytes per lane = 64 bytes per warp instruction and ran at
+// 40 % of the HBM peak).  C % 8 == 0 on the NHWC path (the conv engine needs C % 64 == 0 anyway).
 __global__ void __launch_bounds__(256) bn_apply_pack_kernel(const ApplyArgs a, int C, int HW) {
-  __shared__ float tile[32][33];
-  const int img = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  __shared__ float tile[64][33];
+  const int img = blockIdx.z, c0 = blockIdx.y * 64, p0 = blockIdx.x * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  for (int r = ty; r < 32; r += 8) {
-    const int c = c0 + r, pp = p0 + tx;
+  const int pp1 = p0 + tx;
+  // all loads of the thread's eight (channel, pixel) elements first -- 8 to 24 independent requests in flight -- then the
+  // arithmetic and the stores
+  float yv[8], gv[8], rv[8];
+  bool ok[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = c0 + ty + 8 * i;
+    ok[i] = c < C && pp1 < HW;
+    const size_t o = ((size_t)img * C + c) * HW + pp1;
+    yv[i] = ok[i] ? __ldg(a.y + o) : 0.f;
+    gv[i] = (ok[i] && a.mode != 0) ? __ldg(a.g + o) : 0.f;
+    rv[i] = (ok[i] && a.out_f32 && a.res) ? __ldg(a.res + o) : 0.f;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = c0 + ty + 8 * i;
     float v = 0.f;
-    if (c < C && pp < HW) {
-      const size_t o = ((size_t)img * C + c) * HW + pp;
-      const float yv = a.y[o];
-      const float act = fmaf(yv, a.scale[c], a.shift[c]);
+    if (ok[i]) {
+      const size_t o = ((size_t)img * C + c) * HW + pp1;
+      const float sc = __ldg(a.scale + c);
+      const float act = fmaf(yv[i], sc, __ldg(a.shift + c));
       if (a.mode == 0) {
         v = a.relu ? fmaxf(act, 0.f) : act;
       } else {
-        float gp = a.g[o];
+        float gp = gv[i];
         if (a.relu && !(act > 0.f)) gp = 0.f;
         if (a.mode == 1) {
-          const float yhat = (yv - a.mean[c]) * a.invstd[c];
+          const float yhat = (yv[i] - __ldg(a.mean + c)) * __ldg(a.invstd + c);
           const float mg = (float)(a.bsums[c] * a.inv_count), mgy = (float)(a.bsums[C + c] * a.inv_count);
-          v = a.scale[c] * (gp - mg - yhat * mgy);
+          v = sc * (gp - mg - yhat * mgy);
         } else {
-          v = a.scale[c] * gp;
+          v = sc * gp;
         }
       }
-      if (a.out_f32) a.out_f32[o] = a.res ? v + a.res[o] : v;
+      if (a.out_f32) a.out_f32[o] = v + rv[i];
       if (a.nchw) {
         __nv_bfloat16 hi, lo;
         split_bf16_t(v, hi, lo);
@@ -145,19 +164,19 @@ __global__ void __launch_bounds__(256) bn_apply_pack_kernel(const ApplyArgs a, i
         a.nchw[o + a.plane_stride] = lo;
       }
     }
-    tile[r][tx] = v;
+    tile[ty + 8 * i][tx] = v;
   }
   if (!a.nhwc) return;
   __syncthreads();
-  for (int r = ty; r < 32; r += 8) {
-    const int pp = p0 + r, c = c0 + tx;
-    if (pp < HW && c < C) {
-      __nv_bfloat16 hi, lo;
-      split_bf16_t(tile[tx][r], hi, lo);
-      const size_t o = ((size_t)img * HW + pp) * C + c;
-      a.nhwc[o] = hi;
-      a.nhwc[o + a.plane_stride] = lo;
-    }
+  const int px = threadIdx.x >> 3, cg = threadIdx.x & 7;         // pixel within the tile, 8-channel group
+  const int pp = p0 + px, c = c0 + cg * 8;
+  if (pp < HW && c < C) {
+    uint32_t hp[4], lp[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ptx::split_pack_bf16x2(tile[cg * 8 + 2 * j][px], tile[cg * 8 + 2 * j + 1][px], hp[j], lp[j]);
+    __nv_bfloat16* dst = a.nhwc + ((size_t)img * HW + pp) * C + c;
+    *reinterpret_cast<uint4*>(dst) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+    *reinterpret_cast<uint4*>(dst + a.plane_stride) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
   }
 }
 
@@ -239,8 +258,12 @@ constexpr int WG_BLOCK_K = 64;    // pixels per pipeline stage
 constexpr int WG_BOX_BYTES = WG_BLOCK_K * 64 * 2;          // [64 px][64 ch] bf16 = 8 KB
 constexpr int WG_A_BYTES = (WG_BLOCK_M / 64) * WG_BOX_BYTES;
 constexpr int WG_B_BYTES = (WG_BLOCK_N / 64) * WG_BOX_BYTES;
-constexpr int WG_STAGE_BYTES = WG_A_BYTES + WG_B_BYTES;    // 48 KB
-constexpr int WG_STAGES = 4;
+// A stage holds the hi AND lo planes of both operands: [A hi][A lo][B hi][B lo] = 96 KB, loaded once per K block and used
+// by the three MMA passes (hi,hi) (hi,lo) (lo,hi) -- 8 KB of L2 -> shared-memory traffic per MMA instead of 12 KB when
+// every pass streamed K on its own.  That traffic, not the tensor pipe, bounded the kernel: 10.6 GB per launch at the
+// shipped shape = 12.8 TB/s out of L2 over 0.83 ms.
+constexpr int WG_STAGE_BYTES = 2 * (WG_A_BYTES + WG_B_BYTES);    // 96 KB
+constexpr int WG_STAGES = 2;
 constexpr int WG_BAR_OFFSET = WG_STAGES * WG_STAGE_BYTES;
 constexpr int WG_SMEM = WG_BAR_OFFSET + 256 + 1024;
 
@@ -314,23 +337,24 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         WG_DECODE(wi, mt, nt, tap, sp)
         const int dy = ntaps == 9 ? tap / 3 - 1 : 0, dx = ntaps == 9 ? tap % 3 - 1 : 0;
         const int i0 = sp * p.imgs_per_split, i1 = min(p.b, i0 + p.imgs_per_split);
-        for (int ps = 0; ps < p.n_pass; ++ps) {
-          const int pa = ps == 2 ? 1 : 0, pb = ps == 1 ? 1 : 0;   // (hi,hi) (hi,lo) (lo,hi)
-          for (int img = i0; img < i1; ++img) {
-            for (int kb = 0; kb < p.kb_per_img; ++kb) {
-              const int h0 = (kb / p.chunks_per_row) * p.rows_per_kb, w0 = (kb % p.chunks_per_row) * 64;
-              ptx::mbar_wait(&empty_bar[s], ph ^ 1, 21);
-              ptx::mbar_expect_tx(&full_bar[s], (WG_BLOCK_M / 64 + WG_BLOCK_N / 64) * p.k_bytes);
-              uint8_t* dst = smem + s * WG_STAGE_BYTES;
+        const int planes = p.n_pass == 3 ? 2 : 1;
+        for (int img = i0; img < i1; ++img) {
+          for (int kb = 0; kb < p.kb_per_img; ++kb) {
+            const int h0 = (kb / p.chunks_per_row) * p.rows_per_kb, w0 = (kb % p.chunks_per_row) * 64;
+            ptx::mbar_wait(&empty_bar[s], ph ^ 1, 21);
+            ptx::mbar_expect_tx(&full_bar[s], planes * (WG_BLOCK_M / 64 + WG_BLOCK_N / 64) * p.k_bytes);
+            uint8_t* dst = smem + s * WG_STAGE_BYTES;
+            for (int pl = 0; pl < planes; ++pl) {
 #pragma unroll
               for (int i = 0; i < WG_BLOCK_M / 64; ++i)
-                ptx::tma_load_5d(dst + i * WG_BOX_BYTES, &tmA, &full_bar[s], mt * WG_BLOCK_M + i * 64, w0, h0, img, pa);
+                ptx::tma_load_5d(dst + pl * WG_A_BYTES + i * WG_BOX_BYTES, &tmA, &full_bar[s], mt * WG_BLOCK_M + i * 64, w0, h0,
+                                 img, pl);
 #pragma unroll
               for (int i = 0; i < WG_BLOCK_N / 64; ++i)
-                ptx::tma_load_5d(dst + WG_A_BYTES + i * WG_BOX_BYTES, &tmB, &full_bar[s], nt * WG_BLOCK_N + i * 64, w0 + dx,
-                                 h0 + dy, img, pb);
-              if (++s == WG_STAGES) { s = 0; ph ^= 1; }
+                ptx::tma_load_5d(dst + 2 * WG_A_BYTES + pl * WG_B_BYTES + i * WG_BOX_BYTES, &tmB, &full_bar[s],
+                                 nt * WG_BLOCK_N + i * 64, w0 + dx, h0 + dy, img, pl);
             }
+            if (++s == WG_STAGES) { s = 0; ph ^= 1; }
           }
         }
       }
@@ -344,7 +368,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         WG_DECODE(wi, mt, nt, tap, sp)
         (void)mt; (void)nt; (void)tap;
         const int i0 = sp * p.imgs_per_split, i1 = min(p.b, i0 + p.imgs_per_split);
-        const int kb_total = p.n_pass * (i1 - i0) * p.kb_per_img;
+        const int kb_total = (i1 - i0) * p.kb_per_img;
+        const bool three = p.n_pass == 3;
         const int acc = it & 1;
         const uint32_t acc_ph = (it >> 1) & 1;
         ptx::mbar_wait(&tmem_empty[acc], acc_ph ^ 1, 22);
@@ -354,12 +379,18 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           ptx::mbar_wait(&full_bar[s], ph, 23);
           ptx::tc_fence_after();
           const uint32_t a_addr = ptx::smem_u32(smem + s * WG_STAGE_BYTES);
-          const uint64_t adesc = ptx::umma_desc_mn_sw128(a_addr, WG_BOX_BYTES);
-          const uint64_t bdesc = ptx::umma_desc_mn_sw128(a_addr + WG_A_BYTES, WG_BOX_BYTES);
+          const uint64_t a_hi = ptx::umma_desc_mn_sw128(a_addr, WG_BOX_BYTES);
+          const uint64_t a_lo = ptx::umma_desc_mn_sw128(a_addr + WG_A_BYTES, WG_BOX_BYTES);
+          const uint64_t b_hi = ptx::umma_desc_mn_sw128(a_addr + 2 * WG_A_BYTES, WG_BOX_BYTES);
+          const uint64_t b_lo = ptx::umma_desc_mn_sw128(a_addr + 2 * WG_A_BYTES + WG_B_BYTES, WG_BOX_BYTES);
 #pragma unroll
           for (int k4 = 0; k4 < WG_BLOCK_K / 16; ++k4) {
             // 16 pixels (K) = 16 rows of 128 B = 2048 B further down each box: +128 in the (>>4) address field
-            ptx::mma_f16_ss(d_tmem, adesc + 128 * k4, bdesc + 128 * k4, idesc, (kb | k4) != 0 ? 1u : 0u);
+            ptx::mma_f16_ss(d_tmem, a_hi + 128 * k4, b_hi + 128 * k4, idesc, (kb | k4) != 0 ? 1u : 0u);
+            if (three) {
+              ptx::mma_f16_ss(d_tmem, a_hi + 128 * k4, b_lo + 128 * k4, idesc, 1u);
+              ptx::mma_f16_ss(d_tmem, a_lo + 128 * k4, b_hi + 128 * k4, idesc, 1u);
+            }
           }
           ptx::mma_commit(&empty_bar[s]);
           if (kb == kb_total - 1) ptx::mma_commit(&tmem_full[acc]);
@@ -511,7 +542,8 @@ extern "C" int ammc_bn_batch_stats_staged(const float* y, const float* gamma, co
 static int launch_apply(const ApplyArgs& a, int b, int C, int h, int w, cudaStream_t st) {
   AMMC_REQUIRE(b <= 65535, "batch %d too large for one launch", b);
   const int HW = h * w;
-  bn_apply_pack_kernel<<<dim3(ceil_div(HW, 32), ceil_div(C, 32), b), 256, 0, st>>>(a, C, HW);
+  AMMC_REQUIRE(!a.nhwc || C % 8 == 0, "NHWC plane output needs C %% 8 == 0 (got %d)", C);
+  bn_apply_pack_kernel<<<dim3(ceil_div(HW, 32), ceil_div(C, 64), b), 256, 0, st>>>(a, C, HW);
   AMMC_LAUNCH_CHECK("bn_apply_pack_kernel");
   return 0;
 }
@@ -622,7 +654,20 @@ int conv_wgrad_run(const void* gy_nhwc_planes, const void* x_nhwc_planes, float*
   p.block_n = min(Cin, WG_BLOCK_N);
   p.ntaps = ntaps;
   const int base_items = p.tiles_m * p.tiles_n * ntaps;
-  p.splits = max(1, min(b, ceil_div(2 * num_sms(), base_items)));
+  // split-K over images: the kernel's time is (rounds of work items over the SMs) x (images per item), so take the split
+  // count that minimises that product -- a tail round with a few items costs as much as a full one (b = 64, 72 base
+  // items: 2 splits = 144 items in ONE round of 32 images; the old "2 items per SM" rule gave 5 splits = 360 items in
+  // three rounds of 13) -- and among equals the smallest one (fewer atomics)
+  {
+    long long best_cost = -1;
+    int best = 1;
+    for (int sp = 1; sp <= min(b, 32); ++sp) {
+      const int ips = ceil_div(b, sp), eff = ceil_div(b, ips);
+      const long long cost = (long long)ceil_div((long long)base_items * eff, num_sms()) * ips;
+      if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = eff; }
+    }
+    p.splits = best;
+  }
   p.imgs_per_split = ceil_div(b, p.splits);
   p.splits = ceil_div(b, p.imgs_per_split);
   p.n_pass = precision;
