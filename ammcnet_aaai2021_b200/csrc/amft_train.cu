@@ -661,7 +661,7 @@ int conv_wgrad_run(const void* gy_nhwc_planes, const void* x_nhwc_planes, float*
   {
     long long best_cost = -1;
     int best = 1;
-    for (int sp = 1; sp <= min(b, 32); ++sp) {
+    for (int sp = 1; sp <= min(b, 256); ++sp) {
       const int ips = ceil_div(b, sp), eff = ceil_div(b, ips);
       const long long cost = (long long)ceil_div((long long)base_items * eff, num_sms()) * ips;
       if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = eff; }
