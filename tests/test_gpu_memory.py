@@ -208,7 +208,8 @@ def _quantize_both(z, embed, k, addressing_mode):
 
 @pytest.mark.parametrize("N,D,M,k", [(4096, 64, 256, 2), (1000, 64, 16, 1), (777, 128, 100, 3), (2048, 256, 1000, 4),
                                       (130, 64, 2000, 2), (4096, 512, 300, 2), (65536, 64, 256, 2),
-                                      (3000, 192, 500, 2), (2048, 1024, 600, 2), (5000, 128, 64, 1), (4100, 320, 2100, 3)])
+                                      (3000, 192, 500, 2), (2048, 1024, 600, 2), (5000, 128, 64, 1), (4100, 320, 2100, 3),
+                                      (1500, 128, 4200, 2), (2000, 256, 2100, 4), (700, 512, 4100, 1)])   # long banks: one-sweep epilogue
 def test_tensor_path_bit_identical_to_fp32_path(N, D, M, k, addressing_mode):
     g = torch.Generator().manual_seed(N + D + M)
     z = torch.randn((1, N, 1, D), generator=g).to(DEV)
@@ -251,6 +252,21 @@ def test_tensor_path_adversarial_banks_wide_rows(addressing_mode):
     a, b = o["fp32"], o["tensor"]
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[3], b[3])
     assert torch.equal(a[4], b[4]) and torch.equal(a[2], b[2])                 # per-frame SSE and the commit scalar
+
+
+def test_tensor_path_adversarial_long_bank(addressing_mode):
+    """Long bank (one-sweep filter epilogue with a running threshold): clusters of near-duplicates spread over many item
+    tiles, so hits keep arriving after the threshold has tightened, plus rows whose best items sit in the LAST tile."""
+    g = torch.Generator().manual_seed(13)
+    D, M, N, k = 128, 2304, 4000, 2
+    base = torch.randn((D, 36), generator=g)
+    embed = base.repeat(1, 64) + 1e-3 * torch.randn((D, M), generator=g)      # item j and j + 36 i are near-duplicates
+    z = embed.t()[torch.randint(0, M, (N,), generator=g)] + 1e-4 * torch.randn((N, D), generator=g)
+    z[:500] = embed.t()[M - 500:] * (1 + 1e-6)                                 # best matches in the last item tile
+    z[500:1500] = torch.randn((1000, D), generator=g)
+    o = _quantize_both(z.view(4, N // 4, 1, D).to(DEV), embed.to(DEV), k, addressing_mode)
+    a, b = o["fp32"], o["tensor"]
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[3], b[3]) and torch.equal(a[4], b[4])
 
 
 def test_filter_decides_separated_rows(addressing_mode):
