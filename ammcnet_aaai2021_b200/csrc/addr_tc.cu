@@ -205,6 +205,16 @@ addr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         ptx::tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BLOCK_N + half * HALF_N;
         const int col0 = ti * BLOCK_N + half * HALF_N;
+        // accumulator chunks (32 columns) and their item norms are fetched ONE CHUNK AHEAD into a second register buffer:
+        // the TMEM load and the global loads of chunk c + 1 are in flight while chunk c is scanned
+        uint32_t vbuf[2][32];
+        float4 ebuf[2][8];
+        const float4* e4base = reinterpret_cast<const float4*>(p.en2pad + col0);
+        auto fetch = [&](int c, uint32_t (&vv)[32], float4 (&ee)[8]) {
+          ptx::tmem_ld_32x32(taddr + c * 32, vv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) ee[j] = __ldg(e4base + c * 8 + j);
+        };
         if (SWEEP) {
         // ---- one sweep over the tile with a RUNNING threshold thr = (KSEL-th best score so far) + margin.  thr only
         // falls, so every column within the row's FINAL threshold is a hit when it is visited: the list stays a superset
@@ -225,12 +235,13 @@ addr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (cnt < ADDR_CAPH) { lv[cnt] = av; li[cnt] = (uint16_t)col; ++cnt; }
           else overflow = true;
         };
-#pragma unroll 1
+        fetch(0, vbuf[0], ebuf[0]);
+#pragma unroll
         for (int c = 0; c < CHUNKS; ++c) {
-          uint32_t v[32];
-          ptx::tmem_ld_32x32(taddr + c * 32, v);
           ptx::tmem_ld_wait();
-          const float4* e4 = reinterpret_cast<const float4*>(p.en2pad + col0 + c * 32);
+          if (c + 1 < CHUNKS) fetch(c + 1, vbuf[(c + 1) & 1], ebuf[(c + 1) & 1]);
+          uint32_t (&v)[32] = vbuf[c & 1];
+          float4 (&e4)[8] = ebuf[c & 1];
           uint32_t hits = 0;
           const bool first = ti == 0 && c == 0;              // first 32 columns of the row: no threshold yet ->
           if (first) {                                       // branch-free selection of the KSEL best, then the hits
@@ -241,7 +252,7 @@ addr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               for (int i = 0; i < KSEL; ++i) ma[g][i] = INFINITY;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float4 e = __ldg(e4 + j);
+              const float4 e = e4[j];
               sel_insert<KSEL>(ma[0], fmaf(cs, __uint_as_float(v[4 * j + 0]), e.x));
               sel_insert<KSEL>(ma[1], fmaf(cs, __uint_as_float(v[4 * j + 1]), e.y));
               sel_insert<KSEL>(ma[2], fmaf(cs, __uint_as_float(v[4 * j + 2]), e.z));
@@ -255,7 +266,7 @@ addr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float4 e = __ldg(e4 + j);
+            const float4 e = e4[j];
             hits |= (fmaf(cs, __uint_as_float(v[4 * j + 0]), e.x) <= thr ? 1u : 0u) << (4 * j + 0);
             hits |= (fmaf(cs, __uint_as_float(v[4 * j + 1]), e.y) <= thr ? 1u : 0u) << (4 * j + 1);
             hits |= (fmaf(cs, __uint_as_float(v[4 * j + 2]), e.z) <= thr ? 1u : 0u) << (4 * j + 2);
@@ -275,12 +286,14 @@ addr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         } else {
         // ---- pass A
-#pragma unroll 1
+        fetch(0, vbuf[0], ebuf[0]);
+#pragma unroll
         for (int c = 0; c < CHUNKS; ++c) {
-          uint32_t v[32];
-          ptx::tmem_ld_32x32(taddr + c * 32, v);
           ptx::tmem_ld_wait();
-          const float4* e4 = reinterpret_cast<const float4*>(p.en2pad + col0 + c * 32);
+          if (c + 1 < CHUNKS) fetch(c + 1, vbuf[(c + 1) & 1], ebuf[(c + 1) & 1]);
+          else fetch(0, vbuf[(c + 1) & 1], ebuf[(c + 1) & 1]);       // first chunk of pass B
+          uint32_t (&v)[32] = vbuf[c & 1];
+          float4 (&e4)[8] = ebuf[c & 1];
           float ma[4][KSEL];
 #pragma unroll
           for (int g = 0; g < 4; ++g)
@@ -288,7 +301,7 @@ addr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int i = 0; i < KSEL; ++i) ma[g][i] = INFINITY;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float4 e = __ldg(e4 + j);
+            const float4 e = e4[j];
             sel_insert<KSEL>(ma[0], fmaf(cs, __uint_as_float(v[4 * j + 0]), e.x));
             sel_insert<KSEL>(ma[1], fmaf(cs, __uint_as_float(v[4 * j + 1]), e.y));
             sel_insert<KSEL>(ma[2], fmaf(cs, __uint_as_float(v[4 * j + 2]), e.z));
@@ -301,16 +314,17 @@ addr_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         // ---- pass B
         thr = fminf(m[KSEL - 1] + margin, FLT_MAX);   // padded columns score +inf and never hit
-#pragma unroll 1
+#pragma unroll
         for (int c = 0; c < CHUNKS; ++c) {
-          uint32_t v[32];
-          ptx::tmem_ld_32x32(taddr + c * 32, v);
           ptx::tmem_ld_wait();
-          const float4* e4 = reinterpret_cast<const float4*>(p.en2pad + col0 + c * 32);
+          // pass A left chunk 0 of this pass in buffer CHUNKS & 1; the buffers keep alternating from there
+          if (c + 1 < CHUNKS) fetch(c + 1, vbuf[(CHUNKS + c + 1) & 1], ebuf[(CHUNKS + c + 1) & 1]);
+          uint32_t (&v)[32] = vbuf[(CHUNKS + c) & 1];
+          float4 (&e4)[8] = ebuf[(CHUNKS + c) & 1];
           uint32_t hits = 0;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float4 e = __ldg(e4 + j);
+            const float4 e = e4[j];
             hits |= (fmaf(cs, __uint_as_float(v[4 * j + 0]), e.x) <= thr ? 1u : 0u) << (4 * j + 0);
             hits |= (fmaf(cs, __uint_as_float(v[4 * j + 1]), e.y) <= thr ? 1u : 0u) << (4 * j + 1);
             hits |= (fmaf(cs, __uint_as_float(v[4 * j + 2]), e.z) <= thr ? 1u : 0u) << (4 * j + 2);

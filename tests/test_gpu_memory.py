@@ -209,7 +209,8 @@ def _quantize_both(z, embed, k, addressing_mode):
 @pytest.mark.parametrize("N,D,M,k", [(4096, 64, 256, 2), (1000, 64, 16, 1), (777, 128, 100, 3), (2048, 256, 1000, 4),
                                       (130, 64, 2000, 2), (4096, 512, 300, 2), (65536, 64, 256, 2),
                                       (3000, 192, 500, 2), (2048, 1024, 600, 2), (5000, 128, 64, 1), (4100, 320, 2100, 3),
-                                      (1500, 128, 4200, 2), (2000, 256, 2100, 4), (700, 512, 4100, 1)])   # long banks: one-sweep epilogue
+                                      (1500, 128, 4200, 2), (2000, 256, 2100, 4), (700, 512, 4100, 1),   # long banks: one-sweep epilogue
+                                      (1100, 512, 700, 2), (129, 1024, 256, 2), (40000, 512, 2048, 2)])   # CTA pairs, odd tile counts
 def test_tensor_path_bit_identical_to_fp32_path(N, D, M, k, addressing_mode):
     g = torch.Generator().manual_seed(N + D + M)
     z = torch.randn((1, N, 1, D), generator=g).to(DEV)
