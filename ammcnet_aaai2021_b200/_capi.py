@@ -60,7 +60,9 @@ SIGNATURES = {
     "ammc_q_act_bytes": (Z, [L]),
     "ammc_q_weight_bytes": (Z, [I, I]),
     "ammc_pack_nhwc_q": (I, [P, P, I, I, I, I, P]),
+    "ammc_pack_nhwc_q_planes": (I, [P, P, P, I, I, I, I, P]),
     "ammc_pack_conv_weights_q": (I, [P, P, I, I, I, P]),
+    "ammc_pack_conv_weights_q_pair": (I, [P, P, P, I, I, I, P]),
     "ammc_conv3x3_bn_relu": (I, [P] * 7 + [I] * 7 + [P]),
     "ammc_conv_layer_run": (I, [ctypes.POINTER(ConvLayer), P]),
     "ammc_pack_conv_weights_padded": (I, [P, P, I, I, I, I, I, P]),
@@ -74,6 +76,10 @@ SIGNATURES = {
     "ammc_conv1x1_bn_relu": (I, [P] * 7 + [I] * 7 + [P]),
     "ammc_bn_batch_stats": (I, [P] * 9 + [P, Z] + [I, I, I, I, F, F, I, P]),
     "ammc_bn_apply": (I, [P, P, P, I, P, P, P, P, I, I, I, I, P]),
+    "ammc_bn_q_workspace_bytes": (Z, [I]),
+    "ammc_bn_batch_stats_q": (I, [P] * 9 + [P, Z] + [I] * 4 + [F, F, P]),
+    "ammc_bn_apply_q": (I, [P, P, P, I, P, P, P] + [I] * 4 + [P]),
+    "ammc_bn_backward_q": (I, [P] * 6 + [I, I, P, P, P, P, P, Z] + [I] * 4 + [P]),
     "ammc_bn_backward": (I, [P] * 6 + [I, I] + [P] * 4 + [P, Z] + [I, I, I, I, P]),
     "ammc_bn_batch_stats_staged": (I, [P] * 9 + [P, Z] + [I, I, I, I, F, F, I, I, c_double, P]),
     "ammc_bn_backward_staged": (I, [P] * 6 + [I, I] + [P] * 4 + [P, Z] + [I, I, I, I, I, c_double, P]),

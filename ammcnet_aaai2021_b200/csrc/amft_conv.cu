@@ -757,9 +757,12 @@ __global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ x
 __global__ void qscale_from_absmax_kernel(const unsigned* __restrict__ amax_bits, float* __restrict__ qs) {
   if (threadIdx.x == 0) qs[0] = q_scale_for_bound(__uint_as_float(amax_bits[0]));
 }
-// weights: one block per output channel; w [Cout][Cin][taps] -> q planes with k = tap*Cin + cin, L1 row sums
+// weights: one block per output channel; w [Cout][Cin][taps] -> q planes with k = tap*Cin + cin, L1 row sums.
+// dgrad = 1: the data-gradient weights of the same tensor, w'[ci][co][tap] = w[co][ci][taps - 1 - tap] (taps flipped, channel
+// roles swapped): Cout / Cin are then the ROWS / COLUMNS of the packed matrix, i.e. the original Cin / Cout.
 __global__ void __launch_bounds__(256) pack_weights_q_kernel(const float* __restrict__ w, uint8_t* __restrict__ wq, int Cout,
-                                                             int Cin, int taps, const unsigned* __restrict__ amax_bits) {
+                                                             int Cin, int taps, const unsigned* __restrict__ amax_bits,
+                                                             int dgrad = 0) {
   __shared__ float red[33];
   const int co = blockIdx.x;
   const long long K = (long long)taps * Cin, n = (long long)Cout * K;
@@ -771,7 +774,7 @@ __global__ void __launch_bounds__(256) pack_weights_q_kernel(const float* __rest
   float l1 = 0.f;
   for (long long e = threadIdx.x; e < K; e += blockDim.x) {
     const int cin = (int)(e % Cin), tap = (int)(e / Cin);
-    const float v = w[((size_t)co * Cin + cin) * taps + tap];
+    const float v = dgrad ? w[((size_t)cin * Cout + co) * taps + (taps - 1 - tap)] : w[((size_t)co * Cin + cin) * taps + tap];
     l1 += fabsf(v);
     const float t = v * s;
     const __half hh = __float2half_rn(t);
@@ -785,9 +788,46 @@ __global__ void __launch_bounds__(256) pack_weights_q_kernel(const float* __rest
     if (co == 0) reinterpret_cast<float*>(wq + 4 * n + 4 * (long long)Cout)[0] = s;
   }
 }
-// activations: x [b][C][HW] fp32 -> q planes [b][HW][C]; 32 x 32 (channel, pixel) tiles through shared memory
-__global__ void __launch_bounds__(256) pack_nhwc_q_kernel(const float* __restrict__ x, uint8_t* __restrict__ xq, int C, int HW,
-                                                          long long n, const float* __restrict__ qs) {
+// activations: x [b][C][HW] fp32 -> q planes [b][HW][C] (+ optionally the bf16 hi/lo planes of the same tensor, which the
+// training path needs beside them for the weight gradient).  64 (channel) x 32 (pixel) tiles through shared memory: 128-byte
+// coalesced reads along the pixels, then one (pixel, 8-channel group) per thread with 16 / 8-byte stores.  C % 8 == 0.
+__global__ void __launch_bounds__(256) pack_nhwc_q_kernel(const float* __restrict__ x, uint8_t* __restrict__ xq,
+                                                          __nv_bfloat16* __restrict__ xp, int C, int HW, long long n,
+                                                          const float* __restrict__ qs) {
+  __shared__ float tile[64][33];
+  const int img = blockIdx.z, c0 = blockIdx.y * 64, p0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const float s = qs[0];
+#pragma unroll
+  for (int r = ty; r < 64; r += 8) {
+    const int c = c0 + r, pp = p0 + tx;
+    tile[r][tx] = (c < C && pp < HW) ? __ldg(x + ((size_t)img * C + c) * HW + pp) : 0.f;
+  }
+  __syncthreads();
+  const int px = threadIdx.x >> 3, cg = threadIdx.x & 7;         // pixel within the tile, 8-channel group
+  const int pp = p0 + px, c = c0 + cg * 8;
+  if (pp < HW && c < C) {
+    const size_t o = ((size_t)img * HW + pp) * C + c;
+    uint32_t h16[4], h8[4], l8[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      ptx::split_pack_q(tile[cg * 8 + 2 * j][px] * s, tile[cg * 8 + 2 * j + 1][px] * s, h16[j], h8[j], l8[j]);
+    *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(xq) + o) = make_uint4(h16[0], h16[1], h16[2], h16[3]);
+    *reinterpret_cast<uint2*>(xq + 2 * n + o) = make_uint2(h8[0] | (h8[1] << 16), h8[2] | (h8[3] << 16));
+    *reinterpret_cast<uint2*>(xq + 3 * n + o) = make_uint2(l8[0] | (l8[1] << 16), l8[2] | (l8[3] << 16));
+    if (xp) {
+      uint32_t hp[4], lp[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) ptx::split_pack_bf16x2(tile[cg * 8 + 2 * j][px], tile[cg * 8 + 2 * j + 1][px], hp[j], lp[j]);
+      *reinterpret_cast<uint4*>(xp + o) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+      *reinterpret_cast<uint4*>(xp + n + o) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+    }
+  }
+}
+
+// same, scalar stores: channel counts that are not a multiple of 8
+__global__ void __launch_bounds__(256) pack_nhwc_q_scalar_kernel(const float* __restrict__ x, uint8_t* __restrict__ xq, int C,
+                                                                 int HW, long long n, const float* __restrict__ qs) {
   __shared__ float tile[32][33];
   const int img = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -1117,7 +1157,37 @@ extern "C" int ammc_pack_conv_weights_q(const float* w, void* wq, int Cout, int 
   return 0;
 }
 
+static int pack_nhwc_q_impl(const float* x, void* xq, void* xp, int b, int C, int h, int w, void* stream);
+
+// forward AND data-gradient q weights of one conv weight tensor, one max|w| reduction for both
+extern "C" int ammc_pack_conv_weights_q_pair(const float* w, void* wq, void* wq_dgrad, int Cout, int Cin, int taps,
+                                             void* stream) {
+  AMMC_REQUIRE(w && wq && wq_dgrad && Cout > 0 && Cin > 0 && (taps == 9 || taps == 1), "bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long n = (long long)Cout * Cin * taps;
+  unsigned* amax = reinterpret_cast<unsigned*>((uint8_t*)wq + 4 * n + 4 * (long long)Cout + 4);   // scratch word of the tail
+  AMMC_CUDA_CHECK(cudaMemsetAsync(amax, 0, 4, st));
+  absmax_kernel<<<min(ceil_div(n, 1024), 1184), 256, 0, st>>>(w, n, amax);
+  AMMC_LAUNCH_CHECK("absmax_kernel");
+  pack_weights_q_kernel<<<Cout, 256, 0, st>>>(w, (uint8_t*)wq, Cout, Cin, taps, amax, 0);
+  AMMC_LAUNCH_CHECK("pack_weights_q_kernel");
+  pack_weights_q_kernel<<<Cin, 256, 0, st>>>(w, (uint8_t*)wq_dgrad, Cin, Cout, taps, amax, 1);
+  AMMC_LAUNCH_CHECK("pack_weights_q_kernel (dgrad)");
+  return 0;
+}
+
 extern "C" int ammc_pack_nhwc_q(const float* x, void* xq, int b, int C, int h, int w, void* stream) {
+  return pack_nhwc_q_impl(x, xq, nullptr, b, C, h, w, stream);
+}
+
+// the q buffer AND the bf16 hi/lo planes [2][b,h,w,C] of the same tensor in one pass over x (training: the forward conv
+// takes the q operand, the weight gradient the bf16 planes); C % 8 == 0
+extern "C" int ammc_pack_nhwc_q_planes(const float* x, void* xq, void* xp, int b, int C, int h, int w, void* stream) {
+  AMMC_REQUIRE(xp != nullptr && C % 8 == 0, "bf16 planes output needs a buffer and C %% 8 == 0");
+  return pack_nhwc_q_impl(x, xq, xp, b, C, h, w, stream);
+}
+
+static int pack_nhwc_q_impl(const float* x, void* xq, void* xp, int b, int C, int h, int w, void* stream) {
   AMMC_REQUIRE(x && xq && b > 0 && C > 0 && h > 0 && w > 0 && b <= 65535, "bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   const long long n = (long long)b * C * h * w;
@@ -1128,7 +1198,11 @@ extern "C" int ammc_pack_nhwc_q(const float* x, void* xq, int b, int C, int h, i
   AMMC_LAUNCH_CHECK("absmax_kernel");
   qscale_from_absmax_kernel<<<1, 32, 0, st>>>(amax, qs);
   AMMC_LAUNCH_CHECK("qscale_from_absmax_kernel");
-  pack_nhwc_q_kernel<<<dim3(ceil_div(h * w, 32), ceil_div(C, 32), b), 256, 0, st>>>(x, (uint8_t*)xq, C, h * w, n, qs);
+  if (C % 8 == 0)
+    pack_nhwc_q_kernel<<<dim3(ceil_div(h * w, 32), ceil_div(C, 64), b), 256, 0, st>>>(x, (uint8_t*)xq, (__nv_bfloat16*)xp, C,
+                                                                                      h * w, n, qs);
+  else
+    pack_nhwc_q_scalar_kernel<<<dim3(ceil_div(h * w, 32), ceil_div(C, 32), b), 256, 0, st>>>(x, (uint8_t*)xq, C, h * w, n, qs);
   AMMC_LAUNCH_CHECK("pack_nhwc_q_kernel");
   return 0;
 }

@@ -32,17 +32,24 @@ __device__ __forceinline__ void split_bf16_t(float v, __nv_bfloat16& hi, __nv_bf
 // BatchNorm forward statistics
 // ------------------------------------------------------------------------------------------------
 // grid (C, splits); block 256.  sums[c] += sum y, sums[C + c] += sum y^2 over the images of this split
+// amax (optional, zeroed by the host): amax[c] = max |y| as the bits of a non-negative float -- behind the power-of-two scale
+// of the q-format planes bn_apply_pack_kernel writes for the training path at precision 2
 __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ y, double* __restrict__ sums, int b, int C,
-                                                        int hw, int imgs_per_split) {
+                                                        int hw, int imgs_per_split, unsigned* __restrict__ amax = nullptr) {
   __shared__ double red[2][8];
   const int c = blockIdx.x;
   const int i0 = blockIdx.y * imgs_per_split, i1 = min(b, i0 + imgs_per_split);
   double s = 0.0, s2 = 0.0;
+  float am = 0.f;
   for (int img = i0; img < i1; ++img) {
     const float* p = y + ((size_t)img * C + c) * hw;
     float fs = 0.f, fs2 = 0.f;
-    for (int i = threadIdx.x; i < hw; i += 256) { const float v = p[i]; fs += v; fs2 = fmaf(v, v, fs2); }
+    for (int i = threadIdx.x; i < hw; i += 256) { const float v = p[i]; fs += v; fs2 = fmaf(v, v, fs2); am = fmaxf(am, fabsf(v)); }
     s += (double)fs; s2 += (double)fs2;
+  }
+  if (amax) {
+    am = warp_max(am);
+    if ((threadIdx.x & 31) == 0 && am > 0.f) atomicMax(&amax[c], __float_as_uint(am));
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
@@ -61,7 +68,8 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, const float*
                                    const float* __restrict__ beta, float* __restrict__ running_mean,
                                    float* __restrict__ running_var, float* __restrict__ scale, float* __restrict__ shift,
                                    float* __restrict__ mean_out, float* __restrict__ invstd_out, int C, double count,
-                                   float momentum, float eps, int update_running) {
+                                   float momentum, float eps, int update_running, const unsigned* __restrict__ amax = nullptr,
+                                   unsigned* __restrict__ bound_bits = nullptr) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const double mean = sums[c] / count;
@@ -73,6 +81,8 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, const float*
   shift[c] = beta[c] - (float)mean * sc;
   mean_out[c] = (float)mean;
   invstd_out[c] = invstd;
+  if (bound_bits)      // |act(y * scale + shift)| <= |scale| max|y| + |shift|: bound behind the activation's q scale
+    atomicMax(bound_bits, __float_as_uint(fabsf(sc) * __uint_as_float(amax[c]) * 1.0001f + fabsf(beta[c] - (float)mean * sc)));
   if (update_running) {
     const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
     running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
@@ -111,6 +121,11 @@ struct ApplyArgs {
   float* out_f32;          // [b][C][hw] or null
   const float* res;        // added to out_f32, or null
   long long plane_stride;
+  // q-format copy of the NHWC output (precision 2 operand of the next forward / data-gradient conv), or null:
+  __half* q16;             // [b][hw][C] fp16 plane; the e4m3 planes follow at q8 / q8 + plane_stride
+  uint8_t* q8;
+  const unsigned* q_bound; // bits of a bound on max |v| (bn_finalize_kernel / bn_param_grads_kernel)
+  float* q_scale_out;      // scale slot of the q buffer (written by one thread)
 };
 
 // Tile = 64 channels x 32 pixels.  Phase 1 walks the NCHW side (lane = pixel: 128-byte coalesced reads of y / g / res and
@@ -166,17 +181,34 @@ __global__ void __launch_bounds__(256) bn_apply_pack_kernel(const ApplyArgs a, i
     }
     tile[ty + 8 * i][tx] = v;
   }
-  if (!a.nhwc) return;
+  if (!a.nhwc && !a.q16) return;
   __syncthreads();
   const int px = threadIdx.x >> 3, cg = threadIdx.x & 7;         // pixel within the tile, 8-channel group
   const int pp = p0 + px, c = c0 + cg * 8;
+  float qs = 1.f;
+  if (a.q16) {
+    qs = q_scale_for_bound(__uint_as_float(__ldg(a.q_bound)));
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) *a.q_scale_out = qs;
+  }
   if (pp < HW && c < C) {
-    uint32_t hp[4], lp[4];
+    const size_t o = ((size_t)img * HW + pp) * C + c;
+    if (a.nhwc) {
+      uint32_t hp[4], lp[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) ptx::split_pack_bf16x2(tile[cg * 8 + 2 * j][px], tile[cg * 8 + 2 * j + 1][px], hp[j], lp[j]);
-    __nv_bfloat16* dst = a.nhwc + ((size_t)img * HW + pp) * C + c;
-    *reinterpret_cast<uint4*>(dst) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
-    *reinterpret_cast<uint4*>(dst + a.plane_stride) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+      for (int j = 0; j < 4; ++j) ptx::split_pack_bf16x2(tile[cg * 8 + 2 * j][px], tile[cg * 8 + 2 * j + 1][px], hp[j], lp[j]);
+      __nv_bfloat16* dst = a.nhwc + o;
+      *reinterpret_cast<uint4*>(dst) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+      *reinterpret_cast<uint4*>(dst + a.plane_stride) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+    }
+    if (a.q16) {           // 8 channels = 16 B of fp16 + 8 B of h8 + 8 B of l8
+      uint32_t h16[4], h8[4], l8[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        ptx::split_pack_q(tile[cg * 8 + 2 * j][px] * qs, tile[cg * 8 + 2 * j + 1][px] * qs, h16[j], h8[j], l8[j]);
+      *reinterpret_cast<uint4*>(a.q16 + o) = make_uint4(h16[0], h16[1], h16[2], h16[3]);
+      *reinterpret_cast<uint2*>(a.q8 + o) = make_uint2(h8[0] | (h8[1] << 16), h8[2] | (h8[3] << 16));
+      *reinterpret_cast<uint2*>(a.q8 + a.plane_stride + o) = make_uint2(l8[0] | (l8[1] << 16), l8[2] | (l8[3] << 16));
+    }
   }
 }
 
@@ -185,12 +217,13 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restr
                                                              const float* __restrict__ scale, const float* __restrict__ shift,
                                                              const float* __restrict__ mean, const float* __restrict__ invstd,
                                                              int relu, double* __restrict__ sums, int b, int C, int hw,
-                                                             int imgs_per_split) {
+                                                             int imgs_per_split, unsigned* __restrict__ amax = nullptr) {
   __shared__ double red[2][8];
   const int c = blockIdx.x;
   const int i0 = blockIdx.y * imgs_per_split, i1 = min(b, i0 + imgs_per_split);
   const float sc = scale[c], sh = shift[c], mu = mean[c], is = invstd[c];
   double s = 0.0, s2 = 0.0;
+  float mg = 0.f, myh = 0.f;       // max |g'|, max |yhat|: behind the q scale of the gradient planes (amax[c], amax[C + c])
   for (int img = i0; img < i1; ++img) {
     const size_t base = ((size_t)img * C + c) * hw;
     float fs = 0.f, fs2 = 0.f;
@@ -198,10 +231,21 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restr
       const float yv = y[base + i];
       float gp = g[base + i];
       if (relu && !(fmaf(yv, sc, sh) > 0.f)) gp = 0.f;
+      const float yh = (yv - mu) * is;
       fs += gp;
-      fs2 = fmaf(gp, (yv - mu) * is, fs2);
+      fs2 = fmaf(gp, yh, fs2);
+      mg = fmaxf(mg, fabsf(gp));
+      myh = fmaxf(myh, fabsf(yh));
     }
     s += (double)fs; s2 += (double)fs2;
+  }
+  if (amax) {
+    mg = warp_max(mg);
+    myh = warp_max(myh);
+    if ((threadIdx.x & 31) == 0) {
+      if (mg > 0.f) atomicMax(&amax[c], __float_as_uint(mg));
+      if (myh > 0.f) atomicMax(&amax[C + c], __float_as_uint(myh));
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
@@ -216,12 +260,22 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restr
   }
 }
 
+// bound_bits (optional): max_c |scale_c| (max|g'| + |mean g'| + max|yhat| |mean g' yhat|) >= max |g_y| (training BN; eval BN:
+// |scale_c| max|g'|) -- behind the q scale of the gradient planes
 __global__ void bn_param_grads_kernel(const double* __restrict__ sums, float* __restrict__ g_gamma,
-                                      float* __restrict__ g_beta, int C) {
+                                      float* __restrict__ g_beta, int C, const unsigned* __restrict__ amax = nullptr,
+                                      const float* __restrict__ scale = nullptr, double inv_count = 0.0, int training = 1,
+                                      unsigned* __restrict__ bound_bits = nullptr) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   g_beta[c] = (float)sums[c];
   g_gamma[c] = (float)sums[C + c];
+  if (bound_bits) {
+    const float mg = __uint_as_float(amax[c]), myh = __uint_as_float(amax[C + c]);
+    float bnd = mg;
+    if (training) bnd += fabsf((float)(sums[c] * inv_count)) + myh * fabsf((float)(sums[C + c] * inv_count));
+    atomicMax(bound_bits, __float_as_uint(fabsf(scale[c]) * bnd * 1.0001f));
+  }
 }
 
 // x fp32 (any layout) -> same layout bf16 hi/lo planes
@@ -604,6 +658,86 @@ extern "C" int ammc_bn_backward_staged(const float* g, const float* y, const flo
   a.mode = training ? 1 : 2; a.relu = relu;
   a.nhwc = (__nv_bfloat16*)gy_nhwc_planes; a.nchw = (__nv_bfloat16*)gy_nchw_planes;
   a.plane_stride = (long long)b * C * h * w;
+  return launch_apply(a, b, C, h, w, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// q-format variants (training at precision 2: the forward and data-gradient convs take fp16 + e4m3 operands).  The BN
+// kernels already see every value that ends up in an operand plane, so the power-of-two scale of the q planes comes out
+// of their reductions as a BOUND (loose bounds cost nothing): per-channel max|y| in the statistics pass,
+// max|g'| and max|yhat| in the backward reduction.  Per-rank statistics only (no staged form).
+//   workspace: [2C doubles: sums][2C uint32: maxima][uint32: bound bits]  ->  ammc_bn_q_workspace_bytes(C)
+// ------------------------------------------------------------------------------------------------
+extern "C" size_t ammc_bn_q_workspace_bytes(int C) { return (size_t)2 * C * 8 + (size_t)2 * C * 4 + 16; }
+
+extern "C" int ammc_bn_batch_stats_q(const float* y, const float* gamma, const float* beta, float* running_mean,
+                                     float* running_var, float* scale, float* shift, float* mean, float* invstd,
+                                     void* workspace, size_t workspace_bytes, int b, int C, int h, int w, float momentum,
+                                     float eps, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  AMMC_REQUIRE(y && gamma && beta && running_mean && running_var && scale && shift && mean && invstd && C > 0 && b > 0,
+               "bad argument");
+  if (!workspace || workspace_bytes < ammc_bn_q_workspace_bytes(C)) return fail(AMMC_EWORKSPACE, "workspace too small");
+  double* sums = (double*)workspace;
+  unsigned* amax = (unsigned*)(sums + 2 * C);
+  unsigned* bound = amax + 2 * C;
+  AMMC_CUDA_CHECK(cudaMemsetAsync(workspace, 0, ammc_bn_q_workspace_bytes(C), st));
+  const int splits = max(1, min(b, ceil_div(4 * num_sms(), C)));
+  const int per = ceil_div(b, splits);
+  bn_stats_kernel<<<dim3(C, ceil_div(b, per)), 256, 0, st>>>(y, sums, b, C, h * w, per, amax);
+  AMMC_LAUNCH_CHECK("bn_stats_kernel");
+  bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(sums, gamma, beta, running_mean, running_var, scale, shift, mean,
+                                                       invstd, C, (double)b * h * w, momentum, eps, 1, amax, bound);
+  AMMC_LAUNCH_CHECK("bn_finalize_kernel");
+  return 0;
+}
+
+// relu(y * scale + shift) -> bf16 hi/lo NHWC planes (operand of the weight gradient; may be NULL) and the q buffer
+// `out_q` (ammc_q_act_bytes); `workspace` is the one ammc_bn_batch_stats_q filled
+extern "C" int ammc_bn_apply_q(const float* y, const float* scale, const float* shift, int relu, void* out_nhwc_planes,
+                               void* out_q, const void* workspace, int b, int C, int h, int w, void* stream) {
+  AMMC_REQUIRE(y && scale && shift && out_q && workspace && C % 8 == 0, "bad argument");
+  const long long n = (long long)b * C * h * w;
+  ApplyArgs a{};
+  a.y = y; a.scale = scale; a.shift = shift; a.mode = 0; a.relu = relu;
+  a.nhwc = (__nv_bfloat16*)out_nhwc_planes;
+  a.plane_stride = n;
+  a.q16 = (__half*)out_q; a.q8 = (uint8_t*)out_q + 2 * n;
+  a.q_bound = (const unsigned*)((const double*)workspace + 2 * C) + 2 * C;
+  a.q_scale_out = (float*)((uint8_t*)out_q + 4 * n);
+  return launch_apply(a, b, C, h, w, (cudaStream_t)stream);
+}
+
+// gradient through ReLU + BN -> g_y as bf16 hi/lo NHWC planes (weight gradient; may be NULL) and as q planes (data gradient)
+extern "C" int ammc_bn_backward_q(const float* g, const float* y, const float* scale, const float* shift, const float* mean,
+                                  const float* invstd, int relu, int training, void* gy_nhwc_planes, void* gy_q,
+                                  float* g_gamma, float* g_beta, void* workspace, size_t workspace_bytes, int b, int C, int h,
+                                  int w, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  AMMC_REQUIRE(g && y && scale && shift && mean && invstd && g_gamma && g_beta && gy_q && C % 8 == 0 && b > 0, "bad argument");
+  if (!workspace || workspace_bytes < ammc_bn_q_workspace_bytes(C)) return fail(AMMC_EWORKSPACE, "workspace too small");
+  double* sums = (double*)workspace;
+  unsigned* amax = (unsigned*)(sums + 2 * C);
+  unsigned* bound = amax + 2 * C;
+  AMMC_CUDA_CHECK(cudaMemsetAsync(workspace, 0, ammc_bn_q_workspace_bytes(C), st));
+  const int splits = max(1, min(b, ceil_div(4 * num_sms(), C)));
+  const int per = ceil_div(b, splits);
+  const double inv_count = 1.0 / ((double)b * h * w);
+  bn_bwd_reduce_kernel<<<dim3(C, ceil_div(b, per)), 256, 0, st>>>(g, y, scale, shift, mean, invstd, relu, sums, b, C, h * w,
+                                                                  per, amax);
+  AMMC_LAUNCH_CHECK("bn_bwd_reduce_kernel");
+  bn_param_grads_kernel<<<ceil_div(C, 128), 128, 0, st>>>(sums, g_gamma, g_beta, C, amax, scale, inv_count, training, bound);
+  AMMC_LAUNCH_CHECK("bn_param_grads_kernel");
+  const long long n = (long long)b * C * h * w;
+  ApplyArgs a{};
+  a.y = y; a.g = g; a.scale = scale; a.shift = shift; a.mean = mean; a.invstd = invstd; a.bsums = sums;
+  a.inv_count = inv_count;
+  a.mode = training ? 1 : 2; a.relu = relu;
+  a.nhwc = (__nv_bfloat16*)gy_nhwc_planes;
+  a.plane_stride = n;
+  a.q16 = (__half*)gy_q; a.q8 = (uint8_t*)gy_q + 2 * n;
+  a.q_bound = bound;
+  a.q_scale_out = (float*)((uint8_t*)gy_q + 4 * n);
   return launch_apply(a, b, C, h, w, st);
 }
 

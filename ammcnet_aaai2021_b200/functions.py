@@ -529,6 +529,22 @@ def pack_conv_weights_q(w: torch.Tensor) -> torch.Tensor:
     return wq
 
 
+def pack_conv_weights_q_pair(w: torch.Tensor):
+    """[Cout, Cin, 3, 3] fp32 -> (q weights of the conv, q weights of its data gradient) with one max|w| reduction."""
+    _require_cuda_f32(w, names=("conv weight",))
+    Cout, Cin = w.shape[0], w.shape[1]
+    taps = w[0, 0].numel()
+    if taps not in (1, 9):
+        raise RuntimeError("ammc_b200: only 3x3 and 1x1 conv weights are supported")
+    lib = _capi.load()
+    wq = torch.empty((int(lib.ammc_q_weight_bytes(Cout, taps * Cin)),), dtype=torch.uint8, device=w.device)
+    wd = torch.empty((int(lib.ammc_q_weight_bytes(Cin, taps * Cout)),), dtype=torch.uint8, device=w.device)
+    with torch.cuda.device(w.device):
+        _capi.call("ammc_pack_conv_weights_q_pair", _p(w.contiguous()), _p(wq), _p(wd), Cout, Cin, taps, _stream())
+    _count(3)
+    return wq, wd
+
+
 def pack_nhwc_q(x: torch.Tensor) -> QPlanes:
     """[b, C, h, w] fp32 NCHW -> q operand buffer (max|x| reduction + pack)."""
     _require_cuda_f32(x, names=("activation",))
@@ -538,6 +554,18 @@ def pack_nhwc_q(x: torch.Tensor) -> QPlanes:
         _capi.call("ammc_pack_nhwc_q", _p(x.contiguous()), _p(q.buf), b, C, h, w, _stream())
     _count(3)
     return q
+
+
+def pack_nhwc_q_planes(x: torch.Tensor):
+    """[b, C, h, w] fp32 NCHW -> (QPlanes, bf16 hi/lo planes [2,b,h,w,C]) in one pass over x (C % 8 == 0)."""
+    _require_cuda_f32(x, names=("activation",))
+    b, C, h, w = x.shape
+    q = QPlanes.empty(b, h, w, C, x.device)
+    xp = torch.empty((2, b, h, w, C), dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        _capi.call("ammc_pack_nhwc_q_planes", _p(x.contiguous()), _p(q.buf), _p(xp), b, C, h, w, _stream())
+    _count(3)
+    return q, xp
 
 
 def bn_fold(gamma, beta, mean, var, eps: float):
@@ -776,6 +804,53 @@ def bn_apply(y, scale, shift, *, relu=True, nhwc=False, nchw=False, f32=False, r
     return o_nhwc, o_nchw, o_f32
 
 
+def bn_batch_stats_q(y, gamma, beta, running_mean, running_var, momentum: float, eps: float):
+    """Training-mode bn_batch_stats that also leaves, in the returned workspace, the bound behind the q scale of
+    act(y*scale+shift) (per-rank statistics).  -> (scale, shift, mean, invstd, workspace)"""
+    b, C, h, w = y.shape
+    dev = y.device
+    scale, shift, mean, invstd = (torch.empty((C,), dtype=torch.float32, device=dev) for _ in range(4))
+    ws = torch.empty((int(_capi.load().ammc_bn_q_workspace_bytes(C)),), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _capi.call("ammc_bn_batch_stats_q", _p(y), _p(gamma.contiguous()), _p(beta.contiguous()), _p(running_mean),
+                   _p(running_var), _p(scale), _p(shift), _p(mean), _p(invstd), _p(ws), ws.numel(), b, C, h, w,
+                   float(momentum), float(eps), _stream())
+    _count(3)
+    torch.autograd.graph.increment_version(running_mean)
+    torch.autograd.graph.increment_version(running_var)
+    return scale, shift, mean, invstd, ws
+
+
+def bn_apply_q(y, scale, shift, ws, *, relu=True, nhwc=True):
+    """relu(y*scale+shift) -> (bf16 hi/lo NHWC planes | None, QPlanes); `ws` from bn_batch_stats_q."""
+    b, C, h, w = y.shape
+    dev = y.device
+    o_nhwc = torch.empty((2, b, h, w, C), dtype=torch.bfloat16, device=dev) if nhwc else None
+    q = QPlanes.empty(b, h, w, C, dev)
+    with torch.cuda.device(dev):
+        _capi.call("ammc_bn_apply_q", _p(y), _p(scale), _p(shift), int(bool(relu)), _p(o_nhwc), _p(q), _p(ws), b, C, h, w,
+                   _stream())
+    _count(1)
+    return o_nhwc, q
+
+
+def bn_backward_q(g, y, scale, shift, mean, invstd, *, relu=True, training=True):
+    """Gradient through ReLU+BN -> (g_y as bf16 hi/lo NHWC planes, g_y as QPlanes, g_gamma, g_beta); per-rank statistics."""
+    b, C, h, w = y.shape
+    dev = y.device
+    gy_nhwc = torch.empty((2, b, h, w, C), dtype=torch.bfloat16, device=dev)
+    gy_q = QPlanes.empty(b, h, w, C, dev)
+    gg = torch.empty((C,), dtype=torch.float32, device=dev)
+    gb = torch.empty((C,), dtype=torch.float32, device=dev)
+    ws = _workspace(int(_capi.load().ammc_bn_q_workspace_bytes(C)), dev)
+    with torch.cuda.device(dev):
+        _capi.call("ammc_bn_backward_q", _p(g.contiguous()), _p(y), _p(scale), _p(shift), _p(mean), _p(invstd),
+                   int(bool(relu)), int(bool(training)), _p(gy_nhwc), _p(gy_q), _p(gg), _p(gb), _p(ws), ws.numel(), b, C, h, w,
+                   _stream())
+    _count(4)
+    return gy_nhwc, gy_q, gg, gb
+
+
 def bn_backward(g, y, scale, shift, mean, invstd, *, relu=True, training=True):
     """Gradient through ReLU+BN: -> (g_y as NHWC bf16 planes, g_gamma, g_beta)."""
     b, C, h, w = y.shape
@@ -854,23 +929,48 @@ class AmftBranchFn(torch.autograd.Function):
         one = torch.ones((C,), dtype=torch.float32, device=dev)
         zero = torch.zeros((C,), dtype=torch.float32, device=dev)
         need_grad = any(ctx.needs_input_grad)
-        up = pack_nhwc(u)
-        y1 = conv3x3_bn_relu(up, pack_conv_weights(w1), one, zero, to_planes=False, precision=precision, relu=False)
-        sc1, sh1, mu1, is1 = bn_batch_stats(y1, g1, b1, rm1, rv1, momentum, eps, training)
-        a1_nhwc, _, _ = bn_apply(y1, sc1, sh1, relu=True, nhwc=True)
-        y2 = conv3x3_bn_relu(a1_nhwc, pack_conv_weights(w2), one, zero, to_planes=False, precision=precision, relu=False)
+        # precision 2 (fp16 + e4m3 operands, two tensor-core pass-equivalents) for the forward and data-gradient convs: in
+        # training with per-rank BatchNorm statistics, where the BN passes deliver the planes' scales; the weight gradient
+        # keeps its split-bf16 planes.  Otherwise (eval-mode BN under autograd, global-batch BN, small channel counts) x3.
+        q = bool(training) and int(precision) == 2 and BN_SYNC["allreduce"] is None and q_conv_supported(C, C)
+        prec3 = 3 if int(precision) == 2 else int(precision)
+        if q:
+            uq, up = pack_nhwc_q_planes(u)
+            # the data-gradient weights are packed here too (same max|w| reduction) and kept for backward
+            w1q, w1d = pack_conv_weights_q_pair(w1) if need_grad else (pack_conv_weights_q(w1), None)
+            w2q, w2d = pack_conv_weights_q_pair(w2) if need_grad else (pack_conv_weights_q(w2), None)
+            y1 = conv3x3_bn_relu(uq, w1q, one, zero, to_planes=False, precision=2, relu=False)
+            sc1, sh1, mu1, is1, ws1 = bn_batch_stats_q(y1, g1, b1, rm1, rv1, momentum, eps)
+            a1_nhwc, a1_q = bn_apply_q(y1, sc1, sh1, ws1, relu=True, nhwc=need_grad)
+            y2 = conv3x3_bn_relu(a1_q, w2q, one, zero, to_planes=False, precision=2, relu=False)
+        else:
+            up = pack_nhwc(u)
+            y1 = conv3x3_bn_relu(up, pack_conv_weights(w1), one, zero, to_planes=False, precision=prec3, relu=False)
+            sc1, sh1, mu1, is1 = bn_batch_stats(y1, g1, b1, rm1, rv1, momentum, eps, training)
+            a1_nhwc, _, _ = bn_apply(y1, sc1, sh1, relu=True, nhwc=True)
+            y2 = conv3x3_bn_relu(a1_nhwc, pack_conv_weights(w2), one, zero, to_planes=False, precision=prec3, relu=False)
         sc2, sh2, mu2, is2 = bn_batch_stats(y2, g2, b2, rm2, rv2, momentum, eps, training)
         _, _, out = bn_apply(y2, sc2, sh2, relu=True, f32=True, res=res)
         if need_grad:
             ctx.save_for_backward(up, w1, w2, y1, y2, a1_nhwc, sc1, sh1, mu1, is1, sc2, sh2, mu2, is2, one, zero)
-            ctx.cfg = (bool(training), int(precision))
+            ctx.cfg = (bool(training), prec3, q)
+            ctx.dgrad_q = (w1d, w2d) if q else None          # derived buffers, no autograd history
         return out
 
     @staticmethod
     def backward(ctx, g_out):
         up, w1, w2, y1, y2, a1_nhwc, sc1, sh1, mu1, is1, sc2, sh2, mu2, is2, one, zero = ctx.saved_tensors
-        training, precision = ctx.cfg
+        training, precision, q = ctx.cfg
         g_out = g_out.contiguous()
+        if q:
+            w1d, w2d = ctx.dgrad_q       # w'[ci][co][tap] = w[co][ci][8 - tap] in the q format, packed in forward
+            gy2_nhwc, gy2_q, gg2, gb2 = bn_backward_q(g_out, y2, sc2, sh2, mu2, is2, relu=True, training=training)
+            gw2 = conv3x3_wgrad(gy2_nhwc, a1_nhwc, precision)
+            g_a1 = conv3x3_bn_relu(gy2_q, w2d, one, zero, to_planes=False, precision=2, relu=False)
+            gy1_nhwc, gy1_q, gg1, gb1 = bn_backward_q(g_a1, y1, sc1, sh1, mu1, is1, relu=True, training=training)
+            gw1 = conv3x3_wgrad(gy1_nhwc, up, precision)
+            g_u = conv3x3_bn_relu(gy1_q, w1d, one, zero, to_planes=False, precision=2, relu=False)
+            return (g_u, g_out, gw1, gg1, gb1, None, None, gw2, gg2, gb2, None, None, None, None, None, None)
         gy2_nhwc, gg2, gb2 = bn_backward(g_out, y2, sc2, sh2, mu2, is2, relu=True, training=training)
         gw2 = conv3x3_wgrad(gy2_nhwc, a1_nhwc, precision)
         g_a1 = conv3x3_bn_relu(gy2_nhwc, pack_conv_weights_dgrad(w2), one, zero, to_planes=False, precision=precision,

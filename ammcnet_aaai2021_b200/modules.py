@@ -216,9 +216,10 @@ class bridge(nn.Module):
                 raise RuntimeError("ammc_b200: bfloat16 feature I/O is an inference variant; train with float32 tensors")
         if self.training or needs_graph:
             # batch-statistic BN and/or autograd: unfused pipeline (raw conv -> BN stats -> apply), tcgen05 dgrad/wgrad
-            prec = 3 if self.precision == 2 else self.precision
-            x = self.O2F.forward_autograd(zy, zx, prec)
-            y = self.F20.forward_autograd(zx, zy, prec)
+            # precision 2 stays 2 here: AmftBranchFn runs the forward / data-gradient convs on q operands when it can
+            # (training-mode BN with per-rank statistics) and falls back to the split-bf16 x3 kernels otherwise
+            x = self.O2F.forward_autograd(zy, zx, self.precision)
+            y = self.F20.forward_autograd(zx, zy, self.precision)
             return x, y
         # the memory modules' dec epilogue already wrote the NHWC operand planes of its output; otherwise pack here
         prec = self.eval_precision(zx.shape[1])

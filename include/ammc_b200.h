@@ -213,7 +213,13 @@ int ammc_pack_nhwc(const float* x, void* xp, int b, int C, int h, int w, void* s
 size_t ammc_q_act_bytes(int64_t n);
 size_t ammc_q_weight_bytes(int Cout, int K);
 int ammc_pack_nhwc_q(const float* x, void* xq, int b, int C, int h, int w, void* stream);
+/* the q buffer and the bf16 hi/lo planes [2][b,h,w,C] of the same tensor in one pass (training at precision 2: the forward
+ * conv takes the q operand, the weight gradient the bf16 planes); C % 8 == 0 */
+int ammc_pack_nhwc_q_planes(const float* x, void* xq, void* xp, int b, int C, int h, int w, void* stream);
 int ammc_pack_conv_weights_q(const float* w, void* wq, int Cout, int Cin, int taps, void* stream);
+/* forward and data-gradient q weights (w'[ci][co][tap] = w[co][ci][taps-1-tap]; buffer of ammc_q_weight_bytes(Cin, taps*Cout))
+ * of one weight tensor in one call: one max|w| reduction serves both */
+int ammc_pack_conv_weights_q_pair(const float* w, void* wq, void* wq_dgrad, int Cout, int Cin, int taps, void* stream);
 int ammc_conv3x3_bn_relu(const void* xp, const void* wp, const float* scale, const float* shift,
                          void* out_planes, float* out_nchw, const float* res_nchw,
                          int b, int Cin, int Cout, int h, int w, int precision, int relu, void* stream);
@@ -293,6 +299,23 @@ int ammc_conv1x1_bn_relu(const void* xp, const void* wp, const float* scale, con
 int ammc_bn_batch_stats(const float* y, const float* gamma, const float* beta, float* running_mean, float* running_var,
                         float* scale, float* shift, float* mean, float* invstd, void* workspace, size_t workspace_bytes,
                         int b, int C, int h, int w, float momentum, float eps, int training, void* stream);
+/* q-format variants for training at precision 2 (the forward and data-gradient convs of `bridge` take fp16 + e4m3 operands):
+ * the BatchNorm passes see every value that lands in an operand plane, so the planes' power-of-two scale comes out of their
+ * reductions as a bound -- per-channel max|y| in the statistics pass, max|g'| and max|yhat| in the backward reduction.
+ *   ammc_bn_batch_stats_q   = ammc_bn_batch_stats (training) + the bound on |act(y*scale+shift)|, left in `workspace`
+ *   ammc_bn_apply_q         relu(y*scale+shift) -> bf16 hi/lo NHWC planes (weight-gradient operand, may be NULL) and the q
+ *                           buffer out_q (ammc_q_act_bytes); `workspace` is the one ammc_bn_batch_stats_q filled
+ *   ammc_bn_backward_q      = ammc_bn_backward, g_y written as bf16 hi/lo planes (may be NULL) and as q planes
+ * workspace: ammc_bn_q_workspace_bytes(C) bytes.  Per-rank statistics (no staged / all-reduced form). */
+size_t ammc_bn_q_workspace_bytes(int C);
+int ammc_bn_batch_stats_q(const float* y, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                          float* scale, float* shift, float* mean, float* invstd, void* workspace, size_t workspace_bytes,
+                          int b, int C, int h, int w, float momentum, float eps, void* stream);
+int ammc_bn_apply_q(const float* y, const float* scale, const float* shift, int relu, void* out_nhwc_planes, void* out_q,
+                    const void* workspace, int b, int C, int h, int w, void* stream);
+int ammc_bn_backward_q(const float* g, const float* y, const float* scale, const float* shift, const float* mean,
+                       const float* invstd, int relu, int training, void* gy_nhwc_planes, void* gy_q, float* g_gamma,
+                       float* g_beta, void* workspace, size_t workspace_bytes, int b, int C, int h, int w, void* stream);
 int ammc_bn_apply(const float* y, const float* scale, const float* shift, int relu, void* out_nhwc_planes,
                   void* out_nchw_planes, float* out_f32, const float* res, int b, int C, int h, int w, void* stream);
 int ammc_bn_backward(const float* g, const float* y, const float* scale, const float* shift, const float* mean,

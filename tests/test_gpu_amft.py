@@ -257,11 +257,19 @@ def _relu_masks_of_branch(u, w1, g1, b1, w2, g2, b2):
     one, zero = torch.ones(C, device=DEV), torch.zeros(C, device=DEV)
     rm, rv = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
     d = lambda t: t.to(DEV)
-    y1 = F_.conv3x3_bn_relu(F_.pack_nhwc(d(u)), F_.pack_conv_weights(d(w1)), one, zero, to_planes=False, precision=3,
-                            relu=False)
-    sc1, sh1, _, _ = F_.bn_batch_stats(y1, d(g1), d(b1), rm.clone(), rv.clone(), 0.1, 1e-5, True)
-    a1p, _, a1 = F_.bn_apply(y1, sc1, sh1, relu=True, nhwc=True, f32=True)
-    y2 = F_.conv3x3_bn_relu(a1p, F_.pack_conv_weights(d(w2)), one, zero, to_planes=False, precision=3, relu=False)
+    if F_.q_conv_supported(C, C):       # the training path of bridge(precision=2) runs these layers on q operands
+        y1 = F_.conv3x3_bn_relu(F_.pack_nhwc_q(d(u)), F_.pack_conv_weights_q(d(w1)), one, zero, to_planes=False, precision=2,
+                                relu=False)
+        sc1, sh1, _, _, ws1 = F_.bn_batch_stats_q(y1, d(g1), d(b1), rm.clone(), rv.clone(), 0.1, 1e-5)
+        _, a1q = F_.bn_apply_q(y1, sc1, sh1, ws1, relu=True, nhwc=False)
+        _, _, a1 = F_.bn_apply(y1, sc1, sh1, relu=True, f32=True)
+        y2 = F_.conv3x3_bn_relu(a1q, F_.pack_conv_weights_q(d(w2)), one, zero, to_planes=False, precision=2, relu=False)
+    else:
+        y1 = F_.conv3x3_bn_relu(F_.pack_nhwc(d(u)), F_.pack_conv_weights(d(w1)), one, zero, to_planes=False, precision=3,
+                                relu=False)
+        sc1, sh1, _, _ = F_.bn_batch_stats(y1, d(g1), d(b1), rm.clone(), rv.clone(), 0.1, 1e-5, True)
+        a1p, _, a1 = F_.bn_apply(y1, sc1, sh1, relu=True, nhwc=True, f32=True)
+        y2 = F_.conv3x3_bn_relu(a1p, F_.pack_conv_weights(d(w2)), one, zero, to_planes=False, precision=3, relu=False)
     sc2, sh2, _, _ = F_.bn_batch_stats(y2, d(g2), d(b2), rm.clone(), rv.clone(), 0.1, 1e-5, True)
     _, _, a2 = F_.bn_apply(y2, sc2, sh2, relu=True, f32=True)
     return (a1 > 0).cpu(), (a2 > 0).cpu()
