@@ -35,6 +35,18 @@ def timed(fn, n=10):
     return a.elapsed_time(b) / n
 
 
+class gm_wrap:
+    """a graphed callable with the zero_grad interface `step` uses"""
+    def __init__(self, fn, mod):
+        self.fn, self.mod = fn, mod
+
+    def __call__(self, *a):
+        return self.fn(*a)
+
+    def zero_grad(self, set_to_none=True):
+        self.mod.zero_grad(set_to_none=set_to_none)
+
+
 def main():
     C = 512
     p = synth.amft_params(5, C)
@@ -89,6 +101,17 @@ def main():
         row["single_bf16_pass_gx_vs_cudnn_fp32"] = cmp(zx.grad.clone(), gx_ref)
         ours.precision = 2
         F_.check_pipeline_watchdog()
+        # the same step with forward and backward captured in CUDA graphs (torch.cuda.make_graphed_callables): what is left
+        # when the ~60 launches per branch are replayed instead of issued -- matters at the small per-GPU batch of configs[3]
+        for name, mod, tf32 in (("ours_graphed_ms", ours, False), ("cudnn_tf32_graphed_ms", ref, True)):
+            try:
+                torch.backends.cudnn.allow_tf32 = tf32
+                gm = torch.cuda.make_graphed_callables(mod, (zx.detach().clone().requires_grad_(True),
+                                                             zy.detach().clone().requires_grad_(True)))
+                row[name] = timed(step(gm_wrap(gm, mod)))
+            except Exception as e:                      # noqa: BLE001  (report, do not hide)
+                row[name] = "failed: %s" % (str(e).splitlines()[0][:160],)
+        torch.backends.cudnn.allow_tf32 = False
         res.append(row)
         print(json.dumps(row), flush=True)
     json.dump(res, open("gpurun_out/train_amft_bench.json", "w"), indent=1)
