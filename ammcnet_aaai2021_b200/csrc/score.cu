@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(PSNR_THREADS) psnr_partial_kernel(const float*
     is_last = atomicAdd(&tickets[frame], 1u) == (unsigned)(blocks_per_frame - 1);
   }
   __syncthreads();
-  if (is_last && threadIdx.x < 32) {                        // one warp, fixed summation order (as psnr_final_kernel)
+  if (is_last && threadIdx.x < 32) {                        // one warp, fixed summation order
     __threadfence();
     const volatile float* pf = partial + (size_t)frame * blocks_per_frame;
     float t = 0.f;
