@@ -66,3 +66,69 @@ def test_fp16_plus_e4m3_cross_terms_as_built(scale, looseness):
     assert err < 2e-4, err
     # without the cross terms the fp16 product alone is outside the budget two chained convolutions have
     assert (_conv(xh, wh) / (sx * sw) - ref).abs().max() / rms > err
+
+
+# --------------------------------------------------------------------------------------------------
+# addressing filter (csrc/addr_tc.cu): fp16 operands with power-of-two scales, rigorous margin, and the round-2 rule that
+# lets the filter DECIDE a row without any exact distance
+# --------------------------------------------------------------------------------------------------
+def _pow2_scale(bound):
+    """q_scale_for_bound for a tensor of bounds: largest power of two s with bound * s < 2^15"""
+    e = torch.frexp(bound)[1]                       # bound = m * 2^e, m in [0.5, 1)
+    return torch.ldexp(torch.ones_like(bound), 15 - e)
+
+
+def _filter_model(z, bank, k):
+    """The filter's arithmetic on the CPU: (approximate scores a~ [N,M], margin [N]) exactly as the kernel forms them,
+    up to the accumulation order of the MMA (covered by the margin's fp32 slack term)."""
+    D = z.shape[1]
+    s_n = _pow2_scale(z.abs().amax(1))                                   # per query row
+    t = _pow2_scale(bank.abs().max().reshape(1))                         # per bank
+    zq = (z * s_n[:, None]).to(torch.float16).float()
+    eq = (bank * t).to(torch.float16).float()                            # [D, M]
+    dot = zq @ eq                                                        # fp16 products are exact in fp32
+    en2 = (bank * bank).sum(0)
+    a = en2[None, :] + (-2.0 / (s_n * t))[:, None] * dot
+    zn = z.pow(2).sum(1).sqrt()
+    emax = en2.max().sqrt()
+    margin = 8 * 2.0 ** -11 * 1.01 * zn * emax + 2.0 ** -23 * (4 * D * zn * emax + D * emax ** 2 + 3 * (zn + emax) ** 2) + 1e-30
+    return a, margin
+
+
+def _exact_fp32_and_fp64(z, bank):
+    d32 = (z.pow(2).sum(1, keepdim=True) - 2 * (z @ bank)) + bank.pow(2).sum(0, keepdim=True)       # unet.py:283-288
+    z64, b64 = z.double(), bank.double()
+    d64 = (z64.pow(2).sum(1, keepdim=True) - 2 * (z64 @ b64)) + b64.pow(2).sum(0, keepdim=True)
+    return d32, d64
+
+
+@pytest.mark.parametrize("N,D,M,k,kind", [(3000, 64, 256, 2, "random"), (2000, 512, 2048, 2, "random"), (1500, 128, 700, 3, "random"),
+                                          (2000, 64, 256, 2, "clusters"), (1500, 256, 512, 2, "clusters"), (1000, 1024, 300, 1, "random")])
+def test_addressing_filter_margin_is_a_superset_and_its_decisions_are_exact(N, D, M, k, kind):
+    g = torch.Generator().manual_seed(N + D + M)
+    if kind == "random":
+        z, bank = torch.randn((N, D), generator=g), torch.randn((D, M), generator=g)
+    else:                                           # near-duplicate items, queries sitting on items, a few huge rows
+        base = torch.randn((D, M // 16), generator=g)
+        bank = base.repeat(1, 16) + 1e-3 * torch.randn((D, M), generator=g)
+        z = bank.t()[torch.randint(0, M, (N,), generator=g)] + 1e-4 * torch.randn((N, D), generator=g)
+        z[:50] *= 1e3
+    a, margin = _filter_model(z, bank, k)
+    d32, d64 = _exact_fp32_and_fp64(z, bank)
+    ksel = 2 if k <= 2 else 4
+    srt, order = a.sort(1)
+    thr = srt[:, ksel - 1] + margin                                    # final threshold of the row
+    cand = a <= thr[:, None]
+    top32 = d32.topk(k, dim=1, largest=False).indices
+    top64 = d64.topk(k, dim=1, largest=False).indices
+    # (1) the candidate set holds the exact top-k, of the fp32 evaluation the kernels rank by and of the fp64 truth
+    assert bool(cand.gather(1, top32).all()) and bool(cand.gather(1, top64).all())
+    # (2) rows the filter decides -- k candidates' consecutive scores, and the next survivor, more than `margin` apart --
+    # are ranked exactly as the exact distances rank them
+    gaps = srt[:, 1:k + 1] - srt[:, :k]
+    decided = (gaps > margin[:, None]).all(1)
+    assert bool(torch.equal(order[decided][:, :k], top32[decided])) and bool(torch.equal(order[decided][:, :k], top64[decided]))
+    frac = float(decided.float().mean())
+    print(kind, N, D, M, k, "decided by the filter: %.3f, mean candidates %.2f" % (frac, float(cand.sum(1).float().mean())))
+    if kind == "random":
+        assert frac > 0.2                           # on well-separated data the rule must actually fire
