@@ -132,3 +132,37 @@ def test_addressing_filter_margin_is_a_superset_and_its_decisions_are_exact(N, D
     print(kind, N, D, M, k, "decided by the filter: %.3f, mean candidates %.2f" % (frac, float(cand.sum(1).float().mean())))
     if kind == "random":
         assert frac > 0.2                           # on well-separated data the rule must actually fire
+
+
+# --------------------------------------------------------------------------------------------------
+# precision 2 in training (csrc/amft_train.cu): the q planes' power-of-two scales come from BOUNDS the BatchNorm reductions
+# deliver; a bound below the true maximum would saturate the fp16 plane
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("seed,scale", [(0, 1.0), (1, 1e-3), (2, 3e3)])
+def test_batchnorm_bounds_behind_the_training_q_scales(seed, scale):
+    g = torch.Generator().manual_seed(seed)
+    b, C, hw = 3, 16, 40
+    y = (torch.randn((b, C, hw), generator=g) * (0.2 + 3 * torch.rand((1, C, 1), generator=g)) + torch.randn((1, C, 1), generator=g)) * scale
+    gamma, beta = 0.5 + torch.rand((C,), generator=g), 0.3 * torch.randn((C,), generator=g)
+    gr = torch.randn((b, C, hw), generator=g) * (1 + 10 * torch.rand((1, C, 1), generator=g))
+    mean = y.mean((0, 2))
+    var = y.var((0, 2), unbiased=False)
+    invstd = 1 / (var + 1e-5).sqrt()
+    sc, sh = gamma * invstd, beta - mean * gamma * invstd
+    V = lambda t: t.view(1, C, 1)
+    # forward: |relu(y*scale+shift)| <= |scale| max|y| + |shift|   (bn_stats_kernel / bn_finalize_kernel)
+    act = torch.relu(y * V(sc) + V(sh))
+    bound_f = (sc.abs() * y.abs().amax((0, 2)) * 1.0001 + sh.abs()).max()
+    assert float(act.abs().max()) <= float(bound_f)
+    # backward: g_y = scale * (g' - mean(g') - yhat * mean(g' yhat)),  g' = g * [act > 0]
+    gp = gr * (act > 0)
+    yhat = (y - V(mean)) * V(invstd)
+    mg, mgy = gp.mean((0, 2)), (gp * yhat).mean((0, 2))
+    gy = V(sc) * (gp - V(mg) - yhat * V(mgy))
+    bound_b = (sc.abs() * (gp.abs().amax((0, 2)) + mg.abs() + yhat.abs().amax((0, 2)) * mgy.abs()) * 1.0001).max()
+    assert float(gy.abs().max()) <= float(bound_b)
+    # the scale derived from a bound keeps every value inside fp16's finite range and loses at most a few binades
+    for bound, vals in ((bound_f, act), (bound_b, gy)):
+        s = _pow2_scale(bound.reshape(1))
+        assert float((vals * s).abs().max()) < 2 ** 15
+        assert float(bound * s) >= 2 ** 14 and float(bound / vals.abs().max()) < 2 ** 6
