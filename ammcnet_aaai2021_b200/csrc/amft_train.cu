@@ -212,6 +212,82 @@ __global__ void __launch_bounds__(256) bn_apply_pack_kernel(const ApplyArgs a, i
   }
 }
 
+// Same transform for HW % 64 == 0, C % 64 == 0, no NCHW planes (the shipped shapes): tile = 64 channels x 64 pixels, the
+// NCHW side is walked with 16-byte accesses (256 contiguous bytes per channel row and pass instead of 128).
+__device__ __forceinline__ float bn_apply_one(const ApplyArgs& a, float yv, float gv, float sc, float sh, float mu, float is,
+                                              float mg, float mgy) {
+  const float act = fmaf(yv, sc, sh);
+  if (a.mode == 0) return a.relu ? fmaxf(act, 0.f) : act;
+  float gp = gv;
+  if (a.relu && !(act > 0.f)) gp = 0.f;
+  if (a.mode == 1) return sc * (gp - mg - (yv - mu) * is * mgy);
+  return sc * gp;
+}
+
+__global__ void __launch_bounds__(256, 4) bn_apply_pack64_kernel(const ApplyArgs a, int C, int HW) {
+  __shared__ float tile[64][65];
+  const int img = blockIdx.z, c0 = blockIdx.y * 64, p0 = blockIdx.x * 64;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;       // 16 float4 lanes per channel row, 16 rows per pass
+  float4 yv[4], gv[4], rv[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const size_t o = ((size_t)img * C + c0 + ty + 16 * i) * HW + p0 + 4 * tx;
+    yv[i] = __ldg(reinterpret_cast<const float4*>(a.y + o));
+    gv[i] = a.mode != 0 ? __ldg(reinterpret_cast<const float4*>(a.g + o)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    rv[i] = (a.out_f32 && a.res) ? __ldg(reinterpret_cast<const float4*>(a.res + o)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = ty + 16 * i, c = c0 + r;
+    const float sc = __ldg(a.scale + c), sh = __ldg(a.shift + c);
+    float mu = 0.f, is = 0.f, mg = 0.f, mgy = 0.f;
+    if (a.mode == 1) {
+      mu = __ldg(a.mean + c); is = __ldg(a.invstd + c);
+      mg = (float)(a.bsums[c] * a.inv_count); mgy = (float)(a.bsums[C + c] * a.inv_count);
+    }
+    float4 v;
+    v.x = bn_apply_one(a, yv[i].x, gv[i].x, sc, sh, mu, is, mg, mgy);
+    v.y = bn_apply_one(a, yv[i].y, gv[i].y, sc, sh, mu, is, mg, mgy);
+    v.z = bn_apply_one(a, yv[i].z, gv[i].z, sc, sh, mu, is, mg, mgy);
+    v.w = bn_apply_one(a, yv[i].w, gv[i].w, sc, sh, mu, is, mg, mgy);
+    if (a.out_f32) {
+      const size_t o = ((size_t)img * C + c) * HW + p0 + 4 * tx;
+      *reinterpret_cast<float4*>(a.out_f32 + o) = make_float4(v.x + rv[i].x, v.y + rv[i].y, v.z + rv[i].z, v.w + rv[i].w);
+    }
+    tile[r][4 * tx + 0] = v.x; tile[r][4 * tx + 1] = v.y; tile[r][4 * tx + 2] = v.z; tile[r][4 * tx + 3] = v.w;
+  }
+  if (!a.nhwc && !a.q16) return;
+  __syncthreads();
+  float qs = 1.f;
+  if (a.q16) {
+    qs = q_scale_for_bound(__uint_as_float(__ldg(a.q_bound)));
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) *a.q_scale_out = qs;
+  }
+  const int cg = threadIdx.x & 7, c = c0 + cg * 8;
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+    const int px = (threadIdx.x >> 3) + 32 * hh;               // pixel within the tile
+    const size_t o = ((size_t)img * HW + p0 + px) * C + c;
+    if (a.nhwc) {
+      uint32_t hp[4], lp[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) ptx::split_pack_bf16x2(tile[cg * 8 + 2 * j][px], tile[cg * 8 + 2 * j + 1][px], hp[j], lp[j]);
+      __nv_bfloat16* dst = a.nhwc + o;
+      *reinterpret_cast<uint4*>(dst) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+      *reinterpret_cast<uint4*>(dst + a.plane_stride) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+    }
+    if (a.q16) {
+      uint32_t h16[4], h8[4], l8[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        ptx::split_pack_q(tile[cg * 8 + 2 * j][px] * qs, tile[cg * 8 + 2 * j + 1][px] * qs, h16[j], h8[j], l8[j]);
+      *reinterpret_cast<uint4*>(a.q16 + o) = make_uint4(h16[0], h16[1], h16[2], h16[3]);
+      *reinterpret_cast<uint2*>(a.q8 + o) = make_uint2(h8[0] | (h8[1] << 16), h8[2] | (h8[3] << 16));
+      *reinterpret_cast<uint2*>(a.q8 + a.plane_stride + o) = make_uint2(l8[0] | (l8[1] << 16), l8[2] | (l8[3] << 16));
+    }
+  }
+}
+
 // sums[c] += sum g', sums[C+c] += sum g' * yhat
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restrict__ g, const float* __restrict__ y,
                                                              const float* __restrict__ scale, const float* __restrict__ shift,
@@ -597,6 +673,12 @@ static int launch_apply(const ApplyArgs& a, int b, int C, int h, int w, cudaStre
   AMMC_REQUIRE(b <= 65535, "batch %d too large for one launch", b);
   const int HW = h * w;
   AMMC_REQUIRE(!a.nhwc || C % 8 == 0, "NHWC plane output needs C %% 8 == 0 (got %d)", C);
+  const bool aligned16 = (((uintptr_t)a.y | (uintptr_t)a.g | (uintptr_t)a.res | (uintptr_t)a.out_f32) & 15) == 0;
+  if (HW % 64 == 0 && C % 64 == 0 && !a.nchw && aligned16) {
+    bn_apply_pack64_kernel<<<dim3(HW / 64, C / 64, b), 256, 0, st>>>(a, C, HW);
+    AMMC_LAUNCH_CHECK("bn_apply_pack64_kernel");
+    return 0;
+  }
   bn_apply_pack_kernel<<<dim3(ceil_div(HW, 32), ceil_div(C, 64), b), 256, 0, st>>>(a, C, HW);
   AMMC_LAUNCH_CHECK("bn_apply_pack_kernel");
   return 0;
