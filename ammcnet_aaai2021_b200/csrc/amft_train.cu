@@ -41,10 +41,21 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__
   const int i0 = blockIdx.y * imgs_per_split, i1 = min(b, i0 + imgs_per_split);
   double s = 0.0, s2 = 0.0;
   float am = 0.f;
+  const bool vec = (hw & 3) == 0 && ((uintptr_t)y & 15) == 0;      // 16-byte loads: one 4 KB channel row per block pass
   for (int img = i0; img < i1; ++img) {
     const float* p = y + ((size_t)img * C + c) * hw;
     float fs = 0.f, fs2 = 0.f;
-    for (int i = threadIdx.x; i < hw; i += 256) { const float v = p[i]; fs += v; fs2 = fmaf(v, v, fs2); am = fmaxf(am, fabsf(v)); }
+    if (vec) {
+      const float4* p4 = reinterpret_cast<const float4*>(p);
+      for (int i = threadIdx.x; i < (hw >> 2); i += 256) {
+        const float4 v = __ldg(p4 + i);
+        fs += (v.x + v.y) + (v.z + v.w);
+        fs2 = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, fs2))));
+        am = fmaxf(am, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+      }
+    } else {
+      for (int i = threadIdx.x; i < hw; i += 256) { const float v = p[i]; fs += v; fs2 = fmaf(v, v, fs2); am = fmaxf(am, fabsf(v)); }
+    }
     s += (double)fs; s2 += (double)fs2;
   }
   if (amax) {

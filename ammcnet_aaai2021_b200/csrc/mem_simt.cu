@@ -672,9 +672,49 @@ __global__ void __launch_bounds__(256) pack_nhwc64_kernel(const float* __restric
   }
 }
 
+// HW % 64 == 0, C % 64 == 0, 16-byte aligned x: 64 x 64 tiles, 16-byte accesses on both sides (256 contiguous bytes per
+// channel row and pass on the NCHW side instead of 128)
+__global__ void __launch_bounds__(256, 4) pack_nhwc64x64_kernel(const float* __restrict__ g, __nv_bfloat16* __restrict__ gp, int C,
+                                                                 int HW, long long plane_stride) {
+  __shared__ float tile[64][65];
+  const int img = blockIdx.z, c0 = blockIdx.y * 64, p0 = blockIdx.x * 64;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float4 v[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    v[i] = __ldg(reinterpret_cast<const float4*>(g + ((size_t)img * C + c0 + ty + 16 * i) * HW + p0 + 4 * tx));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = ty + 16 * i;
+    tile[r][4 * tx + 0] = v[i].x; tile[r][4 * tx + 1] = v[i].y; tile[r][4 * tx + 2] = v[i].z; tile[r][4 * tx + 3] = v[i].w;
+  }
+  __syncthreads();
+  const int cg = threadIdx.x & 7;
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+    const int px = (threadIdx.x >> 3) + 32 * hh;
+    uint32_t hp[4], lp[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float v0 = tile[cg * 8 + 2 * j][px], v1 = tile[cg * 8 + 2 * j + 1][px];
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+      const __nv_bfloat16 l0 = __float2bfloat16_rn(v0 - __bfloat162float(h0));
+      const __nv_bfloat16 l1 = __float2bfloat16_rn(v1 - __bfloat162float(h1));
+      hp[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+      lp[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    }
+    __nv_bfloat16* dst = gp + ((size_t)img * HW + p0 + px) * C + c0 + cg * 8;
+    *reinterpret_cast<uint4*>(dst) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+    *reinterpret_cast<uint4*>(dst + plane_stride) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+  }
+}
+
 int pack_nhwc64(const float* x, void* xp, int b, int C, int HW, cudaStream_t st) {     // C % 8 == 0
-  pack_nhwc64_kernel<<<dim3(ceil_div(HW, 32), ceil_div(C, 64), b), 256, 0, st>>>(x, (__nv_bfloat16*)xp, C, HW,
-                                                                                  (long long)b * HW * C);
+  if (HW % 64 == 0 && C % 64 == 0 && ((uintptr_t)x & 15) == 0)
+    pack_nhwc64x64_kernel<<<dim3(HW / 64, C / 64, b), 256, 0, st>>>(x, (__nv_bfloat16*)xp, C, HW, (long long)b * HW * C);
+  else
+    pack_nhwc64_kernel<<<dim3(ceil_div(HW, 32), ceil_div(C, 64), b), 256, 0, st>>>(x, (__nv_bfloat16*)xp, C, HW,
+                                                                                    (long long)b * HW * C);
   AMMC_LAUNCH_CHECK("pack_nhwc64_kernel");
   return 0;
 }
@@ -1316,10 +1356,8 @@ extern "C" int ammc_mem_bwd(const float* x, const float* enc_w, const float* emb
       __nv_bfloat16* rdpl = ws.take<__nv_bfloat16>((size_t)2 * N * k * D);
       float* gdwT = ws.take<float>((size_t)k * D * C);
       if (!ws.ok()) return fail(AMMC_EWORKSPACE, "workspace too small");
-      const dim3 pgrid(ceil_div(HW, 32), ceil_div(C, 64), b);
-      pack_nhwc64_kernel<<<pgrid, 256, 0, st>>>(x, xpl, C, HW, (long long)N * C);
-      pack_nhwc64_kernel<<<pgrid, 256, 0, st>>>(g_out, gopl, C, HW, (long long)N * C);
-      AMMC_LAUNCH_CHECK("pack_nhwc64_kernel");
+      if (int rc = pack_nhwc64(x, xpl, b, C, HW, st)) return rc;
+      if (int rc = pack_nhwc64(g_out, gopl, b, C, HW, st)) return rc;
       {
         const int per = max(1, b / 8);
         channel_sum_kernel<<<dim3(C, ceil_div(b, per)), 256, 0, st>>>(g_out, g_dec_b, b, C, HW, per);
