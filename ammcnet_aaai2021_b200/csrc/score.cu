@@ -22,17 +22,11 @@ __device__ __forceinline__ float sqdiff01(float g, float t) {
   return d * d;
 }
 
-// One launch: every block leaves the partial sum of its slice; the LAST block of a frame to finish (ticket counter, zeroed
-// by the host) adds the frame's partials in a fixed order and writes the PSNR -- deterministic, and the second launch with
-// its dependency gap (a quarter of the time at 64 frames) is gone.
 __global__ void __launch_bounds__(PSNR_THREADS) psnr_partial_kernel(const float* __restrict__ gen,
                                                                     const float* __restrict__ gt,
                                                                     float* __restrict__ partial, int64_t elems,
-                                                                    int blocks_per_frame, int vec_ok,
-                                                                    unsigned* __restrict__ tickets, float* __restrict__ psnr,
-                                                                    float inv_elems) {
+                                                                    int blocks_per_frame, int vec_ok) {
   __shared__ float red[33];
-  __shared__ int is_last;
   const int frame = blockIdx.y;
   const float* g = gen + (size_t)frame * elems;
   const float* t = gt + (size_t)frame * elems;
@@ -62,20 +56,19 @@ __global__ void __launch_bounds__(PSNR_THREADS) psnr_partial_kernel(const float*
     for (int64_t e = beg + threadIdx.x; e < end; e += PSNR_THREADS) s += sqdiff01(g[e], t[e]);
   }
   s = block_sum(s, red);
-  if (threadIdx.x == 0) {
-    partial[(size_t)frame * blocks_per_frame + blockIdx.x] = s;
-    __threadfence();                                        // the partial is visible before the ticket is taken
-    is_last = atomicAdd(&tickets[frame], 1u) == (unsigned)(blocks_per_frame - 1);
-  }
-  __syncthreads();
-  if (is_last && threadIdx.x < 32) {                        // one warp, fixed summation order
-    __threadfence();
-    const volatile float* pf = partial + (size_t)frame * blocks_per_frame;
-    float t = 0.f;
-    for (int i = threadIdx.x; i < blocks_per_frame; i += 32) t += pf[i];
-    t = warp_sum(t);
-    if (threadIdx.x == 0) psnr[frame] = 10.f * log10f(__fdiv_rn(1.0f, __fmul_rn(inv_elems, t)));  // utils.py:147
-  }
+  if (threadIdx.x == 0) partial[(size_t)frame * blocks_per_frame + blockIdx.x] = s;
+}
+
+__global__ void psnr_final_kernel(const float* __restrict__ partial, float* __restrict__ psnr, int n,
+                                  int blocks_per_frame, float inv_elems) {
+  // one warp per frame; fixed summation order -> deterministic
+  const int frame = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (frame >= n) return;
+  float s = 0.f;
+  for (int i = lane; i < blocks_per_frame; i += 32) s += partial[(size_t)frame * blocks_per_frame + i];
+  s = warp_sum(s);
+  if (lane == 0) psnr[frame] = 10.f * log10f(__fdiv_rn(1.0f, __fmul_rn(inv_elems, s)));  // utils.py:147
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -155,7 +148,7 @@ using namespace ammc;
 
 extern "C" size_t ammc_psnr_workspace_bytes(int n, int64_t elems) {
   int bpf = ceil_div(elems, PSNR_ELEMS_PER_BLOCK);
-  return align_up((size_t)n * bpf * 4, 256) + align_up((size_t)n * 4, 256);      // partials + per-frame tickets
+  return align_up((size_t)n * bpf * 4, 256);
 }
 
 extern "C" int ammc_psnr_batch(const float* gen, const float* gt, float* psnr, void* workspace,
@@ -169,11 +162,10 @@ extern "C" int ammc_psnr_batch(const float* gen, const float* gt, float* psnr, v
     return fail(AMMC_EWORKSPACE, "workspace too small");
   float* partial = (float*)workspace;
   const int vec_ok = (elems % 4 == 0) && ((uintptr_t)gen % 16 == 0) && ((uintptr_t)gt % 16 == 0);
-  unsigned* tickets = reinterpret_cast<unsigned*>((char*)workspace + align_up((size_t)n * bpf * 4, 256));
-  AMMC_CUDA_CHECK(cudaMemsetAsync(tickets, 0, (size_t)n * 4, st));
-  psnr_partial_kernel<<<dim3(bpf, n), PSNR_THREADS, 0, st>>>(gen, gt, partial, elems, bpf, vec_ok, tickets, psnr,
-                                                             (float)(1.0 / (double)elems));
+  psnr_partial_kernel<<<dim3(bpf, n), PSNR_THREADS, 0, st>>>(gen, gt, partial, elems, bpf, vec_ok);
   AMMC_LAUNCH_CHECK("psnr_partial_kernel");
+  psnr_final_kernel<<<ceil_div(n, 8), 256, 0, st>>>(partial, psnr, n, bpf, (float)(1.0 / (double)elems));
+  AMMC_LAUNCH_CHECK("psnr_final_kernel");
   return 0;
 }
 

@@ -1006,7 +1006,7 @@ def psnr_per_frame(gen: torch.Tensor, gt: torch.Tensor) -> torch.Tensor:
     ws = _workspace(lib.ammc_psnr_workspace_bytes(n, elems), gen.device)
     with torch.cuda.device(gen.device):
         _capi.call("ammc_psnr_batch", _p(g), _p(t), _p(out), _p(ws), ws.numel(), n, elems, _stream())
-    _count(1)
+    _count(2)
     return out
 
 
