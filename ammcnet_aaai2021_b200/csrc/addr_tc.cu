@@ -10,16 +10,22 @@
 // operands, Cauchy-Schwarz), so with margin = 8 u (1 + 1%) ||z|| max||e|| (+ fp32 accumulation slack) the kept set is a
 // superset of the exact top-k.  fp16 instead of bf16 shrinks that margin -- and with it the candidate lists -- eightfold:
 // at D = 1024, M = 8192 the bf16 margin admitted ~11 items per column half (lists of 12 overflowed on 6 % of the rows,
-// each paying an exact scan of the whole bank), the fp16 margin ~2-3.  `refine_kernel` then recomputes the candidates'
-// exact fp32 distances with the SAME arithmetic as the generic fp32 path (mem_simt.cu) and ranks them; rows whose list
-// still overflowed (near-degenerate neighbourhoods) are re-scanned exactly over all M items, so the indices are
+// each paying an exact scan of the whole bank), the fp16 margin ~2-3.  Rows whose k best approximate scores (and the next
+// survivor) lie more than the margin apart are ranked by the filter itself; for the others the tail recomputes the
+// candidates' exact fp32 distances with the SAME arithmetic as the generic fp32 path (mem_simt.cu) and ranks them; rows whose
+// list still overflowed (near-degenerate neighbourhoods) are re-scanned exactly over all M items, so the indices are
 // bit-identical to the fp32 path for every input; the number of such rows is reported in the stats block.
 //
-//   addr_tc_kernel<BLOCK_N>   persistent; per 128-query tile loops over item tiles; TMA (128B swizzle) -> smem ->
-//                             tcgen05.mma (M128 x N BLOCK_N x K16, fp32 accum in TMEM, 2 accumulator buffers);
-//                             4 epilogue warps: tcgen05.ld -> a~ -> running top-8 in registers across item tiles.
-//   refine_kernel<K>          4-lane team per query: exact distances of the candidates, top-k, miss test / exact
-//                             fallback, gathers (read, q1), per-pixel SSE, EMA statistics.
+//   addr_tc_kernel<BLOCK_N, KSEL, SWEEP>   persistent; per 128-query tile loops over item tiles; TMA (128B swizzle) -> smem
+//                             -> tcgen05.mma (M128 x N BLOCK_N x K16, fp32 accum in TMEM, 2 accumulator buffers); 8 epilogue
+//                             warps: tcgen05.ld -> a~ -> the KSEL best and every column within the margin (two passes per
+//                             tile, or one sweep with a running threshold for long banks); at the end of a query tile the
+//                             two column halves are merged and the row is DECIDED when the approximate ranking is proven
+//   addr_tail_kernel<K>       D >= 128, warp per query: decided rows are a pure gather; the others get the exact fp32
+//                             distances of their candidates (same fmaf chains as the fp32 kernel), then the same gather
+//   refine_kernel<K>          D = 64, 4-lane team per query: exact distances of the candidates, top-k, gathers (read, q1),
+//                             per-pixel SSE, EMA statistics
+//   rescan_kernel<K>          exact scan over all items for rows whose candidate list overflowed (rare)
 #include "common.cuh"
 #include "ptx.cuh"
 #include "topk.cuh"

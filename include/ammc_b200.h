@@ -130,10 +130,16 @@ int ammc_cast_f32_bf16(const float* src, void* dst_bf16, int64_t n, void* stream
  *                               [2^14, 2^15): no overflow, no lost small rows), zmeta [N,2] = (||z_n||^2, 1 / s_n)
  *   ammc_addr_pack_bank         embed [D,M] -> bank_t [M,D] fp32, en2 [M], bank_hi [Mpad,D] fp16 of the bank scaled by one power
  *                               of two t, en2pad [Mpad], emax [4] = {max ||e||, 1 / t, scratch, -}
- *   ammc_addr_filter            zp x bank_hi on tcgen05 (kind::f16, fp32 accumulate) -> cand [N,24] int32 (-1 = empty slot; a
- *                               guaranteed superset of the exact top-k unless a half overflowed: every item whose approximate
- *                               score lies within 8 * 2^-11 * ||z|| max||e|| of the k-th smallest), cand_cnt [N,2] (hits per
- *                               column half; > 12 = overflow -> the refine stage re-scans that query exactly) */
+ *   ammc_addr_filter            zp x bank_hi on tcgen05 (kind::f16, fp32 accumulate) -> per query the merged candidate list
+ *                               cand [N,24] int32 and cand_cnt [N,2]:
+ *                                 cand_cnt[n][0] = entries used.  The list is a guaranteed superset of the exact top-k:
+ *                                 every item whose approximate score lies within the margin (8 * 2^-11 * ||z|| max||e|| +
+ *                                 an fp32 evaluation slack) of the k-th smallest.  > 24 = a list overflowed -> the tail
+ *                                 re-scans that query exactly over all items;
+ *                                 cand_cnt[n][1] = 1 when the filter DECIDED the row: the k best approximate scores (and
+ *                                 the next survivor) lie more than the margin apart, so cand[n][0..k) are the final
+ *                                 indices in rank order and no exact distance is needed; 0 = the tail ranks the
+ *                                 candidates by their exact fp32 distances */
 #define AMMC_ADDR_CAND 24
 int ammc_addr_padded_items(int M);
 int ammc_addr_pack_queries(const float* z, void* zp, float* zmeta, int64_t N, int D, void* stream);
