@@ -188,8 +188,11 @@ class bridge(nn.Module):
     """AMFT: x' = zx + O2F(zy), y' = zy + F20(zx) (reference unet.py:956-965).
 
     `precision` = 2 (default): fp16 main product + e4m3 cross terms on tcgen05, fp32-parity numerics at two tensor-core
-                  pass-equivalents (eval / no-grad forward, channels % 256 == 0; other cases run precision 3);
-    `precision` = 3: split-bf16 three-pass convolution, fp32-parity numerics (also the training / autograd path);
+                  pass-equivalents -- the eval / no-grad forward and, in training with per-rank BatchNorm statistics, the
+                  forward and data-gradient convs (channels % 256 == 0; other cases, global-batch BatchNorm, eval-mode BN
+                  under autograd and every weight gradient run precision 3);
+    `precision` = 3: split-bf16 three-pass convolution, fp32-parity numerics;
+    bf16 inputs (both): the bf16 feature-I/O variant -- same arithmetic, bf16 residuals in and bf16 results out (inference);
     `precision` = 1: single bf16 pass (the "bf16 variant", stated separately in every report).
     """
 
