@@ -319,7 +319,9 @@ template <int MODE> struct PairCfg {
 constexpr int PAIR_EPI_WARPS = 8;
 constexpr int PAIR_THREADS = 64 + 32 * PAIR_EPI_WARPS;    // warp 0: TMA, warp 1: MMA, warps 2-9: epilogue
 
-template <int MODE>
+// IO16: out_nchw / res_nchw are bf16 NCHW tensors (bf16 feature-I/O variant) -- a compile-time variant, so that the fp32
+// kernels carry none of its branches
+template <int MODE, bool IO16 = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1)
 conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                        const __grid_constant__ CUtensorMap tmA8, const __grid_constant__ CUtensorMap tmB8, const ConvParams p) {
@@ -583,7 +585,7 @@ conv_igemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       // 16 columns at a time, software-pipelined two chunks deep: the residual loads of chunks c+1 and c+2 are in
       // flight while chunk c is converted and stored (the loads are the only latency on the epilogue's critical path)
       float rv0[16], rv1[16];
-      const bool io16 = p.io_bf16 != 0;
+      constexpr bool io16 = IO16;
       const unsigned short* const res16 = reinterpret_cast<const unsigned short*>(p.res_nchw);
       auto load_res = [&](size_t i) -> float {
         return io16 ? __uint_as_float((uint32_t)__ldg(res16 + i) << 16) : __ldg(p.res_nchw + i);
@@ -1090,16 +1092,24 @@ int conv_run(const ammc_conv_layer& L, cudaStream_t st) {
       AMMC_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_pair_kernel<PAIR_STREAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM));
       AMMC_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_pair_kernel<PAIR_FUSED3>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM));
       AMMC_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_pair_kernel<PAIR_Q>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM));
+      AMMC_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_pair_kernel<PAIR_STREAM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM));
+      AMMC_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_pair_kernel<PAIR_FUSED3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM));
+      AMMC_CUDA_CHECK(cudaFuncSetAttribute(conv_igemm_pair_kernel<PAIR_Q, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Q_SMEM));
       configured[dev] = true;
     }
     const int pair_tiles = ((p.tiles_m + 1) / 2) * p.tiles_n;
     const int clusters = min(num_sms() / 2, pair_tiles);
-    if (qmode)
-      conv_igemm_pair_kernel<PAIR_Q><<<2 * clusters, PAIR_THREADS, Q_SMEM, st>>>(tmA, tmB, tmA8, tmB8, p);
-    else if (L.precision == 3 && g_conv_fused3)
-      conv_igemm_pair_kernel<PAIR_FUSED3><<<2 * clusters, PAIR_THREADS, PAIR_SMEM, st>>>(tmA, tmB, tmA, tmB, p);
-    else
-      conv_igemm_pair_kernel<PAIR_STREAM><<<2 * clusters, PAIR_THREADS, PAIR_SMEM, st>>>(tmA, tmB, tmA, tmB, p);
+    const bool io16 = p.io_bf16 != 0;
+    if (qmode) {
+      if (io16) conv_igemm_pair_kernel<PAIR_Q, true><<<2 * clusters, PAIR_THREADS, Q_SMEM, st>>>(tmA, tmB, tmA8, tmB8, p);
+      else conv_igemm_pair_kernel<PAIR_Q><<<2 * clusters, PAIR_THREADS, Q_SMEM, st>>>(tmA, tmB, tmA8, tmB8, p);
+    } else if (L.precision == 3 && g_conv_fused3) {
+      if (io16) conv_igemm_pair_kernel<PAIR_FUSED3, true><<<2 * clusters, PAIR_THREADS, PAIR_SMEM, st>>>(tmA, tmB, tmA, tmB, p);
+      else conv_igemm_pair_kernel<PAIR_FUSED3><<<2 * clusters, PAIR_THREADS, PAIR_SMEM, st>>>(tmA, tmB, tmA, tmB, p);
+    } else {
+      if (io16) conv_igemm_pair_kernel<PAIR_STREAM, true><<<2 * clusters, PAIR_THREADS, PAIR_SMEM, st>>>(tmA, tmB, tmA, tmB, p);
+      else conv_igemm_pair_kernel<PAIR_STREAM><<<2 * clusters, PAIR_THREADS, PAIR_SMEM, st>>>(tmA, tmB, tmA, tmB, p);
+    }
     AMMC_LAUNCH_CHECK("conv_igemm_pair_kernel");
     return 0;
   }
