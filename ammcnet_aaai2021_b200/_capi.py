@@ -94,6 +94,9 @@ SIGNATURES = {
     "ammc_frame_losses_workspace_bytes": (Z, [I, I, I]),
     "ammc_frame_losses_fwd": (I, [P, P, P, P, Z, I, I, I, I, P]),
     "ammc_frame_losses_bwd": (I, [P, P, P, P, P, I, I, I, I, P]),
+    "ammc_elem_loss_workspace_bytes": (Z, [L]),
+    "ammc_elem_loss_fwd": (I, [P, P, P, I, L, P, Z, P]),
+    "ammc_elem_loss_bwd": (I, [P, P, P, P, P, I, L, P]),
     "ammc_psnr_workspace_bytes": (Z, [I, L]),
     "ammc_psnr_batch": (I, [P, P, P, P, Z, I, L, P]),
     "ammc_score_workspace_bytes": (Z, [L, I]),

@@ -149,3 +149,138 @@ extern "C" int ammc_frame_losses_bwd(const float* gen, const float* gt, const fl
   AMMC_LAUNCH_CHECK("frame_loss_bwd_kernel");
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------------------------------------
+// Element-wise mean objectives of the training step (reference Code/models/losses/losses_utils.py:10-15,103-113; consumer
+// Code/models/losses/loss_zoo.py:331-336 and Code/run_helper/train_helper.py:318-326):
+//   ELEM_L1        Flow_Loss          mean |a - b|
+//   ELEM_LSGAN_G   Adversarial_Loss   mean (a - 1)^2 / 2                       (a = discriminator map of the prediction)
+//   ELEM_LSGAN_D   Discriminate_Loss  mean (a - 1)^2 / 2 + mean b^2 / 2        (a = map of the real frame, b = of the fake)
+// The reference spends 3-6 ATen kernels + their autograd twins per objective; here one grid-stride pass (16-byte loads when
+// both pointers allow) + the fixed-order final sum, and one pass for the gradient.  HBM-bound: 4 bytes per element read.
+// ------------------------------------------------------------------------------------------------------------------------
+namespace ammc {
+
+enum { ELEM_L1 = 0, ELEM_LSGAN_G = 1, ELEM_LSGAN_D = 2 };
+
+template <int MODE>
+__device__ __forceinline__ void elem_terms(float a, float b, float& sa, float& sb) {
+  if (MODE == ELEM_L1) sa += fabsf(a - b);
+  else if (MODE == ELEM_LSGAN_G) sa = fmaf(0.5f * (a - 1.f), a - 1.f, sa);
+  else { sa = fmaf(0.5f * (a - 1.f), a - 1.f, sa); sb = fmaf(0.5f * b, b, sb); }
+}
+
+// partial[2*block] = sum of the a-terms, partial[2*block+1] = sum of the b-terms (ELEM_LSGAN_D only) over the block's share;
+// n = element count shared by a and b (ELEM_LSGAN_D with maps of different sizes runs as two ELEM_LSGAN_G-style launches)
+template <int MODE, bool VEC>
+__global__ void __launch_bounds__(256) elem_loss_partial_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                                 float* __restrict__ partial, int64_t n) {
+  __shared__ float red[33];
+  float sa = 0.f, sb = 0.f;
+  const int64_t stride = (int64_t)gridDim.x * 256, t = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (VEC) {
+    const int64_t n4 = n >> 2;
+    for (int64_t i = t; i < n4; i += stride) {
+      const float4 va = reinterpret_cast<const float4*>(a)[i];
+      float4 vb = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (MODE != ELEM_LSGAN_G) vb = reinterpret_cast<const float4*>(b)[i];
+      elem_terms<MODE>(va.x, vb.x, sa, sb); elem_terms<MODE>(va.y, vb.y, sa, sb);
+      elem_terms<MODE>(va.z, vb.z, sa, sb); elem_terms<MODE>(va.w, vb.w, sa, sb);
+    }
+    for (int64_t i = (n4 << 2) + t; i < n; i += stride) elem_terms<MODE>(a[i], MODE != ELEM_LSGAN_G ? b[i] : 0.f, sa, sb);
+  } else {
+    for (int64_t i = t; i < n; i += stride) elem_terms<MODE>(a[i], MODE != ELEM_LSGAN_G ? b[i] : 0.f, sa, sb);
+  }
+  const float ra = block_sum(sa, red);
+  __syncthreads();
+  const float rb = MODE == ELEM_LSGAN_D ? block_sum(sb, red) : 0.f;
+  if (threadIdx.x == 0) { partial[2 * blockIdx.x] = ra; partial[2 * blockIdx.x + 1] = rb; }
+}
+
+// out[0] = (sum of a-partials + sum of b-partials) / n, fixed summation order (deterministic)
+__global__ void __launch_bounds__(256) elem_loss_final_kernel(const float* __restrict__ partial, float* __restrict__ out,
+                                                               int n_partials, double inv_count) {
+  __shared__ double red[8];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < 2 * n_partials; i += 256) s += (double)partial[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < 8; ++i) t += red[i];
+    out[0] = (float)(t * inv_count);
+  }
+}
+
+// grad_a = g * d/da, grad_b = g * d/db (either may be NULL; ELEM_LSGAN_G has no b)
+template <int MODE>
+__global__ void __launch_bounds__(256) elem_loss_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                             const float* __restrict__ g, float* __restrict__ grad_a,
+                                                             float* __restrict__ grad_b, int64_t n, float inv_count) {
+  const float k = g[0] * inv_count;
+  const int64_t stride = (int64_t)gridDim.x * 256;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) {
+    if (MODE == ELEM_L1) {
+      const float d = a[i] - b[i];
+      const float s = k * sgn(d);
+      if (grad_a) grad_a[i] = s;
+      if (grad_b) grad_b[i] = -s;
+    } else {
+      if (grad_a) grad_a[i] = k * (a[i] - 1.f);
+      if (MODE == ELEM_LSGAN_D && grad_b) grad_b[i] = k * b[i];
+    }
+  }
+}
+
+static inline int elem_blocks(int64_t n) {
+  const int64_t want = (n + 256 * 8 - 1) / (256 * 8);            // ~8 elements per thread before the grid stops growing
+  const int64_t cap = (int64_t)num_sms() * 8;
+  return (int)(want < 1 ? 1 : (want > cap ? cap : want));
+}
+
+}  // namespace ammc
+
+extern "C" size_t ammc_elem_loss_workspace_bytes(int64_t n) {
+  return align_up((size_t)elem_blocks(n > 0 ? n : 1) * 2 * sizeof(float), 256);
+}
+
+extern "C" int ammc_elem_loss_fwd(const float* a, const float* b, float* out1, int mode, int64_t n, void* workspace,
+                                  size_t workspace_bytes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  AMMC_REQUIRE(a && out1 && n > 0, "bad argument");
+  AMMC_REQUIRE(mode >= ELEM_L1 && mode <= ELEM_LSGAN_D, "unknown objective %d", mode);
+  AMMC_REQUIRE(mode == ELEM_LSGAN_G || b, "objective %d needs two tensors", mode);
+  if (!workspace || workspace_bytes < ammc_elem_loss_workspace_bytes(n)) return fail(AMMC_EWORKSPACE, "workspace too small");
+  const int blocks = elem_blocks(n);
+  float* partial = (float*)workspace;
+  const bool vec = ((((uintptr_t)a) | ((uintptr_t)(mode == ELEM_LSGAN_G ? a : b))) & 15) == 0;
+#define AMMC_EL_LAUNCH(M)                                                                             \
+  if (vec) elem_loss_partial_kernel<M, true><<<blocks, 256, 0, st>>>(a, b, partial, n);               \
+  else elem_loss_partial_kernel<M, false><<<blocks, 256, 0, st>>>(a, b, partial, n);
+  if (mode == ELEM_L1) { AMMC_EL_LAUNCH(ELEM_L1) }
+  else if (mode == ELEM_LSGAN_G) { AMMC_EL_LAUNCH(ELEM_LSGAN_G) }
+  else { AMMC_EL_LAUNCH(ELEM_LSGAN_D) }
+#undef AMMC_EL_LAUNCH
+  AMMC_LAUNCH_CHECK("elem_loss_partial_kernel");
+  elem_loss_final_kernel<<<1, 256, 0, st>>>(partial, out1, blocks, 1.0 / (double)n);
+  AMMC_LAUNCH_CHECK("elem_loss_final_kernel");
+  return 0;
+}
+
+extern "C" int ammc_elem_loss_bwd(const float* a, const float* b, const float* g, float* grad_a, float* grad_b, int mode,
+                                  int64_t n, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  AMMC_REQUIRE(a && g && (grad_a || grad_b) && n > 0, "bad argument");
+  AMMC_REQUIRE(mode >= ELEM_L1 && mode <= ELEM_LSGAN_D, "unknown objective %d", mode);
+  AMMC_REQUIRE(mode == ELEM_LSGAN_G || b, "objective %d needs two tensors", mode);
+  AMMC_REQUIRE(mode != ELEM_LSGAN_G || !grad_b, "objective %d has one tensor", mode);
+  const int blocks = elem_blocks(n);
+  const float inv = (float)(1.0 / (double)n);
+  if (mode == ELEM_L1) elem_loss_bwd_kernel<ELEM_L1><<<blocks, 256, 0, st>>>(a, b, g, grad_a, grad_b, n, inv);
+  else if (mode == ELEM_LSGAN_G) elem_loss_bwd_kernel<ELEM_LSGAN_G><<<blocks, 256, 0, st>>>(a, b, g, grad_a, grad_b, n, inv);
+  else elem_loss_bwd_kernel<ELEM_LSGAN_D><<<blocks, 256, 0, st>>>(a, b, g, grad_a, grad_b, n, inv);
+  AMMC_LAUNCH_CHECK("elem_loss_bwd_kernel");
+  return 0;
+}

@@ -114,3 +114,28 @@ def get_twostream(in_channel=(12, 6), out_channel=(3, 2), embed_dim=64, n_embed=
     """Shipped configuration (reference Code/models/unet.py:1241-1249, net_params/*.pkl)."""
     return twostream(in_channel[0], out_channel[0], in_channel[1], out_channel[1], embed_dim=embed_dim,
                      n_embed=n_embed, k=k)
+
+
+class PixelDiscriminator(nn.Module):
+    """Host-side mirror of the reference discriminator (Code/models/pix2pix_networks.py:580-631; built as
+    `PixelDiscriminator(3, [128, 256, 512, 512], use_norm=False)`, Code/models/__init__.py:123-124,323): a stack of 4x4
+    stride-2 convolutions with LeakyReLU(0.1), optional norm layers after the inner activations, and a 4x4 stride-1 head
+    giving one map value per receptive field.  Same constructor arguments and the same `net.<i>` parameter names, so a
+    reference discriminator checkpoint loads with strict=True.  The layers are stock torch.nn modules (cuDNN): this is
+    training-step plumbing outside the hot path -- what this package adds to the adversarial
+    part of the step are the fused objectives in `losses.py` that consume its maps."""
+
+    def __init__(self, input_nc, num_filters, use_norm=False, norm_layer=nn.BatchNorm2d):
+        super().__init__()
+        inner = getattr(norm_layer, "func", norm_layer)
+        bias = (inner != nn.InstanceNorm2d) if use_norm else True
+        layers = [nn.Conv2d(input_nc, num_filters[0], kernel_size=4, stride=2, padding=2), nn.LeakyReLU(0.1, True)]
+        for cin, cout in zip(num_filters[:-2], num_filters[1:-1]):
+            layers += [nn.Conv2d(cin, cout, 4, 2, 2, bias=bias), nn.LeakyReLU(0.1, True)]
+            if use_norm:
+                layers.append(norm_layer(cout))
+        layers.append(nn.Conv2d(num_filters[-1], 1, 4, 1, 2))
+        self.net = nn.Sequential(*layers)
+
+    def forward(self, input):
+        return self.net(input)

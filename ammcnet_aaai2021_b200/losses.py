@@ -1,5 +1,7 @@
-"""Image-space generator losses with the reference's class names (Code/models/losses/losses_utils.py:17-59):
-`Intensity_Loss` (channel-wise L2 norm, averaged) and `Gradient_Loss` (|dx| + |dy| of the channel-summed difference).
+"""Training objectives with the reference's class names (Code/models/losses/losses_utils.py:10-59,103-113 and their consumer
+Code/models/losses/loss_zoo.py:307-350): `Intensity_Loss` (channel-wise L2 norm, averaged), `Gradient_Loss` (|dx| + |dy| of
+the channel-summed difference), `Flow_Loss` (mean |a - b|), `Adversarial_Loss` / `Discriminate_Loss` (least-squares GAN
+objectives on the discriminator maps) and `Twostream_vq_Loss`, the weighted generator objective of the joint training step.
 
 SURVEY section 8(f) rank 4, the part that needs no external weights.  Both losses of a (prediction, target) pair come from
 ONE fused forward kernel and ONE backward kernel (`ammc_frame_losses_fwd/bwd`) instead of ~14 ATen kernels and their
@@ -82,3 +84,107 @@ class Gradient_Loss(nn.Module):
         if gen_frames.shape[1] != self.channels:
             raise RuntimeError("ammc_b200.Gradient_Loss: built for %d channels, got %d" % (self.channels, gen_frames.shape[1]))
         return frame_losses(gen_frames, gt_frames)[1]
+
+
+OBJ_L1, OBJ_LSGAN_G, OBJ_LSGAN_D = 0, 1, 2          # AMMC_OBJ_* of include/ammc_b200.h
+
+
+class ElemLossFn(torch.autograd.Function):
+    """(mode, a, b) -> 0-d mean objective from one pass over a (and b) + the deterministic final sum; the backward is one
+    pass writing the gradient(s).  `b` is None for OBJ_LSGAN_G."""
+
+    @staticmethod
+    def forward(ctx, mode, a, b):
+        _require_cuda_f32(a, b, names=("first tensor", "second tensor"))
+        if b is not None and (a.shape != b.shape or a.device != b.device):
+            raise RuntimeError("ammc_b200: the objective needs two tensors of equal shape on one device, got %s / %s"
+                               % (tuple(a.shape), tuple(b.shape)))
+        if a.numel() == 0:
+            raise RuntimeError("ammc_b200: the objective of an empty tensor is undefined (the reference returns nan)")
+        _check_device(a.device)
+        a = a.contiguous()
+        b = None if b is None else b.contiguous()
+        out = torch.empty((1,), dtype=torch.float32, device=a.device)
+        lib = _capi.load()
+        ws = _workspace(lib.ammc_elem_loss_workspace_bytes(a.numel()), a.device)
+        with torch.cuda.device(a.device):
+            _capi.call("ammc_elem_loss_fwd", _p(a), _p(b), _p(out), mode, a.numel(), _p(ws), ws.numel(), _stream())
+        _count(2)
+        ctx.mode = mode
+        ctx.save_for_backward(a, b)
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        need_a, need_b = ctx.needs_input_grad[1], b is not None and ctx.needs_input_grad[2]
+        if not (need_a or need_b):
+            return None, None, None
+        ga = torch.empty_like(a) if need_a else None
+        gb = torch.empty_like(b) if need_b else None
+        g = g.contiguous().float().reshape(1)
+        with torch.cuda.device(a.device):
+            _capi.call("ammc_elem_loss_bwd", _p(a), _p(b), _p(g), _p(ga), _p(gb), ctx.mode, a.numel(), _stream())
+        _count(1)
+        return None, ga, gb
+
+
+class Flow_Loss(nn.Module):
+    """losses_utils.py:10-15: mean |gen_flows - gt_flows| (equal shapes; the reference's only call site passes two
+    FlowNet2-SD outputs of the same size, train_helper.py:316-322)."""
+
+    def forward(self, gen_flows, gt_flows):
+        return ElemLossFn.apply(OBJ_L1, gen_flows, gt_flows)
+
+
+class Adversarial_Loss(nn.Module):
+    """losses_utils.py:103-107: mean (fake_outputs - 1)^2 / 2 on the discriminator map of the prediction."""
+
+    def forward(self, fake_outputs):
+        return ElemLossFn.apply(OBJ_LSGAN_G, fake_outputs, None)
+
+
+class Discriminate_Loss(nn.Module):
+    """losses_utils.py:109-113: mean (real_outputs - 1)^2 / 2 + mean fake_outputs^2 / 2 (maps of equal shape: both come
+    from the same discriminator on frames of one size, train_helper.py:324-326)."""
+
+    def forward(self, real_outputs, fake_outputs):
+        return ElemLossFn.apply(OBJ_LSGAN_D, real_outputs, fake_outputs)
+
+
+class Twostream_vq_Loss(nn.Module):
+    """Generator objective of the joint training step, loss_zoo.py:307-350 (ctor: base_Loss, loss_zoo.py:15-45): same
+    arguments, same weighted sum, same `g_*` float attributes after the call.  The reference reads eight scalars back with
+    eight `.item()` synchronisations per step; here the eight values travel in ONE device-to-host copy.  `latent_diff` is
+    what the generator returns as its third output: one tensor, or the (rgb, op) tuple of commit losses, which is summed
+    (Code/models/unet.py:1065)."""
+
+    def __init__(self, lam_adv=None, lam_gdl=None, lam_flow=None, lam_lp=None, lam_latent=None, lam_lp_op=None,
+                 lam_adv_op=None):
+        super().__init__()
+        self.lam_lp, self.lam_adv, self.lam_gdl, self.lam_flow = lam_lp, lam_adv, lam_gdl, lam_flow
+        self.lam_latent, self.lam_lp_op, self.lam_adv_op = lam_latent, lam_lp_op, lam_adv_op
+        self.adversarial_loss_fn = Adversarial_Loss()
+        self.flow_loss_fn = Flow_Loss()
+        self.int_loss_fn = Intensity_Loss()
+        self.gd_loss_fn = Gradient_Loss()
+        self.int_loss_fn_op = Intensity_Loss()
+        self.adversarial_loss_fn_op = Adversarial_Loss()
+        self.g_loss = self.g_adv_loss = self.g_flow_loss = self.g_int_loss = self.g_gd_loss = None
+        self.g_int_loss_op = self.g_adv_loss_op = self.g_latent_loss = None
+
+    def forward(self, flow_pred, flow_gt, rgb_G_output, rgb_target, op_G_output, op_target, latent_diff, d_gen):
+        g_adv_loss = self.adversarial_loss_fn(d_gen)
+        g_flow_loss = self.flow_loss_fn(flow_pred, flow_gt)
+        g_int_loss, g_gd_loss = frame_losses(rgb_G_output, rgb_target)          # both from one fused pass
+        g_int_loss_op = self.int_loss_fn_op(op_G_output, op_target)
+        if isinstance(latent_diff, (tuple, list)):
+            latent_diff = sum(d.sum() for d in latent_diff)
+        g_latent_loss = latent_diff.sum() if latent_diff.dim() else latent_diff
+        g_loss = self.lam_adv * g_adv_loss + self.lam_gdl * g_gd_loss + self.lam_flow * g_flow_loss + \
+            self.lam_lp * g_int_loss + self.lam_latent * g_latent_loss + self.lam_lp_op * g_int_loss_op
+        vals = torch.stack([v.detach().float().reshape(()) for v in
+                            (g_loss, g_adv_loss, g_flow_loss, g_int_loss, g_gd_loss, g_int_loss_op, g_latent_loss)]).tolist()
+        (self.g_loss, self.g_adv_loss, self.g_flow_loss, self.g_int_loss, self.g_gd_loss, self.g_int_loss_op,
+         self.g_latent_loss) = vals
+        return g_loss

@@ -180,6 +180,18 @@ def frames(seed: int, b: int, c: int = 3, h: int = 256, w: int = 256, noise: flo
     return gen, gt
 
 
+def objective_inputs(c):
+    """Seeded inputs of one objective case (oracle/gen_golden.py gen_objectives and tests/test_gpu_losses.py share them): predicted / target frames and flows,
+    FlowNet-style flow pairs, discriminator maps of a real and a generated frame ([b, 1, hd, wd]), a commit-loss scalar."""
+    s, b, h, w = c["seed"], c["b"], c["h"], c["w"]
+    rgb_out, rgb_tgt = frames(s, b, 3, h, w)
+    op_out, op_tgt = frames(s + 100, b, 2, h, w, noise=0.02)
+    flow_pred, flow_gt = frames(s + 200, b, 2, h, w, noise=0.05)
+    d_gen, d_real = frames(s + 300, b, 1, c["hd"], c["wd"], noise=0.5)
+    latent = torch.tensor([0.0371 + 1e-3 * s])
+    return dict(flow_pred=flow_pred, flow_gt=flow_gt, rgb_out=rgb_out, rgb_tgt=rgb_tgt, op_out=op_out, op_tgt=op_tgt,
+                latent=latent, d_gen=d_gen, d_real=d_real)
+
 # video-length lists of the three datasets (frames per sub-video), recovered from the recorded score
 # pickles shipped with the reference (Code/ammcnet_os/model_result_save/*; SURVEY.md section 4).
 PED2_VIDEO_LENGTHS = [180, 180, 150, 180, 150, 180, 180, 180, 120, 150, 180, 180]

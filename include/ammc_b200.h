@@ -399,6 +399,22 @@ int ammc_frame_losses_fwd(const float* gen, const float* gt, float* out2, void* 
 int ammc_frame_losses_bwd(const float* gen, const float* gt, const float* g_int, const float* g_gd, float* grad_gen, int n,
                           int C, int H, int W, void* stream);
 
+/* ---- element-wise mean objectives of the training step (Code/models/losses/losses_utils.py:10-15,103-113; consumers
+ * Code/models/losses/loss_zoo.py:331-336, Code/run_helper/train_helper.py:318-326) ---------------------------------------
+ *   AMMC_OBJ_L1       Flow_Loss          out1[0] = mean |a - b|
+ *   AMMC_OBJ_LSGAN_G  Adversarial_Loss   out1[0] = mean (a - 1)^2 / 2                    (b unused, may be NULL)
+ *   AMMC_OBJ_LSGAN_D  Discriminate_Loss  out1[0] = mean (a - 1)^2 / 2 + mean b^2 / 2     (a = real map, b = fake map)
+ * a and b hold n fp32 elements each.  bwd: grad_a = g * d out1/d a, grad_b = g * d out1/d b; g is a device scalar, either
+ * gradient pointer may be NULL.  One pass + a fixed-order final sum (deterministic); needs workspace_bytes(n). */
+#define AMMC_OBJ_L1 0
+#define AMMC_OBJ_LSGAN_G 1
+#define AMMC_OBJ_LSGAN_D 2
+size_t ammc_elem_loss_workspace_bytes(int64_t n);
+int ammc_elem_loss_fwd(const float* a, const float* b, float* out1, int mode, int64_t n, void* workspace,
+                       size_t workspace_bytes, void* stream);
+int ammc_elem_loss_bwd(const float* a, const float* b, const float* g, float* grad_a, float* grad_b, int mode, int64_t n,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -394,6 +394,37 @@ def gradient_loss(gen: torch.Tensor, gt: torch.Tensor, alpha: int = 1) -> torch.
     return torch.mean(torch.abs(gt_dx - gen_dx) ** alpha + torch.abs(gt_dy - gen_dy) ** alpha)
 
 
+def flow_loss(gen_flows: torch.Tensor, gt_flows: torch.Tensor) -> torch.Tensor:
+    """Flow_Loss, Code/models/losses/losses_utils.py:10-15."""
+    return torch.mean(torch.abs(gen_flows - gt_flows))
+
+
+def adversarial_loss(fake_outputs: torch.Tensor) -> torch.Tensor:
+    """Adversarial_Loss, losses_utils.py:103-107 (least-squares GAN, generator side)."""
+    return torch.mean((fake_outputs - 1) ** 2 / 2)
+
+
+def discriminate_loss(real_outputs: torch.Tensor, fake_outputs: torch.Tensor) -> torch.Tensor:
+    """Discriminate_Loss, losses_utils.py:109-113 (least-squares GAN, discriminator side)."""
+    return torch.mean((real_outputs - 1) ** 2 / 2) + torch.mean(fake_outputs ** 2 / 2)
+
+
+def twostream_vq_loss(lam: Dict[str, float], flow_pred, flow_gt, rgb_out, rgb_target, op_out, op_target, latent_diff, d_gen):
+    """Twostream_vq_Loss.forward, Code/models/losses/loss_zoo.py:312-350: the weighted generator objective of the joint
+    training step.  `lam` holds lam_adv, lam_gdl, lam_flow, lam_lp, lam_latent, lam_lp_op (base_Loss, loss_zoo.py:15-31).
+    Returns (g_loss, dict of the seven scalars the reference stores as attributes)."""
+    g_adv = adversarial_loss(d_gen)
+    g_flow = flow_loss(flow_pred, flow_gt)
+    g_int = intensity_loss(rgb_out, rgb_target)
+    g_gd = gradient_loss(rgb_out, rgb_target)
+    g_int_op = intensity_loss(op_out, op_target)
+    g_loss = lam["lam_adv"] * g_adv + lam["lam_gdl"] * g_gd + lam["lam_flow"] * g_flow + lam["lam_lp"] * g_int + \
+        lam["lam_latent"] * latent_diff + lam["lam_lp_op"] * g_int_op
+    parts = dict(g_loss=g_loss, g_adv_loss=g_adv, g_flow_loss=g_flow, g_int_loss=g_int, g_gd_loss=g_gd, g_int_loss_op=g_int_op,
+                 g_latent_loss=latent_diff)
+    return g_loss, parts
+
+
 def path_forward(x_rgb, x_op, gen, gt, params: Dict[str, torch.Tensor], k: int):
     """The starred region of twostream.forward (Code/models/unet.py:985-994) followed by the per-frame rgb
     PSNR of test_helper.py:445-452.  `params` uses the reference state_dict key names

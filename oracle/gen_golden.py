@@ -376,13 +376,77 @@ def gen_losses():
     _save("losses", dict(kind="losses", cases=LOSS_CASES), **out)
 
 
+OBJECTIVE_CASES = {"obj_small": dict(b=2, h=16, w=20, hd=9, wd=11, seed=61), "obj_odd": dict(b=3, h=9, w=7, hd=6, wd=5, seed=62),
+                   "obj_256": dict(b=2, h=256, w=256, hd=33, wd=33, seed=63)}
+OBJECTIVE_LAMBDAS = dict(lam_adv=0.05, lam_gdl=1.0, lam_flow=2.0, lam_lp=1.0, lam_latent=0.25, lam_lp_op=2.0)
+
+
+def gen_objectives():
+    """Flow_Loss / Adversarial_Loss / Discriminate_Loss (losses_utils.py:10-15,103-113) and Twostream_vq_Loss
+    (loss_zoo.py:307-350) of the reference, imported unmodified, with autograd gradients; stubs as in gen_losses."""
+    import types
+    ref_harness.import_reference()
+    stub = types.ModuleType("Code.main.constant_train")
+    stub.const = types.SimpleNamespace(gpu_idx="0")
+    sys.modules["Code.main.constant_train"] = stub
+    import Code.models.losses.losses_utils as LU
+    import Code.models.losses.loss_zoo as LZ
+    cuda_orig = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        out = {}
+        for name, c in OBJECTIVE_CASES.items():
+            t = synth.objective_inputs(c)
+            small = c["h"] * c["w"] <= 1024
+            # the three element-wise objectives on their own
+            fp = t["flow_pred"].clone().requires_grad_(True)
+            lf = LU.Flow_Loss()(fp, t["flow_gt"])
+            (g_fp,) = torch.autograd.grad(lf, fp)
+            dg = t["d_gen"].clone().requires_grad_(True)
+            la = LU.Adversarial_Loss()(dg)
+            (g_dg,) = torch.autograd.grad(la, dg)
+            dr, df = t["d_real"].clone().requires_grad_(True), t["d_gen"].clone().requires_grad_(True)
+            ld = LU.Discriminate_Loss()(dr, df)
+            g_dr, g_df = torch.autograd.grad(ld, (dr, df))
+            _close(O.flow_loss(t["flow_pred"], t["flow_gt"]), lf, 1e-6, name + ".flow")
+            _close(O.adversarial_loss(t["d_gen"]), la, 1e-6, name + ".adv")
+            _close(O.discriminate_loss(t["d_real"], t["d_gen"]), ld, 1e-6, name + ".dis")
+            out[name + "_flow"], out[name + "_adv"], out[name + "_dis"] = lf.detach(), la.detach(), ld.detach()
+            out[name + "_g_adv"], out[name + "_g_dis_real"], out[name + "_g_dis_fake"] = g_dg, g_dr, g_df
+            if small:
+                out[name + "_g_flow"] = g_fp
+            else:
+                out[name + "_g_flow_sum"] = (g_fp.double() * t["flow_gt"].double()).sum()
+            # the generator objective: gradients w.r.t. everything the generator produces
+            leaves = {k: t[k].clone().requires_grad_(True) for k in ("rgb_out", "op_out", "latent", "d_gen")}
+            fn = LZ.Twostream_vq_Loss(**OBJECTIVE_LAMBDAS)
+            g_loss = fn(t["flow_pred"], t["flow_gt"], leaves["rgb_out"], t["rgb_tgt"], leaves["op_out"], t["op_tgt"],
+                        leaves["latent"], leaves["d_gen"])
+            grads = torch.autograd.grad(g_loss, list(leaves.values()))
+            o_loss, o_parts = O.twostream_vq_loss(OBJECTIVE_LAMBDAS, t["flow_pred"], t["flow_gt"], t["rgb_out"], t["rgb_tgt"],
+                                                  t["op_out"], t["op_tgt"], t["latent"], t["d_gen"])
+            _close(o_loss, g_loss, 1e-6, name + ".g_loss")
+            for k in ("g_loss", "g_adv_loss", "g_flow_loss", "g_int_loss", "g_gd_loss", "g_int_loss_op", "g_latent_loss"):
+                _close(o_parts[k], getattr(fn, k), 1e-6, name + "." + k)
+                out[name + "_attr_" + k] = np.float64(getattr(fn, k))
+            out[name + "_g_loss"] = g_loss.detach()
+            for (k, leaf), g in zip(leaves.items(), grads):
+                if small or k in ("latent", "d_gen"):
+                    out[name + "_dg_" + k] = g
+                else:
+                    out[name + "_dg_" + k + "_sum"] = (g.double() * t[k].double()).sum()
+    finally:
+        torch.Tensor.cuda = cuda_orig
+    _save("objectives", dict(kind="objectives", cases=OBJECTIVE_CASES, lambdas=OBJECTIVE_LAMBDAS), **out)
+
+
 def main():
     torch.set_num_threads(os.cpu_count())
     ref_unet, ref_utils, ref_eval = ref_harness.import_reference()
     only = set(sys.argv[1:])                    # e.g. `python oracle/gen_golden.py amft` rewrites one family
     steps = [("memory", lambda: gen_memory(ref_unet)), ("amft", lambda: gen_amft(ref_unet)),
              ("psnr", lambda: gen_psnr(ref_utils)), ("scores", lambda: gen_scores(ref_eval)), ("records", gen_records),
-             ("generator", lambda: gen_generator(ref_unet)), ("preprocess", gen_preprocess), ("losses", gen_losses)]
+             ("generator", lambda: gen_generator(ref_unet)), ("preprocess", gen_preprocess), ("losses", gen_losses), ("objectives", gen_objectives)]
     for name, fn in steps:
         if not only or name in only:
             fn()

@@ -53,3 +53,76 @@ def test_losses_refuse_what_they_do_not_cover():
         A.frame_losses(torch.zeros(1, 9, 4, 4, device=DEV), torch.zeros(1, 9, 4, 4, device=DEV))
     with pytest.raises(RuntimeError, match="alpha=1"):
         A.Gradient_Loss(alpha=2)
+
+
+def test_training_objectives_vs_reference_golden():
+    """Flow_Loss / Adversarial_Loss / Discriminate_Loss (one fused pass each) and the generator objective Twostream_vq_Loss
+    against what the reference itself returned, stored and back-propagated (tests/golden/objectives.npz)."""
+    c, g = load_golden("objectives")
+    for name, cs in c["cases"].items():
+        t = {k: v.to(DEV) for k, v in synth.objective_inputs(cs).items()}
+        fp = t["flow_pred"].clone().requires_grad_(True)
+        lf = A.Flow_Loss()(fp, t["flow_gt"])
+        assert lf.dim() == 0
+        assert_close(lf.detach().cpu(), g[name + "_flow"], 1e-5, name + ".flow")
+        g_fp = torch.autograd.grad(lf, fp)[0].cpu()
+        if name + "_g_flow" in g:
+            assert_close(g_fp, g[name + "_g_flow"], 1e-5, name + ".g_flow")
+        else:
+            assert_close((g_fp.double() * t["flow_gt"].cpu().double()).sum(), g[name + "_g_flow_sum"], 1e-4, name + ".g_flow_sum")
+        dg = t["d_gen"].clone().requires_grad_(True)
+        la = A.Adversarial_Loss()(dg)
+        assert_close(la.detach().cpu(), g[name + "_adv"], 1e-5, name + ".adv")
+        assert_close(torch.autograd.grad(la, dg)[0].cpu(), g[name + "_g_adv"], 1e-5, name + ".g_adv")
+        dr, df = t["d_real"].clone().requires_grad_(True), t["d_gen"].clone().requires_grad_(True)
+        ld = A.Discriminate_Loss()(dr, df)
+        assert_close(ld.detach().cpu(), g[name + "_dis"], 1e-5, name + ".dis")
+        g_dr, g_df = torch.autograd.grad(ld, (dr, df))
+        assert_close(g_dr.cpu(), g[name + "_g_dis_real"], 1e-5, name + ".g_dis_real")
+        assert_close(g_df.cpu(), g[name + "_g_dis_fake"], 1e-5, name + ".g_dis_fake")
+        # generator objective: same weighted sum, same attributes, same gradients to everything the generator produces
+        leaves = {k: t[k].clone().requires_grad_(True) for k in ("rgb_out", "op_out", "latent", "d_gen")}
+        fn = A.Twostream_vq_Loss(**c["lambdas"])
+        loss = fn(t["flow_pred"], t["flow_gt"], leaves["rgb_out"], t["rgb_tgt"], leaves["op_out"], t["op_tgt"],
+                  leaves["latent"], leaves["d_gen"])
+        assert_close(loss.detach().cpu().reshape(1), g[name + "_g_loss"], 1e-5, name + ".g_loss")
+        for k in ("g_loss", "g_adv_loss", "g_flow_loss", "g_int_loss", "g_gd_loss", "g_int_loss_op", "g_latent_loss"):
+            assert isinstance(getattr(fn, k), float)
+            assert_close(torch.tensor(getattr(fn, k)), g[name + "_attr_" + k], 1e-5, name + ".attr." + k)
+        grads = torch.autograd.grad(loss, list(leaves.values()))
+        for (k, leaf), gr in zip(leaves.items(), grads):
+            if name + "_dg_" + k in g:
+                assert_close(gr.cpu(), g[name + "_dg_" + k], 1e-5, name + ".dg_" + k)
+            else:
+                assert_close((gr.cpu().double() * t[k].cpu().double()).sum(), g[name + "_dg_" + k + "_sum"], 1e-4,
+                             name + ".dg_" + k + "_sum")
+
+
+@pytest.mark.parametrize("n", [1, 3, 255, 1024, 4097, 3 * 1000 * 1000 + 5])
+def test_elementwise_objectives_any_length_and_alignment(n):
+    """Lengths around the 16-byte vector width and the grid-stride cap, and views that start off a 16-byte boundary."""
+    g = torch.Generator().manual_seed(n)
+    a, b = torch.randn(n + 1, generator=g), torch.randn(n + 1, generator=g)
+    for off in (0, 1):
+        ad, bd = a.to(DEV)[off:off + n].requires_grad_(True), b.to(DEV)[off:off + n].requires_grad_(True)
+        ar, br = a[off:off + n].double().requires_grad_(True), b[off:off + n].double().requires_grad_(True)
+        for ours, ref in ((A.Flow_Loss()(ad, bd), O.flow_loss(ar, br)), (A.Discriminate_Loss()(ad, bd), O.discriminate_loss(ar, br)),
+                          (A.Adversarial_Loss()(ad), O.adversarial_loss(ar))):
+            assert_close(ours.detach().cpu(), ref.detach(), 1e-5, "value n=%d off=%d" % (n, off))
+            go = torch.autograd.grad(ours, [ad, bd], allow_unused=True)
+            gr = torch.autograd.grad(ref, [ar, br], allow_unused=True)
+            for x, y in zip(go, gr):
+                assert (x is None) == (y is None)
+                if x is not None:
+                    assert_close(x.cpu(), y, 1e-5, "grad n=%d off=%d" % (n, off))
+
+
+def test_objectives_refuse_what_they_do_not_cover():
+    with pytest.raises(RuntimeError, match="CUDA"):
+        A.Flow_Loss()(torch.zeros(4), torch.zeros(4))
+    with pytest.raises(RuntimeError, match="equal shape"):
+        A.Discriminate_Loss()(torch.zeros(1, 1, 4, 4, device=DEV), torch.zeros(1, 1, 4, 5, device=DEV))
+    with pytest.raises(RuntimeError, match="float32"):
+        A.Adversarial_Loss()(torch.zeros(4, device=DEV, dtype=torch.float16))
+    with pytest.raises(RuntimeError, match="empty"):
+        A.Adversarial_Loss()(torch.zeros(0, device=DEV))

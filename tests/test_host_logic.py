@@ -74,3 +74,47 @@ def test_swap_and_patch_against_live_reference():
     finally:
         A.unpatch_reference(ref_unet, saved, ref_utils)
     assert ref_unet.bridge is saved["bridge"]
+
+
+def test_pixel_discriminator_layout():
+    """The configuration the reference trains with (Code/models/__init__.py:123-124,323): 4 convolutions, 128-256-512-1 maps,
+    LeakyReLU(0.1); a 256 x 256 frame gives a 34 x 34 map (129 -> 65 -> 33 under 4/2/2, +1 under the 4/1/2 head)."""
+    d = A.PixelDiscriminator(3, [128, 256, 512, 512], use_norm=False)
+    sd = d.state_dict()
+    assert list(sd) == ["net.0.weight", "net.0.bias", "net.2.weight", "net.2.bias", "net.4.weight", "net.4.bias",
+                        "net.6.weight", "net.6.bias"]
+    assert [tuple(sd[k].shape) for k in list(sd)[::2]] == [(128, 3, 4, 4), (256, 128, 4, 4), (512, 256, 4, 4), (1, 512, 4, 4)]
+    assert tuple(d(torch.zeros(1, 3, 256, 256)).shape) == (1, 1, 34, 34)
+    n = A.PixelDiscriminator(3, [8, 16, 32, 32], use_norm=True)
+    assert [type(m).__name__ for m in n.net] == ["Conv2d", "LeakyReLU", "Conv2d", "LeakyReLU", "BatchNorm2d", "Conv2d",
+                                                 "LeakyReLU", "BatchNorm2d", "Conv2d"]
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference tree only exists in the build container")
+def test_pixel_discriminator_against_live_reference():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_pix2pix", "/root/reference/Code/models/pix2pix_networks.py")
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    torch.manual_seed(3)
+    x = torch.randn(2, 3, 40, 56)
+    for use_norm in (False, True):
+        r = ref.PixelDiscriminator(3, [16, 32, 64, 64], use_norm=use_norm)
+        o = A.PixelDiscriminator(3, [16, 32, 64, 64], use_norm=use_norm)
+        assert list(o.state_dict()) == list(r.state_dict())
+        o.load_state_dict(r.state_dict(), strict=True)
+        assert torch.equal(o(x), r(x))
+
+
+def test_objectives_refuse_cpu_tensors():
+    """The training objectives have no CPU path either."""
+    with pytest.raises(RuntimeError, match="CUDA"):
+        A.Flow_Loss()(torch.zeros(2, 2, 4, 4), torch.zeros(2, 2, 4, 4))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        A.Discriminate_Loss()(torch.zeros(1, 1, 4, 4), torch.zeros(1, 1, 4, 4))
+    f = A.Twostream_vq_Loss(lam_adv=0.05, lam_gdl=1.0, lam_flow=2.0, lam_lp=1.0, lam_latent=0.1, lam_lp_op=2.0)
+    assert (f.lam_adv, f.lam_gdl, f.lam_flow, f.lam_lp, f.lam_latent, f.lam_lp_op, f.lam_adv_op) == (0.05, 1.0, 2.0, 1.0, 0.1, 2.0, None)
+    assert f.g_loss is None and f.g_latent_loss is None
+    z = torch.zeros(1, 3, 8, 8)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        f(z[:, :2], z[:, :2], z, z, z[:, :2], z[:, :2], torch.zeros(1), torch.zeros(1, 1, 3, 3))

@@ -174,3 +174,32 @@ def test_frame_losses_oracle_vs_reference():
         else:
             assert_close((gi.double() * gt.double()).sum(), g[name + "_g_int_sum"], 1e-6, name + ".g_int_sum")
             assert_close((gg.double() * gt.double()).sum(), g[name + "_g_gd_sum"], 1e-6, name + ".g_gd_sum")
+
+
+def test_training_objectives_oracle_vs_reference():
+    """Flow_Loss / Adversarial_Loss / Discriminate_Loss / Twostream_vq_Loss restatement (losses_utils.py:10-15,103-113,
+    loss_zoo.py:307-350) against the values, stored attributes and autograd gradients of the reference itself."""
+    c, g = load_golden("objectives")
+    lam = c["lambdas"]
+    for name, cs in c["cases"].items():
+        t = synth.objective_inputs(cs)
+        assert_close(O.flow_loss(t["flow_pred"], t["flow_gt"]), g[name + "_flow"], 1e-6, name + ".flow")
+        assert_close(O.adversarial_loss(t["d_gen"]), g[name + "_adv"], 1e-6, name + ".adv")
+        dr, df = t["d_real"].clone().requires_grad_(True), t["d_gen"].clone().requires_grad_(True)
+        ld = O.discriminate_loss(dr, df)
+        assert_close(ld.detach(), g[name + "_dis"], 1e-6, name + ".dis")
+        g_dr, g_df = torch.autograd.grad(ld, (dr, df))
+        assert_close(g_dr, g[name + "_g_dis_real"], 1e-6, name + ".g_dis_real")
+        assert_close(g_df, g[name + "_g_dis_fake"], 1e-6, name + ".g_dis_fake")
+        leaves = {k: t[k].clone().requires_grad_(True) for k in ("rgb_out", "op_out", "latent", "d_gen")}
+        loss, parts = O.twostream_vq_loss(lam, t["flow_pred"], t["flow_gt"], leaves["rgb_out"], t["rgb_tgt"], leaves["op_out"],
+                                          t["op_tgt"], leaves["latent"], leaves["d_gen"])
+        assert_close(loss.detach(), g[name + "_g_loss"], 1e-6, name + ".g_loss")
+        for k, v in parts.items():
+            assert_close(v.detach().reshape(()), g[name + "_attr_" + k], 1e-6, name + "." + k)
+        grads = torch.autograd.grad(loss, list(leaves.values()))
+        for (k, leaf), gr in zip(leaves.items(), grads):
+            if name + "_dg_" + k in g:
+                assert_close(gr, g[name + "_dg_" + k], 1e-6, name + ".dg_" + k)
+            else:
+                assert_close((gr.double() * t[k].double()).sum(), g[name + "_dg_" + k + "_sum"], 1e-6, name + ".dg_" + k + "_sum")

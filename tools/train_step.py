@@ -6,6 +6,14 @@ cuDNN layers (unchanged host code).  Losses follow the reference step structure 
 Code/models/losses/loss_zoo.py:307-350) without the parts that need unavailable weights (FlowNet2-SD, discriminator):
 intensity L2 on the rgb prediction, L1 on the flow prediction, lam_latent * (rgb_diff + op_diff).
 
+`--gan` runs the reference's adversarial step structure (train_helper.py:318-339): the discriminator
+(`PixelDiscriminator(3, [128, 256, 512, 512])`, cuDNN layers) is updated on (target, detached prediction) with the fused
+`Discriminate_Loss`, then the generator on `Twostream_vq_Loss` (fused adversarial / flow / intensity / gradient objectives,
+one host read of its eight scalars).  The discriminator update comes first here: the reference back-propagates the
+generator objective through discriminator weights its optimizer has already stepped, which current autograd refuses.
+FlowNet2-SD is not built (no weights offline): `Flow_Loss` is fed the flow-stream prediction / target instead of two
+FlowNet outputs -- tensors of the same shape and role.
+
     torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/train_step.py --steps 10 --batch 8
 """
 import argparse, json, os, sys, time
@@ -24,6 +32,7 @@ def main():
     ap.add_argument("--batch", type=int, default=8)       # per GPU (reference script: batch 8, training_com.sh:21)
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--sync-bn", action="store_true", help="global-batch BatchNorm statistics (single-GPU semantics)")
+    ap.add_argument("--gan", action="store_true", help="adversarial step structure: discriminator + Twostream_vq_Loss")
     args = ap.parse_args()
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
     torch.cuda.set_device(local)
@@ -44,8 +53,34 @@ def main():
     rgb_in, rgb_tgt = rgb[:, :-1].flatten(1, 2), rgb[:, -1]
     op_in, op_tgt = op[:, :-1].flatten(1, 2), op[:, -1]
     lam_latent = 1.0
+    if args.gan:
+        D = A.PixelDiscriminator(3, [128, 256, 512, 512], use_norm=False).to(dev).train()
+        opt_d = torch.optim.Adam(D.parameters(), lr=2e-5)
+        d_params = [p for p in D.parameters()]
+        g_loss_fn = A.Twostream_vq_Loss(lam_adv=0.05, lam_gdl=1.0, lam_flow=2.0, lam_lp=1.0, lam_latent=0.1, lam_lp_op=2.0)
+        d_loss_fn = A.Discriminate_Loss()
+
+    def gan_step():
+        pr, po, diffs, _ = g(rgb_in, op_in)
+        opt_d.zero_grad(set_to_none=True)                       # (1) discriminator on (real, detached fake)
+        d_loss = d_loss_fn(D(rgb_tgt), D(pr.detach()))
+        d_loss.backward()
+        adist.allreduce_gradients(d_params)
+        opt_d.step()
+        opt.zero_grad(set_to_none=True)                         # (2) generator; the discriminator only carries the gradient
+        for p in d_params:
+            p.requires_grad_(False)
+        loss = g_loss_fn(po, op_tgt, pr, rgb_tgt, po, op_tgt, diffs, D(pr))
+        loss.backward()
+        for p in d_params:
+            p.requires_grad_(True)
+        adist.allreduce_gradients(params)
+        opt.step()
+        return loss.detach().reshape(())
 
     def step():
+        if args.gan:
+            return gan_step()
         opt.zero_grad(set_to_none=True)
         pr, po, (d_rgb, d_op), _ = g(rgb_in, op_in)
         # the reference's generator objective without the adversarial / FlowNet terms (loss_zoo.py:124-126, 190-192): intensity +
@@ -86,7 +121,7 @@ def main():
         dist.all_reduce(bank_max_dev, op=dist.ReduceOp.MAX); dist.all_reduce(w_max_dev, op=dist.ReduceOp.MAX)
     if rank == 0:
         ls = [float(l) for l in losses]
-        print(json.dumps({"what": "joint training step (generator fwd+bwd, EMA stats + gradient all-reduce, Adam)",
+        print(json.dumps({"what": "joint training step (generator fwd+bwd, EMA stats + gradient all-reduce, Adam)" + (" + discriminator update, Twostream_vq_Loss" if args.gan else ""),
                           "n_gpus": world, "batch_per_gpu": B, "batch_norm": "global batch (all-reduced sums)" if args.sync_bn else "per rank", "steps": args.steps, "ms_per_step": float(ms) / args.steps,
                           "frames_per_s": world * B * args.steps / (float(ms) * 1e-3), "loss_first": ls[0], "loss_last": ls[-1],
                           "finite": all(l == l and abs(l) < 1e30 for l in ls),
