@@ -97,6 +97,9 @@ SIGNATURES = {
     "ammc_elem_loss_workspace_bytes": (Z, [L]),
     "ammc_elem_loss_fwd": (I, [P, P, P, I, L, P, Z, P]),
     "ammc_elem_loss_bwd": (I, [P, P, P, P, P, I, L, P]),
+    "ammc_gen_objective_workspace_bytes": (Z, [I] * 6 + [L, L]),
+    "ammc_gen_objective_fwd": (I, [P] * 8 + [I] * 8 + [L, L, I] + [F] * 6 + [P, P, Z, P]),
+    "ammc_gen_objective_bwd": (I, [P] * 8 + [I] * 8 + [L, L] + [F] * 6 + [P] * 5 + [P]),
     "ammc_psnr_workspace_bytes": (Z, [I, L]),
     "ammc_psnr_batch": (I, [P, P, P, P, Z, I, L, P]),
     "ammc_score_workspace_bytes": (Z, [L, I]),

@@ -284,3 +284,167 @@ extern "C" int ammc_elem_loss_bwd(const float* a, const float* b, const float* g
   AMMC_LAUNCH_CHECK("elem_loss_bwd_kernel");
   return 0;
 }
+
+// ------------------------------------------------------------------------------------------------------------------------
+// Generator objective of the joint training step in one call (Twostream_vq_Loss.forward, Code/models/losses/loss_zoo.py:312-350):
+//   g_loss = lam_adv * adv(d_gen) + lam_gdl * gd(rgb) + lam_flow * flow + lam_lp * int(rgb) + lam_latent * sum(latent) + lam_lp_op * int(op)
+// The reference runs ~35 ATen kernels forward, as many backward, ~12 scalar kernels for the weighted sum and eight .item()
+// synchronisations.  Here: four partial-sum passes (one per tensor pair) + ONE final kernel that reduces every segment in a
+// fixed order and forms the weighted sum -> out8 = [g_loss, adv, flow, int, gd, int_op, latent, 0]; the backward is one scalar
+// kernel (chain rule through the weighted sum) + one gradient pass per tensor that needs one.
+// ------------------------------------------------------------------------------------------------------------------------
+namespace ammc {
+
+struct ObjSegments { int rgb, op, flow, adv, n_latent; };       // partial PAIRS per segment, laid out in this order
+
+__global__ void __launch_bounds__(256) gen_objective_final_kernel(const float* __restrict__ partial, const float* __restrict__ latent,
+                                                                   ObjSegments seg, double inv_rgb, double inv_op, double inv_flow,
+                                                                   double inv_adv, float lam_adv, float lam_gdl, float lam_flow,
+                                                                   float lam_lp, float lam_latent, float lam_lp_op,
+                                                                   float* __restrict__ out8) {
+  __shared__ double red[6][8];
+  double v[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};                 // int, gd, int_op, flow, adv, latent
+  const float* p = partial;
+  for (int i = threadIdx.x; i < seg.rgb; i += 256) { v[0] += (double)p[2 * i]; v[1] += (double)p[2 * i + 1]; }
+  p += 2 * (size_t)seg.rgb;
+  for (int i = threadIdx.x; i < seg.op; i += 256) v[2] += (double)p[2 * i];
+  p += 2 * (size_t)seg.op;
+  for (int i = threadIdx.x; i < seg.flow; i += 256) v[3] += (double)p[2 * i];
+  p += 2 * (size_t)seg.flow;
+  for (int i = threadIdx.x; i < seg.adv; i += 256) v[4] += (double)p[2 * i];
+  for (int i = threadIdx.x; i < seg.n_latent; i += 256) v[5] += (double)latent[i];
+#pragma unroll
+  for (int q = 0; q < 6; ++q) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[q] += __shfl_xor_sync(0xffffffffu, v[q], o);
+    if ((threadIdx.x & 31) == 0) red[q][threadIdx.x >> 5] = v[q];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s[6];
+    for (int q = 0; q < 6; ++q) { s[q] = 0.0; for (int i = 0; i < 8; ++i) s[q] += red[q][i]; }
+    const float g_int = (float)(s[0] * inv_rgb), g_gd = (float)(s[1] * inv_rgb), g_int_op = (float)(s[2] * inv_op);
+    const float g_flow = (float)(s[3] * inv_flow), g_adv = (float)(s[4] * inv_adv), g_lat = (float)s[5];
+    // same association as the reference expression (loss_zoo.py:336-339), fp32 like its tensors
+    float g = lam_adv * g_adv + lam_gdl * g_gd;
+    g += lam_flow * g_flow;
+    g += lam_lp * g_int;
+    g += lam_latent * g_lat;
+    g += lam_lp_op * g_int_op;
+    out8[0] = g; out8[1] = g_adv; out8[2] = g_flow; out8[3] = g_int; out8[4] = g_gd; out8[5] = g_int_op; out8[6] = g_lat;
+    out8[7] = 0.f;
+  }
+}
+
+// scal8 = d(sum_i g8[i] * out8[i]) / d(component): [-, adv, flow, int, gd, int_op, latent, -]
+__global__ void gen_objective_scalars_kernel(const float* __restrict__ g8, float lam_adv, float lam_gdl, float lam_flow, float lam_lp,
+                                             float lam_latent, float lam_lp_op, float* __restrict__ scal8) {
+  if (threadIdx.x == 0) {
+    const float g = g8[0];
+    scal8[0] = g;
+    scal8[1] = fmaf(g, lam_adv, g8[1]);
+    scal8[2] = fmaf(g, lam_flow, g8[2]);
+    scal8[3] = fmaf(g, lam_lp, g8[3]);
+    scal8[4] = fmaf(g, lam_gdl, g8[4]);
+    scal8[5] = fmaf(g, lam_lp_op, g8[5]);
+    scal8[6] = fmaf(g, lam_latent, g8[6]);
+    scal8[7] = 0.f;
+  }
+}
+
+static int launch_frame_partial(const float* gen, const float* gt, float* partial, int n, int C, int H, int W, cudaStream_t st) {
+  const int bx = ceil_div((int64_t)H * W, 256);
+  switch (C) {
+#define AMMC_FL_CASE(CC) case CC: frame_loss_partial_kernel<CC><<<dim3(bx, n), 256, 0, st>>>(gen, gt, partial, H, W); break;
+    AMMC_FL_CASE(1) AMMC_FL_CASE(2) AMMC_FL_CASE(3) AMMC_FL_CASE(4) AMMC_FL_CASE(5) AMMC_FL_CASE(6) AMMC_FL_CASE(7) AMMC_FL_CASE(8)
+#undef AMMC_FL_CASE
+    default: return fail(AMMC_EINVAL, "frame losses support 1..%d channels (got %d)", LOSS_MAX_C, C);
+  }
+  AMMC_LAUNCH_CHECK("frame_loss_partial_kernel");
+  return 0;
+}
+
+}  // namespace ammc
+
+extern "C" size_t ammc_gen_objective_workspace_bytes(int n_rgb, int H_rgb, int W_rgb, int n_op, int H_op, int W_op, int64_t n_flow,
+                                                     int64_t n_dgen) {
+  const size_t pairs = (size_t)n_rgb * ceil_div((int64_t)H_rgb * W_rgb, 256) + (size_t)n_op * ceil_div((int64_t)H_op * W_op, 256) +
+                       (size_t)elem_blocks(n_flow > 0 ? n_flow : 1) + (size_t)elem_blocks(n_dgen > 0 ? n_dgen : 1);
+  return align_up(pairs * 2 * sizeof(float), 256);
+}
+
+extern "C" int ammc_gen_objective_fwd(const float* rgb_out, const float* rgb_tgt, const float* op_out, const float* op_tgt,
+                                      const float* flow_pred, const float* flow_gt, const float* d_gen, const float* latent,
+                                      int n_rgb, int C_rgb, int H_rgb, int W_rgb, int n_op, int C_op, int H_op, int W_op,
+                                      int64_t n_flow, int64_t n_dgen, int n_latent, float lam_adv, float lam_gdl, float lam_flow,
+                                      float lam_lp, float lam_latent, float lam_lp_op, float* out8, void* workspace,
+                                      size_t workspace_bytes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  AMMC_REQUIRE(rgb_out && rgb_tgt && op_out && op_tgt && flow_pred && flow_gt && d_gen && latent && out8, "bad argument");
+  AMMC_REQUIRE(n_rgb > 0 && H_rgb > 0 && W_rgb > 0 && n_op > 0 && H_op > 0 && W_op > 0 && n_flow > 0 && n_dgen > 0 && n_latent > 0,
+               "empty tensor");
+  AMMC_REQUIRE(n_rgb <= 65535 && n_op <= 65535, "batch too large for one launch");
+  if (!workspace || workspace_bytes < ammc_gen_objective_workspace_bytes(n_rgb, H_rgb, W_rgb, n_op, H_op, W_op, n_flow, n_dgen))
+    return fail(AMMC_EWORKSPACE, "workspace too small");
+  ObjSegments seg;
+  seg.rgb = n_rgb * ceil_div((int64_t)H_rgb * W_rgb, 256);
+  seg.op = n_op * ceil_div((int64_t)H_op * W_op, 256);
+  seg.flow = elem_blocks(n_flow);
+  seg.adv = elem_blocks(n_dgen);
+  seg.n_latent = n_latent;
+  float* p_rgb = (float*)workspace;
+  float* p_op = p_rgb + 2 * (size_t)seg.rgb;
+  float* p_flow = p_op + 2 * (size_t)seg.op;
+  float* p_adv = p_flow + 2 * (size_t)seg.flow;
+  int rc = launch_frame_partial(rgb_out, rgb_tgt, p_rgb, n_rgb, C_rgb, H_rgb, W_rgb, st);
+  if (rc) return rc;
+  rc = launch_frame_partial(op_out, op_tgt, p_op, n_op, C_op, H_op, W_op, st);
+  if (rc) return rc;
+  if (((((uintptr_t)flow_pred) | ((uintptr_t)flow_gt)) & 15) == 0)
+    elem_loss_partial_kernel<ELEM_L1, true><<<seg.flow, 256, 0, st>>>(flow_pred, flow_gt, p_flow, n_flow);
+  else
+    elem_loss_partial_kernel<ELEM_L1, false><<<seg.flow, 256, 0, st>>>(flow_pred, flow_gt, p_flow, n_flow);
+  AMMC_LAUNCH_CHECK("elem_loss_partial_kernel");
+  if ((((uintptr_t)d_gen) & 15) == 0)
+    elem_loss_partial_kernel<ELEM_LSGAN_G, true><<<seg.adv, 256, 0, st>>>(d_gen, nullptr, p_adv, n_dgen);
+  else
+    elem_loss_partial_kernel<ELEM_LSGAN_G, false><<<seg.adv, 256, 0, st>>>(d_gen, nullptr, p_adv, n_dgen);
+  AMMC_LAUNCH_CHECK("elem_loss_partial_kernel");
+  gen_objective_final_kernel<<<1, 256, 0, st>>>(p_rgb, latent, seg, 1.0 / ((double)n_rgb * H_rgb * W_rgb),
+                                                1.0 / ((double)n_op * H_op * W_op), 1.0 / (double)n_flow, 1.0 / (double)n_dgen,
+                                                lam_adv, lam_gdl, lam_flow, lam_lp, lam_latent, lam_lp_op, out8);
+  AMMC_LAUNCH_CHECK("gen_objective_final_kernel");
+  return 0;
+}
+
+extern "C" int ammc_gen_objective_bwd(const float* rgb_out, const float* rgb_tgt, const float* op_out, const float* op_tgt,
+                                      const float* flow_pred, const float* flow_gt, const float* d_gen, const float* g8,
+                                      int n_rgb, int C_rgb, int H_rgb, int W_rgb, int n_op, int C_op, int H_op, int W_op,
+                                      int64_t n_flow, int64_t n_dgen, float lam_adv, float lam_gdl, float lam_flow, float lam_lp,
+                                      float lam_latent, float lam_lp_op, float* scal8, float* grad_rgb, float* grad_op,
+                                      float* grad_flow_pred, float* grad_d_gen, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  AMMC_REQUIRE(g8 && scal8, "bad argument");
+  gen_objective_scalars_kernel<<<1, 32, 0, st>>>(g8, lam_adv, lam_gdl, lam_flow, lam_lp, lam_latent, lam_lp_op, scal8);
+  AMMC_LAUNCH_CHECK("gen_objective_scalars_kernel");
+  int rc = 0;
+  if (grad_rgb) {
+    AMMC_REQUIRE(rgb_out && rgb_tgt, "bad argument");
+    rc = ammc_frame_losses_bwd(rgb_out, rgb_tgt, scal8 + 3, scal8 + 4, grad_rgb, n_rgb, C_rgb, H_rgb, W_rgb, stream);
+    if (rc) return rc;
+  }
+  if (grad_op) {
+    AMMC_REQUIRE(op_out && op_tgt, "bad argument");
+    rc = ammc_frame_losses_bwd(op_out, op_tgt, scal8 + 5, nullptr, grad_op, n_op, C_op, H_op, W_op, stream);
+    if (rc) return rc;
+  }
+  if (grad_flow_pred) {
+    rc = ammc_elem_loss_bwd(flow_pred, flow_gt, scal8 + 2, grad_flow_pred, nullptr, ELEM_L1, n_flow, stream);
+    if (rc) return rc;
+  }
+  if (grad_d_gen) {
+    rc = ammc_elem_loss_bwd(d_gen, nullptr, scal8 + 1, grad_d_gen, nullptr, ELEM_LSGAN_G, n_dgen, stream);
+    if (rc) return rc;
+  }
+  return 0;
+}

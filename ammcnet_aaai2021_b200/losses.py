@@ -152,10 +152,65 @@ class Discriminate_Loss(nn.Module):
         return ElemLossFn.apply(OBJ_LSGAN_D, real_outputs, fake_outputs)
 
 
+class GenObjectiveFn(torch.autograd.Function):
+    """(lams, flow_pred, flow_gt, rgb_out, rgb_tgt, op_out, op_tgt, latent, d_gen) -> out8 = [g_loss, adv, flow, int, gd,
+    int_op, latent, 0] from ONE native call (four partial-sum passes + one final kernel); the backward is one native call
+    (chain-rule scalars + one gradient pass per input that needs one).  `lams` = (lam_adv, lam_gdl, lam_flow, lam_lp,
+    lam_latent, lam_lp_op); `latent` is a flat tensor whose elements are summed."""
+
+    @staticmethod
+    def forward(ctx, lams, flow_pred, flow_gt, rgb_out, rgb_tgt, op_out, op_tgt, latent, d_gen):
+        names = ("flow_pred", "flow_gt", "rgb_G_output", "rgb_target", "op_G_output", "op_target", "latent_diff", "d_gen")
+        ts = (flow_pred, flow_gt, rgb_out, rgb_tgt, op_out, op_tgt, latent, d_gen)
+        _require_cuda_f32(*ts, names=names)
+        for (x, y), what in (((flow_pred, flow_gt), "flows"), ((rgb_out, rgb_tgt), "rgb frames"), ((op_out, op_tgt), "flow-stream frames")):
+            if x.shape != y.shape:
+                raise RuntimeError("ammc_b200: %s need two tensors of equal shape, got %s / %s" % (what, tuple(x.shape), tuple(y.shape)))
+        if rgb_out.dim() != 4 or op_out.dim() != 4:
+            raise RuntimeError("ammc_b200: the generator objective needs [n, C, H, W] predictions")
+        if any(t.numel() == 0 for t in ts):
+            raise RuntimeError("ammc_b200: the generator objective of an empty tensor is undefined")
+        if any(t.device != rgb_out.device for t in ts):
+            raise RuntimeError("ammc_b200: the generator objective needs all its tensors on one device")
+        _check_device(rgb_out.device)
+        flow_pred, flow_gt, rgb_out, rgb_tgt, op_out, op_tgt, latent, d_gen = (t.contiguous() for t in ts)
+        out = torch.empty((8,), dtype=torch.float32, device=rgb_out.device)
+        dims = tuple(rgb_out.shape) + tuple(op_out.shape) + (flow_pred.numel(), d_gen.numel())
+        lib = _capi.load()
+        ws = _workspace(lib.ammc_gen_objective_workspace_bytes(dims[0], dims[2], dims[3], dims[4], dims[6], dims[7], dims[8],
+                                                               dims[9]), rgb_out.device)
+        with torch.cuda.device(rgb_out.device):
+            _capi.call("ammc_gen_objective_fwd", _p(rgb_out), _p(rgb_tgt), _p(op_out), _p(op_tgt), _p(flow_pred), _p(flow_gt),
+                       _p(d_gen), _p(latent), *dims, latent.numel(), *lams, _p(out), _p(ws), ws.numel(), _stream())
+        _count(5)
+        ctx.lams, ctx.dims, ctx.latent_shape = lams, dims, latent.shape
+        ctx.save_for_backward(flow_pred, flow_gt, rgb_out, rgb_tgt, op_out, op_tgt, d_gen)
+        return out
+
+    @staticmethod
+    def backward(ctx, g8):
+        flow_pred, flow_gt, rgb_out, rgb_tgt, op_out, op_tgt, d_gen = ctx.saved_tensors
+        need = ctx.needs_input_grad                         # (lams, flow_pred, flow_gt, rgb_out, rgb_tgt, op_out, op_tgt, latent, d_gen)
+        g_flow = torch.empty_like(flow_pred) if need[1] else None
+        g_rgb = torch.empty_like(rgb_out) if need[3] else None
+        g_op = torch.empty_like(op_out) if need[5] else None
+        g_d = torch.empty_like(d_gen) if need[8] else None
+        scal = torch.empty((8,), dtype=torch.float32, device=rgb_out.device)
+        g8 = g8.contiguous().float()
+        with torch.cuda.device(rgb_out.device):
+            _capi.call("ammc_gen_objective_bwd", _p(rgb_out), _p(rgb_tgt), _p(op_out), _p(op_tgt), _p(flow_pred), _p(flow_gt),
+                       _p(d_gen), _p(g8), *ctx.dims, *ctx.lams, _p(scal), _p(g_rgb), _p(g_op), _p(g_flow), _p(g_d), _stream())
+        _count(1 + sum(g is not None for g in (g_flow, g_rgb, g_op, g_d)))
+        g_lat = scal[6].expand(ctx.latent_shape) if need[7] else None
+        return None, g_flow, None, g_rgb, None, g_op, None, g_lat, g_d
+
+
 class Twostream_vq_Loss(nn.Module):
     """Generator objective of the joint training step, loss_zoo.py:307-350 (ctor: base_Loss, loss_zoo.py:15-45): same
-    arguments, same weighted sum, same `g_*` float attributes after the call.  The reference reads eight scalars back with
-    eight `.item()` synchronisations per step; here the eight values travel in ONE device-to-host copy.  `latent_diff` is
+    arguments, same weighted sum, same `g_*` float attributes after the call.  The reference runs ~35 ATen kernels each way and
+    reads eight scalars back with eight `.item()` synchronisations per step; here the forward is one native call
+    (`ammc_gen_objective_fwd`: four partial-sum passes + one final kernel), the backward another, and the scalars travel in
+    ONE device-to-host copy.  `latent_diff` is
     what the generator returns as its third output: one tensor, or the (rgb, op) tuple of commit losses, which is summed
     (Code/models/unet.py:1065)."""
 
@@ -174,17 +229,15 @@ class Twostream_vq_Loss(nn.Module):
         self.g_int_loss_op = self.g_adv_loss_op = self.g_latent_loss = None
 
     def forward(self, flow_pred, flow_gt, rgb_G_output, rgb_target, op_G_output, op_target, latent_diff, d_gen):
-        g_adv_loss = self.adversarial_loss_fn(d_gen)
-        g_flow_loss = self.flow_loss_fn(flow_pred, flow_gt)
-        g_int_loss, g_gd_loss = frame_losses(rgb_G_output, rgb_target)          # both from one fused pass
-        g_int_loss_op = self.int_loss_fn_op(op_G_output, op_target)
         if isinstance(latent_diff, (tuple, list)):
-            latent_diff = sum(d.sum() for d in latent_diff)
-        g_latent_loss = latent_diff.sum() if latent_diff.dim() else latent_diff
-        g_loss = self.lam_adv * g_adv_loss + self.lam_gdl * g_gd_loss + self.lam_flow * g_flow_loss + \
-            self.lam_lp * g_int_loss + self.lam_latent * g_latent_loss + self.lam_lp_op * g_int_loss_op
-        vals = torch.stack([v.detach().float().reshape(()) for v in
-                            (g_loss, g_adv_loss, g_flow_loss, g_int_loss, g_gd_loss, g_int_loss_op, g_latent_loss)]).tolist()
+            shape, latent = (), torch.cat([d.reshape(-1) for d in latent_diff])
+        else:
+            shape, latent = latent_diff.shape, latent_diff.reshape(-1)
+            if latent.numel() != 1:
+                raise RuntimeError("ammc_b200.Twostream_vq_Loss: latent_diff must hold one value (the reference reads it with "
+                                   ".item()), or be the (rgb, op) tuple the generator returns")
+        lams = tuple(float(v) for v in (self.lam_adv, self.lam_gdl, self.lam_flow, self.lam_lp, self.lam_latent, self.lam_lp_op))
+        out = GenObjectiveFn.apply(lams, flow_pred, flow_gt, rgb_G_output, rgb_target, op_G_output, op_target, latent, d_gen)
         (self.g_loss, self.g_adv_loss, self.g_flow_loss, self.g_int_loss, self.g_gd_loss, self.g_int_loss_op,
-         self.g_latent_loss) = vals
-        return g_loss
+         self.g_latent_loss) = out.detach()[:7].tolist()            # the step's only device-to-host read
+        return out[0].reshape(shape)

@@ -34,6 +34,31 @@ def unpatch_reference(unet_module, saved, utils_module=None):
         utils_module.psnr_error = saved["psnr_error"]
 
 
+_LOSS_NAMES = ("Flow_Loss", "Intensity_Loss", "Gradient_Loss", "Adversarial_Loss", "Discriminate_Loss", "Twostream_vq_Loss")
+
+
+def patch_reference_losses(loss_zoo_module, losses_utils_module=None):
+    """Rebind the training objectives inside the reference's `Code.models.losses.loss_zoo` (which imports the element
+    classes by name from `losses_utils`, loss_zoo.py:3-7, and defines `Twostream_vq_Loss`, loss_zoo.py:307) and, optionally,
+    inside `losses_utils` itself (`Discriminate_Loss` is constructed from there by the training scripts).  Returns what
+    `unpatch_reference_losses` needs."""
+    from . import losses as L
+    saved = {}
+    for mod in (loss_zoo_module, losses_utils_module):
+        if mod is None:
+            continue
+        for n in _LOSS_NAMES:
+            if hasattr(mod, n):
+                saved[(mod.__name__, n)] = (mod, getattr(mod, n))
+                setattr(mod, n, getattr(L, n))
+    return saved
+
+
+def unpatch_reference_losses(saved):
+    for (_, n), (mod, cls) in saved.items():
+        setattr(mod, n, cls)
+
+
 def _convert(child: nn.Module):
     name = type(child).__name__
     if name == "enc_quan_dec_res_topk" and not isinstance(child, M.enc_quan_dec_res_topk):

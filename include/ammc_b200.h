@@ -415,6 +415,28 @@ int ammc_elem_loss_fwd(const float* a, const float* b, float* out1, int mode, in
 int ammc_elem_loss_bwd(const float* a, const float* b, const float* g, float* grad_a, float* grad_b, int mode, int64_t n,
                        void* stream);
 
+/* ---- generator objective of the joint training step in one call (Twostream_vq_Loss.forward,
+ * Code/models/losses/loss_zoo.py:312-350; ctor base_Loss, loss_zoo.py:15-45) ----------------------------------------------
+ *   out8[0] = lam_adv * adv + lam_gdl * gd + lam_flow * flow + lam_lp * int + lam_latent * latent + lam_lp_op * int_op
+ *   out8[1..6] = adv (Adversarial_Loss of d_gen), flow (Flow_Loss), int / gd (Intensity / Gradient loss of the rgb pair),
+ *   int_op (Intensity loss of the flow-stream pair), latent (sum of the n_latent commit-loss values); out8[7] = 0.
+ * rgb pair [n_rgb, C_rgb, H_rgb, W_rgb], op pair [n_op, C_op, H_op, W_op], flows n_flow elements each, d_gen n_dgen elements.
+ * fwd: four partial-sum passes + one final kernel (fixed summation order).  bwd: g8 = gradient w.r.t. out8 (device, 8 floats);
+ * scal8 (device, 8 floats, output) receives the chain-rule scalars [g8[0], d/d adv, d/d flow, d/d int, d/d gd, d/d int_op,
+ * d/d latent, 0]; each non-NULL gradient pointer is written by one pass (grad of the latent values = scal8[6] each). */
+size_t ammc_gen_objective_workspace_bytes(int n_rgb, int H_rgb, int W_rgb, int n_op, int H_op, int W_op, int64_t n_flow,
+                                          int64_t n_dgen);
+int ammc_gen_objective_fwd(const float* rgb_out, const float* rgb_tgt, const float* op_out, const float* op_tgt,
+                           const float* flow_pred, const float* flow_gt, const float* d_gen, const float* latent, int n_rgb,
+                           int C_rgb, int H_rgb, int W_rgb, int n_op, int C_op, int H_op, int W_op, int64_t n_flow, int64_t n_dgen,
+                           int n_latent, float lam_adv, float lam_gdl, float lam_flow, float lam_lp, float lam_latent,
+                           float lam_lp_op, float* out8, void* workspace, size_t workspace_bytes, void* stream);
+int ammc_gen_objective_bwd(const float* rgb_out, const float* rgb_tgt, const float* op_out, const float* op_tgt,
+                           const float* flow_pred, const float* flow_gt, const float* d_gen, const float* g8, int n_rgb, int C_rgb,
+                           int H_rgb, int W_rgb, int n_op, int C_op, int H_op, int W_op, int64_t n_flow, int64_t n_dgen,
+                           float lam_adv, float lam_gdl, float lam_flow, float lam_lp, float lam_latent, float lam_lp_op,
+                           float* scal8, float* grad_rgb, float* grad_op, float* grad_flow_pred, float* grad_d_gen, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -126,3 +126,46 @@ def test_objectives_refuse_what_they_do_not_cover():
         A.Adversarial_Loss()(torch.zeros(4, device=DEV, dtype=torch.float16))
     with pytest.raises(RuntimeError, match="empty"):
         A.Adversarial_Loss()(torch.zeros(0, device=DEV))
+
+
+@pytest.mark.parametrize("b,h,w,hd,wd", [(1, 8, 8, 3, 3), (2, 33, 17, 5, 4), (3, 64, 48, 34, 34)])
+def test_generator_objective_every_component_differentiates(b, h, w, hd, wd):
+    """All seven outputs of the fused objective carry gradients (a caller may log or weight them separately), every input that
+    asks for a gradient gets one (the flow prediction too), and the generator's (rgb, op) commit-loss tuple is accepted."""
+    from ammcnet_aaai2021_b200.losses import GenObjectiveFn
+    t = synth.objective_inputs(dict(seed=70 + h, b=b, h=h, w=w, hd=hd, wd=wd))
+    lam = dict(lam_adv=0.05, lam_gdl=1.0, lam_flow=2.0, lam_lp=1.0, lam_latent=0.25, lam_lp_op=2.0)
+    keys = ("flow_pred", "rgb_out", "op_out", "d_gen")
+    lat2 = torch.tensor([[0.031], [0.012]])                                     # two [1]-shaped commit losses, stacked
+    wts = torch.tensor([1.0, 0.3, -0.2, 0.5, 0.7, -0.4, 1.5, 9.0])
+    dv = {k: v.to(DEV) for k, v in t.items()}
+    for k in keys:
+        dv[k].requires_grad_(True)
+    lat_d = lat2.to(DEV).requires_grad_(True)
+    lams = (lam["lam_adv"], lam["lam_gdl"], lam["lam_flow"], lam["lam_lp"], lam["lam_latent"], lam["lam_lp_op"])
+    out = GenObjectiveFn.apply(lams, dv["flow_pred"], dv["flow_gt"], dv["rgb_out"], dv["rgb_tgt"], dv["op_out"], dv["op_tgt"],
+                               lat_d.reshape(-1), dv["d_gen"])
+    (out * wts.to(DEV)).sum().backward()
+    rv = {k: v.double() for k, v in t.items()}
+    for k in keys:
+        rv[k].requires_grad_(True)
+    lat_r = lat2.double().requires_grad_(True)
+    loss, parts = O.twostream_vq_loss(lam, rv["flow_pred"], rv["flow_gt"], rv["rgb_out"], rv["rgb_tgt"], rv["op_out"], rv["op_tgt"],
+                                      lat_r.sum(), rv["d_gen"])
+    order = ("g_loss", "g_adv_loss", "g_flow_loss", "g_int_loss", "g_gd_loss", "g_int_loss_op", "g_latent_loss")
+    ref = torch.stack([parts[k].reshape(()) for k in order])
+    assert_close(out.detach().cpu()[:7], ref.detach(), 1e-5, "out8")
+    assert float(out.detach()[7]) == 0.0
+    (ref * wts[:7].double()).sum().backward()
+    for k in keys:
+        assert_close(dv[k].grad.cpu(), rv[k].grad, 1e-5, "grad " + k)
+    assert_close(lat_d.grad.cpu(), lat_r.grad, 1e-5, "grad latent")
+    # the module form with the tuple the generator returns as its third output
+    fn = A.Twostream_vq_Loss(**lam)
+    got = fn(dv["flow_pred"], dv["flow_gt"], dv["rgb_out"], dv["rgb_tgt"], dv["op_out"], dv["op_tgt"],
+             (lat_d[0], lat_d[1]), dv["d_gen"])
+    assert got.dim() == 0
+    assert_close(got.detach().cpu(), loss.detach(), 1e-5, "module g_loss")
+    assert abs(fn.g_latent_loss - float(lat2.sum())) < 1e-6
+    with pytest.raises(RuntimeError, match="one value"):
+        fn(dv["flow_pred"], dv["flow_gt"], dv["rgb_out"], dv["rgb_tgt"], dv["op_out"], dv["op_tgt"], lat_d, dv["d_gen"])

@@ -118,3 +118,30 @@ def test_objectives_refuse_cpu_tensors():
     z = torch.zeros(1, 3, 8, 8)
     with pytest.raises(RuntimeError, match="CUDA"):
         f(z[:, :2], z[:, :2], z, z, z[:, :2], z[:, :2], torch.zeros(1), torch.zeros(1, 1, 3, 3))
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference tree only exists in the build container")
+def test_patch_reference_losses_against_live_reference():
+    """The reference's loss modules rebound to this package's classes: the `Twostream_vq_Loss` a training script then builds
+    through loss_zoo is ours, with the same constructor keywords and sub-module attribute names; unpatching restores."""
+    import sys, types
+    import ref_harness
+    ref_harness.import_reference()
+    stub = types.ModuleType("Code.main.constant_train")
+    stub.const = types.SimpleNamespace(gpu_idx="0")
+    sys.modules.setdefault("Code.main.constant_train", stub)
+    import Code.models.losses.losses_utils as LU
+    import Code.models.losses.loss_zoo as LZ
+    ref_cls = LZ.Twostream_vq_Loss
+    ref_obj = ref_cls(lam_adv=0.05, lam_gdl=1.0, lam_flow=2.0, lam_lp=1.0, lam_latent=0.1, lam_lp_op=2.0)
+    saved = A.patch_reference_losses(LZ, LU)
+    try:
+        ours = LZ.Twostream_vq_Loss(lam_adv=0.05, lam_gdl=1.0, lam_flow=2.0, lam_lp=1.0, lam_latent=0.1, lam_lp_op=2.0)
+        assert isinstance(ours, A.Twostream_vq_Loss) and LU.Discriminate_Loss is A.Discriminate_Loss
+        assert LZ.Flow_Loss is A.Flow_Loss and LZ.Intensity_Loss is A.Intensity_Loss
+        ref_attrs = {k for k in vars(ref_obj) if k.startswith(("lam_", "g_"))} | set(dict(ref_obj.named_children()))
+        our_attrs = {k for k in vars(ours) if k.startswith(("lam_", "g_"))} | set(dict(ours.named_children()))
+        assert ref_attrs <= our_attrs, ref_attrs - our_attrs
+    finally:
+        A.unpatch_reference_losses(saved)
+    assert LZ.Twostream_vq_Loss is ref_cls and LU.Discriminate_Loss is not A.Discriminate_Loss

@@ -72,7 +72,7 @@ for n in (8, 64):
         loss, parts = O.twostream_vq_loss(LAM, t["flow_pred"], t["flow_gt"], t["rgb_out"], t["rgb_tgt"], t["op_out"], t["op_tgt"],
                                           t["latent"], t["d_gen"])
         loss.backward()
-        [float(v) for v in parts.values()]                      # the reference's per-scalar .item() reads (loss_zoo.py:341-348)
+        [v.item() for v in parts.values()]                      # the reference's per-scalar .item() reads (loss_zoo.py:341-348)
 
     fa, fb, da, db, oa, ob = (timed(f) for f in (flow_ours, flow_torch, dis_ours, dis_torch, obj_ours, obj_torch))
     fby = t["flow_pred"].numel() * 4 * 5
