@@ -9,7 +9,7 @@ from .modules import Quantize_topk, enc_quan_dec_topk, enc_quan_dec_res_topk, br
 from .functions import psnr_per_frame
 from .scoring import VideoScorer, assemble_video_records, score_reduce, evaluate, LAM_MAP
 from .patch import patch_reference, unpatch_reference, swap_modules, patch_reference_losses, unpatch_reference_losses
-from .host_model import twostream, UNetMem_v7, get_twostream, PixelDiscriminator
+from .host_model import twostream, UNetMem_v7, get_twostream, PixelDiscriminator, FlowNet2SD
 from .graphs import GraphedPath
 from .generator import GeneratorEngine
 from .preprocess import preprocess_frames, preprocess_flow, load_video, widen_bf16, narrow_bf16
@@ -20,6 +20,6 @@ from .loader import VideoLoader, read_flo, write_flo, decode_frame
 __all__ = [
     "Quantize_topk", "enc_quan_dec_topk", "enc_quan_dec_res_topk", "bridge", "double_conv", "psnr_error",
     "psnr_per_frame", "VideoScorer", "assemble_video_records", "score_reduce", "evaluate", "LAM_MAP",
-    "patch_reference", "unpatch_reference", "swap_modules", "patch_reference_losses", "unpatch_reference_losses", "twostream", "UNetMem_v7", "get_twostream", "PixelDiscriminator", "GraphedPath", "GeneratorEngine", "preprocess_frames", "preprocess_flow", "load_video", "widen_bf16", "narrow_bf16", "Intensity_Loss", "Gradient_Loss", "frame_losses", "Flow_Loss", "Adversarial_Loss", "Discriminate_Loss",
+    "patch_reference", "unpatch_reference", "swap_modules", "patch_reference_losses", "unpatch_reference_losses", "twostream", "UNetMem_v7", "get_twostream", "PixelDiscriminator", "FlowNet2SD", "GraphedPath", "GeneratorEngine", "preprocess_frames", "preprocess_flow", "load_video", "widen_bf16", "narrow_bf16", "Intensity_Loss", "Gradient_Loss", "frame_losses", "Flow_Loss", "Adversarial_Loss", "Discriminate_Loss",
     "Twostream_vq_Loss", "VideoLoader", "read_flo", "write_flo", "decode_frame",
 ]

@@ -139,3 +139,75 @@ class PixelDiscriminator(nn.Module):
 
     def forward(self, input):
         return self.net(input)
+
+
+def _flow_conv(bn, cin, cout, stride=1, act=True):
+    layers = [nn.Conv2d(cin, cout, 3, stride, 1, bias=not (bn and act))]
+    if bn:
+        layers.append(nn.BatchNorm2d(cout))
+    if act:
+        layers.append(nn.LeakyReLU(0.1, inplace=True))
+    return nn.Sequential(*layers)
+
+
+class FlowNet2SD(nn.Module):
+    """Host-side mirror of the frozen flow estimator of the training step (reference Code/models/flownet2/models.py:9-58 on
+    Code/models/flownet2/FlowNetSD.py:7-100 and submodules.py:8-48; called twice per step on (last input frame, prediction)
+    and (last input frame, target), train_helper.py:309-322).  Same constructor, same module names -- a reference /
+    NVIDIA FlowNet2-SD checkpoint loads with strict=True (45 371 666 parameters) -- and the same forward: per-sample channel
+    means removed, /255, the two frames stacked on the channel axis, 13 encoder convolutions (6 of them stride 2), a
+    4-level refinement decoder (transposed convolutions + flow up-sampling + skip concatenation), x`div_flow` and 4x bilinear
+    up-sampling in eval mode; the five multi-scale flows in training mode.  Stock torch.nn layers (cuDNN): plumbing for
+    `tools/train_step.py --gan --flownet`, outside the hot path; the `Flow_Loss` that consumes its two outputs is a kernel of
+    this package (`losses.py`).  No weights ship with either repository: tools build it with random initial weights."""
+
+    _ENCODER = (("conv0", 6, 64, 1), ("conv1", 64, 64, 2), ("conv1_1", 64, 128, 1), ("conv2", 128, 128, 2),
+                ("conv2_1", 128, 128, 1), ("conv3", 128, 256, 2), ("conv3_1", 256, 256, 1), ("conv4", 256, 512, 2),
+                ("conv4_1", 512, 512, 1), ("conv5", 512, 512, 2), ("conv5_1", 512, 512, 1), ("conv6", 512, 1024, 2),
+                ("conv6_1", 1024, 1024, 1))
+    _SKIP = {2: 128, 3: 256, 4: 512, 5: 512}                      # channels of the encoder output joined at each level
+    _DECODER = {5: 512, 4: 256, 3: 128, 2: 64}                    # channels the level's transposed convolution produces
+
+    def __init__(self, batchNorm=False, div_flow=20):
+        super().__init__()
+        self.batchNorm, self.rgb_max, self.div_flow = batchNorm, 255., div_flow
+        for name, cin, cout, stride in self._ENCODER:
+            setattr(self, name, _flow_conv(batchNorm, cin, cout, stride))
+        levels = (5, 4, 3, 2)
+        joined = {lvl: self._SKIP[lvl] + self._DECODER[lvl] + 2 for lvl in levels}      # skip + decoded + up-sampled flow
+        for lvl in levels:                                          # registration order = the reference's state_dict order
+            below = 1024 if lvl == 5 else joined[lvl + 1]
+            setattr(self, "deconv%d" % lvl, nn.Sequential(nn.ConvTranspose2d(below, self._DECODER[lvl], 4, 2, 1),
+                                                          nn.LeakyReLU(0.1, inplace=True)))
+        for lvl in levels:
+            setattr(self, "inter_conv%d" % lvl, _flow_conv(batchNorm, joined[lvl], self._DECODER[lvl], act=False))
+        self.predict_flow6 = nn.Conv2d(1024, 2, 3, 1, 1)
+        for lvl in levels:
+            setattr(self, "predict_flow%d" % lvl, nn.Conv2d(self._DECODER[lvl], 2, 3, 1, 1))
+        for lvl in levels:
+            setattr(self, "upsampled_flow%d_to_%d" % (lvl + 1, lvl), nn.ConvTranspose2d(2, 2, 4, 2, 1))
+        for m in self.modules():                                    # FlowNetSD.py:46-56
+            if isinstance(m, (nn.Conv2d, nn.ConvTranspose2d)):
+                if m.bias is not None:
+                    nn.init.uniform_(m.bias)
+                nn.init.xavier_uniform_(m.weight)
+        self.upsample1 = nn.Upsample(scale_factor=4, mode="bilinear")
+
+    def forward(self, inputs):
+        """inputs [b, 3, 2, h, w] in (0, 255), h and w multiples of 64."""
+        mean = inputs.flatten(2).mean(dim=-1)[:, :, None, None, None]
+        x = ((inputs - mean) / self.rgb_max).transpose(1, 2).flatten(1, 2)          # frame 0's channels, then frame 1's
+        skips = {}
+        for name, _, _, _ in self._ENCODER:
+            x = getattr(self, name)(x)
+            if name.endswith("_1"):
+                skips[int(name[4])] = x
+        joined = skips[6]
+        flows = [self.predict_flow6(joined)]
+        for lvl in (5, 4, 3, 2):
+            up = getattr(self, "upsampled_flow%d_to_%d" % (lvl + 1, lvl))(flows[-1])
+            joined = torch.cat((skips[lvl], getattr(self, "deconv%d" % lvl)(joined), up), 1)
+            flows.append(getattr(self, "predict_flow%d" % lvl)(getattr(self, "inter_conv%d" % lvl)(joined)))
+        if self.training:
+            return tuple(reversed(flows))                           # flow2 ... flow6
+        return self.upsample1(flows[-1] * self.div_flow)

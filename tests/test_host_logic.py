@@ -145,3 +145,32 @@ def test_patch_reference_losses_against_live_reference():
     finally:
         A.unpatch_reference_losses(saved)
     assert LZ.Twostream_vq_Loss is ref_cls and LU.Discriminate_Loss is not A.Discriminate_Loss
+
+
+def test_flownet2sd_layout():
+    """'Parameter count = 45,371,666' (reference Code/models/flownet2/FlowNetSD.py:4)."""
+    f = A.FlowNet2SD()
+    assert sum(p.numel() for p in f.parameters()) == 45371666
+    sd = f.state_dict()
+    assert tuple(sd["deconv4.0.weight"].shape) == (1026, 256, 4, 4) and tuple(sd["inter_conv2.0.weight"].shape) == (64, 194, 3, 3)
+    assert tuple(sd["upsampled_flow6_to_5.weight"].shape) == (2, 2, 4, 4) and "conv6_1.0.bias" in sd
+    with torch.no_grad():
+        assert tuple(f.eval()(torch.rand(1, 3, 2, 64, 64) * 255).shape) == (1, 2, 64, 64)
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference tree only exists in the build container")
+def test_flownet2sd_against_live_reference():
+    import ref_harness
+    ref_harness.import_reference()
+    import Code.models.flownet2.models as RM
+    torch.manual_seed(5)
+    x = torch.rand(2, 3, 2, 64, 128) * 255
+    for bn in (False, True):
+        r = RM.FlowNet2SD(batchNorm=bn)
+        o = A.FlowNet2SD(batchNorm=bn)
+        assert list(o.state_dict()) == list(r.state_dict())
+        o.load_state_dict(r.state_dict(), strict=True)
+        with torch.no_grad():
+            assert torch.equal(o.eval()(x), r.eval()(x))
+            for a, b in zip(o.train()(x), r.train()(x)):
+                assert torch.equal(a, b)

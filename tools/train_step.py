@@ -11,8 +11,10 @@ intensity L2 on the rgb prediction, L1 on the flow prediction, lam_latent * (rgb
 `Discriminate_Loss`, then the generator on `Twostream_vq_Loss` (fused adversarial / flow / intensity / gradient objectives,
 one host read of its eight scalars).  The discriminator update comes first here: the reference back-propagates the
 generator objective through discriminator weights its optimizer has already stepped, which current autograd refuses.
-FlowNet2-SD is not built (no weights offline): `Flow_Loss` is fed the flow-stream prediction / target instead of two
-FlowNet outputs -- tensors of the same shape and role.
+With `--flownet` the frozen flow estimator (`FlowNet2SD` host mirror on cuDNN layers, random initial weights: no checkpoint
+exists offline) produces the two flows `Flow_Loss` compares, exactly as train_helper.py:309-322 does (detached, inputs
+rescaled to (0, 255), outputs / 255); without it `Flow_Loss` is fed the flow-stream prediction / target -- tensors of the
+same shape and role.
 
     torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/train_step.py --steps 10 --batch 8
 """
@@ -33,6 +35,7 @@ def main():
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--sync-bn", action="store_true", help="global-batch BatchNorm statistics (single-GPU semantics)")
     ap.add_argument("--gan", action="store_true", help="adversarial step structure: discriminator + Twostream_vq_Loss")
+    ap.add_argument("--flownet", action="store_true", help="with --gan: frozen FlowNet2SD (random weights) feeds Flow_Loss")
     args = ap.parse_args()
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
     torch.cuda.set_device(local)
@@ -59,6 +62,15 @@ def main():
         d_params = [p for p in D.parameters()]
         g_loss_fn = A.Twostream_vq_Loss(lam_adv=0.05, lam_gdl=1.0, lam_flow=2.0, lam_lp=1.0, lam_latent=0.1, lam_lp_op=2.0)
         d_loss_fn = A.Discriminate_Loss()
+        flow_net = A.FlowNet2SD().to(dev).eval() if args.flownet else None
+        rgb_last = rgb[:, -1]                                   # `rgb_input_last` of train_helper.py:299
+
+    def flows_of(pr):
+        if flow_net is None:
+            return None
+        with torch.no_grad():
+            pair = lambda second: (torch.stack([rgb_last, second], 2) * 0.5 + 0.5) * 255.0
+            return flow_net(pair(pr.detach())) / 255.0, flow_net(pair(rgb_tgt)) / 255.0
 
     def gan_step():
         pr, po, diffs, _ = g(rgb_in, op_in)
@@ -70,7 +82,9 @@ def main():
         opt.zero_grad(set_to_none=True)                         # (2) generator; the discriminator only carries the gradient
         for p in d_params:
             p.requires_grad_(False)
-        loss = g_loss_fn(po, op_tgt, pr, rgb_tgt, po, op_tgt, diffs, D(pr))
+        fl = flows_of(pr)
+        flow_pred, flow_gt = fl if fl is not None else (po, op_tgt)
+        loss = g_loss_fn(flow_pred, flow_gt, pr, rgb_tgt, po, op_tgt, diffs, D(pr))
         loss.backward()
         for p in d_params:
             p.requires_grad_(True)
@@ -121,7 +135,7 @@ def main():
         dist.all_reduce(bank_max_dev, op=dist.ReduceOp.MAX); dist.all_reduce(w_max_dev, op=dist.ReduceOp.MAX)
     if rank == 0:
         ls = [float(l) for l in losses]
-        print(json.dumps({"what": "joint training step (generator fwd+bwd, EMA stats + gradient all-reduce, Adam)" + (" + discriminator update, Twostream_vq_Loss" if args.gan else ""),
+        print(json.dumps({"what": "joint training step (generator fwd+bwd, EMA stats + gradient all-reduce, Adam)" + (" + discriminator update, Twostream_vq_Loss" + (", frozen FlowNet2SD x2" if args.flownet else "") if args.gan else ""),
                           "n_gpus": world, "batch_per_gpu": B, "batch_norm": "global batch (all-reduced sums)" if args.sync_bn else "per rank", "steps": args.steps, "ms_per_step": float(ms) / args.steps,
                           "frames_per_s": world * B * args.steps / (float(ms) * 1e-3), "loss_first": ls[0], "loss_last": ls[-1],
                           "finite": all(l == l and abs(l) < 1e30 for l in ls),
