@@ -54,18 +54,22 @@ __global__ void __launch_bounds__(256) frame_loss_partial_kernel(const float* __
 }
 
 // out[0] = intensity, out[1] = gradient: fixed-order sum of the partials (deterministic), divided by the pixel count
-__global__ void __launch_bounds__(256) frame_loss_final_kernel(const float* __restrict__ partial, float* __restrict__ out,
-                                                                int n_partials, double inv_count) {
-  __shared__ double red[2][8];
+__global__ void __launch_bounds__(1024) frame_loss_final_kernel(const float* __restrict__ partial, float* __restrict__ out,
+                                                                 int n_partials, double inv_count) {
+  __shared__ double red[2][32];
   double a = 0.0, b = 0.0;
-  for (int i = threadIdx.x; i < n_partials; i += 256) { a += (double)partial[2 * i]; b += (double)partial[2 * i + 1]; }
+  for (int i = threadIdx.x; i < n_partials; i += 1024) {
+    const float2 v = reinterpret_cast<const float2*>(partial)[i];
+    a += (double)v.x;
+    b += (double)v.y;
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
   if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = a; red[1][threadIdx.x >> 5] = b; }
   __syncthreads();
   if (threadIdx.x == 0) {
     double sa = 0.0, sb = 0.0;
-    for (int i = 0; i < 8; ++i) { sa += red[0][i]; sb += red[1][i]; }
+    for (int i = 0; i < 32; ++i) { sa += red[0][i]; sb += red[1][i]; }
     out[0] = (float)(sa * inv_count);
     out[1] = (float)(sb * inv_count);
   }
@@ -104,6 +108,145 @@ __global__ void __launch_bounds__(256) frame_loss_bwd_kernel(const float* __rest
   for (int c = 0; c < C; ++c) grad_gen[img + c * plane + p] = -(ki * d[c]) - kg;
 }
 
+
+// ---- 4 pixels per thread (W % 4 == 0, 16-byte aligned tensors): 16-byte loads / stores, the channel sums of the left / right /
+// upper / lower neighbours come from the block's shared table where the neighbour quad belongs to the block, from L1/L2-resident
+// global memory otherwise; a quarter of the partials for the final sum.
+template <int C>
+__device__ __forceinline__ float4 chan_sum_diff4(const float* __restrict__ gen, const float* __restrict__ gt, size_t base,
+                                                 size_t plane) {
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    const float4 a = *reinterpret_cast<const float4*>(gt + base + c * plane);
+    const float4 b = *reinterpret_cast<const float4*>(gen + base + c * plane);
+    s.x += a.x - b.x; s.y += a.y - b.y; s.z += a.z - b.z; s.w += a.w - b.w;
+  }
+  return s;
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) frame_loss_partial4_kernel(const float* __restrict__ gen, const float* __restrict__ gt,
+                                                                   float* __restrict__ partial, int H, int W) {
+  __shared__ float red[33];
+  __shared__ float4 sS[256];
+  const size_t plane = (size_t)H * W;
+  const int nq = (H * W) >> 2, wq = W >> 2, tid = threadIdx.x;
+  const int q = blockIdx.x * 256 + tid;
+  const size_t img = (size_t)blockIdx.y * C * plane;
+  const bool live = q < nq;
+  const int p = q << 2, h = live ? p / W : 0, w = live ? p - h * W : 0;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  float vi = 0.f, vg = 0.f;
+  if (live) {
+    float4 n2 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float4 a = *reinterpret_cast<const float4*>(gt + img + c * plane + p);
+      const float4 b = *reinterpret_cast<const float4*>(gen + img + c * plane + p);
+      const float dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z, dw = a.w - b.w;
+      n2.x = fmaf(dx, dx, n2.x); n2.y = fmaf(dy, dy, n2.y); n2.z = fmaf(dz, dz, n2.z); n2.w = fmaf(dw, dw, n2.w);
+      s.x += dx; s.y += dy; s.z += dz; s.w += dw;
+    }
+    vi = (sqrtf(n2.x) + sqrtf(n2.y)) + (sqrtf(n2.z) + sqrtf(n2.w));
+  }
+  sS[tid] = s;
+  __syncthreads();
+  if (live) {
+    float sl0 = 0.f;
+    if (w > 0) sl0 = tid > 0 ? sS[tid - 1].w : chan_sum_diff<C>(gen, gt, img + p - 1, plane);
+    float4 su = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (h > 0) su = tid >= wq ? sS[tid - wq] : chan_sum_diff4<C>(gen, gt, img + p - W, plane);
+    vg = (fabsf(s.x - sl0) + fabsf(s.x - su.x)) + (fabsf(s.y - s.x) + fabsf(s.y - su.y)) +
+         (fabsf(s.z - s.y) + fabsf(s.z - su.z)) + (fabsf(s.w - s.z) + fabsf(s.w - su.w));
+  }
+  const float a = block_sum(vi, red);
+  __syncthreads();
+  const float b = block_sum(vg, red);
+  if (tid == 0) {
+    const size_t o = ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 2;
+    partial[o] = a;
+    partial[o + 1] = b;
+  }
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) frame_loss_bwd4_kernel(const float* __restrict__ gen, const float* __restrict__ gt,
+                                                               const float* __restrict__ g_int, const float* __restrict__ g_gd,
+                                                               float* __restrict__ grad_gen, int H, int W, float inv_count) {
+  __shared__ float4 sS[256];
+  const size_t plane = (size_t)H * W;
+  const int nq = (H * W) >> 2, wq = W >> 2, tid = threadIdx.x;
+  const int q = blockIdx.x * 256 + tid;
+  const size_t img = (size_t)blockIdx.y * C * plane;
+  const bool live = q < nq;
+  const int p = q << 2, h = live ? p / W : 0, w = live ? p - h * W : 0;
+  float4 d[C];
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f), n2 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (live) {
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float4 a = *reinterpret_cast<const float4*>(gt + img + c * plane + p);
+      const float4 b = *reinterpret_cast<const float4*>(gen + img + c * plane + p);
+      d[c] = make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w);
+      n2.x = fmaf(d[c].x, d[c].x, n2.x); n2.y = fmaf(d[c].y, d[c].y, n2.y);
+      n2.z = fmaf(d[c].z, d[c].z, n2.z); n2.w = fmaf(d[c].w, d[c].w, n2.w);
+      s.x += d[c].x; s.y += d[c].y; s.z += d[c].z; s.w += d[c].w;
+    }
+  }
+  sS[tid] = s;
+  __syncthreads();
+  if (!live) return;
+  const float gi = g_int ? g_int[0] : 0.f, gg = g_gd ? g_gd[0] : 0.f;
+  float sl0 = 0.f;
+  if (w > 0) sl0 = tid > 0 ? sS[tid - 1].w : chan_sum_diff<C>(gen, gt, img + p - 1, plane);
+  float4 su = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (h > 0) su = tid >= wq ? sS[tid - wq] : chan_sum_diff4<C>(gen, gt, img + p - W, plane);
+  // forward differences of this quad's own terms (zero padding on the left / top keeps the term)
+  float4 t = make_float4(sgn(s.x - sl0) + sgn(s.x - su.x), sgn(s.y - s.x) + sgn(s.y - su.y), sgn(s.z - s.y) + sgn(s.z - su.z),
+                         sgn(s.w - s.z) + sgn(s.w - su.w));
+  // minus the terms of the right / lower neighbours in which this pixel is the subtrahend
+  t.x -= sgn(s.y - s.x); t.y -= sgn(s.z - s.y); t.z -= sgn(s.w - s.z);
+  if (w + 4 < W) t.w -= sgn((tid < 255 ? sS[tid + 1].x : chan_sum_diff<C>(gen, gt, img + p + 4, plane)) - s.w);
+  if (h + 1 < H) {
+    const float4 sd = tid + wq < 256 ? sS[tid + wq] : chan_sum_diff4<C>(gen, gt, img + p + W, plane);
+    t.x -= sgn(sd.x - s.x); t.y -= sgn(sd.y - s.y); t.z -= sgn(sd.z - s.z); t.w -= sgn(sd.w - s.w);
+  }
+  const float gic = gi * inv_count, ggc = gg * inv_count;
+  const float4 nr = make_float4(sqrtf(n2.x), sqrtf(n2.y), sqrtf(n2.z), sqrtf(n2.w));
+  const float4 ki = make_float4(nr.x > 0.f ? gic / nr.x : 0.f, nr.y > 0.f ? gic / nr.y : 0.f, nr.z > 0.f ? gic / nr.z : 0.f,
+                                nr.w > 0.f ? gic / nr.w : 0.f);
+  const float4 kg = make_float4(ggc * t.x, ggc * t.y, ggc * t.z, ggc * t.w);
+#pragma unroll
+  for (int c = 0; c < C; ++c)
+    *reinterpret_cast<float4*>(grad_gen + img + c * plane + p) =
+        make_float4(-(ki.x * d[c].x) - kg.x, -(ki.y * d[c].y) - kg.y, -(ki.z * d[c].z) - kg.z, -(ki.w * d[c].w) - kg.w);
+}
+
+static inline bool frame_quads_ok(const void* a, const void* b, const void* c, int W) {
+  return W % 4 == 0 && (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c) & 15) == 0;
+}
+
+// launches the partial-sum pass of one (gen, gt) pair; *n_partials = number of (intensity, gradient) PAIRS written
+static int launch_frame_partial(const float* gen, const float* gt, float* partial, int n, int C, int H, int W, cudaStream_t st,
+                                int* n_partials) {
+  const bool quads = frame_quads_ok(gen, gt, nullptr, W);
+  const int bx = quads ? ceil_div(((int64_t)H * W) >> 2, 256) : ceil_div((int64_t)H * W, 256);
+  switch (C) {
+#define AMMC_FL_CASE(CC)                                                                                      \
+  case CC:                                                                                                    \
+    if (quads) frame_loss_partial4_kernel<CC><<<dim3(bx, n), 256, 0, st>>>(gen, gt, partial, H, W);           \
+    else frame_loss_partial_kernel<CC><<<dim3(bx, n), 256, 0, st>>>(gen, gt, partial, H, W);                  \
+    break;
+    AMMC_FL_CASE(1) AMMC_FL_CASE(2) AMMC_FL_CASE(3) AMMC_FL_CASE(4) AMMC_FL_CASE(5) AMMC_FL_CASE(6) AMMC_FL_CASE(7) AMMC_FL_CASE(8)
+#undef AMMC_FL_CASE
+    default: return fail(AMMC_EINVAL, "frame losses support 1..%d channels (got %d)", LOSS_MAX_C, C);
+  }
+  AMMC_LAUNCH_CHECK("frame_loss_partial_kernel");
+  *n_partials = bx * n;
+  return 0;
+}
+
 }  // namespace ammc
 
 using namespace ammc;
@@ -119,15 +262,10 @@ extern "C" int ammc_frame_losses_fwd(const float* gen, const float* gt, float* o
   AMMC_REQUIRE(C >= 1 && C <= LOSS_MAX_C, "frame losses support 1..%d channels (got %d)", LOSS_MAX_C, C);
   AMMC_REQUIRE(n <= 65535, "batch %d too large for one launch", n);
   if (!workspace || workspace_bytes < ammc_frame_losses_workspace_bytes(n, H, W)) return fail(AMMC_EWORKSPACE, "workspace too small");
-  const int bx = ceil_div((int64_t)H * W, 256);
   float* partial = (float*)workspace;
-  switch (C) {
-#define AMMC_FL_CASE(CC) case CC: frame_loss_partial_kernel<CC><<<dim3(bx, n), 256, 0, st>>>(gen, gt, partial, H, W); break;
-    AMMC_FL_CASE(1) AMMC_FL_CASE(2) AMMC_FL_CASE(3) AMMC_FL_CASE(4) AMMC_FL_CASE(5) AMMC_FL_CASE(6) AMMC_FL_CASE(7) AMMC_FL_CASE(8)
-#undef AMMC_FL_CASE
-  }
-  AMMC_LAUNCH_CHECK("frame_loss_partial_kernel");
-  frame_loss_final_kernel<<<1, 256, 0, st>>>(partial, out2, bx * n, 1.0 / ((double)n * H * W));
+  int n_partials = 0;
+  if (int rc = launch_frame_partial(gen, gt, partial, n, C, H, W, st, &n_partials)) return rc;
+  frame_loss_final_kernel<<<1, 1024, 0, st>>>(partial, out2, n_partials, 1.0 / ((double)n * H * W));
   AMMC_LAUNCH_CHECK("frame_loss_final_kernel");
   return 0;
 }
@@ -138,11 +276,15 @@ extern "C" int ammc_frame_losses_bwd(const float* gen, const float* gt, const fl
   AMMC_REQUIRE(gen && gt && grad_gen && (g_int || g_gd) && n > 0 && H > 0 && W > 0, "bad argument");
   AMMC_REQUIRE(C >= 1 && C <= LOSS_MAX_C, "frame losses support 1..%d channels (got %d)", LOSS_MAX_C, C);
   AMMC_REQUIRE(n <= 65535, "batch %d too large for one launch", n);
-  const int bx = ceil_div((int64_t)H * W, 256);
+  const bool quads = frame_quads_ok(gen, gt, grad_gen, W);
+  const int bx = quads ? ceil_div(((int64_t)H * W) >> 2, 256) : ceil_div((int64_t)H * W, 256);
   const float inv = (float)(1.0 / ((double)n * H * W));
   switch (C) {
-#define AMMC_FL_CASE(CC) \
-  case CC: frame_loss_bwd_kernel<CC><<<dim3(bx, n), 256, 0, st>>>(gen, gt, g_int, g_gd, grad_gen, H, W, inv); break;
+#define AMMC_FL_CASE(CC)                                                                                                     \
+  case CC:                                                                                                                   \
+    if (quads) frame_loss_bwd4_kernel<CC><<<dim3(bx, n), 256, 0, st>>>(gen, gt, g_int, g_gd, grad_gen, H, W, inv);           \
+    else frame_loss_bwd_kernel<CC><<<dim3(bx, n), 256, 0, st>>>(gen, gt, g_int, g_gd, grad_gen, H, W, inv);                  \
+    break;
     AMMC_FL_CASE(1) AMMC_FL_CASE(2) AMMC_FL_CASE(3) AMMC_FL_CASE(4) AMMC_FL_CASE(5) AMMC_FL_CASE(6) AMMC_FL_CASE(7) AMMC_FL_CASE(8)
 #undef AMMC_FL_CASE
   }
@@ -297,22 +439,22 @@ namespace ammc {
 
 struct ObjSegments { int rgb, op, flow, adv, n_latent; };       // partial PAIRS per segment, laid out in this order
 
-__global__ void __launch_bounds__(256) gen_objective_final_kernel(const float* __restrict__ partial, const float* __restrict__ latent,
-                                                                   ObjSegments seg, double inv_rgb, double inv_op, double inv_flow,
-                                                                   double inv_adv, float lam_adv, float lam_gdl, float lam_flow,
-                                                                   float lam_lp, float lam_latent, float lam_lp_op,
-                                                                   float* __restrict__ out8) {
-  __shared__ double red[6][8];
+__global__ void __launch_bounds__(1024) gen_objective_final_kernel(const float* __restrict__ partial, const float* __restrict__ latent,
+                                                                    ObjSegments seg, double inv_rgb, double inv_op, double inv_flow,
+                                                                    double inv_adv, float lam_adv, float lam_gdl, float lam_flow,
+                                                                    float lam_lp, float lam_latent, float lam_lp_op,
+                                                                    float* __restrict__ out8) {
+  __shared__ double red[6][32];
   double v[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};                 // int, gd, int_op, flow, adv, latent
-  const float* p = partial;
-  for (int i = threadIdx.x; i < seg.rgb; i += 256) { v[0] += (double)p[2 * i]; v[1] += (double)p[2 * i + 1]; }
-  p += 2 * (size_t)seg.rgb;
-  for (int i = threadIdx.x; i < seg.op; i += 256) v[2] += (double)p[2 * i];
-  p += 2 * (size_t)seg.op;
-  for (int i = threadIdx.x; i < seg.flow; i += 256) v[3] += (double)p[2 * i];
-  p += 2 * (size_t)seg.flow;
-  for (int i = threadIdx.x; i < seg.adv; i += 256) v[4] += (double)p[2 * i];
-  for (int i = threadIdx.x; i < seg.n_latent; i += 256) v[5] += (double)latent[i];
+  const float2* p = reinterpret_cast<const float2*>(partial);   // (a-term, b-term) pairs, 8-byte aligned segments
+  for (int i = threadIdx.x; i < seg.rgb; i += 1024) { const float2 t = p[i]; v[0] += (double)t.x; v[1] += (double)t.y; }
+  p += seg.rgb;
+  for (int i = threadIdx.x; i < seg.op; i += 1024) v[2] += (double)p[i].x;
+  p += seg.op;
+  for (int i = threadIdx.x; i < seg.flow; i += 1024) v[3] += (double)p[i].x;
+  p += seg.flow;
+  for (int i = threadIdx.x; i < seg.adv; i += 1024) v[4] += (double)p[i].x;
+  for (int i = threadIdx.x; i < seg.n_latent; i += 1024) v[5] += (double)latent[i];
 #pragma unroll
   for (int q = 0; q < 6; ++q) {
 #pragma unroll
@@ -322,7 +464,7 @@ __global__ void __launch_bounds__(256) gen_objective_final_kernel(const float* _
   __syncthreads();
   if (threadIdx.x == 0) {
     double s[6];
-    for (int q = 0; q < 6; ++q) { s[q] = 0.0; for (int i = 0; i < 8; ++i) s[q] += red[q][i]; }
+    for (int q = 0; q < 6; ++q) { s[q] = 0.0; for (int i = 0; i < 32; ++i) s[q] += red[q][i]; }
     const float g_int = (float)(s[0] * inv_rgb), g_gd = (float)(s[1] * inv_rgb), g_int_op = (float)(s[2] * inv_op);
     const float g_flow = (float)(s[3] * inv_flow), g_adv = (float)(s[4] * inv_adv), g_lat = (float)s[5];
     // same association as the reference expression (loss_zoo.py:336-339), fp32 like its tensors
@@ -352,18 +494,6 @@ __global__ void gen_objective_scalars_kernel(const float* __restrict__ g8, float
   }
 }
 
-static int launch_frame_partial(const float* gen, const float* gt, float* partial, int n, int C, int H, int W, cudaStream_t st) {
-  const int bx = ceil_div((int64_t)H * W, 256);
-  switch (C) {
-#define AMMC_FL_CASE(CC) case CC: frame_loss_partial_kernel<CC><<<dim3(bx, n), 256, 0, st>>>(gen, gt, partial, H, W); break;
-    AMMC_FL_CASE(1) AMMC_FL_CASE(2) AMMC_FL_CASE(3) AMMC_FL_CASE(4) AMMC_FL_CASE(5) AMMC_FL_CASE(6) AMMC_FL_CASE(7) AMMC_FL_CASE(8)
-#undef AMMC_FL_CASE
-    default: return fail(AMMC_EINVAL, "frame losses support 1..%d channels (got %d)", LOSS_MAX_C, C);
-  }
-  AMMC_LAUNCH_CHECK("frame_loss_partial_kernel");
-  return 0;
-}
-
 }  // namespace ammc
 
 extern "C" size_t ammc_gen_objective_workspace_bytes(int n_rgb, int H_rgb, int W_rgb, int n_op, int H_op, int W_op, int64_t n_flow,
@@ -386,20 +516,19 @@ extern "C" int ammc_gen_objective_fwd(const float* rgb_out, const float* rgb_tgt
   AMMC_REQUIRE(n_rgb <= 65535 && n_op <= 65535, "batch too large for one launch");
   if (!workspace || workspace_bytes < ammc_gen_objective_workspace_bytes(n_rgb, H_rgb, W_rgb, n_op, H_op, W_op, n_flow, n_dgen))
     return fail(AMMC_EWORKSPACE, "workspace too small");
+  // segments follow each other in the workspace; their sizes are the partial PAIRS each pass writes
   ObjSegments seg;
-  seg.rgb = n_rgb * ceil_div((int64_t)H_rgb * W_rgb, 256);
-  seg.op = n_op * ceil_div((int64_t)H_op * W_op, 256);
+  float* p_rgb = (float*)workspace;
+  int rc = launch_frame_partial(rgb_out, rgb_tgt, p_rgb, n_rgb, C_rgb, H_rgb, W_rgb, st, &seg.rgb);
+  if (rc) return rc;
+  float* p_op = p_rgb + 2 * (size_t)seg.rgb;
+  rc = launch_frame_partial(op_out, op_tgt, p_op, n_op, C_op, H_op, W_op, st, &seg.op);
+  if (rc) return rc;
   seg.flow = elem_blocks(n_flow);
   seg.adv = elem_blocks(n_dgen);
   seg.n_latent = n_latent;
-  float* p_rgb = (float*)workspace;
-  float* p_op = p_rgb + 2 * (size_t)seg.rgb;
   float* p_flow = p_op + 2 * (size_t)seg.op;
   float* p_adv = p_flow + 2 * (size_t)seg.flow;
-  int rc = launch_frame_partial(rgb_out, rgb_tgt, p_rgb, n_rgb, C_rgb, H_rgb, W_rgb, st);
-  if (rc) return rc;
-  rc = launch_frame_partial(op_out, op_tgt, p_op, n_op, C_op, H_op, W_op, st);
-  if (rc) return rc;
   if (((((uintptr_t)flow_pred) | ((uintptr_t)flow_gt)) & 15) == 0)
     elem_loss_partial_kernel<ELEM_L1, true><<<seg.flow, 256, 0, st>>>(flow_pred, flow_gt, p_flow, n_flow);
   else
@@ -410,7 +539,7 @@ extern "C" int ammc_gen_objective_fwd(const float* rgb_out, const float* rgb_tgt
   else
     elem_loss_partial_kernel<ELEM_LSGAN_G, false><<<seg.adv, 256, 0, st>>>(d_gen, nullptr, p_adv, n_dgen);
   AMMC_LAUNCH_CHECK("elem_loss_partial_kernel");
-  gen_objective_final_kernel<<<1, 256, 0, st>>>(p_rgb, latent, seg, 1.0 / ((double)n_rgb * H_rgb * W_rgb),
+  gen_objective_final_kernel<<<1, 1024, 0, st>>>(p_rgb, latent, seg, 1.0 / ((double)n_rgb * H_rgb * W_rgb),
                                                 1.0 / ((double)n_op * H_op * W_op), 1.0 / (double)n_flow, 1.0 / (double)n_dgen,
                                                 lam_adv, lam_gdl, lam_flow, lam_lp, lam_latent, lam_lp_op, out8);
   AMMC_LAUNCH_CHECK("gen_objective_final_kernel");
