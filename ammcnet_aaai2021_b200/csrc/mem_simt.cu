@@ -674,8 +674,11 @@ __global__ void __launch_bounds__(256) pack_nhwc64_kernel(const float* __restric
 
 // HW % 64 == 0, C % 64 == 0, 16-byte aligned x: 64 x 64 tiles, 16-byte accesses on both sides (256 contiguous bytes per
 // channel row and pass on the NCHW side instead of 128)
+// SUMS: the block also writes the sums of its 64 channels over its 64 pixels to part[img * gridDim.x + blockIdx.x][C]
+// (16-lane shuffle reduction of the values already in registers) -- the channel sums of g (g_dec_b) without a second read of g.
+template <bool SUMS>
 __global__ void __launch_bounds__(256, 4) pack_nhwc64x64_kernel(const float* __restrict__ g, __nv_bfloat16* __restrict__ gp, int C,
-                                                                 int HW, long long plane_stride) {
+                                                                 int HW, long long plane_stride, float* __restrict__ part) {
   __shared__ float tile[64][65];
   const int img = blockIdx.z, c0 = blockIdx.y * 64, p0 = blockIdx.x * 64;
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -683,6 +686,15 @@ __global__ void __launch_bounds__(256, 4) pack_nhwc64x64_kernel(const float* __r
 #pragma unroll
   for (int i = 0; i < 4; ++i)
     v[i] = __ldg(reinterpret_cast<const float4*>(g + ((size_t)img * C + c0 + ty + 16 * i) * HW + p0 + 4 * tx));
+  if (SUMS) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float a = (v[i].x + v[i].y) + (v[i].z + v[i].w);
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);      // the 16 lanes that share ty
+      if (tx == 0) part[((size_t)img * gridDim.x + blockIdx.x) * C + c0 + ty + 16 * i] = a;
+    }
+  }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int r = ty + 16 * i;
@@ -709,9 +721,43 @@ __global__ void __launch_bounds__(256, 4) pack_nhwc64x64_kernel(const float* __r
   }
 }
 
+static inline bool pack64x64_ok(const float* x, int C, int HW) { return HW % 64 == 0 && C % 64 == 0 && ((uintptr_t)x & 15) == 0; }
+
+// colsum[c] += sum over the rows of part [rows][C]; grid (C / 32, 8), 256 threads = 8 row lanes x 32 channels
+__global__ void __launch_bounds__(256) colsum_rows_kernel(const float* __restrict__ part, float* __restrict__ colsum, int rows, int C) {
+  __shared__ float red[8][33];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31), lane_r = threadIdx.x >> 5;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  const int step = 8 * gridDim.y;
+  int r = blockIdx.y * 8 + lane_r;
+  for (; r + 3 * step < rows; r += 4 * step) {
+    a0 += part[(size_t)r * C + c]; a1 += part[(size_t)(r + step) * C + c];
+    a2 += part[(size_t)(r + 2 * step) * C + c]; a3 += part[(size_t)(r + 3 * step) * C + c];
+  }
+  for (; r < rows; r += step) a0 += part[(size_t)r * C + c];
+  red[lane_r][threadIdx.x & 31] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  if (lane_r == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
+    atomicAdd(&colsum[c], t);
+  }
+}
+
+// pack + channel sums of g in one read of g (64 x 64-tile shapes only: the caller checks pack64x64_ok); colsum must be zeroed
+static int pack_nhwc64_colsum(const float* g, void* gp, float* part, float* colsum, int b, int C, int HW, cudaStream_t st) {
+  pack_nhwc64x64_kernel<true><<<dim3(HW / 64, C / 64, b), 256, 0, st>>>(g, (__nv_bfloat16*)gp, C, HW, (long long)b * HW * C, part);
+  AMMC_LAUNCH_CHECK("pack_nhwc64x64_kernel");
+  colsum_rows_kernel<<<dim3(C / 32, 8), 256, 0, st>>>(part, colsum, b * (HW / 64), C);
+  AMMC_LAUNCH_CHECK("colsum_rows_kernel");
+  return 0;
+}
+
 int pack_nhwc64(const float* x, void* xp, int b, int C, int HW, cudaStream_t st) {     // C % 8 == 0
-  if (HW % 64 == 0 && C % 64 == 0 && ((uintptr_t)x & 15) == 0)
-    pack_nhwc64x64_kernel<<<dim3(HW / 64, C / 64, b), 256, 0, st>>>(x, (__nv_bfloat16*)xp, C, HW, (long long)b * HW * C);
+  if (pack64x64_ok(x, C, HW))
+    pack_nhwc64x64_kernel<false><<<dim3(HW / 64, C / 64, b), 256, 0, st>>>(x, (__nv_bfloat16*)xp, C, HW, (long long)b * HW * C,
+                                                                          nullptr);
   else
     pack_nhwc64_kernel<<<dim3(ceil_div(HW, 32), ceil_div(C, 64), b), 256, 0, st>>>(x, (__nv_bfloat16*)xp, C, HW,
                                                                                     (long long)b * HW * C);
@@ -913,6 +959,10 @@ static bool use_tc(int64_t N, int D, int M, int k) {
 __global__ void fill_kernel(float* p, float v, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
+}
+__global__ void fill2_kernel(float* p0, float v0, float* p1, float v1, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { p0[i] = v0; p1[i] = v1; }
 }
 
 static bool use_tc_dec(int b, int h, int w, int C, int D, int k) {
@@ -1301,7 +1351,9 @@ extern "C" size_t ammc_mem_bwd_workspace_bytes(int b, int h, int w, int C, int D
          align_up((size_t)C * D * 4, 256) +
          // tensor-core weight gradients: NHWC planes of x and g_out, planes of the gathered read, g_dec_w^T
          2 * align_up((size_t)2 * N * C * 2, 256) + align_up((size_t)2 * N * k * D * 2, 256) +
-         align_up((size_t)k * D * C * 4, 256);
+         align_up((size_t)k * D * C * 4, 256) +
+         // per-block channel sums of g_out from its pack pass (one row of C values per 64 pixels)
+         align_up((size_t)((N + 63) / 64) * C * 4, 256);
 }
 
 extern "C" int ammc_mem_bwd(const float* x, const float* enc_w, const float* embed, const int64_t* idx,
@@ -1323,14 +1375,18 @@ extern "C" int ammc_mem_bwd(const float* x, const float* enc_w, const float* emb
   if (!ws.ok()) return fail(AMMC_EWORKSPACE, "workspace too small");
   bank_transpose_kernel<<<dim3(ceil_div(M, 32), ceil_div(D, 32)), dim3(32, 8), 0, st>>>(embed, bank_t, D, M);
   AMMC_LAUNCH_CHECK("bank_transpose_kernel");
+  const bool tc_gx = g_dec_mode != 1 && D % 64 == 0 && C % 64 == 0;     // ammc_set_dec_mode(1) keeps every 1x1 GEMM on CUDA cores
+  const bool tc_wgrad = tc_gx && w <= 128 && b <= 65535;
   AMMC_CUDA_CHECK(cudaMemsetAsync(g_enc_b, 0, (size_t)D * 4, st));
-  AMMC_CUDA_CHECK(cudaMemsetAsync(g_enc_w, 0, (size_t)D * C * 4, st));
   AMMC_CUDA_CHECK(cudaMemsetAsync(g_dec_b, 0, (size_t)C * 4, st));
-  AMMC_CUDA_CHECK(cudaMemsetAsync(G, 0, (size_t)k * M * C * 4, st));
+  if (!tc_wgrad) {                 // the CUDA-core weight gradients accumulate; the tensor-core ones zero their own outputs
+    AMMC_CUDA_CHECK(cudaMemsetAsync(g_enc_w, 0, (size_t)D * C * 4, st));
+    AMMC_CUDA_CHECK(cudaMemsetAsync(G, 0, (size_t)k * M * C * 4, st));
+  }
   gz_kernel<<<ceil_div(N, 64), 256, (size_t)D * 4, st>>>(z, bank_t, idx, g_diff, g_q1, gz, g_enc_b, (int)N, D, k,
                                                         1.0 / ((double)N * (double)D));
   AMMC_LAUNCH_CHECK("gz_kernel");
-  if (g_dec_mode != 1 && D % 64 == 0 && C % 64 == 0) {        // ammc_set_dec_mode(1) keeps every 1x1 GEMM on CUDA cores
+  if (tc_gx) {
     // gx = (residual ? g_out : 0) + g_z . enc_w  as a split-bf16 x3 1x1 GEMM on tcgen05 (the conv engine with K = D):
     // operands = NHWC planes of g_z and enc_w^T [C][D]; the residual add and the NCHW store are its epilogue
     __nv_bfloat16* gzp = ws.take<__nv_bfloat16>((size_t)2 * N * D);
@@ -1343,12 +1399,11 @@ extern "C" int ammc_mem_bwd(const float* x, const float* enc_w, const float* emb
     bank_transpose_kernel<<<dim3(ceil_div(C, 32), ceil_div(D, 32)), dim3(32, 8), 0, st>>>(enc_w, wt, D, C);   // [D][C] -> [C][D]
     AMMC_LAUNCH_CHECK("bank_transpose_kernel");
     if (int rc = pack_weights_1x1(wt, wtp, C, D, st)) return rc;
-    fill_kernel<<<ceil_div(C, 256), 256, 0, st>>>(ones, 1.f, C);
-    fill_kernel<<<ceil_div(C, 256), 256, 0, st>>>(zeros, 0.f, C);
-    AMMC_LAUNCH_CHECK("fill_kernel");
+    fill2_kernel<<<ceil_div(C, 256), 256, 0, st>>>(ones, 1.f, zeros, 0.f, C);
+    AMMC_LAUNCH_CHECK("fill2_kernel");
     if (int rc = conv_igemm(gzp, wtp, ones, zeros, nullptr, gx, residual ? g_out : nullptr, b, D, C, h, w, 1, 3, 0, st))
       return rc;
-    if (w <= 128 && b <= 65535) {
+    if (tc_wgrad) {
       // both weight gradients are GEMMs with K = pixels: the tcgen05 weight-gradient kernel (amft_train.cu) on NHWC bf16
       // hi/lo planes.   g_enc_w [D][C] = g_z^T . x ;   g_dec_w^T [kD][C] = read^T . g_out ;   g_dec_b from the pack pass
       __nv_bfloat16* xpl = ws.take<__nv_bfloat16>((size_t)2 * N * C);
@@ -1357,8 +1412,12 @@ extern "C" int ammc_mem_bwd(const float* x, const float* enc_w, const float* emb
       float* gdwT = ws.take<float>((size_t)k * D * C);
       if (!ws.ok()) return fail(AMMC_EWORKSPACE, "workspace too small");
       if (int rc = pack_nhwc64(x, xpl, b, C, HW, st)) return rc;
-      if (int rc = pack_nhwc64(g_out, gopl, b, C, HW, st)) return rc;
-      {
+      if (pack64x64_ok(g_out, C, HW)) {             // g_dec_b from the pack pass: g_out is read once
+        float* part = ws.take<float>((size_t)(N / 64) * C);
+        if (!ws.ok()) return fail(AMMC_EWORKSPACE, "workspace too small");
+        if (int rc = pack_nhwc64_colsum(g_out, gopl, part, g_dec_b, b, C, HW, st)) return rc;
+      } else {
+        if (int rc = pack_nhwc64(g_out, gopl, b, C, HW, st)) return rc;
         const int per = max(1, b / 8);
         channel_sum_kernel<<<dim3(C, ceil_div(b, per)), 256, 0, st>>>(g_out, g_dec_b, b, C, HW, per);
         AMMC_LAUNCH_CHECK("channel_sum_kernel");

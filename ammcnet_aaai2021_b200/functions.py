@@ -378,6 +378,9 @@ class MemoryModuleFn(torch.autograd.Function):
         outs = (r["out"], r["diff"], r["q1"].view(b, h, w, D), r["idx"], r["sse_frame"],
                 r["counts"] if want_stats else empty, r["embed_sum"] if want_stats else empty)
         ctx.mark_non_differentiable(*outs[3:])
+        # outputs the loss does not use (q1 in every training script of the reference) arrive as None in backward instead of
+        # as zero tensors autograd would have to fill -- [N, D] floats per call for q1 -- and the kernel would have to read
+        ctx.set_materialize_grads(False)
         return outs
 
     @staticmethod
