@@ -429,6 +429,70 @@ __global__ void __launch_bounds__(256) gz_kernel(const float* __restrict__ z, co
   for (int d = threadIdx.x; d < D; d += blockDim.x) atomicAdd(&g_enc_b[d], colsum[d]);
 }
 
+// Same values with 16-byte accesses for D = 4 * (power of two <= 256): a thread owns four embedding coordinates of every R-th
+// row of the block's 64 rows, keeps their column sums in registers (no per-element shared atomics), and -- when gzp is given --
+// also writes g_z as bf16 hi/lo planes [2][N*D], the operand format of the tensor-core input / weight gradients (what
+// pack_planes_f32 would produce from gz in a second pass).
+__global__ void __launch_bounds__(256) gz4_kernel(const float* __restrict__ z, const float* __restrict__ bank_t,
+                                                   const int64_t* __restrict__ idx, const float* __restrict__ g_diff,
+                                                   const float* __restrict__ g_q1, float* __restrict__ gz,
+                                                   __nv_bfloat16* __restrict__ gzp, float* __restrict__ g_enc_b, int N, int D,
+                                                   int K, double inv_count) {
+  __shared__ float4 part[256];
+  const int L = D >> 2, R = 256 / L;
+  const int lane = threadIdx.x & (L - 1), rl = threadIdx.x / L;
+  const float coef = (float)((double)g_diff[0] * 2.0 * inv_count);
+  const int n0 = blockIdx.x * 64;
+  const size_t plane = (size_t)N * D;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int p = rl; p < 64 && n0 + p < N; p += R) {
+    const size_t n = (size_t)(n0 + p), o = n * D + 4 * lane;
+    const int i1 = (int)idx[n * K];
+    const float4 zz = *reinterpret_cast<const float4*>(z + o);
+    const float4 ee = __ldg(reinterpret_cast<const float4*>(bank_t + (size_t)i1 * D + 4 * lane));
+    float4 v = make_float4(coef * (zz.x - ee.x), coef * (zz.y - ee.y), coef * (zz.z - ee.z), coef * (zz.w - ee.w));
+    if (g_q1) {
+      const float4 q = *reinterpret_cast<const float4*>(g_q1 + o);
+      v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+    }
+    *reinterpret_cast<float4*>(gz + o) = v;
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    if (gzp) {
+      const float vv[4] = {v.x, v.y, v.z, v.w};
+      uint32_t hp[2], lp[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(vv[2 * j]), h1 = __float2bfloat16_rn(vv[2 * j + 1]);
+        const __nv_bfloat16 l0 = __float2bfloat16_rn(vv[2 * j] - __bfloat162float(h0));
+        const __nv_bfloat16 l1 = __float2bfloat16_rn(vv[2 * j + 1] - __bfloat162float(h1));
+        hp[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+        lp[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+      }
+      *reinterpret_cast<uint2*>(gzp + o) = make_uint2(hp[0], hp[1]);
+      *reinterpret_cast<uint2*>(gzp + plane + o) = make_uint2(lp[0], lp[1]);
+    }
+  }
+  part[threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.x < L) {
+    float4 t = part[threadIdx.x];
+    for (int r = 1; r < R; ++r) {
+      const float4 u = part[threadIdx.x + r * L];
+      t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+    }
+    atomicAdd(&g_enc_b[4 * threadIdx.x + 0], t.x);
+    atomicAdd(&g_enc_b[4 * threadIdx.x + 1], t.y);
+    atomicAdd(&g_enc_b[4 * threadIdx.x + 2], t.z);
+    atomicAdd(&g_enc_b[4 * threadIdx.x + 3], t.w);
+  }
+}
+
+static inline bool gz4_ok(int D, const void* a, const void* b, const void* c, const void* d) {
+  const int L = D >> 2;
+  return D % 4 == 0 && L >= 1 && L <= 256 && (L & (L - 1)) == 0 &&
+         (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c | (uintptr_t)d) & 15) == 0;
+}
+
 // gx[img,c,p] = sum_d enc_w[d,c] gz[n,d] (+ g_out[img,c,p])
 __global__ void __launch_bounds__(256) gx_kernel(const float* __restrict__ gz, const float* __restrict__ enc_w,
                                                   const float* __restrict__ g_out, float* __restrict__ gx,
@@ -1383,19 +1447,29 @@ extern "C" int ammc_mem_bwd(const float* x, const float* enc_w, const float* emb
     AMMC_CUDA_CHECK(cudaMemsetAsync(g_enc_w, 0, (size_t)D * C * 4, st));
     AMMC_CUDA_CHECK(cudaMemsetAsync(G, 0, (size_t)k * M * C * 4, st));
   }
-  gz_kernel<<<ceil_div(N, 64), 256, (size_t)D * 4, st>>>(z, bank_t, idx, g_diff, g_q1, gz, g_enc_b, (int)N, D, k,
-                                                        1.0 / ((double)N * (double)D));
+  __nv_bfloat16* gzp = nullptr;                    // bf16 hi/lo planes of g_z (tensor-core route)
+  if (tc_gx) {
+    gzp = ws.take<__nv_bfloat16>((size_t)2 * N * D);
+    if (!ws.ok()) return fail(AMMC_EWORKSPACE, "workspace too small");
+  }
+  const bool gz4 = gz4_ok(D, z, bank_t, g_q1, gz) && (!gzp || ((uintptr_t)gzp & 7) == 0);
+  if (gz4)
+    gz4_kernel<<<ceil_div(N, 64), 256, 0, st>>>(z, bank_t, idx, g_diff, g_q1, gz, gzp, g_enc_b, (int)N, D, k,
+                                                1.0 / ((double)N * (double)D));
+  else
+    gz_kernel<<<ceil_div(N, 64), 256, (size_t)D * 4, st>>>(z, bank_t, idx, g_diff, g_q1, gz, g_enc_b, (int)N, D, k,
+                                                          1.0 / ((double)N * (double)D));
   AMMC_LAUNCH_CHECK("gz_kernel");
   if (tc_gx) {
     // gx = (residual ? g_out : 0) + g_z . enc_w  as a split-bf16 x3 1x1 GEMM on tcgen05 (the conv engine with K = D):
     // operands = NHWC planes of g_z and enc_w^T [C][D]; the residual add and the NCHW store are its epilogue
-    __nv_bfloat16* gzp = ws.take<__nv_bfloat16>((size_t)2 * N * D);
     __nv_bfloat16* wtp = ws.take<__nv_bfloat16>((size_t)2 * C * D);
     float* ones = ws.take<float>(C);
     float* zeros = ws.take<float>(C);
     float* wt = ws.take<float>((size_t)C * D);
     if (!ws.ok()) return fail(AMMC_EWORKSPACE, "workspace too small");
-    if (int rc = pack_planes_f32(gz, gzp, (long long)N * D, st)) return rc;
+    if (!gz4)
+      if (int rc = pack_planes_f32(gz, gzp, (long long)N * D, st)) return rc;
     bank_transpose_kernel<<<dim3(ceil_div(C, 32), ceil_div(D, 32)), dim3(32, 8), 0, st>>>(enc_w, wt, D, C);   // [D][C] -> [C][D]
     AMMC_LAUNCH_CHECK("bank_transpose_kernel");
     if (int rc = pack_weights_1x1(wt, wtp, C, D, st)) return rc;
