@@ -14,12 +14,12 @@ from .graphs import GraphedPath
 from .generator import GeneratorEngine
 from .preprocess import preprocess_frames, preprocess_flow, load_video, widen_bf16, narrow_bf16
 from .losses import (Intensity_Loss, Gradient_Loss, frame_losses, Flow_Loss, Adversarial_Loss, Discriminate_Loss,
-                     Twostream_vq_Loss)
+                     Twostream_vq_Loss, Twostream_Loss, rgb_Loss, rgb_vq_Loss, op_loss, op_vq_Loss, op_loss_v1, op_vq_Loss_v1)
 from .loader import VideoLoader, read_flo, write_flo, decode_frame
 
 __all__ = [
     "Quantize_topk", "enc_quan_dec_topk", "enc_quan_dec_res_topk", "bridge", "double_conv", "psnr_error",
     "psnr_per_frame", "VideoScorer", "assemble_video_records", "score_reduce", "evaluate", "LAM_MAP",
     "patch_reference", "unpatch_reference", "swap_modules", "patch_reference_losses", "unpatch_reference_losses", "twostream", "UNetMem_v7", "get_twostream", "PixelDiscriminator", "FlowNet2SD", "GraphedPath", "GeneratorEngine", "preprocess_frames", "preprocess_flow", "load_video", "widen_bf16", "narrow_bf16", "Intensity_Loss", "Gradient_Loss", "frame_losses", "Flow_Loss", "Adversarial_Loss", "Discriminate_Loss",
-    "Twostream_vq_Loss", "VideoLoader", "read_flo", "write_flo", "decode_frame",
+    "Twostream_vq_Loss", "Twostream_Loss", "rgb_Loss", "rgb_vq_Loss", "op_loss", "op_vq_Loss", "op_loss_v1", "op_vq_Loss_v1", "VideoLoader", "read_flo", "write_flo", "decode_frame",
 ]

@@ -241,3 +241,110 @@ class Twostream_vq_Loss(nn.Module):
         (self.g_loss, self.g_adv_loss, self.g_flow_loss, self.g_int_loss, self.g_gd_loss, self.g_int_loss_op,
          self.g_latent_loss) = out.detach()[:7].tolist()            # the step's only device-to-host read
         return out[0].reshape(shape)
+
+
+def _latent_scalar(latent_diff):
+    """The commit term as the loss sees it: one value, or the (rgb, op) tuple of a two-stream generator summed."""
+    if isinstance(latent_diff, (tuple, list)):
+        return sum(d.sum() for d in latent_diff)
+    return latent_diff
+
+
+class _ComposedObjective(nn.Module):
+    """Constructor and bookkeeping shared by the other objectives of loss_zoo.py (base_Loss, loss_zoo.py:15-45): the stage-1
+    single-stream losses and the variants without a commit term.  Their components come from the fused kernels above
+    (`frame_losses`: both image losses of a pair in one pass; `ElemLossFn`: one pass per element-wise objective); the weighted
+    sum is formed in the reference's own order and every scalar the reference reads with its own `.item()` travels to the host
+    in ONE copy (`_finish`)."""
+
+    def __init__(self, lam_adv=None, lam_gdl=None, lam_flow=None, lam_lp=None, lam_latent=None, lam_lp_op=None,
+                 lam_adv_op=None):
+        super().__init__()
+        self.lam_lp, self.lam_adv, self.lam_gdl, self.lam_flow = lam_lp, lam_adv, lam_gdl, lam_flow
+        self.lam_latent, self.lam_lp_op, self.lam_adv_op = lam_latent, lam_lp_op, lam_adv_op
+        self.adversarial_loss_fn = Adversarial_Loss()
+        self.flow_loss_fn = Flow_Loss()
+        self.int_loss_fn = Intensity_Loss()
+        self.gd_loss_fn = Gradient_Loss()
+        self.int_loss_fn_op = Intensity_Loss()
+        self.adversarial_loss_fn_op = Adversarial_Loss()
+        self.g_adv_loss = self.g_flow_loss = self.g_int_loss = self.g_gd_loss = None
+        self.g_int_loss_op = self.g_adv_loss_op = self.g_latent_loss = None
+
+    def _finish(self, total_name, terms):
+        """terms: (attribute name, weight, tensor) in the reference's order -> weighted sum; sets the float attributes."""
+        total = None
+        for _, lam, t in terms:
+            total = lam * t if total is None else total + lam * t
+        vals = torch.stack([v.detach().float().reshape(()) for v in [total] + [t for _, _, t in terms]]).tolist()
+        setattr(self, total_name, vals[0])
+        for (name, _, _), v in zip(terms, vals[1:]):
+            setattr(self, name, v)
+        return total
+
+
+class rgb_Loss(_ComposedObjective):
+    """loss_zoo.py:64-99: adversarial + gradient + flow + intensity terms of the appearance stream."""
+
+    def forward(self, flow_pred, flow_gt, rgb_G_output, rgb_target, d_gen):
+        g_int, g_gd = frame_losses(rgb_G_output, rgb_target)
+        return self._finish("g_loss", [("g_adv_loss", self.lam_adv, self.adversarial_loss_fn(d_gen)),
+                                       ("g_gd_loss", self.lam_gdl, g_gd),
+                                       ("g_flow_loss", self.lam_flow, self.flow_loss_fn(flow_pred, flow_gt)),
+                                       ("g_int_loss", self.lam_lp, g_int)])
+
+
+class rgb_vq_Loss(_ComposedObjective):
+    """loss_zoo.py:101-140: `rgb_Loss` + lam_latent * commit loss (stage-1 training of the appearance stream)."""
+
+    def forward(self, flow_pred, flow_gt, rgb_G_output, rgb_target, latent_diff, d_gen):
+        g_int, g_gd = frame_losses(rgb_G_output, rgb_target)
+        return self._finish("g_loss", [("g_adv_loss", self.lam_adv, self.adversarial_loss_fn(d_gen)),
+                                       ("g_gd_loss", self.lam_gdl, g_gd),
+                                       ("g_flow_loss", self.lam_flow, self.flow_loss_fn(flow_pred, flow_gt)),
+                                       ("g_int_loss", self.lam_lp, g_int),
+                                       ("g_latent_loss", self.lam_latent, _latent_scalar(latent_diff))])
+
+
+class op_loss(_ComposedObjective):
+    """loss_zoo.py:142-169: intensity + adversarial terms of the motion stream."""
+
+    def forward(self, op_G_output, op_target, d_gen):
+        return self._finish("g_loss_op", [("g_int_loss_op", self.lam_lp_op, self.int_loss_fn_op(op_G_output, op_target)),
+                                          ("g_adv_loss_op", self.lam_adv_op, self.adversarial_loss_fn_op(d_gen))])
+
+
+class op_vq_Loss(_ComposedObjective):
+    """loss_zoo.py:171-201: `op_loss` + lam_latent * commit loss."""
+
+    def forward(self, op_G_output, op_target, d_gen, latent_diff):
+        return self._finish("g_loss_op", [("g_int_loss_op", self.lam_lp_op, self.int_loss_fn_op(op_G_output, op_target)),
+                                          ("g_adv_loss_op", self.lam_adv_op, self.adversarial_loss_fn_op(d_gen)),
+                                          ("g_latent_loss", self.lam_latent, _latent_scalar(latent_diff))])
+
+
+class op_loss_v1(_ComposedObjective):
+    """loss_zoo.py:203-230: the intensity term of the motion stream alone."""
+
+    def forward(self, op_G_output, op_target):
+        return self._finish("g_loss_op", [("g_int_loss_op", self.lam_lp_op, self.int_loss_fn_op(op_G_output, op_target))])
+
+
+class op_vq_Loss_v1(_ComposedObjective):
+    """loss_zoo.py:232-263: intensity term + lam_latent * commit loss (stage-1 training of the motion stream)."""
+
+    def forward(self, op_G_output, op_target, latent_diff):
+        return self._finish("g_loss_op", [("g_int_loss_op", self.lam_lp_op, self.int_loss_fn_op(op_G_output, op_target)),
+                                          ("g_latent_loss_op", self.lam_latent, _latent_scalar(latent_diff))])
+
+
+class Twostream_Loss(_ComposedObjective):
+    """loss_zoo.py:265-305: the two-stream objective without a commit term."""
+
+    def forward(self, flow_pred, flow_gt, rgb_G_output, rgb_target, op_G_output, op_target, d_gen):
+        g_int, g_gd = frame_losses(rgb_G_output, rgb_target)
+        return self._finish("g_loss", [("g_adv_loss", self.lam_adv, self.adversarial_loss_fn(d_gen)),
+                                       ("g_gd_loss", self.lam_gdl, g_gd),
+                                       ("g_flow_loss", self.lam_flow, self.flow_loss_fn(flow_pred, flow_gt)),
+                                       ("g_int_loss", self.lam_lp, g_int),
+                                       ("g_int_loss_op", self.lam_lp_op, self.int_loss_fn_op(op_G_output, op_target))])

@@ -34,7 +34,8 @@ def unpatch_reference(unet_module, saved, utils_module=None):
         utils_module.psnr_error = saved["psnr_error"]
 
 
-_LOSS_NAMES = ("Flow_Loss", "Intensity_Loss", "Gradient_Loss", "Adversarial_Loss", "Discriminate_Loss", "Twostream_vq_Loss")
+_LOSS_NAMES = ("Flow_Loss", "Intensity_Loss", "Gradient_Loss", "Adversarial_Loss", "Discriminate_Loss", "Twostream_vq_Loss",
+               "Twostream_Loss", "rgb_Loss", "rgb_vq_Loss", "op_loss", "op_vq_Loss", "op_loss_v1", "op_vq_Loss_v1")
 
 
 def patch_reference_losses(loss_zoo_module, losses_utils_module=None):

@@ -169,3 +169,11 @@ def test_generator_objective_every_component_differentiates(b, h, w, hd, wd):
     assert abs(fn.g_latent_loss - float(lat2.sum())) < 1e-6
     with pytest.raises(RuntimeError, match="one value"):
         fn(dv["flow_pred"], dv["flow_gt"], dv["rgb_out"], dv["rgb_tgt"], dv["op_out"], dv["op_tgt"], lat_d, dv["d_gen"])
+
+
+def test_composed_objectives_on_the_kernels():
+    """rgb_Loss, rgb_vq_Loss, op_loss, op_vq_Loss, op_loss_v1, op_vq_Loss_v1, Twostream_Loss (loss_zoo.py:64-305) on the fused
+    kernels: totals, stored attributes and gradients against the oracle in float64 (table pinned to the reference classes
+    in tests/test_host_logic.py)."""
+    import objective_checks
+    objective_checks.check_composed(DEV, 1e-5)

@@ -174,3 +174,49 @@ def test_flownet2sd_against_live_reference():
             assert torch.equal(o.eval()(x), r.eval()(x))
             for a, b in zip(o.train()(x), r.train()(x)):
                 assert torch.equal(a, b)
+
+
+def _oracle_kernels(monkeypatch):
+    """The kernel entry points of losses.py replaced by their oracle formulas (CPU tensors allowed)."""
+    import ammc_oracle as O
+    from ammcnet_aaai2021_b200 import losses as L
+    monkeypatch.setattr(L, "frame_losses", lambda a, b: (O.intensity_loss(a, b), O.gradient_loss(a, b)))
+    fakes = {L.OBJ_L1: lambda a, b: O.flow_loss(a, b), L.OBJ_LSGAN_G: lambda a, b: O.adversarial_loss(a),
+             L.OBJ_LSGAN_D: lambda a, b: O.discriminate_loss(a, b)}
+    monkeypatch.setattr(L.ElemLossFn, "apply", staticmethod(lambda mode, a, b: fakes[mode](a, b)))
+
+
+def test_composed_objectives_composition(monkeypatch):
+    """rgb_Loss ... Twostream_Loss: argument order, weights, attribute names and gradient flow, with the kernels replaced by
+    their oracle formulas (the same routine runs on the real kernels in tests/test_gpu_losses.py)."""
+    import objective_checks
+    _oracle_kernels(monkeypatch)
+    objective_checks.check_composed("cpu", 1e-5)
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference tree only exists in the build container")
+def test_composed_objectives_table_against_live_reference():
+    """The weights / attribute table the two checks above rest on, against the reference classes themselves."""
+    import sys, types
+    import objective_checks as C
+    import ref_harness
+    ref_harness.import_reference()
+    stub = types.ModuleType("Code.main.constant_train")
+    stub.const = types.SimpleNamespace(gpu_idx="0")
+    sys.modules.setdefault("Code.main.constant_train", stub)
+    import Code.models.losses.loss_zoo as LZ
+    cuda_orig = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        for name, (total_attr, terms, argkeys) in C.TABLE.items():
+            t = C.inputs("cpu")
+            ref = getattr(LZ, name)(**C.LAM)
+            got = ref(*[t[k] for k in argkeys])
+            want, attrs = C.expected(name, t)
+            assert abs(float(got.detach()) - float(want.detach())) <= 1e-6 * abs(float(want.detach())), name
+            for a, v in attrs.items():
+                assert abs(getattr(ref, a) - float(v.detach())) <= 1e-6 * max(abs(float(v.detach())), 1e-6), name + "." + a
+            ours = getattr(A, name)(**C.LAM)
+            assert {k for k in vars(ref) if k.startswith(("lam_", "g_"))} <= {k for k in vars(ours) if k.startswith(("lam_", "g_"))} | {total_attr} | set(attrs)
+    finally:
+        torch.Tensor.cuda = cuda_orig
