@@ -66,6 +66,19 @@ def _worker(rank, world, port, out_dir):
         adist.allreduce_gradients(list(lin.parameters()))
         for p in lin.parameters():
             assert torch.allclose(p.grad, torch.full_like(p, (world - 1) / 2.0))
+        # adversarial step (tools/train_step.py --gan): the discriminator is a second parameter group with its own all-reduce;
+        # parameters without a gradient (the frozen flow estimator, a discriminator frozen for the generator update) are skipped
+        import ammcnet_aaai2021_b200 as A0
+        D = A0.PixelDiscriminator(3, [4, 8, 8, 8], use_norm=False)
+        d_params = list(D.parameters())
+        for i, p in enumerate(d_params):
+            p.grad = torch.full_like(p, float(rank * (i + 1))) if i % 2 == 0 else None
+        adist.allreduce_gradients(d_params)
+        for i, p in enumerate(d_params):
+            if i % 2 == 0:
+                assert torch.allclose(p.grad, torch.full_like(p, (i + 1) * (world - 1) / 2.0))
+            else:
+                assert p.grad is None
         # global-batch BatchNorm: the hook sums the per-channel statistics over ranks and reports the world size; stock
         # BatchNorm2d layers outside the AMFT block become SyncBatchNorm, the block's own parameter containers stay
         import ammcnet_aaai2021_b200 as A
